@@ -1,0 +1,794 @@
+// C ABI of the kmerseek B200 sketch-and-search path (include/kmerseek_b200.h).
+// Host orchestration only: pinned packing, H2D streaming, stage launches, result hand-back.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <new>
+
+#include "host_util.hpp"
+#include "index_build.cuh"
+#include "search.cuh"
+#include "sketch.cuh"
+#include "util.cuh"
+
+using namespace ks;
+
+// ------------------------------------------------------------------------------------------------
+// error slot
+// ------------------------------------------------------------------------------------------------
+namespace {
+thread_local std::string g_err;
+thread_local uint32_t g_err_ch = 0;
+thread_local uint64_t g_err_pos = 0, g_err_protein = 0;
+
+ks_status set_error(ks_status s, const std::string& m) { g_err = m; return s; }
+
+template <class F>
+ks_status guarded(F&& f) {
+    try {
+        f();
+        return KS_OK;
+    } catch (const KsError& e) {
+        return set_error(e.status, e.message);
+    } catch (const std::bad_alloc&) {
+        return set_error(KS_ERR_OUT_OF_MEMORY, "out of host memory");
+    } catch (const std::exception& e) {
+        return set_error(KS_ERR_VALIDATION, e.what());
+    }
+}
+
+[[noreturn]] void fail_residue(const InvalidResidue& b) {
+    g_err_ch = b.ch; g_err_pos = b.pos; g_err_protein = b.protein;
+    char msg[128];
+    // src/rust/errors.rs:14-15
+    snprintf(msg, sizeof msg, "Invalid amino acid '%c' found at position %llu", (char)b.ch, (unsigned long long)b.pos);
+    fail(KS_ERR_INVALID_AMINO_ACID, msg);
+}
+
+int clz64(uint64_t x) { return x ? __builtin_clzll(x) : 64; }
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// proteome (pinned host buffers)
+// ------------------------------------------------------------------------------------------------
+struct ks_proteome {
+    uint8_t* residues = nullptr;
+    uint64_t* offsets = nullptr;
+    uint64_t n_prot = 0, n_res = 0;
+    bool pinned = false;
+    std::vector<std::string> names;
+};
+
+namespace {
+void* host_alloc(size_t bytes, bool* pinned) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) == cudaSuccess) { *pinned = true; return p; }
+    (void)cudaGetLastError();  // no device in this process (CPU-only host tests): pageable memory
+    *pinned = false;
+    p = malloc(bytes);
+    if (!p) throw std::bad_alloc();
+    return p;
+}
+void host_free(void* p, bool pinned) {
+    if (!p) return;
+    if (pinned) cudaFreeHost(p); else free(p);
+}
+
+ks_proteome* make_proteome(const uint8_t* res, uint64_t n_res, const uint64_t* offs, uint64_t n_prot) {
+    ks_proteome* p = new ks_proteome();
+    bool pin_a = false, pin_b = false;
+    p->residues = (uint8_t*)host_alloc(n_res + 64, &pin_a);
+    p->offsets = (uint64_t*)host_alloc((n_prot + 1) * 8, &pin_b);
+    p->pinned = pin_a && pin_b;
+    if (pin_a != pin_b) {  // keep one allocator for both
+        host_free(p->residues, pin_a); host_free(p->offsets, pin_b);
+        p->residues = (uint8_t*)malloc(n_res + 64); p->offsets = (uint64_t*)malloc((n_prot + 1) * 8);
+        p->pinned = false;
+        if (!p->residues || !p->offsets) throw std::bad_alloc();
+    }
+    if (n_res) memcpy(p->residues, res, n_res);
+    memset(p->residues + n_res, 0, 64);
+    memcpy(p->offsets, offs, (n_prot + 1) * 8);
+    p->n_prot = n_prot;
+    p->n_res = n_res;
+    return p;
+}
+}  // namespace
+
+extern "C" {
+
+const char* ks_last_error_message(void) { return g_err.c_str(); }
+void ks_last_error_detail(uint32_t* ch, uint64_t* pos, uint64_t* protein_index) {
+    if (ch) *ch = g_err_ch;
+    if (pos) *pos = g_err_pos;
+    if (protein_index) *protein_index = g_err_protein;
+}
+int ks_abi_version(void) { return KS_ABI_VERSION; }
+int ks_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
+    return n;
+}
+
+ks_status ks_moltype_from_str(const char* m, ks_moltype* out) {
+    std::string s = m ? m : "";
+    if (s == "protein" || s == "raw") { *out = KS_PROTEIN; return KS_OK; }
+    if (s == "hp") { *out = KS_HP; return KS_OK; }
+    if (s == "dayhoff") { *out = KS_DAYHOFF; return KS_OK; }
+    // src/rust/encoding.rs:22-25
+    return set_error(KS_ERR_INVALID_MOLTYPE, "Invalid moltype: " + s + ", only 'protein', 'hp', or 'dayhoff' are supported");
+}
+const char* ks_moltype_name(ks_moltype m) { return m == KS_DAYHOFF ? "dayhoff" : m == KS_HP ? "hp" : "protein"; }
+
+uint64_t ks_max_hash(uint32_t scaled) {
+    if (scaled == 0) return 0;
+    if (scaled == 1) return UINT64_MAX;
+    return (uint64_t)(18446744073709551616.0 / (double)scaled);
+}
+uint8_t ks_translate_residue(uint8_t aa, ks_moltype m) {
+    Lut256 lut;
+    fill_lut((int)m, &lut);
+    return lut.b[aa];
+}
+void ks_md5_of_mins(const uint64_t* mins, uint64_t n, uint32_t ksize, char out[33]) {
+    Md5 md;
+    char buf[32];
+    int l = snprintf(buf, sizeof buf, "%u", ksize * KS_PROTEIN_TO_MINHASH_RATIO);
+    md.update(buf, l);
+    for (uint64_t i = 0; i < n; i++) {
+        l = snprintf(buf, sizeof buf, "%llu", (unsigned long long)mins[i]);
+        md.update(buf, l);
+    }
+    md.hex(out);
+}
+void ks_id_of_mins(const uint64_t* mins, uint64_t n, char out[17]) {
+    uint64_t s = 0;
+    for (uint64_t i = 0; i < n; i++) s += mins[i];
+    snprintf(out, 17, "%llx", (unsigned long long)s);
+}
+
+// ---- ingest -------------------------------------------------------------------------------------
+ks_status ks_proteome_from_sequences(const char* const* seqs, const uint64_t* lens, const char* const* names, uint64_t n,
+                                     uint64_t ambig_seed, ks_proteome** out) {
+    return guarded([&] {
+        if (!out || (n && (!seqs || !lens))) fail(KS_ERR_VALIDATION, "Validation error: null argument");
+        std::vector<uint8_t> res;
+        std::vector<uint64_t> offs(n + 1, 0);
+        uint64_t total = 0;
+        for (uint64_t i = 0; i < n; i++) total += lens[i];
+        res.reserve(total);
+        for (uint64_t i = 0; i < n; i++) {
+            InvalidResidue bad;
+            if (!normalize_into(seqs[i], lens[i], i, ambig_seed, res, &bad)) fail_residue(bad);
+            if (res.size() - offs[i] > 0xffffffffull) fail(KS_ERR_CAPACITY, "protein longer than 2^32-1 residues");
+            offs[i + 1] = res.size();
+        }
+        ks_proteome* p = make_proteome(res.data(), res.size(), offs.data(), n);
+        if (names) for (uint64_t i = 0; i < n; i++) p->names.emplace_back(names[i] ? names[i] : "");
+        *out = p;
+    });
+}
+
+ks_status ks_proteome_from_fasta(const char* path, uint64_t ambig_seed, ks_proteome** out) {
+    return guarded([&] {
+        if (!out || !path) fail(KS_ERR_VALIDATION, "Validation error: null argument");
+        std::vector<std::string> names, seqs;
+        read_fasta(path, names, seqs);
+        std::vector<uint8_t> res;
+        std::vector<uint64_t> offs(seqs.size() + 1, 0);
+        for (size_t i = 0; i < seqs.size(); i++) {
+            InvalidResidue bad;
+            if (!normalize_into(seqs[i].data(), seqs[i].size(), i, ambig_seed, res, &bad)) fail_residue(bad);
+            if (res.size() - offs[i] > 0xffffffffull) fail(KS_ERR_CAPACITY, "protein longer than 2^32-1 residues");
+            offs[i + 1] = res.size();
+            std::string().swap(seqs[i]);
+        }
+        ks_proteome* p = make_proteome(res.data(), res.size(), offs.data(), names.size());
+        p->names = std::move(names);
+        *out = p;
+    });
+}
+
+ks_status ks_proteome_from_packed(const uint8_t* residues, const uint64_t* offsets, uint64_t n_proteins, ks_proteome** out) {
+    return guarded([&] {
+        if (!out || !offsets || (offsets[n_proteins] && !residues)) fail(KS_ERR_VALIDATION, "Validation error: null argument");
+        if (offsets[0] != 0) fail(KS_ERR_VALIDATION, "Validation error: offsets[0] must be 0");
+        for (uint64_t i = 0; i < n_proteins; i++) {
+            if (offsets[i + 1] < offsets[i]) fail(KS_ERR_VALIDATION, "Validation error: offsets must be non-decreasing");
+            if (offsets[i + 1] - offsets[i] > 0xffffffffull) fail(KS_ERR_CAPACITY, "protein longer than 2^32-1 residues");
+        }
+        *out = make_proteome(residues, offsets[n_proteins], offsets, n_proteins);
+    });
+}
+
+uint64_t ks_proteome_n_proteins(const ks_proteome* p) { return p ? p->n_prot : 0; }
+uint64_t ks_proteome_n_residues(const ks_proteome* p) { return p ? p->n_res : 0; }
+const uint8_t* ks_proteome_residues(const ks_proteome* p) { return p ? p->residues : nullptr; }
+const uint64_t* ks_proteome_offsets(const ks_proteome* p) { return p ? p->offsets : nullptr; }
+const char* ks_proteome_name(const ks_proteome* p, uint64_t i) {
+    return (p && i < p->names.size()) ? p->names[i].c_str() : "";
+}
+void ks_proteome_free(ks_proteome* p) {
+    if (!p) return;
+    host_free(p->residues, p->pinned);
+    host_free(p->offsets, p->pinned);
+    delete p;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// index handle
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+struct DeviceBatch {  // residues + offsets resident in HBM
+    uint8_t* res = nullptr;
+    uint64_t* offs = nullptr;
+    uint64_t res_cap = 0, offs_cap = 0;
+    uint64_t n_prot = 0, n_res = 0, n_windows = 0;
+    bool valid = false;
+};
+
+uint64_t count_windows(const uint64_t* offs, uint64_t n_prot, uint32_t k) {
+    uint64_t w = 0;
+    for (uint64_t i = 0; i < n_prot; i++) {
+        uint64_t len = offs[i + 1] - offs[i];
+        if (len >= k) w += len - k + 1;
+    }
+    return w;
+}
+
+}  // namespace
+
+struct ks_index {
+    ks_params params{};
+    uint64_t max_hash = 0;
+    int lz = 0;  // known-zero leading bits of every kept hash
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[10] = {};
+    uint64_t live_bytes = 0;
+    Arena* arena = nullptr;
+
+    DeviceBatch batch, qbatch;
+    // tuples
+    uint64_t *d_hash = nullptr, *d_loc = nullptr;
+    uint64_t cap = 0, n_tuples = 0;
+    uint64_t n_prot = 0, n_res = 0, n_windows = 0;
+    uint64_t* d_count = nullptr;
+    void* ws = nullptr;
+    size_t ws_bytes = 0;
+    // csr
+    bool finalized = false;
+    uint64_t* keys = nullptr;
+    uint32_t *key_grp = nullptr, *grp_start = nullptr, *t_size = nullptr, *t_abund = nullptr, *dir = nullptr;
+    uint64_t* d_counts = nullptr;
+    int dir_bits = 0, dir_shift = 0;
+    uint64_t U = 0, G = 0, n_ids = 0;
+    // bookkeeping
+    uint64_t l_sketch = 0, l_sort = 0, l_csr = 0, l_search = 0;
+    bool t_upload = false, t_sketch = false, t_sort = false, t_csr = false;
+    float ms_search = 0;
+
+    void use() { KS_CUDA(cudaSetDevice(params.device)); }
+    int end_bit() const { return 64 - lz; }
+};
+
+namespace {
+
+enum { EV_UP0, EV_UP1, EV_SK0, EV_SK1, EV_SO0, EV_SO1, EV_CS0, EV_CS1, EV_Q0, EV_Q1 };
+
+void ensure_ws(ks_index* x, size_t bytes) {
+    if (bytes <= x->ws_bytes) return;
+    if (x->ws) x->arena->release(x->ws);
+    x->ws = x->arena->alloc<char>(bytes);
+    x->ws_bytes = bytes;
+}
+
+void upload_batch(ks_index* x, DeviceBatch& b, const ks_proteome* p) {
+    if (p->n_prot >= 0xffffffffull) fail(KS_ERR_CAPACITY, "more than 2^32-2 proteins in one batch");
+    if (p->n_res + 64 > b.res_cap) {
+        if (b.res) x->arena->release(b.res);
+        b.res_cap = p->n_res + 64;
+        b.res = x->arena->alloc<uint8_t>(b.res_cap);
+    }
+    if (p->n_prot + 1 > b.offs_cap) {
+        if (b.offs) x->arena->release(b.offs);
+        b.offs_cap = p->n_prot + 1;
+        b.offs = x->arena->alloc<uint64_t>(b.offs_cap);
+    }
+    KS_CUDA(cudaMemcpyAsync(b.res, p->residues, p->n_res + 64, cudaMemcpyHostToDevice, x->stream));
+    KS_CUDA(cudaMemcpyAsync(b.offs, p->offsets, (p->n_prot + 1) * 8, cudaMemcpyHostToDevice, x->stream));
+    b.n_prot = p->n_prot;
+    b.n_res = p->n_res;
+    b.n_windows = count_windows(p->offsets, p->n_prot, x->params.ksize);
+    b.valid = true;
+}
+
+void drop_csr(ks_index* x) {
+    void* ptrs[] = {x->keys, x->key_grp, x->grp_start, x->t_size, x->t_abund, x->dir, x->d_counts};
+    for (void* p : ptrs) if (p) x->arena->release(p);
+    x->keys = nullptr; x->key_grp = x->grp_start = x->t_size = x->t_abund = x->dir = nullptr; x->d_counts = nullptr;
+    x->finalized = false;
+    x->U = x->G = x->n_ids = 0;
+}
+
+void grow_tuples(ks_index* x, uint64_t need) {
+    if (need <= x->cap) return;
+    uint64_t ncap = std::max<uint64_t>(need, x->n_tuples ? x->cap + x->cap / 2 : need);
+    uint64_t* nh = x->arena->alloc<uint64_t>(ncap);
+    uint64_t* nl = x->arena->alloc<uint64_t>(ncap);
+    if (x->n_tuples) {
+        KS_CUDA(cudaMemcpyAsync(nh, x->d_hash, x->n_tuples * 8, cudaMemcpyDeviceToDevice, x->stream));
+        KS_CUDA(cudaMemcpyAsync(nl, x->d_loc, x->n_tuples * 8, cudaMemcpyDeviceToDevice, x->stream));
+    }
+    if (x->d_hash) x->arena->release(x->d_hash);
+    if (x->d_loc) x->arena->release(x->d_loc);
+    x->d_hash = nh; x->d_loc = nl; x->cap = ncap;
+}
+
+uint64_t expected_kept(const ks_index* x, uint64_t windows) {
+    if (x->params.scaled <= 1) return windows;
+    double e = (double)windows / (double)x->params.scaled;
+    uint64_t est = (uint64_t)(e * 1.05 + 8.0 * std::sqrt(e + 1.0)) + 1024;
+    return std::min(windows, est);
+}
+
+// Sketch batch `b` into (out_hash, out_loc) of `capacity`; returns the number of tuples the batch produces
+// (which may exceed capacity, in which case nothing past capacity was written).
+uint64_t run_sketch(ks_index* x, const DeviceBatch& b, uint32_t pid_base, uint64_t* out_hash, uint64_t* out_loc,
+                    uint64_t capacity) {
+    ensure_ws(x, sketch_workspace_bytes(b.n_res));
+    SketchArgs a;
+    a.residues = b.res; a.offsets = b.offs; a.n_res = b.n_res; a.n_prot = b.n_prot;
+    a.k = x->params.ksize; a.moltype = x->params.moltype; a.max_hash = x->max_hash; a.pid_base = pid_base;
+    a.out_hash = out_hash; a.out_loc = out_loc; a.capacity = capacity; a.d_count = x->d_count; a.workspace = x->ws;
+    KS_CUDA(launch_sketch(a, x->stream, &x->l_sketch));
+    uint64_t n = 0;
+    KS_CUDA(cudaMemcpyAsync(&n, x->d_count, 8, cudaMemcpyDeviceToHost, x->stream));
+    KS_CUDA(cudaStreamSynchronize(x->stream));
+    return n;
+}
+
+void sketch_resident(ks_index* x) {
+    DeviceBatch& b = x->batch;
+    if (!b.valid) fail(KS_ERR_VALIDATION, "Validation error: no batch is resident (call ks_index_upload first)");
+    if (x->n_prot + b.n_prot >= 0xffffffffull) fail(KS_ERR_CAPACITY, "more than 2^32-2 proteins on one shard");
+    if (x->finalized) fail(KS_ERR_VALIDATION, "Validation error: index is finalized; ks_index_clear before adding more");
+    grow_tuples(x, x->n_tuples + expected_kept(x, b.n_windows));
+    KS_CUDA(cudaEventRecord(x->ev[EV_SK0], x->stream));
+    uint64_t n = run_sketch(x, b, (uint32_t)x->n_prot, x->d_hash + x->n_tuples, x->d_loc + x->n_tuples, x->cap - x->n_tuples);
+    if (n > x->cap - x->n_tuples) {  // estimate for scaled > 1 was short: grow to the exact size and redo
+        grow_tuples(x, x->n_tuples + n);
+        KS_CUDA(cudaEventRecord(x->ev[EV_SK0], x->stream));
+        n = run_sketch(x, b, (uint32_t)x->n_prot, x->d_hash + x->n_tuples, x->d_loc + x->n_tuples, x->cap - x->n_tuples);
+    }
+    KS_CUDA(cudaEventRecord(x->ev[EV_SK1], x->stream));
+    x->t_sketch = true;
+    x->n_tuples += n;
+    x->n_prot += b.n_prot;
+    x->n_res += b.n_res;
+    x->n_windows += b.n_windows;
+}
+
+void finalize(ks_index* x) {
+    if (x->finalized) return;
+    const uint64_t n = x->n_tuples;
+    if (n > MAX_TUPLES) fail(KS_ERR_CAPACITY, "more than 2^31-1 tuples on one shard: shard the proteome over more GPUs");
+    const uint32_t P = (uint32_t)x->n_prot;
+    x->t_abund = x->arena->alloc<uint32_t>(P);
+    x->t_size = x->arena->alloc<uint32_t>(P);
+    KS_CUDA(cudaEventRecord(x->ev[EV_SO0], x->stream));
+    KS_CUDA(launch_protein_abund(x->d_loc, n, P, x->t_abund, x->stream, &x->l_csr));
+    if (P) KS_CUDA(cudaMemcpyAsync(x->t_size, x->t_abund, (size_t)P * 4, cudaMemcpyDeviceToDevice, x->stream));
+    if (n) {
+        uint64_t* hb = x->arena->alloc<uint64_t>(n);
+        uint64_t* lb = x->arena->alloc<uint64_t>(n);
+        size_t tb = sort_temp_bytes(n, x->end_bit());
+        void* temp = x->arena->alloc<char>(tb);
+        int in_a = 1;
+        KS_CUDA(launch_sort(x->d_hash, x->d_loc, hb, lb, n, x->end_bit(), temp, tb, x->stream, &in_a, &x->l_sort));
+        x->arena->release(temp);
+        if (in_a) {
+            x->arena->release(hb); x->arena->release(lb);
+        } else {
+            x->arena->release(x->d_hash); x->arena->release(x->d_loc);
+            x->d_hash = hb; x->d_loc = lb; x->cap = n;
+        }
+    }
+    KS_CUDA(cudaEventRecord(x->ev[EV_SO1], x->stream));
+    x->t_sort = true;
+    int bits = 8;
+    while (bits < 26 && (1ull << bits) < n) bits++;
+    x->dir_bits = bits;
+    x->dir_shift = 64 - x->lz - bits;
+    x->keys = x->arena->alloc<uint64_t>(n);
+    x->key_grp = x->arena->alloc<uint32_t>(n + 1);
+    x->grp_start = x->arena->alloc<uint32_t>(n + 1);
+    x->dir = x->arena->alloc<uint32_t>((1ull << bits) + 1);
+    x->d_counts = x->arena->alloc<uint64_t>(2);
+    ensure_ws(x, csr_workspace_bytes(n));
+    KS_CUDA(cudaEventRecord(x->ev[EV_CS0], x->stream));
+    KS_CUDA(launch_csr(x->d_hash, x->d_loc, n, x->keys, x->key_grp, x->grp_start, x->t_size, x->d_counts, x->dir,
+                       x->dir_bits, x->dir_shift, x->ws, x->stream, &x->l_csr));
+    KS_CUDA(cudaEventRecord(x->ev[EV_CS1], x->stream));
+    x->t_csr = true;
+    uint64_t c[2];
+    KS_CUDA(cudaMemcpyAsync(c, x->d_counts, 16, cudaMemcpyDeviceToHost, x->stream));
+    KS_CUDA(cudaStreamSynchronize(x->stream));
+    x->U = c[0]; x->G = c[1];
+    x->finalized = true;
+}
+
+CsrView view_of(const ks_index* x) {
+    CsrView v;
+    v.hash = x->d_hash; v.loc = x->d_loc; v.keys = x->keys; v.key_grp = x->key_grp; v.grp_start = x->grp_start;
+    v.t_size = x->t_size; v.t_abund = x->t_abund; v.dir = x->dir; v.d_counts = x->d_counts; v.n = x->n_tuples;
+    v.n_prot = (uint32_t)x->n_prot; v.dir_bits = x->dir_bits; v.dir_shift = x->dir_shift;
+    return v;
+}
+
+template <class T>
+T* to_host(const T* d, uint64_t n, cudaStream_t st) {
+    T* h = (T*)malloc((n ? n : 1) * sizeof(T));
+    if (!h) throw std::bad_alloc();
+    if (n) KS_CUDA(cudaMemcpyAsync(h, d, n * sizeof(T), cudaMemcpyDeviceToHost, st));
+    return h;
+}
+
+// Fill a ks_sketch from grouped tuples.  tuple_hash/tuple_loc: the tuple list to export alongside.
+ks_sketch* sketch_to_host(const Grouped& g, const uint64_t* tuple_hash, const uint64_t* tuple_loc, uint64_t n,
+                          uint64_t n_prot, cudaStream_t st) {
+    ks_sketch* s = (ks_sketch*)calloc(1, sizeof(ks_sketch));
+    if (!s) throw std::bad_alloc();
+    s->n_proteins = n_prot;
+    s->n_tuples = n;
+    s->hash = to_host(tuple_hash, n, st);
+    uint64_t* loc = to_host(tuple_loc, n, st);
+    s->sig_ptr = to_host(g.sig_ptr, n_prot + 1, st);
+    s->mins = to_host(g.ent_hash, g.n_entries, st);
+    uint32_t* first = to_host(g.ent_first, g.n_entries + 1, st);
+    KS_CUDA(cudaStreamSynchronize(st));
+    s->pid = (uint32_t*)malloc((n ? n : 1) * 4);
+    s->pos = (uint32_t*)malloc((n ? n : 1) * 4);
+    s->abunds = (uint64_t*)malloc((g.n_entries ? g.n_entries : 1) * 8);
+    if (!s->pid || !s->pos || !s->abunds) throw std::bad_alloc();
+    for (uint64_t i = 0; i < n; i++) { s->pid[i] = (uint32_t)(loc[i] >> 32); s->pos[i] = (uint32_t)loc[i]; }
+    for (uint64_t e = 0; e < g.n_entries; e++) s->abunds[e] = first[e + 1] - first[e];
+    free(loc);
+    free(first);
+    return s;
+}
+
+struct ResultDevice {
+    Arena* arena;
+    std::map<std::string, void*> cols;
+};
+
+}  // namespace
+
+extern "C" {
+
+ks_status ks_index_create(const ks_params* params, ks_index** out) {
+    return guarded([&] {
+        if (!params || !out) fail(KS_ERR_VALIDATION, "Validation error: null argument");
+        if (params->moltype < 0 || params->moltype > 2)
+            fail(KS_ERR_INVALID_MOLTYPE, "Invalid moltype: " + std::to_string(params->moltype) +
+                                             ", only 'protein', 'hp', or 'dayhoff' are supported");
+        if (params->ksize == 0 || params->ksize > (uint32_t)SK_MAX_K)
+            fail(KS_ERR_INVALID_KSIZE, "Invalid k-mer size: " + std::to_string(params->ksize));  // errors.rs:20-21
+        if (params->scaled == 0) fail(KS_ERR_VALIDATION, "Validation error: scaled must be >= 1");
+        int n = ks_device_count();
+        if (n == 0) fail(KS_ERR_NO_DEVICE, "no CUDA device: kmerseek_b200 has no CPU fallback");
+        if (params->device < 0 || params->device >= n) fail(KS_ERR_NO_DEVICE, "CUDA device ordinal out of range");
+        ks_index* x = new ks_index();
+        x->params = *params;
+        x->max_hash = ks_max_hash(params->scaled);
+        x->lz = clz64(x->max_hash);
+        try {
+            x->use();
+            KS_CUDA(cudaStreamCreateWithFlags(&x->stream, cudaStreamNonBlocking));
+            for (auto& e : x->ev) KS_CUDA(cudaEventCreate(&e));
+            cudaMemPool_t pool;
+            KS_CUDA(cudaDeviceGetDefaultMemPool(&pool, params->device));
+            uint64_t thr = UINT64_MAX;  // keep freed blocks in the pool: steady-state steps never reach the driver
+            KS_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+            x->arena = new Arena(x->stream, &x->live_bytes);
+            x->d_count = x->arena->alloc<uint64_t>(1);
+        } catch (...) {
+            ks_index_destroy(x);
+            throw;
+        }
+        *out = x;
+    });
+}
+
+void ks_index_destroy(ks_index* x) {
+    if (!x) return;
+    cudaSetDevice(x->params.device);
+    if (x->stream) cudaStreamSynchronize(x->stream);
+    delete x->arena;
+    if (x->stream) cudaStreamSynchronize(x->stream);
+    for (auto& e : x->ev) if (e) cudaEventDestroy(e);
+    if (x->stream) cudaStreamDestroy(x->stream);
+    delete x;
+}
+
+ks_status ks_index_params(const ks_index* x, ks_params* out) {
+    if (!x || !out) return set_error(KS_ERR_VALIDATION, "Validation error: null argument");
+    *out = x->params;
+    return KS_OK;
+}
+void* ks_index_stream(const ks_index* x) { return x ? (void*)x->stream : nullptr; }
+ks_status ks_index_sync(ks_index* x) {
+    return guarded([&] { x->use(); KS_CUDA(cudaStreamSynchronize(x->stream)); });
+}
+
+ks_status ks_index_upload(ks_index* x, const ks_proteome* p) {
+    return guarded([&] {
+        if (!x || !p) fail(KS_ERR_VALIDATION, "Validation error: null argument");
+        x->use();
+        KS_CUDA(cudaEventRecord(x->ev[EV_UP0], x->stream));
+        upload_batch(x, x->batch, p);
+        KS_CUDA(cudaEventRecord(x->ev[EV_UP1], x->stream));
+        x->t_upload = true;
+    });
+}
+ks_status ks_index_sketch_resident(ks_index* x) {
+    return guarded([&] { x->use(); sketch_resident(x); });
+}
+ks_status ks_index_add_proteome(ks_index* x, const ks_proteome* p) {
+    ks_status s = ks_index_upload(x, p);
+    return s != KS_OK ? s : ks_index_sketch_resident(x);
+}
+ks_status ks_index_finalize(ks_index* x) {
+    return guarded([&] { x->use(); finalize(x); });
+}
+ks_status ks_index_clear(ks_index* x) {
+    return guarded([&] {
+        x->use();
+        drop_csr(x);
+        x->n_tuples = 0; x->n_prot = 0; x->n_res = 0; x->n_windows = 0;
+    });
+}
+ks_status ks_index_process_fasta(ks_index* x, const char* path, uint64_t ambig_seed) {
+    ks_proteome* p = nullptr;
+    ks_status s = ks_proteome_from_fasta(path, ambig_seed, &p);
+    if (s != KS_OK) return s;
+    s = ks_index_add_proteome(x, p);
+    ks_proteome_free(p);
+    return s != KS_OK ? s : ks_index_finalize(x);
+}
+
+ks_status ks_index_add_tuples(ks_index* x, const uint64_t* hash, const uint32_t* pid, const uint32_t* pos, uint64_t n,
+                              uint64_t n_proteins) {
+    return guarded([&] {
+        if (!x || (n && (!hash || !pid || !pos))) fail(KS_ERR_VALIDATION, "Validation error: null argument");
+        x->use();
+        if (x->n_prot + n_proteins >= 0xffffffffull) fail(KS_ERR_CAPACITY, "more than 2^32-2 proteins on one shard");
+        std::vector<uint64_t> loc(n);
+        for (uint64_t i = 0; i < n; i++) {
+            if (pid[i] >= n_proteins) fail(KS_ERR_VALIDATION, "Validation error: tuple protein index out of range");
+            loc[i] = ((uint64_t)(pid[i] + (uint32_t)x->n_prot) << 32) | pos[i];
+            if (i && loc[i] <= loc[i - 1]) fail(KS_ERR_VALIDATION, "Validation error: tuples must be ordered by (protein, pos)");
+        }
+        if (x->finalized) fail(KS_ERR_VALIDATION, "Validation error: index is finalized; ks_index_clear before adding more");
+        grow_tuples(x, x->n_tuples + n);
+        if (n) {
+            KS_CUDA(cudaMemcpyAsync(x->d_hash + x->n_tuples, hash, n * 8, cudaMemcpyHostToDevice, x->stream));
+            KS_CUDA(cudaMemcpyAsync(x->d_loc + x->n_tuples, loc.data(), n * 8, cudaMemcpyHostToDevice, x->stream));
+            KS_CUDA(cudaStreamSynchronize(x->stream));
+        }
+        x->n_tuples += n;
+        x->n_prot += n_proteins;
+    });
+}
+
+ks_status ks_index_stats(ks_index* x, ks_stats* out) {
+    return guarded([&] {
+        if (!x || !out) fail(KS_ERR_VALIDATION, "Validation error: null argument");
+        x->use();
+        KS_CUDA(cudaStreamSynchronize(x->stream));
+        ks_stats s{};
+        s.n_proteins = x->n_prot; s.n_residues = x->n_res; s.n_windows = x->n_windows; s.n_tuples = x->n_tuples;
+        s.n_unique_hashes = x->U; s.n_groups = x->G; s.n_distinct_ids = x->n_ids; s.device_bytes = x->live_bytes;
+        s.sketch_launches = x->l_sketch; s.sort_launches = x->l_sort; s.csr_launches = x->l_csr; s.search_launches = x->l_search;
+        if (x->t_upload) KS_CUDA(cudaEventElapsedTime(&s.ms_upload, x->ev[EV_UP0], x->ev[EV_UP1]));
+        if (x->t_sketch) KS_CUDA(cudaEventElapsedTime(&s.ms_sketch, x->ev[EV_SK0], x->ev[EV_SK1]));
+        if (x->t_sort) KS_CUDA(cudaEventElapsedTime(&s.ms_sort, x->ev[EV_SO0], x->ev[EV_SO1]));
+        if (x->t_csr) KS_CUDA(cudaEventElapsedTime(&s.ms_csr, x->ev[EV_CS0], x->ev[EV_CS1]));
+        s.ms_search = x->ms_search;
+        s.finalized = x->finalized ? 1 : 0;
+        *out = s;
+    });
+}
+
+// ---- sketch export ------------------------------------------------------------------------------
+ks_status ks_sketch_batch(ks_index* x, const ks_proteome* p, ks_sketch** out) {
+    return guarded([&] {
+        if (!x || !p || !out) fail(KS_ERR_VALIDATION, "Validation error: null argument");
+        x->use();
+        DeviceBatch b;
+        Arena keep(x->stream, &x->live_bytes), tmp(x->stream, &x->live_bytes);
+        // a private batch: the index's resident batch and tuples are left alone
+        b.res = keep.alloc<uint8_t>(p->n_res + 64);
+        b.offs = keep.alloc<uint64_t>(p->n_prot + 1);
+        b.res_cap = p->n_res + 64; b.offs_cap = p->n_prot + 1;
+        KS_CUDA(cudaMemcpyAsync(b.res, p->residues, p->n_res + 64, cudaMemcpyHostToDevice, x->stream));
+        KS_CUDA(cudaMemcpyAsync(b.offs, p->offsets, (p->n_prot + 1) * 8, cudaMemcpyHostToDevice, x->stream));
+        b.n_prot = p->n_prot; b.n_res = p->n_res; b.n_windows = count_windows(p->offsets, p->n_prot, x->params.ksize);
+        b.valid = true;
+        const uint64_t cap = b.n_windows;
+        uint64_t* h = keep.alloc<uint64_t>(cap);
+        uint64_t* l = keep.alloc<uint64_t>(cap);
+        uint64_t n = run_sketch(x, b, 0, h, l, cap);
+        Grouped g;
+        group_by_owner(keep, tmp, h, l, n, (uint32_t)p->n_prot, x->end_bit(), &g, &x->l_sketch);
+        *out = sketch_to_host(g, h, l, n, p->n_prot, x->stream);
+    });
+}
+
+ks_status ks_index_export(ks_index* x, ks_sketch** out) {
+    return guarded([&] {
+        if (!x || !out) fail(KS_ERR_VALIDATION, "Validation error: null argument");
+        if (!x->finalized) fail(KS_ERR_NOT_FINALIZED, "index is not finalized");
+        x->use();
+        Arena keep(x->stream, &x->live_bytes), tmp(x->stream, &x->live_bytes);
+        Grouped g;
+        group_by_owner(keep, tmp, x->d_hash, x->d_loc, x->n_tuples, (uint32_t)x->n_prot, x->end_bit(), &g, &x->l_csr);
+        *out = sketch_to_host(g, x->d_hash, x->d_loc, x->n_tuples, x->n_prot, x->stream);
+    });
+}
+
+void ks_sketch_free(ks_sketch* s) {
+    if (!s) return;
+    free(s->hash); free(s->pid); free(s->pos); free(s->sig_ptr); free(s->mins); free(s->abunds);
+    free(s);
+}
+
+ks_status ks_index_csr(ks_index* x, ks_csr** out) {
+    return guarded([&] {
+        if (!x || !out) fail(KS_ERR_VALIDATION, "Validation error: null argument");
+        if (!x->finalized) fail(KS_ERR_NOT_FINALIZED, "index is not finalized");
+        x->use();
+        ks_csr* c = (ks_csr*)calloc(1, sizeof(ks_csr));
+        if (!c) throw std::bad_alloc();
+        c->n_keys = x->U; c->n_postings = x->n_tuples;
+        c->keys = to_host(x->keys, x->U, x->stream);
+        uint32_t* kg = to_host(x->key_grp, x->U + 1, x->stream);
+        uint32_t* gs = to_host(x->grp_start, x->G + 1, x->stream);
+        uint64_t* loc = to_host(x->d_loc, x->n_tuples, x->stream);
+        KS_CUDA(cudaStreamSynchronize(x->stream));
+        c->row_ptr = (uint64_t*)malloc((x->U + 1) * 8);
+        c->pid = (uint32_t*)malloc((x->n_tuples ? x->n_tuples : 1) * 4);
+        c->pos = (uint32_t*)malloc((x->n_tuples ? x->n_tuples : 1) * 4);
+        if (!c->row_ptr || !c->pid || !c->pos) throw std::bad_alloc();
+        for (uint64_t u = 0; u <= x->U; u++) c->row_ptr[u] = gs[kg[u]];
+        for (uint64_t i = 0; i < x->n_tuples; i++) { c->pid[i] = (uint32_t)(loc[i] >> 32); c->pos[i] = (uint32_t)loc[i]; }
+        free(kg); free(gs); free(loc);
+        *out = c;
+    });
+}
+void ks_csr_free(ks_csr* c) {
+    if (!c) return;
+    free(c->keys); free(c->row_ptr); free(c->pid); free(c->pos);
+    free(c);
+}
+
+// ---- search --------------------------------------------------------------------------------------
+ks_status ks_query_upload(ks_index* x, const ks_proteome* q) {
+    return guarded([&] {
+        if (!x || !q) fail(KS_ERR_VALIDATION, "Validation error: null argument");
+        x->use();
+        upload_batch(x, x->qbatch, q);
+    });
+}
+
+ks_status ks_search_resident(ks_index* x, uint32_t flags, ks_search_result** out) {
+    return guarded([&] {
+        if (!x || !out) fail(KS_ERR_VALIDATION, "Validation error: null argument");
+        if (!x->finalized) fail(KS_ERR_NOT_FINALIZED, "index is not finalized");
+        if (!x->qbatch.valid) fail(KS_ERR_VALIDATION, "Validation error: no query batch is resident");
+        x->use();
+        cudaStream_t st = x->stream;
+        const DeviceBatch& qb = x->qbatch;
+        Arena* keep = new Arena(st, &x->live_bytes);
+        ks_search_result* r = (ks_search_result*)calloc(1, sizeof(ks_search_result));
+        ResultDevice* rd = new ResultDevice{keep, {}};
+        if (!r) { delete rd; delete keep; throw std::bad_alloc(); }
+        r->device_block = rd;
+        try {
+            Arena tmp(st, &x->live_bytes);
+            KS_CUDA(cudaEventRecord(x->ev[EV_Q0], st));
+            uint64_t* qh = tmp.alloc<uint64_t>(qb.n_windows);
+            uint64_t* ql = tmp.alloc<uint64_t>(qb.n_windows);
+            const uint64_t nqt = run_sketch(x, qb, 0, qh, ql, qb.n_windows);
+            Grouped qs;
+            SearchDevice sd;
+            search_device(*keep, tmp, view_of(x), qh, ql, nqt, (uint32_t)qb.n_prot, x->params.ksize, x->end_bit(),
+                          (flags & KS_SEARCH_HITS) != 0, &qs, &sd, &x->l_search);
+            KS_CUDA(cudaEventRecord(x->ev[EV_Q1], st));
+            r->n_queries = qb.n_prot;
+            r->n_pairs = sd.n_pairs;
+            r->n_hits = sd.n_hits;
+            static const char* score_names[N_SCORE_COLS] = {
+                "containment", "containment_target_in_query", "max_containment", "jaccard", "query_containment_ani",
+                "match_containment_ani", "average_containment_ani", "max_containment_ani", "average_abund",
+                "median_abund", "std_abund", "f_weighted_target_in_query"};
+            rd->cols["pair_qid"] = sd.pair_qid; rd->cols["pair_pid"] = sd.pair_pid;
+            rd->cols["intersect_hashes"] = sd.intersect; rd->cols["q_size"] = sd.q_size; rd->cols["t_size"] = sd.t_size;
+            rd->cols["n_weighted_found"] = sd.n_weighted_found; rd->cols["total_weighted_hashes"] = sd.total_weighted;
+            for (int i = 0; i < N_SCORE_COLS; i++) rd->cols[score_names[i]] = sd.score[i];
+            rd->cols["hit_qid"] = sd.hit_qid; rd->cols["hit_pid"] = sd.hit_pid; rd->cols["hit_qpos"] = sd.hit_qpos;
+            rd->cols["hit_tpos"] = sd.hit_tpos; rd->cols["hit_hash"] = sd.hit_hash;
+            rd->cols["q_sig_ptr"] = qs.sig_ptr; rd->cols["q_mins"] = qs.ent_hash;
+            // query sketches always come back (they are small): md5 / |Q| need them
+            r->q_sig_ptr = to_host(qs.sig_ptr, qb.n_prot + 1, st);
+            r->q_mins = to_host(qs.ent_hash, qs.n_entries, st);
+            uint32_t* first = to_host(qs.ent_first, qs.n_entries + 1, st);
+            if (!(flags & KS_SEARCH_DEVICE_ONLY)) {
+                const uint64_t np = sd.n_pairs, nh = sd.n_hits;
+                r->pair_qid = to_host(sd.pair_qid, np, st); r->pair_pid = to_host(sd.pair_pid, np, st);
+                r->intersect_hashes = to_host(sd.intersect, np, st);
+                r->q_size = to_host(sd.q_size, np, st); r->t_size = to_host(sd.t_size, np, st);
+                r->n_weighted_found = to_host(sd.n_weighted_found, np, st);
+                r->total_weighted_hashes = to_host(sd.total_weighted, np, st);
+                double** dst[N_SCORE_COLS] = {&r->containment, &r->containment_target_in_query, &r->max_containment,
+                                              &r->jaccard, &r->query_containment_ani, &r->match_containment_ani,
+                                              &r->average_containment_ani, &r->max_containment_ani, &r->average_abund,
+                                              &r->median_abund, &r->std_abund, &r->f_weighted_target_in_query};
+                for (int i = 0; i < N_SCORE_COLS; i++) *dst[i] = to_host(sd.score[i], np, st);
+                if (flags & KS_SEARCH_HITS) {
+                    r->hit_qid = to_host(sd.hit_qid, nh, st); r->hit_pid = to_host(sd.hit_pid, nh, st);
+                    r->hit_qpos = to_host(sd.hit_qpos, nh, st); r->hit_tpos = to_host(sd.hit_tpos, nh, st);
+                    r->hit_hash = to_host(sd.hit_hash, nh, st);
+                }
+            }
+            KS_CUDA(cudaStreamSynchronize(st));
+            r->q_abunds = (uint64_t*)malloc((qs.n_entries ? qs.n_entries : 1) * 8);
+            if (!r->q_abunds) throw std::bad_alloc();
+            for (uint64_t e = 0; e < qs.n_entries; e++) r->q_abunds[e] = first[e + 1] - first[e];
+            free(first);
+            KS_CUDA(cudaEventElapsedTime(&r->ms_device, x->ev[EV_Q0], x->ev[EV_Q1]));
+            x->ms_search = r->ms_device;
+        } catch (...) {
+            ks_search_result_free(r);
+            throw;
+        }
+        *out = r;
+    });
+}
+
+ks_status ks_search_batch(ks_index* x, const ks_proteome* queries, uint32_t flags, ks_search_result** out) {
+    ks_status s = ks_query_upload(x, queries);
+    return s != KS_OK ? s : ks_search_resident(x, flags, out);
+}
+
+void* ks_search_result_device_column(const ks_search_result* r, const char* name) {
+    if (!r || !r->device_block || !name) return nullptr;
+    ResultDevice* rd = (ResultDevice*)r->device_block;
+    auto it = rd->cols.find(name);
+    return it == rd->cols.end() ? nullptr : it->second;
+}
+
+void ks_search_result_free(ks_search_result* r) {
+    if (!r) return;
+    void* ptrs[] = {r->q_sig_ptr, r->q_mins, r->q_abunds, r->pair_qid, r->pair_pid, r->intersect_hashes, r->q_size,
+                    r->t_size, r->n_weighted_found, r->total_weighted_hashes, r->containment,
+                    r->containment_target_in_query, r->max_containment, r->jaccard, r->query_containment_ani,
+                    r->match_containment_ani, r->average_containment_ani, r->max_containment_ani, r->average_abund,
+                    r->median_abund, r->std_abund, r->f_weighted_target_in_query, r->hit_qid, r->hit_pid, r->hit_qpos,
+                    r->hit_tpos, r->hit_hash};
+    for (void* p : ptrs) free(p);
+    if (r->device_block) {
+        ResultDevice* rd = (ResultDevice*)r->device_block;
+        delete rd->arena;
+        delete rd;
+    }
+    free(r);
+}
+
+}  // extern "C"

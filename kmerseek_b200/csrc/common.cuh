@@ -1,0 +1,77 @@
+// Shared device helpers for the kmerseek B200 kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ks {
+
+constexpr uint64_t C1 = 0x87c37b91114253d5ULL;
+constexpr uint64_t C2 = 0x4cf5ad432745937fULL;
+constexpr uint64_t SEED = 42;
+
+__host__ __device__ __forceinline__ uint64_t rotl64(uint64_t x, int r) { return (x << r) | (x >> (64 - r)); }
+
+__host__ __device__ __forceinline__ uint64_t fmix64(uint64_t k) {
+    k ^= k >> 33;
+    k *= 0xff51afd7ed558ccdULL;
+    k ^= k >> 33;
+    k *= 0xc4ceb9fe1a85ec53ULL;
+    k ^= k >> 33;
+    return k;
+}
+__host__ __device__ __forceinline__ uint64_t mix_k1(uint64_t k1) { return rotl64(k1 * C1, 31) * C2; }
+__host__ __device__ __forceinline__ uint64_t mix_k2(uint64_t k2) { return rotl64(k2 * C2, 33) * C1; }
+
+// ---------------------------------------------------------------------------------------------
+// Single-pass chained scan state ("decoupled look-back").  One 64-bit word per tile carries the
+// flag in the top two bits and the value in the low 62, so a reader never sees a flag without its
+// value and no fence is needed between them.
+// ---------------------------------------------------------------------------------------------
+constexpr uint64_t SCAN_AGG = 1ULL << 62;  // tile aggregate available
+constexpr uint64_t SCAN_PFX = 2ULL << 62;  // inclusive prefix available
+constexpr uint64_t SCAN_VAL = (1ULL << 62) - 1;
+
+__device__ __forceinline__ uint64_t ld_relaxed(const uint64_t* p) {
+    uint64_t v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed(uint64_t* p, uint64_t v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// Called by ONE full warp of the tile.  Publishes this tile's aggregate, walks back over the
+// predecessors' words 32 at a time, returns the exclusive prefix (same value in every lane) and
+// publishes the inclusive prefix.  `value` must be < 2^62.
+__device__ __forceinline__ uint64_t scan_lookback(uint64_t* status, uint32_t tile, uint64_t value) {
+    const uint32_t lane = threadIdx.x & 31;
+    if (tile == 0) {
+        if (lane == 0) st_relaxed(status, SCAN_PFX | value);
+        return 0;
+    }
+    if (lane == 0) st_relaxed(status + tile, SCAN_AGG | value);
+    uint64_t excl = 0;
+    int64_t base = (int64_t)tile - 1;
+    while (true) {
+        int64_t idx = base - lane;
+        uint64_t w = SCAN_PFX;  // tiles before 0: prefix 0
+        if (idx >= 0) {
+            do { w = ld_relaxed(status + idx); } while ((w >> 62) == 0);
+        }
+        uint32_t pfx_mask = __ballot_sync(0xffffffffu, (w >> 62) == 2);
+        uint64_t v = w & SCAN_VAL;
+        if (pfx_mask) {
+            int first = __ffs(pfx_mask) - 1;  // nearest predecessor that holds an inclusive prefix
+            if ((int)lane > first) v = 0;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        excl += v;
+        if (pfx_mask) break;
+        base -= 32;
+    }
+    if (lane == 0) st_relaxed(status + tile, SCAN_PFX | ((excl + value) & SCAN_VAL));
+    return excl;
+}
+
+}  // namespace ks

@@ -1,0 +1,337 @@
+// Fused sketch kernel for sm_100a.
+//
+// One launch does, for every k-mer window of every protein of the resident batch:
+//   reduced-alphabet translation (256-entry LUT in shared memory)        -- src/rust/encoding.rs:43-53
+//   MurmurHash3_x64_128(translated k-mer, seed 42), low word            -- sourmash::_hash_murmur, src/rust/index.rs:766
+//   FracMinHash filter  h != 0 && h <= max_hash                          -- KmerMinHash::add_protein, src/rust/signature.rs:273-274
+//   ordered compaction of the surviving (hash, protein, pos) tuples      -- process_kmers, src/rust/index.rs:749-786
+// (paths relative to the reference repository).  Data layout and roofline: DESIGN.md section 3.
+//
+// Shape: the residue stream is cut into tiles of SK_TILE window-start positions.  A CTA takes a tile
+// (dynamic ticket, so a tile's predecessors have always started), pulls SK_TILE + k - 1 residues with
+// coalesced 16-byte loads, translates them once into shared memory, and each warp then walks 8 rows of
+// 32 consecutive windows: lane l of row r owns window (warp*8 + r)*32 + l, rebuilds its k bytes from
+// aligned shared-memory words with funnel shifts, hashes in registers, and the row is compacted with a
+// ballot into a per-warp staging area (conflict-free, lanes write consecutive slots).  Tile totals are
+// chained across CTAs with a single-pass decoupled look-back, after which every warp streams its staged
+// tuples to their final, globally ordered position with fully coalesced stores.  Output order is
+// (protein, pos), independent of scheduling, so the later stable sort by hash is deterministic.
+#include "common.cuh"
+#include "sketch.cuh"
+
+namespace ks {
+
+namespace {
+
+constexpr int OFFS_CACHE = 256;  // offsets of the proteins that intersect a tile, cached in smem when they fit
+
+template <int K>
+__device__ __forceinline__ uint64_t murmur_words(const uint32_t* a) {
+    // a[] = the K translated bytes, little-endian packed, bytes past K zeroed.
+    constexpr int NB = K / 16, REM = K % 16, NWORDS = (K + 3) / 4;
+    uint64_t h1 = SEED, h2 = SEED;
+#pragma unroll
+    for (int b = 0; b < NB; b++) {
+        uint64_t k1 = (uint64_t)a[4 * b] | ((uint64_t)a[4 * b + 1] << 32);
+        uint64_t k2 = (uint64_t)a[4 * b + 2] | ((uint64_t)a[4 * b + 3] << 32);
+        h1 ^= mix_k1(k1);
+        h1 = rotl64(h1, 27) + h2;
+        h1 = h1 * 5 + 0x52dce729;
+        h2 ^= mix_k2(k2);
+        h2 = rotl64(h2, 31) + h1;
+        h2 = h2 * 5 + 0x38495ab5;
+    }
+    auto word = [&](int i) -> uint64_t { return i < NWORDS ? (uint64_t)a[i] : 0ull; };
+    if (REM > 8) {
+        uint64_t k2 = word(4 * NB + 2) | (word(4 * NB + 3) << 32);
+        h2 ^= mix_k2(k2);
+    }
+    if (REM > 0) {
+        uint64_t k1 = word(4 * NB) | (word(4 * NB + 1) << 32);
+        h1 ^= mix_k1(k1);
+    }
+    h1 ^= (uint64_t)K;
+    h2 ^= (uint64_t)K;
+    h1 += h2;
+    h2 += h1;
+    h1 = fmix64(h1);
+    h2 = fmix64(h2);
+    return h1 + h2;
+}
+
+// Generic k (> SK_MAX_TEMPLATE_K): byte loop over shared memory.  Rare path, kept simple.
+__device__ __forceinline__ uint64_t murmur_bytes(const uint8_t* s, uint32_t k) {
+    uint64_t h1 = SEED, h2 = SEED;
+    uint32_t nb = k / 16;
+    for (uint32_t b = 0; b < nb; b++) {
+        uint64_t k1 = 0, k2 = 0;
+        for (int i = 0; i < 8; i++) {
+            k1 |= (uint64_t)s[16 * b + i] << (8 * i);
+            k2 |= (uint64_t)s[16 * b + 8 + i] << (8 * i);
+        }
+        h1 ^= mix_k1(k1);
+        h1 = rotl64(h1, 27) + h2;
+        h1 = h1 * 5 + 0x52dce729;
+        h2 ^= mix_k2(k2);
+        h2 = rotl64(h2, 31) + h1;
+        h2 = h2 * 5 + 0x38495ab5;
+    }
+    const uint8_t* t = s + 16 * nb;
+    uint32_t rem = k & 15;
+    uint64_t k1 = 0, k2 = 0;
+    for (uint32_t i = 8; i < rem; i++) k2 |= (uint64_t)t[i] << (8 * (i - 8));
+    for (uint32_t i = 0; i < (rem < 8 ? rem : 8); i++) k1 |= (uint64_t)t[i] << (8 * i);
+    if (rem > 8) h2 ^= mix_k2(k2);
+    if (rem > 0) h1 ^= mix_k1(k1);
+    h1 ^= k;
+    h2 ^= k;
+    h1 += h2;
+    h2 += h1;
+    h1 = fmix64(h1);
+    h2 = fmix64(h2);
+    return h1 + h2;
+}
+
+struct Workspace {
+    uint32_t* ticket;
+    uint64_t* status;
+    uint32_t* tile_pid;
+};
+
+__host__ __device__ inline uint64_t n_tiles_of(uint64_t n_res) { return (n_res + SK_TILE - 1) / SK_TILE; }
+
+__host__ inline Workspace carve(void* ws, uint64_t n_res) {
+    uint64_t nt = n_tiles_of(n_res);
+    char* p = (char*)ws;
+    Workspace w;
+    w.ticket = (uint32_t*)p;
+    w.status = (uint64_t*)(p + 16);
+    w.tile_pid = (uint32_t*)(p + 16 + nt * 8);
+    return w;
+}
+
+// tile_pid[t] = index of the protein that contains residue t*SK_TILE (last p with offsets[p] <= that
+// position, clipped to n_prot-1); one entry past the last tile bounds the last tile's protein range.
+__global__ void tile_pid_kernel(const uint64_t* __restrict__ offsets, uint64_t n_prot, uint64_t n_tiles,
+                                uint32_t* __restrict__ tile_pid) {
+    uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (t > n_tiles) return;
+    uint64_t g = t * SK_TILE;
+    uint64_t lo = 0, hi = n_prot - 1;  // invariant offsets[lo] <= g (offsets[0] == 0)
+    while (lo < hi) {
+        uint64_t mid = (lo + hi + 1) >> 1;
+        if (offsets[mid] <= g) lo = mid; else hi = mid - 1;
+    }
+    tile_pid[t] = (uint32_t)lo;
+}
+
+template <int K, bool TRANSLATE>
+__global__ void __launch_bounds__(SK_THREADS)
+sketch_kernel(SketchArgs a, Lut256 lut, uint32_t* __restrict__ ticket, uint64_t* __restrict__ status,
+              const uint32_t* __restrict__ tile_pid) {
+    constexpr int KMAX = K == 0 ? SK_MAX_K : K;
+    constexpr int RES_WORDS = (SK_TILE + KMAX + 16 + 3) / 4;
+    __shared__ __align__(16) uint32_t s_res[RES_WORDS];
+    __shared__ __align__(16) uint64_t s_hash[SK_TILE];
+    __shared__ __align__(16) uint64_t s_loc[SK_TILE];
+    __shared__ uint64_t s_offs[OFFS_CACHE];
+    __shared__ uint8_t s_lut[256];
+    __shared__ uint32_t s_wtot[SK_THREADS / 32];
+    __shared__ uint32_t s_tile;
+    __shared__ uint64_t s_base;
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t k = K == 0 ? a.k : (uint32_t)K;
+
+    if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+    if (TRANSLATE) s_lut[tid] = lut.b[tid];
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const uint64_t g0 = (uint64_t)tile * SK_TILE;
+    const uint64_t n_tiles = n_tiles_of(a.n_res);
+
+    // proteins that intersect this tile: [p_lo, p_hi]; cache offsets[p_lo .. p_hi+1]
+    const uint32_t p_lo = tile_pid[tile], p_hi = tile_pid[tile + 1];
+    const uint32_t n_off = p_hi - p_lo + 2;
+    const bool cached = n_off <= OFFS_CACHE;
+    if (cached)
+        for (uint32_t i = tid; i < n_off; i += SK_THREADS) s_offs[i] = a.offsets[p_lo + i];
+
+    // stage residues: coalesced 16-byte loads, translate once, 16-byte shared stores
+    {
+        const uint32_t n_chunks = (SK_TILE + k - 1 + 15) / 16;
+        if (tid < n_chunks) {
+            uint64_t g = g0 + 16ull * tid;
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (g < a.n_res) v = __ldg(reinterpret_cast<const uint4*>(a.residues + g));
+            if (TRANSLATE) {
+                uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    uint32_t x = w[i];
+                    w[i] = (uint32_t)s_lut[x & 0xff] | ((uint32_t)s_lut[(x >> 8) & 0xff] << 8) |
+                           ((uint32_t)s_lut[(x >> 16) & 0xff] << 16) | ((uint32_t)s_lut[x >> 24] << 24);
+                }
+                v = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+            reinterpret_cast<uint4*>(s_res)[tid] = v;
+        }
+    }
+    __syncthreads();
+
+    const uint64_t* offs = cached ? (const uint64_t*)s_offs - p_lo : a.offsets;
+
+    // protein of this lane's first window
+    const uint32_t w0 = warp * (SK_ROWS * 32) + lane;  // tile-local index of row 0's window
+    uint64_t g = g0 + w0;
+    uint32_t p = p_lo;
+    uint64_t pstart = 0, pend = 0;
+    if (g < a.n_res) {
+        uint32_t lo = p_lo, hi = p_hi;
+        while (lo < hi) {
+            uint32_t mid = (lo + hi + 1) >> 1;
+            if (offs[mid] <= g) lo = mid; else hi = mid - 1;
+        }
+        p = lo;
+        pstart = offs[p];
+        pend = offs[p + 1];
+    }
+
+    uint32_t wcount = 0;  // tuples staged by this warp so far (uniform across the warp)
+    const uint32_t sh = (lane & 3) * 8;
+#pragma unroll
+    for (int r = 0; r < SK_ROWS; r++, g += 32) {
+        const uint32_t wi = w0 + r * 32;
+        bool valid = false;
+        if (g < a.n_res) {
+            while (g >= pend) { p++; pstart = pend; pend = offs[p + 1]; }
+            valid = g + k <= pend;
+        }
+        uint64_t h;
+        if (K == 0) {
+            h = valid ? murmur_bytes(reinterpret_cast<const uint8_t*>(s_res) + wi, k) : 0;
+        } else {
+            constexpr int NW = (KMAX + 3 + 3) / 4;  // aligned words that cover bytes [wi, wi+K)
+            constexpr int KW = (KMAX + 3) / 4;
+            uint32_t x[NW + 1];
+#pragma unroll
+            for (int i = 0; i < NW; i++) x[i] = s_res[(wi >> 2) + i];
+            x[NW] = 0;
+            uint32_t b[KW];
+#pragma unroll
+            for (int i = 0; i < KW; i++) b[i] = __funnelshift_r(x[i], x[i + 1], sh);
+            if (KMAX % 4) b[KW - 1] &= (1u << (8 * (KMAX % 4))) - 1u;
+            h = murmur_words<KMAX>(b);
+        }
+        const bool keep = valid && h != 0 && h <= a.max_hash;
+        const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+        if (keep) {
+            const uint32_t slot = warp * (SK_ROWS * 32) + wcount + __popc(bal & ((1u << lane) - 1u));
+            s_hash[slot] = h;
+            s_loc[slot] = ((uint64_t)(a.pid_base + p) << 32) | (uint64_t)(uint32_t)(g - pstart);
+        }
+        wcount += __popc(bal);
+    }
+
+    if (lane == 0) s_wtot[warp] = wcount;
+    __syncthreads();
+    uint32_t wprefix = 0, btotal = 0;
+#pragma unroll
+    for (int i = 0; i < SK_THREADS / 32; i++) {
+        uint32_t t = s_wtot[i];
+        if (i < (int)warp) wprefix += t;
+        btotal += t;
+    }
+    if (warp == 0) {
+        uint64_t excl = scan_lookback(status, tile, btotal);
+        if (lane == 0) {
+            s_base = excl;
+            if (tile == n_tiles - 1) *a.d_count = excl + btotal;
+        }
+    }
+    __syncthreads();
+    const uint64_t base = s_base + wprefix;
+    const uint32_t sbase = warp * (SK_ROWS * 32);
+    for (uint32_t i = lane; i < wcount; i += 32) {
+        if (base + i < a.capacity) {
+            a.out_hash[base + i] = s_hash[sbase + i];
+            a.out_loc[base + i] = s_loc[sbase + i];
+        }
+    }
+}
+
+template <int K>
+cudaError_t launch_k(const SketchArgs& a, const Lut256& lut, const Workspace& w, uint64_t n_tiles, cudaStream_t st) {
+    if (a.moltype == 0)
+        sketch_kernel<K, false><<<(unsigned)n_tiles, SK_THREADS, 0, st>>>(a, lut, w.ticket, w.status, w.tile_pid);
+    else
+        sketch_kernel<K, true><<<(unsigned)n_tiles, SK_THREADS, 0, st>>>(a, lut, w.ticket, w.status, w.tile_pid);
+    return cudaGetLastError();
+}
+
+template <int K>
+struct Dispatch {
+    static cudaError_t run(const SketchArgs& a, const Lut256& lut, const Workspace& w, uint64_t nt, cudaStream_t st) {
+        if (a.k == (uint32_t)K) return launch_k<K>(a, lut, w, nt, st);
+        return Dispatch<K - 1>::run(a, lut, w, nt, st);
+    }
+};
+template <>
+struct Dispatch<0> {
+    static cudaError_t run(const SketchArgs& a, const Lut256& lut, const Workspace& w, uint64_t nt, cudaStream_t st) {
+        return launch_k<0>(a, lut, w, nt, st);
+    }
+};
+
+}  // namespace
+
+void fill_lut(int moltype, Lut256* lut) {
+    for (int i = 0; i < 256; i++) {
+        uint8_t c = (uint8_t)i, o = c;
+        if (moltype == 1) {
+            switch (c) {
+                case '*': o = '*'; break;
+                case 'C': o = 'a'; break;
+                case 'A': case 'G': case 'P': case 'S': case 'T': o = 'b'; break;
+                case 'D': case 'E': case 'N': case 'Q': o = 'c'; break;
+                case 'H': case 'K': case 'R': o = 'd'; break;
+                case 'I': case 'L': case 'M': case 'V': o = 'e'; break;
+                case 'F': case 'W': case 'Y': o = 'f'; break;
+                default: o = 'X';
+            }
+        } else if (moltype == 2) {
+            switch (c) {
+                case '*': o = '*'; break;
+                case 'A': case 'F': case 'G': case 'I': case 'L': case 'M': case 'P': case 'V': case 'W': case 'Y':
+                    o = 'h'; break;
+                case 'C': case 'D': case 'E': case 'H': case 'K': case 'N': case 'Q': case 'R': case 'S': case 'T':
+                    o = 'p'; break;
+                default: o = 'X';
+            }
+        }
+        lut->b[i] = o;
+    }
+}
+
+size_t sketch_workspace_bytes(uint64_t n_res) {
+    uint64_t nt = n_tiles_of(n_res);
+    return 16 + nt * 8 + (nt + 1) * 4 + 16;
+}
+
+cudaError_t launch_sketch(const SketchArgs& a, cudaStream_t stream, uint64_t* n_launches) {
+    if (a.n_res == 0 || a.n_prot == 0) return cudaMemsetAsync(a.d_count, 0, 8, stream);
+    const uint64_t nt = n_tiles_of(a.n_res);
+    Workspace w = carve(a.workspace, a.n_res);
+    cudaError_t e = cudaMemsetAsync(a.workspace, 0, 16 + nt * 8, stream);
+    if (e != cudaSuccess) return e;
+    tile_pid_kernel<<<(unsigned)((nt + 1 + 255) / 256), 256, 0, stream>>>(a.offsets, a.n_prot, nt, w.tile_pid);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    Lut256 lut;
+    fill_lut(a.moltype, &lut);
+    e = Dispatch<SK_MAX_TEMPLATE_K>::run(a, lut, w, nt, stream);
+    if (n_launches) *n_launches += 2;
+    return e;
+}
+
+}  // namespace ks

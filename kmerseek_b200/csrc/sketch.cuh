@@ -1,0 +1,37 @@
+// Fused sketch stage: internal interface between the C ABI (api.cu) and the kernels (sketch.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ks {
+
+constexpr int SK_THREADS = 256;
+constexpr int SK_ROWS = 8;                         // windows per thread
+constexpr int SK_TILE = SK_THREADS * SK_ROWS;      // window start positions per CTA
+constexpr int SK_MAX_TEMPLATE_K = 32;              // k above this takes the generic (byte-loop) kernel
+constexpr int SK_MAX_K = 256;                      // bound of the generic kernel's halo
+
+struct Lut256 { uint8_t b[256]; };
+
+struct SketchArgs {
+    const uint8_t* residues;   // device, n_res bytes followed by >= 64 readable pad bytes, 16 B aligned
+    const uint64_t* offsets;   // device, n_prot + 1
+    uint64_t n_res;
+    uint64_t n_prot;
+    uint32_t k;
+    int moltype;               // 0 protein (identity), 1 dayhoff, 2 hp
+    uint64_t max_hash;
+    uint32_t pid_base;         // added to the local protein index in the emitted tuples
+    uint64_t* out_hash;        // device, capacity entries (already offset to the append position)
+    uint64_t* out_loc;         // (pid << 32) | pos
+    uint64_t capacity;
+    uint64_t* d_count;         // device: tuples kept by this launch (may exceed capacity: nothing is written past it)
+    void* workspace;           // sketch_workspace_bytes(n_res)
+};
+
+size_t sketch_workspace_bytes(uint64_t n_res);
+// Enqueues memset + tile->protein map + the fused kernel on `stream`; adds the number of kernels launched.
+cudaError_t launch_sketch(const SketchArgs& a, cudaStream_t stream, uint64_t* n_launches);
+void fill_lut(int moltype, Lut256* lut);
+
+}  // namespace ks

@@ -1,0 +1,131 @@
+"""Search over a GPU-resident ProteomeIndex: the host side of ks_search_batch.
+
+Mirrors what `kmerseek search` computes (src/python/kmerseek/search.py:125-141 -> branchwater manysearch,
+:198-240 -> k-mer join and stitching) with the reference's column names (tests/test_search.py:33).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _ffi
+from .errors import check
+from .index import Proteome, ProteomeIndex, _np, md5_of_mins, translate
+
+MANYSEARCH_COLUMNS = [
+    "query_name", "query_md5", "match_name", "containment", "intersect_hashes", "ksize", "scaled", "moltype",
+    "match_md5", "jaccard", "max_containment", "average_abund", "median_abund", "std_abund",
+    "query_containment_ani", "match_containment_ani", "average_containment_ani", "max_containment_ani",
+    "n_weighted_found", "total_weighted_hashes", "containment_target_in_query", "f_weighted_target_in_query",
+]
+
+PAIR_INT_COLUMNS = {"pair_qid": np.uint32, "pair_pid": np.uint32, "intersect_hashes": np.uint32, "q_size": np.uint32,
+                    "t_size": np.uint32, "n_weighted_found": np.uint64, "total_weighted_hashes": np.uint64}
+HIT_COLUMNS = {"hit_qid": np.uint32, "hit_pid": np.uint32, "hit_qpos": np.uint32, "hit_tpos": np.uint32,
+               "hit_hash": np.uint64}
+
+
+class SearchResult:
+    """Host copy of a ks_search_result: `pairs` (dict of columns, ordered by (query, target)), `hits`
+    (dict of columns, ordered by (query, qpos, target, tpos)), `query_sketches` [(mins, abunds)]."""
+
+    def __init__(self, pairs, hits, query_sketches, ms_device):
+        self.pairs, self.hits, self.query_sketches, self.ms_device = pairs, hits, query_sketches, ms_device
+
+    @property
+    def n_pairs(self):
+        return len(self.pairs["pair_qid"])
+
+    @property
+    def n_hits(self):
+        return len(self.hits["hit_qid"]) if self.hits else 0
+
+
+def _collect(r, want_hits):
+    np_, nh, nq = r.n_pairs, r.n_hits, r.n_queries
+    pairs = {n: _np(getattr(r, n), np_, dt) for n, dt in PAIR_INT_COLUMNS.items()}
+    for n in _ffi.SCORE_COLUMNS:
+        pairs[n] = _np(getattr(r, n), np_, np.float64)
+    hits = {n: _np(getattr(r, n), nh, dt) for n, dt in HIT_COLUMNS.items()} if want_hits else None
+    sig_ptr = _np(r.q_sig_ptr, nq + 1, np.uint64)
+    E = int(sig_ptr[-1]) if nq else 0
+    qm, qa = _np(r.q_mins, E, np.uint64), _np(r.q_abunds, E, np.uint64)
+    qs = [(qm[int(sig_ptr[i]):int(sig_ptr[i + 1])], qa[int(sig_ptr[i]):int(sig_ptr[i + 1])]) for i in range(nq)]
+    return SearchResult(pairs, hits, qs, r.ms_device)
+
+
+def search(index: ProteomeIndex, queries: Proteome, hits=True) -> SearchResult:
+    """One batched search of `queries` against a finalized index (ks_search_batch)."""
+    index.finalize()
+    flags = _ffi.KS_SEARCH_HITS if hits else 0
+    out = C.POINTER(_ffi.ks_search_result)()
+    check(_ffi.lib().ks_search_batch(index._h, queries._h, flags, C.byref(out)))
+    try:
+        return _collect(out.contents, hits)
+    finally:
+        _ffi.lib().ks_search_result_free(out)
+
+
+def manysearch_rows(result: SearchResult, index: ProteomeIndex, query_names, target_names=None, target_sketches=None):
+    """The 22-column manysearch table (tests/test_search.py:33) as a list of dicts."""
+    target_names = target_names if target_names is not None else index.names()
+    if target_sketches is None:
+        target_sketches = index.export_sketches()
+    p = result.pairs
+    rows = []
+    qmd5 = {}
+    for j in range(result.n_pairs):
+        q, t = int(p["pair_qid"][j]), int(p["pair_pid"][j])
+        if q not in qmd5:
+            qmd5[q] = md5_of_mins(result.query_sketches[q][0], index.ksize)
+        row = {
+            "query_name": query_names[q], "query_md5": qmd5[q], "match_name": target_names[t],
+            "intersect_hashes": int(p["intersect_hashes"][j]), "ksize": 3 * index.ksize, "scaled": index.scaled,
+            "moltype": index.moltype, "match_md5": md5_of_mins(target_sketches[t][0], index.ksize),
+            "n_weighted_found": int(p["n_weighted_found"][j]), "total_weighted_hashes": int(p["total_weighted_hashes"][j]),
+        }
+        for c in _ffi.SCORE_COLUMNS:
+            row[c] = float(p[c][j])
+        rows.append({c: row[c] for c in MANYSEARCH_COLUMNS})
+    return rows
+
+
+def _stitch(kmers, starts):
+    # single_stitch_together_kmers, src/python/kmerseek/search.py:37-61
+    out, prev = "", 0
+    for i, (s, km) in enumerate(zip(starts, kmers)):
+        if i == 0:
+            out = km
+        else:
+            d = s - prev
+            out += km[-d:] if d != 0 else km
+        prev = s
+    return out
+
+
+def stitch_hits(result: SearchResult, index: ProteomeIndex, query_seqs, target_seqs, query_names, target_names):
+    """Per (query, match) pair, the stitched region table of `kmerseek search --extract-kmers`
+    (src/python/kmerseek/search.py:64-121), quirks included.  SURVEY section 8f row N4."""
+    h = result.hits
+    k = index.ksize
+    groups = {}
+    for i in range(result.n_hits):
+        q, t = int(h["hit_qid"][i]), int(h["hit_pid"][i])
+        a, b = int(h["hit_qpos"][i]), int(h["hit_tpos"][i])
+        groups.setdefault((q, t), []).append((a, b))
+    out = []
+    for (q, t), lst in groups.items():
+        lst.sort(key=lambda r: r[0])
+        qk = [query_seqs[q][a:a + k] for a, _ in lst]
+        tk = [target_seqs[t][b:b + k] for _, b in lst]
+        ek = [translate(x, index.moltype) for x in qk]
+        qs_, ts_ = [a for a, _ in lst], [b for _, b in lst]
+        query = _stitch(qk, ts_)  # the reference stitches the query with the match starts (search.py:78)
+        alpha = _stitch(ek, qs_)
+        match = _stitch(tk, ts_)
+        if not (len(query) == len(alpha) == len(match)):
+            raise AssertionError("stitched lengths differ (the reference asserts the same, search.py:87-88)")
+        out.append({"match_name": target_names[t], "query_name": query_names[q], "query_start": min(qs_),
+                    "query_end": min(qs_) + len(query), "query": query, "match_start": min(ts_),
+                    "match_end": min(ts_) + len(query), "match": match, "encoded": alpha, "length": len(query)})
+    out.sort(key=lambda r: (r["query_start"], r["query_end"]))
+    return out

@@ -1,0 +1,324 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle and the reference's golden vectors.
+Bit-exact for hashes, retained k-mers, positions, postings and hit lists; scores within 1e-6 relative
+(the tolerance BASELINE.json's north_star states).  Needs a GPU: run with -m gpu."""
+import csv
+import io
+
+import numpy as np
+import pytest
+
+from conftest import fasta_path
+
+pytestmark = pytest.mark.gpu
+
+SCORE_RTOL = 1e-6  # north_star: "floating-point scores within 1e-6 relative"
+
+
+@pytest.fixture(scope="module")
+def K():
+    import kmerseek_b200
+    return kmerseek_b200
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import oracle
+    return oracle
+
+
+def _oracle_tuples(O, prot, k, moltype, scaled):
+    return O.sketch_tuples(prot.residues, prot.offsets, k, moltype, scaled)
+
+
+def _gpu_tuples(K, prot, k, moltype, scaled):
+    """(hash, pid, pos) in (pid, pos) order + per-protein sketches, via ks_sketch_batch."""
+    import ctypes as C
+    from kmerseek_b200 import _ffi
+    from kmerseek_b200.errors import check
+    from kmerseek_b200.index import _np
+    with K.ProteomeIndex("t", k, scaled, moltype) as idx:
+        out = C.POINTER(_ffi.ks_sketch)()
+        check(_ffi.lib().ks_sketch_batch(idx._h, prot._h, C.byref(out)))
+        s = out.contents
+        n, P = s.n_tuples, s.n_proteins
+        h, pid, pos = _np(s.hash, n, np.uint64), _np(s.pid, n, np.uint32), _np(s.pos, n, np.uint32)
+        sp = _np(s.sig_ptr, P + 1, np.uint64)
+        E = int(sp[-1]) if P else 0
+        mins, ab = _np(s.mins, E, np.uint64), _np(s.abunds, E, np.uint64)
+        _ffi.lib().ks_sketch_free(out)
+    return h, pid, pos, [(mins[int(sp[i]):int(sp[i + 1])], ab[int(sp[i]):int(sp[i + 1])]) for i in range(P)]
+
+
+# ---- golden vectors of the reference -------------------------------------------------------------
+@pytest.mark.parametrize("moltype", ["protein", "dayhoff", "hp"])
+def test_golden_kmer_infos(K, golden_rust, moltype):
+    g = golden_rust["kmer_tables"][moltype]  # src/rust/index.rs:1084-1103,1187-1205,1309-1326
+    with K.ProteomeIndex("t", g["ksize"], g["scaled"], moltype) as idx:
+        sig = idx.create_protein_signature(g["sequence"], "test_protein")
+        infos = sig.kmer_infos()
+        assert len(infos) == len(g["rows"])
+        for row in g["rows"]:
+            ki = infos[int(row["hash"])]
+            if row["encoded"] is not None:
+                assert ki.encoded_kmer == row["encoded"]
+            assert set(ki.original_kmer_to_position) == set(row["originals"])
+            assert sorted(p for v in ki.original_kmer_to_position.values() for p in v) == sorted(row["positions"])
+        idx.store_signatures([sig])  # src/rust/index.rs:1414-1441
+        assert idx.signature_count() == 1
+        assert idx.combined_minhash_size() == len(g["rows"])
+
+
+@pytest.mark.parametrize("moltype", ["protein", "dayhoff", "hp"])
+def test_golden_two_record_fasta(K, golden_rust, moltype, tmp_path):
+    g = golden_rust["index_tests"][f"test_process_fasta_moltype_{moltype}"]
+    f = tmp_path / "test.fasta"
+    f.write_text(golden_rust["fixtures"]["TEST_FASTA_CONTENT"])
+    with K.ProteomeIndex(tmp_path / "db", g["ksize"], g["scaled"], moltype) as idx:
+        idx.process_fasta(f, 0, 1000)
+        sigs = idx.get_signatures()
+        assert len(sigs) == g["n_signatures"]
+        for i, n in g["ids"].items():
+            assert len(sigs[i][1]) == n
+        assert idx.combined_minhash_size() == g["combined_size"]
+
+
+@pytest.mark.parametrize("test", ["test_process_fasta_gz_moltype_protein", "test_process_fasta_gz_moltype_dayhoff",
+                                  "test_process_fasta_gz_moltype_hp", "test_manual_vs_auto_index_equivalence"])
+def test_golden_bcl2_first25(K, golden_rust, test):
+    g = golden_rust["index_tests"][test]  # src/rust/index.rs:1812-1843,1871-1902,1937-1968,2403-2418
+    with K.ProteomeIndex("db", g["ksize"], g["scaled"], g["moltype"]) as idx:
+        idx.process_fasta(fasta_path("bcl2_first25.fasta.gz"), 0, 1000)
+        sigs = idx.get_signatures()
+        assert len(sigs) == 25 and idx.signature_count() == 25
+        for i, n in g["ids"].items():
+            assert len(sigs[i][1]) == n
+        assert idx.combined_minhash_size() == g["combined_size"]
+        st = idx.stats()
+        assert st["n_proteins"] == 25 and st["n_residues"] == 9288
+
+
+@pytest.mark.parametrize("key,k", [("hp.k16.scaled5", 16), ("hp.k15.scaled5", 15), ("hp.k24.scaled5", 24)])
+def test_golden_sig_zip_and_kmers(K, golden_sigs, golden_kmers, key, k):
+    prot = K.Proteome.from_fasta(fasta_path("bcl2_first25.fasta.gz"))
+    names = prot.names
+    h, pid, pos, sk = _gpu_tuples(K, prot, k, "hp", 5)
+    by_name = dict(zip(names, sk))
+    for g in golden_sigs[key]["signatures"]:
+        mins, ab = by_name[g["name"]]
+        assert [int(x) for x in g["mins"]] == mins.tolist()
+        assert g["abundances"] == ab.tolist()
+        assert g["md5sum"] == K.md5_of_mins(mins, k)
+        assert int(g["max_hash"]) == K.max_hash(5)
+    seqs = [prot.sequence(i) for i in range(prot.n_proteins)]
+    mine = set()
+    for hv, p, s in zip(h.tolist(), pid.tolist(), pos.tolist()):
+        km = seqs[p][s:s + k]
+        mine.add((names[p], s, hv if hv < 2**63 else hv - 2**64, km, K.translate(km, "hp")))
+    gold = {(r["name"], r["start"], int(r["hashval"]), r["kmer"], r["encoded"]) for r in golden_kmers[key]}
+    assert gold == mine
+
+
+def _ced9_vs_bcl2(K):
+    q = K.Proteome.from_fasta(fasta_path("ced9.fasta"))
+    t = K.Proteome.from_fasta(fasta_path("bcl2_first25.fasta.gz"))
+    idx = K.ProteomeIndex("db", 16, 5, "hp")
+    idx.add_proteome(t)
+    res = K.search(idx, q, hits=True)
+    return idx, q, t, res
+
+
+def test_golden_manysearch(K, golden_search):
+    idx, q, t, res = _ced9_vs_bcl2(K)
+    rows = K.manysearch_rows(res, idx, q.names)
+    gold = list(csv.DictReader(io.StringIO(golden_search["manysearch_csv"])))  # tests/test_search.py:33-39
+    assert len(rows) == len(gold) == 5
+    by = {r["match_name"]: r for r in rows}
+    for g in gold:
+        r = by[g["match_name"]]
+        for col, v in r.items():
+            if isinstance(v, float):
+                assert v == pytest.approx(float(g[col]), rel=SCORE_RTOL, abs=0), col
+            else:
+                assert str(v) == g[col], col
+    idx.close()
+
+
+def test_golden_stitched(K, golden_search):
+    idx, q, t, res = _ced9_vs_bcl2(K)
+    qs = [q.sequence(i) for i in range(q.n_proteins)]
+    ts = [t.sequence(i) for i in range(t.n_proteins)]
+    rows = K.stitch_hits(res, idx, qs, ts, q.names, t.names)
+    gold = list(csv.DictReader(io.StringIO(golden_search["stitched_csv"])))  # tests/test_search.py:88-94
+    assert len(rows) == len(gold) == 5
+    by = {r["match_name"]: r for r in rows}
+    for g in gold:
+        for col, v in by[g["match_name"]].items():
+            assert str(v) == g[col], col
+    idx.close()
+
+
+def test_invalid_residue_and_moltype_errors(K, golden_rust):
+    with K.ProteomeIndex("db", 5, 1, "protein") as idx:
+        for e in golden_rust["errors"]:  # src/rust/index.rs:2031-2046
+            with pytest.raises(K.InvalidAminoAcid) as ei:
+                idx.create_protein_signature(e["sequence"], "test_protein")
+            assert e["message"] in str(ei.value)
+        for seq in ["PLANTANDANIMALGENBMES", "PLANTANDANIMALGENZMES", "PLANTANDANIMALGENJMES"]:
+            assert idx.create_protein_signature(seq, "p").size() == 17  # resolved, not rejected (index.rs:2052-2075)
+    with pytest.raises(K.InvalidMoltype):
+        K.ProteomeIndex("db", 5, 1, "dna")
+
+
+# ---- against the oracle on seeded synthetic inputs -----------------------------------------------------
+def _edge_proteome(K, seed, n_res=300_000):
+    """Synthetic proteome with the awkward cases mixed in: empty and shorter-than-k proteins, a protein much
+    longer than a tile, runs of tiny proteins (more boundaries than the kernel's offsets cache), X/U/O/*,
+    lower case, low-complexity repeats (duplicate hashes)."""
+    from kmerseek_b200 import synth
+    rng = np.random.default_rng(seed)
+    res, offs = synth.proteome(n_res, seed)
+    seqs = [res[int(offs[i]):int(offs[i + 1])].tobytes().decode() for i in range(len(offs) - 1)]
+    seqs[3] = ""
+    seqs[4] = "AC"
+    seqs[5] = seqs[5].lower()
+    seqs[6] = seqs[6][:40] + "XUO" + seqs[6][40:80] + "*" + seqs[6][80:]
+    seqs[7] = "A" * 700 + "ACDEFGHIKL" * 50
+    seqs[8] = "".join(rng.choice(list("ACDEFGHIKLMNPQRSTVWY"), size=9000))
+    tiny = ["".join(rng.choice(list("ACDEFGHIKLMNPQRSTVWY"), size=int(n))) for n in rng.integers(0, 6, size=900)]
+    seqs = seqs[:20] + tiny + seqs[20:] + ["", "M", ""]
+    return K.Proteome.from_sequences(seqs, [f"p{i}" for i in range(len(seqs))]), seqs
+
+
+SWEEP = [(k, m, 1) for k in (1, 2, 5, 7, 8, 9, 12, 15, 16, 17, 21, 24, 25, 31, 32, 33, 40) for m in ("protein", "dayhoff", "hp")]
+SWEEP += [(7, "protein", 10), (16, "dayhoff", 5), (24, "hp", 100), (10, "hp", 2), (5, "protein", 1000)]
+
+
+@pytest.mark.parametrize("k,moltype,scaled", SWEEP)
+def test_sketch_tuples_bit_exact(K, O, k, moltype, scaled):
+    prot, _ = _edge_proteome(K, 1234, 120_000)
+    h, pid, pos, sk = _gpu_tuples(K, prot, k, moltype, scaled)
+    oh, opid, opos = _oracle_tuples(O, prot, k, moltype, scaled)
+    assert len(h) == len(oh)
+    assert np.array_equal(h, oh) and np.array_equal(pid, opid) and np.array_equal(pos, opos)
+    osk = O.protein_sketches(oh, opid, prot.n_proteins)
+    assert len(sk) == len(osk)
+    for (m, a), (om, oa) in zip(sk, osk):
+        assert np.array_equal(m, om) and np.array_equal(a, oa)
+
+
+@pytest.mark.parametrize("k,moltype,scaled", [(5, "protein", 1), (16, "dayhoff", 1), (24, "hp", 1), (7, "protein", 10),
+                                              (12, "hp", 5)])
+def test_index_csr_and_search_bit_exact(K, O, k, moltype, scaled):
+    from kmerseek_b200 import synth
+    prot, seqs = _edge_proteome(K, 99, 400_000)
+    res, offs = prot.residues, prot.offsets
+    qres, qoffs, _ = synth.queries(res, offs, 64, 7, min_len=max(30, k + 3), max_len=200)
+    queries = K.Proteome.from_packed(qres, qoffs)
+    with K.ProteomeIndex("db", k, scaled, moltype) as idx:
+        idx.add_proteome(prot)
+        idx.finalize()
+        keys, row_ptr, pid, pos = idx.csr()
+        oh, opid, opos = _oracle_tuples(O, prot, k, moltype, scaled)
+        okeys, orow, ops, oqs = O.build_index(oh, opid, opos)
+        assert np.array_equal(keys, okeys) and np.array_equal(row_ptr, orow)
+        assert np.array_equal(pid, ops) and np.array_equal(pos, oqs)
+        st = idx.stats()
+        assert st["n_tuples"] == len(oh) and st["n_unique_hashes"] == len(okeys)
+        osk = O.protein_sketches(oh, opid, prot.n_proteins)
+        assert st["n_groups"] == sum(len(m) for m, _ in osk)
+        sk = idx.export_sketches()
+        for (m, a), (om, oa) in zip(sk, osk):
+            assert np.array_equal(m, om) and np.array_equal(a, oa)
+        cm, ca = idx.get_combined_minhash()
+        ocm, oca = O.combined_sketch(osk)
+        assert np.array_equal(cm, ocm) and np.array_equal(ca, oca)
+
+        r = K.search(idx, queries, hits=True)
+        qh, qid, qpos = O.sketch_tuples(qres, qoffs, k, moltype, scaled)
+        ohits = O.hits(qh, qid, qpos, oh, opid, opos)
+        hh = r.hits
+        mine = list(zip(hh["hit_qid"].tolist(), hh["hit_pid"].tolist(), hh["hit_hash"].tolist(),
+                        hh["hit_qpos"].tolist(), hh["hit_tpos"].tolist()))
+        assert mine == ohits  # same rows, same (query, qpos, target, tpos) order
+        assert len(mine) > 0
+
+        qsk = O.protein_sketches(qh, qid, queries.n_proteins)
+        for (m, a), (om, oa) in zip(r.query_sketches, qsk):
+            assert np.array_equal(m, om) and np.array_equal(a, oa)
+        orows = O.manysearch(qsk, osk, k, scaled, moltype)
+        p = r.pairs
+        assert r.n_pairs == len(orows)
+        for j, o in enumerate(orows):
+            assert (int(p["pair_qid"][j]), int(p["pair_pid"][j])) == (o["qid"], o["pid"])
+            assert int(p["intersect_hashes"][j]) == o["intersect_hashes"]
+            assert int(p["n_weighted_found"][j]) == o["n_weighted_found"]
+            assert int(p["total_weighted_hashes"][j]) == o["total_weighted_hashes"]
+            for c in ("containment", "containment_target_in_query", "max_containment", "jaccard",
+                      "query_containment_ani", "match_containment_ani", "average_containment_ani",
+                      "max_containment_ani", "average_abund", "median_abund", "std_abund",
+                      "f_weighted_target_in_query"):
+                assert float(p[c][j]) == pytest.approx(o[c], rel=SCORE_RTOL, abs=1e-12), (c, j)
+
+
+def test_empty_and_degenerate_inputs(K, O):
+    with K.ProteomeIndex("db", 7, 1, "dayhoff") as idx:
+        idx.add_proteome(K.Proteome.from_sequences([], []))
+        idx.finalize()
+        assert idx.stats()["n_tuples"] == 0 and idx.combined_minhash_size() == 0
+    with K.ProteomeIndex("db", 7, 1, "dayhoff") as idx:
+        prot = K.Proteome.from_sequences(["", "ACD", "ACDEFG"], ["a", "b", "c"])
+        idx.add_proteome(prot)
+        idx.finalize()
+        assert idx.stats()["n_tuples"] == 0
+        r = K.search(idx, K.Proteome.from_sequences(["ACDEFGHIKLMN"], ["q"]))
+        assert r.n_pairs == 0 and r.n_hits == 0
+    with K.ProteomeIndex("db", 7, 1, "dayhoff") as idx:
+        prot = K.Proteome.from_sequences(["ACDEFGHIKLMNPQRSTVWY" * 3], ["a"])
+        idx.add_proteome(prot)
+        r = K.search(idx, K.Proteome.from_sequences(["", "AC", "WWWWWWWWWWWW"], ["q0", "q1", "q2"]))
+        assert r.n_pairs == 0
+
+
+def test_tile_boundary_sizes(K, O):
+    # residue counts exactly at, one below and one above the kernel tile (2048 window starts)
+    rng = np.random.default_rng(3)
+    for n in (2047, 2048, 2049, 4096, 4096 + 23):
+        seq = "".join(rng.choice(list("ACDEFGHIKLMNPQRSTVWY"), size=n))
+        prot = K.Proteome.from_sequences([seq[:1000], seq[1000:]], ["a", "b"])
+        h, pid, pos, _ = _gpu_tuples(K, prot, 24, "hp", 1)
+        oh, opid, opos = _oracle_tuples(O, prot, 24, "hp", 1)
+        assert np.array_equal(h, oh) and np.array_equal(pid, opid) and np.array_equal(pos, opos)
+
+
+def test_batches_append_and_store_signatures(K, O):
+    prot, seqs = _edge_proteome(K, 5, 60_000)
+    half = len(seqs) // 2
+    a = K.Proteome.from_sequences(seqs[:half], [f"p{i}" for i in range(half)])
+    b = K.Proteome.from_sequences(seqs[half:], [f"p{i}" for i in range(half, len(seqs))])
+    with K.ProteomeIndex("one", 9, 1, "dayhoff") as one, K.ProteomeIndex("two", 9, 1, "dayhoff") as two, \
+            K.ProteomeIndex("three", 9, 1, "dayhoff") as three:
+        one.add_proteome(prot)
+        two.add_proteome(a)
+        two.add_proteome(b)
+        sigs = three.create_protein_signatures(seqs[:50], [f"p{i}" for i in range(50)])
+        three.store_signatures(sigs)
+        three.store_signatures(three.create_protein_signatures(seqs[50:], [f"p{i}" for i in range(50, len(seqs))]))
+        c1, c2, c3 = one.csr(), two.csr(), three.csr()
+        for x, y, z in zip(c1, c2, c3):
+            assert np.array_equal(x, y) and np.array_equal(x, z)
+        assert one.is_equivalent_to(two) and one.is_equivalent_to(three)
+
+
+def test_medium_scale_against_oracle(K, O):
+    """20 M residues, the C2 alphabet/k: tuples are compared through order-sensitive checksums, the CSR fully."""
+    from kmerseek_b200 import synth
+    res, offs = synth.proteome(20_000_000, 20260102)
+    prot = K.Proteome.from_packed(res, offs)
+    with K.ProteomeIndex("db", 24, 1, "hp") as idx:
+        idx.add_proteome(prot)
+        idx.finalize()
+        keys, row_ptr, pid, pos = idx.csr()
+        oh, opid, opos = O.sketch_tuples(res, offs, 24, "hp", 1)
+        okeys, orow, ops, oqs = O.build_index(oh, opid, opos)
+        assert np.array_equal(keys, okeys) and np.array_equal(row_ptr, orow)
+        assert np.array_equal(pid, ops) and np.array_equal(pos, oqs)

@@ -1,0 +1,175 @@
+"""CPU-only tests: the C-ABI library loads and exports every declared symbol, and the host-side logic
+(normalisation, FASTA ingest, md5/id strings, builder and error conventions) matches the oracle and the
+reference's conventions.  No compute entry point is called here (there is no GPU in this container)."""
+import gzip
+import hashlib
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, fasta_path, has_gpu
+import kmerseek_b200 as K
+from kmerseek_b200 import _ffi, synth
+from oracle import oracle as O
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "kmerseek_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(ks_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 40
+    L = _ffi.lib()
+    for name in declared:
+        assert hasattr(L, name), f"{name} is declared in the header but not exported"
+    assert declared == set(_ffi.SIGNATURES), declared ^ set(_ffi.SIGNATURES)
+    assert L.ks_abi_version() == 1
+
+
+def test_scalars_match_oracle():
+    for s in (0, 1, 2, 5, 10, 100, 1000, 7, 3, 4096):
+        assert K.max_hash(s) == O.max_hash(s)
+    L = _ffi.lib()
+    for m, name in ((0, "protein"), (1, "dayhoff"), (2, "hp")):
+        for c in range(256):
+            assert L.ks_translate_residue(c, m) == O.lib().kso_translate(c, O.MOLTYPES[name])
+    assert K.translate("LIVINGALIVE", "dayhoff") == "eeeecbbeeec"  # src/rust/encoding.rs:195
+    assert K.translate("LIVINGALIVE", "hp") == "hhhhphhhhhp"  # src/rust/encoding.rs:209
+    assert K.translate("AX*UOB", "hp") == "hX*XXX" and K.translate("AX*", "protein") == "AX*"
+
+
+def test_md5_and_id_strings(golden_sigs):
+    rng = np.random.default_rng(0)
+    for n in (0, 1, 5, 100, 1000):
+        mins = np.sort(rng.integers(0, 2**63, size=n, dtype=np.uint64))
+        for k in (5, 16, 24):
+            m = hashlib.md5(str(3 * k).encode() + b"".join(str(int(x)).encode() for x in mins)).hexdigest()
+            assert K.md5_of_mins(mins, k) == m == O.md5sum(mins, k)
+        assert K.id_of_mins(mins) == O.signature_id(mins)
+    g = golden_sigs["hp.k16.scaled5"]["signatures"][0]
+    assert K.md5_of_mins(np.array([int(x) for x in g["mins"]], dtype=np.uint64), 16) == g["md5sum"]
+    assert K.id_of_mins(np.array([2**63, 2**63, 5], dtype=np.uint64)) == "5"
+    assert K.id_of_mins(np.zeros(0, dtype=np.uint64)) == "0"
+
+
+def test_normalisation_matches_oracle():
+    rng = np.random.default_rng(7)
+    alphabet = list("ACDEFGHIKLMNPQRSTVWYXUOBZJacdefghiklmnpqrstvwyxuobzj*")
+    seqs = ["".join(rng.choice(alphabet, size=int(n))) for n in rng.integers(0, 120, size=300)]
+    for seed in (0, 12345):
+        p = K.Proteome.from_sequences(seqs, None, ambig_seed=seed)
+        for i, s in enumerate(seqs):
+            assert p.sequence(i) == O.normalize(s, i, seed)
+        assert p.n_residues == sum(len(O.normalize(s, i, seed)) for i, s in enumerate(seqs))
+        assert p.offsets[0] == 0 and p.offsets[-1] == p.n_residues
+
+
+def test_invalid_residue_error_convention(golden_rust):
+    for e in golden_rust["errors"]:  # src/rust/index.rs:2031-2046
+        with pytest.raises(K.InvalidAminoAcid) as ei:
+            K.Proteome.from_sequences(["ACDEF", e["sequence"]])
+        assert e["message"] in str(ei.value)
+        assert str(ei.value) == f"Invalid amino acid '{e['sequence'][17]}' found at position 18"
+        assert (ei.value.pos, ei.value.protein_index) == (18, 1)
+    with pytest.raises(K.InvalidAminoAcid) as ei:
+        K.Proteome.from_sequences(["acd1"])
+    assert ei.value.char == "1" and ei.value.pos == 4
+    # '*' ends the sequence before the bad character is ever looked at (src/rust/aminoacid.rs:79-83)
+    assert K.Proteome.from_sequences(["ACD*1"]).sequence(0) == "ACD*"
+
+
+def test_fasta_ingest_matches_oracle(tmp_path):
+    for name in ("bcl2_first25.fasta.gz", "ced9.fasta", "test_compression.fasta", "test_mixed_case.fasta",
+                 "bcl2_all300.fasta.gz"):
+        p = K.Proteome.from_fasta(fasta_path(name))
+        names, seqs = O.read_fasta(fasta_path(name))
+        assert p.names == names
+        for i, s in enumerate(seqs):
+            assert p.sequence(i) == O.normalize(s, i)
+    p = K.Proteome.from_fasta(fasta_path("bcl2_first25.fasta.gz"))
+    assert (p.n_proteins, p.n_residues) == (25, 9288)  # SURVEY section 4 fixtures
+    f = tmp_path / "crlf.fasta"
+    f.write_bytes(b">a b c\r\nACDE\r\nFGH\r\n\r\n>second\r\n>third\r\nKLMN")
+    p = K.Proteome.from_fasta(f)
+    assert p.names == ["a b c", "second", "third"]
+    assert [p.sequence(i) for i in range(3)] == ["ACDEFGH", "", "KLMN"]
+    g = tmp_path / "x.fasta.gz"
+    with gzip.open(g, "wb") as fh:
+        fh.write(b">p1\nPLANTANDANIMALGENQMES\n>p2\nlivingalive\n")
+    p = K.Proteome.from_fasta(g)
+    assert [p.sequence(i) for i in range(2)] == ["PLANTANDANIMALGENQMES", "LIVINGALIVE"]
+
+
+def test_fasta_errors(tmp_path):
+    with pytest.raises(K.ParseError):
+        K.Proteome.from_fasta(tmp_path / "missing.fasta")
+    e = tmp_path / "empty.fasta"
+    e.write_bytes(b"")
+    with pytest.raises(K.ParseError):
+        K.Proteome.from_fasta(e)
+    b = tmp_path / "bad.fasta"
+    b.write_bytes(b"ACDEFG\n")
+    with pytest.raises(K.ParseError):
+        K.Proteome.from_fasta(b)
+    z = tmp_path / "z.fasta.zst"
+    z.write_bytes(b"\x28\xb5\x2f\xfd" + b"\0" * 16)
+    with pytest.raises(K.ParseError, match="zstd"):
+        K.Proteome.from_fasta(z)
+    bad = tmp_path / "bad_res.fasta"
+    bad.write_bytes(b">ok\nACDEF\n>bad\nPLANTANDANIMALGEN1MES\n")
+    with pytest.raises(K.InvalidAminoAcid, match="Invalid amino acid '1' found at position 18"):
+        K.Proteome.from_fasta(bad)  # src/rust/index.rs:2251-2282
+
+
+def test_packed_validation():
+    with pytest.raises(K.ValidationError):
+        K.Proteome.from_packed(np.zeros(4, np.uint8), np.array([1, 4], np.uint64))
+    with pytest.raises(K.ValidationError):
+        K.Proteome.from_packed(np.zeros(4, np.uint8), np.array([0, 3, 2], np.uint64))
+    p = K.Proteome.from_packed(np.frombuffer(b"ACDEFG", np.uint8), np.array([0, 2, 2, 6], np.uint64))
+    assert [p.sequence(i) for i in range(3)] == ["AC", "", "DEFG"] and p.names == ["", "", ""]
+
+
+def test_builder_and_moltype_conventions():
+    B = K.ProteomeIndex.builder
+    for fn, msg in [(lambda: B().ksize(5).scaled(1).moltype("hp").build(), "Database path is required"),
+                    (lambda: B().ksize(5).scaled(1).moltype("hp").build_with_auto_filename(), "Base path is required"),
+                    (lambda: B().path("x").scaled(1).moltype("hp").build(), "K-mer size is required"),
+                    (lambda: B().path("x").ksize(5).moltype("hp").build(), "Scaled value is required"),
+                    (lambda: B().path("x").ksize(5).scaled(1).build(), "Molecular type is required")]:
+        with pytest.raises(K.BuilderError) as ei:  # src/rust/index.rs:3021-3036
+            fn()
+        assert str(ei.value) == f"Builder error: {msg}"
+    with pytest.raises(K.InvalidMoltype) as ei:  # src/rust/encoding.rs:22-25
+        K.ProteomeIndex("x", 5, 1, "dna")
+    assert str(ei.value) == "Invalid moltype: dna, only 'protein', 'hp', or 'dayhoff' are supported"
+
+
+@pytest.mark.skipif(has_gpu(), reason="only meaningful without a device")
+def test_no_device_fails_loudly():
+    with pytest.raises(K.NoDevice, match="no CPU fallback"):
+        K.ProteomeIndex("x", 5, 1, "hp")
+    with pytest.raises(K.NoDevice):
+        K.ProteomeIndex.builder().path("x").ksize(5).scaled(1).moltype("raw").build()
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "kmerseek_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".hpp", ".h", ".cpp")):
+                src = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "oracle" not in src.lower(), f"{f} mentions the oracle"
+
+
+def test_synth_generator_is_deterministic_and_shaped():
+    r1, o1 = synth.proteome(200_000, 20260102)
+    r2, o2 = synth.proteome(200_000, 20260102)
+    assert np.array_equal(r1, r2) and np.array_equal(o1, o2)
+    assert o1[-1] == len(r1) == 200_000
+    lens = np.diff(o1.astype(np.int64))
+    assert lens.min() >= 30 and lens.max() <= 35000
+    assert set(np.unique(r1)) <= set(b"ACDEFGHIKLMNPQRSTVWY")
+    q, qo, src = synth.queries(r1, o1, 50, 78)
+    assert len(qo) == 51 and qo[-1] == len(q) and (np.diff(qo.astype(np.int64)) >= 30).all()
