@@ -5,6 +5,8 @@
 // serial sorted-Vec merge into combined_minhash (src/rust/index.rs:824-827).
 #include <cub/device/device_radix_sort.cuh>
 
+#include <vector>
+
 #include "common.cuh"
 #include "index_build.cuh"
 
@@ -134,22 +136,260 @@ __global__ void dir_kernel(const uint64_t* __restrict__ keys, const uint64_t* __
         for (uint32_t x = b + 1; x <= nb; x++) dir[x] = (uint32_t)U;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Bucket-local sort (the last pass of the MSD sort).
+//
+// After the tuples have been partitioned by the top `tb` bits of the normalised hash (normalised =
+// shifted left by the `lz` leading bits that are zero under max_hash), every bucket is a contiguous range
+// of a few thousand tuples.  One CTA sorts one bucket entirely in shared memory:
+//   item = (remaining key bits, left-aligned, low 12 bits replaced by the tuple's index in the bucket)
+// so that comparing items compares (hash, original order) exactly -- the sort is stable by construction.
+// Two stable 8-bit counting passes (warp-private digit counters, MATCH.ANY ranks) order the items by the
+// next 16 key bits; hashes are uniform, so what is left are isolated inversions between neighbours, which
+// an odd-even transposition loop removes in a handful of sweeps (it runs until a sweep swaps nothing, so
+// the result is exact for any input).  The hash is rebuilt from the item, loc is gathered from a staged
+// copy, and the bucket streams back to HBM in sorted order: one read and one write of every tuple.
+// ---------------------------------------------------------------------------------------------
+constexpr int LS_THREADS = 512;
+constexpr int LS_WARPS = LS_THREADS / 32;
+constexpr int LS_CAP = 4096;  // tuples per bucket that fit the shared-memory layout (12 index bits)
+constexpr size_t LS_SMEM = (size_t)LS_CAP * 8 * 3 + LS_WARPS * 256 * 2 + 256 * 4 + 64;
+
+__global__ void bucket_start_kernel(const uint64_t* __restrict__ hash, uint64_t n, int lz, int tb,
+                                    uint32_t* __restrict__ start, uint32_t* __restrict__ oversize) {
+    const uint32_t nb = 1u << tb;
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b > nb) return;
+    if (b == 0) oversize[0] = 0;
+    if (b == nb) { start[b] = (uint32_t)n; return; }
+    uint64_t lo = 0, hi = n;  // first i with bucket(hash[i]) >= b
+    while (lo < hi) {
+        uint64_t mid = (lo + hi) >> 1;
+        uint32_t bm = tb ? (uint32_t)((hash[mid] << lz) >> (64 - tb)) : 0u;
+        if (bm < b) lo = mid + 1; else hi = mid;
+    }
+    start[b] = (uint32_t)lo;
+}
+
+// Buckets too large for shared memory (only heavy repeats of one hash can do that) are listed for the
+// host, which sorts those ranges with the library radix sort.
+__global__ void oversize_list_kernel(const uint32_t* __restrict__ start, int tb, uint32_t* __restrict__ oversize,
+                                     uint32_t max_list) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= (1u << tb)) return;
+    if (start[b + 1] - start[b] > (uint32_t)LS_CAP) {
+        uint32_t slot = atomicAdd(&oversize[0], 1u);
+        if (slot < max_list) oversize[1 + slot] = b;
+    }
+}
+
+__global__ void __launch_bounds__(LS_THREADS)
+bucket_sort_kernel(const uint64_t* __restrict__ in_hash, const uint64_t* __restrict__ in_loc,
+                   uint64_t* __restrict__ out_hash, uint64_t* __restrict__ out_loc,
+                   const uint32_t* __restrict__ start, int lz, int tb) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t* A = reinterpret_cast<uint64_t*>(smem_raw);
+    uint64_t* B = A + LS_CAP;
+    uint64_t* L = B + LS_CAP;
+    uint16_t* cnt = reinterpret_cast<uint16_t*>(L + LS_CAP);       // [LS_WARPS][256] warp-private digit counters
+    uint32_t* dbase = reinterpret_cast<uint32_t*>(cnt + LS_WARPS * 256);  // [256] exclusive digit offsets
+    __shared__ uint32_t s_wsum[8];
+
+    const uint32_t b = blockIdx.x;
+    const uint32_t s = start[b], e = start[b + 1];
+    const uint32_t m = e - s;
+    if (m == 0 || m > (uint32_t)LS_CAP) return;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int sh = lz + tb;  // >= 12 on this path: the low 12 bits of (hash << sh) are zero and carry the index
+
+    // rows of 32 consecutive elements; every warp owns R consecutive rows
+    const uint32_t R = (m + LS_THREADS - 1) / LS_THREADS;  // 1..8
+    const uint32_t padded = R * LS_THREADS;
+
+    for (uint32_t j = tid; j < padded; j += LS_THREADS) {
+        uint64_t item = ~0ull;
+        if (j < m) {
+            item = ((in_hash[s + j] << sh) & ~0xfffull) | j;
+            L[j] = in_loc[s + j];
+        }
+        A[j] = item;
+    }
+
+    uint64_t* src = A;
+    uint64_t* dst = B;
+    const uint32_t lt = (1u << lane) - 1u;
+    uint16_t* my = cnt + warp * 256;
+#pragma unroll 1
+    for (int pass = 0; pass < 2; pass++) {
+        const int dshift = 48 + 8 * pass;
+        for (uint32_t i = tid; i < LS_WARPS * 256 / 2; i += LS_THREADS) reinterpret_cast<uint32_t*>(cnt)[i] = 0;
+        __syncthreads();
+        // sweep 1: warp-private digit counts
+        for (uint32_t r = 0; r < R; r++) {
+            const uint32_t d = (uint32_t)(src[(warp * R + r) * 32 + lane] >> dshift) & 255u;
+            const uint32_t peers = __match_any_sync(0xffffffffu, d);
+            if ((peers & lt) == 0) my[d] += (uint16_t)__popc(peers);
+            __syncwarp();
+        }
+        __syncthreads();
+        // exclusive scan: over warps within a digit, then over digits
+        uint32_t total = 0;
+        if (tid < 256) {
+#pragma unroll
+            for (int w = 0; w < LS_WARPS; w++) {
+                uint32_t c = cnt[w * 256 + tid];
+                cnt[w * 256 + tid] = (uint16_t)total;
+                total += c;
+            }
+            uint32_t incl = total;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+                if ((int)lane >= o) incl += v;
+            }
+            if (lane == 31) s_wsum[warp] = incl;
+            total = incl - total;  // exclusive within this warp of digits
+        }
+        __syncthreads();
+        if (tid < 256) {
+            uint32_t off = 0;
+            for (uint32_t w = 0; w < warp; w++) off += s_wsum[w];
+            dbase[tid] = off + total;
+        }
+        __syncthreads();
+        // sweep 2: stable scatter
+        for (uint32_t r = 0; r < R; r++) {
+            const uint64_t item = src[(warp * R + r) * 32 + lane];
+            const uint32_t d = (uint32_t)(item >> dshift) & 255u;
+            const uint32_t peers = __match_any_sync(0xffffffffu, d);
+            const uint32_t base = dbase[d] + my[d];
+            __syncwarp();
+            if ((peers & lt) == 0) my[d] += (uint16_t)__popc(peers);
+            __syncwarp();
+            dst[base + __popc(peers & lt)] = item;
+        }
+        __syncthreads();
+        uint64_t* t = src; src = dst; dst = t;
+    }
+    // src == A again.  Remove the remaining inversions (items are distinct, so the order is total).
+    while (true) {
+        int swapped = 0;
+        for (uint32_t i = 2 * tid; i + 1 < padded; i += 2 * LS_THREADS) {
+            uint64_t a = src[i], c = src[i + 1];
+            if (a > c) { src[i] = c; src[i + 1] = a; swapped = 1; }
+        }
+        __syncthreads();
+        for (uint32_t i = 2 * tid + 1; i + 1 < padded; i += 2 * LS_THREADS) {
+            uint64_t a = src[i], c = src[i + 1];
+            if (a > c) { src[i] = c; src[i + 1] = a; swapped = 1; }
+        }
+        if (!__syncthreads_or(swapped)) break;
+    }
+    const uint64_t top = tb ? ((uint64_t)b << (64 - tb)) : 0ull;
+    for (uint32_t j = tid; j < m; j += LS_THREADS) {
+        const uint64_t item = src[j];
+        out_hash[s + j] = (top | ((item & ~0xfffull) >> tb)) >> lz;
+        out_loc[s + j] = L[item & 0xfffu];
+    }
+}
+
 }  // namespace
 
 size_t sort_temp_bytes(uint64_t n, int end_bit) {
-    size_t bytes = 0;
+    size_t a = 0, b = 0;
     cub::DoubleBuffer<uint64_t> k(nullptr, nullptr), v(nullptr, nullptr);
-    cub::DeviceRadixSort::SortPairs(nullptr, bytes, k, v, (int64_t)n, 0, end_bit);
-    return bytes;
+    cub::DeviceRadixSort::SortPairs(nullptr, a, k, v, (int64_t)n, 0, end_bit);
+    cub::DeviceRadixSort::SortPairs(nullptr, b, (const uint64_t*)nullptr, (uint64_t*)nullptr, (const uint64_t*)nullptr,
+                                    (uint64_t*)nullptr, (int64_t)n, 0, end_bit);
+    size_t table = (((size_t)(1u << 24) + 2 + 1024) * 4 + 255) & ~(size_t)255;
+    if (n < (1ull << 24)) table = (((size_t)n + 4096 + 2 + 1024) * 4 + 255) & ~(size_t)255;
+    return table + (a > b ? a : b) + 256;
+}
+
+int msd_top_bits(uint64_t n, int lz) {
+    // smallest tb with n / 2^tb <= 3072 (average bucket; LS_CAP = 4096 leaves > 18 sigma for uniform hashes)
+    int tb = 0;
+    while (tb < 24 && (n >> tb) > 3072) tb++;
+    if (lz + tb < 12 || lz + tb > 52) return -1;  // index bits would collide with key bits: library sort instead
+    return tb;
+}
+
+static cudaError_t library_sort(uint64_t* hash_a, uint64_t* loc_a, uint64_t* hash_b, uint64_t* loc_b, uint64_t n,
+                                int begin_bit, int end_bit, void* temp, size_t temp_bytes, cudaStream_t stream,
+                                int* out_in_a, uint64_t* n_launches) {
+    cub::DoubleBuffer<uint64_t> k(hash_a, hash_b), v(loc_a, loc_b);
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(temp, temp_bytes, k, v, (int64_t)n, begin_bit, end_bit, stream);
+    *out_in_a = k.Current() == hash_a ? 1 : 0;
+    if (n_launches) *n_launches += 2 + (end_bit - begin_bit + 7) / 8;  // histogram + scan + one onesweep pass per 8 bits
+    return e;
 }
 
 cudaError_t launch_sort(uint64_t* hash_a, uint64_t* loc_a, uint64_t* hash_b, uint64_t* loc_b, uint64_t n, int end_bit,
                         void* temp, size_t temp_bytes, cudaStream_t stream, int* out_in_a, uint64_t* n_launches) {
-    cub::DoubleBuffer<uint64_t> k(hash_a, hash_b), v(loc_a, loc_b);
-    cudaError_t e = cub::DeviceRadixSort::SortPairs(temp, temp_bytes, k, v, (int64_t)n, 0, end_bit, stream);
-    *out_in_a = k.Current() == hash_a ? 1 : 0;
-    if (n_launches) *n_launches += 2 + (end_bit + 7) / 8;  // histogram + scan + one onesweep pass per 8 bits
-    return e;
+    const int lz = 64 - end_bit;
+    const int tb = msd_top_bits(n, lz);
+    if (tb < 0) return library_sort(hash_a, loc_a, hash_b, loc_b, n, 0, end_bit, temp, temp_bytes, stream, out_in_a, n_launches);
+
+    // 1. partition by the top tb bits (stable): library onesweep passes over those bits only
+    int in_a = 1;
+    cudaError_t e = cudaSuccess;
+    if (tb > 0) {
+        e = library_sort(hash_a, loc_a, hash_b, loc_b, n, end_bit - tb, end_bit, temp, temp_bytes, stream, &in_a, n_launches);
+        if (e != cudaSuccess) return e;
+    }
+    uint64_t* sh = in_a ? hash_a : hash_b;
+    uint64_t* sl = in_a ? loc_a : loc_b;
+    uint64_t* dh = in_a ? hash_b : hash_a;
+    uint64_t* dl = in_a ? loc_b : loc_a;
+    // 2. bucket boundaries, 3. one CTA per bucket sorts it in shared memory
+    const uint32_t nb = 1u << tb;
+    uint32_t* start = (uint32_t*)temp;                 // [nb + 1]
+    uint32_t* oversize = start + nb + 1;               // [0] = count, then up to MAX_OVERSIZE bucket ids
+    constexpr uint32_t MAX_OVERSIZE = 1024;
+    bucket_start_kernel<<<(nb + 1 + 255) / 256, 256, 0, stream>>>(sh, n, lz, tb, start, oversize);
+    oversize_list_kernel<<<(nb + 255) / 256, 256, 0, stream>>>(start, tb, oversize, MAX_OVERSIZE);
+    static bool attr_set = false;
+    if (!attr_set) {
+        e = cudaFuncSetAttribute(bucket_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LS_SMEM);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    bucket_sort_kernel<<<nb, LS_THREADS, LS_SMEM, stream>>>(sh, sl, dh, dl, start, lz, tb);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    if (n_launches) *n_launches += 3;
+    // 4. oversize buckets (heavy repeats of few hashes): library sort of the remaining bits, range by range
+    uint32_t h_over[1 + MAX_OVERSIZE];
+    e = cudaMemcpyAsync(h_over, oversize, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream);
+    if (e != cudaSuccess) return e;
+    e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) return e;
+    if (h_over[0]) {
+        const uint32_t cnt = h_over[0];
+        std::vector<uint32_t> ids;
+        std::vector<uint32_t> st(nb + 1);
+        e = cudaMemcpy(st.data(), start, (nb + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) return e;
+        if (cnt <= MAX_OVERSIZE) {
+            ids.resize(cnt);
+            e = cudaMemcpy(ids.data(), oversize + 1, cnt * sizeof(uint32_t), cudaMemcpyDeviceToHost);
+            if (e != cudaSuccess) return e;
+        } else {
+            for (uint32_t b = 0; b < nb; b++) if (st[b + 1] - st[b] > (uint32_t)LS_CAP) ids.push_back(b);
+        }
+        void* big_temp = (char*)temp + (((size_t)(nb + 2 + MAX_OVERSIZE) * 4 + 255) & ~(size_t)255);
+        size_t big_bytes = temp_bytes - ((char*)big_temp - (char*)temp);
+        for (uint32_t b : ids) {
+            const uint64_t s0 = st[b], m = st[b + 1] - st[b];
+            e = cub::DeviceRadixSort::SortPairs(big_temp, big_bytes, sh + s0, dh + s0, sl + s0, dl + s0, (int64_t)m, 0,
+                                                end_bit - tb, stream);
+            if (e != cudaSuccess) return e;
+            if (n_launches) *n_launches += 2 + (end_bit - tb + 7) / 8;
+        }
+    }
+    *out_in_a = in_a ? 0 : 1;
+    return cudaSuccess;
 }
 
 cudaError_t launch_protein_abund(const uint64_t* loc, uint64_t n, uint32_t n_prot, uint32_t* t_abund, cudaStream_t stream,

@@ -322,3 +322,40 @@ def test_medium_scale_against_oracle(K, O):
         okeys, orow, ops, oqs = O.build_index(oh, opid, opos)
         assert np.array_equal(keys, okeys) and np.array_equal(row_ptr, orow)
         assert np.array_equal(pid, ops) and np.array_equal(pos, oqs)
+
+
+def test_bucket_sort_path_with_oversize_buckets(K, O):
+    """Enough tuples for the hand-written bucket sort (needs >= 2^12 buckets) plus low-complexity proteins whose
+    repeated hashes overflow a shared-memory bucket (library-sort fallback for those ranges)."""
+    from kmerseek_b200 import synth
+    res, offs = synth.proteome(14_000_000, 4242)
+    seqs_extra = ["A" * 30000, "AG" * 9000, "ACDEFGHIKL" * 2500, "M" + "L" * 7000]
+    extra = np.frombuffer("".join(seqs_extra).encode(), dtype=np.uint8)
+    eoffs = np.cumsum([0] + [len(s) for s in seqs_extra]).astype(np.uint64)
+    res2 = np.concatenate([res[: int(offs[1000])], extra, res[int(offs[1000]):]])
+    offs2 = np.concatenate([offs[:1001], offs[1000] + eoffs[1:], offs[1001:] + eoffs[-1]])
+    prot = K.Proteome.from_packed(res2, offs2)
+    for k, moltype, scaled in ((16, "dayhoff", 1), (24, "hp", 1)):
+        with K.ProteomeIndex("db", k, scaled, moltype) as idx:
+            idx.add_proteome(prot)
+            idx.finalize()
+            keys, row_ptr, pid, pos = idx.csr()
+            oh, opid, opos = O.sketch_tuples(res2, offs2, k, moltype, scaled)
+            okeys, orow, ops, oqs = O.build_index(oh, opid, opos)
+            assert np.array_equal(keys, okeys) and np.array_equal(row_ptr, orow)
+            assert np.array_equal(pid, ops) and np.array_equal(pos, oqs)
+            assert int(np.diff(orow).max()) > 4096  # a hash that alone overflows a bucket
+
+
+def test_bucket_sort_path_scaled(K, O):
+    from kmerseek_b200 import synth
+    res, offs = synth.proteome(30_000_000, 777)
+    prot = K.Proteome.from_packed(res, offs)
+    with K.ProteomeIndex("db", 7, 10, "protein") as idx:  # the C4 alphabet / k / scaled
+        idx.add_proteome(prot)
+        idx.finalize()
+        keys, row_ptr, pid, pos = idx.csr()
+        oh, opid, opos = O.sketch_tuples(res, offs, 7, "protein", 10)
+        okeys, orow, ops, oqs = O.build_index(oh, opid, opos)
+        assert np.array_equal(keys, okeys) and np.array_equal(row_ptr, orow)
+        assert np.array_equal(pid, ops) and np.array_equal(pos, oqs)
