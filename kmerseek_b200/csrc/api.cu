@@ -401,8 +401,8 @@ void finalize(ks_index* x) {
     }
     KS_CUDA(cudaEventRecord(x->ev[EV_SO1], x->stream));
     x->t_sort = true;
-    int bits = 8;
-    while (bits < 26 && (1ull << bits) < n) bits++;
+    int bits = 8;  // ~4 tuples (<= 4 keys) per directory bucket: the table stays small next to the keys
+    while (bits < 24 && (4ull << bits) < n) bits++;
     x->dir_bits = bits;
     x->dir_shift = 64 - x->lz - bits;
     x->keys = x->arena->alloc<uint64_t>(n);

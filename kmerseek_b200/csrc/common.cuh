@@ -41,9 +41,12 @@ __device__ __forceinline__ void st_relaxed(uint64_t* p, uint64_t v) {
 }
 
 // Called by ONE full warp of the tile.  Publishes this tile's aggregate, walks back over the
-// predecessors' words 32 at a time, returns the exclusive prefix (same value in every lane) and
-// publishes the inclusive prefix.  `value` must be < 2^62.
+// predecessors' words 128 at a time (4 per lane, independent loads), returns the exclusive prefix (same
+// value in every lane) and publishes the inclusive prefix.  `value` must be < 2^62.
+// The window is wide on purpose: with hundreds of tiles in flight none of a tile's near predecessors has
+// a prefix yet, and every 32-wide round would cost a full L2 round trip.
 __device__ __forceinline__ uint64_t scan_lookback(uint64_t* status, uint32_t tile, uint64_t value) {
+    constexpr int W = 4;
     const uint32_t lane = threadIdx.x & 31;
     if (tile == 0) {
         if (lane == 0) st_relaxed(status, SCAN_PFX | value);
@@ -53,22 +56,44 @@ __device__ __forceinline__ uint64_t scan_lookback(uint64_t* status, uint32_t til
     uint64_t excl = 0;
     int64_t base = (int64_t)tile - 1;
     while (true) {
-        int64_t idx = base - lane;
-        uint64_t w = SCAN_PFX;  // tiles before 0: prefix 0
-        if (idx >= 0) {
-            do { w = ld_relaxed(status + idx); } while ((w >> 62) == 0);
-        }
-        uint32_t pfx_mask = __ballot_sync(0xffffffffu, (w >> 62) == 2);
-        uint64_t v = w & SCAN_VAL;
+        // lane l looks at predecessors base - (l*W + j), j = 0..W-1: distance grows with (lane, j)
+        uint64_t w[W];
+        bool ready;
+        do {
+            ready = true;
+#pragma unroll
+            for (int j = 0; j < W; j++) {
+                int64_t idx = base - (int64_t)(lane * W + j);
+                w[j] = idx >= 0 ? ld_relaxed(status + idx) : SCAN_PFX;  // tiles before 0: prefix 0
+                ready &= (w[j] >> 62) != 0;
+            }
+            // only the words nearer than the nearest prefix matter; older tiles publish earlier, so waiting
+            // for the whole window costs nothing extra and keeps the loop simple
+        } while (!__all_sync(0xffffffffu, ready));
+        // nearest prefix: smallest distance d = lane*W + j with flag == 2
+        int my_first = W;  // j of this lane's nearest prefix word
+#pragma unroll
+        for (int j = W - 1; j >= 0; j--) if ((w[j] >> 62) == 2) my_first = j;
+        const uint32_t pfx_mask = __ballot_sync(0xffffffffu, my_first < W);
+        uint64_t v = 0;
         if (pfx_mask) {
-            int first = __ffs(pfx_mask) - 1;  // nearest predecessor that holds an inclusive prefix
-            if ((int)lane > first) v = 0;
+            const int first_lane = __ffs(pfx_mask) - 1;
+            if ((int)lane < first_lane) {
+#pragma unroll
+                for (int j = 0; j < W; j++) v += w[j] & SCAN_VAL;
+            } else if ((int)lane == first_lane) {
+#pragma unroll
+                for (int j = 0; j < W; j++) if (j <= my_first) v += w[j] & SCAN_VAL;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < W; j++) v += w[j] & SCAN_VAL;
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
         excl += v;
         if (pfx_mask) break;
-        base -= 32;
+        base -= 32 * W;
     }
     if (lane == 0) st_relaxed(status + tile, SCAN_PFX | ((excl + value) & SCAN_VAL));
     return excl;

@@ -14,8 +14,8 @@ namespace ks {
 
 namespace {
 
-constexpr int CSR_THREADS = 256;
-constexpr int CSR_ROWS = 8;
+constexpr int CSR_THREADS = 512;  // big tiles: few tiles in flight keeps the look-back chain short
+constexpr int CSR_ROWS = 16;
 constexpr int CSR_TILE = CSR_THREADS * CSR_ROWS;
 
 __global__ void protein_abund_kernel(const uint64_t* __restrict__ loc, uint64_t n, uint32_t n_prot,
@@ -52,22 +52,25 @@ csr_kernel(const uint64_t* __restrict__ hash, const uint64_t* __restrict__ loc, 
     const uint64_t n_tiles = (n + CSR_TILE - 1) / CSR_TILE;
     const uint64_t i0 = (uint64_t)tile * CSR_TILE + warp * (CSR_ROWS * 32) + lane;
 
-    uint64_t h[CSR_ROWS];
     uint32_t bk[CSR_ROWS], bg[CSR_ROWS];
     uint32_t wk = 0, wg = 0;
 #pragma unroll
     for (int r = 0; r < CSR_ROWS; r++) {
         const uint64_t i = i0 + r * 32;
         bool hk = false, hg = false;
-        h[r] = 0;
+        uint64_t h = 0;
+        uint32_t pid = 0;
+        if (i < n) { h = hash[i]; pid = (uint32_t)(loc[i] >> 32); }
+        // the predecessor comes from the neighbouring lane; lane 0 reads it (same cache line as the row before)
+        uint64_t hp = __shfl_up_sync(0xffffffffu, h, 1);
+        uint32_t pp = __shfl_up_sync(0xffffffffu, pid, 1);
         if (i < n) {
-            h[r] = hash[i];
-            const uint32_t pid = (uint32_t)(loc[i] >> 32);
+            if (lane == 0 && i > 0) { hp = hash[i - 1]; pp = (uint32_t)(loc[i - 1] >> 32); }
             if (i == 0) {
                 hk = hg = true;
             } else {
-                hk = h[r] != hash[i - 1];
-                hg = hk || pid != (uint32_t)(loc[i - 1] >> 32);
+                hk = h != hp;
+                hg = hk || pid != pp;
             }
             if (!hg) atomicSub(&t_size[pid], 1u);  // a repeat of (hash, protein): not a new min of that sketch
         }
@@ -110,7 +113,7 @@ csr_kernel(const uint64_t* __restrict__ hash, const uint64_t* __restrict__ loc, 
         if (hg) grp_start[g] = (uint32_t)i;
         if (hk) {
             const uint32_t u = rk + __popc(bk[r] & lt);
-            keys[u] = h[r];
+            keys[u] = hash[i];  // L1/L2 hit: this CTA read it a moment ago
             key_grp[u] = g;
         }
         rk += __popc(bk[r]);
@@ -225,12 +228,27 @@ bucket_sort_kernel(const uint64_t* __restrict__ in_hash, const uint64_t* __restr
         const int dshift = 48 + 8 * pass;
         for (uint32_t i = tid; i < LS_WARPS * 256 / 2; i += LS_THREADS) reinterpret_cast<uint32_t*>(cnt)[i] = 0;
         __syncthreads();
-        // sweep 1: warp-private digit counts
-        for (uint32_t r = 0; r < R; r++) {
-            const uint32_t d = (uint32_t)(src[(warp * R + r) * 32 + lane] >> dshift) & 255u;
-            const uint32_t peers = __match_any_sync(0xffffffffu, d);
-            if ((peers & lt) == 0) my[d] += (uint16_t)__popc(peers);
-            __syncwarp();
+        // sweep 1: lanes of a row that share a digit ("peers") from 8 ballots -- MATCH.ANY would do this in one
+        // instruction but runs on the ADU pipe at ~40 cycles per warp; the lowest peer adds the group to the
+        // warp-private counter.  digit, rank among peers and group size are kept for sweep 2.
+        uint32_t info[8];
+#pragma unroll
+        for (uint32_t r = 0; r < 8; r++) {
+            info[r] = 0;
+            if (r < R) {
+                const uint32_t d = (uint32_t)(src[(warp * R + r) * 32 + lane] >> dshift) & 255u;
+                uint32_t peers = 0xffffffffu;
+#pragma unroll
+                for (int bit = 0; bit < 8; bit++) {
+                    const bool on = (d >> bit) & 1u;
+                    const uint32_t v = __ballot_sync(0xffffffffu, on);
+                    peers &= on ? v : ~v;
+                }
+                const uint32_t rank = __popc(peers & lt), size = __popc(peers);
+                if (rank == 0) my[d] += (uint16_t)size;
+                info[r] = d | (rank << 8) | (size << 16);
+                __syncwarp();
+            }
         }
         __syncthreads();
         // exclusive scan: over warps within a digit, then over digits
@@ -259,15 +277,17 @@ bucket_sort_kernel(const uint64_t* __restrict__ in_hash, const uint64_t* __restr
         }
         __syncthreads();
         // sweep 2: stable scatter
-        for (uint32_t r = 0; r < R; r++) {
-            const uint64_t item = src[(warp * R + r) * 32 + lane];
-            const uint32_t d = (uint32_t)(item >> dshift) & 255u;
-            const uint32_t peers = __match_any_sync(0xffffffffu, d);
-            const uint32_t base = dbase[d] + my[d];
-            __syncwarp();
-            if ((peers & lt) == 0) my[d] += (uint16_t)__popc(peers);
-            __syncwarp();
-            dst[base + __popc(peers & lt)] = item;
+#pragma unroll
+        for (uint32_t r = 0; r < 8; r++) {
+            if (r < R) {
+                const uint64_t item = src[(warp * R + r) * 32 + lane];
+                const uint32_t d = info[r] & 255u, rank = (info[r] >> 8) & 255u, size = info[r] >> 16;
+                const uint32_t base = dbase[d] + my[d];
+                __syncwarp();
+                if (rank == 0) my[d] += (uint16_t)size;
+                __syncwarp();
+                dst[base + rank] = item;
+            }
         }
         __syncthreads();
         uint64_t* t = src; src = dst; dst = t;
