@@ -379,43 +379,40 @@ void finalize(ks_index* x) {
     const uint64_t n = x->n_tuples;
     if (n > MAX_TUPLES) fail(KS_ERR_CAPACITY, "more than 2^31-1 tuples on one shard: shard the proteome over more GPUs");
     const uint32_t P = (uint32_t)x->n_prot;
-    x->t_abund = x->arena->alloc<uint32_t>(P);
-    x->t_size = x->arena->alloc<uint32_t>(P);
-    KS_CUDA(cudaEventRecord(x->ev[EV_SO0], x->stream));
-    KS_CUDA(launch_protein_abund(x->d_loc, n, P, x->t_abund, x->stream, &x->l_csr));
-    if (P) KS_CUDA(cudaMemcpyAsync(x->t_size, x->t_abund, (size_t)P * 4, cudaMemcpyDeviceToDevice, x->stream));
-    if (n) {
-        uint64_t* hb = x->arena->alloc<uint64_t>(n);
-        uint64_t* lb = x->arena->alloc<uint64_t>(n);
-        size_t tb = sort_temp_bytes(n, x->end_bit());
-        void* temp = x->arena->alloc<char>(tb);
-        int in_a = 1;
-        KS_CUDA(launch_sort(x->d_hash, x->d_loc, hb, lb, n, x->end_bit(), temp, tb, x->stream, &in_a, &x->l_sort));
-        x->arena->release(temp);
-        if (in_a) {
-            x->arena->release(hb); x->arena->release(lb);
-        } else {
-            x->arena->release(x->d_hash); x->arena->release(x->d_loc);
-            x->d_hash = hb; x->d_loc = lb; x->cap = n;
-        }
-    }
-    KS_CUDA(cudaEventRecord(x->ev[EV_SO1], x->stream));
-    x->t_sort = true;
     int bits = 8;  // ~4 tuples (<= 4 keys) per directory bucket: the table stays small next to the keys
     while (bits < 24 && (4ull << bits) < n) bits++;
     x->dir_bits = bits;
     x->dir_shift = 64 - x->lz - bits;
+    x->t_abund = x->arena->alloc<uint32_t>(P);
+    x->t_size = x->arena->alloc<uint32_t>(P);
     x->keys = x->arena->alloc<uint64_t>(n);
     x->key_grp = x->arena->alloc<uint32_t>(n + 1);
     x->grp_start = x->arena->alloc<uint32_t>(n + 1);
     x->dir = x->arena->alloc<uint32_t>((1ull << bits) + 1);
     x->d_counts = x->arena->alloc<uint64_t>(2);
-    ensure_ws(x, csr_workspace_bytes(n));
-    KS_CUDA(cudaEventRecord(x->ev[EV_CS0], x->stream));
-    KS_CUDA(launch_csr(x->d_hash, x->d_loc, n, x->keys, x->key_grp, x->grp_start, x->t_size, x->d_counts, x->dir,
-                       x->dir_bits, x->dir_shift, x->ws, x->stream, &x->l_csr));
+    uint64_t* hb = x->arena->alloc<uint64_t>(n);
+    uint64_t* lb = x->arena->alloc<uint64_t>(n);
+    BuildArgs a;
+    a.hash_a = x->d_hash; a.loc_a = x->d_loc; a.hash_b = hb; a.loc_b = lb;
+    a.n = n; a.n_prot = P; a.end_bit = x->end_bit();
+    a.keys = x->keys; a.key_grp = x->key_grp; a.grp_start = x->grp_start; a.t_size = x->t_size; a.t_abund = x->t_abund;
+    a.d_counts = x->d_counts; a.dir = x->dir; a.dir_bits = x->dir_bits; a.dir_shift = x->dir_shift;
+    a.temp_bytes = build_temp_bytes(n, x->end_bit());
+    a.temp = x->arena->alloc<char>(a.temp_bytes);
+    a.ev_sorted = x->ev[EV_SO1];
+    int in_a = 1;
+    KS_CUDA(cudaEventRecord(x->ev[EV_SO0], x->stream));
+    KS_CUDA(build_index(a, x->stream, &in_a, &x->l_sort, &x->l_csr));
     KS_CUDA(cudaEventRecord(x->ev[EV_CS1], x->stream));
-    x->t_csr = true;
+    x->t_sort = x->t_csr = true;
+    x->arena->release(a.temp);
+    if (in_a) {
+        x->arena->release(hb); x->arena->release(lb);
+    } else {
+        if (x->d_hash) x->arena->release(x->d_hash);
+        if (x->d_loc) x->arena->release(x->d_loc);
+        x->d_hash = hb; x->d_loc = lb; x->cap = n;
+    }
     uint64_t c[2];
     KS_CUDA(cudaMemcpyAsync(c, x->d_counts, 16, cudaMemcpyDeviceToHost, x->stream));
     KS_CUDA(cudaStreamSynchronize(x->stream));
@@ -599,7 +596,7 @@ ks_status ks_index_stats(ks_index* x, ks_stats* out) {
         if (x->t_upload) KS_CUDA(cudaEventElapsedTime(&s.ms_upload, x->ev[EV_UP0], x->ev[EV_UP1]));
         if (x->t_sketch) KS_CUDA(cudaEventElapsedTime(&s.ms_sketch, x->ev[EV_SK0], x->ev[EV_SK1]));
         if (x->t_sort) KS_CUDA(cudaEventElapsedTime(&s.ms_sort, x->ev[EV_SO0], x->ev[EV_SO1]));
-        if (x->t_csr) KS_CUDA(cudaEventElapsedTime(&s.ms_csr, x->ev[EV_CS0], x->ev[EV_CS1]));
+        if (x->t_csr) KS_CUDA(cudaEventElapsedTime(&s.ms_csr, x->ev[EV_SO1], x->ev[EV_CS1]));
         s.ms_search = x->ms_search;
         s.finalized = x->finalized ? 1 : 0;
         *out = s;

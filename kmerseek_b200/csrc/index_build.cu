@@ -1,10 +1,22 @@
-// Index build for sm_100a: sort of the sketch tuples by hash and single-pass CSR construction.
+// Index build for sm_100a: MSD sort of the sketch tuples by hash and chain-free CSR construction.
 //
 // Replaces, on the hot path, the reference's per-protein sorted Vec inserts (sourmash KmerMinHash via
 // src/rust/signature.rs:273-274), the nested HashMap position records (src/rust/index.rs:770-780) and the
 // serial sorted-Vec merge into combined_minhash (src/rust/index.rs:824-827).
+//
+// Pipeline:
+//   1. partition the tuples by the top `tb` bits of the hash (library onesweep passes over those bits only)
+//   2. bucket_sort_kernel: one CTA sorts one bucket (a few thousand tuples) entirely in shared memory, writes
+//      it back in final order and counts the bucket's unique hashes / (hash, protein) groups on the way out
+//   3. scan_counts_kernel: exclusive scan of the per-bucket counts (one CTA)
+//   4. csr_write_kernel: one CTA per bucket re-reads its sorted tuples once and writes keys / key_grp /
+//      grp_start at their final offsets -- no inter-CTA dependency, no look-back chain
+//   5. dir_kernel: bucket directory over the unique keys
+// Small inputs (and hash ranges where the shared-memory item layout does not apply) take the library sort for
+// all bits and the same steps 3-5 over fixed 4096-tuple ranges.
 #include <cub/device/device_radix_sort.cuh>
 
+#include <algorithm>
 #include <vector>
 
 #include "common.cuh"
@@ -14,12 +26,14 @@ namespace ks {
 
 namespace {
 
-constexpr int CSR_THREADS = 512;  // big tiles: few tiles in flight keeps the look-back chain short
-constexpr int CSR_ROWS = 16;
-constexpr int CSR_TILE = CSR_THREADS * CSR_ROWS;
+constexpr int LS_THREADS = 512;
+constexpr int LS_WARPS = LS_THREADS / 32;
+constexpr int LS_CAP = 4096;  // tuples per bucket that fit the shared-memory layout (12 index bits)
+constexpr size_t LS_SMEM = (size_t)LS_CAP * 8 * 3 + LS_WARPS * 256 * 2 + 256 * 4 + 64;
+constexpr uint32_t MAX_OVERSIZE = 1024;
 
 __global__ void protein_abund_kernel(const uint64_t* __restrict__ loc, uint64_t n, uint32_t n_prot,
-                                     uint32_t* __restrict__ t_abund) {
+                                     uint32_t* __restrict__ t_abund, uint32_t* __restrict__ t_size) {
     uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n_prot) return;
     // tuples are ordered by (protein, pos): count = lower_bound((p+1)<<32) - lower_bound(p<<32)
@@ -31,133 +45,10 @@ __global__ void protein_abund_kernel(const uint64_t* __restrict__ loc, uint64_t 
         }
         return lo;
     };
-    uint64_t a = lb((uint64_t)p << 32);
-    uint64_t b = (p + 1 == 0) ? n : lb(((uint64_t)p + 1) << 32);
-    t_abund[p] = (uint32_t)(b - a);
+    const uint32_t c = (uint32_t)(lb(((uint64_t)p + 1) << 32) - lb((uint64_t)p << 32));
+    t_abund[p] = c;
+    t_size[p] = c;  // repeats of a (hash, protein) pair are subtracted while the groups are counted
 }
-
-// One pass over the sorted tuples.  Two running counts (unique hashes, (hash, protein) groups) are packed
-// into one scan word and chained across CTAs with the same decoupled look-back the sketch kernel uses.
-__global__ void __launch_bounds__(CSR_THREADS)
-csr_kernel(const uint64_t* __restrict__ hash, const uint64_t* __restrict__ loc, uint64_t n, uint64_t* __restrict__ keys,
-           uint32_t* __restrict__ key_grp, uint32_t* __restrict__ grp_start, uint32_t* __restrict__ t_size,
-           uint64_t* __restrict__ d_counts, uint32_t* __restrict__ ticket, uint64_t* __restrict__ status) {
-    __shared__ uint32_t s_wk[CSR_THREADS / 32], s_wg[CSR_THREADS / 32];
-    __shared__ uint32_t s_tile;
-    __shared__ uint64_t s_base;
-    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_tile = atomicAdd(ticket, 1u);
-    __syncthreads();
-    const uint32_t tile = s_tile;
-    const uint64_t n_tiles = (n + CSR_TILE - 1) / CSR_TILE;
-    const uint64_t i0 = (uint64_t)tile * CSR_TILE + warp * (CSR_ROWS * 32) + lane;
-
-    uint32_t bk[CSR_ROWS], bg[CSR_ROWS];
-    uint32_t wk = 0, wg = 0;
-#pragma unroll
-    for (int r = 0; r < CSR_ROWS; r++) {
-        const uint64_t i = i0 + r * 32;
-        bool hk = false, hg = false;
-        uint64_t h = 0;
-        uint32_t pid = 0;
-        if (i < n) { h = hash[i]; pid = (uint32_t)(loc[i] >> 32); }
-        // the predecessor comes from the neighbouring lane; lane 0 reads it (same cache line as the row before)
-        uint64_t hp = __shfl_up_sync(0xffffffffu, h, 1);
-        uint32_t pp = __shfl_up_sync(0xffffffffu, pid, 1);
-        if (i < n) {
-            if (lane == 0 && i > 0) { hp = hash[i - 1]; pp = (uint32_t)(loc[i - 1] >> 32); }
-            if (i == 0) {
-                hk = hg = true;
-            } else {
-                hk = h != hp;
-                hg = hk || pid != pp;
-            }
-            if (!hg) atomicSub(&t_size[pid], 1u);  // a repeat of (hash, protein): not a new min of that sketch
-        }
-        bk[r] = __ballot_sync(0xffffffffu, hk);
-        bg[r] = __ballot_sync(0xffffffffu, hg);
-        wk += __popc(bk[r]);
-        wg += __popc(bg[r]);
-    }
-    if (lane == 0) { s_wk[warp] = wk; s_wg[warp] = wg; }
-    __syncthreads();
-    uint32_t pk = 0, pg = 0, tk = 0, tg = 0;
-#pragma unroll
-    for (int w = 0; w < CSR_THREADS / 32; w++) {
-        if (w < (int)warp) { pk += s_wk[w]; pg += s_wg[w]; }
-        tk += s_wk[w];
-        tg += s_wg[w];
-    }
-    if (warp == 0) {
-        uint64_t excl = scan_lookback(status, tile, (uint64_t)tk | ((uint64_t)tg << 31));
-        if (lane == 0) {
-            s_base = excl;
-            if (tile == n_tiles - 1) {
-                uint64_t U = (excl & 0x7fffffffu) + tk, G = (excl >> 31) + tg;
-                d_counts[0] = U;
-                d_counts[1] = G;
-                key_grp[U] = (uint32_t)G;
-                grp_start[G] = (uint32_t)n;
-            }
-        }
-    }
-    __syncthreads();
-    uint32_t rk = (uint32_t)(s_base & 0x7fffffffu) + pk;
-    uint32_t rg = (uint32_t)(s_base >> 31) + pg;
-    const uint32_t lt = (1u << lane) - 1u;
-#pragma unroll
-    for (int r = 0; r < CSR_ROWS; r++) {
-        const uint64_t i = i0 + r * 32;
-        const bool hk = (bk[r] >> lane) & 1u, hg = (bg[r] >> lane) & 1u;
-        const uint32_t g = rg + __popc(bg[r] & lt);
-        if (hg) grp_start[g] = (uint32_t)i;
-        if (hk) {
-            const uint32_t u = rk + __popc(bk[r] & lt);
-            keys[u] = hash[i];  // L1/L2 hit: this CTA read it a moment ago
-            key_grp[u] = g;
-        }
-        rk += __popc(bk[r]);
-        rg += __popc(bg[r]);
-    }
-}
-
-// dir[b] = index of the first key whose bucket is >= b; dir[2^bits] = U.
-__global__ void dir_kernel(const uint64_t* __restrict__ keys, const uint64_t* __restrict__ d_counts,
-                           uint32_t* __restrict__ dir, int bits, int shift) {
-    const uint64_t U = d_counts[0];
-    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    const uint32_t nb = 1u << bits;
-    if (U == 0) {
-        for (uint64_t b = i; b <= nb; b += (uint64_t)gridDim.x * blockDim.x) dir[b] = 0;
-        return;
-    }
-    if (i >= U) return;
-    const uint32_t b = (uint32_t)(keys[i] >> shift);
-    const int64_t bp = i ? (int64_t)(uint32_t)(keys[i - 1] >> shift) : -1;
-    for (int64_t x = bp + 1; x <= (int64_t)b; x++) dir[x] = (uint32_t)i;
-    if (i == U - 1)
-        for (uint32_t x = b + 1; x <= nb; x++) dir[x] = (uint32_t)U;
-}
-
-
-// ---------------------------------------------------------------------------------------------
-// Bucket-local sort (the last pass of the MSD sort).
-//
-// After the tuples have been partitioned by the top `tb` bits of the normalised hash (normalised =
-// shifted left by the `lz` leading bits that are zero under max_hash), every bucket is a contiguous range
-// of a few thousand tuples.  One CTA sorts one bucket entirely in shared memory:
-//   item = (remaining key bits, left-aligned, low 12 bits replaced by the tuple's index in the bucket)
-// so that comparing items compares (hash, original order) exactly -- the sort is stable by construction.
-// Two stable 8-bit counting passes (warp-private digit counters, MATCH.ANY ranks) order the items by the
-// next 16 key bits; hashes are uniform, so what is left are isolated inversions between neighbours, which
-// an odd-even transposition loop removes in a handful of sweeps (it runs until a sweep swaps nothing, so
-// the result is exact for any input).  The hash is rebuilt from the item, loc is gathered from a staged
-// copy, and the bucket streams back to HBM in sorted order: one read and one write of every tuple.
-// ---------------------------------------------------------------------------------------------
-constexpr int LS_THREADS = 512;
-constexpr int LS_WARPS = LS_THREADS / 32;
-constexpr int LS_CAP = 4096;  // tuples per bucket that fit the shared-memory layout (12 index bits)
-constexpr size_t LS_SMEM = (size_t)LS_CAP * 8 * 3 + LS_WARPS * 256 * 2 + 256 * 4 + 64;
 
 __global__ void bucket_start_kernel(const uint64_t* __restrict__ hash, uint64_t n, int lz, int tb,
                                     uint32_t* __restrict__ start, uint32_t* __restrict__ oversize) {
@@ -175,35 +66,60 @@ __global__ void bucket_start_kernel(const uint64_t* __restrict__ hash, uint64_t 
     start[b] = (uint32_t)lo;
 }
 
-// Buckets too large for shared memory (only heavy repeats of one hash can do that) are listed for the
-// host, which sorts those ranges with the library radix sort.
-__global__ void oversize_list_kernel(const uint32_t* __restrict__ start, int tb, uint32_t* __restrict__ oversize,
-                                     uint32_t max_list) {
+__global__ void fixed_ranges_kernel(uint64_t n, uint32_t nb, uint32_t* __restrict__ start) {
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= (1u << tb)) return;
-    if (start[b + 1] - start[b] > (uint32_t)LS_CAP) {
-        uint32_t slot = atomicAdd(&oversize[0], 1u);
-        if (slot < max_list) oversize[1 + slot] = b;
-    }
+    if (b > nb) return;
+    const uint64_t s = (uint64_t)b * LS_CAP;
+    start[b] = (uint32_t)(s < n ? s : n);
 }
 
+// Buckets too large for shared memory (only heavy repeats of one hash can do that) are counted for the
+// host, which sorts those ranges with the library radix sort.
+__global__ void oversize_count_kernel(const uint32_t* __restrict__ start, uint32_t nb, uint32_t* __restrict__ oversize) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nb) return;
+    if (start[b + 1] - start[b] > (uint32_t)LS_CAP) atomicAdd(&oversize[0], 1u);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Bucket-local sort (the last pass of the MSD sort).
+//
+// After the partition by the top `tb` bits of the normalised hash (normalised = shifted left by the `lz`
+// leading bits that are zero under max_hash) every bucket is a contiguous range of a few thousand tuples.
+// One CTA sorts one bucket in shared memory:
+//   item = remaining key bits, left-aligned, low 12 bits replaced by the tuple's index in the bucket
+// so comparing items compares (hash, original order) exactly and the result is the stable order.
+// Two stable 8-bit counting passes order the items by the next 16 key bits: every warp owns consecutive
+// rows of 32 items, lanes that share a digit find each other with 8 ballots (MATCH.ANY would do it in one
+// instruction but sits on the ADU pipe at ~40 cycles per warp), the lowest lane of each group updates the
+// warp-private digit counter.  Hashes are uniform, so what is left after 32 known bits are a few short runs
+// that share those bits: their inversions are listed in one parallel sweep and each listed run is put in
+// order by one thread (insertion sort; exact for any input).  The hash is rebuilt from the item, loc is
+// gathered from a staged copy, and the bucket streams back to HBM once, in final order.  On the way out the
+// CTA counts unique hashes and (hash, protein) groups and subtracts repeated (hash, protein) pairs from the
+// protein's sketch size.
+// ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(LS_THREADS)
 bucket_sort_kernel(const uint64_t* __restrict__ in_hash, const uint64_t* __restrict__ in_loc,
                    uint64_t* __restrict__ out_hash, uint64_t* __restrict__ out_loc,
-                   const uint32_t* __restrict__ start, int lz, int tb) {
+                   const uint32_t* __restrict__ start, int lz, int tb, uint64_t* __restrict__ counts,
+                   uint32_t* __restrict__ t_size) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t* A = reinterpret_cast<uint64_t*>(smem_raw);
     uint64_t* B = A + LS_CAP;
     uint64_t* L = B + LS_CAP;
-    uint16_t* cnt = reinterpret_cast<uint16_t*>(L + LS_CAP);       // [LS_WARPS][256] warp-private digit counters
+    uint16_t* cnt = reinterpret_cast<uint16_t*>(L + LS_CAP);              // [LS_WARPS][256] warp-private counters
     uint32_t* dbase = reinterpret_cast<uint32_t*>(cnt + LS_WARPS * 256);  // [256] exclusive digit offsets
     __shared__ uint32_t s_wsum[8];
+    __shared__ uint32_t s_ninv;
+    __shared__ uint32_t s_tk[LS_WARPS], s_tg[LS_WARPS];
 
     const uint32_t b = blockIdx.x;
     const uint32_t s = start[b], e = start[b + 1];
     const uint32_t m = e - s;
-    if (m == 0 || m > (uint32_t)LS_CAP) return;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (m == 0) { if (tid == 0) counts[b] = 0; return; }
+    if (m > (uint32_t)LS_CAP) return;  // oversize: sorted and counted by the host-driven fallback
     const int sh = lz + tb;  // >= 12 on this path: the low 12 bits of (hash << sh) are zero and carry the index
 
     // rows of 32 consecutive elements; every warp owns R consecutive rows
@@ -218,6 +134,7 @@ bucket_sort_kernel(const uint64_t* __restrict__ in_hash, const uint64_t* __restr
         }
         A[j] = item;
     }
+    if (tid == 0) s_ninv = 0;
 
     uint64_t* src = A;
     uint64_t* dst = B;
@@ -228,9 +145,7 @@ bucket_sort_kernel(const uint64_t* __restrict__ in_hash, const uint64_t* __restr
         const int dshift = 48 + 8 * pass;
         for (uint32_t i = tid; i < LS_WARPS * 256 / 2; i += LS_THREADS) reinterpret_cast<uint32_t*>(cnt)[i] = 0;
         __syncthreads();
-        // sweep 1: lanes of a row that share a digit ("peers") from 8 ballots -- MATCH.ANY would do this in one
-        // instruction but runs on the ADU pipe at ~40 cycles per warp; the lowest peer adds the group to the
-        // warp-private counter.  digit, rank among peers and group size are kept for sweep 2.
+        // sweep 1: groups of equal digits within a row; digit, rank in the group and group size are kept for sweep 2
         uint32_t info[8];
 #pragma unroll
         for (uint32_t r = 0; r < 8; r++) {
@@ -292,52 +207,246 @@ bucket_sort_kernel(const uint64_t* __restrict__ in_hash, const uint64_t* __restr
         __syncthreads();
         uint64_t* t = src; src = dst; dst = t;
     }
-    // src == A again.  Remove the remaining inversions (items are distinct, so the order is total).
-    while (true) {
-        int swapped = 0;
-        for (uint32_t i = 2 * tid; i + 1 < padded; i += 2 * LS_THREADS) {
-            uint64_t a = src[i], c = src[i + 1];
-            if (a > c) { src[i] = c; src[i + 1] = a; swapped = 1; }
-        }
-        __syncthreads();
-        for (uint32_t i = 2 * tid + 1; i + 1 < padded; i += 2 * LS_THREADS) {
-            uint64_t a = src[i], c = src[i + 1];
-            if (a > c) { src[i] = c; src[i + 1] = a; swapped = 1; }
-        }
-        if (!__syncthreads_or(swapped)) break;
+    // src == A.  Items are ordered by the 16 digit bits; list the inversions inside runs that share them.
+    uint32_t* inv = reinterpret_cast<uint32_t*>(B);
+    for (uint32_t j = tid + 1; j < m; j += LS_THREADS) {
+        const uint64_t a = src[j - 1], c = src[j];
+        if (((a ^ c) >> 48) == 0 && a > c) inv[atomicAdd(&s_ninv, 1u)] = j;
     }
+    __syncthreads();
+    const uint32_t ninv = s_ninv;
+    for (uint32_t k = tid; k < ninv; k += LS_THREADS) {
+        const uint32_t j = inv[k];
+        const uint64_t pj = src[j] >> 48;
+        uint32_t a0 = j - 1;
+        while (a0 > 0 && (src[a0 - 1] >> 48) == pj) a0--;
+        bool first = true;  // one thread per run: the one that holds the run's first inversion
+        for (uint32_t t = a0 + 1; t < j; t++)
+            if (src[t - 1] > src[t]) { first = false; break; }
+        if (first) {
+            uint32_t b0 = j + 1;
+            while (b0 < m && (src[b0] >> 48) == pj) b0++;
+            for (uint32_t t = a0 + 1; t < b0; t++) {
+                const uint64_t x = src[t];
+                uint32_t u = t;
+                while (u > a0 && src[u - 1] > x) { src[u] = src[u - 1]; u--; }
+                src[u] = x;
+            }
+        }
+    }
+    if (ninv) __syncthreads();
+
+    // write back in final order; count key heads and (hash, protein) group heads
     const uint64_t top = tb ? ((uint64_t)b << (64 - tb)) : 0ull;
-    for (uint32_t j = tid; j < m; j += LS_THREADS) {
-        const uint64_t item = src[j];
-        out_hash[s + j] = (top | ((item & ~0xfffull) >> tb)) >> lz;
-        out_loc[s + j] = L[item & 0xfffu];
+    uint32_t tk = 0, tg = 0;
+    for (uint32_t j0 = 0; j0 < m; j0 += LS_THREADS) {
+        const uint32_t j = j0 + tid;
+        bool hk = false, hg = false;
+        if (j < m) {
+            const uint64_t item = src[j];
+            const uint64_t loc = L[item & 0xfffu];
+            out_hash[s + j] = (top | ((item & ~0xfffull) >> tb)) >> lz;
+            out_loc[s + j] = loc;
+            if (j == 0) {
+                hk = hg = true;  // a bucket's first tuple differs from everything before it in its top bits
+            } else {
+                const uint64_t prev = src[j - 1];
+                hk = ((prev ^ item) >> 12) != 0;
+                hg = hk || (uint32_t)(L[prev & 0xfffu] >> 32) != (uint32_t)(loc >> 32);
+            }
+            if (!hg) atomicSub(&t_size[(uint32_t)(loc >> 32)], 1u);
+        }
+        tk += __popc(__ballot_sync(0xffffffffu, hk));
+        tg += __popc(__ballot_sync(0xffffffffu, hg));
+    }
+    if (lane == 0) { s_tk[warp] = tk; s_tg[warp] = tg; }
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t k = 0, g = 0;
+        for (int w = 0; w < LS_WARPS; w++) { k += s_tk[w]; g += s_tg[w]; }
+        counts[b] = (uint64_t)k | ((uint64_t)g << 32);
     }
 }
 
-}  // namespace
+// Counts for ranges the bucket sort did not handle: oversize buckets (only_oversize = 1), or every range on the
+// library-sort path (only_oversize = 0).
+__global__ void __launch_bounds__(256)
+range_count_kernel(const uint64_t* __restrict__ hash, const uint64_t* __restrict__ loc, const uint32_t* __restrict__ start,
+                   int only_oversize, uint64_t* __restrict__ counts, uint32_t* __restrict__ t_size) {
+    __shared__ uint32_t s_tk[8], s_tg[8];
+    const uint32_t b = blockIdx.x;
+    const uint32_t s = start[b], e = start[b + 1];
+    if (only_oversize && e - s <= (uint32_t)LS_CAP) return;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint32_t tk = 0, tg = 0;
+    for (uint32_t i0 = s; i0 < e; i0 += 256) {
+        const uint32_t i = i0 + tid;
+        bool hk = false, hg = false;
+        if (i < e) {
+            const uint64_t h = hash[i];
+            const uint32_t pid = (uint32_t)(loc[i] >> 32);
+            if (i == 0) {
+                hk = hg = true;
+            } else {
+                hk = h != hash[i - 1];
+                hg = hk || pid != (uint32_t)(loc[i - 1] >> 32);
+            }
+            if (!hg) atomicSub(&t_size[pid], 1u);
+        }
+        tk += __popc(__ballot_sync(0xffffffffu, hk));
+        tg += __popc(__ballot_sync(0xffffffffu, hg));
+    }
+    if (lane == 0) { s_tk[warp] = tk; s_tg[warp] = tg; }
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t k = 0, g = 0;
+        for (int w = 0; w < 8; w++) { k += s_tk[w]; g += s_tg[w]; }
+        counts[b] = (uint64_t)k | ((uint64_t)g << 32);
+    }
+}
 
-size_t sort_temp_bytes(uint64_t n, int end_bit) {
-    size_t a = 0, b = 0;
-    cub::DoubleBuffer<uint64_t> k(nullptr, nullptr), v(nullptr, nullptr);
-    cub::DeviceRadixSort::SortPairs(nullptr, a, k, v, (int64_t)n, 0, end_bit);
-    cub::DeviceRadixSort::SortPairs(nullptr, b, (const uint64_t*)nullptr, (uint64_t*)nullptr, (const uint64_t*)nullptr,
-                                    (uint64_t*)nullptr, (int64_t)n, 0, end_bit);
-    size_t table = (((size_t)(1u << 24) + 2 + 1024) * 4 + 255) & ~(size_t)255;
-    if (n < (1ull << 24)) table = (((size_t)n + 4096 + 2 + 1024) * 4 + 255) & ~(size_t)255;
-    return table + (a > b ? a : b) + 256;
+// Exclusive scan of the per-range counts (both 32-bit halves at once), one CTA.  Also writes the totals and
+// the two sentinel entries of the CSR arrays.
+__global__ void __launch_bounds__(1024)
+scan_counts_kernel(const uint64_t* __restrict__ counts, uint32_t nb, uint64_t* __restrict__ prefix, uint64_t n,
+                   uint64_t* __restrict__ d_counts, uint32_t* __restrict__ key_grp, uint32_t* __restrict__ grp_start) {
+    __shared__ uint64_t s_w[32];
+    __shared__ uint64_t s_carry;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < nb; base += 1024) {
+        const uint32_t i = base + tid;
+        const uint64_t v = i < nb ? counts[i] : 0;
+        uint64_t incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint64_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((int)lane >= o) incl += t;
+        }
+        if (lane == 31) s_w[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            uint64_t w = s_w[lane], wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                uint64_t t = __shfl_up_sync(0xffffffffu, wi, o);
+                if ((int)lane >= o) wi += t;
+            }
+            s_w[lane] = wi - w;
+        }
+        __syncthreads();
+        const uint64_t excl = s_carry + s_w[warp] + incl - v;
+        if (i < nb) prefix[i] = excl;
+        __syncthreads();
+        if (tid == 1023) s_carry = excl + v;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        const uint64_t U = s_carry & 0xffffffffu, G = s_carry >> 32;
+        prefix[nb] = s_carry;
+        d_counts[0] = U;
+        d_counts[1] = G;
+        key_grp[U] = (uint32_t)G;
+        grp_start[G] = (uint32_t)n;
+    }
+}
+
+// One CTA per range: recompute the head flags of the sorted tuples and write the CSR arrays at the offsets
+// the scan produced.  Ranges of any length are walked in chunks with a running base.
+constexpr int CW_THREADS = 256;
+constexpr int CW_ROWS = 8;
+__global__ void __launch_bounds__(CW_THREADS)
+csr_write_kernel(const uint64_t* __restrict__ hash, const uint64_t* __restrict__ loc, const uint32_t* __restrict__ start,
+                 const uint64_t* __restrict__ prefix, uint64_t* __restrict__ keys, uint32_t* __restrict__ key_grp,
+                 uint32_t* __restrict__ grp_start) {
+    __shared__ uint32_t s_wk[CW_THREADS / 32], s_wg[CW_THREADS / 32];
+    const uint32_t b = blockIdx.x;
+    const uint32_t s = start[b], e = start[b + 1];
+    if (s == e) return;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint64_t pfx = prefix[b];
+    uint32_t base_k = (uint32_t)pfx, base_g = (uint32_t)(pfx >> 32);
+    const uint32_t lt = (1u << lane) - 1u;
+    for (uint32_t c0 = s; c0 < e; c0 += CW_THREADS * CW_ROWS) {
+        uint64_t h[CW_ROWS];
+        uint32_t bk[CW_ROWS], bg[CW_ROWS];
+        uint32_t wk = 0, wg = 0;
+#pragma unroll
+        for (int r = 0; r < CW_ROWS; r++) {
+            const uint32_t i = c0 + (warp * CW_ROWS + r) * 32 + lane;
+            bool hk = false, hg = false;
+            h[r] = 0;
+            if (i < e) {
+                h[r] = hash[i];
+                if (i == 0) {
+                    hk = hg = true;
+                } else {
+                    hk = h[r] != hash[i - 1];
+                    hg = hk || (uint32_t)(loc[i] >> 32) != (uint32_t)(loc[i - 1] >> 32);
+                }
+            }
+            bk[r] = __ballot_sync(0xffffffffu, hk);
+            bg[r] = __ballot_sync(0xffffffffu, hg);
+            wk += __popc(bk[r]);
+            wg += __popc(bg[r]);
+        }
+        if (lane == 0) { s_wk[warp] = wk; s_wg[warp] = wg; }
+        __syncthreads();
+        uint32_t rk = base_k, rg = base_g;
+#pragma unroll
+        for (int w = 0; w < CW_THREADS / 32; w++) {
+            if (w < (int)warp) { rk += s_wk[w]; rg += s_wg[w]; }
+            base_k += s_wk[w];
+            base_g += s_wg[w];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < CW_ROWS; r++) {
+            const uint32_t i = c0 + (warp * CW_ROWS + r) * 32 + lane;
+            const uint32_t g = rg + __popc(bg[r] & lt);
+            if ((bg[r] >> lane) & 1u) grp_start[g] = i;
+            if ((bk[r] >> lane) & 1u) {
+                const uint32_t u = rk + __popc(bk[r] & lt);
+                keys[u] = h[r];
+                key_grp[u] = g;
+            }
+            rk += __popc(bk[r]);
+            rg += __popc(bg[r]);
+        }
+    }
+}
+
+// dir[b] = index of the first key whose bucket is >= b; dir[2^bits] = U.
+__global__ void dir_kernel(const uint64_t* __restrict__ keys, const uint64_t* __restrict__ d_counts,
+                           uint32_t* __restrict__ dir, int bits, int shift) {
+    const uint64_t U = d_counts[0];
+    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    const uint32_t nb = 1u << bits;
+    if (U == 0) {
+        for (uint64_t b = i; b <= nb; b += (uint64_t)gridDim.x * blockDim.x) dir[b] = 0;
+        return;
+    }
+    if (i >= U) return;
+    const uint32_t b = (uint32_t)(keys[i] >> shift);
+    const int64_t bp = i ? (int64_t)(uint32_t)(keys[i - 1] >> shift) : -1;
+    for (int64_t x = bp + 1; x <= (int64_t)b; x++) dir[x] = (uint32_t)i;
+    if (i == U - 1)
+        for (uint32_t x = b + 1; x <= nb; x++) dir[x] = (uint32_t)U;
 }
 
 int msd_top_bits(uint64_t n, int lz) {
     // smallest tb with n / 2^tb <= 3072 (average bucket; LS_CAP = 4096 leaves > 18 sigma for uniform hashes)
     int tb = 0;
     while (tb < 24 && (n >> tb) > 3072) tb++;
-    if (lz + tb < 12 || lz + tb > 52) return -1;  // index bits would collide with key bits: library sort instead
+    if ((n >> tb) > 3072) return -1;
+    if (lz + tb < 12) return -1;  // index bits would collide with key bits: library sort for all bits instead
     return tb;
 }
 
-static cudaError_t library_sort(uint64_t* hash_a, uint64_t* loc_a, uint64_t* hash_b, uint64_t* loc_b, uint64_t n,
-                                int begin_bit, int end_bit, void* temp, size_t temp_bytes, cudaStream_t stream,
-                                int* out_in_a, uint64_t* n_launches) {
+cudaError_t library_sort(uint64_t* hash_a, uint64_t* loc_a, uint64_t* hash_b, uint64_t* loc_b, uint64_t n, int begin_bit,
+                         int end_bit, void* temp, size_t temp_bytes, cudaStream_t stream, int* out_in_a,
+                         uint64_t* n_launches) {
     cub::DoubleBuffer<uint64_t> k(hash_a, hash_b), v(loc_a, loc_b);
     cudaError_t e = cub::DeviceRadixSort::SortPairs(temp, temp_bytes, k, v, (int64_t)n, begin_bit, end_bit, stream);
     *out_in_a = k.Current() == hash_a ? 1 : 0;
@@ -345,109 +454,119 @@ static cudaError_t library_sort(uint64_t* hash_a, uint64_t* loc_a, uint64_t* has
     return e;
 }
 
-cudaError_t launch_sort(uint64_t* hash_a, uint64_t* loc_a, uint64_t* hash_b, uint64_t* loc_b, uint64_t n, int end_bit,
-                        void* temp, size_t temp_bytes, cudaStream_t stream, int* out_in_a, uint64_t* n_launches) {
-    const int lz = 64 - end_bit;
-    const int tb = msd_top_bits(n, lz);
-    if (tb < 0) return library_sort(hash_a, loc_a, hash_b, loc_b, n, 0, end_bit, temp, temp_bytes, stream, out_in_a, n_launches);
-
-    // 1. partition by the top tb bits (stable): library onesweep passes over those bits only
-    int in_a = 1;
-    cudaError_t e = cudaSuccess;
-    if (tb > 0) {
-        e = library_sort(hash_a, loc_a, hash_b, loc_b, n, end_bit - tb, end_bit, temp, temp_bytes, stream, &in_a, n_launches);
-        if (e != cudaSuccess) return e;
-    }
-    uint64_t* sh = in_a ? hash_a : hash_b;
-    uint64_t* sl = in_a ? loc_a : loc_b;
-    uint64_t* dh = in_a ? hash_b : hash_a;
-    uint64_t* dl = in_a ? loc_b : loc_a;
-    // 2. bucket boundaries, 3. one CTA per bucket sorts it in shared memory
-    const uint32_t nb = 1u << tb;
-    uint32_t* start = (uint32_t*)temp;                 // [nb + 1]
-    uint32_t* oversize = start + nb + 1;               // [0] = count, then up to MAX_OVERSIZE bucket ids
-    constexpr uint32_t MAX_OVERSIZE = 1024;
-    bucket_start_kernel<<<(nb + 1 + 255) / 256, 256, 0, stream>>>(sh, n, lz, tb, start, oversize);
-    oversize_list_kernel<<<(nb + 255) / 256, 256, 0, stream>>>(start, tb, oversize, MAX_OVERSIZE);
-    static bool attr_set = false;
-    if (!attr_set) {
-        e = cudaFuncSetAttribute(bucket_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LS_SMEM);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
-    bucket_sort_kernel<<<nb, LS_THREADS, LS_SMEM, stream>>>(sh, sl, dh, dl, start, lz, tb);
-    e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
-    if (n_launches) *n_launches += 3;
-    // 4. oversize buckets (heavy repeats of few hashes): library sort of the remaining bits, range by range
-    uint32_t h_over[1 + MAX_OVERSIZE];
-    e = cudaMemcpyAsync(h_over, oversize, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream);
-    if (e != cudaSuccess) return e;
-    e = cudaStreamSynchronize(stream);
-    if (e != cudaSuccess) return e;
-    if (h_over[0]) {
-        const uint32_t cnt = h_over[0];
-        std::vector<uint32_t> ids;
-        std::vector<uint32_t> st(nb + 1);
-        e = cudaMemcpy(st.data(), start, (nb + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost);
-        if (e != cudaSuccess) return e;
-        if (cnt <= MAX_OVERSIZE) {
-            ids.resize(cnt);
-            e = cudaMemcpy(ids.data(), oversize + 1, cnt * sizeof(uint32_t), cudaMemcpyDeviceToHost);
-            if (e != cudaSuccess) return e;
-        } else {
-            for (uint32_t b = 0; b < nb; b++) if (st[b + 1] - st[b] > (uint32_t)LS_CAP) ids.push_back(b);
-        }
-        void* big_temp = (char*)temp + (((size_t)(nb + 2 + MAX_OVERSIZE) * 4 + 255) & ~(size_t)255);
-        size_t big_bytes = temp_bytes - ((char*)big_temp - (char*)temp);
-        for (uint32_t b : ids) {
-            const uint64_t s0 = st[b], m = st[b + 1] - st[b];
-            e = cub::DeviceRadixSort::SortPairs(big_temp, big_bytes, sh + s0, dh + s0, sl + s0, dl + s0, (int64_t)m, 0,
-                                                end_bit - tb, stream);
-            if (e != cudaSuccess) return e;
-            if (n_launches) *n_launches += 2 + (end_bit - tb + 7) / 8;
-        }
-    }
-    *out_in_a = in_a ? 0 : 1;
-    return cudaSuccess;
+uint64_t max_ranges(uint64_t n) {
+    uint64_t nb = std::max<uint64_t>(n / 1024 + 2, 4096);  // msd_top_bits: average bucket > 1536
+    nb = std::min<uint64_t>(nb, 1ull << 24);
+    return std::max<uint64_t>(nb, n / LS_CAP + 2);
 }
 
-cudaError_t launch_protein_abund(const uint64_t* loc, uint64_t n, uint32_t n_prot, uint32_t* t_abund, cudaStream_t stream,
-                                 uint64_t* n_launches) {
-    if (n_prot == 0) return cudaSuccess;
-    protein_abund_kernel<<<(n_prot + 255) / 256, 256, 0, stream>>>(loc, n, n_prot, t_abund);
-    if (n_launches) *n_launches += 1;
-    return cudaGetLastError();
+size_t table_bytes(uint64_t n) {
+    // start[nb+1] + oversize[2] (u32), counts[nb] + prefix[nb+1] (u64)
+    const uint64_t nb = max_ranges(n);
+    return (size_t)(((nb + 8) * 4 + (2 * nb + 4) * 8 + 1023) & ~(size_t)255);
 }
 
-size_t csr_workspace_bytes(uint64_t n) { return 16 + ((n + CSR_TILE - 1) / CSR_TILE) * 8 + 16; }
+}  // namespace
 
-cudaError_t launch_csr(const uint64_t* hash, const uint64_t* loc, uint64_t n, uint64_t* keys, uint32_t* key_grp,
-                       uint32_t* grp_start, uint32_t* t_size, uint64_t* d_counts, uint32_t* dir, int dir_bits,
-                       int dir_shift, void* workspace, cudaStream_t stream, uint64_t* n_launches) {
-    cudaError_t e;
+size_t build_temp_bytes(uint64_t n, int end_bit) {
+    size_t a = 0, b = 0;
+    cub::DoubleBuffer<uint64_t> k(nullptr, nullptr), v(nullptr, nullptr);
+    cub::DeviceRadixSort::SortPairs(nullptr, a, k, v, (int64_t)n, 0, end_bit);
+    cub::DeviceRadixSort::SortPairs(nullptr, b, (const uint64_t*)nullptr, (uint64_t*)nullptr, (const uint64_t*)nullptr,
+                                    (uint64_t*)nullptr, (int64_t)n, 0, end_bit);
+    return table_bytes(n) + (a > b ? a : b) + 512;
+}
+
+cudaError_t build_index(const BuildArgs& a, cudaStream_t stream, int* out_in_a, uint64_t* sort_launches,
+                        uint64_t* csr_launches) {
+#define KS_TRY(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return e_; } while (0)
+    const uint64_t n = a.n;
+    const int lz = 64 - a.end_bit;
+    *out_in_a = 1;
+    if (a.n_prot) {
+        protein_abund_kernel<<<(a.n_prot + 255) / 256, 256, 0, stream>>>(a.loc_a, n, a.n_prot, a.t_abund, a.t_size);
+        KS_TRY(cudaGetLastError());
+        *csr_launches += 1;
+    }
     if (n == 0) {
-        e = cudaMemsetAsync(d_counts, 0, 16, stream);
-        if (e != cudaSuccess) return e;
-        e = cudaMemsetAsync(key_grp, 0, 4, stream);
-        if (e != cudaSuccess) return e;
-        e = cudaMemsetAsync(grp_start, 0, 4, stream);
-        if (e != cudaSuccess) return e;
-    } else {
-        const uint64_t nt = (n + CSR_TILE - 1) / CSR_TILE;
-        e = cudaMemsetAsync(workspace, 0, 16 + nt * 8, stream);
-        if (e != cudaSuccess) return e;
-        csr_kernel<<<(unsigned)nt, CSR_THREADS, 0, stream>>>(hash, loc, n, keys, key_grp, grp_start, t_size, d_counts,
-                                                            (uint32_t*)workspace, (uint64_t*)((char*)workspace + 16));
-        e = cudaGetLastError();
-        if (e != cudaSuccess) return e;
-        if (n_launches) *n_launches += 1;
+        KS_TRY(cudaMemsetAsync(a.d_counts, 0, 16, stream));
+        KS_TRY(cudaMemsetAsync(a.key_grp, 0, 4, stream));
+        KS_TRY(cudaMemsetAsync(a.grp_start, 0, 4, stream));
+        if (a.ev_sorted) KS_TRY(cudaEventRecord(a.ev_sorted, stream));
+        dir_kernel<<<1, 256, 0, stream>>>(a.keys, a.d_counts, a.dir, a.dir_bits, a.dir_shift);
+        *csr_launches += 1;
+        return cudaGetLastError();
     }
-    const uint64_t work = n ? n : 1;
-    unsigned blocks = (unsigned)((work + 255) / 256);
-    dir_kernel<<<blocks, 256, 0, stream>>>(keys, d_counts, dir, dir_bits, dir_shift);
-    if (n_launches) *n_launches += 1;
+    // carve temp: [tables | library scratch]
+    const size_t tbytes = table_bytes(n);
+    char* tp = (char*)a.temp;
+    void* lib_temp = tp + tbytes;
+    size_t lib_bytes = a.temp_bytes - tbytes;
+    const int tb = msd_top_bits(n, lz);
+    const uint32_t nb = tb >= 0 ? (1u << tb) : (uint32_t)((n + LS_CAP - 1) / LS_CAP);
+    uint32_t* start = (uint32_t*)tp;                                             // [nb + 1]
+    uint32_t* oversize = start + nb + 1;                                          // [2]
+    uint64_t* counts = (uint64_t*)(tp + (((size_t)(nb + 8) * 4 + 7) & ~(size_t)7));  // [nb]
+    uint64_t* prefix = counts + nb;                                               // [nb + 1]
+
+    const uint64_t *fh, *fl;  // final sorted tuples
+    if (tb < 0) {
+        int in_a = 1;
+        KS_TRY(library_sort(a.hash_a, a.loc_a, a.hash_b, a.loc_b, n, 0, a.end_bit, lib_temp, lib_bytes, stream, &in_a, sort_launches));
+        *out_in_a = in_a;
+        fh = in_a ? a.hash_a : a.hash_b;
+        fl = in_a ? a.loc_a : a.loc_b;
+        if (a.ev_sorted) KS_TRY(cudaEventRecord(a.ev_sorted, stream));
+        fixed_ranges_kernel<<<(nb + 1 + 255) / 256, 256, 0, stream>>>(n, nb, start);
+        range_count_kernel<<<nb, 256, 0, stream>>>(fh, fl, start, 0, counts, a.t_size);
+        KS_TRY(cudaGetLastError());
+        *csr_launches += 2;
+    } else {
+        // 1. partition by the top tb bits (stable): library onesweep passes over those bits only
+        int in_a = 1;
+        if (tb > 0) KS_TRY(library_sort(a.hash_a, a.loc_a, a.hash_b, a.loc_b, n, a.end_bit - tb, a.end_bit, lib_temp, lib_bytes, stream, &in_a, sort_launches));
+        uint64_t* sh = in_a ? a.hash_a : a.hash_b;
+        uint64_t* sl = in_a ? a.loc_a : a.loc_b;
+        uint64_t* dh = in_a ? a.hash_b : a.hash_a;
+        uint64_t* dl = in_a ? a.loc_b : a.loc_a;
+        // 2. bucket boundaries; one CTA per bucket sorts it in shared memory and counts its heads
+        bucket_start_kernel<<<(nb + 1 + 255) / 256, 256, 0, stream>>>(sh, n, lz, tb, start, oversize);
+        oversize_count_kernel<<<(nb + 255) / 256, 256, 0, stream>>>(start, nb, oversize);
+        KS_TRY(cudaFuncSetAttribute(bucket_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LS_SMEM));
+        bucket_sort_kernel<<<nb, LS_THREADS, LS_SMEM, stream>>>(sh, sl, dh, dl, start, lz, tb, counts, a.t_size);
+        KS_TRY(cudaGetLastError());
+        *sort_launches += 3;
+        // 3. oversize buckets (heavy repeats of few hashes): library sort of the remaining bits, range by range
+        uint32_t n_over = 0;
+        KS_TRY(cudaMemcpyAsync(&n_over, oversize, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+        KS_TRY(cudaStreamSynchronize(stream));
+        if (n_over) {
+            std::vector<uint32_t> st(nb + 1);
+            KS_TRY(cudaMemcpyAsync(st.data(), start, (size_t)(nb + 1) * 4, cudaMemcpyDeviceToHost, stream));
+            KS_TRY(cudaStreamSynchronize(stream));
+            for (uint32_t b = 0; b < nb; b++) {
+                const uint64_t s0 = st[b], m = st[b + 1] - st[b];
+                if (m <= (uint64_t)LS_CAP) continue;
+                KS_TRY(cub::DeviceRadixSort::SortPairs(lib_temp, lib_bytes, sh + s0, dh + s0, sl + s0, dl + s0, (int64_t)m, 0,
+                                                       a.end_bit - tb, stream));
+                *sort_launches += 2 + (a.end_bit - tb + 7) / 8;
+            }
+            range_count_kernel<<<nb, 256, 0, stream>>>(dh, dl, start, 1, counts, a.t_size);
+            KS_TRY(cudaGetLastError());
+            *sort_launches += 1;
+        }
+        *out_in_a = in_a ? 0 : 1;
+        fh = dh;
+        fl = dl;
+        if (a.ev_sorted) KS_TRY(cudaEventRecord(a.ev_sorted, stream));
+    }
+    // 4. scan of the range counts, CSR write, directory
+    scan_counts_kernel<<<1, 1024, 0, stream>>>(counts, nb, prefix, n, a.d_counts, a.key_grp, a.grp_start);
+    csr_write_kernel<<<nb, CW_THREADS, 0, stream>>>(fh, fl, start, prefix, a.keys, a.key_grp, a.grp_start);
+    dir_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(a.keys, a.d_counts, a.dir, a.dir_bits, a.dir_shift);
+    *csr_launches += 3;
     return cudaGetLastError();
+#undef KS_TRY
 }
 
 }  // namespace ks

@@ -5,7 +5,7 @@
 
 namespace ks {
 
-constexpr uint64_t MAX_TUPLES = (1ull << 31) - 1;  // per shard: two 31-bit counters share one scan word
+constexpr uint64_t MAX_TUPLES = (1ull << 31) - 1;  // per shard: 32-bit postings offsets, 31-bit scan halves
 
 // Device-resident CSR index over the sorted tuples.
 //   hash[n], loc[n]            tuples ordered by (hash, protein, pos); loc = (protein << 32) | pos
@@ -31,21 +31,28 @@ struct CsrView {
     int dir_shift;
 };
 
-size_t sort_temp_bytes(uint64_t n, int end_bit);
-// Sorts (hash, loc) pairs by hash, stable.  Input in (hash_a, loc_a); result is left in whichever
-// pair *out_in_a says (1 = a, 0 = b).  LSD radix over bits [0, end_bit).
-cudaError_t launch_sort(uint64_t* hash_a, uint64_t* loc_a, uint64_t* hash_b, uint64_t* loc_b, uint64_t n, int end_bit,
-                        void* temp, size_t temp_bytes, cudaStream_t stream, int* out_in_a, uint64_t* n_launches);
+struct BuildArgs {
+    // tuples in (protein, pos) order in the `a` pair; `b` is scratch of the same size.
+    uint64_t *hash_a, *loc_a, *hash_b, *loc_b;
+    uint64_t n;
+    uint32_t n_prot;
+    int end_bit;  // hashes are < 2^end_bit (64 - leading zeros of max_hash)
+    // outputs (device, preallocated): keys[n], key_grp[n+1], grp_start[n+1], t_size[P], t_abund[P], d_counts[2],
+    // dir[2^dir_bits + 1]
+    uint64_t* keys;
+    uint32_t *key_grp, *grp_start, *t_size, *t_abund;
+    uint64_t* d_counts;
+    uint32_t* dir;
+    int dir_bits, dir_shift;
+    void* temp;
+    size_t temp_bytes;
+    cudaEvent_t ev_sorted;  // recorded between the sort and the CSR write (stage timing); may be null
+};
 
-// t_abund[p] = number of tuples of protein pid_base + p in a list ordered by (protein, pos).
-cudaError_t launch_protein_abund(const uint64_t* loc, uint64_t n, uint32_t n_prot, uint32_t* t_abund, cudaStream_t stream,
-                                 uint64_t* n_launches);
-
-size_t csr_workspace_bytes(uint64_t n);
-// Builds keys / key_grp / grp_start / t_size (t_size must hold t_abund on entry: non-head tuples are
-// subtracted) and d_counts from sorted tuples, then the bucket directory.
-cudaError_t launch_csr(const uint64_t* hash, const uint64_t* loc, uint64_t n, uint64_t* keys, uint32_t* key_grp,
-                       uint32_t* grp_start, uint32_t* t_size, uint64_t* d_counts, uint32_t* dir, int dir_bits,
-                       int dir_shift, void* workspace, cudaStream_t stream, uint64_t* n_launches);
+size_t build_temp_bytes(uint64_t n, int end_bit);
+// Sort by hash (stable) + CSR build + directory.  *out_in_a = 1 when the sorted tuples ended in the `a` pair.
+// Synchronises the stream once (oversize-bucket count).  Adds the kernels launched to the two counters.
+cudaError_t build_index(const BuildArgs& a, cudaStream_t stream, int* out_in_a, uint64_t* sort_launches,
+                        uint64_t* csr_launches);
 
 }  // namespace ks
