@@ -7,6 +7,7 @@
 #include <cstring>
 #include <map>
 #include <new>
+#include <time.h>
 
 #include "host_util.hpp"
 #include "index_build.cuh"
@@ -233,6 +234,22 @@ struct DeviceBatch {  // residues + offsets resident in HBM
     bool valid = false;
 };
 
+// Grow-only device buffer: steady-state steps (clear + build again) never go back to the allocator.
+struct Buf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    template <class T>
+    T* ensure(Arena* ar, size_t n) {
+        const size_t need = (n ? n : 1) * sizeof(T);
+        if (need > bytes) {
+            if (p) ar->release(p);
+            p = ar->alloc<char>(need);
+            bytes = need;
+        }
+        return (T*)p;
+    }
+};
+
 uint64_t count_windows(const uint64_t* offs, uint64_t n_prot, uint32_t k) {
     uint64_t w = 0;
     for (uint64_t i = 0; i < n_prot; i++) {
@@ -266,6 +283,7 @@ struct ks_index {
     uint64_t* keys = nullptr;
     uint32_t *key_grp = nullptr, *grp_start = nullptr, *t_size = nullptr, *t_abund = nullptr, *dir = nullptr;
     uint64_t* d_counts = nullptr;
+    Buf b_keys, b_key_grp, b_grp_start, b_t_size, b_t_abund, b_dir, b_counts, b_alt_hash, b_alt_loc, b_temp;
     int dir_bits = 0, dir_shift = 0;
     uint64_t U = 0, G = 0, n_ids = 0;
     // bookkeeping
@@ -308,9 +326,7 @@ void upload_batch(ks_index* x, DeviceBatch& b, const ks_proteome* p) {
     b.valid = true;
 }
 
-void drop_csr(ks_index* x) {
-    void* ptrs[] = {x->keys, x->key_grp, x->grp_start, x->t_size, x->t_abund, x->dir, x->d_counts};
-    for (void* p : ptrs) if (p) x->arena->release(p);
+void drop_csr(ks_index* x) {  // the buffers stay with the handle (grow-only), only the index state is dropped
     x->keys = nullptr; x->key_grp = x->grp_start = x->t_size = x->t_abund = x->dir = nullptr; x->d_counts = nullptr;
     x->finalized = false;
     x->U = x->G = x->n_ids = 0;
@@ -374,8 +390,16 @@ void sketch_resident(ks_index* x) {
     x->n_windows += b.n_windows;
 }
 
+static double now_ms() {
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+
 void finalize(ks_index* x) {
     if (x->finalized) return;
+    const bool dbg = getenv("KS_TIMING") != nullptr;
+    double t0 = dbg ? now_ms() : 0;
     const uint64_t n = x->n_tuples;
     if (n > MAX_TUPLES) fail(KS_ERR_CAPACITY, "more than 2^31-1 tuples on one shard: shard the proteome over more GPUs");
     const uint32_t P = (uint32_t)x->n_prot;
@@ -383,41 +407,44 @@ void finalize(ks_index* x) {
     while (bits < 24 && (4ull << bits) < n) bits++;
     x->dir_bits = bits;
     x->dir_shift = 64 - x->lz - bits;
-    x->t_abund = x->arena->alloc<uint32_t>(P);
-    x->t_size = x->arena->alloc<uint32_t>(P);
-    x->keys = x->arena->alloc<uint64_t>(n);
-    x->key_grp = x->arena->alloc<uint32_t>(n + 1);
-    x->grp_start = x->arena->alloc<uint32_t>(n + 1);
-    x->dir = x->arena->alloc<uint32_t>((1ull << bits) + 1);
-    x->d_counts = x->arena->alloc<uint64_t>(2);
-    uint64_t* hb = x->arena->alloc<uint64_t>(n);
-    uint64_t* lb = x->arena->alloc<uint64_t>(n);
+    Arena* ar = x->arena;
+    x->t_abund = x->b_t_abund.ensure<uint32_t>(ar, P);
+    x->t_size = x->b_t_size.ensure<uint32_t>(ar, P);
+    x->keys = x->b_keys.ensure<uint64_t>(ar, n);
+    x->key_grp = x->b_key_grp.ensure<uint32_t>(ar, n + 1);
+    x->grp_start = x->b_grp_start.ensure<uint32_t>(ar, n + 1);
+    x->dir = x->b_dir.ensure<uint32_t>(ar, (1ull << bits) + 1);
+    x->d_counts = x->b_counts.ensure<uint64_t>(ar, 2);
+    uint64_t* hb = x->b_alt_hash.ensure<uint64_t>(ar, n);
+    uint64_t* lb = x->b_alt_loc.ensure<uint64_t>(ar, n);
     BuildArgs a;
     a.hash_a = x->d_hash; a.loc_a = x->d_loc; a.hash_b = hb; a.loc_b = lb;
     a.n = n; a.n_prot = P; a.end_bit = x->end_bit();
     a.keys = x->keys; a.key_grp = x->key_grp; a.grp_start = x->grp_start; a.t_size = x->t_size; a.t_abund = x->t_abund;
     a.d_counts = x->d_counts; a.dir = x->dir; a.dir_bits = x->dir_bits; a.dir_shift = x->dir_shift;
     a.temp_bytes = build_temp_bytes(n, x->end_bit());
-    a.temp = x->arena->alloc<char>(a.temp_bytes);
+    a.temp = x->b_temp.ensure<char>(ar, a.temp_bytes);
     a.ev_sorted = x->ev[EV_SO1];
     int in_a = 1;
+    double t1 = dbg ? now_ms() : 0;
     KS_CUDA(cudaEventRecord(x->ev[EV_SO0], x->stream));
     KS_CUDA(build_index(a, x->stream, &in_a, &x->l_sort, &x->l_csr));
     KS_CUDA(cudaEventRecord(x->ev[EV_CS1], x->stream));
+    double t2 = dbg ? now_ms() : 0;
     x->t_sort = x->t_csr = true;
-    x->arena->release(a.temp);
-    if (in_a) {
-        x->arena->release(hb); x->arena->release(lb);
-    } else {
-        if (x->d_hash) x->arena->release(x->d_hash);
-        if (x->d_loc) x->arena->release(x->d_loc);
-        x->d_hash = hb; x->d_loc = lb; x->cap = n;
+    if (!in_a) {  // the sorted tuples sit in the alternate pair: swap roles, nothing is freed
+        std::swap(x->d_hash, hb); std::swap(x->d_loc, lb);
+        const size_t cap_bytes = x->cap * 8;
+        x->cap = x->b_alt_hash.bytes / 8;
+        x->b_alt_hash.p = hb; x->b_alt_hash.bytes = cap_bytes;
+        x->b_alt_loc.p = lb; x->b_alt_loc.bytes = cap_bytes;
     }
     uint64_t c[2];
     KS_CUDA(cudaMemcpyAsync(c, x->d_counts, 16, cudaMemcpyDeviceToHost, x->stream));
     KS_CUDA(cudaStreamSynchronize(x->stream));
     x->U = c[0]; x->G = c[1];
     x->finalized = true;
+    if (dbg) fprintf(stderr, "[ks] finalize: alloc %.3f ms, build_index (host) %.3f ms, tail %.3f ms\n", t1 - t0, t2 - t1, now_ms() - t2);
 }
 
 CsrView view_of(const ks_index* x) {

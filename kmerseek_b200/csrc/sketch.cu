@@ -260,12 +260,247 @@ sketch_kernel(SketchArgs a, Lut256 lut, uint32_t* __restrict__ ticket, uint64_t*
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Fast path (k <= 32): every lane owns 4 consecutive windows ("a quad").
+//
+// The 4 + k - 1 bytes of a quad are 4-byte aligned in shared memory, so they are fetched once as whole words
+// and each window is cut out with constant funnel shifts.  MurmurHash3 runs on explicit 32-bit limbs so that a
+// 64-bit multiply by a constant is three IMADs and a 64-bit rotate two SHFs (left to the compiler, the same
+// arithmetic took about twice the instructions, and the kernel is issue-bound before it is HBM-bound).
+// Positions are tile-relative 32-bit values.  Kept tuples are staged in shared memory at their ordered slot;
+// the slot -> address map interleaves the four windows of a quad over four segments so that both the quad
+// writes and the linear read-out are bank-conflict free.
+// ---------------------------------------------------------------------------------------------
+struct L64 { uint32_t lo, hi; };
+
+__device__ __forceinline__ L64 mul_c(L64 a, uint64_t c) {
+    const uint32_t clo = (uint32_t)c, chi = (uint32_t)(c >> 32);
+    uint32_t t = a.lo * chi;
+    t = a.hi * clo + t;
+    const uint64_t p = (uint64_t)a.lo * clo + ((uint64_t)t << 32);
+    return {(uint32_t)p, (uint32_t)(p >> 32)};
+}
+__device__ __forceinline__ L64 rotl_c(L64 a, int r) {  // 0 < r < 64, r != 32
+    if (r < 32) return {__funnelshift_l(a.hi, a.lo, r), __funnelshift_l(a.lo, a.hi, r)};
+    return {__funnelshift_l(a.lo, a.hi, r - 32), __funnelshift_l(a.hi, a.lo, r - 32)};
+}
+__device__ __forceinline__ L64 xor_(L64 a, L64 b) { return {a.lo ^ b.lo, a.hi ^ b.hi}; }
+__device__ __forceinline__ L64 add_(L64 a, L64 b) {
+    const uint64_t s = (((uint64_t)a.hi << 32) | a.lo) + (((uint64_t)b.hi << 32) | b.lo);
+    return {(uint32_t)s, (uint32_t)(s >> 32)};
+}
+__device__ __forceinline__ L64 mul5_add(L64 a, uint32_t c) {  // a * 5 + c
+    const uint64_t p = (uint64_t)a.lo * 5u + c;
+    return {(uint32_t)p, (uint32_t)(p >> 32) + a.hi * 5u};
+}
+__device__ __forceinline__ L64 fmix_l(L64 k) {
+    k.lo ^= k.hi >> 1;  // k ^= k >> 33
+    k = mul_c(k, 0xff51afd7ed558ccdULL);
+    k.lo ^= k.hi >> 1;
+    k = mul_c(k, 0xc4ceb9fe1a85ec53ULL);
+    k.lo ^= k.hi >> 1;
+    return k;
+}
+__device__ __forceinline__ L64 mix1(L64 k) { return mul_c(rotl_c(mul_c(k, C1), 31), C2); }
+__device__ __forceinline__ L64 mix2(L64 k) { return mul_c(rotl_c(mul_c(k, C2), 33), C1); }
+
+template <int K>
+__device__ __forceinline__ uint64_t murmur_limbs(const uint32_t* a) {
+    // a[] = the K translated bytes, little-endian packed, bytes past K zeroed.
+    constexpr int NB = K / 16, REM = K % 16, NWORDS = (K + 3) / 4;
+    L64 h1 = {(uint32_t)SEED, 0}, h2 = {(uint32_t)SEED, 0};
+#pragma unroll
+    for (int b = 0; b < NB; b++) {
+        h1 = xor_(h1, mix1({a[4 * b], a[4 * b + 1]}));
+        h1 = add_(rotl_c(h1, 27), h2);
+        h1 = mul5_add(h1, 0x52dce729u);
+        h2 = xor_(h2, mix2({a[4 * b + 2], a[4 * b + 3]}));
+        h2 = add_(rotl_c(h2, 31), h1);
+        h2 = mul5_add(h2, 0x38495ab5u);
+    }
+    auto word = [&](int i) -> uint32_t { return i < NWORDS ? a[i] : 0u; };
+    if (REM > 8) h2 = xor_(h2, mix2({word(4 * NB + 2), word(4 * NB + 3)}));
+    if (REM > 0) h1 = xor_(h1, mix1({word(4 * NB), word(4 * NB + 1)}));
+    h1.lo ^= (uint32_t)K;
+    h2.lo ^= (uint32_t)K;
+    h1 = add_(h1, h2);
+    h2 = add_(h2, h1);
+    h1 = fmix_l(h1);
+    h2 = fmix_l(h2);
+    h1 = add_(h1, h2);
+    return ((uint64_t)h1.hi << 32) | h1.lo;
+}
+
+constexpr int SQ_ROWS = SK_TILE / (SK_THREADS * 4);   // quad rows per warp (2)
+constexpr int SQ_SEG = SK_TILE / 4 + 4;                // staging segment stride in slots: = 4 (mod 16)
+__device__ __forceinline__ uint32_t stage_addr(uint32_t slot) { return (slot & 3u) * SQ_SEG + (slot >> 2); }
+
+template <int K, bool TRANSLATE, bool FULL>
+__global__ void __launch_bounds__(SK_THREADS)
+sketch_quad_kernel(SketchArgs a, Lut256 lut, uint32_t* __restrict__ ticket, uint64_t* __restrict__ status,
+                   const uint32_t* __restrict__ tile_pid) {
+    constexpr int RES_WORDS = (SK_TILE + K + 16 + 3) / 4;
+    constexpr int NW = (K + 3 + 3) / 4;  // words that cover the 4 + K - 1 bytes of a quad
+    constexpr int KW = (K + 3) / 4;
+    __shared__ __align__(16) uint32_t s_res[RES_WORDS];
+    __shared__ __align__(16) uint64_t s_hash[4 * SQ_SEG];
+    __shared__ __align__(16) uint64_t s_loc[4 * SQ_SEG];
+    __shared__ uint64_t s_offs[OFFS_CACHE];
+    __shared__ uint8_t s_lut[256];
+    __shared__ uint32_t s_wtot[SK_THREADS / 32];
+    __shared__ uint32_t s_tile;
+    __shared__ uint64_t s_base;
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+    if (TRANSLATE) s_lut[tid] = lut.b[tid];
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const uint64_t g0 = (uint64_t)tile * SK_TILE;
+    const uint64_t n_tiles = n_tiles_of(a.n_res);
+    const uint32_t p_lo = tile_pid[tile], p_hi = tile_pid[tile + 1];
+    const uint32_t n_off = p_hi - p_lo + 2;
+    const bool cached = n_off <= OFFS_CACHE;
+    if (cached)
+        for (uint32_t i = tid; i < n_off; i += SK_THREADS) s_offs[i] = a.offsets[p_lo + i];
+    {
+        constexpr uint32_t n_chunks = (SK_TILE + K - 1 + 15) / 16;
+        if (tid < n_chunks) {
+            const uint64_t g = g0 + 16ull * tid;
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (g < a.n_res) v = __ldg(reinterpret_cast<const uint4*>(a.residues + g));
+            if (TRANSLATE) {
+                uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const uint32_t x = w[i];
+                    w[i] = (uint32_t)s_lut[x & 0xff] | ((uint32_t)s_lut[(x >> 8) & 0xff] << 8) |
+                           ((uint32_t)s_lut[(x >> 16) & 0xff] << 16) | ((uint32_t)s_lut[x >> 24] << 24);
+                }
+                v = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+            reinterpret_cast<uint4*>(s_res)[tid] = v;
+        }
+    }
+    __syncthreads();
+
+    const uint64_t* offs = cached ? (const uint64_t*)s_offs - p_lo : a.offsets;
+    const uint64_t left = a.n_res - g0;
+    const uint32_t nres_rel = left > 0x40000000ull ? 0x40000000u : (uint32_t)left;  // residues from the tile start on
+    auto rel = [&](uint64_t o) -> uint32_t {  // protein end, relative to the tile start, clamped
+        const uint64_t d = o - g0;
+        return d > 0x7fffffffull ? 0x7fffffffu : (uint32_t)d;
+    };
+
+    uint32_t p = p_lo, pstart_lo = 0, pend_rel = 0;
+    const uint32_t w_first = (warp * SQ_ROWS * 32 + lane) * 4;
+    if (w_first < nres_rel) {
+        const uint64_t g = g0 + w_first;
+        uint32_t lo = p_lo, hi = p_hi;
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi + 1) >> 1;
+            if (offs[mid] <= g) lo = mid; else hi = mid - 1;
+        }
+        p = lo;
+        pstart_lo = (uint32_t)offs[p];
+        pend_rel = rel(offs[p + 1]);
+    }
+
+    const uint32_t lt = (1u << lane) - 1u;
+    const uint32_t g0_lo = (uint32_t)g0;
+    uint32_t wcount = 0;  // tuples staged by this warp so far (uniform across the warp)
+#pragma unroll
+    for (int rr = 0; rr < SQ_ROWS; rr++) {
+        const uint32_t q = (warp * SQ_ROWS + rr) * 32 + lane;
+        uint32_t x[NW + 1];
+#pragma unroll
+        for (int i = 0; i < NW; i++) x[i] = s_res[q + i];
+        x[NW] = 0;
+        uint64_t h[4], loc[4];
+        bool keep[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint32_t w = q * 4 + j;
+            bool valid = false;
+            if (w < nres_rel) {
+                while (w >= pend_rel) { p++; pstart_lo = (uint32_t)offs[p]; pend_rel = rel(offs[p + 1]); }
+                valid = w + K <= pend_rel;
+            }
+            uint32_t b[KW];
+#pragma unroll
+            for (int i = 0; i < KW; i++) b[i] = j == 0 ? x[i] : __funnelshift_r(x[i], x[i + 1], 8 * j);
+            if (K % 4) b[KW - 1] &= (1u << (8 * (K % 4))) - 1u;
+            h[j] = murmur_limbs<K>(b);
+            keep[j] = valid && h[j] != 0 && (FULL || h[j] <= a.max_hash);
+            loc[j] = ((uint64_t)(a.pid_base + p) << 32) | (uint64_t)(g0_lo + w - pstart_lo);
+        }
+        uint32_t below = 0, total = 0;
+        uint32_t bal[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            bal[j] = __ballot_sync(0xffffffffu, keep[j]);
+            below += __popc(bal[j] & lt);
+            total += __popc(bal[j]);
+        }
+        uint32_t slot = warp * (SK_TILE / (SK_THREADS / 32)) + wcount + below;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            if (keep[j]) {
+                const uint32_t ad = stage_addr(slot);
+                s_hash[ad] = h[j];
+                s_loc[ad] = loc[j];
+                slot++;
+            }
+        }
+        wcount += total;
+    }
+
+    if (lane == 0) s_wtot[warp] = wcount;
+    __syncthreads();
+    uint32_t wprefix = 0, btotal = 0;
+#pragma unroll
+    for (int i = 0; i < SK_THREADS / 32; i++) {
+        const uint32_t t = s_wtot[i];
+        if (i < (int)warp) wprefix += t;
+        btotal += t;
+    }
+    if (warp == 0) {
+        const uint64_t excl = scan_lookback(status, tile, btotal);
+        if (lane == 0) {
+            s_base = excl;
+            if (tile == n_tiles - 1) *a.d_count = excl + btotal;
+        }
+    }
+    __syncthreads();
+    const uint64_t base = s_base + wprefix;
+    const uint32_t sbase = warp * (SK_TILE / (SK_THREADS / 32));
+    for (uint32_t i = lane; i < wcount; i += 32) {
+        if (base + i < a.capacity) {
+            const uint32_t ad = stage_addr(sbase + i);
+            a.out_hash[base + i] = s_hash[ad];
+            a.out_loc[base + i] = s_loc[ad];
+        }
+    }
+}
+
 template <int K>
 cudaError_t launch_k(const SketchArgs& a, const Lut256& lut, const Workspace& w, uint64_t n_tiles, cudaStream_t st) {
-    if (a.moltype == 0)
-        sketch_kernel<K, false><<<(unsigned)n_tiles, SK_THREADS, 0, st>>>(a, lut, w.ticket, w.status, w.tile_pid);
-    else
-        sketch_kernel<K, true><<<(unsigned)n_tiles, SK_THREADS, 0, st>>>(a, lut, w.ticket, w.status, w.tile_pid);
+    const unsigned grid = (unsigned)n_tiles;
+    if constexpr (K == 0) {
+        if (a.moltype == 0)
+            sketch_kernel<0, false><<<grid, SK_THREADS, 0, st>>>(a, lut, w.ticket, w.status, w.tile_pid);
+        else
+            sketch_kernel<0, true><<<grid, SK_THREADS, 0, st>>>(a, lut, w.ticket, w.status, w.tile_pid);
+    } else {
+        const bool full = a.max_hash == ~0ull;
+        if (a.moltype == 0) {
+            if (full) sketch_quad_kernel<K, false, true><<<grid, SK_THREADS, 0, st>>>(a, lut, w.ticket, w.status, w.tile_pid);
+            else sketch_quad_kernel<K, false, false><<<grid, SK_THREADS, 0, st>>>(a, lut, w.ticket, w.status, w.tile_pid);
+        } else {
+            if (full) sketch_quad_kernel<K, true, true><<<grid, SK_THREADS, 0, st>>>(a, lut, w.ticket, w.status, w.tile_pid);
+            else sketch_quad_kernel<K, true, false><<<grid, SK_THREADS, 0, st>>>(a, lut, w.ticket, w.status, w.tile_pid);
+        }
+    }
     return cudaGetLastError();
 }
 
