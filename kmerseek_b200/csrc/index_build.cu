@@ -152,12 +152,19 @@ bucket_sort_kernel(const uint64_t* __restrict__ in_hash, const uint64_t* __restr
             info[r] = 0;
             if (r < R) {
                 const uint32_t d = (uint32_t)(src[(warp * R + r) * 32 + lane] >> dshift) & 255u;
-                uint32_t peers = 0xffffffffu;
+                // lanes of the row that share the digit: MATCH.ANY (ADU pipe, ~40 cycles per warp) in the first
+                // pass, 8 ballots (ALU pipe) in the second, so that neither pipe carries both passes
+                uint32_t peers;
+                if (pass == 0) {
+                    peers = __match_any_sync(0xffffffffu, d);
+                } else {
+                    peers = 0xffffffffu;
 #pragma unroll
-                for (int bit = 0; bit < 8; bit++) {
-                    const bool on = (d >> bit) & 1u;
-                    const uint32_t v = __ballot_sync(0xffffffffu, on);
-                    peers &= on ? v : ~v;
+                    for (int bit = 0; bit < 8; bit++) {
+                        const bool on = (d >> bit) & 1u;
+                        const uint32_t v = __ballot_sync(0xffffffffu, on);
+                        peers &= on ? v : ~v;
+                    }
                 }
                 const uint32_t rank = __popc(peers & lt), size = __popc(peers);
                 if (rank == 0) my[d] += (uint16_t)size;
@@ -207,34 +214,93 @@ bucket_sort_kernel(const uint64_t* __restrict__ in_hash, const uint64_t* __restr
         __syncthreads();
         uint64_t* t = src; src = dst; dst = t;
     }
-    // src == A.  Items are ordered by the 16 digit bits; list the inversions inside runs that share them.
-    uint32_t* inv = reinterpret_cast<uint32_t*>(B);
-    for (uint32_t j = tid + 1; j < m; j += LS_THREADS) {
-        const uint64_t a = src[j - 1], c = src[j];
-        if (((a ^ c) >> 48) == 0 && a > c) inv[atomicAdd(&s_ninv, 1u)] = j;
-    }
-    __syncthreads();
-    const uint32_t ninv = s_ninv;
-    for (uint32_t k = tid; k < ninv; k += LS_THREADS) {
-        const uint32_t j = inv[k];
-        const uint64_t pj = src[j] >> 48;
-        uint32_t a0 = j - 1;
-        while (a0 > 0 && (src[a0 - 1] >> 48) == pj) a0--;
-        bool first = true;  // one thread per run: the one that holds the run's first inversion
-        for (uint32_t t = a0 + 1; t < j; t++)
-            if (src[t - 1] > src[t]) { first = false; break; }
-        if (first) {
-            uint32_t b0 = j + 1;
-            while (b0 < m && (src[b0] >> 48) == pj) b0++;
-            for (uint32_t t = a0 + 1; t < b0; t++) {
-                const uint64_t x = src[t];
-                uint32_t u = t;
-                while (u > a0 && src[u - 1] > x) { src[u] = src[u - 1]; u--; }
-                src[u] = x;
+    // src == A.  Items are ordered by the 16 digit bits.  Runs that share those bits and hold an inversion are
+    // re-ranked by a warp each: every lane counts the run's items below its own (items are distinct).
+    uint32_t* headmap = reinterpret_cast<uint32_t*>(B);  // bit j: item j starts a run        [padded / 32 words]
+    uint32_t* dirty = headmap + LS_CAP / 32;              // bit j: the run that starts at j has an inversion
+    uint32_t* runs = dirty + LS_CAP / 32;                 // run starts to fix                  [<= m]
+    for (uint32_t j = tid; j < padded; j += LS_THREADS) {
+        bool head = false, inv = false;
+        if (j < m) {
+            const uint64_t c = src[j];
+            if (j == 0) head = true;
+            else {
+                const uint64_t a = src[j - 1];
+                head = ((a ^ c) >> 48) != 0;
+                inv = !head && a > c;
             }
         }
+        const uint32_t hb = __ballot_sync(0xffffffffu, head);
+        const uint32_t ib = __ballot_sync(0xffffffffu, inv);
+        if (lane == 0) { headmap[j >> 5] = hb; dirty[j >> 5] = 0; }
+        if (ib && lane == 0) atomicAdd(&s_ninv, 1u);
     }
-    if (ninv) __syncthreads();
+    __syncthreads();
+    const uint32_t any_inv = s_ninv;
+    __syncthreads();
+    if (any_inv) {  // uniform
+        if (tid == 0) s_ninv = 0;
+        __syncthreads();
+        // mark the run of every inversion: its start is the last head bit at or below j
+        for (uint32_t j = tid + 1; j < m; j += LS_THREADS) {
+            const uint64_t a = src[j - 1], c = src[j];
+            if (((a ^ c) >> 48) == 0 && a > c) {
+                uint32_t w = j >> 5;
+                uint32_t bits = headmap[w] & (0xffffffffu >> (31 - (j & 31)));
+                while (bits == 0) bits = headmap[--w];
+                const uint32_t st = (w << 5) + 31 - __clz(bits);
+                atomicOr(&dirty[st >> 5], 1u << (st & 31));
+            }
+        }
+        __syncthreads();
+        for (uint32_t w = tid; w < padded / 32; w += LS_THREADS) {
+            uint32_t bits = dirty[w];
+            while (bits) {
+                const uint32_t bpos = __ffs(bits) - 1;
+                bits &= bits - 1;
+                runs[atomicAdd(&s_ninv, 1u)] = (w << 5) + bpos;
+            }
+        }
+        __syncthreads();
+        const uint32_t nruns = s_ninv;
+        for (uint32_t k = warp; k < nruns; k += LS_WARPS) {
+            const uint32_t a0 = runs[k];
+            // run end: next head bit after a0 (or m)
+            uint32_t w = a0 >> 5;
+            uint32_t bits = (a0 & 31) == 31 ? 0u : (headmap[w] & (0xffffffffu << ((a0 & 31) + 1)));
+            while (bits == 0 && ++w < padded / 32) bits = headmap[w];
+            uint32_t b0 = bits ? (w << 5) + __ffs(bits) - 1 : m;
+            if (b0 > m) b0 = m;
+            const uint32_t r = b0 - a0;
+            if (r <= 128) {
+                uint64_t mine[4];
+                uint32_t rank[4];
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const uint32_t t = a0 + lane + 32 * q;
+                    mine[q] = t < b0 ? src[t] : ~0ull;
+                    rank[q] = 0;
+                }
+                for (uint32_t t = a0; t < b0; t++) {
+                    const uint64_t x = src[t];
+#pragma unroll
+                    for (int q = 0; q < 4; q++) rank[q] += x < mine[q];
+                }
+                __syncwarp();
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                    if (a0 + lane + 32 * q < b0) src[a0 + rank[q]] = mine[q];
+            } else if (lane == 0) {  // long mixed run (pathological input): insertion sort by one thread
+                for (uint32_t t = a0 + 1; t < b0; t++) {
+                    const uint64_t x = src[t];
+                    uint32_t u = t;
+                    while (u > a0 && src[u - 1] > x) { src[u] = src[u - 1]; u--; }
+                    src[u] = x;
+                }
+            }
+        }
+        __syncthreads();
+    }
 
     // write back in final order; count key heads and (hash, protein) group heads
     const uint64_t top = tb ? ((uint64_t)b << (64 - tb)) : 0ull;
@@ -242,17 +308,23 @@ bucket_sort_kernel(const uint64_t* __restrict__ in_hash, const uint64_t* __restr
     for (uint32_t j0 = 0; j0 < m; j0 += LS_THREADS) {
         const uint32_t j = j0 + tid;
         bool hk = false, hg = false;
+        uint64_t item = 0, loc = 0;
         if (j < m) {
-            const uint64_t item = src[j];
-            const uint64_t loc = L[item & 0xfffu];
+            item = src[j];
+            loc = L[item & 0xfffu];
+        }
+        // the predecessor sits in the lane below; lane 0 looks it up
+        uint64_t prev = __shfl_up_sync(0xffffffffu, item, 1);
+        uint32_t ppid = __shfl_up_sync(0xffffffffu, (uint32_t)(loc >> 32), 1);
+        if (j < m) {
             out_hash[s + j] = (top | ((item & ~0xfffull) >> tb)) >> lz;
             out_loc[s + j] = loc;
             if (j == 0) {
                 hk = hg = true;  // a bucket's first tuple differs from everything before it in its top bits
             } else {
-                const uint64_t prev = src[j - 1];
+                if (lane == 0) { prev = src[j - 1]; ppid = (uint32_t)(L[prev & 0xfffu] >> 32); }
                 hk = ((prev ^ item) >> 12) != 0;
-                hg = hk || (uint32_t)(L[prev & 0xfffu] >> 32) != (uint32_t)(loc >> 32);
+                hg = hk || ppid != (uint32_t)(loc >> 32);
             }
             if (!hg) atomicSub(&t_size[(uint32_t)(loc >> 32)], 1u);
         }
@@ -354,7 +426,7 @@ scan_counts_kernel(const uint64_t* __restrict__ counts, uint32_t nb, uint64_t* _
 
 // One CTA per range: recompute the head flags of the sorted tuples and write the CSR arrays at the offsets
 // the scan produced.  Ranges of any length are walked in chunks with a running base.
-constexpr int CW_THREADS = 256;
+constexpr int CW_THREADS = 384;  // 384 x 8 = 3072 tuples per chunk: an average bucket in one chunk
 constexpr int CW_ROWS = 8;
 __global__ void __launch_bounds__(CW_THREADS)
 csr_write_kernel(const uint64_t* __restrict__ hash, const uint64_t* __restrict__ loc, const uint32_t* __restrict__ start,
@@ -377,13 +449,17 @@ csr_write_kernel(const uint64_t* __restrict__ hash, const uint64_t* __restrict__
             const uint32_t i = c0 + (warp * CW_ROWS + r) * 32 + lane;
             bool hk = false, hg = false;
             h[r] = 0;
+            uint32_t pid = 0;
+            if (i < e) { h[r] = hash[i]; pid = (uint32_t)(loc[i] >> 32); }
+            uint64_t hp = __shfl_up_sync(0xffffffffu, h[r], 1);
+            uint32_t pp = __shfl_up_sync(0xffffffffu, pid, 1);
             if (i < e) {
-                h[r] = hash[i];
                 if (i == 0) {
                     hk = hg = true;
                 } else {
-                    hk = h[r] != hash[i - 1];
-                    hg = hk || (uint32_t)(loc[i] >> 32) != (uint32_t)(loc[i - 1] >> 32);
+                    if (lane == 0) { hp = hash[i - 1]; pp = (uint32_t)(loc[i - 1] >> 32); }
+                    hk = h[r] != hp;
+                    hg = hk || pid != pp;
                 }
             }
             bk[r] = __ballot_sync(0xffffffffu, hk);
