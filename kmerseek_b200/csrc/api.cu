@@ -362,11 +362,16 @@ uint64_t run_sketch(ks_index* x, const DeviceBatch& b, uint32_t pid_base, uint64
     a.residues = b.res; a.offsets = b.offs; a.n_res = b.n_res; a.n_prot = b.n_prot;
     a.k = x->params.ksize; a.moltype = x->params.moltype; a.max_hash = x->max_hash; a.pid_base = pid_base;
     a.out_hash = out_hash; a.out_loc = out_loc; a.capacity = capacity; a.d_count = x->d_count; a.workspace = x->ws;
-    KS_CUDA(launch_sketch(a, x->stream, &x->l_sketch));
-    uint64_t n = 0;
-    KS_CUDA(cudaMemcpyAsync(&n, x->d_count, 8, cudaMemcpyDeviceToHost, x->stream));
-    KS_CUDA(cudaStreamSynchronize(x->stream));
-    return n;
+    a.force_general = getenv("KS_SKETCH_GENERAL") ? 1 : 0;  // test hook: exercise the look-back path at scaled == 1
+    uint64_t r[2] = {0, 0};
+    for (int attempt = 0; attempt < 2; attempt++) {
+        KS_CUDA(launch_sketch(a, x->stream, &x->l_sketch));
+        KS_CUDA(cudaMemcpyAsync(r, x->d_count, 16, cudaMemcpyDeviceToHost, x->stream));
+        KS_CUDA(cudaStreamSynchronize(x->stream));
+        if ((r[1] >> 32) == 0) break;  // no zero hash on the exact path
+        a.force_general = 1;           // a hash of exactly 0 must be dropped: redo on the look-back path
+    }
+    return r[0];
 }
 
 void sketch_resident(ks_index* x) {
@@ -419,7 +424,7 @@ void finalize(ks_index* x) {
     uint64_t* lb = x->b_alt_loc.ensure<uint64_t>(ar, n);
     BuildArgs a;
     a.hash_a = x->d_hash; a.loc_a = x->d_loc; a.hash_b = hb; a.loc_b = lb;
-    a.n = n; a.n_prot = P; a.end_bit = x->end_bit();
+    a.n = n; a.n_prot = P; a.end_bit = x->end_bit(); a.max_hash = x->max_hash;
     a.keys = x->keys; a.key_grp = x->key_grp; a.grp_start = x->grp_start; a.t_size = x->t_size; a.t_abund = x->t_abund;
     a.d_counts = x->d_counts; a.dir = x->dir; a.dir_bits = x->dir_bits; a.dir_shift = x->dir_shift;
     a.temp_bytes = build_temp_bytes(n, x->end_bit());
@@ -521,7 +526,7 @@ ks_status ks_index_create(const ks_params* params, ks_index** out) {
             uint64_t thr = UINT64_MAX;  // keep freed blocks in the pool: steady-state steps never reach the driver
             KS_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
             x->arena = new Arena(x->stream, &x->live_bytes);
-            x->d_count = x->arena->alloc<uint64_t>(1);
+            x->d_count = x->arena->alloc<uint64_t>(2);
         } catch (...) {
             ks_index_destroy(x);
             throw;

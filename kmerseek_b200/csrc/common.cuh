@@ -41,12 +41,12 @@ __device__ __forceinline__ void st_relaxed(uint64_t* p, uint64_t v) {
 }
 
 // Called by ONE full warp of the tile.  Publishes this tile's aggregate, walks back over the
-// predecessors' words 128 at a time (4 per lane, independent loads), returns the exclusive prefix (same
+// predecessors' words 64 at a time (2 per lane, independent loads), returns the exclusive prefix (same
 // value in every lane) and publishes the inclusive prefix.  `value` must be < 2^62.
 // The window is wide on purpose: with hundreds of tiles in flight none of a tile's near predecessors has
 // a prefix yet, and every 32-wide round would cost a full L2 round trip.
 __device__ __forceinline__ uint64_t scan_lookback(uint64_t* status, uint32_t tile, uint64_t value) {
-    constexpr int W = 4;
+    constexpr int W = 2;
     const uint32_t lane = threadIdx.x & 31;
     if (tile == 0) {
         if (lane == 0) st_relaxed(status, SCAN_PFX | value);
@@ -59,7 +59,10 @@ __device__ __forceinline__ uint64_t scan_lookback(uint64_t* status, uint32_t til
         // lane l looks at predecessors base - (l*W + j), j = 0..W-1: distance grows with (lane, j)
         uint64_t w[W];
         bool ready;
+        bool first_poll = true;
         do {
+            if (!first_poll) __nanosleep(100);  // leave the issue slots to the warps that still hash
+            first_poll = false;
             ready = true;
 #pragma unroll
             for (int j = 0; j < W; j++) {

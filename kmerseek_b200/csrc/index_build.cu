@@ -17,6 +17,7 @@
 #include <cub/device/device_radix_sort.cuh>
 
 #include <algorithm>
+#include <cmath>
 #include <vector>
 
 #include "common.cuh"
@@ -493,29 +494,33 @@ csr_write_kernel(const uint64_t* __restrict__ hash, const uint64_t* __restrict__
     }
 }
 
-// dir[b] = index of the first key whose bucket is >= b; dir[2^bits] = U.
+// dir[b] = index of the first key whose bucket is >= b; dir[2^bits] = U.  Grid-stride: U is only known on the device.
 __global__ void dir_kernel(const uint64_t* __restrict__ keys, const uint64_t* __restrict__ d_counts,
                            uint32_t* __restrict__ dir, int bits, int shift) {
     const uint64_t U = d_counts[0];
-    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t i0 = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     const uint32_t nb = 1u << bits;
     if (U == 0) {
-        for (uint64_t b = i; b <= nb; b += (uint64_t)gridDim.x * blockDim.x) dir[b] = 0;
+        for (uint64_t b = i0; b <= nb; b += stride) dir[b] = 0;
         return;
     }
-    if (i >= U) return;
-    const uint32_t b = (uint32_t)(keys[i] >> shift);
-    const int64_t bp = i ? (int64_t)(uint32_t)(keys[i - 1] >> shift) : -1;
-    for (int64_t x = bp + 1; x <= (int64_t)b; x++) dir[x] = (uint32_t)i;
-    if (i == U - 1)
-        for (uint32_t x = b + 1; x <= nb; x++) dir[x] = (uint32_t)U;
+    for (uint64_t i = i0; i < U; i += stride) {
+        const uint32_t b = (uint32_t)(keys[i] >> shift);
+        const int64_t bp = i ? (int64_t)(uint32_t)(keys[i - 1] >> shift) : -1;
+        for (int64_t x = bp + 1; x <= (int64_t)b; x++) dir[x] = (uint32_t)i;
+        if (i == U - 1)
+            for (uint32_t x = b + 1; x <= nb; x++) dir[x] = (uint32_t)U;
+    }
 }
 
-int msd_top_bits(uint64_t n, int lz) {
-    // smallest tb with n / 2^tb <= 3072 (average bucket; LS_CAP = 4096 leaves > 18 sigma for uniform hashes)
+int msd_top_bits(uint64_t n, int lz, uint64_t max_hash) {
+    // smallest tb whose average bucket is <= 3072 tuples (LS_CAP = 4096 leaves > 18 sigma for uniform hashes).
+    // Hashes fill only [0, max_hash] of the 2^(64-lz) range the buckets span, so the used buckets are fuller.
+    const double fill = lz >= 64 ? 1.0 : ((double)max_hash + 1.0) / std::ldexp(1.0, 64 - lz);
     int tb = 0;
-    while (tb < 24 && (n >> tb) > 3072) tb++;
-    if ((n >> tb) > 3072) return -1;
+    while (tb < 24 && (double)n / (std::ldexp(1.0, tb) * fill) > 3072.0) tb++;
+    if ((double)n / (std::ldexp(1.0, tb) * fill) > 3072.0) return -1;
     if (lz + tb < 12) return -1;  // index bits would collide with key bits: library sort for all bits instead
     return tb;
 }
@@ -531,7 +536,7 @@ cudaError_t library_sort(uint64_t* hash_a, uint64_t* loc_a, uint64_t* hash_b, ui
 }
 
 uint64_t max_ranges(uint64_t n) {
-    uint64_t nb = std::max<uint64_t>(n / 1024 + 2, 4096);  // msd_top_bits: average bucket > 1536
+    uint64_t nb = std::max<uint64_t>(n / 512 + 2, 4096);  // msd_top_bits: average used bucket > 1536, fill > 0.5
     nb = std::min<uint64_t>(nb, 1ull << 24);
     return std::max<uint64_t>(nb, n / LS_CAP + 2);
 }
@@ -578,7 +583,7 @@ cudaError_t build_index(const BuildArgs& a, cudaStream_t stream, int* out_in_a, 
     char* tp = (char*)a.temp;
     void* lib_temp = tp + tbytes;
     size_t lib_bytes = a.temp_bytes - tbytes;
-    const int tb = msd_top_bits(n, lz);
+    const int tb = msd_top_bits(n, lz, a.max_hash);
     const uint32_t nb = tb >= 0 ? (1u << tb) : (uint32_t)((n + LS_CAP - 1) / LS_CAP);
     uint32_t* start = (uint32_t*)tp;                                             // [nb + 1]
     uint32_t* oversize = start + nb + 1;                                          // [2]
@@ -639,7 +644,7 @@ cudaError_t build_index(const BuildArgs& a, cudaStream_t stream, int* out_in_a, 
     // 4. scan of the range counts, CSR write, directory
     scan_counts_kernel<<<1, 1024, 0, stream>>>(counts, nb, prefix, n, a.d_counts, a.key_grp, a.grp_start);
     csr_write_kernel<<<nb, CW_THREADS, 0, stream>>>(fh, fl, start, prefix, a.keys, a.key_grp, a.grp_start);
-    dir_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(a.keys, a.d_counts, a.dir, a.dir_bits, a.dir_shift);
+    dir_kernel<<<148 * 8, 256, 0, stream>>>(a.keys, a.d_counts, a.dir, a.dir_bits, a.dir_shift);
     *csr_launches += 3;
     return cudaGetLastError();
 #undef KS_TRY

@@ -16,6 +16,8 @@
 // chained across CTAs with a single-pass decoupled look-back, after which every warp streams its staged
 // tuples to their final, globally ordered position with fully coalesced stores.  Output order is
 // (protein, pos), independent of scheduling, so the later stable sort by hash is deterministic.
+#include <cub/device/device_scan.cuh>
+
 #include "common.cuh"
 #include "sketch.cuh"
 
@@ -93,12 +95,22 @@ __device__ __forceinline__ uint64_t murmur_bytes(const uint8_t* s, uint32_t k) {
 }
 
 struct Workspace {
-    uint32_t* ticket;
-    uint64_t* status;
-    uint32_t* tile_pid;
+    uint32_t* ticket;      // [0] tile ticket, [1] zero-hash flag (exact path)
+    uint64_t* status;      // look-back words, one per tile
+    uint32_t* tile_pid;    // [nt + 1]
+    uint64_t* tile_cnt;    // [nt + 1] valid windows per tile (exact path)
+    uint64_t* tile_base;   // [nt + 1] exclusive scan of tile_cnt
+    void* scan_temp;
+    size_t scan_temp_bytes;
 };
 
 __host__ __device__ inline uint64_t n_tiles_of(uint64_t n_res) { return (n_res + SK_TILE - 1) / SK_TILE; }
+
+inline size_t scan_temp_bytes_for(uint64_t n) {
+    size_t bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, bytes, (const uint64_t*)nullptr, (uint64_t*)nullptr, (int64_t)n);
+    return (bytes + 255) & ~(size_t)255;
+}
 
 __host__ inline Workspace carve(void* ws, uint64_t n_res) {
     uint64_t nt = n_tiles_of(n_res);
@@ -107,6 +119,12 @@ __host__ inline Workspace carve(void* ws, uint64_t n_res) {
     w.ticket = (uint32_t*)p;
     w.status = (uint64_t*)(p + 16);
     w.tile_pid = (uint32_t*)(p + 16 + nt * 8);
+    size_t off = (16 + nt * 8 + (nt + 1) * 4 + 15) & ~(size_t)15;
+    w.tile_cnt = (uint64_t*)(p + off);
+    w.tile_base = w.tile_cnt + nt + 1;
+    off += 2 * (nt + 1) * 8;
+    w.scan_temp = p + off;
+    w.scan_temp_bytes = scan_temp_bytes_for(nt + 1);
     return w;
 }
 
@@ -123,6 +141,26 @@ __global__ void tile_pid_kernel(const uint64_t* __restrict__ offsets, uint64_t n
         if (offsets[mid] <= g) lo = mid; else hi = mid - 1;
     }
     tile_pid[t] = (uint32_t)lo;
+}
+
+// Exact path (scaled == 1): the number of tuples a tile emits is its number of valid windows, known from the
+// offsets alone (a hash of exactly 0 is the one exception, flagged by the kernel and redone on the general path).
+__global__ void tile_count_kernel(const uint64_t* __restrict__ offsets, uint64_t n_res, uint32_t k, uint64_t n_tiles,
+                                  const uint32_t* __restrict__ tile_pid, uint64_t* __restrict__ tile_cnt) {
+    uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (t > n_tiles) return;
+    if (t == n_tiles) { tile_cnt[t] = 0; return; }
+    const uint64_t g0 = t * SK_TILE, g1 = g0 + SK_TILE;
+    uint64_t c = 0;
+    for (uint32_t p = tile_pid[t]; p <= tile_pid[t + 1]; p++) {
+        const uint64_t a = offsets[p], b = offsets[p + 1];
+        if (b - a < k) continue;
+        const uint64_t lo = a > g0 ? a : g0;              // window starts of p inside the tile: [lo, hi)
+        const uint64_t last = b - k + 1;                  // one past the last window start of p
+        const uint64_t hi = last < g1 ? last : g1;
+        if (hi > lo) c += hi - lo;
+    }
+    tile_cnt[t] = c;
 }
 
 template <int K, bool TRANSLATE>
@@ -335,10 +373,12 @@ constexpr int SQ_ROWS = SK_TILE / (SK_THREADS * 4);   // quad rows per warp (2)
 constexpr int SQ_SEG = SK_TILE / 4 + 4;                // staging segment stride in slots: = 4 (mod 16)
 __device__ __forceinline__ uint32_t stage_addr(uint32_t slot) { return (slot & 3u) * SQ_SEG + (slot >> 2); }
 
+// FULL (max_hash = 2^64 - 1, i.e. scaled == 1): tile bases come from tile_count_kernel + scan, so there is no
+// ticket, no look-back chain and no cross-CTA dependency at all.
 template <int K, bool TRANSLATE, bool FULL>
 __global__ void __launch_bounds__(SK_THREADS)
 sketch_quad_kernel(SketchArgs a, Lut256 lut, uint32_t* __restrict__ ticket, uint64_t* __restrict__ status,
-                   const uint32_t* __restrict__ tile_pid) {
+                   const uint32_t* __restrict__ tile_pid, const uint64_t* __restrict__ tile_base) {
     constexpr int RES_WORDS = (SK_TILE + K + 16 + 3) / 4;
     constexpr int NW = (K + 3 + 3) / 4;  // words that cover the 4 + K - 1 bytes of a quad
     constexpr int KW = (K + 3) / 4;
@@ -352,10 +392,10 @@ sketch_quad_kernel(SketchArgs a, Lut256 lut, uint32_t* __restrict__ ticket, uint
     __shared__ uint64_t s_base;
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+    if (!FULL && tid == 0) s_tile = atomicAdd(ticket, 1u);
     if (TRANSLATE) s_lut[tid] = lut.b[tid];
-    __syncthreads();
-    const uint32_t tile = s_tile;
+    if (!FULL || TRANSLATE) __syncthreads();
+    const uint32_t tile = FULL ? blockIdx.x : s_tile;
     const uint64_t g0 = (uint64_t)tile * SK_TILE;
     const uint64_t n_tiles = n_tiles_of(a.n_res);
     const uint32_t p_lo = tile_pid[tile], p_hi = tile_pid[tile + 1];
@@ -431,7 +471,12 @@ sketch_quad_kernel(SketchArgs a, Lut256 lut, uint32_t* __restrict__ ticket, uint
             for (int i = 0; i < KW; i++) b[i] = j == 0 ? x[i] : __funnelshift_r(x[i], x[i + 1], 8 * j);
             if (K % 4) b[KW - 1] &= (1u << (8 * (K % 4))) - 1u;
             h[j] = murmur_limbs<K>(b);
-            keep[j] = valid && h[j] != 0 && (FULL || h[j] <= a.max_hash);
+            if (FULL) {
+                keep[j] = valid;  // the count was fixed in advance; a zero hash (1 in 2^64) sends the batch to the general path
+                if (valid && h[j] == 0) atomicOr(ticket + 1, 1u);
+            } else {
+                keep[j] = valid && h[j] != 0 && h[j] <= a.max_hash;
+            }
             loc[j] = ((uint64_t)(a.pid_base + p) << 32) | (uint64_t)(g0_lo + w - pstart_lo);
         }
         uint32_t below = 0, total = 0;
@@ -464,15 +509,21 @@ sketch_quad_kernel(SketchArgs a, Lut256 lut, uint32_t* __restrict__ ticket, uint
         if (i < (int)warp) wprefix += t;
         btotal += t;
     }
-    if (warp == 0) {
-        const uint64_t excl = scan_lookback(status, tile, btotal);
-        if (lane == 0) {
-            s_base = excl;
-            if (tile == n_tiles - 1) *a.d_count = excl + btotal;
+    uint64_t base;
+    if (FULL) {
+        base = tile_base[tile] + wprefix;
+        if (tid == 0 && tile == n_tiles - 1) *a.d_count = tile_base[tile] + btotal;
+    } else {
+        if (warp == 0) {
+            const uint64_t excl = scan_lookback(status, tile, btotal);
+            if (lane == 0) {
+                s_base = excl;
+                if (tile == n_tiles - 1) *a.d_count = excl + btotal;
+            }
         }
+        __syncthreads();
+        base = s_base + wprefix;
     }
-    __syncthreads();
-    const uint64_t base = s_base + wprefix;
     const uint32_t sbase = warp * (SK_TILE / (SK_THREADS / 32));
     for (uint32_t i = lane; i < wcount; i += 32) {
         if (base + i < a.capacity) {
@@ -492,13 +543,13 @@ cudaError_t launch_k(const SketchArgs& a, const Lut256& lut, const Workspace& w,
         else
             sketch_kernel<0, true><<<grid, SK_THREADS, 0, st>>>(a, lut, w.ticket, w.status, w.tile_pid);
     } else {
-        const bool full = a.max_hash == ~0ull;
+        const bool full = a.max_hash == ~0ull && !a.force_general;
         if (a.moltype == 0) {
-            if (full) sketch_quad_kernel<K, false, true><<<grid, SK_THREADS, 0, st>>>(a, lut, w.ticket, w.status, w.tile_pid);
-            else sketch_quad_kernel<K, false, false><<<grid, SK_THREADS, 0, st>>>(a, lut, w.ticket, w.status, w.tile_pid);
+            if (full) sketch_quad_kernel<K, false, true><<<grid, SK_THREADS, 0, st>>>(a, lut, w.ticket, w.status, w.tile_pid, w.tile_base);
+            else sketch_quad_kernel<K, false, false><<<grid, SK_THREADS, 0, st>>>(a, lut, w.ticket, w.status, w.tile_pid, w.tile_base);
         } else {
-            if (full) sketch_quad_kernel<K, true, true><<<grid, SK_THREADS, 0, st>>>(a, lut, w.ticket, w.status, w.tile_pid);
-            else sketch_quad_kernel<K, true, false><<<grid, SK_THREADS, 0, st>>>(a, lut, w.ticket, w.status, w.tile_pid);
+            if (full) sketch_quad_kernel<K, true, true><<<grid, SK_THREADS, 0, st>>>(a, lut, w.ticket, w.status, w.tile_pid, w.tile_base);
+            else sketch_quad_kernel<K, true, false><<<grid, SK_THREADS, 0, st>>>(a, lut, w.ticket, w.status, w.tile_pid, w.tile_base);
         }
     }
     return cudaGetLastError();
@@ -549,22 +600,33 @@ void fill_lut(int moltype, Lut256* lut) {
 }
 
 size_t sketch_workspace_bytes(uint64_t n_res) {
-    uint64_t nt = n_tiles_of(n_res);
-    return 16 + nt * 8 + (nt + 1) * 4 + 16;
+    const uint64_t nt = n_tiles_of(n_res);
+    return ((16 + nt * 8 + (nt + 1) * 4 + 15) & ~(size_t)15) + 2 * (nt + 1) * 8 + scan_temp_bytes_for(nt + 1) + 64;
 }
 
 cudaError_t launch_sketch(const SketchArgs& a, cudaStream_t stream, uint64_t* n_launches) {
-    if (a.n_res == 0 || a.n_prot == 0) return cudaMemsetAsync(a.d_count, 0, 8, stream);
+    if (a.n_res == 0 || a.n_prot == 0) return cudaMemsetAsync(a.d_count, 0, 16, stream);
     const uint64_t nt = n_tiles_of(a.n_res);
     Workspace w = carve(a.workspace, a.n_res);
-    cudaError_t e = cudaMemsetAsync(a.workspace, 0, 16 + nt * 8, stream);
+    const bool exact = a.max_hash == ~0ull && !a.force_general && a.k <= (uint32_t)SK_MAX_TEMPLATE_K;
+    cudaError_t e = cudaMemsetAsync(a.workspace, 0, exact ? 16 : 16 + nt * 8, stream);
     if (e != cudaSuccess) return e;
     tile_pid_kernel<<<(unsigned)((nt + 1 + 255) / 256), 256, 0, stream>>>(a.offsets, a.n_prot, nt, w.tile_pid);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
+    if (exact) {
+        tile_count_kernel<<<(unsigned)((nt + 1 + 255) / 256), 256, 0, stream>>>(a.offsets, a.n_res, a.k, nt, w.tile_pid, w.tile_cnt);
+        size_t tb = w.scan_temp_bytes;
+        e = cub::DeviceScan::ExclusiveSum(w.scan_temp, tb, w.tile_cnt, w.tile_base, (int64_t)(nt + 1), stream);
+        if (e != cudaSuccess) return e;
+        if (n_launches) *n_launches += 3;
+    }
     Lut256 lut;
     fill_lut(a.moltype, &lut);
     e = Dispatch<SK_MAX_TEMPLATE_K>::run(a, lut, w, nt, stream);
+    if (e != cudaSuccess) return e;
+    // d_count[1] <- zero-hash flag of the exact path (always 0 on the general path)
+    e = cudaMemcpyAsync(a.d_count + 1, w.ticket, 8, cudaMemcpyDeviceToDevice, stream);
     if (n_launches) *n_launches += 2;
     return e;
 }

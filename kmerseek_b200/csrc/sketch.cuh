@@ -25,7 +25,9 @@ struct SketchArgs {
     uint64_t* out_hash;        // device, capacity entries (already offset to the append position)
     uint64_t* out_loc;         // (pid << 32) | pos
     uint64_t capacity;
-    uint64_t* d_count;         // device: tuples kept by this launch (may exceed capacity: nothing is written past it)
+    uint64_t* d_count;         // device u64[2]: [0] tuples kept by this launch (may exceed capacity: nothing is written
+                               // past it); [1] low word = ticket, high word != 0: a zero hash was met on the exact path
+    int force_general;         // 1: take the look-back path even when scaled == 1
     void* workspace;           // sketch_workspace_bytes(n_res)
 };
 

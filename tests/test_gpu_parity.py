@@ -359,3 +359,14 @@ def test_bucket_sort_path_scaled(K, O):
         okeys, orow, ops, oqs = O.build_index(oh, opid, opos)
         assert np.array_equal(keys, okeys) and np.array_equal(row_ptr, orow)
         assert np.array_equal(pid, ops) and np.array_equal(pos, oqs)
+
+
+def test_general_sketch_path_at_scaled_1(K, O, monkeypatch):
+    """scaled == 1 normally takes the chain-free exact path; the look-back path must give the same tuples
+    (it is what a batch is redone on if a hash of exactly 0 ever shows up)."""
+    monkeypatch.setenv("KS_SKETCH_GENERAL", "1")
+    prot, _ = _edge_proteome(K, 1234, 120_000)
+    for k, moltype in ((24, "hp"), (16, "dayhoff"), (5, "protein")):
+        h, pid, pos, _ = _gpu_tuples(K, prot, k, moltype, 1)
+        oh, opid, opos = _oracle_tuples(O, prot, k, moltype, 1)
+        assert np.array_equal(h, oh) and np.array_equal(pid, opid) and np.array_equal(pos, opos)
