@@ -84,6 +84,11 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures of the C2
+# workload (profiles/r01_*): only meaningful for that workload, null otherwise.
+TRAFFIC = {}
+
+
 def algorithmic_bytes(n_res, n_prot, n_tuples, n_unique):
     """BASELINE.md section 3."""
     sketch = n_res + (n_prot + 1) * 8 + n_tuples * 16
@@ -216,11 +221,12 @@ def main():
     for _ in range(W):
         build_resident()
     st0 = idx.stats()
-    stage_ms = {"sketch": [], "sort": [], "csr": []}
+    stage_ms = {"sketch": [], "partition": [], "bucket": [], "csr": []}
 
     def collect():
         s = idx.stats()
-        stage_ms["sketch"].append(s["ms_sketch"]); stage_ms["sort"].append(s["ms_sort"]); stage_ms["csr"].append(s["ms_csr"])
+        stage_ms["sketch"].append(s["ms_sketch"]); stage_ms["partition"].append(s["ms_sort_partition"])
+        stage_ms["bucket"].append(s["ms_sort_bucket"]); stage_ms["csr"].append(s["ms_csr"])
 
     sampler = ClockSampler(local)
     if rank == 0:
@@ -275,17 +281,24 @@ def main():
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant stage ----
+    # ---- roofline of the dominant kernel (stage times: CUDA events the library records on its own stream) ----
     peak, peak_src = peaks()
-    sk_bytes, bd_bytes = algorithmic_bytes(n_res, n_prot, n_tuples, n_unique)
-    ms_sk, ms_so, ms_cs = (float(np.mean(stage_ms[k])) for k in ("sketch", "sort", "csr"))
-    stages = {
-        "sketch": {"ms": ms_sk, "algorithmic_bytes": sk_bytes, "achieved_gbs": sk_bytes / ms_sk / 1e6},
-        "sort+csr": {"ms": ms_so + ms_cs, "algorithmic_bytes": bd_bytes, "achieved_gbs": bd_bytes / (ms_so + ms_cs) / 1e6},
+    n_groups = st["n_groups"]
+    ms = {k: float(np.mean(v)) for k, v in stage_ms.items()}
+    alg = {
+        # BASELINE.md section 3; per launch = per step (every stage runs once per step)
+        "sketch_quad_kernel": ("sketch", n_res + (n_prot + 1) * 8 + n_tuples * 16),
+        "partition (2 library onesweep passes)": ("partition", n_tuples * 16 * 2),          # one read + one write
+        "bucket_sort_kernel": ("bucket", n_tuples * 16 * 2),                                 # one read + one write
+        "csr (scan + csr_write_kernel + dir_kernel)": ("csr", n_tuples * 16 + n_groups * 4 + n_unique * 12),
     }
-    dom = max(stages, key=lambda k: stages[k]["ms"])
+    stages = {name: {"ms": ms[key], "algorithmic_bytes": int(b), "achieved_gbs": b / ms[key] / 1e6 if ms[key] > 0 else 0.0}
+              for name, (key, b) in alg.items()}
+    own = {k: v for k, v in stages.items() if "library" not in k}
+    dom = max(own, key=lambda k: own[k]["ms"])
+    sk_bytes, bd_bytes = algorithmic_bytes(n_res, n_prot, n_tuples, n_unique)
     roof = {"bound": "hbm", "kernel": dom, "achieved": stages[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
-            "frac": stages[dom]["achieved_gbs"] / peak, "traffic": None, "peak_source": peak_src,
+            "frac": stages[dom]["achieved_gbs"] / peak, "traffic": TRAFFIC.get(dom), "peak_source": peak_src,
             "stages": {k: {"ms": round(v["ms"], 4), "achieved_gbs": round(v["achieved_gbs"], 1),
                            "frac": round(v["achieved_gbs"] / peak, 4)} for k, v in stages.items()},
             "whole_step": {"algorithmic_bytes": sk_bytes + bd_bytes,

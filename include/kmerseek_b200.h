@@ -161,6 +161,8 @@ typedef struct ks_stats {
     uint64_t sketch_launches, sort_launches, csr_launches, search_launches; /* kernels launched so far */
     float ms_upload, ms_sketch, ms_sort, ms_csr; /* device time of the last run of each stage (CUDA events) */
     float ms_search;
+    float ms_sort_partition; /* part of ms_sort: partition by the top hash bits (library onesweep passes) */
+    float ms_sort_bucket;    /* part of ms_sort: bucket_sort_kernel (+ bucket table kernels) */
     uint32_t finalized;
 } ks_stats;
 /* Synchronises the handle's stream. */

@@ -31,7 +31,8 @@ class ks_stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
         "n_proteins", "n_residues", "n_windows", "n_tuples", "n_unique_hashes", "n_groups", "n_distinct_ids",
         "device_bytes", "sketch_launches", "sort_launches", "csr_launches", "search_launches")] + [
-        (n, C.c_float) for n in ("ms_upload", "ms_sketch", "ms_sort", "ms_csr", "ms_search")] + [
+        (n, C.c_float) for n in ("ms_upload", "ms_sketch", "ms_sort", "ms_csr", "ms_search", "ms_sort_partition",
+                                 "ms_sort_bucket")] + [
         ("finalized", C.c_uint32)]
 
 

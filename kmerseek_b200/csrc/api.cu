@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <new>
 #include <time.h>
 
@@ -266,7 +267,7 @@ struct ks_index {
     uint64_t max_hash = 0;
     int lz = 0;  // known-zero leading bits of every kept hash
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev[10] = {};
+    cudaEvent_t ev[12] = {};
     uint64_t live_bytes = 0;
     Arena* arena = nullptr;
 
@@ -297,7 +298,7 @@ struct ks_index {
 
 namespace {
 
-enum { EV_UP0, EV_UP1, EV_SK0, EV_SK1, EV_SO0, EV_SO1, EV_CS0, EV_CS1, EV_Q0, EV_Q1 };
+enum { EV_UP0, EV_UP1, EV_SK0, EV_SK1, EV_SO0, EV_SO1, EV_CS0, EV_CS1, EV_Q0, EV_Q1, EV_PART };
 
 void ensure_ws(ks_index* x, size_t bytes) {
     if (bytes <= x->ws_bytes) return;
@@ -430,6 +431,7 @@ void finalize(ks_index* x) {
     a.temp_bytes = build_temp_bytes(n, x->end_bit());
     a.temp = x->b_temp.ensure<char>(ar, a.temp_bytes);
     a.ev_sorted = x->ev[EV_SO1];
+    a.ev_partitioned = x->ev[EV_PART];
     int in_a = 1;
     double t1 = dbg ? now_ms() : 0;
     KS_CUDA(cudaEventRecord(x->ev[EV_SO0], x->stream));
@@ -495,7 +497,43 @@ ks_sketch* sketch_to_host(const Grouped& g, const uint64_t* tuple_hash, const ui
 struct ResultDevice {
     Arena* arena;
     std::map<std::string, void*> cols;
+    void* pinned = nullptr;   // one pinned block that holds every pair / hit column of the host copy
+    size_t pinned_bytes = 0;
 };
+
+// Pinned blocks are recycled across searches: cudaHostAlloc of a result-sized block costs more than the copy.
+std::mutex g_pin_mu;
+std::vector<std::pair<void*, size_t>> g_pin_free;
+size_t g_pin_pooled = 0;
+
+void* pinned_get(size_t bytes, size_t* got) {
+    {
+        std::lock_guard<std::mutex> lk(g_pin_mu);
+        int best = -1;
+        for (size_t i = 0; i < g_pin_free.size(); i++)
+            if (g_pin_free[i].second >= bytes && (best < 0 || g_pin_free[i].second < g_pin_free[best].second)) best = (int)i;
+        if (best >= 0) {
+            auto b = g_pin_free[best];
+            g_pin_free.erase(g_pin_free.begin() + best);
+            g_pin_pooled -= b.second;
+            *got = b.second;
+            return b.first;
+        }
+    }
+    size_t want = bytes + bytes / 4 + (1u << 20);
+    void* p = nullptr;
+    KS_CUDA(cudaHostAlloc(&p, want, cudaHostAllocDefault));
+    *got = want;
+    return p;
+}
+
+void pinned_put(void* p, size_t bytes) {
+    if (!p) return;
+    std::lock_guard<std::mutex> lk(g_pin_mu);
+    if (g_pin_pooled + bytes > (8ull << 30)) { cudaFreeHost(p); return; }
+    g_pin_free.emplace_back(p, bytes);
+    g_pin_pooled += bytes;
+}
 
 }  // namespace
 
@@ -627,7 +665,11 @@ ks_status ks_index_stats(ks_index* x, ks_stats* out) {
         s.sketch_launches = x->l_sketch; s.sort_launches = x->l_sort; s.csr_launches = x->l_csr; s.search_launches = x->l_search;
         if (x->t_upload) KS_CUDA(cudaEventElapsedTime(&s.ms_upload, x->ev[EV_UP0], x->ev[EV_UP1]));
         if (x->t_sketch) KS_CUDA(cudaEventElapsedTime(&s.ms_sketch, x->ev[EV_SK0], x->ev[EV_SK1]));
-        if (x->t_sort) KS_CUDA(cudaEventElapsedTime(&s.ms_sort, x->ev[EV_SO0], x->ev[EV_SO1]));
+        if (x->t_sort) {
+            KS_CUDA(cudaEventElapsedTime(&s.ms_sort, x->ev[EV_SO0], x->ev[EV_SO1]));
+            KS_CUDA(cudaEventElapsedTime(&s.ms_sort_partition, x->ev[EV_SO0], x->ev[EV_PART]));
+            KS_CUDA(cudaEventElapsedTime(&s.ms_sort_bucket, x->ev[EV_PART], x->ev[EV_SO1]));
+        }
         if (x->t_csr) KS_CUDA(cudaEventElapsedTime(&s.ms_csr, x->ev[EV_SO1], x->ev[EV_CS1]));
         s.ms_search = x->ms_search;
         s.finalized = x->finalized ? 1 : 0;
@@ -759,21 +801,30 @@ ks_status ks_search_resident(ks_index* x, uint32_t flags, ks_search_result** out
             r->q_mins = to_host(qs.ent_hash, qs.n_entries, st);
             uint32_t* first = to_host(qs.ent_first, qs.n_entries + 1, st);
             if (!(flags & KS_SEARCH_DEVICE_ONLY)) {
-                const uint64_t np = sd.n_pairs, nh = sd.n_hits;
-                r->pair_qid = to_host(sd.pair_qid, np, st); r->pair_pid = to_host(sd.pair_pid, np, st);
-                r->intersect_hashes = to_host(sd.intersect, np, st);
-                r->q_size = to_host(sd.q_size, np, st); r->t_size = to_host(sd.t_size, np, st);
-                r->n_weighted_found = to_host(sd.n_weighted_found, np, st);
-                r->total_weighted_hashes = to_host(sd.total_weighted, np, st);
+                const uint64_t np = sd.n_pairs, nh = (flags & KS_SEARCH_HITS) ? sd.n_hits : 0;
+                const size_t need = np * (5 * 4 + 2 * 8 + N_SCORE_COLS * 8) + nh * (4 * 4 + 8) + 64 * 32;
+                rd->pinned = pinned_get(need, &rd->pinned_bytes);
+                char* cur = (char*)rd->pinned;
+                auto take = [&](const void* dev, size_t bytes) -> void* {
+                    void* h = cur;
+                    if (bytes) KS_CUDA(cudaMemcpyAsync(h, dev, bytes, cudaMemcpyDeviceToHost, st));
+                    cur += (bytes + 63) & ~(size_t)63;
+                    return h;
+                };
+                r->pair_qid = (uint32_t*)take(sd.pair_qid, np * 4); r->pair_pid = (uint32_t*)take(sd.pair_pid, np * 4);
+                r->intersect_hashes = (uint32_t*)take(sd.intersect, np * 4);
+                r->q_size = (uint32_t*)take(sd.q_size, np * 4); r->t_size = (uint32_t*)take(sd.t_size, np * 4);
+                r->n_weighted_found = (uint64_t*)take(sd.n_weighted_found, np * 8);
+                r->total_weighted_hashes = (uint64_t*)take(sd.total_weighted, np * 8);
                 double** dst[N_SCORE_COLS] = {&r->containment, &r->containment_target_in_query, &r->max_containment,
                                               &r->jaccard, &r->query_containment_ani, &r->match_containment_ani,
                                               &r->average_containment_ani, &r->max_containment_ani, &r->average_abund,
                                               &r->median_abund, &r->std_abund, &r->f_weighted_target_in_query};
-                for (int i = 0; i < N_SCORE_COLS; i++) *dst[i] = to_host(sd.score[i], np, st);
+                for (int i = 0; i < N_SCORE_COLS; i++) *dst[i] = (double*)take(sd.score[i], np * 8);
                 if (flags & KS_SEARCH_HITS) {
-                    r->hit_qid = to_host(sd.hit_qid, nh, st); r->hit_pid = to_host(sd.hit_pid, nh, st);
-                    r->hit_qpos = to_host(sd.hit_qpos, nh, st); r->hit_tpos = to_host(sd.hit_tpos, nh, st);
-                    r->hit_hash = to_host(sd.hit_hash, nh, st);
+                    r->hit_qid = (uint32_t*)take(sd.hit_qid, nh * 4); r->hit_pid = (uint32_t*)take(sd.hit_pid, nh * 4);
+                    r->hit_qpos = (uint32_t*)take(sd.hit_qpos, nh * 4); r->hit_tpos = (uint32_t*)take(sd.hit_tpos, nh * 4);
+                    r->hit_hash = (uint64_t*)take(sd.hit_hash, nh * 8);
                 }
             }
             KS_CUDA(cudaStreamSynchronize(st));
@@ -805,15 +856,10 @@ void* ks_search_result_device_column(const ks_search_result* r, const char* name
 
 void ks_search_result_free(ks_search_result* r) {
     if (!r) return;
-    void* ptrs[] = {r->q_sig_ptr, r->q_mins, r->q_abunds, r->pair_qid, r->pair_pid, r->intersect_hashes, r->q_size,
-                    r->t_size, r->n_weighted_found, r->total_weighted_hashes, r->containment,
-                    r->containment_target_in_query, r->max_containment, r->jaccard, r->query_containment_ani,
-                    r->match_containment_ani, r->average_containment_ani, r->max_containment_ani, r->average_abund,
-                    r->median_abund, r->std_abund, r->f_weighted_target_in_query, r->hit_qid, r->hit_pid, r->hit_qpos,
-                    r->hit_tpos, r->hit_hash};
-    for (void* p : ptrs) free(p);
+    free(r->q_sig_ptr); free(r->q_mins); free(r->q_abunds);  // the pair / hit columns live in the pinned block
     if (r->device_block) {
         ResultDevice* rd = (ResultDevice*)r->device_block;
+        pinned_put(rd->pinned, rd->pinned_bytes);
         delete rd->arena;
         delete rd;
     }

@@ -573,6 +573,7 @@ cudaError_t build_index(const BuildArgs& a, cudaStream_t stream, int* out_in_a, 
         KS_TRY(cudaMemsetAsync(a.d_counts, 0, 16, stream));
         KS_TRY(cudaMemsetAsync(a.key_grp, 0, 4, stream));
         KS_TRY(cudaMemsetAsync(a.grp_start, 0, 4, stream));
+        if (a.ev_partitioned) KS_TRY(cudaEventRecord(a.ev_partitioned, stream));
         if (a.ev_sorted) KS_TRY(cudaEventRecord(a.ev_sorted, stream));
         dir_kernel<<<1, 256, 0, stream>>>(a.keys, a.d_counts, a.dir, a.dir_bits, a.dir_shift);
         *csr_launches += 1;
@@ -597,6 +598,7 @@ cudaError_t build_index(const BuildArgs& a, cudaStream_t stream, int* out_in_a, 
         *out_in_a = in_a;
         fh = in_a ? a.hash_a : a.hash_b;
         fl = in_a ? a.loc_a : a.loc_b;
+        if (a.ev_partitioned) KS_TRY(cudaEventRecord(a.ev_partitioned, stream));
         if (a.ev_sorted) KS_TRY(cudaEventRecord(a.ev_sorted, stream));
         fixed_ranges_kernel<<<(nb + 1 + 255) / 256, 256, 0, stream>>>(n, nb, start);
         range_count_kernel<<<nb, 256, 0, stream>>>(fh, fl, start, 0, counts, a.t_size);
@@ -606,6 +608,7 @@ cudaError_t build_index(const BuildArgs& a, cudaStream_t stream, int* out_in_a, 
         // 1. partition by the top tb bits (stable): library onesweep passes over those bits only
         int in_a = 1;
         if (tb > 0) KS_TRY(library_sort(a.hash_a, a.loc_a, a.hash_b, a.loc_b, n, a.end_bit - tb, a.end_bit, lib_temp, lib_bytes, stream, &in_a, sort_launches));
+        if (a.ev_partitioned) KS_TRY(cudaEventRecord(a.ev_partitioned, stream));
         uint64_t* sh = in_a ? a.hash_a : a.hash_b;
         uint64_t* sl = in_a ? a.loc_a : a.loc_b;
         uint64_t* dh = in_a ? a.hash_b : a.hash_a;

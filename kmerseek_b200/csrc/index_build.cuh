@@ -47,7 +47,8 @@ struct BuildArgs {
     int dir_bits, dir_shift;
     void* temp;
     size_t temp_bytes;
-    cudaEvent_t ev_sorted;  // recorded between the sort and the CSR write (stage timing); may be null
+    cudaEvent_t ev_partitioned;  // recorded after the partition by the top bits (stage timing); may be null
+    cudaEvent_t ev_sorted;       // recorded between the sort and the CSR write; may be null
 };
 
 size_t build_temp_bytes(uint64_t n, int end_bit);

@@ -115,29 +115,54 @@ def gather_blocks(blocks, count):
     return (out if rank == 0 else None), counts
 
 
+def _to_host(t):
+    """Device tensor -> numpy through a pinned staging tensor (pageable D2H is several times slower)."""
+    import torch
+    if t.device.type == "cpu":
+        return t.numpy()
+    h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    h.copy_(t, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    return h.numpy()
+
+
+def _base_vector(counts, pid_bases, device):
+    import torch
+    return torch.repeat_interleave(torch.tensor(pid_bases, dtype=torch.int32, device=device),
+                                   torch.tensor(counts, dtype=torch.int64, device=device))
+
+
 def merge_pairs(gathered, counts, pid_bases):
-    """Rank-0 merge: globalise protein ids with each shard's base and order rows by (query, target)."""
-    u32 = gathered["u32"].cpu().numpy().view(np.uint32)
-    u64 = gathered["u64"].cpu().numpy().view(np.uint64)
-    f64 = gathered["f64"].cpu().numpy()
-    base = np.repeat(np.asarray(pid_bases, dtype=np.uint32), counts)
-    cols = {n: u32[i].copy() for i, n in enumerate(PAIR_U32)}
-    cols["pair_pid"] = cols["pair_pid"] + base
-    cols.update({n: u64[i].copy() for i, n in enumerate(PAIR_U64)})
-    cols.update({n: f64[i].copy() for i, n in enumerate(PAIR_F64)})
-    order = np.lexsort((cols["pair_pid"], cols["pair_qid"]))
-    return {k: v[order] for k, v in cols.items()}
+    """Rank-0 merge, on the device the blocks live on: globalise protein ids with each shard's base and order
+    rows by (query, target).  Shards arrive in rank order = ascending protein ranges and every shard is already
+    ordered by (query, target), so one stable sort by query is the whole merge."""
+    import torch
+    u32, u64, f64 = gathered["u32"], gathered["u64"], gathered["f64"]
+    u32 = u32.clone()
+    u32[1] += _base_vector(counts, pid_bases, u32.device)
+    order = torch.sort(u32[0], stable=True).indices
+    u32h = _to_host(u32[:, order].contiguous()).view(np.uint32)
+    u64h = _to_host(u64[:, order].contiguous()).view(np.uint64)
+    f64h = _to_host(f64[:, order].contiguous())
+    cols = {n: u32h[i] for i, n in enumerate(PAIR_U32)}
+    cols.update({n: u64h[i] for i, n in enumerate(PAIR_U64)})
+    cols.update({n: f64h[i] for i, n in enumerate(PAIR_F64)})
+    return cols
 
 
 def merge_hits(gathered, counts, pid_bases):
-    u32 = gathered["h32"].cpu().numpy().view(np.uint32)
-    u64 = gathered["h64"].cpu().numpy().view(np.uint64)
-    base = np.repeat(np.asarray(pid_bases, dtype=np.uint32), counts)
-    cols = {n: u32[i].copy() for i, n in enumerate(HIT_U32)}
-    cols["hit_pid"] = cols["hit_pid"] + base
-    cols["hit_hash"] = u64[0].copy()
-    order = np.lexsort((cols["hit_tpos"], cols["hit_pid"], cols["hit_qpos"], cols["hit_qid"]))
-    return {k: v[order] for k, v in cols.items()}
+    """Hits are ordered by (query, qpos, target, tpos) inside a shard; across shards targets ascend with the rank,
+    so a stable sort by (query, qpos) merges them."""
+    import torch
+    h32, h64 = gathered["h32"].clone(), gathered["h64"]
+    h32[1] += _base_vector(counts, pid_bases, h32.device)
+    key = (h32[0].to(torch.int64) << 32) | (h32[2].to(torch.int64) & 0xffffffff)
+    order = torch.sort(key, stable=True).indices
+    h32h = _to_host(h32[:, order].contiguous()).view(np.uint32)
+    h64h = _to_host(h64[:, order].contiguous()).view(np.uint64)
+    cols = {n: h32h[i] for i, n in enumerate(HIT_U32)}
+    cols["hit_hash"] = h64h[0]
+    return cols
 
 
 def search_and_gather(index, queries, pid_base=0, hits=False):

@@ -35,6 +35,8 @@ pub struct ks_stats {
     pub ms_sort: f32,
     pub ms_csr: f32,
     pub ms_search: f32,
+    pub ms_sort_partition: f32,
+    pub ms_sort_bucket: f32,
     pub finalized: u32,
 }
 
