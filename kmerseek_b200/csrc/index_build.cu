@@ -509,9 +509,10 @@ __global__ void dir_kernel(const uint64_t* __restrict__ keys, const uint64_t* __
         const uint32_t b = (uint32_t)(keys[i] >> shift);
         const int64_t bp = i ? (int64_t)(uint32_t)(keys[i - 1] >> shift) : -1;
         for (int64_t x = bp + 1; x <= (int64_t)b; x++) dir[x] = (uint32_t)i;
-        if (i == U - 1)
-            for (uint32_t x = b + 1; x <= nb; x++) dir[x] = (uint32_t)U;
     }
+    // buckets above the last key (a large share when max_hash is not a power of two): filled by everybody
+    const uint32_t b_last = (uint32_t)(keys[U - 1] >> shift);
+    for (uint64_t x = (uint64_t)b_last + 1 + i0; x <= nb; x += stride) dir[x] = (uint32_t)U;
 }
 
 int msd_top_bits(uint64_t n, int lz, uint64_t max_hash) {
