@@ -30,7 +30,7 @@ namespace {
 constexpr int LS_THREADS = 512;
 constexpr int LS_WARPS = LS_THREADS / 32;
 constexpr int LS_CAP = 4096;  // tuples per bucket that fit the shared-memory layout (12 index bits)
-constexpr size_t LS_SMEM = (size_t)LS_CAP * 8 * 3 + LS_WARPS * 256 * 2 + 256 * 4 + 64;
+constexpr size_t LS_SMEM = (size_t)LS_CAP * 8 * 2 + LS_WARPS * 256 * 2 + 256 * 4 + 64;  // 73 KB: 3 CTAs per SM
 constexpr uint32_t MAX_OVERSIZE = 1024;
 
 __global__ void protein_abund_kernel(const uint64_t* __restrict__ loc, uint64_t n, uint32_t n_prot,
@@ -108,8 +108,7 @@ bucket_sort_kernel(const uint64_t* __restrict__ in_hash, const uint64_t* __restr
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t* A = reinterpret_cast<uint64_t*>(smem_raw);
     uint64_t* B = A + LS_CAP;
-    uint64_t* L = B + LS_CAP;
-    uint16_t* cnt = reinterpret_cast<uint16_t*>(L + LS_CAP);              // [LS_WARPS][256] warp-private counters
+    uint16_t* cnt = reinterpret_cast<uint16_t*>(B + LS_CAP);              // [LS_WARPS][256] warp-private counters
     uint32_t* dbase = reinterpret_cast<uint32_t*>(cnt + LS_WARPS * 256);  // [256] exclusive digit offsets
     __shared__ uint32_t s_wsum[8];
     __shared__ uint32_t s_ninv;
@@ -129,10 +128,7 @@ bucket_sort_kernel(const uint64_t* __restrict__ in_hash, const uint64_t* __restr
 
     for (uint32_t j = tid; j < padded; j += LS_THREADS) {
         uint64_t item = ~0ull;
-        if (j < m) {
-            item = ((in_hash[s + j] << sh) & ~0xfffull) | j;
-            L[j] = in_loc[s + j];
-        }
+        if (j < m) item = ((in_hash[s + j] << sh) & ~0xfffull) | j;
         A[j] = item;
     }
     if (tid == 0) s_ninv = 0;
@@ -312,7 +308,7 @@ bucket_sort_kernel(const uint64_t* __restrict__ in_hash, const uint64_t* __restr
         uint64_t item = 0, loc = 0;
         if (j < m) {
             item = src[j];
-            loc = L[item & 0xfffu];
+            loc = in_loc[s + (uint32_t)(item & 0xfffu)];  // gathered from the bucket's own 23 KB window (L1/L2)
         }
         // the predecessor sits in the lane below; lane 0 looks it up
         uint64_t prev = __shfl_up_sync(0xffffffffu, item, 1);
@@ -323,7 +319,7 @@ bucket_sort_kernel(const uint64_t* __restrict__ in_hash, const uint64_t* __restr
             if (j == 0) {
                 hk = hg = true;  // a bucket's first tuple differs from everything before it in its top bits
             } else {
-                if (lane == 0) { prev = src[j - 1]; ppid = (uint32_t)(L[prev & 0xfffu] >> 32); }
+                if (lane == 0) { prev = src[j - 1]; ppid = (uint32_t)(in_loc[s + (uint32_t)(prev & 0xfffu)] >> 32); }
                 hk = ((prev ^ item) >> 12) != 0;
                 hg = hk || ppid != (uint32_t)(loc >> 32);
             }
