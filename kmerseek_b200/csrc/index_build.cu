@@ -32,6 +32,9 @@ constexpr int LS_WARPS = LS_THREADS / 32;
 constexpr int LS_CAP = 4096;  // tuples per bucket that fit the shared-memory layout (12 index bits)
 constexpr size_t LS_SMEM = (size_t)LS_CAP * 8 * 2 + LS_WARPS * 256 * 2 + 256 * 4 + 64;  // 73 KB: 3 CTAs per SM
 constexpr uint32_t MAX_OVERSIZE = 1024;
+#ifndef LS_MATCH_BOTH
+#define LS_MATCH_BOTH 1
+#endif
 
 __global__ void protein_abund_kernel(const uint64_t* __restrict__ loc, uint64_t n, uint32_t n_prot,
                                      uint32_t* __restrict__ t_abund, uint32_t* __restrict__ t_size) {
@@ -152,7 +155,7 @@ bucket_sort_kernel(const uint64_t* __restrict__ in_hash, const uint64_t* __restr
                 // lanes of the row that share the digit: MATCH.ANY (ADU pipe, ~40 cycles per warp) in the first
                 // pass, 8 ballots (ALU pipe) in the second, so that neither pipe carries both passes
                 uint32_t peers;
-                if (pass == 0) {
+                if (pass == 0 || LS_MATCH_BOTH) {
                     peers = __match_any_sync(0xffffffffu, d);
                 } else {
                     peers = 0xffffffffu;
