@@ -426,6 +426,11 @@ void finalize(ks_index* x) {
     BuildArgs a;
     a.hash_a = x->d_hash; a.loc_a = x->d_loc; a.hash_b = hb; a.loc_b = lb;
     a.n = n; a.n_prot = P; a.end_bit = x->end_bit(); a.max_hash = x->max_hash;
+    {   // distinct k-mers possible under this alphabet vs tuples: hp k=24 has 2^24 of them for ~2*10^8 tuples
+        const double alphabet = x->params.moltype == KS_HP ? 2.0 : x->params.moltype == KS_DAYHOFF ? 6.0 : 20.0;
+        const double space = std::pow(alphabet, (double)x->params.ksize) / (double)x->params.scaled;
+        a.repeat_heavy = (double)n > 0.25 * space ? 1 : 0;  // measured: the one-pass kernel only wins when repeats are rare
+    }
     a.keys = x->keys; a.key_grp = x->key_grp; a.grp_start = x->grp_start; a.t_size = x->t_size; a.t_abund = x->t_abund;
     a.d_counts = x->d_counts; a.dir = x->dir; a.dir_bits = x->dir_bits; a.dir_shift = x->dir_shift;
     a.temp_bytes = build_temp_bytes(n, x->end_bit());

@@ -18,6 +18,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 #include "common.cuh"
@@ -30,11 +31,6 @@ namespace {
 constexpr int LS_THREADS = 512;
 constexpr int LS_WARPS = LS_THREADS / 32;
 constexpr int LS_CAP = 4096;  // tuples per bucket that fit the shared-memory layout (12 index bits)
-constexpr size_t LS_SMEM = (size_t)LS_CAP * 8 * 2 + LS_WARPS * 256 * 2 + 256 * 4 + 64;  // 73 KB: 3 CTAs per SM
-constexpr uint32_t MAX_OVERSIZE = 1024;
-#ifndef LS_MATCH_BOTH
-#define LS_MATCH_BOTH 1
-#endif
 
 __global__ void protein_abund_kernel(const uint64_t* __restrict__ loc, uint64_t n, uint32_t n_prot,
                                      uint32_t* __restrict__ t_abund, uint32_t* __restrict__ t_size) {
@@ -90,21 +86,237 @@ __global__ void oversize_count_kernel(const uint32_t* __restrict__ start, uint32
 //
 // After the partition by the top `tb` bits of the normalised hash (normalised = shifted left by the `lz`
 // leading bits that are zero under max_hash) every bucket is a contiguous range of a few thousand tuples.
-// One CTA sorts one bucket in shared memory:
+// One 512-thread CTA sorts one bucket in shared memory:
 //   item = remaining key bits, left-aligned, low 12 bits replaced by the tuple's index in the bucket
-// so comparing items compares (hash, original order) exactly and the result is the stable order.
-// Two stable 8-bit counting passes order the items by the next 16 key bits: every warp owns consecutive
-// rows of 32 items, lanes that share a digit find each other with 8 ballots (MATCH.ANY would do it in one
-// instruction but sits on the ADU pipe at ~40 cycles per warp), the lowest lane of each group updates the
-// warp-private digit counter.  Hashes are uniform, so what is left after 32 known bits are a few short runs
-// that share those bits: their inversions are listed in one parallel sweep and each listed run is put in
-// order by one thread (insertion sort; exact for any input).  The hash is rebuilt from the item, loc is
-// gathered from a staged copy, and the bucket streams back to HBM once, in final order.  On the way out the
-// CTA counts unique hashes and (hash, protein) groups and subtracts repeated (hash, protein) pairs from the
-// protein's sketch size.
+// so comparing items compares (hash, original order) exactly and sorting items IS the stable sort.
+//   1. one stable counting pass over the next 9 key bits: every warp owns consecutive rows of 32 tuples,
+//      lanes that share a digit find each other with one MATCH.ANY, the lowest lane of a group updates the
+//      warp-private digit counter; a (digit, warp) scan turns the counters into offsets and the items are
+//      scattered into 512 sub-buckets (about 6 items each);
+//   2. thread t puts sub-bucket t in order by insertion on the full item -- exact for any input, a handful of
+//      moves for uniform hashes, none for repeats of one hash (they arrive in order); sub-buckets too long for
+//      one thread (heavy repeats) are checked, and if needed ranked, by a whole warp;
+//   3. the bucket streams back to HBM once, in final order: the hash is rebuilt from the item, loc is gathered
+//      from the bucket's own window of the input, and the CTA counts unique hashes and (hash, protein) groups
+//      and subtracts repeated (hash, protein) pairs from the protein's sketch size on the way out.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(LS_THREADS)
+constexpr int LS_DBITS = 9;
+constexpr int LS_ND = 1 << LS_DBITS;
+constexpr int LS_LONG = 48;  // sub-buckets longer than this (repeats of a hash, mostly) are left to a warp
+static_assert(LS_ND == LS_THREADS, "one thread per digit / sub-bucket");
+constexpr size_t LS_SMEM = (size_t)LS_CAP * 8 + (size_t)LS_WARPS * LS_ND * 2 + (LS_ND + 1) * 4 + 64;  // ~50 KB (one pass)
+constexpr size_t LS_SMEM2 = LS_SMEM + (size_t)LS_CAP * 8;                                              // ~82 KB (two passes)
+
+__global__ void __launch_bounds__(LS_THREADS, 3)
 bucket_sort_kernel(const uint64_t* __restrict__ in_hash, const uint64_t* __restrict__ in_loc,
+                   uint64_t* __restrict__ out_hash, uint64_t* __restrict__ out_loc,
+                   const uint32_t* __restrict__ start, int lz, int tb, uint64_t* __restrict__ counts,
+                   uint32_t* __restrict__ t_size, uint32_t long_threshold, int n_pass) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t* B = reinterpret_cast<uint64_t*>(smem_raw);                  // [LS_CAP] items, grouped by digit
+    uint16_t* cnt = reinterpret_cast<uint16_t*>(B + (n_pass == 2 ? 2 : 1) * LS_CAP);  // [LS_WARPS][LS_ND] warp-private counters
+    uint32_t* dstart = reinterpret_cast<uint32_t*>(cnt + LS_WARPS * LS_ND);  // [LS_ND + 1] sub-bucket offsets
+    __shared__ uint32_t s_wsum[LS_WARPS];
+    __shared__ uint32_t s_nlong;
+    __shared__ uint32_t s_long[LS_ND];
+    __shared__ uint32_t s_tk[LS_WARPS], s_tg[LS_WARPS];
+
+    const uint32_t b = blockIdx.x;
+    const uint32_t s = start[b], e = start[b + 1];
+    const uint32_t m = e - s;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (m == 0) { if (tid == 0) counts[b] = 0; return; }
+    if (m > (uint32_t)LS_CAP) return;  // oversize: sorted and counted by the host-driven fallback
+    const int sh = lz + tb;  // >= 12 on this path: the low 12 bits of (hash << sh) are zero and carry the index
+
+    // rows of 32 consecutive tuples; every warp owns R consecutive rows
+    const uint32_t R = (m + LS_THREADS - 1) / LS_THREADS;  // 1..8
+    const uint32_t lt = (1u << lane) - 1u;
+    uint16_t* my = cnt + warp * LS_ND;
+
+    if (tid == 0) s_nlong = 0;
+    // Counting passes, least significant digit first.  One pass (9 bits) when hashes rarely repeat; two passes
+    // (7 + 9 bits) when they do (small alphabets: a bucket then holds few distinct hashes, each many times, and
+    // lists that interleave two of them are expensive to put in order by comparison).
+    uint64_t* B1 = B + LS_CAP;  // second item buffer, only allocated for two passes
+#pragma unroll 1
+    for (int pass = 0; pass < n_pass; pass++) {
+        const bool from_input = pass == 0;
+        const bool last = pass == n_pass - 1;
+        const int dshift = last ? 64 - LS_DBITS : 48;
+        const uint32_t dmask = last ? (uint32_t)(LS_ND - 1) : 127u;
+        uint64_t* dst = last ? B : B1;
+        for (uint32_t i = tid; i < LS_WARPS * LS_ND / 2; i += LS_THREADS) reinterpret_cast<uint32_t*>(cnt)[i] = 0;
+        __syncthreads();
+        // sweep 1: digit groups within a row; digit, rank in the group and group size are kept for sweep 2
+        uint32_t info[8];
+#pragma unroll
+        for (uint32_t r = 0; r < 8; r++) {
+            info[r] = 0xffffffffu;
+            if (r < R) {
+                const uint32_t j = (warp * R + r) * 32 + lane;
+                uint32_t d = dmask;  // tuples past the end: never counted, never scattered
+                if (j < m) d = (uint32_t)((from_input ? (in_hash[s + j] << sh) : B1[j]) >> dshift) & dmask;
+                const uint32_t peers = __match_any_sync(0xffffffffu, d | (j < m ? 0u : 0x10000u));
+                const uint32_t rank = __popc(peers & lt), size = __popc(peers);
+                if (rank == 0 && j < m) my[d] += (uint16_t)size;
+                info[r] = d | (rank << 9) | (size << 15) | (j < m ? 0u : 0x80000000u);
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+        // exclusive scan in (digit, warp) order: thread t owns digit t
+        {
+            uint32_t total = 0;
+#pragma unroll
+            for (int w = 0; w < LS_WARPS; w++) {
+                const uint32_t c = cnt[w * LS_ND + tid];
+                cnt[w * LS_ND + tid] = (uint16_t)total;
+                total += c;
+            }
+            uint32_t incl = total;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+                if ((int)lane >= o) incl += v;
+            }
+            if (lane == 31) s_wsum[warp] = incl;
+            __syncthreads();
+            uint32_t off = 0;
+            for (uint32_t w = 0; w < warp; w++) off += s_wsum[w];
+            dstart[tid] = off + incl - total;
+            if (tid == LS_THREADS - 1) dstart[LS_ND] = off + incl;  // == m
+        }
+        __syncthreads();
+        // sweep 2: stable scatter (first pass: items are built from the input, still in L1/L2)
+#pragma unroll
+        for (uint32_t r = 0; r < 8; r++) {
+            if (r < R) {
+                const uint32_t j = (warp * R + r) * 32 + lane;
+                const bool real = !(info[r] >> 31);
+                const uint32_t d = info[r] & (LS_ND - 1), rank = (info[r] >> 9) & 63u, size = (info[r] >> 15) & 63u;
+                uint32_t base = 0;
+                if (real) base = dstart[d] + my[d];
+                __syncwarp();
+                if (real && rank == 0) my[d] += (uint16_t)size;
+                __syncwarp();
+                if (real) dst[base + rank] = from_input ? (((in_hash[s + j] << sh) & ~0xfffull) | j) : B1[j];
+            }
+        }
+        __syncthreads();
+    }
+    // every sub-bucket in order: one thread each; long ones are listed for the warps
+    {
+        const uint32_t a0 = dstart[tid], b0 = dstart[tid + 1];
+        if (b0 - a0 > long_threshold) {
+            s_long[atomicAdd(&s_nlong, 1u)] = tid;
+        } else {
+            if (b0 > a0) {
+                uint64_t prev = B[a0];  // the largest item placed so far
+                for (uint32_t t = a0 + 1; t < b0; t++) {
+                    const uint64_t x = B[t];
+                    if (x >= prev) { prev = x; continue; }  // already in place (always, for repeats of one hash)
+                    uint32_t u = t;
+                    do { B[u] = B[u - 1]; u--; } while (u > a0 && B[u - 1] > x);
+                    B[u] = x;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (s_nlong) {  // uniform: written before the barrier, not modified after
+        const uint32_t nlong = s_nlong;
+        for (uint32_t k = warp; k < nlong; k += LS_WARPS) {
+            const uint32_t a0 = dstart[s_long[k]], b0 = dstart[s_long[k] + 1];
+            bool sorted = true;
+            for (uint32_t t = a0 + 1 + lane; t < b0; t += 32) sorted &= B[t - 1] <= B[t];
+            if (__all_sync(0xffffffffu, sorted)) continue;  // repeats of few hashes arrive in order
+            // mixed list (repeats of two or more hashes that share 25 bits, interleaved): every lane ranks its items
+            // against the whole list (items are distinct)
+            const uint32_t n = b0 - a0;
+            if (n <= 128) {
+                uint64_t mine[4];
+                uint32_t below[4];
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const uint32_t t = a0 + lane + 32 * q;
+                    mine[q] = t < b0 ? B[t] : ~0ull;
+                    below[q] = 0;
+                }
+                for (uint32_t u = a0; u < b0; u++) {
+                    const uint64_t x = B[u];
+#pragma unroll
+                    for (int q = 0; q < 4; q++) below[q] += x < mine[q];
+                }
+                __syncwarp();
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                    if (a0 + lane + 32 * q < b0) B[a0 + below[q]] = mine[q];
+            } else {
+                // longer than the registers hold: the bucket's own output window, rewritten in final order right
+                // below, serves as the scratch copy
+                for (uint32_t t = a0 + lane; t < b0; t += 32) out_hash[s + t] = B[t];
+                __syncwarp();
+                for (uint32_t t = a0 + lane; t < b0; t += 32) {
+                    const uint64_t x = out_hash[s + t];
+                    uint32_t bl = 0;
+                    for (uint32_t u = a0; u < b0; u++) bl += out_hash[s + u] < x;
+                    B[a0 + bl] = x;
+                }
+            }
+            __syncwarp();
+        }
+        __syncthreads();
+    }
+
+    // write back in final order; count key heads and (hash, protein) group heads
+    const uint64_t top = tb ? ((uint64_t)b << (64 - tb)) : 0ull;
+    uint32_t tk = 0, tg = 0;
+    for (uint32_t j0 = 0; j0 < m; j0 += LS_THREADS) {
+        const uint32_t j = j0 + tid;
+        bool hk = false, hg = false;
+        uint64_t item = 0, loc = 0;
+        if (j < m) {
+            item = B[j];
+            loc = in_loc[s + (uint32_t)(item & 0xfffu)];  // gathered from the bucket's own 23 KB window (L1/L2)
+        }
+        // the predecessor sits in the lane below; lane 0 looks it up
+        uint64_t prev = __shfl_up_sync(0xffffffffu, item, 1);
+        uint32_t ppid = __shfl_up_sync(0xffffffffu, (uint32_t)(loc >> 32), 1);
+        if (j < m) {
+            out_hash[s + j] = (top | ((item & ~0xfffull) >> tb)) >> lz;
+            out_loc[s + j] = loc;
+            if (j == 0) {
+                hk = hg = true;  // a bucket's first tuple differs from everything before it in its top bits
+            } else {
+                if (lane == 0) { prev = B[j - 1]; ppid = (uint32_t)(in_loc[s + (uint32_t)(prev & 0xfffu)] >> 32); }
+                hk = ((prev ^ item) >> 12) != 0;
+                hg = hk || ppid != (uint32_t)(loc >> 32);
+            }
+            if (!hg) atomicSub(&t_size[(uint32_t)(loc >> 32)], 1u);
+        }
+        tk += __popc(__ballot_sync(0xffffffffu, hk));
+        tg += __popc(__ballot_sync(0xffffffffu, hg));
+    }
+    if (lane == 0) { s_tk[warp] = tk; s_tg[warp] = tg; }
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t k = 0, g = 0;
+        for (int w = 0; w < LS_WARPS; w++) { k += s_tk[w]; g += s_tg[w]; }
+        counts[b] = (uint64_t)k | ((uint64_t)g << 32);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Bucket-local sort for repeat-heavy inputs (small k-mer space, e.g. hp k=24: a bucket holds a few hundred
+// distinct hashes, each about ten times).  Comparison-based clean-up is expensive there (lists that interleave
+// two repeated hashes), so this variant resolves 16 more bits with two stable 8-bit counting passes, after
+// which runs that still hold an inversion are rare; those are re-ranked by a warp each.
+// ---------------------------------------------------------------------------------------------
+constexpr size_t LS_SMEM_REP = (size_t)LS_CAP * 8 * 2 + LS_WARPS * 256 * 2 + 256 * 4 + 64;  // 73 KB: 3 CTAs per SM
+
+__global__ void __launch_bounds__(LS_THREADS)
+bucket_sort_rep_kernel(const uint64_t* __restrict__ in_hash, const uint64_t* __restrict__ in_loc,
                    uint64_t* __restrict__ out_hash, uint64_t* __restrict__ out_loc,
                    const uint32_t* __restrict__ start, int lz, int tb, uint64_t* __restrict__ counts,
                    uint32_t* __restrict__ t_size) {
@@ -155,7 +367,7 @@ bucket_sort_kernel(const uint64_t* __restrict__ in_hash, const uint64_t* __restr
                 // lanes of the row that share the digit: MATCH.ANY (ADU pipe, ~40 cycles per warp) in the first
                 // pass, 8 ballots (ALU pipe) in the second, so that neither pipe carries both passes
                 uint32_t peers;
-                if (pass == 0 || LS_MATCH_BOTH) {
+                if (true) {
                     peers = __match_any_sync(0xffffffffu, d);
                 } else {
                     peers = 0xffffffffu;
@@ -339,6 +551,7 @@ bucket_sort_kernel(const uint64_t* __restrict__ in_hash, const uint64_t* __restr
         counts[b] = (uint64_t)k | ((uint64_t)g << 32);
     }
 }
+
 
 // Counts for ranges the bucket sort did not handle: oversize buckets (only_oversize = 1), or every range on the
 // library-sort path (only_oversize = 0).
@@ -616,8 +829,18 @@ cudaError_t build_index(const BuildArgs& a, cudaStream_t stream, int* out_in_a, 
         // 2. bucket boundaries; one CTA per bucket sorts it in shared memory and counts its heads
         bucket_start_kernel<<<(nb + 1 + 255) / 256, 256, 0, stream>>>(sh, n, lz, tb, start, oversize);
         oversize_count_kernel<<<(nb + 255) / 256, 256, 0, stream>>>(start, nb, oversize);
-        KS_TRY(cudaFuncSetAttribute(bucket_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LS_SMEM));
-        bucket_sort_kernel<<<nb, LS_THREADS, LS_SMEM, stream>>>(sh, sl, dh, dl, start, lz, tb, counts, a.t_size);
+        KS_TRY(cudaFuncSetAttribute(bucket_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LS_SMEM2));
+        const char* lt_env = getenv("KS_LS_LONG");  // test hook: force the warp path for short sub-buckets too
+        const uint32_t long_thr = lt_env ? (uint32_t)atoi(lt_env) : (uint32_t)LS_LONG;
+        // repeat-heavy inputs (small k-mer space) take the two-pass variant; KS_LS_VARIANT=rep|uni is a test hook
+        const char* v_env = getenv("KS_LS_VARIANT");
+        const bool rep = v_env ? (v_env[0] == 'r') : (a.repeat_heavy != 0);
+        if (rep) {
+            KS_TRY(cudaFuncSetAttribute(bucket_sort_rep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LS_SMEM_REP));
+            bucket_sort_rep_kernel<<<nb, LS_THREADS, LS_SMEM_REP, stream>>>(sh, sl, dh, dl, start, lz, tb, counts, a.t_size);
+        } else {
+            bucket_sort_kernel<<<nb, LS_THREADS, LS_SMEM, stream>>>(sh, sl, dh, dl, start, lz, tb, counts, a.t_size, long_thr, 1);
+        }
         KS_TRY(cudaGetLastError());
         *sort_launches += 3;
         // 3. oversize buckets (heavy repeats of few hashes): library sort of the remaining bits, range by range

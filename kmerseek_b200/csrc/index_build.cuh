@@ -38,6 +38,7 @@ struct BuildArgs {
     uint32_t n_prot;
     int end_bit;  // hashes are < 2^end_bit (64 - leading zeros of max_hash)
     uint64_t max_hash;
+    int repeat_heavy;  // the k-mer space is small next to n (hashes repeat many times): two local counting passes
     // outputs (device, preallocated): keys[n], key_grp[n+1], grp_start[n+1], t_size[P], t_abund[P], d_counts[2],
     // dir[2^dir_bits + 1]
     uint64_t* keys;
