@@ -289,8 +289,9 @@ def main():
         # BASELINE.md section 3; per launch = per step (every stage runs once per step)
         "sketch_quad_kernel": ("sketch", n_res + (n_prot + 1) * 8 + n_tuples * 16),
         "partition (2 library onesweep passes)": ("partition", n_tuples * 16 * 2),          # one read + one write
-        "bucket_sort_kernel": ("bucket", n_tuples * 16 * 2),                                 # one read + one write
-        "csr (scan + csr_write_kernel + dir_kernel)": ("csr", n_tuples * 16 + n_groups * 4 + n_unique * 12),
+        # one read + one write of every tuple, plus the CSR arrays the kernel emits (keys, key_grp, grp_start)
+        "bucket_sort_kernel (+ fused CSR write)": ("bucket", n_tuples * 16 * 2 + n_groups * 4 + n_unique * 12),
+        "dir_kernel": ("csr", n_unique * 8 + (st["n_tuples"] // 4) * 4),
     }
     stages = {name: {"ms": ms[key], "algorithmic_bytes": int(b), "achieved_gbs": b / ms[key] / 1e6 if ms[key] > 0 else 0.0}
               for name, (key, b) in alg.items()}

@@ -82,6 +82,130 @@ __global__ void oversize_count_kernel(const uint32_t* __restrict__ start, uint32
 }
 
 // ---------------------------------------------------------------------------------------------
+// Shared tail of both bucket-sort kernels: stream the sorted bucket back to HBM, count its unique hashes and
+// (hash, protein) groups, and -- when no bucket is oversize -- write the bucket's part of the CSR arrays too.
+// The CSR offsets of a bucket are the totals of all buckets before it: they come from a decoupled look-back
+// over one status word per bucket.  Buckets are long-lived CTAs (tens of microseconds, ~20 finish per
+// microsecond), well inside what the chain sustains, and the CSR entries are produced from the items still in
+// shared memory instead of re-reading 16 bytes per tuple in a separate kernel.
+// ---------------------------------------------------------------------------------------------
+struct CsrOut {
+    uint64_t* status;          // [nb] look-back words, zeroed per build
+    const uint32_t* oversize;  // [0] = number of oversize buckets; the CSR is fused only when it is 0
+    uint64_t* keys;
+    uint32_t* key_grp;
+    uint32_t* grp_start;
+    uint64_t* d_counts;
+    uint64_t n;
+    uint32_t nb;
+};
+
+__device__ __forceinline__ void csr_totals(const CsrOut& f, uint64_t incl) {
+    const uint64_t U = incl & 0x7fffffffu, G = incl >> 31;
+    f.d_counts[0] = U;
+    f.d_counts[1] = G;
+    f.key_grp[U] = (uint32_t)G;
+    f.grp_start[G] = (uint32_t)f.n;
+}
+
+// An empty bucket still has to pass the running totals on (and the last bucket writes them out).
+__device__ __forceinline__ void bucket_empty(uint32_t b, const CsrOut& f) {
+    if ((threadIdx.x >> 5) != 0 || f.oversize[0] != 0) return;
+    const uint64_t excl = scan_lookback(f.status, b, 0);
+    if (b == f.nb - 1 && (threadIdx.x & 31) == 0) csr_totals(f, excl);
+}
+
+__device__ __forceinline__ void bucket_finish(const uint64_t* items, uint32_t m, uint32_t s, uint32_t b, int lz, int tb,
+                                              const uint64_t* __restrict__ in_loc, uint64_t* __restrict__ out_hash,
+                                              uint64_t* __restrict__ out_loc, uint64_t* __restrict__ counts,
+                                              uint32_t* __restrict__ t_size, const CsrOut& f) {
+    __shared__ uint32_t s_cw[8 * LS_WARPS];  // per (chunk, warp): key heads | group heads << 16, then their prefix
+    __shared__ uint64_t s_base;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t lt = (1u << lane) - 1u;
+    const uint64_t top = tb ? ((uint64_t)b << (64 - tb)) : 0ull;
+    const uint32_t n_chunks = (m + LS_THREADS - 1) / LS_THREADS;
+    uint32_t flags = 0;  // 2 bits per chunk: this thread's element is a key head / a group head
+    for (uint32_t c = 0; c < n_chunks; c++) {
+        const uint32_t j = c * LS_THREADS + tid;
+        bool hk = false, hg = false;
+        uint64_t item = 0, loc = 0;
+        if (j < m) {
+            item = items[j];
+            loc = in_loc[s + (uint32_t)(item & 0xfffu)];  // gathered from the bucket's own 23 KB window (L1/L2)
+        }
+        // the predecessor sits in the lane below; lane 0 looks it up
+        uint64_t prev = __shfl_up_sync(0xffffffffu, item, 1);
+        uint32_t ppid = __shfl_up_sync(0xffffffffu, (uint32_t)(loc >> 32), 1);
+        if (j < m) {
+            out_hash[s + j] = (top | ((item & ~0xfffull) >> tb)) >> lz;
+            out_loc[s + j] = loc;
+            if (j == 0) {
+                hk = hg = true;  // a bucket's first tuple differs from everything before it in its top bits
+            } else {
+                if (lane == 0) { prev = items[j - 1]; ppid = (uint32_t)(in_loc[s + (uint32_t)(prev & 0xfffu)] >> 32); }
+                hk = ((prev ^ item) >> 12) != 0;
+                hg = hk || ppid != (uint32_t)(loc >> 32);
+            }
+            if (!hg) atomicSub(&t_size[(uint32_t)(loc >> 32)], 1u);
+        }
+        flags |= ((hk ? 1u : 0u) | (hg ? 2u : 0u)) << (2 * c);
+        const uint32_t ck = __popc(__ballot_sync(0xffffffffu, hk)), cg = __popc(__ballot_sync(0xffffffffu, hg));
+        if (lane == 0) s_cw[c * LS_WARPS + warp] = ck | (cg << 16);
+    }
+    __syncthreads();
+    if (warp == 0) {
+        // exclusive prefix over the (chunk, warp) counts, 4 entries per lane; both halves stay below 2^16
+        const uint32_t n_ent = n_chunks * LS_WARPS;
+        uint32_t v[4], local = 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const uint32_t e = lane * 4 + i;
+            v[i] = e < n_ent ? s_cw[e] : 0u;
+            local += v[i];
+        }
+        uint32_t incl = local;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((int)lane >= o) incl += t;
+        }
+        uint32_t run = incl - local;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const uint32_t e = lane * 4 + i;
+            if (e < n_ent) s_cw[e] = run;
+            run += v[i];
+        }
+        const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
+        const uint32_t tk = tot & 0xffffu, tg = tot >> 16;
+        if (lane == 0) counts[b] = (uint64_t)tk | ((uint64_t)tg << 32);
+        uint64_t excl = ~0ull;
+        if (f.oversize[0] == 0) {
+            excl = scan_lookback(f.status, b, (uint64_t)tk | ((uint64_t)tg << 31));
+            if (b == f.nb - 1 && lane == 0) csr_totals(f, excl + ((uint64_t)tk | ((uint64_t)tg << 31)));
+        }
+        if (lane == 0) s_base = excl;
+    }
+    __syncthreads();
+    if (s_base == ~0ull) return;  // an oversize bucket exists: the CSR is written by csr_write_kernel after the fallback
+    const uint32_t base_k = (uint32_t)(s_base & 0x7fffffffu), base_g = (uint32_t)(s_base >> 31);
+    for (uint32_t c = 0; c < n_chunks; c++) {
+        const uint32_t j = c * LS_THREADS + tid;
+        const bool hk = (flags >> (2 * c)) & 1u, hg = (flags >> (2 * c)) & 2u;
+        const uint32_t bk = __ballot_sync(0xffffffffu, hk), bg = __ballot_sync(0xffffffffu, hg);
+        const uint32_t pre = s_cw[c * LS_WARPS + warp];
+        const uint32_t g = base_g + (pre >> 16) + __popc(bg & lt);
+        if (hg) f.grp_start[g] = s + j;
+        if (hk) {
+            const uint32_t u = base_k + (pre & 0xffffu) + __popc(bk & lt);
+            f.keys[u] = (top | ((items[j] & ~0xfffull) >> tb)) >> lz;
+            f.key_grp[u] = g;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Bucket-local sort (the last pass of the MSD sort).
 //
 // After the partition by the top `tb` bits of the normalised hash (normalised = shifted left by the `lz`
@@ -111,7 +235,7 @@ __global__ void __launch_bounds__(LS_THREADS, 3)
 bucket_sort_kernel(const uint64_t* __restrict__ in_hash, const uint64_t* __restrict__ in_loc,
                    uint64_t* __restrict__ out_hash, uint64_t* __restrict__ out_loc,
                    const uint32_t* __restrict__ start, int lz, int tb, uint64_t* __restrict__ counts,
-                   uint32_t* __restrict__ t_size, uint32_t long_threshold, int n_pass) {
+                   uint32_t* __restrict__ t_size, uint32_t long_threshold, int n_pass, CsrOut f) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t* B = reinterpret_cast<uint64_t*>(smem_raw);                  // [LS_CAP] items, grouped by digit
     uint16_t* cnt = reinterpret_cast<uint16_t*>(B + (n_pass == 2 ? 2 : 1) * LS_CAP);  // [LS_WARPS][LS_ND] warp-private counters
@@ -119,13 +243,12 @@ bucket_sort_kernel(const uint64_t* __restrict__ in_hash, const uint64_t* __restr
     __shared__ uint32_t s_wsum[LS_WARPS];
     __shared__ uint32_t s_nlong;
     __shared__ uint32_t s_long[LS_ND];
-    __shared__ uint32_t s_tk[LS_WARPS], s_tg[LS_WARPS];
 
     const uint32_t b = blockIdx.x;
     const uint32_t s = start[b], e = start[b + 1];
     const uint32_t m = e - s;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (m == 0) { if (tid == 0) counts[b] = 0; return; }
+    if (m == 0) { if (tid == 0) counts[b] = 0; bucket_empty(b, f); return; }
     if (m > (uint32_t)LS_CAP) return;  // oversize: sorted and counted by the host-driven fallback
     const int sh = lz + tb;  // >= 12 on this path: the low 12 bits of (hash << sh) are zero and carry the index
 
@@ -269,42 +392,7 @@ bucket_sort_kernel(const uint64_t* __restrict__ in_hash, const uint64_t* __restr
         __syncthreads();
     }
 
-    // write back in final order; count key heads and (hash, protein) group heads
-    const uint64_t top = tb ? ((uint64_t)b << (64 - tb)) : 0ull;
-    uint32_t tk = 0, tg = 0;
-    for (uint32_t j0 = 0; j0 < m; j0 += LS_THREADS) {
-        const uint32_t j = j0 + tid;
-        bool hk = false, hg = false;
-        uint64_t item = 0, loc = 0;
-        if (j < m) {
-            item = B[j];
-            loc = in_loc[s + (uint32_t)(item & 0xfffu)];  // gathered from the bucket's own 23 KB window (L1/L2)
-        }
-        // the predecessor sits in the lane below; lane 0 looks it up
-        uint64_t prev = __shfl_up_sync(0xffffffffu, item, 1);
-        uint32_t ppid = __shfl_up_sync(0xffffffffu, (uint32_t)(loc >> 32), 1);
-        if (j < m) {
-            out_hash[s + j] = (top | ((item & ~0xfffull) >> tb)) >> lz;
-            out_loc[s + j] = loc;
-            if (j == 0) {
-                hk = hg = true;  // a bucket's first tuple differs from everything before it in its top bits
-            } else {
-                if (lane == 0) { prev = B[j - 1]; ppid = (uint32_t)(in_loc[s + (uint32_t)(prev & 0xfffu)] >> 32); }
-                hk = ((prev ^ item) >> 12) != 0;
-                hg = hk || ppid != (uint32_t)(loc >> 32);
-            }
-            if (!hg) atomicSub(&t_size[(uint32_t)(loc >> 32)], 1u);
-        }
-        tk += __popc(__ballot_sync(0xffffffffu, hk));
-        tg += __popc(__ballot_sync(0xffffffffu, hg));
-    }
-    if (lane == 0) { s_tk[warp] = tk; s_tg[warp] = tg; }
-    __syncthreads();
-    if (tid == 0) {
-        uint32_t k = 0, g = 0;
-        for (int w = 0; w < LS_WARPS; w++) { k += s_tk[w]; g += s_tg[w]; }
-        counts[b] = (uint64_t)k | ((uint64_t)g << 32);
-    }
+    bucket_finish(B, m, s, b, lz, tb, in_loc, out_hash, out_loc, counts, t_size, f);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -319,7 +407,7 @@ __global__ void __launch_bounds__(LS_THREADS)
 bucket_sort_rep_kernel(const uint64_t* __restrict__ in_hash, const uint64_t* __restrict__ in_loc,
                    uint64_t* __restrict__ out_hash, uint64_t* __restrict__ out_loc,
                    const uint32_t* __restrict__ start, int lz, int tb, uint64_t* __restrict__ counts,
-                   uint32_t* __restrict__ t_size) {
+                   uint32_t* __restrict__ t_size, CsrOut f) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t* A = reinterpret_cast<uint64_t*>(smem_raw);
     uint64_t* B = A + LS_CAP;
@@ -327,13 +415,12 @@ bucket_sort_rep_kernel(const uint64_t* __restrict__ in_hash, const uint64_t* __r
     uint32_t* dbase = reinterpret_cast<uint32_t*>(cnt + LS_WARPS * 256);  // [256] exclusive digit offsets
     __shared__ uint32_t s_wsum[8];
     __shared__ uint32_t s_ninv;
-    __shared__ uint32_t s_tk[LS_WARPS], s_tg[LS_WARPS];
 
     const uint32_t b = blockIdx.x;
     const uint32_t s = start[b], e = start[b + 1];
     const uint32_t m = e - s;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (m == 0) { if (tid == 0) counts[b] = 0; return; }
+    if (m == 0) { if (tid == 0) counts[b] = 0; bucket_empty(b, f); return; }
     if (m > (uint32_t)LS_CAP) return;  // oversize: sorted and counted by the host-driven fallback
     const int sh = lz + tb;  // >= 12 on this path: the low 12 bits of (hash << sh) are zero and carry the index
 
@@ -514,42 +601,7 @@ bucket_sort_rep_kernel(const uint64_t* __restrict__ in_hash, const uint64_t* __r
         __syncthreads();
     }
 
-    // write back in final order; count key heads and (hash, protein) group heads
-    const uint64_t top = tb ? ((uint64_t)b << (64 - tb)) : 0ull;
-    uint32_t tk = 0, tg = 0;
-    for (uint32_t j0 = 0; j0 < m; j0 += LS_THREADS) {
-        const uint32_t j = j0 + tid;
-        bool hk = false, hg = false;
-        uint64_t item = 0, loc = 0;
-        if (j < m) {
-            item = src[j];
-            loc = in_loc[s + (uint32_t)(item & 0xfffu)];  // gathered from the bucket's own 23 KB window (L1/L2)
-        }
-        // the predecessor sits in the lane below; lane 0 looks it up
-        uint64_t prev = __shfl_up_sync(0xffffffffu, item, 1);
-        uint32_t ppid = __shfl_up_sync(0xffffffffu, (uint32_t)(loc >> 32), 1);
-        if (j < m) {
-            out_hash[s + j] = (top | ((item & ~0xfffull) >> tb)) >> lz;
-            out_loc[s + j] = loc;
-            if (j == 0) {
-                hk = hg = true;  // a bucket's first tuple differs from everything before it in its top bits
-            } else {
-                if (lane == 0) { prev = src[j - 1]; ppid = (uint32_t)(in_loc[s + (uint32_t)(prev & 0xfffu)] >> 32); }
-                hk = ((prev ^ item) >> 12) != 0;
-                hg = hk || ppid != (uint32_t)(loc >> 32);
-            }
-            if (!hg) atomicSub(&t_size[(uint32_t)(loc >> 32)], 1u);
-        }
-        tk += __popc(__ballot_sync(0xffffffffu, hk));
-        tg += __popc(__ballot_sync(0xffffffffu, hg));
-    }
-    if (lane == 0) { s_tk[warp] = tk; s_tg[warp] = tg; }
-    __syncthreads();
-    if (tid == 0) {
-        uint32_t k = 0, g = 0;
-        for (int w = 0; w < LS_WARPS; w++) { k += s_tk[w]; g += s_tg[w]; }
-        counts[b] = (uint64_t)k | ((uint64_t)g << 32);
-    }
+    bucket_finish(src, m, s, b, lz, tb, in_loc, out_hash, out_loc, counts, t_size, f);
 }
 
 
@@ -755,9 +807,9 @@ uint64_t max_ranges(uint64_t n) {
 }
 
 size_t table_bytes(uint64_t n) {
-    // start[nb+1] + oversize[2] (u32), counts[nb] + prefix[nb+1] (u64)
+    // start[nb+1] + oversize[2] (u32), counts[nb] + prefix[nb+1] + status[nb] (u64)
     const uint64_t nb = max_ranges(n);
-    return (size_t)(((nb + 8) * 4 + (2 * nb + 4) * 8 + 1023) & ~(size_t)255);
+    return (size_t)(((nb + 8) * 4 + (3 * nb + 4) * 8 + 1023) & ~(size_t)255);
 }
 
 }  // namespace
@@ -803,6 +855,7 @@ cudaError_t build_index(const BuildArgs& a, cudaStream_t stream, int* out_in_a, 
     uint32_t* oversize = start + nb + 1;                                          // [2]
     uint64_t* counts = (uint64_t*)(tp + (((size_t)(nb + 8) * 4 + 7) & ~(size_t)7));  // [nb]
     uint64_t* prefix = counts + nb;                                               // [nb + 1]
+    uint64_t* status = prefix + nb + 1;                                           // [nb] look-back words (fused CSR)
 
     const uint64_t *fh, *fl;  // final sorted tuples
     if (tb < 0) {
@@ -832,14 +885,18 @@ cudaError_t build_index(const BuildArgs& a, cudaStream_t stream, int* out_in_a, 
         KS_TRY(cudaFuncSetAttribute(bucket_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LS_SMEM2));
         const char* lt_env = getenv("KS_LS_LONG");  // test hook: force the warp path for short sub-buckets too
         const uint32_t long_thr = lt_env ? (uint32_t)atoi(lt_env) : (uint32_t)LS_LONG;
+        CsrOut f;
+        f.status = status; f.oversize = oversize; f.keys = a.keys; f.key_grp = a.key_grp; f.grp_start = a.grp_start;
+        f.d_counts = a.d_counts; f.n = n; f.nb = nb;
+        KS_TRY(cudaMemsetAsync(status, 0, (size_t)nb * 8, stream));
         // repeat-heavy inputs (small k-mer space) take the two-pass variant; KS_LS_VARIANT=rep|uni is a test hook
         const char* v_env = getenv("KS_LS_VARIANT");
         const bool rep = v_env ? (v_env[0] == 'r') : (a.repeat_heavy != 0);
         if (rep) {
             KS_TRY(cudaFuncSetAttribute(bucket_sort_rep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LS_SMEM_REP));
-            bucket_sort_rep_kernel<<<nb, LS_THREADS, LS_SMEM_REP, stream>>>(sh, sl, dh, dl, start, lz, tb, counts, a.t_size);
+            bucket_sort_rep_kernel<<<nb, LS_THREADS, LS_SMEM_REP, stream>>>(sh, sl, dh, dl, start, lz, tb, counts, a.t_size, f);
         } else {
-            bucket_sort_kernel<<<nb, LS_THREADS, LS_SMEM, stream>>>(sh, sl, dh, dl, start, lz, tb, counts, a.t_size, long_thr, 1);
+            bucket_sort_kernel<<<nb, LS_THREADS, LS_SMEM, stream>>>(sh, sl, dh, dl, start, lz, tb, counts, a.t_size, long_thr, 1, f);
         }
         KS_TRY(cudaGetLastError());
         *sort_launches += 3;
@@ -866,6 +923,11 @@ cudaError_t build_index(const BuildArgs& a, cudaStream_t stream, int* out_in_a, 
         fh = dh;
         fl = dl;
         if (a.ev_sorted) KS_TRY(cudaEventRecord(a.ev_sorted, stream));
+        if (n_over == 0) {  // the bucket sort wrote keys / key_grp / grp_start itself: only the directory is left
+            dir_kernel<<<148 * 8, 256, 0, stream>>>(a.keys, a.d_counts, a.dir, a.dir_bits, a.dir_shift);
+            *csr_launches += 1;
+            return cudaGetLastError();
+        }
     }
     // 4. scan of the range counts, CSR write, directory
     scan_counts_kernel<<<1, 1024, 0, stream>>>(counts, nb, prefix, n, a.d_counts, a.key_grp, a.grp_start);

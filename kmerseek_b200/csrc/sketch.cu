@@ -448,6 +448,7 @@ sketch_quad_kernel(SketchArgs a, Lut256 lut, uint32_t* __restrict__ ticket, uint
 
     const uint32_t lt = (1u << lane) - 1u;
     const uint32_t g0_lo = (uint32_t)g0;
+    bool zero_seen = false;
     uint32_t wcount = 0;  // tuples staged by this warp so far (uniform across the warp)
 #pragma unroll
     for (int rr = 0; rr < SQ_ROWS; rr++) {
@@ -473,7 +474,7 @@ sketch_quad_kernel(SketchArgs a, Lut256 lut, uint32_t* __restrict__ ticket, uint
             h[j] = murmur_limbs<K>(b);
             if (FULL) {
                 keep[j] = valid;  // the count was fixed in advance; a zero hash (1 in 2^64) sends the batch to the general path
-                if (valid && h[j] == 0) atomicOr(ticket + 1, 1u);
+                zero_seen |= valid && h[j] == 0;
             } else {
                 keep[j] = valid && h[j] != 0 && h[j] <= a.max_hash;
             }
@@ -500,6 +501,7 @@ sketch_quad_kernel(SketchArgs a, Lut256 lut, uint32_t* __restrict__ ticket, uint
         wcount += total;
     }
 
+    if (FULL && zero_seen) atomicOr(ticket + 1, 1u);
     if (lane == 0) s_wtot[warp] = wcount;
     __syncthreads();
     uint32_t wprefix = 0, btotal = 0;
