@@ -316,6 +316,20 @@ class ProteomeIndex:
         prot.close()
         return sigs
 
+    def sketch_proteome(self, proteome: "Proteome"):
+        """[(mins, abunds)] for every protein of a packed proteome (ks_sketch_batch); the index is left untouched."""
+        out = C.POINTER(_ffi.ks_sketch)()
+        check(_ffi.lib().ks_sketch_batch(self._h, proteome._h, C.byref(out)))
+        try:
+            s = out.contents
+            P = s.n_proteins
+            sig_ptr = _np(s.sig_ptr, P + 1, np.uint64)
+            E = int(sig_ptr[-1]) if P else 0
+            mins, abunds = _np(s.mins, E, np.uint64), _np(s.abunds, E, np.uint64)
+        finally:
+            _ffi.lib().ks_sketch_free(out)
+        return [(mins[int(sig_ptr[i]):int(sig_ptr[i + 1])], abunds[int(sig_ptr[i]):int(sig_ptr[i + 1])]) for i in range(P)]
+
     def create_protein_signature(self, sequence, name):
         """src/rust/index.rs:719-747"""
         return self.create_protein_signatures([sequence], [name])[0]

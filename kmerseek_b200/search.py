@@ -65,12 +65,25 @@ def search(index: ProteomeIndex, queries: Proteome, hits=True) -> SearchResult:
         _ffi.lib().ks_search_result_free(out)
 
 
-def manysearch_rows(result: SearchResult, index: ProteomeIndex, query_names, target_names=None, target_sketches=None):
-    """The 22-column manysearch table (tests/test_search.py:33) as a list of dicts."""
+def manysearch_rows(result: SearchResult, index: ProteomeIndex, query_names, target_names=None, target_sketches=None,
+                    targets: Proteome = None):
+    """The 22-column manysearch table (tests/test_search.py:33) as a list of dicts.  `match_md5` needs the matched
+    targets' sketches: pass `targets` (the indexed proteome) and only the matched proteins are sketched again, or
+    `target_sketches`; otherwise every sketch of the index is exported."""
     target_names = target_names if target_names is not None else index.names()
+    p = result.pairs
+    if target_sketches is None and targets is not None:
+        matched = np.unique(p["pair_pid"]).astype(np.int64)
+        offs, res = targets.offsets.astype(np.int64), targets.residues
+        lens = offs[matched + 1] - offs[matched]
+        sub_offs = np.zeros(len(matched) + 1, dtype=np.uint64)
+        np.cumsum(lens, out=sub_offs[1:])
+        idx = np.repeat(offs[matched] - sub_offs[:-1].astype(np.int64), lens) + np.arange(int(sub_offs[-1]))
+        sub = Proteome.from_packed(res[idx], sub_offs)
+        target_sketches = dict(zip(matched.tolist(), index.sketch_proteome(sub)))
+        sub.close()
     if target_sketches is None:
         target_sketches = index.export_sketches()
-    p = result.pairs
     rows = []
     qmd5 = {}
     for j in range(result.n_pairs):

@@ -3,6 +3,7 @@ Bit-exact for hashes, retained k-mers, positions, postings and hit lists; scores
 (the tolerance BASELINE.json's north_star states).  Needs a GPU: run with -m gpu."""
 import csv
 import io
+import os
 
 import numpy as np
 import pytest
@@ -407,3 +408,46 @@ def test_bucket_sort_both_variants(K, O, monkeypatch, variant):
             okeys, orow, ops, oqs = O.build_index(oh, opid, opos)
             assert np.array_equal(keys, okeys) and np.array_equal(row_ptr, orow)
             assert np.array_equal(pid, ops) and np.array_equal(pos, oqs)
+
+
+def test_cli_search_and_index_against_goldens(K, golden_search, golden_sigs, tmp_path):
+    """`python -m kmerseek_b200 search|index` end to end (tests/test_search.py:9-60,63-139, src/rust/tests/test_cli.rs)."""
+    import json
+    import subprocess
+    import sys
+    import zipfile
+    import gzip
+    from conftest import ROOT
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    base = [sys.executable, "-m", "kmerseek_b200"]
+    r = subprocess.run(base + ["search", "--ksize", "16", fasta_path("ced9.fasta"), fasta_path("bcl2_first25.fasta.gz")],
+                       capture_output=True, text=True, env=env)
+    assert r.returncode == 0, r.stderr
+    got = {x["match_name"]: x for x in csv.DictReader(io.StringIO(r.stdout))}
+    gold = list(csv.DictReader(io.StringIO(golden_search["manysearch_csv"])))
+    assert len(got) == len(gold) == 5
+    for g in gold:
+        for c, v in g.items():
+            try:
+                assert float(got[g["match_name"]][c]) == pytest.approx(float(v), rel=SCORE_RTOL), c
+            except ValueError:
+                assert got[g["match_name"]][c] == v, c
+    r = subprocess.run(base + ["search", "--extract-kmers", "--ksize", "16", fasta_path("ced9.fasta"),
+                               fasta_path("bcl2_first25.fasta.gz")], capture_output=True, text=True, env=env)
+    assert r.returncode == 0, r.stderr
+    key = lambda x: x["match_name"]
+    assert sorted(csv.DictReader(io.StringIO(r.stdout)), key=key) == \
+        sorted(csv.DictReader(io.StringIO(golden_search["stitched_csv"])), key=key)
+    assert "query: MSIGESIDGKINDWEEPGIVGVVVCGRMMFSLK (59-92)" in r.stderr  # tests/test_search.py:112-117
+    out = tmp_path / "db"
+    r = subprocess.run(base + ["index", "--input", fasta_path("bcl2_first25.fasta.gz"), "--output", str(out), "--ksize", "16",
+                               "--scaled", "5", "--encoding", "hp"], capture_output=True, text=True, env=env)
+    assert r.returncode == 0 and "Indexing completed successfully!" in r.stdout and out.exists()  # test_cli.rs:46
+    z = zipfile.ZipFile(out / "bcl2_first25.fasta.gz.hp.k16.scaled5.sig.zip")
+    for s in golden_sigs["hp.k16.scaled5"]["signatures"]:
+        sk = json.loads(gzip.decompress(z.read(f"signatures/{s['md5sum']}.sig.gz")))[0]["signatures"][0]
+        assert [str(x) for x in sk["mins"]] == s["mins"] and sk["abundances"] == s["abundances"]
+    r = subprocess.run(base + ["index", "--input", str(tmp_path / "nope.fasta")], capture_output=True, text=True, env=env)
+    assert r.returncode != 0 and "No such file or directory" in r.stderr  # test_cli.rs:125
+    r = subprocess.run(base + ["index"], capture_output=True, text=True, env=env)
+    assert r.returncode != 0 and "required" in r.stderr  # test_cli.rs:135
