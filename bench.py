@@ -193,8 +193,7 @@ def main():
 
     def build_from_host():
         chk(L.ks_index_clear(idx._h))
-        chk(L.ks_index_upload(idx._h, prot._h))
-        chk(L.ks_index_sketch_resident(idx._h))
+        chk(L.ks_index_add_proteome(idx._h, prot._h))  # pinned host buffers -> HBM (chunked) overlapped with the sketch
         chk(L.ks_index_finalize(idx._h))
         return idx.stats()  # the step's result read back on the host
 

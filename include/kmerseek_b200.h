@@ -232,7 +232,8 @@ typedef struct ks_search_result {
     uint64_t n_hits;
     uint32_t *hit_qid, *hit_pid, *hit_qpos, *hit_tpos;
     uint64_t *hit_hash;
-    /* device-resident copies of the pair/hit columns (valid until ks_search_result_free); used by
+    /* device-resident copies of the pair/hit columns (kept only with KS_SEARCH_DEVICE_ONLY, then valid until
+     * ks_search_result_free, which must precede ks_index_destroy); used by
      * the multi-GPU host to gather shards with NCCL without a host round trip.  Layout: see
      * ks_search_result_device_column(). */
     void *device_block;

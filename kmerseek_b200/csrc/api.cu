@@ -267,6 +267,8 @@ struct ks_index {
     uint64_t max_hash = 0;
     int lz = 0;  // known-zero leading bits of every kept hash
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;  // H2D of residue chunks while earlier tiles are being hashed
+    cudaEvent_t ev_chunk[9] = {};
     cudaEvent_t ev[12] = {};
     uint64_t live_bytes = 0;
     Arena* arena = nullptr;
@@ -394,6 +396,77 @@ void sketch_resident(ks_index* x) {
     x->n_prot += b.n_prot;
     x->n_res += b.n_res;
     x->n_windows += b.n_windows;
+}
+
+// upload + sketch with the residues streamed in: the offsets go first (everything the tile -> protein map and
+// the exact tile bases need), then the residues in chunks on the copy stream; the fused kernel runs over the
+// tile range of a chunk as soon as that chunk has landed.  Exact path only (scaled == 1): tile bases are known
+// before any hash.  Returns false when the batch does not qualify (caller takes upload + sketch_resident).
+bool add_proteome_pipelined(ks_index* x, const ks_proteome* p) {
+    constexpr int CHUNKS = 8;
+    if (x->max_hash != ~0ull || x->params.ksize > (uint32_t)SK_MAX_TEMPLATE_K || getenv("KS_SKETCH_GENERAL") ||
+        getenv("KS_NO_PIPELINE"))  // test hooks
+        return false;
+    if (p->n_res < (64u << 20) || p->n_prot == 0) return false;  // small batches: one copy, one launch
+    if (x->finalized) fail(KS_ERR_VALIDATION, "Validation error: index is finalized; ks_index_clear before adding more");
+    if (p->n_prot >= 0xffffffffull || x->n_prot + p->n_prot >= 0xffffffffull) fail(KS_ERR_CAPACITY, "more than 2^32-2 proteins on one shard");
+    DeviceBatch& b = x->batch;
+    if (p->n_res + 64 > b.res_cap) {
+        if (b.res) x->arena->release(b.res);
+        b.res_cap = p->n_res + 64;
+        b.res = x->arena->alloc<uint8_t>(b.res_cap);
+    }
+    if (p->n_prot + 1 > b.offs_cap) {
+        if (b.offs) x->arena->release(b.offs);
+        b.offs_cap = p->n_prot + 1;
+        b.offs = x->arena->alloc<uint64_t>(b.offs_cap);
+    }
+    b.n_prot = p->n_prot; b.n_res = p->n_res;
+    b.n_windows = count_windows(p->offsets, p->n_prot, x->params.ksize);
+    b.valid = true;
+    grow_tuples(x, x->n_tuples + b.n_windows);
+    ensure_ws(x, sketch_workspace_bytes(b.n_res));
+    KS_CUDA(cudaEventRecord(x->ev[EV_UP0], x->stream));
+    KS_CUDA(cudaEventRecord(x->ev[EV_SK0], x->stream));
+    // buffers were (re)allocated in compute-stream order: the copy stream must not run ahead of that
+    KS_CUDA(cudaEventRecord(x->ev_chunk[CHUNKS], x->stream));
+    KS_CUDA(cudaStreamWaitEvent(x->copy_stream, x->ev_chunk[CHUNKS], 0));
+    KS_CUDA(cudaMemcpyAsync(b.offs, p->offsets, (p->n_prot + 1) * 8, cudaMemcpyHostToDevice, x->stream));
+    SketchArgs a;
+    a.residues = b.res; a.offsets = b.offs; a.n_res = b.n_res; a.n_prot = b.n_prot;
+    a.k = x->params.ksize; a.moltype = x->params.moltype; a.max_hash = x->max_hash; a.pid_base = (uint32_t)x->n_prot;
+    a.out_hash = x->d_hash + x->n_tuples; a.out_loc = x->d_loc + x->n_tuples; a.capacity = x->cap - x->n_tuples;
+    a.d_count = x->d_count; a.workspace = x->ws; a.force_general = 0;
+    KS_CUDA(launch_sketch_prepare(a, x->stream, &x->l_sketch));
+    const uint64_t nt = (b.n_res + SK_TILE - 1) / SK_TILE;
+    const uint64_t per = (nt + CHUNKS - 1) / CHUNKS;
+    for (int c = 0; c < CHUNKS; c++) {
+        const uint64_t t0 = (uint64_t)c * per, t1 = std::min<uint64_t>(nt, t0 + per);
+        if (t0 >= t1) break;
+        const uint64_t byte0 = t0 * SK_TILE;
+        const uint64_t byte1 = std::min<uint64_t>(p->n_res + 64, t1 * SK_TILE + 64);  // halo of the last tile included
+        KS_CUDA(cudaMemcpyAsync(b.res + byte0, p->residues + byte0, byte1 - byte0, cudaMemcpyHostToDevice, x->copy_stream));
+        KS_CUDA(cudaEventRecord(x->ev_chunk[c], x->copy_stream));
+        KS_CUDA(cudaStreamWaitEvent(x->stream, x->ev_chunk[c], 0));
+        a.tile_begin = (uint32_t)t0; a.tile_end = (uint32_t)t1;
+        KS_CUDA(launch_sketch_tiles(a, x->stream, &x->l_sketch));
+    }
+    KS_CUDA(launch_sketch_finish(a, x->stream));
+    uint64_t r[2] = {0, 0};
+    KS_CUDA(cudaMemcpyAsync(r, x->d_count, 16, cudaMemcpyDeviceToHost, x->stream));
+    KS_CUDA(cudaEventRecord(x->ev[EV_UP1], x->stream));
+    KS_CUDA(cudaEventRecord(x->ev[EV_SK1], x->stream));
+    KS_CUDA(cudaStreamSynchronize(x->stream));
+    x->t_upload = x->t_sketch = true;
+    if ((r[1] >> 32) != 0) {  // a zero hash: redo the batch (now resident) on the look-back path
+        sketch_resident(x);
+        return true;
+    }
+    x->n_tuples += r[0];
+    x->n_prot += b.n_prot;
+    x->n_res += b.n_res;
+    x->n_windows += b.n_windows;
+    return true;
 }
 
 static double now_ms() {
@@ -563,6 +636,8 @@ ks_status ks_index_create(const ks_params* params, ks_index** out) {
         try {
             x->use();
             KS_CUDA(cudaStreamCreateWithFlags(&x->stream, cudaStreamNonBlocking));
+            KS_CUDA(cudaStreamCreateWithFlags(&x->copy_stream, cudaStreamNonBlocking));
+            for (auto& e : x->ev_chunk) KS_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
             for (auto& e : x->ev) KS_CUDA(cudaEventCreate(&e));
             cudaMemPool_t pool;
             KS_CUDA(cudaDeviceGetDefaultMemPool(&pool, params->device));
@@ -585,6 +660,8 @@ void ks_index_destroy(ks_index* x) {
     delete x->arena;
     if (x->stream) cudaStreamSynchronize(x->stream);
     for (auto& e : x->ev) if (e) cudaEventDestroy(e);
+    for (auto& e : x->ev_chunk) if (e) cudaEventDestroy(e);
+    if (x->copy_stream) { cudaStreamSynchronize(x->copy_stream); cudaStreamDestroy(x->copy_stream); }
     if (x->stream) cudaStreamDestroy(x->stream);
     delete x;
 }
@@ -613,7 +690,14 @@ ks_status ks_index_sketch_resident(ks_index* x) {
     return guarded([&] { x->use(); sketch_resident(x); });
 }
 ks_status ks_index_add_proteome(ks_index* x, const ks_proteome* p) {
-    ks_status s = ks_index_upload(x, p);
+    bool done = false;
+    ks_status s = guarded([&] {
+        if (!x || !p) fail(KS_ERR_VALIDATION, "Validation error: null argument");
+        x->use();
+        done = add_proteome_pipelined(x, p);
+    });
+    if (s != KS_OK || done) return s;
+    s = ks_index_upload(x, p);
     return s != KS_OK ? s : ks_index_sketch_resident(x);
 }
 ks_status ks_index_finalize(ks_index* x) {
@@ -839,6 +923,13 @@ ks_status ks_search_resident(ks_index* x, uint32_t flags, ks_search_result** out
             free(first);
             KS_CUDA(cudaEventElapsedTime(&r->ms_device, x->ev[EV_Q0], x->ev[EV_Q1]));
             x->ms_search = r->ms_device;
+            if (!(flags & KS_SEARCH_DEVICE_ONLY)) {
+                // the host copy is complete: give the device columns back now, so that the result no longer
+                // depends on the index (and its stream) staying alive
+                delete rd->arena;
+                rd->arena = nullptr;
+                rd->cols.clear();
+            }
         } catch (...) {
             ks_search_result_free(r);
             throw;

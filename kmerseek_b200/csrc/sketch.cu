@@ -395,7 +395,7 @@ sketch_quad_kernel(SketchArgs a, Lut256 lut, uint32_t* __restrict__ ticket, uint
     if (!FULL && tid == 0) s_tile = atomicAdd(ticket, 1u);
     if (TRANSLATE) s_lut[tid] = lut.b[tid];
     if (!FULL || TRANSLATE) __syncthreads();
-    const uint32_t tile = FULL ? blockIdx.x : s_tile;
+    const uint32_t tile = FULL ? blockIdx.x + a.tile_begin : s_tile;
     const uint64_t g0 = (uint64_t)tile * SK_TILE;
     const uint64_t n_tiles = n_tiles_of(a.n_res);
     const uint32_t p_lo = tile_pid[tile], p_hi = tile_pid[tile + 1];
@@ -538,7 +538,8 @@ sketch_quad_kernel(SketchArgs a, Lut256 lut, uint32_t* __restrict__ ticket, uint
 
 template <int K>
 cudaError_t launch_k(const SketchArgs& a, const Lut256& lut, const Workspace& w, uint64_t n_tiles, cudaStream_t st) {
-    const unsigned grid = (unsigned)n_tiles;
+    const bool ranged = a.tile_end > a.tile_begin;  // exact path only: a sub-range of the tiles
+    const unsigned grid = ranged ? (unsigned)(a.tile_end - a.tile_begin) : (unsigned)n_tiles;
     if constexpr (K == 0) {
         if (a.moltype == 0)
             sketch_kernel<0, false><<<grid, SK_THREADS, 0, st>>>(a, lut, w.ticket, w.status, w.tile_pid);
@@ -606,16 +607,21 @@ size_t sketch_workspace_bytes(uint64_t n_res) {
     return ((16 + nt * 8 + (nt + 1) * 4 + 15) & ~(size_t)15) + 2 * (nt + 1) * 8 + scan_temp_bytes_for(nt + 1) + 64;
 }
 
-cudaError_t launch_sketch(const SketchArgs& a, cudaStream_t stream, uint64_t* n_launches) {
+static bool exact_path(const SketchArgs& a) {
+    return a.max_hash == ~0ull && !a.force_general && a.k <= (uint32_t)SK_MAX_TEMPLATE_K;
+}
+
+cudaError_t launch_sketch_prepare(const SketchArgs& a, cudaStream_t stream, uint64_t* n_launches) {
     if (a.n_res == 0 || a.n_prot == 0) return cudaMemsetAsync(a.d_count, 0, 16, stream);
     const uint64_t nt = n_tiles_of(a.n_res);
     Workspace w = carve(a.workspace, a.n_res);
-    const bool exact = a.max_hash == ~0ull && !a.force_general && a.k <= (uint32_t)SK_MAX_TEMPLATE_K;
+    const bool exact = exact_path(a);
     cudaError_t e = cudaMemsetAsync(a.workspace, 0, exact ? 16 : 16 + nt * 8, stream);
     if (e != cudaSuccess) return e;
     tile_pid_kernel<<<(unsigned)((nt + 1 + 255) / 256), 256, 0, stream>>>(a.offsets, a.n_prot, nt, w.tile_pid);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
+    if (n_launches) *n_launches += 1;
     if (exact) {
         tile_count_kernel<<<(unsigned)((nt + 1 + 255) / 256), 256, 0, stream>>>(a.offsets, a.n_res, a.k, nt, w.tile_pid, w.tile_cnt);
         size_t tb = w.scan_temp_bytes;
@@ -623,14 +629,36 @@ cudaError_t launch_sketch(const SketchArgs& a, cudaStream_t stream, uint64_t* n_
         if (e != cudaSuccess) return e;
         if (n_launches) *n_launches += 3;
     }
+    return cudaSuccess;
+}
+
+// The fused kernel over tiles [a.tile_begin, a.tile_end) (exact path; 0, 0 = all tiles).
+cudaError_t launch_sketch_tiles(const SketchArgs& a, cudaStream_t stream, uint64_t* n_launches) {
+    if (a.n_res == 0 || a.n_prot == 0) return cudaSuccess;
+    const uint64_t nt = n_tiles_of(a.n_res);
+    Workspace w = carve(a.workspace, a.n_res);
     Lut256 lut;
     fill_lut(a.moltype, &lut);
-    e = Dispatch<SK_MAX_TEMPLATE_K>::run(a, lut, w, nt, stream);
-    if (e != cudaSuccess) return e;
-    // d_count[1] <- zero-hash flag of the exact path (always 0 on the general path)
-    e = cudaMemcpyAsync(a.d_count + 1, w.ticket, 8, cudaMemcpyDeviceToDevice, stream);
-    if (n_launches) *n_launches += 2;
+    cudaError_t e = Dispatch<SK_MAX_TEMPLATE_K>::run(a, lut, w, nt, stream);
+    if (n_launches) *n_launches += 1;
     return e;
+}
+
+// d_count[1] <- zero-hash flag of the exact path (always 0 on the general path)
+cudaError_t launch_sketch_finish(const SketchArgs& a, cudaStream_t stream) {
+    if (a.n_res == 0 || a.n_prot == 0) return cudaSuccess;
+    Workspace w = carve(a.workspace, a.n_res);
+    return cudaMemcpyAsync(a.d_count + 1, w.ticket, 8, cudaMemcpyDeviceToDevice, stream);
+}
+
+bool sketch_is_exact(const SketchArgs& a) { return exact_path(a); }
+
+cudaError_t launch_sketch(const SketchArgs& a, cudaStream_t stream, uint64_t* n_launches) {
+    cudaError_t e = launch_sketch_prepare(a, stream, n_launches);
+    if (e != cudaSuccess) return e;
+    e = launch_sketch_tiles(a, stream, n_launches);
+    if (e != cudaSuccess) return e;
+    return launch_sketch_finish(a, stream);
 }
 
 }  // namespace ks

@@ -28,12 +28,19 @@ struct SketchArgs {
     uint64_t* d_count;         // device u64[2]: [0] tuples kept by this launch (may exceed capacity: nothing is written
                                // past it); [1] low word = ticket, high word != 0: a zero hash was met on the exact path
     int force_general;         // 1: take the look-back path even when scaled == 1
+    uint32_t tile_begin = 0, tile_end = 0;  // exact path: launch_sketch_tiles covers [tile_begin, tile_end); 0,0 = all
     void* workspace;           // sketch_workspace_bytes(n_res)
 };
 
 size_t sketch_workspace_bytes(uint64_t n_res);
 // Enqueues memset + tile->protein map + the fused kernel on `stream`; adds the number of kernels launched.
 cudaError_t launch_sketch(const SketchArgs& a, cudaStream_t stream, uint64_t* n_launches);
+// The same in three steps, so that the host can stream the residues in while earlier tiles are hashed:
+// prepare needs only the offsets; tiles [tile_begin, tile_end) need the residues up to tile_end * SK_TILE + k.
+cudaError_t launch_sketch_prepare(const SketchArgs& a, cudaStream_t stream, uint64_t* n_launches);
+cudaError_t launch_sketch_tiles(const SketchArgs& a, cudaStream_t stream, uint64_t* n_launches);
+cudaError_t launch_sketch_finish(const SketchArgs& a, cudaStream_t stream);
+bool sketch_is_exact(const SketchArgs& a);
 void fill_lut(int moltype, Lut256* lut);
 
 }  // namespace ks

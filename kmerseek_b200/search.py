@@ -25,11 +25,21 @@ HIT_COLUMNS = {"hit_qid": np.uint32, "hit_pid": np.uint32, "hit_qpos": np.uint32
 
 
 class SearchResult:
-    """Host copy of a ks_search_result: `pairs` (dict of columns, ordered by (query, target)), `hits`
-    (dict of columns, ordered by (query, qpos, target, tpos)), `query_sketches` [(mins, abunds)]."""
+    """A ks_search_result on the host: `pairs` (dict of columns, ordered by (query, target)), `hits`
+    (dict of columns, ordered by (query, qpos, target, tpos)), `query_sketches` [(mins, abunds)].
+    The pair / hit columns are numpy views of the library's pinned result block (no second copy of what can be
+    a gigabyte); the block is released when this object is."""
 
-    def __init__(self, pairs, hits, query_sketches, ms_device):
+    def __init__(self, pairs, hits, query_sketches, ms_device, owner=None):
         self.pairs, self.hits, self.query_sketches, self.ms_device = pairs, hits, query_sketches, ms_device
+        self._owner = owner  # POINTER(ks_search_result) kept alive for the views
+
+    def close(self):
+        """Detach from the pinned block: columns become owned copies."""
+        if self._owner is not None:
+            self.pairs = {k: v.copy() for k, v in self.pairs.items()} if self.pairs else self.pairs
+            self.hits = {k: v.copy() for k, v in self.hits.items()} if self.hits else self.hits
+            self._owner = None
 
     @property
     def n_pairs(self):
@@ -40,17 +50,44 @@ class SearchResult:
         return len(self.hits["hit_qid"]) if self.hits else 0
 
 
-def _collect(r, want_hits):
+class _Block:
+    """Frees a ks_search_result when the last numpy view of its pinned block is gone."""
+
+    def __init__(self, ptr):
+        self.ptr = ptr
+
+    def __del__(self):
+        try:
+            if self.ptr is not None:
+                _ffi.lib().ks_search_result_free(self.ptr)
+                self.ptr = None
+        except Exception:
+            pass
+
+
+def _view(ptr, n, dtype, block):
+    if n == 0:
+        return np.zeros(0, dtype=dtype)
+    ctype = {np.uint32: C.c_uint32, np.uint64: C.c_uint64, np.float64: C.c_double}[dtype]
+    arr = (ctype * n).from_address(C.addressof(ptr.contents))
+    arr._block = block  # the view's base keeps the block (and with it the pinned memory) alive
+    return np.frombuffer(arr, dtype=dtype)
+
+
+def _collect(r, want_hits, owner=None):
+    """owner given: columns are views of the pinned block (owner is freed with the SearchResult); else copies."""
+    block = _Block(owner) if owner is not None else None
+    get = (lambda p, n, dt: _view(p, n, dt, block)) if owner is not None else _np
     np_, nh, nq = r.n_pairs, r.n_hits, r.n_queries
-    pairs = {n: _np(getattr(r, n), np_, dt) for n, dt in PAIR_INT_COLUMNS.items()}
+    pairs = {n: get(getattr(r, n), np_, dt) for n, dt in PAIR_INT_COLUMNS.items()}
     for n in _ffi.SCORE_COLUMNS:
-        pairs[n] = _np(getattr(r, n), np_, np.float64)
-    hits = {n: _np(getattr(r, n), nh, dt) for n, dt in HIT_COLUMNS.items()} if want_hits else None
+        pairs[n] = get(getattr(r, n), np_, np.float64)
+    hits = {n: get(getattr(r, n), nh, dt) for n, dt in HIT_COLUMNS.items()} if want_hits else None
     sig_ptr = _np(r.q_sig_ptr, nq + 1, np.uint64)
     E = int(sig_ptr[-1]) if nq else 0
     qm, qa = _np(r.q_mins, E, np.uint64), _np(r.q_abunds, E, np.uint64)
     qs = [(qm[int(sig_ptr[i]):int(sig_ptr[i + 1])], qa[int(sig_ptr[i]):int(sig_ptr[i + 1])]) for i in range(nq)]
-    return SearchResult(pairs, hits, qs, r.ms_device)
+    return SearchResult(pairs, hits, qs, r.ms_device, block)
 
 
 def search(index: ProteomeIndex, queries: Proteome, hits=True) -> SearchResult:
@@ -60,9 +97,10 @@ def search(index: ProteomeIndex, queries: Proteome, hits=True) -> SearchResult:
     out = C.POINTER(_ffi.ks_search_result)()
     check(_ffi.lib().ks_search_batch(index._h, queries._h, flags, C.byref(out)))
     try:
-        return _collect(out.contents, hits)
-    finally:
+        return _collect(out.contents, hits, owner=out)
+    except Exception:
         _ffi.lib().ks_search_result_free(out)
+        raise
 
 
 def manysearch_rows(result: SearchResult, index: ProteomeIndex, query_names, target_names=None, target_sketches=None,

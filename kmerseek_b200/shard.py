@@ -180,11 +180,14 @@ def search_and_gather(index, queries, pid_base=0, hits=False):
         r = out.contents
         if world == 1:
             from .search import _collect
-            res = _collect(r, hits)
-            res.pairs["pair_pid"] = res.pairs["pair_pid"] + np.uint32(pid_base)
-            if hits:
-                res.hits["hit_pid"] = res.hits["hit_pid"] + np.uint32(pid_base)
-            return {"n_pairs": res.n_pairs, "pairs": res.pairs, "hits": res.hits, "query_sketches": res.query_sketches}
+            res = _collect(r, hits, owner=out)
+            out = None  # ownership moved to the SearchResult
+            if pid_base:
+                res.pairs["pair_pid"] = res.pairs["pair_pid"] + np.uint32(pid_base)
+                if hits:
+                    res.hits["hit_pid"] = res.hits["hit_pid"] + np.uint32(pid_base)
+            return {"n_pairs": res.n_pairs, "pairs": res.pairs, "hits": res.hits, "query_sketches": res.query_sketches,
+                    "result": res}
         n = int(r.n_pairs)
         # integer columns travel as their signed twins (same bits); merge_* views them back as unsigned
         blocks = {"u32": _device_columns(out, PAIR_U32, n, "<i4", torch.int32),
@@ -207,4 +210,5 @@ def search_and_gather(index, queries, pid_base=0, hits=False):
                 result["hits"] = merge_hits(hg, hcounts, bases)
         return result
     finally:
-        L.ks_search_result_free(out)
+        if out is not None:
+            L.ks_search_result_free(out)

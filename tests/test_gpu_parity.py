@@ -451,3 +451,24 @@ def test_cli_search_and_index_against_goldens(K, golden_search, golden_sigs, tmp
     assert r.returncode != 0 and "No such file or directory" in r.stderr  # test_cli.rs:125
     r = subprocess.run(base + ["index"], capture_output=True, text=True, env=env)
     assert r.returncode != 0 and "required" in r.stderr  # test_cli.rs:135
+
+
+def test_pipelined_upload_matches_single_copy(K, monkeypatch):
+    """Batches above 64 MB stream the residues in chunks while earlier tiles are hashed (ks_index_add_proteome);
+    the index must be identical to the one built from a single copy + single launch."""
+    from kmerseek_b200 import synth
+    res, offs = synth.proteome(80_000_000, 31337)
+    prot = K.Proteome.from_packed(res, offs)
+    lens = np.diff(offs.astype(np.int64))
+    out = []
+    for no_pipe in (False, True):
+        if no_pipe:
+            monkeypatch.setenv("KS_NO_PIPELINE", "1")
+        with K.ProteomeIndex("db", 16, 1, "dayhoff") as idx:
+            idx.add_proteome(prot)
+            idx.finalize()
+            st = idx.stats()
+            assert st["n_tuples"] == int(np.maximum(lens - 15, 0).sum())
+            out.append(idx.csr())
+    for a, b in zip(*out):
+        assert np.array_equal(a, b)
