@@ -45,14 +45,24 @@ __device__ __forceinline__ void st_relaxed(uint64_t* p, uint64_t v) {
 // value in every lane) and publishes the inclusive prefix.  `value` must be < 2^62.
 // The window is wide on purpose: with hundreds of tiles in flight none of a tile's near predecessors has
 // a prefix yet, and every 32-wide round would cost a full L2 round trip.
+// First half of scan_lookback: make this tile's aggregate visible (tile 0: its inclusive prefix).  A tile that
+// has other work left can publish early and collect its prefix later with scan_collect.
+__device__ __forceinline__ void scan_publish(uint64_t* status, uint32_t tile, uint64_t value) {
+    if ((threadIdx.x & 31) == 0) st_relaxed(status + tile, (tile == 0 ? SCAN_PFX : SCAN_AGG) | value);
+}
+
+__device__ __forceinline__ uint64_t scan_collect(uint64_t* status, uint32_t tile, uint64_t value);
+
 __device__ __forceinline__ uint64_t scan_lookback(uint64_t* status, uint32_t tile, uint64_t value) {
+    scan_publish(status, tile, value);
+    return scan_collect(status, tile, value);
+}
+
+// Second half: walk back over the predecessors, return the exclusive prefix, publish the inclusive one.
+__device__ __forceinline__ uint64_t scan_collect(uint64_t* status, uint32_t tile, uint64_t value) {
     constexpr int W = 2;
     const uint32_t lane = threadIdx.x & 31;
-    if (tile == 0) {
-        if (lane == 0) st_relaxed(status, SCAN_PFX | value);
-        return 0;
-    }
-    if (lane == 0) st_relaxed(status + tile, SCAN_AGG | value);
+    if (tile == 0) return 0;
     uint64_t excl = 0;
     int64_t base = (int64_t)tile - 1;
     while (true) {

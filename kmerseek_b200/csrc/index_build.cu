@@ -115,6 +115,9 @@ __device__ __forceinline__ void bucket_empty(uint32_t b, const CsrOut& f) {
     if (b == f.nb - 1 && (threadIdx.x & 31) == 0) csr_totals(f, excl);
 }
 
+// SPLIT: tuples are written back in a second pass, after the aggregate is published (the wait for the predecessors
+// hides behind the stores); !SPLIT: one pass does both (cheaper when the kernel is issue-bound: repeat-heavy variant).
+template <bool SPLIT>
 __device__ __forceinline__ void bucket_finish(const uint64_t* items, uint32_t m, uint32_t s, uint32_t b, int lz, int tb,
                                               const uint64_t* __restrict__ in_loc, uint64_t* __restrict__ out_hash,
                                               uint64_t* __restrict__ out_loc, uint64_t* __restrict__ counts,
@@ -125,35 +128,41 @@ __device__ __forceinline__ void bucket_finish(const uint64_t* items, uint32_t m,
     const uint32_t lt = (1u << lane) - 1u;
     const uint64_t top = tb ? ((uint64_t)b << (64 - tb)) : 0ull;
     const uint32_t n_chunks = (m + LS_THREADS - 1) / LS_THREADS;
+    const bool fused = f.oversize[0] == 0;
     uint32_t flags = 0;  // 2 bits per chunk: this thread's element is a key head / a group head
+    // pass A: head flags and their counts (shared memory + the loc gather only)
     for (uint32_t c = 0; c < n_chunks; c++) {
         const uint32_t j = c * LS_THREADS + tid;
         bool hk = false, hg = false;
         uint64_t item = 0, loc = 0;
         if (j < m) {
             item = items[j];
-            loc = in_loc[s + (uint32_t)(item & 0xfffu)];  // gathered from the bucket's own 23 KB window (L1/L2)
+            loc = in_loc[s + (uint32_t)(item & 0xfffu)];  // the bucket's own 23 KB window (L1/L2)
         }
+        const uint32_t pid = (uint32_t)(loc >> 32);
         // the predecessor sits in the lane below; lane 0 looks it up
         uint64_t prev = __shfl_up_sync(0xffffffffu, item, 1);
-        uint32_t ppid = __shfl_up_sync(0xffffffffu, (uint32_t)(loc >> 32), 1);
+        uint32_t ppid = __shfl_up_sync(0xffffffffu, pid, 1);
         if (j < m) {
-            out_hash[s + j] = (top | ((item & ~0xfffull) >> tb)) >> lz;
-            out_loc[s + j] = loc;
             if (j == 0) {
                 hk = hg = true;  // a bucket's first tuple differs from everything before it in its top bits
             } else {
                 if (lane == 0) { prev = items[j - 1]; ppid = (uint32_t)(in_loc[s + (uint32_t)(prev & 0xfffu)] >> 32); }
                 hk = ((prev ^ item) >> 12) != 0;
-                hg = hk || ppid != (uint32_t)(loc >> 32);
+                hg = hk || ppid != pid;
             }
-            if (!hg) atomicSub(&t_size[(uint32_t)(loc >> 32)], 1u);
+            if (!SPLIT) {
+                out_hash[s + j] = (top | ((item & ~0xfffull) >> tb)) >> lz;
+                out_loc[s + j] = loc;
+                if (!hg) atomicSub(&t_size[pid], 1u);
+            }
         }
         flags |= ((hk ? 1u : 0u) | (hg ? 2u : 0u)) << (2 * c);
         const uint32_t ck = __popc(__ballot_sync(0xffffffffu, hk)), cg = __popc(__ballot_sync(0xffffffffu, hg));
         if (lane == 0) s_cw[c * LS_WARPS + warp] = ck | (cg << 16);
     }
     __syncthreads();
+    uint64_t agg = 0;
     if (warp == 0) {
         // exclusive prefix over the (chunk, warp) counts, 4 entries per lane; both halves stay below 2^16
         const uint32_t n_ent = n_chunks * LS_WARPS;
@@ -180,10 +189,25 @@ __device__ __forceinline__ void bucket_finish(const uint64_t* items, uint32_t m,
         const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
         const uint32_t tk = tot & 0xffffu, tg = tot >> 16;
         if (lane == 0) counts[b] = (uint64_t)tk | ((uint64_t)tg << 32);
+        agg = (uint64_t)tk | ((uint64_t)tg << 31);
+        if (fused) scan_publish(f.status, b, agg);  // successors can go on; our own prefix is collected after pass B
+    }
+    // pass B: the tuples go back to HBM in final order (this is where the wait for the predecessors is hidden)
+    for (uint32_t c = 0; SPLIT && c < n_chunks; c++) {
+        const uint32_t j = c * LS_THREADS + tid;
+        if (j < m) {
+            const uint64_t item = items[j];
+            const uint64_t loc = in_loc[s + (uint32_t)(item & 0xfffu)];
+            out_hash[s + j] = (top | ((item & ~0xfffull) >> tb)) >> lz;
+            out_loc[s + j] = loc;
+            if (!((flags >> (2 * c)) & 2u)) atomicSub(&t_size[(uint32_t)(loc >> 32)], 1u);
+        }
+    }
+    if (warp == 0) {
         uint64_t excl = ~0ull;
-        if (f.oversize[0] == 0) {
-            excl = scan_lookback(f.status, b, (uint64_t)tk | ((uint64_t)tg << 31));
-            if (b == f.nb - 1 && lane == 0) csr_totals(f, excl + ((uint64_t)tk | ((uint64_t)tg << 31)));
+        if (fused) {
+            excl = scan_collect(f.status, b, agg);
+            if (b == f.nb - 1 && lane == 0) csr_totals(f, excl + agg);
         }
         if (lane == 0) s_base = excl;
     }
@@ -392,7 +416,7 @@ bucket_sort_kernel(const uint64_t* __restrict__ in_hash, const uint64_t* __restr
         __syncthreads();
     }
 
-    bucket_finish(B, m, s, b, lz, tb, in_loc, out_hash, out_loc, counts, t_size, f);
+    bucket_finish<true>(B, m, s, b, lz, tb, in_loc, out_hash, out_loc, counts, t_size, f);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -601,7 +625,7 @@ bucket_sort_rep_kernel(const uint64_t* __restrict__ in_hash, const uint64_t* __r
         __syncthreads();
     }
 
-    bucket_finish(src, m, s, b, lz, tb, in_loc, out_hash, out_loc, counts, t_size, f);
+    bucket_finish<false>(src, m, s, b, lz, tb, in_loc, out_hash, out_loc, counts, t_size, f);
 }
 
 
