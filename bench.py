@@ -86,7 +86,10 @@ class ClockSampler:
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures of the C2
 # workload (profiles/r01_*): only meaningful for that workload, null otherwise.
-TRAFFIC = {}
+TRAFFIC = {  # bytes per launch, C2 workload, profiles/r01_c_ncu_full_raw_c2.csv
+    "bucket_sort_kernel (+ fused CSR write)": 2_991_602_000 + 3_886_829_000,
+    "sketch_quad_kernel": 205_893_000 + 2_934_864_000,
+}
 
 
 def algorithmic_bytes(n_res, n_prot, n_tuples, n_unique):
@@ -216,6 +219,9 @@ def main():
             ms = float(t.item())
         return ms
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     chk(L.ks_index_upload(idx._h, prot._h))
     for _ in range(W):
         build_resident()
@@ -227,9 +233,6 @@ def main():
         stage_ms["sketch"].append(s["ms_sketch"]); stage_ms["partition"].append(s["ms_sort_partition"])
         stage_ms["bucket"].append(s["ms_sort_bucket"]); stage_ms["csr"].append(s["ms_csr"])
 
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     ms_total = timed(build_resident, args.steps, per_step=collect)
     st1 = idx.stats()
     launches = sum(st1[k] - st0[k] for k in ("sketch_launches", "sort_launches", "csr_launches"))
@@ -298,7 +301,8 @@ def main():
     dom = max(own, key=lambda k: own[k]["ms"])
     sk_bytes, bd_bytes = algorithmic_bytes(n_res, n_prot, n_tuples, n_unique)
     roof = {"bound": "hbm", "kernel": dom, "achieved": stages[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
-            "frac": stages[dom]["achieved_gbs"] / peak, "traffic": TRAFFIC.get(dom), "peak_source": peak_src,
+            "frac": stages[dom]["achieved_gbs"] / peak,
+            "traffic": TRAFFIC.get(dom) if args.workload == "c2_swissprot_hp_k24_s1" else None, "peak_source": peak_src,
             "stages": {k: {"ms": round(v["ms"], 4), "achieved_gbs": round(v["achieved_gbs"], 1),
                            "frac": round(v["achieved_gbs"] / peak, 4)} for k, v in stages.items()},
             "whole_step": {"algorithmic_bytes": sk_bytes + bd_bytes,
