@@ -5,7 +5,7 @@ One "step" = one index build of the workload's proteome that is already resident
     fused sketch kernel -> radix sort by hash -> CSR build (ks_index_clear + ks_index_sketch_resident +
     ks_index_finalize through the C ABI).
 `value` = residues/s over all ranks with inputs resident in HBM; `e2e` = the same metric through the public
-host API with HOST buffers (pinned residues/offsets -> H2D -> build -> stats read back) inside the timed
+host API with HOST buffers (pinned 5-bit packed residues + offsets -> H2D -> build -> stats read back) inside the timed
 region.  A batched search of 10 000 planted query domains against the built index is timed beside it
 (`search`: query x proteome residues/s).  Multi-GPU: the proteome is sharded by protein, one rank per GPU,
 no data-path collective in the build (weak scaling: every rank builds a shard of the workload's size);
@@ -330,7 +330,7 @@ def main():
                    "unique_hashes_per_gpu": n_unique, "parallelism": f"protein-sharded x{world}",
                    "l2": "inputs (0.2 GB residues, 3 GB tuples) exceed the 126 MB L2; no flush needed"},
         "e2e": {"value": e2e_value, "unit": "residues/s", "ms_per_step": ms_e2e,
-                "h2d_bytes_per_step": int(n_res + 64 + (n_prot + 1) * 8), "d2h_bytes_per_step": 8 + 16 + 136},
+                "h2d_bytes_per_step": int((n_res + 7) // 8 * 5 + 72 + (n_prot + 1) * 8), "d2h_bytes_per_step": 8 + 16 + 136},
         "gpu_launches": int(launches),
         "roofline": roof,
         "cpu_baseline": cpu,

@@ -61,6 +61,9 @@ struct ks_proteome {
     uint64_t* offsets = nullptr;
     uint64_t n_prot = 0, n_res = 0;
     bool pinned = false;
+    // upload format: 5-bit codes, 8 residues per 5 bytes (null when a byte outside A-Z and '*' is present)
+    uint8_t* packed = nullptr;
+    bool packed_pinned = false;
     std::vector<std::string> names;
 };
 
@@ -96,6 +99,11 @@ ks_proteome* make_proteome(const uint8_t* res, uint64_t n_res, const uint64_t* o
     memcpy(p->offsets, offs, (n_prot + 1) * 8);
     p->n_prot = n_prot;
     p->n_res = n_res;
+    p->packed = (uint8_t*)host_alloc(packed_bytes(n_res), &p->packed_pinned);
+    if (!pack_residues(p->residues, n_res, p->packed)) {
+        host_free(p->packed, p->packed_pinned);
+        p->packed = nullptr;
+    }
     return p;
 }
 }  // namespace
@@ -217,6 +225,7 @@ void ks_proteome_free(ks_proteome* p) {
     if (!p) return;
     host_free(p->residues, p->pinned);
     host_free(p->offsets, p->pinned);
+    host_free(p->packed, p->packed_pinned);
     delete p;
 }
 
@@ -233,6 +242,7 @@ struct DeviceBatch {  // residues + offsets resident in HBM
     uint64_t res_cap = 0, offs_cap = 0;
     uint64_t n_prot = 0, n_res = 0, n_windows = 0;
     bool valid = false;
+    bool packed = false;  // res holds 5-bit codes
 };
 
 // Grow-only device buffer: steady-state steps (clear + build again) never go back to the allocator.
@@ -309,11 +319,13 @@ void ensure_ws(ks_index* x, size_t bytes) {
     x->ws_bytes = bytes;
 }
 
-void upload_batch(ks_index* x, DeviceBatch& b, const ks_proteome* p) {
+void upload_batch(ks_index* x, DeviceBatch& b, const ks_proteome* p, bool allow_packed = false) {
+    const bool packed = allow_packed && p->packed && x->params.ksize <= (uint32_t)SK_MAX_TEMPLATE_K;
+    const uint64_t res_bytes = packed ? packed_bytes(p->n_res) : p->n_res + 64;
     if (p->n_prot >= 0xffffffffull) fail(KS_ERR_CAPACITY, "more than 2^32-2 proteins in one batch");
-    if (p->n_res + 64 > b.res_cap) {
+    if (res_bytes > b.res_cap) {
         if (b.res) x->arena->release(b.res);
-        b.res_cap = p->n_res + 64;
+        b.res_cap = res_bytes;
         b.res = x->arena->alloc<uint8_t>(b.res_cap);
     }
     if (p->n_prot + 1 > b.offs_cap) {
@@ -321,7 +333,8 @@ void upload_batch(ks_index* x, DeviceBatch& b, const ks_proteome* p) {
         b.offs_cap = p->n_prot + 1;
         b.offs = x->arena->alloc<uint64_t>(b.offs_cap);
     }
-    KS_CUDA(cudaMemcpyAsync(b.res, p->residues, p->n_res + 64, cudaMemcpyHostToDevice, x->stream));
+    b.packed = packed;
+    KS_CUDA(cudaMemcpyAsync(b.res, packed ? p->packed : p->residues, res_bytes, cudaMemcpyHostToDevice, x->stream));
     KS_CUDA(cudaMemcpyAsync(b.offs, p->offsets, (p->n_prot + 1) * 8, cudaMemcpyHostToDevice, x->stream));
     b.n_prot = p->n_prot;
     b.n_res = p->n_res;
@@ -362,7 +375,7 @@ uint64_t run_sketch(ks_index* x, const DeviceBatch& b, uint32_t pid_base, uint64
                     uint64_t capacity) {
     ensure_ws(x, sketch_workspace_bytes(b.n_res));
     SketchArgs a;
-    a.residues = b.res; a.offsets = b.offs; a.n_res = b.n_res; a.n_prot = b.n_prot;
+    a.residues = b.res; a.packed = b.packed ? 1 : 0; a.offsets = b.offs; a.n_res = b.n_res; a.n_prot = b.n_prot;
     a.k = x->params.ksize; a.moltype = x->params.moltype; a.max_hash = x->max_hash; a.pid_base = pid_base;
     a.out_hash = out_hash; a.out_loc = out_loc; a.capacity = capacity; a.d_count = x->d_count; a.workspace = x->ws;
     a.force_general = getenv("KS_SKETCH_GENERAL") ? 1 : 0;  // test hook: exercise the look-back path at scaled == 1
@@ -411,9 +424,13 @@ bool add_proteome_pipelined(ks_index* x, const ks_proteome* p) {
     if (x->finalized) fail(KS_ERR_VALIDATION, "Validation error: index is finalized; ks_index_clear before adding more");
     if (p->n_prot >= 0xffffffffull || x->n_prot + p->n_prot >= 0xffffffffull) fail(KS_ERR_CAPACITY, "more than 2^32-2 proteins on one shard");
     DeviceBatch& b = x->batch;
-    if (p->n_res + 64 > b.res_cap) {
+    const bool packed = p->packed != nullptr;  // 5 bits per residue over PCIe instead of 8
+    const uint64_t res_bytes = packed ? packed_bytes(p->n_res) : p->n_res + 64;
+    const uint8_t* host_res = packed ? p->packed : p->residues;
+    const uint64_t tile_bytes = packed ? SK_TILE / 8 * 5 : SK_TILE;
+    if (res_bytes > b.res_cap) {
         if (b.res) x->arena->release(b.res);
-        b.res_cap = p->n_res + 64;
+        b.res_cap = res_bytes;
         b.res = x->arena->alloc<uint8_t>(b.res_cap);
     }
     if (p->n_prot + 1 > b.offs_cap) {
@@ -421,6 +438,7 @@ bool add_proteome_pipelined(ks_index* x, const ks_proteome* p) {
         b.offs_cap = p->n_prot + 1;
         b.offs = x->arena->alloc<uint64_t>(b.offs_cap);
     }
+    b.packed = packed;
     b.n_prot = p->n_prot; b.n_res = p->n_res;
     b.n_windows = count_windows(p->offsets, p->n_prot, x->params.ksize);
     b.valid = true;
@@ -433,7 +451,7 @@ bool add_proteome_pipelined(ks_index* x, const ks_proteome* p) {
     KS_CUDA(cudaStreamWaitEvent(x->copy_stream, x->ev_chunk[CHUNKS], 0));
     KS_CUDA(cudaMemcpyAsync(b.offs, p->offsets, (p->n_prot + 1) * 8, cudaMemcpyHostToDevice, x->stream));
     SketchArgs a;
-    a.residues = b.res; a.offsets = b.offs; a.n_res = b.n_res; a.n_prot = b.n_prot;
+    a.residues = b.res; a.packed = packed ? 1 : 0; a.offsets = b.offs; a.n_res = b.n_res; a.n_prot = b.n_prot;
     a.k = x->params.ksize; a.moltype = x->params.moltype; a.max_hash = x->max_hash; a.pid_base = (uint32_t)x->n_prot;
     a.out_hash = x->d_hash + x->n_tuples; a.out_loc = x->d_loc + x->n_tuples; a.capacity = x->cap - x->n_tuples;
     a.d_count = x->d_count; a.workspace = x->ws; a.force_general = 0;
@@ -443,9 +461,9 @@ bool add_proteome_pipelined(ks_index* x, const ks_proteome* p) {
     for (int c = 0; c < CHUNKS; c++) {
         const uint64_t t0 = (uint64_t)c * per, t1 = std::min<uint64_t>(nt, t0 + per);
         if (t0 >= t1) break;
-        const uint64_t byte0 = t0 * SK_TILE;
-        const uint64_t byte1 = std::min<uint64_t>(p->n_res + 64, t1 * SK_TILE + 64);  // halo of the last tile included
-        KS_CUDA(cudaMemcpyAsync(b.res + byte0, p->residues + byte0, byte1 - byte0, cudaMemcpyHostToDevice, x->copy_stream));
+        const uint64_t byte0 = t0 * tile_bytes;
+        const uint64_t byte1 = std::min<uint64_t>(res_bytes, t1 * tile_bytes + 64);  // halo of the last tile included
+        KS_CUDA(cudaMemcpyAsync(b.res + byte0, host_res + byte0, byte1 - byte0, cudaMemcpyHostToDevice, x->copy_stream));
         KS_CUDA(cudaEventRecord(x->ev_chunk[c], x->copy_stream));
         KS_CUDA(cudaStreamWaitEvent(x->stream, x->ev_chunk[c], 0));
         a.tile_begin = (uint32_t)t0; a.tile_end = (uint32_t)t1;
@@ -681,7 +699,7 @@ ks_status ks_index_upload(ks_index* x, const ks_proteome* p) {
         if (!x || !p) fail(KS_ERR_VALIDATION, "Validation error: null argument");
         x->use();
         KS_CUDA(cudaEventRecord(x->ev[EV_UP0], x->stream));
-        upload_batch(x, x->batch, p);
+        upload_batch(x, x->batch, p, true);
         KS_CUDA(cudaEventRecord(x->ev[EV_UP1], x->stream));
         x->t_upload = true;
     });

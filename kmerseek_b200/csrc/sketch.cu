@@ -18,6 +18,8 @@
 // (protein, pos), independent of scheduling, so the later stable sort by hash is deterministic.
 #include <cub/device/device_scan.cuh>
 
+#include <cstring>
+
 #include "common.cuh"
 #include "sketch.cuh"
 
@@ -403,7 +405,32 @@ sketch_quad_kernel(SketchArgs a, Lut256 lut, uint32_t* __restrict__ ticket, uint
     const bool cached = n_off <= OFFS_CACHE;
     if (cached)
         for (uint32_t i = tid; i < n_off; i += SK_THREADS) s_offs[i] = a.offsets[p_lo + i];
-    {
+    if (a.packed) {
+        // 5-bit packed residues: thread g unpacks group g (8 residues = 5 bytes) through a 32-entry code table
+        __shared__ uint8_t s_lut32[32];
+        if (tid < 32) {
+            const uint32_t c = tid;
+            s_lut32[c] = c == 0 ? 0 : c <= 26 ? lut.b['A' + c - 1] : c == 27 ? lut.b['*'] : 0;
+        }
+        __syncthreads();
+        constexpr uint32_t n_groups = (SK_TILE + K - 1 + 7) / 8;
+        for (uint32_t grp = tid; grp < n_groups; grp += SK_THREADS) {
+            const uint64_t byte = (g0 / 8 + grp) * 5;
+            const uint32_t* w = reinterpret_cast<const uint32_t*>(a.residues + (byte & ~3ull));
+            const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1);
+            const uint32_t sh8 = (uint32_t)(byte & 3) * 8;
+            const uint32_t lo = __funnelshift_r(w0, w1, sh8), hi = (w1 >> sh8) & 0xffu;  // 40 bits: lo | hi << 32
+            uint32_t o0 = 0, o1 = 0;
+#pragma unroll
+            for (int i = 0; i < 4; i++) o0 |= (uint32_t)s_lut32[(lo >> (5 * i)) & 31u] << (8 * i);
+            o1 |= (uint32_t)s_lut32[(lo >> 20) & 31u];
+            o1 |= (uint32_t)s_lut32[(lo >> 25) & 31u] << 8;
+            o1 |= (uint32_t)s_lut32[((lo >> 30) | (hi << 2)) & 31u] << 16;
+            o1 |= (uint32_t)s_lut32[(hi >> 3) & 31u] << 24;
+            s_res[2 * grp] = o0;
+            s_res[2 * grp + 1] = o1;
+        }
+    } else {
         constexpr uint32_t n_chunks = (SK_TILE + K - 1 + 15) / 16;
         if (tid < n_chunks) {
             const uint64_t g = g0 + 16ull * tid;
@@ -573,6 +600,26 @@ struct Dispatch<0> {
 };
 
 }  // namespace
+
+bool pack_residues(const uint8_t* res, uint64_t n, uint8_t* out) {
+    const uint64_t groups = (n + 7) / 8;
+    for (uint64_t g = 0; g < groups; g++) {
+        uint64_t v = 0;
+        for (int i = 0; i < 8; i++) {
+            const uint64_t idx = g * 8 + i;
+            if (idx >= n) break;
+            const uint8_t c = res[idx];
+            uint32_t code;
+            if (c >= 'A' && c <= 'Z') code = c - 'A' + 1;
+            else if (c == '*') code = 27;
+            else return false;
+            v |= (uint64_t)code << (5 * i);
+        }
+        for (int b = 0; b < 5; b++) out[g * 5 + b] = (uint8_t)(v >> (8 * b));
+    }
+    memset(out + groups * 5, 0, 72);
+    return true;
+}
 
 void fill_lut(int moltype, Lut256* lut) {
     for (int i = 0; i < 256; i++) {

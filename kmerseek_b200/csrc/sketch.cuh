@@ -14,7 +14,9 @@ constexpr int SK_MAX_K = 256;                      // bound of the generic kerne
 struct Lut256 { uint8_t b[256]; };
 
 struct SketchArgs {
-    const uint8_t* residues;   // device, n_res bytes followed by >= 64 readable pad bytes, 16 B aligned
+    const uint8_t* residues;   // device, 16 B aligned.  packed == 0: n_res bytes + >= 64 readable pad bytes;
+                               // packed == 1: 5-bit codes, 8 residues per 5 bytes (pack_residues), + >= 72 pad bytes
+    int packed = 0;
     const uint64_t* offsets;   // device, n_prot + 1
     uint64_t n_res;
     uint64_t n_prot;
@@ -42,5 +44,9 @@ cudaError_t launch_sketch_tiles(const SketchArgs& a, cudaStream_t stream, uint64
 cudaError_t launch_sketch_finish(const SketchArgs& a, cudaStream_t stream);
 bool sketch_is_exact(const SketchArgs& a);
 void fill_lut(int moltype, Lut256* lut);
+// 5-bit residue codes for the packed upload format: 'A'..'Z' -> 1..26, '*' -> 27, 0 = padding.  Returns false (and
+// leaves `out` unspecified) when a byte has no code.  out must hold packed_bytes(n) bytes.
+bool pack_residues(const uint8_t* res, uint64_t n, uint8_t* out);
+inline uint64_t packed_bytes(uint64_t n) { return (n + 7) / 8 * 5 + 72; }
 
 }  // namespace ks

@@ -472,3 +472,21 @@ def test_pipelined_upload_matches_single_copy(K, monkeypatch):
             out.append(idx.csr())
     for a, b in zip(*out):
         assert np.array_equal(a, b)
+
+
+def test_unpackable_residues_take_the_byte_path(K, O):
+    """Index builds upload 5-bit packed residues; a proteome handed over with bytes outside A-Z and '*'
+    (ks_proteome_from_packed does not validate) cannot be packed and must go through the plain byte path."""
+    rng = np.random.default_rng(8)
+    res = rng.choice(np.frombuffer(b"ACDEFGHIKLMNPQRSTVWYacdxyz@#1", dtype=np.uint8), size=50_000)
+    offs = np.array([0, 10_000, 10_000, 35_000, 50_000], dtype=np.uint64)
+    prot = K.Proteome.from_packed(res, offs)
+    for k, moltype in ((7, "protein"), (12, "hp")):
+        with K.ProteomeIndex("db", k, 1, moltype) as idx:
+            idx.add_proteome(prot)
+            idx.finalize()
+            keys, row_ptr, pid, pos = idx.csr()
+            oh, opid, opos = O.sketch_tuples(res, offs, k, moltype, 1)
+            okeys, orow, ops, oqs = O.build_index(oh, opid, opos)
+            assert np.array_equal(keys, okeys) and np.array_equal(row_ptr, orow)
+            assert np.array_equal(pid, ops) and np.array_equal(pos, oqs)
