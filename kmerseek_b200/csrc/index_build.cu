@@ -810,7 +810,10 @@ int msd_top_bits(uint64_t n, int lz, uint64_t max_hash) {
     int tb = 0;
     while (tb < 24 && (double)n / (std::ldexp(1.0, tb) * fill) > 3072.0) tb++;
     if ((double)n / (std::ldexp(1.0, tb) * fill) > 3072.0) return -1;
-    if (lz + tb < 12) return -1;  // index bits would collide with key bits: library sort for all bits instead
+    // the item layout needs lz + tb >= 12 (the index in the bucket takes the low 12 bits of the shifted hash): small
+    // inputs simply get more, smaller buckets -- still two partition passes instead of eight
+    if (lz + tb < 12) tb = 12 - lz;
+    if (n < (1u << 16)) return -1;  // tiny: the library sort of all bits is as fast as anything
     return tb;
 }
 

@@ -415,9 +415,14 @@ sketch_quad_kernel(SketchArgs a, Lut256 lut, uint32_t* __restrict__ ticket, uint
         __syncthreads();
         constexpr uint32_t n_groups = (SK_TILE + K - 1 + 7) / 8;
         for (uint32_t grp = tid; grp < n_groups; grp += SK_THREADS) {
-            const uint64_t byte = (g0 / 8 + grp) * 5;
-            const uint32_t* w = reinterpret_cast<const uint32_t*>(a.residues + (byte & ~3ull));
-            const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1);
+            const uint64_t group = g0 / 8 + grp;
+            const uint64_t byte = group * 5;
+            uint32_t w0 = 0, w1 = 0;
+            if (group * 8 < a.n_res) {  // groups past the last residue are not backed by memory
+                const uint32_t* w = reinterpret_cast<const uint32_t*>(a.residues + (byte & ~3ull));
+                w0 = __ldg(w);
+                w1 = __ldg(w + 1);
+            }
             const uint32_t sh8 = (uint32_t)(byte & 3) * 8;
             const uint32_t lo = __funnelshift_r(w0, w1, sh8), hi = (w1 >> sh8) & 0xffu;  // 40 bits: lo | hi << 32
             uint32_t o0 = 0, o1 = 0;
