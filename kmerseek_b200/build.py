@@ -39,7 +39,7 @@ def build(force=False, verbose=False):
                 raise RuntimeError("nvcc failed: " + " ".join(cmd))
     objs = [os.path.join(objdir, s + ".o") for s in SOURCES]
     if force or jobs or _stale(OUT, objs):
-        cmd = [NVCC, "-shared", "-o", OUT] + objs + ["-lz", "-cudart", "static"]
+        cmd = [NVCC, "-shared", "-o", OUT] + objs + ["-lz", "-ldl", "-cudart", "static"]
         res = subprocess.run(cmd, capture_output=True, text=True)
         if res.returncode:
             sys.stderr.write(res.stdout + res.stderr)

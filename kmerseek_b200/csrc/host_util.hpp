@@ -1,6 +1,8 @@
 // Host-only pieces behind the C ABI: MD5 (for sourmash md5sum), input normalisation, FASTA reader.
 #pragma once
+#include <dlfcn.h>
 #include <stdint.h>
+#include <stdio.h>
 #include <string.h>
 #include <zlib.h>
 
@@ -122,9 +124,136 @@ inline bool normalize_into(const char* s, uint64_t len, uint64_t protein_index, 
     return true;
 }
 
+// ---- decompression of whole files through the system's runtime libraries -------------------------------
+// niffler (the reference's reader, src/rust/index.rs:920) sniffs gzip / zstd / bzip2 / xz.  gzip goes through zlib
+// (headers present).  The other three only have their runtime .so in this image, no headers, so the few entry
+// points needed are declared here and bound with dlopen; if a library is missing the file is reported as ParseError.
+struct DlLib {
+    void* h = nullptr;
+    explicit DlLib(const char* const* names) {
+        for (; *names && !h; names++) h = dlopen(*names, RTLD_NOW | RTLD_LOCAL);
+    }
+    template <class F>
+    F sym(const char* n) const { return h ? reinterpret_cast<F>(dlsym(h, n)) : nullptr; }
+};
+
+inline std::string slurp(const char* path) {
+    FILE* f = fopen(path, "rb");
+    if (!f) fail(KS_ERR_PARSE, std::string("Parse error: cannot open ") + path);
+    std::string out;
+    char buf[1 << 16];
+    size_t n;
+    while ((n = fread(buf, 1, sizeof buf, f)) > 0) out.append(buf, n);
+    fclose(f);
+    return out;
+}
+
+inline std::string decompress_zstd(const std::string& in) {
+    struct InBuf { const void* src; size_t size; size_t pos; };
+    struct OutBuf { void* dst; size_t size; size_t pos; };
+    static const char* names[] = {"libzstd.so.1", "libzstd.so", nullptr};
+    static DlLib lib(names);
+    auto create = lib.sym<void* (*)()>("ZSTD_createDStream");
+    auto init = lib.sym<size_t (*)(void*)>("ZSTD_initDStream");
+    auto step = lib.sym<size_t (*)(void*, OutBuf*, InBuf*)>("ZSTD_decompressStream");
+    auto is_err = lib.sym<unsigned (*)(size_t)>("ZSTD_isError");
+    auto destroy = lib.sym<size_t (*)(void*)>("ZSTD_freeDStream");
+    if (!create || !init || !step || !is_err || !destroy) fail(KS_ERR_PARSE, "Parse error: zstd input but libzstd is not available");
+    void* ds = create();
+    init(ds);
+    std::string out;
+    std::vector<char> buf(1 << 20);
+    InBuf ib{in.data(), in.size(), 0};
+    while (ib.pos < ib.size) {
+        OutBuf ob{buf.data(), buf.size(), 0};
+        const size_t r = step(ds, &ob, &ib);
+        if (is_err(r)) { destroy(ds); fail(KS_ERR_PARSE, "Parse error: corrupt zstd stream"); }
+        out.append(buf.data(), ob.pos);
+        if (r == 0 && ib.pos >= ib.size) break;
+    }
+    destroy(ds);
+    return out;
+}
+
+inline std::string decompress_bz2(const std::string& in) {
+    struct BzStream {
+        char* next_in; unsigned avail_in, total_in_lo32, total_in_hi32;
+        char* next_out; unsigned avail_out, total_out_lo32, total_out_hi32;
+        void* state; void* (*bzalloc)(void*, int, int); void (*bzfree)(void*, void*); void* opaque;
+    };
+    static const char* names[] = {"libbz2.so.1.0", "libbz2.so.1", "libbz2.so", nullptr};
+    static DlLib lib(names);
+    auto init = lib.sym<int (*)(BzStream*, int, int)>("BZ2_bzDecompressInit");
+    auto step = lib.sym<int (*)(BzStream*)>("BZ2_bzDecompress");
+    auto end = lib.sym<int (*)(BzStream*)>("BZ2_bzDecompressEnd");
+    if (!init || !step || !end) fail(KS_ERR_PARSE, "Parse error: bzip2 input but libbz2 is not available");
+    BzStream st{};
+    if (init(&st, 0, 0) != 0) fail(KS_ERR_PARSE, "Parse error: bzip2 init failed");
+    std::string out;
+    std::vector<char> buf(1 << 20);
+    st.next_in = const_cast<char*>(in.data());
+    st.avail_in = (unsigned)in.size();
+    for (;;) {
+        st.next_out = buf.data();
+        st.avail_out = (unsigned)buf.size();
+        const int r = step(&st);
+        out.append(buf.data(), buf.size() - st.avail_out);
+        if (r == 4) break;  // BZ_STREAM_END
+        if (r != 0 || (st.avail_in == 0 && st.avail_out != 0)) { end(&st); fail(KS_ERR_PARSE, "Parse error: corrupt bzip2 stream"); }
+    }
+    end(&st);
+    return out;
+}
+
+inline std::string decompress_xz(const std::string& in) {
+    struct LzmaStream {
+        const uint8_t* next_in; size_t avail_in; uint64_t total_in;
+        uint8_t* next_out; size_t avail_out; uint64_t total_out;
+        const void* allocator; void* internal;
+        void *reserved_ptr1, *reserved_ptr2, *reserved_ptr3, *reserved_ptr4;
+        uint64_t reserved_int1, reserved_int2; size_t reserved_int3, reserved_int4;
+        int reserved_enum1, reserved_enum2;
+    };
+    static const char* names[] = {"liblzma.so.5", "liblzma.so", nullptr};
+    static DlLib lib(names);
+    auto init = lib.sym<int (*)(LzmaStream*, uint64_t, uint32_t)>("lzma_stream_decoder");
+    auto step = lib.sym<int (*)(LzmaStream*, int)>("lzma_code");
+    auto end = lib.sym<void (*)(LzmaStream*)>("lzma_end");
+    if (!init || !step || !end) fail(KS_ERR_PARSE, "Parse error: xz input but liblzma is not available");
+    LzmaStream st{};
+    if (init(&st, UINT64_MAX, 0x08 /* LZMA_CONCATENATED */) != 0) fail(KS_ERR_PARSE, "Parse error: xz init failed");
+    std::string out;
+    std::vector<uint8_t> buf(1 << 20);
+    st.next_in = reinterpret_cast<const uint8_t*>(in.data());
+    st.avail_in = in.size();
+    for (;;) {
+        st.next_out = buf.data();
+        st.avail_out = buf.size();
+        const int r = step(&st, st.avail_in == 0 ? 3 /* LZMA_FINISH */ : 0 /* LZMA_RUN */);
+        out.append(reinterpret_cast<char*>(buf.data()), buf.size() - st.avail_out);
+        if (r == 1) break;  // LZMA_STREAM_END
+        if (r != 0) { end(&st); fail(KS_ERR_PARSE, "Parse error: corrupt xz stream"); }
+    }
+    end(&st);
+    return out;
+}
+
+inline std::string decompress_gzip_or_plain(const char* path) {
+    gzFile f = gzopen(path, "rb");
+    if (!f) fail(KS_ERR_PARSE, std::string("Parse error: cannot open ") + path);
+    gzbuffer(f, 1 << 20);
+    std::string out;
+    std::vector<char> buf(1 << 20);
+    int n;
+    while ((n = gzread(f, buf.data(), (unsigned)buf.size())) > 0) out.append(buf.data(), n);
+    gzclose(f);
+    if (n < 0) fail(KS_ERR_PARSE, "Parse error: read failed (corrupt gzip stream?)");
+    return out;
+}
+
 // FASTA records the way needletail hands them to process_fasta (src/rust/index.rs:920-935): id = the header
-// line without '>', sequence = the following lines joined, CR/LF removed.  Plain or gzip input (zlib); the
-// other codecs niffler auto-detects (bz2/xz/zstd) have no headers in this image and are reported as ParseError.
+// line without '>', sequence = the following lines joined, CR/LF removed.  Plain, gzip, zstd, bzip2 or xz input,
+// sniffed from the magic bytes like niffler does.
 inline void read_fasta(const char* path, std::vector<std::string>& names, std::vector<std::string>& seqs) {
     FILE* probe = fopen(path, "rb");
     if (!probe) fail(KS_ERR_PARSE, std::string("Parse error: cannot open ") + path);
@@ -132,47 +261,32 @@ inline void read_fasta(const char* path, std::vector<std::string>& names, std::v
     size_t got = fread(magic, 1, 6, probe);
     fclose(probe);
     if (got == 0) fail(KS_ERR_PARSE, "Parse error: empty file");
-    if ((got >= 4 && magic[0] == 0x28 && magic[1] == 0xb5 && magic[2] == 0x2f && magic[3] == 0xfd) ||
-        (got >= 3 && magic[0] == 'B' && magic[1] == 'Z' && magic[2] == 'h') ||
-        (got >= 6 && magic[0] == 0xfd && magic[1] == '7' && magic[2] == 'z' && magic[3] == 'X' && magic[4] == 'Z'))
-        fail(KS_ERR_PARSE, "Parse error: zstd/bzip2/xz input is not supported by this build (plain and gzip are)");
-    gzFile f = gzopen(path, "rb");
-    if (!f) fail(KS_ERR_PARSE, std::string("Parse error: cannot open ") + path);
-    gzbuffer(f, 1 << 20);
-    std::vector<char> buf(1 << 20);
-    std::string line;
+    std::string data;
+    if (got >= 4 && magic[0] == 0x28 && magic[1] == 0xb5 && magic[2] == 0x2f && magic[3] == 0xfd) data = decompress_zstd(slurp(path));
+    else if (got >= 3 && magic[0] == 'B' && magic[1] == 'Z' && magic[2] == 'h') data = decompress_bz2(slurp(path));
+    else if (got >= 6 && magic[0] == 0xfd && magic[1] == '7' && magic[2] == 'z' && magic[3] == 'X' && magic[4] == 'Z') data = decompress_xz(slurp(path));
+    else data = decompress_gzip_or_plain(path);
     bool first = true, in_record = false;
-    auto flush_line = [&](std::string& l) {
-        if (!l.empty() && l.back() == '\r') l.pop_back();
+    size_t pos = 0;
+    while (pos < data.size()) {
+        size_t nl = data.find('\n', pos);
+        if (nl == std::string::npos) nl = data.size();
+        size_t end = nl;
+        if (end > pos && data[end - 1] == '\r') end--;
         if (first) {
-            if (l.empty()) return;
-            if (l[0] != '>') { gzclose(f); fail(KS_ERR_PARSE, "Parse error: expected '>' at the start of a FASTA record"); }
+            if (end == pos) { pos = nl + 1; continue; }
+            if (data[pos] != '>') fail(KS_ERR_PARSE, "Parse error: expected '>' at the start of a FASTA record");
             first = false;
         }
-        if (!l.empty() && l[0] == '>') {
-            names.emplace_back(l.substr(1));
+        if (end > pos && data[pos] == '>') {
+            names.emplace_back(data, pos + 1, end - pos - 1);
             seqs.emplace_back();
             in_record = true;
         } else if (in_record) {
-            seqs.back().append(l);
+            seqs.back().append(data, pos, end - pos);
         }
-    };
-    int n;
-    while ((n = gzread(f, buf.data(), (unsigned)buf.size())) > 0) {
-        const char* p = buf.data();
-        const char* e = p + n;
-        while (p < e) {
-            const char* nl = (const char*)memchr(p, '\n', e - p);
-            if (!nl) { line.append(p, e - p); break; }
-            line.append(p, nl - p);
-            flush_line(line);
-            line.clear();
-            p = nl + 1;
-        }
+        pos = nl + 1;
     }
-    if (n < 0) { gzclose(f); fail(KS_ERR_PARSE, "Parse error: read failed (corrupt gzip stream?)"); }
-    if (!line.empty()) flush_line(line);
-    gzclose(f);
     if (first) fail(KS_ERR_PARSE, "Parse error: empty file");
 }
 

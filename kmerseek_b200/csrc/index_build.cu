@@ -115,8 +115,8 @@ __device__ __forceinline__ void bucket_empty(uint32_t b, const CsrOut& f) {
     if (b == f.nb - 1 && (threadIdx.x & 31) == 0) csr_totals(f, excl);
 }
 
-// SPLIT: tuples are written back in a second pass, after the aggregate is published (the wait for the predecessors
-// hides behind the stores); !SPLIT: one pass does both (cheaper when the kernel is issue-bound: repeat-heavy variant).
+// SPLIT: the hashes are written back in a second pass, after the aggregate is published (part of the wait for the
+// predecessors hides behind those stores); !SPLIT: one pass writes both columns.
 template <bool SPLIT>
 __device__ __forceinline__ void bucket_finish(const uint64_t* items, uint32_t m, uint32_t s, uint32_t b, int lz, int tb,
                                               const uint64_t* __restrict__ in_loc, uint64_t* __restrict__ out_hash,
@@ -151,11 +151,9 @@ __device__ __forceinline__ void bucket_finish(const uint64_t* items, uint32_t m,
                 hk = ((prev ^ item) >> 12) != 0;
                 hg = hk || ppid != pid;
             }
-            if (!SPLIT) {
-                out_hash[s + j] = (top | ((item & ~0xfffull) >> tb)) >> lz;
-                out_loc[s + j] = loc;
-                if (!hg) atomicSub(&t_size[pid], 1u);
-            }
+            out_loc[s + j] = loc;
+            if (!hg) atomicSub(&t_size[pid], 1u);
+            if (!SPLIT) out_hash[s + j] = (top | ((item & ~0xfffull) >> tb)) >> lz;
         }
         flags |= ((hk ? 1u : 0u) | (hg ? 2u : 0u)) << (2 * c);
         const uint32_t ck = __popc(__ballot_sync(0xffffffffu, hk)), cg = __popc(__ballot_sync(0xffffffffu, hg));
@@ -195,13 +193,7 @@ __device__ __forceinline__ void bucket_finish(const uint64_t* items, uint32_t m,
     // pass B: the tuples go back to HBM in final order (this is where the wait for the predecessors is hidden)
     for (uint32_t c = 0; SPLIT && c < n_chunks; c++) {
         const uint32_t j = c * LS_THREADS + tid;
-        if (j < m) {
-            const uint64_t item = items[j];
-            const uint64_t loc = in_loc[s + (uint32_t)(item & 0xfffu)];
-            out_hash[s + j] = (top | ((item & ~0xfffull) >> tb)) >> lz;
-            out_loc[s + j] = loc;
-            if (!((flags >> (2 * c)) & 2u)) atomicSub(&t_size[(uint32_t)(loc >> 32)], 1u);
-        }
+        if (j < m) out_hash[s + j] = (top | ((items[j] & ~0xfffull) >> tb)) >> lz;  // rebuilt from the item alone
     }
     if (warp == 0) {
         uint64_t excl = ~0ull;
@@ -625,7 +617,7 @@ bucket_sort_rep_kernel(const uint64_t* __restrict__ in_hash, const uint64_t* __r
         __syncthreads();
     }
 
-    bucket_finish<false>(src, m, s, b, lz, tb, in_loc, out_hash, out_loc, counts, t_size, f);
+    bucket_finish<true>(src, m, s, b, lz, tb, in_loc, out_hash, out_loc, counts, t_size, f);
 }
 
 

@@ -130,6 +130,7 @@ def main():
         (f"fasta/{b25}", "bcl2_first25.fasta.gz"),
         ("fasta/ced9.fasta", "ced9.fasta"),
         ("fasta/test_compression.fasta", "test_compression.fasta"),
+        ("fasta/test_compression.fasta.zst", "test_compression.fasta.zst"),
         ("fasta/uniprotkb_BCL2_AND_model_organism_9606_2025_02_06.fasta.gz", "bcl2_all300.fasta.gz"),
     ]:
         shutil.copyfile(os.path.join(td, src), os.path.join(OUT, "fasta", dst))

@@ -490,3 +490,14 @@ def test_unpackable_residues_take_the_byte_path(K, O):
             okeys, orow, ops, oqs = O.build_index(oh, opid, opos)
             assert np.array_equal(keys, okeys) and np.array_equal(row_ptr, orow)
             assert np.array_equal(pid, ops) and np.array_equal(pos, oqs)
+
+
+def test_golden_zstd_fasta(K, golden_rust):
+    g = golden_rust["index_tests"]["test_process_fasta_zstd_moltype_protein"]  # src/rust/index.rs:1734-1789
+    with K.ProteomeIndex("db", g["ksize"], g["scaled"], g["moltype"]) as idx:
+        idx.process_fasta(fasta_path("test_compression.fasta.zst"), 0, 1000)
+        sigs = idx.get_signatures()
+        assert len(sigs) == g["n_signatures"] == 2
+        for i, n in g["ids"].items():
+            assert len(sigs[i][1]) == n
+        assert idx.combined_minhash_size() == g["combined_size"] == 24
