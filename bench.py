@@ -34,6 +34,8 @@ WORKLOADS = {
     "target_100m_dayhoff_k16_s1": dict(n_residues=100_000_000, k=16, moltype="dayhoff", scaled=1, seed=20260103),
     "c4_slice_protein_k7_s10": dict(n_residues=1_000_000_000, k=7, moltype="protein", scaled=10, seed=20260104),
     "small": dict(n_residues=5_000_000, k=24, moltype="hp", scaled=1, seed=20260102),
+    # one eighth of the target run: what a rank holds when the 100 M-residue proteome is sharded over 8 GPUs
+    "target_shard_12m_dayhoff_k16_s1": dict(n_residues=12_500_000, k=16, moltype="dayhoff", scaled=1, seed=20260103),
 }
 
 
