@@ -91,6 +91,8 @@ __global__ void oversize_count_kernel(const uint32_t* __restrict__ start, uint32
 // ---------------------------------------------------------------------------------------------
 struct CsrOut {
     uint64_t* status;          // [nb] look-back words, zeroed per build
+    uint32_t* ticket;          // bucket tickets: a bucket's predecessors have always started (no reliance on the
+                               // order in which the hardware dispatches blockIdx)
     const uint32_t* oversize;  // [0] = number of oversize buckets; the CSR is fused only when it is 0
     uint64_t* keys;
     uint32_t* key_grp;
@@ -260,10 +262,13 @@ bucket_sort_kernel(const uint64_t* __restrict__ in_hash, const uint64_t* __restr
     __shared__ uint32_t s_nlong;
     __shared__ uint32_t s_long[LS_ND];
 
-    const uint32_t b = blockIdx.x;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __shared__ uint32_t s_bucket;
+    if (tid == 0) s_bucket = atomicAdd(f.ticket, 1u);
+    __syncthreads();
+    const uint32_t b = s_bucket;
     const uint32_t s = start[b], e = start[b + 1];
     const uint32_t m = e - s;
-    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (m == 0) { if (tid == 0) counts[b] = 0; bucket_empty(b, f); return; }
     if (m > (uint32_t)LS_CAP) return;  // oversize: sorted and counted by the host-driven fallback
     const int sh = lz + tb;  // >= 12 on this path: the low 12 bits of (hash << sh) are zero and carry the index
@@ -285,8 +290,11 @@ bucket_sort_kernel(const uint64_t* __restrict__ in_hash, const uint64_t* __restr
         const int dshift = last ? 64 - LS_DBITS : 48;
         const uint32_t dmask = last ? (uint32_t)(LS_ND - 1) : 127u;
         uint64_t* dst = last ? B : B1;
-        for (uint32_t i = tid; i < LS_WARPS * LS_ND / 2; i += LS_THREADS) reinterpret_cast<uint32_t*>(cnt)[i] = 0;
-        __syncthreads();
+        // warp-private counters: cleared by the owning warp (a block-wide barrier is only needed before a second pass
+        // reads what the first one scattered, and that one closes the first pass)
+#pragma unroll
+        for (int i = 0; i < LS_ND / 64; i++) reinterpret_cast<uint32_t*>(my)[lane + 32 * i] = 0;
+        __syncwarp();
         // sweep 1: digit groups within a row; digit, rank in the group and group size are kept for sweep 2
         uint32_t info[8];
 #pragma unroll
@@ -432,10 +440,13 @@ bucket_sort_rep_kernel(const uint64_t* __restrict__ in_hash, const uint64_t* __r
     __shared__ uint32_t s_wsum[8];
     __shared__ uint32_t s_ninv;
 
-    const uint32_t b = blockIdx.x;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __shared__ uint32_t s_bucket;
+    if (tid == 0) s_bucket = atomicAdd(f.ticket, 1u);
+    __syncthreads();
+    const uint32_t b = s_bucket;
     const uint32_t s = start[b], e = start[b + 1];
     const uint32_t m = e - s;
-    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (m == 0) { if (tid == 0) counts[b] = 0; bucket_empty(b, f); return; }
     if (m > (uint32_t)LS_CAP) return;  // oversize: sorted and counted by the host-driven fallback
     const int sh = lz + tb;  // >= 12 on this path: the low 12 bits of (hash << sh) are zero and carry the index
@@ -444,7 +455,9 @@ bucket_sort_rep_kernel(const uint64_t* __restrict__ in_hash, const uint64_t* __r
     const uint32_t R = (m + LS_THREADS - 1) / LS_THREADS;  // 1..8
     const uint32_t padded = R * LS_THREADS;
 
-    for (uint32_t j = tid; j < padded; j += LS_THREADS) {
+    // every warp loads the rows it owns (the same rows it counts below: no block-wide barrier in between)
+    for (uint32_t r = 0; r < R; r++) {
+        const uint32_t j = (warp * R + r) * 32 + lane;
         uint64_t item = ~0ull;
         if (j < m) item = ((in_hash[s + j] << sh) & ~0xfffull) | j;
         A[j] = item;
@@ -458,8 +471,11 @@ bucket_sort_rep_kernel(const uint64_t* __restrict__ in_hash, const uint64_t* __r
 #pragma unroll 1
     for (int pass = 0; pass < 2; pass++) {
         const int dshift = 48 + 8 * pass;
-        for (uint32_t i = tid; i < LS_WARPS * 256 / 2; i += LS_THREADS) reinterpret_cast<uint32_t*>(cnt)[i] = 0;
-        __syncthreads();
+        // the digit counters are warp-private: the owning warp clears them, no block-wide barrier needed (the rows
+        // read next were written by this warp in pass 0, and before the barrier that ends pass 0 in pass 1)
+#pragma unroll
+        for (int i = 0; i < 4; i++) reinterpret_cast<uint32_t*>(my)[lane + 32 * i] = 0;
+        __syncwarp();
         // sweep 1: groups of equal digits within a row; digit, rank in the group and group size are kept for sweep 2
         uint32_t info[8];
 #pragma unroll
@@ -828,7 +844,7 @@ uint64_t max_ranges(uint64_t n) {
 size_t table_bytes(uint64_t n) {
     // start[nb+1] + oversize[2] (u32), counts[nb] + prefix[nb+1] + status[nb] (u64)
     const uint64_t nb = max_ranges(n);
-    return (size_t)(((nb + 8) * 4 + (3 * nb + 4) * 8 + 1023) & ~(size_t)255);
+    return (size_t)(((nb + 8) * 4 + (3 * nb + 6) * 8 + 1023) & ~(size_t)255);
 }
 
 }  // namespace
@@ -875,6 +891,7 @@ cudaError_t build_index(const BuildArgs& a, cudaStream_t stream, int* out_in_a, 
     uint64_t* counts = (uint64_t*)(tp + (((size_t)(nb + 8) * 4 + 7) & ~(size_t)7));  // [nb]
     uint64_t* prefix = counts + nb;                                               // [nb + 1]
     uint64_t* status = prefix + nb + 1;                                           // [nb] look-back words (fused CSR)
+    uint32_t* ticket = (uint32_t*)(status + nb);                                  // [1] bucket ticket
 
     const uint64_t *fh, *fl;  // final sorted tuples
     if (tb < 0) {
@@ -905,9 +922,9 @@ cudaError_t build_index(const BuildArgs& a, cudaStream_t stream, int* out_in_a, 
         const char* lt_env = getenv("KS_LS_LONG");  // test hook: force the warp path for short sub-buckets too
         const uint32_t long_thr = lt_env ? (uint32_t)atoi(lt_env) : (uint32_t)LS_LONG;
         CsrOut f;
-        f.status = status; f.oversize = oversize; f.keys = a.keys; f.key_grp = a.key_grp; f.grp_start = a.grp_start;
+        f.status = status; f.ticket = ticket; f.oversize = oversize; f.keys = a.keys; f.key_grp = a.key_grp; f.grp_start = a.grp_start;
         f.d_counts = a.d_counts; f.n = n; f.nb = nb;
-        KS_TRY(cudaMemsetAsync(status, 0, (size_t)nb * 8, stream));
+        KS_TRY(cudaMemsetAsync(status, 0, (size_t)nb * 8 + 8, stream));
         // repeat-heavy inputs (small k-mer space) take the two-pass variant; KS_LS_VARIANT=rep|uni is a test hook
         const char* v_env = getenv("KS_LS_VARIANT");
         const bool rep = v_env ? (v_env[0] == 'r') : (a.repeat_heavy != 0);
