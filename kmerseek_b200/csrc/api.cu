@@ -293,6 +293,7 @@ struct ks_index {
     size_t ws_bytes = 0;
     // csr
     bool finalized = false;
+    bool hash_col_valid = true;  // false: d_hash of the sorted tuples is rebuilt on demand (ks_index_export)
     uint64_t* keys = nullptr;
     uint32_t *key_grp = nullptr, *grp_start = nullptr, *t_size = nullptr, *t_abund = nullptr, *dir = nullptr;
     uint64_t* d_counts = nullptr;
@@ -345,6 +346,7 @@ void upload_batch(ks_index* x, DeviceBatch& b, const ks_proteome* p, bool allow_
 void drop_csr(ks_index* x) {  // the buffers stay with the handle (grow-only), only the index state is dropped
     x->keys = nullptr; x->key_grp = x->grp_start = x->t_size = x->t_abund = x->dir = nullptr; x->d_counts = nullptr;
     x->finalized = false;
+    x->hash_col_valid = true;
     x->U = x->G = x->n_ids = 0;
 }
 
@@ -528,7 +530,8 @@ void finalize(ks_index* x) {
     a.temp = x->b_temp.ensure<char>(ar, a.temp_bytes);
     a.ev_sorted = x->ev[EV_SO1];
     a.ev_partitioned = x->ev[EV_PART];
-    int in_a = 1;
+    int in_a = 1, hash_written = 1;
+    a.hash_written = &hash_written;
     double t1 = dbg ? now_ms() : 0;
     KS_CUDA(cudaEventRecord(x->ev[EV_SO0], x->stream));
     KS_CUDA(build_index(a, x->stream, &in_a, &x->l_sort, &x->l_csr));
@@ -546,6 +549,7 @@ void finalize(ks_index* x) {
     KS_CUDA(cudaMemcpyAsync(c, x->d_counts, 16, cudaMemcpyDeviceToHost, x->stream));
     KS_CUDA(cudaStreamSynchronize(x->stream));
     x->U = c[0]; x->G = c[1];
+    x->hash_col_valid = hash_written != 0;
     x->finalized = true;
     if (dbg) fprintf(stderr, "[ks] finalize: alloc %.3f ms, build_index (host) %.3f ms, tail %.3f ms\n", t1 - t0, t2 - t1, now_ms() - t2);
 }
@@ -816,6 +820,10 @@ ks_status ks_index_export(ks_index* x, ks_sketch** out) {
         x->use();
         Arena keep(x->stream, &x->live_bytes), tmp(x->stream, &x->live_bytes);
         Grouped g;
+        if (!x->hash_col_valid) {
+            KS_CUDA(expand_sorted_hash(view_of(x), x->d_hash, x->stream));
+            x->hash_col_valid = true;
+        }
         group_by_owner(keep, tmp, x->d_hash, x->d_loc, x->n_tuples, (uint32_t)x->n_prot, x->end_bit(), &g, &x->l_csr);
         *out = sketch_to_host(g, x->d_hash, x->d_loc, x->n_tuples, x->n_prot, x->stream);
     });

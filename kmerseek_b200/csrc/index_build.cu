@@ -100,7 +100,22 @@ struct CsrOut {
     uint64_t* d_counts;
     uint64_t n;
     uint32_t nb;
+    // bucket directory over the unique keys, filled by the bucket that owns the range (dir_sub = dir_bits - tb >= 0:
+    // a sort bucket spans 2^dir_sub directory entries); dir_sub < 0: left to dir_kernel
+    uint32_t* dir;
+    int dir_bits, dir_sub;
 };
+
+// dir[x] = index of the first key whose directory bucket is >= x.  The key with index u and directory bucket x1, whose
+// predecessor (in this sort bucket) sits in x0, owns the entries (x0, x1].
+__device__ __forceinline__ void dir_fill(const CsrOut& f, int64_t x0, int64_t x1, uint32_t u) {
+    for (int64_t x = x0 + 1; x <= x1; x++) f.dir[x] = u;
+}
+// entries after the last key of sort bucket b (and the sentinel after the last bucket) = keys up to and including b
+__device__ __forceinline__ void dir_tail(const CsrOut& f, uint32_t b, int64_t x_last, uint32_t u_end) {
+    const int64_t end = ((int64_t)(b + 1) << f.dir_sub) - (b == f.nb - 1 ? 0 : 1);
+    dir_fill(f, x_last, end, u_end);
+}
 
 __device__ __forceinline__ void csr_totals(const CsrOut& f, uint64_t incl) {
     const uint64_t U = incl & 0x7fffffffu, G = incl >> 31;
@@ -115,6 +130,11 @@ __device__ __forceinline__ void bucket_empty(uint32_t b, const CsrOut& f) {
     if ((threadIdx.x >> 5) != 0 || f.oversize[0] != 0) return;
     const uint64_t excl = scan_lookback(f.status, b, 0);
     if (b == f.nb - 1 && (threadIdx.x & 31) == 0) csr_totals(f, excl);
+    if (f.dir_sub >= 0) {
+        const uint32_t u = (uint32_t)(excl & 0x7fffffffu);
+        const int64_t x0 = (int64_t)b << f.dir_sub, x1 = ((int64_t)(b + 1) << f.dir_sub) + (b == f.nb - 1 ? 1 : 0);
+        for (int64_t x = x0 + (threadIdx.x & 31); x < x1; x += 32) f.dir[x] = u;
+    }
 }
 
 // SPLIT: the hashes are written back in a second pass, after the aggregate is published (part of the wait for the
@@ -126,6 +146,7 @@ __device__ __forceinline__ void bucket_finish(const uint64_t* items, uint32_t m,
                                               uint32_t* __restrict__ t_size, const CsrOut& f) {
     __shared__ uint32_t s_cw[8 * LS_WARPS];  // per (chunk, warp): key heads | group heads << 16, then their prefix
     __shared__ uint64_t s_base;
+    __shared__ uint32_t s_tk;  // unique keys of this bucket
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t lt = (1u << lane) - 1u;
     const uint64_t top = tb ? ((uint64_t)b << (64 - tb)) : 0ull;
@@ -188,7 +209,7 @@ __device__ __forceinline__ void bucket_finish(const uint64_t* items, uint32_t m,
         }
         const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
         const uint32_t tk = tot & 0xffffu, tg = tot >> 16;
-        if (lane == 0) counts[b] = (uint64_t)tk | ((uint64_t)tg << 32);
+        if (lane == 0) { counts[b] = (uint64_t)tk | ((uint64_t)tg << 32); s_tk = tk; }
         agg = (uint64_t)tk | ((uint64_t)tg << 31);
         if (fused) scan_publish(f.status, b, agg);  // successors can go on; our own prefix is collected after pass B
     }
@@ -217,206 +238,16 @@ __device__ __forceinline__ void bucket_finish(const uint64_t* items, uint32_t m,
         if (hg) f.grp_start[g] = s + j;
         if (hk) {
             const uint32_t u = base_k + (pre & 0xffffu) + __popc(bk & lt);
-            f.keys[u] = (top | ((items[j] & ~0xfffull) >> tb)) >> lz;
+            const uint64_t full = top | ((items[j] & ~0xfffull) >> tb);
+            f.keys[u] = full >> lz;
             f.key_grp[u] = g;
+            if (f.dir_sub >= 0)
+                dir_fill(f, j ? (int64_t)((top | ((items[j - 1] & ~0xfffull) >> tb)) >> (64 - f.dir_bits)) : ((int64_t)b << f.dir_sub) - 1,
+                         (int64_t)(full >> (64 - f.dir_bits)), u);
         }
+        if (j == m - 1 && f.dir_sub >= 0)
+            dir_tail(f, b, (int64_t)((top | ((items[j] & ~0xfffull) >> tb)) >> (64 - f.dir_bits)), base_k + s_tk);
     }
-}
-
-// ---------------------------------------------------------------------------------------------
-// Bucket-local sort (the last pass of the MSD sort).
-//
-// After the partition by the top `tb` bits of the normalised hash (normalised = shifted left by the `lz`
-// leading bits that are zero under max_hash) every bucket is a contiguous range of a few thousand tuples.
-// One 512-thread CTA sorts one bucket in shared memory:
-//   item = remaining key bits, left-aligned, low 12 bits replaced by the tuple's index in the bucket
-// so comparing items compares (hash, original order) exactly and sorting items IS the stable sort.
-//   1. one stable counting pass over the next 9 key bits: every warp owns consecutive rows of 32 tuples,
-//      lanes that share a digit find each other with one MATCH.ANY, the lowest lane of a group updates the
-//      warp-private digit counter; a (digit, warp) scan turns the counters into offsets and the items are
-//      scattered into 512 sub-buckets (about 6 items each);
-//   2. thread t puts sub-bucket t in order by insertion on the full item -- exact for any input, a handful of
-//      moves for uniform hashes, none for repeats of one hash (they arrive in order); sub-buckets too long for
-//      one thread (heavy repeats) are checked, and if needed ranked, by a whole warp;
-//   3. the bucket streams back to HBM once, in final order: the hash is rebuilt from the item, loc is gathered
-//      from the bucket's own window of the input, and the CTA counts unique hashes and (hash, protein) groups
-//      and subtracts repeated (hash, protein) pairs from the protein's sketch size on the way out.
-// ---------------------------------------------------------------------------------------------
-constexpr int LS_DBITS = 9;
-constexpr int LS_ND = 1 << LS_DBITS;
-constexpr int LS_LONG = 48;  // sub-buckets longer than this (repeats of a hash, mostly) are left to a warp
-static_assert(LS_ND == LS_THREADS, "one thread per digit / sub-bucket");
-constexpr size_t LS_SMEM = (size_t)LS_CAP * 8 + (size_t)LS_WARPS * LS_ND * 2 + (LS_ND + 1) * 4 + 64;  // ~50 KB (one pass)
-constexpr size_t LS_SMEM2 = LS_SMEM + (size_t)LS_CAP * 8;                                              // ~82 KB (two passes)
-
-__global__ void __launch_bounds__(LS_THREADS, 3)
-bucket_sort_kernel(const uint64_t* __restrict__ in_hash, const uint64_t* __restrict__ in_loc,
-                   uint64_t* __restrict__ out_hash, uint64_t* __restrict__ out_loc,
-                   const uint32_t* __restrict__ start, int lz, int tb, uint64_t* __restrict__ counts,
-                   uint32_t* __restrict__ t_size, uint32_t long_threshold, int n_pass, CsrOut f) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint64_t* B = reinterpret_cast<uint64_t*>(smem_raw);                  // [LS_CAP] items, grouped by digit
-    uint16_t* cnt = reinterpret_cast<uint16_t*>(B + (n_pass == 2 ? 2 : 1) * LS_CAP);  // [LS_WARPS][LS_ND] warp-private counters
-    uint32_t* dstart = reinterpret_cast<uint32_t*>(cnt + LS_WARPS * LS_ND);  // [LS_ND + 1] sub-bucket offsets
-    __shared__ uint32_t s_wsum[LS_WARPS];
-    __shared__ uint32_t s_nlong;
-    __shared__ uint32_t s_long[LS_ND];
-
-    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    __shared__ uint32_t s_bucket;
-    if (tid == 0) s_bucket = atomicAdd(f.ticket, 1u);
-    __syncthreads();
-    const uint32_t b = s_bucket;
-    const uint32_t s = start[b], e = start[b + 1];
-    const uint32_t m = e - s;
-    if (m == 0) { if (tid == 0) counts[b] = 0; bucket_empty(b, f); return; }
-    if (m > (uint32_t)LS_CAP) return;  // oversize: sorted and counted by the host-driven fallback
-    const int sh = lz + tb;  // >= 12 on this path: the low 12 bits of (hash << sh) are zero and carry the index
-
-    // rows of 32 consecutive tuples; every warp owns R consecutive rows
-    const uint32_t R = (m + LS_THREADS - 1) / LS_THREADS;  // 1..8
-    const uint32_t lt = (1u << lane) - 1u;
-    uint16_t* my = cnt + warp * LS_ND;
-
-    if (tid == 0) s_nlong = 0;
-    // Counting passes, least significant digit first.  One pass (9 bits) when hashes rarely repeat; two passes
-    // (7 + 9 bits) when they do (small alphabets: a bucket then holds few distinct hashes, each many times, and
-    // lists that interleave two of them are expensive to put in order by comparison).
-    uint64_t* B1 = B + LS_CAP;  // second item buffer, only allocated for two passes
-#pragma unroll 1
-    for (int pass = 0; pass < n_pass; pass++) {
-        const bool from_input = pass == 0;
-        const bool last = pass == n_pass - 1;
-        const int dshift = last ? 64 - LS_DBITS : 48;
-        const uint32_t dmask = last ? (uint32_t)(LS_ND - 1) : 127u;
-        uint64_t* dst = last ? B : B1;
-        // warp-private counters: cleared by the owning warp (a block-wide barrier is only needed before a second pass
-        // reads what the first one scattered, and that one closes the first pass)
-#pragma unroll
-        for (int i = 0; i < LS_ND / 64; i++) reinterpret_cast<uint32_t*>(my)[lane + 32 * i] = 0;
-        __syncwarp();
-        // sweep 1: digit groups within a row; digit, rank in the group and group size are kept for sweep 2
-        uint32_t info[8];
-#pragma unroll
-        for (uint32_t r = 0; r < 8; r++) {
-            info[r] = 0xffffffffu;
-            if (r < R) {
-                const uint32_t j = (warp * R + r) * 32 + lane;
-                uint32_t d = dmask;  // tuples past the end: never counted, never scattered
-                if (j < m) d = (uint32_t)((from_input ? (in_hash[s + j] << sh) : B1[j]) >> dshift) & dmask;
-                const uint32_t peers = __match_any_sync(0xffffffffu, d | (j < m ? 0u : 0x10000u));
-                const uint32_t rank = __popc(peers & lt), size = __popc(peers);
-                if (rank == 0 && j < m) my[d] += (uint16_t)size;
-                info[r] = d | (rank << 9) | (size << 15) | (j < m ? 0u : 0x80000000u);
-                __syncwarp();
-            }
-        }
-        __syncthreads();
-        // exclusive scan in (digit, warp) order: thread t owns digit t
-        {
-            uint32_t total = 0;
-#pragma unroll
-            for (int w = 0; w < LS_WARPS; w++) {
-                const uint32_t c = cnt[w * LS_ND + tid];
-                cnt[w * LS_ND + tid] = (uint16_t)total;
-                total += c;
-            }
-            uint32_t incl = total;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
-                if ((int)lane >= o) incl += v;
-            }
-            if (lane == 31) s_wsum[warp] = incl;
-            __syncthreads();
-            uint32_t off = 0;
-            for (uint32_t w = 0; w < warp; w++) off += s_wsum[w];
-            dstart[tid] = off + incl - total;
-            if (tid == LS_THREADS - 1) dstart[LS_ND] = off + incl;  // == m
-        }
-        __syncthreads();
-        // sweep 2: stable scatter (first pass: items are built from the input, still in L1/L2)
-#pragma unroll
-        for (uint32_t r = 0; r < 8; r++) {
-            if (r < R) {
-                const uint32_t j = (warp * R + r) * 32 + lane;
-                const bool real = !(info[r] >> 31);
-                const uint32_t d = info[r] & (LS_ND - 1), rank = (info[r] >> 9) & 63u, size = (info[r] >> 15) & 63u;
-                uint32_t base = 0;
-                if (real) base = dstart[d] + my[d];
-                __syncwarp();
-                if (real && rank == 0) my[d] += (uint16_t)size;
-                __syncwarp();
-                if (real) dst[base + rank] = from_input ? (((in_hash[s + j] << sh) & ~0xfffull) | j) : B1[j];
-            }
-        }
-        __syncthreads();
-    }
-    // every sub-bucket in order: one thread each; long ones are listed for the warps
-    {
-        const uint32_t a0 = dstart[tid], b0 = dstart[tid + 1];
-        if (b0 - a0 > long_threshold) {
-            s_long[atomicAdd(&s_nlong, 1u)] = tid;
-        } else {
-            if (b0 > a0) {
-                uint64_t prev = B[a0];  // the largest item placed so far
-                for (uint32_t t = a0 + 1; t < b0; t++) {
-                    const uint64_t x = B[t];
-                    if (x >= prev) { prev = x; continue; }  // already in place (always, for repeats of one hash)
-                    uint32_t u = t;
-                    do { B[u] = B[u - 1]; u--; } while (u > a0 && B[u - 1] > x);
-                    B[u] = x;
-                }
-            }
-        }
-    }
-    __syncthreads();
-    if (s_nlong) {  // uniform: written before the barrier, not modified after
-        const uint32_t nlong = s_nlong;
-        for (uint32_t k = warp; k < nlong; k += LS_WARPS) {
-            const uint32_t a0 = dstart[s_long[k]], b0 = dstart[s_long[k] + 1];
-            bool sorted = true;
-            for (uint32_t t = a0 + 1 + lane; t < b0; t += 32) sorted &= B[t - 1] <= B[t];
-            if (__all_sync(0xffffffffu, sorted)) continue;  // repeats of few hashes arrive in order
-            // mixed list (repeats of two or more hashes that share 25 bits, interleaved): every lane ranks its items
-            // against the whole list (items are distinct)
-            const uint32_t n = b0 - a0;
-            if (n <= 128) {
-                uint64_t mine[4];
-                uint32_t below[4];
-#pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    const uint32_t t = a0 + lane + 32 * q;
-                    mine[q] = t < b0 ? B[t] : ~0ull;
-                    below[q] = 0;
-                }
-                for (uint32_t u = a0; u < b0; u++) {
-                    const uint64_t x = B[u];
-#pragma unroll
-                    for (int q = 0; q < 4; q++) below[q] += x < mine[q];
-                }
-                __syncwarp();
-#pragma unroll
-                for (int q = 0; q < 4; q++)
-                    if (a0 + lane + 32 * q < b0) B[a0 + below[q]] = mine[q];
-            } else {
-                // longer than the registers hold: the bucket's own output window, rewritten in final order right
-                // below, serves as the scratch copy
-                for (uint32_t t = a0 + lane; t < b0; t += 32) out_hash[s + t] = B[t];
-                __syncwarp();
-                for (uint32_t t = a0 + lane; t < b0; t += 32) {
-                    const uint64_t x = out_hash[s + t];
-                    uint32_t bl = 0;
-                    for (uint32_t u = a0; u < b0; u++) bl += out_hash[s + u] < x;
-                    B[a0 + bl] = x;
-                }
-            }
-            __syncwarp();
-        }
-        __syncthreads();
-    }
-
-    bucket_finish<true>(B, m, s, b, lz, tb, in_loc, out_hash, out_loc, counts, t_size, f);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -637,6 +468,233 @@ bucket_sort_rep_kernel(const uint64_t* __restrict__ in_hash, const uint64_t* __r
 }
 
 
+// Tail of the bin variant: like bucket_finish, with the loc gathers of a thread issued back to back, the protein ids
+// parked in shared memory (so a head test reads two neighbouring slots instead of shuffling and re-gathering), and no
+// sorted hash column: on the fused path the CSR arrays carry the hashes (keys) and nothing on the hot path reads
+// hash[i] of the sorted tuples (expand_sorted_hash rebuilds the column for the export calls).
+__device__ __forceinline__ void bucket_finish_bin(const uint64_t* items, uint32_t* spid, uint32_t m, uint32_t s, uint32_t b,
+                                                  int lz, int tb, const uint64_t* __restrict__ in_loc,
+                                                  uint64_t* __restrict__ out_hash, uint64_t* __restrict__ out_loc,
+                                                  uint64_t* __restrict__ counts, uint32_t* __restrict__ t_size,
+                                                  const CsrOut& f) {
+    __shared__ uint32_t s_cw[8 * LS_WARPS];  // per (row, warp): key heads | group heads << 16, then their prefix
+    __shared__ uint64_t s_base;
+    __shared__ uint32_t s_tk;  // unique keys of this bucket
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t lt = (1u << lane) - 1u;
+    const uint64_t top = tb ? ((uint64_t)b << (64 - tb)) : 0ull;
+    const bool fused = f.oversize[0] == 0;
+    uint64_t loc[8];
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        const uint32_t j = r * LS_THREADS + tid;
+        if (j < m) loc[r] = in_loc[s + (uint32_t)(items[j] & 0xfffu)];  // the bucket's own window of the input (L1/L2)
+    }
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        const uint32_t j = r * LS_THREADS + tid;
+        if (j < m) spid[j] = (uint32_t)(loc[r] >> 32);
+    }
+    __syncthreads();
+    uint32_t flags = 0;  // 2 bits per row: this thread's element is a key head / a group head
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        const uint32_t j = r * LS_THREADS + tid;
+        if (r * LS_THREADS < m) {  // uniform
+            bool hk = false, hg = false;
+            if (j < m) {
+                const uint32_t pid = (uint32_t)(loc[r] >> 32);
+                hk = j == 0 || ((items[j - 1] ^ items[j]) >> 12) != 0;
+                hg = hk || spid[j - 1] != pid;
+                if (!hg) atomicSub(&t_size[pid], 1u);
+            }
+            flags |= ((hk ? 1u : 0u) | (hg ? 2u : 0u)) << (2 * r);
+            const uint32_t ck = __popc(__ballot_sync(0xffffffffu, hk)), cg = __popc(__ballot_sync(0xffffffffu, hg));
+            if (lane == 0) s_cw[r * LS_WARPS + warp] = ck | (cg << 16);
+        } else if (lane == 0) {
+            s_cw[r * LS_WARPS + warp] = 0;
+        }
+    }
+    __syncthreads();
+    uint64_t agg = 0;
+    if (warp == 0) {
+        // exclusive prefix over the (row, warp) counts, 4 entries per lane; both halves stay below 2^16
+        uint32_t v[4], local = 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++) { v[i] = s_cw[lane * 4 + i]; local += v[i]; }
+        uint32_t incl = local;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((int)lane >= o) incl += t;
+        }
+        uint32_t run = incl - local;
+#pragma unroll
+        for (int i = 0; i < 4; i++) { s_cw[lane * 4 + i] = run; run += v[i]; }
+        const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
+        const uint32_t tk = tot & 0xffffu, tg = tot >> 16;
+        if (lane == 0) { counts[b] = (uint64_t)tk | ((uint64_t)tg << 32); s_tk = tk; }
+        agg = (uint64_t)tk | ((uint64_t)tg << 31);
+        if (fused) scan_publish(f.status, b, agg);  // successors can go on; our own prefix is collected after the stores
+    }
+    // the tuples go back to HBM in final order (this is where part of the wait for the predecessors is hidden)
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        const uint32_t j = r * LS_THREADS + tid;
+        if (j < m) {
+            out_loc[s + j] = loc[r];
+            if (!fused) out_hash[s + j] = (top | ((items[j] & ~0xfffull) >> tb)) >> lz;  // the fallback passes read it
+        }
+    }
+    if (warp == 0) {
+        uint64_t excl = ~0ull;
+        if (fused) {
+            excl = scan_collect(f.status, b, agg);
+            if (b == f.nb - 1 && lane == 0) csr_totals(f, excl + agg);
+        }
+        if (lane == 0) s_base = excl;
+    }
+    __syncthreads();
+    if (s_base == ~0ull) return;  // an oversize bucket exists: the CSR is written by csr_write_kernel after the fallback
+    const uint32_t base_k = (uint32_t)(s_base & 0x7fffffffu), base_g = (uint32_t)(s_base >> 31);
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        if (r * LS_THREADS < m) {  // uniform
+            const uint32_t j = r * LS_THREADS + tid;
+            const bool hk = (flags >> (2 * r)) & 1u, hg = (flags >> (2 * r)) & 2u;
+            const uint32_t bk = __ballot_sync(0xffffffffu, hk), bg = __ballot_sync(0xffffffffu, hg);
+            const uint32_t pre = s_cw[r * LS_WARPS + warp];
+            const uint32_t g = base_g + (pre >> 16) + __popc(bg & lt);
+            if (hg) f.grp_start[g] = s + j;
+            if (hk) {
+                const uint32_t u = base_k + (pre & 0xffffu) + __popc(bk & lt);
+                const uint64_t full = top | ((items[j] & ~0xfffull) >> tb);
+                f.keys[u] = full >> lz;
+                f.key_grp[u] = g;
+                if (f.dir_sub >= 0)
+                    dir_fill(f, j ? (int64_t)((top | ((items[j - 1] & ~0xfffull) >> tb)) >> (64 - f.dir_bits)) : ((int64_t)b << f.dir_sub) - 1,
+                             (int64_t)(full >> (64 - f.dir_bits)), u);
+            }
+            if (j == m - 1 && f.dir_sub >= 0)
+                dir_tail(f, b, (int64_t)((top | ((items[j] & ~0xfffull) >> tb)) >> (64 - f.dir_bits)), base_k + s_tk);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Bucket-local sort, bin variant (the default): ONE unstable counting pass over the next 12 key bits with
+// shared-memory atomics, then odd-even transposition rounds on the full items until nothing moves.
+//
+// The item carries the tuple's index in the bucket in its low 12 bits, so sorting items by value IS the stable
+// sort: the counting pass does not have to be stable, which removes the warp-private counters, the MATCH.ANY
+// ranking, the (digit, warp) scan and the second pass of the other two variants.  A bin holds the repeats of one
+// hash (hp k=24: ~11) or 0-2 unrelated items (uniform hashes).  Tuples are taken in rows of 512 consecutive
+// items; with a barrier after every row (STEPPED, repeat-heavy input) a bin is filled row by row, so an item is
+// at most a few slots from its final position and a handful of rounds, perfectly balanced over the threads,
+// finish the sort.  The same code is exact for any input: a bucket full of one hash just takes more rounds.
+// ---------------------------------------------------------------------------------------------
+constexpr int BN_BITS = 12;
+constexpr int BN_BINS = 1 << BN_BITS;
+constexpr int BN_PER_THREAD = BN_BINS / LS_THREADS;  // 8 consecutive bins per thread
+constexpr size_t BN_SMEM = (size_t)LS_CAP * 8 + (size_t)BN_BINS * 4;  // 48 KB
+static_assert(BN_PER_THREAD == 8, "two 16-byte loads per thread in the scan");
+
+template <bool STEPPED>
+__global__ void __launch_bounds__(LS_THREADS, 3)
+bucket_sort_bin_kernel(const uint64_t* __restrict__ in_hash, const uint64_t* __restrict__ in_loc,
+                       uint64_t* __restrict__ out_hash, uint64_t* __restrict__ out_loc,
+                       const uint32_t* __restrict__ start, int lz, int tb, uint64_t* __restrict__ counts,
+                       uint32_t* __restrict__ t_size, CsrOut f) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t* B = reinterpret_cast<uint64_t*>(smem_raw);            // [LS_CAP] items, grouped by bin
+    uint32_t* cnt = reinterpret_cast<uint32_t*>(B + LS_CAP);        // [BN_BINS] counts, then exclusive offsets
+    __shared__ uint32_t s_wsum[LS_WARPS];
+    __shared__ uint32_t s_bucket;
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_bucket = atomicAdd(f.ticket, 1u);
+    reinterpret_cast<uint4*>(cnt)[tid] = make_uint4(0, 0, 0, 0);
+    reinterpret_cast<uint4*>(cnt)[tid + LS_THREADS] = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+    const uint32_t b = s_bucket;
+    const uint32_t s = start[b], e = start[b + 1];
+    const uint32_t m = e - s;
+    if (m == 0) { if (tid == 0) counts[b] = 0; bucket_empty(b, f); return; }
+    if (m > (uint32_t)LS_CAP) return;  // oversize: sorted and counted by the host-driven fallback
+    const int sh = lz + tb;  // >= 12 on this path: the low 12 bits of (hash << sh) are zero and carry the index
+
+    // 1. count: rows of 512 consecutive tuples, one per thread; the ticket a tuple draws is its slot in the bin
+    // STEPPED (repeat-heavy input): a barrier after every row, so that a bin is ordered by row and only items of the
+    // same row can be out of order -- the repeats of a hash then need a handful of moves instead of a full sort.
+    uint64_t item[8];
+    uint32_t slot[4] = {0, 0, 0, 0};  // two 16-bit slots per word
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        const uint32_t j = r * LS_THREADS + tid;
+        if (j < m) item[r] = ((in_hash[s + j] << sh) & ~0xfffull) | j;
+    }
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        const uint32_t j = r * LS_THREADS + tid;
+        if (j < m) slot[r >> 1] |= atomicAdd(&cnt[(uint32_t)(item[r] >> (64 - BN_BITS))], 1u) << (16 * (r & 1));
+        if (STEPPED && (r + 1) * LS_THREADS < m) __syncthreads();  // uniform
+    }
+    __syncthreads();
+    // 2. exclusive scan of the bin counts; thread t owns bins 8t .. 8t+7
+    {
+        uint4 c0 = reinterpret_cast<uint4*>(cnt)[2 * tid], c1 = reinterpret_cast<uint4*>(cnt)[2 * tid + 1];
+        const uint32_t total = c0.x + c0.y + c0.z + c0.w + c1.x + c1.y + c1.z + c1.w;
+        uint32_t incl = total;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((int)lane >= o) incl += v;
+        }
+        if (lane == 31) s_wsum[warp] = incl;
+        __syncthreads();
+        uint32_t off = 0;
+#pragma unroll
+        for (int w = 0; w < LS_WARPS; w++) off += w < (int)warp ? s_wsum[w] : 0u;
+        uint4 e0, e1;
+        e0.x = off + incl - total; e0.y = e0.x + c0.x; e0.z = e0.y + c0.y; e0.w = e0.z + c0.z;
+        e1.x = e0.w + c0.w; e1.y = e1.x + c1.x; e1.z = e1.y + c1.y; e1.w = e1.z + c1.z;
+        reinterpret_cast<uint4*>(cnt)[2 * tid] = e0;
+        reinterpret_cast<uint4*>(cnt)[2 * tid + 1] = e1;
+    }
+    __syncthreads();
+    // 3. scatter into the bins
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        const uint32_t j = r * LS_THREADS + tid;
+        if (j < m) B[cnt[(uint32_t)(item[r] >> (64 - BN_BITS))] + ((slot[r >> 1] >> (16 * (r & 1))) & 0xffffu)] = item[r];
+    }
+    __syncthreads();
+    // 4. odd-even transposition until nothing moves.  The array is ordered by bin and, within a bin, by row; only items
+    //    of the same (bin, row) can be out of place, so an item is a few positions from its final one and a handful of
+    //    perfectly balanced rounds finish the sort -- for any input (a bucket full of one hash needs more rounds, not
+    //    a different code path).
+    {
+        const uint32_t np0 = m >> 1, np1 = (m - 1) >> 1;  // pairs (2i, 2i+1) and (2i+1, 2i+2)
+        ulonglong2* B2 = reinterpret_cast<ulonglong2*>(B);
+        int again;
+        do {
+            int sw = 0;
+            for (uint32_t i = tid; i < np0; i += LS_THREADS) {
+                const ulonglong2 v = B2[i];
+                if (v.x > v.y) { B2[i] = make_ulonglong2(v.y, v.x); sw = 1; }
+            }
+            __syncthreads();
+            for (uint32_t i = tid; i < np1; i += LS_THREADS) {
+                const uint64_t x = B[2 * i + 1], y = B[2 * i + 2];
+                if (x > y) { B[2 * i + 1] = y; B[2 * i + 2] = x; sw = 1; }
+            }
+            again = __syncthreads_or(sw);
+        } while (again);
+    }
+
+    bucket_finish_bin(B, cnt, m, s, b, lz, tb, in_loc, out_hash, out_loc, counts, t_size, f);
+}
+
 // Counts for ranges the bucket sort did not handle: oversize buckets (only_oversize = 1), or every range on the
 // library-sort path (only_oversize = 0).
 __global__ void __launch_bounds__(256)
@@ -847,7 +905,25 @@ size_t table_bytes(uint64_t n) {
     return (size_t)(((nb + 8) * 4 + (3 * nb + 6) * 8 + 1023) & ~(size_t)255);
 }
 
+// hash[i] of the sorted tuples from the CSR arrays: one thread per key writes its row.
+__global__ void expand_hash_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ key_grp,
+                                   const uint32_t* __restrict__ grp_start, const uint64_t* __restrict__ d_counts,
+                                   uint64_t* __restrict__ hash) {
+    const uint64_t U = d_counts[0];
+    for (uint64_t u = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; u < U; u += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t h = keys[u];
+        const uint32_t e = grp_start[key_grp[u + 1]];
+        for (uint32_t i = grp_start[key_grp[u]]; i < e; i++) hash[i] = h;
+    }
+}
+
 }  // namespace
+
+cudaError_t expand_sorted_hash(const CsrView& v, uint64_t* hash, cudaStream_t stream) {
+    if (v.n == 0) return cudaSuccess;
+    expand_hash_kernel<<<148 * 8, 256, 0, stream>>>(v.keys, v.key_grp, v.grp_start, v.d_counts, hash);
+    return cudaGetLastError();
+}
 
 size_t build_temp_bytes(uint64_t n, int end_bit) {
     size_t a = 0, b = 0;
@@ -864,6 +940,7 @@ cudaError_t build_index(const BuildArgs& a, cudaStream_t stream, int* out_in_a, 
     const uint64_t n = a.n;
     const int lz = 64 - a.end_bit;
     *out_in_a = 1;
+    if (a.hash_written) *a.hash_written = 1;
     if (a.n_prot) {
         protein_abund_kernel<<<(a.n_prot + 255) / 256, 256, 0, stream>>>(a.loc_a, n, a.n_prot, a.t_abund, a.t_size);
         KS_TRY(cudaGetLastError());
@@ -918,21 +995,24 @@ cudaError_t build_index(const BuildArgs& a, cudaStream_t stream, int* out_in_a, 
         // 2. bucket boundaries; one CTA per bucket sorts it in shared memory and counts its heads
         bucket_start_kernel<<<(nb + 1 + 255) / 256, 256, 0, stream>>>(sh, n, lz, tb, start, oversize);
         oversize_count_kernel<<<(nb + 255) / 256, 256, 0, stream>>>(start, nb, oversize);
-        KS_TRY(cudaFuncSetAttribute(bucket_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LS_SMEM2));
-        const char* lt_env = getenv("KS_LS_LONG");  // test hook: force the warp path for short sub-buckets too
-        const uint32_t long_thr = lt_env ? (uint32_t)atoi(lt_env) : (uint32_t)LS_LONG;
         CsrOut f;
         f.status = status; f.ticket = ticket; f.oversize = oversize; f.keys = a.keys; f.key_grp = a.key_grp; f.grp_start = a.grp_start;
         f.d_counts = a.d_counts; f.n = n; f.nb = nb;
+        f.dir = a.dir; f.dir_bits = a.dir_bits; f.dir_sub = a.dir_bits >= tb && !getenv("KS_DIR_KERNEL") ? a.dir_bits - tb : -1;
         KS_TRY(cudaMemsetAsync(status, 0, (size_t)nb * 8 + 8, stream));
-        // repeat-heavy inputs (small k-mer space) take the two-pass variant; KS_LS_VARIANT=rep|uni is a test hook
+        // repeat-heavy inputs (small k-mer space, e.g. hp k=24) take the two-pass stable variant, everything else the bin
+        // variant; KS_LS_VARIANT = rep | bn | bs (bin variant without / with a barrier per row) is a test hook
         const char* v_env = getenv("KS_LS_VARIANT");
-        const bool rep = v_env ? (v_env[0] == 'r') : (a.repeat_heavy != 0);
-        if (rep) {
+        const bool bin = v_env ? (v_env[0] == 'b') : (a.repeat_heavy == 0);
+        if (bin) {
+            KS_TRY(cudaFuncSetAttribute(bucket_sort_bin_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BN_SMEM));
+            KS_TRY(cudaFuncSetAttribute(bucket_sort_bin_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BN_SMEM));
+            const bool stepped = v_env && v_env[1] == 's';
+            if (stepped) bucket_sort_bin_kernel<true><<<nb, LS_THREADS, BN_SMEM, stream>>>(sh, sl, dh, dl, start, lz, tb, counts, a.t_size, f);
+            else bucket_sort_bin_kernel<false><<<nb, LS_THREADS, BN_SMEM, stream>>>(sh, sl, dh, dl, start, lz, tb, counts, a.t_size, f);
+        } else {
             KS_TRY(cudaFuncSetAttribute(bucket_sort_rep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LS_SMEM_REP));
             bucket_sort_rep_kernel<<<nb, LS_THREADS, LS_SMEM_REP, stream>>>(sh, sl, dh, dl, start, lz, tb, counts, a.t_size, f);
-        } else {
-            bucket_sort_kernel<<<nb, LS_THREADS, LS_SMEM, stream>>>(sh, sl, dh, dl, start, lz, tb, counts, a.t_size, long_thr, 1, f);
         }
         KS_TRY(cudaGetLastError());
         *sort_launches += 3;
@@ -960,8 +1040,11 @@ cudaError_t build_index(const BuildArgs& a, cudaStream_t stream, int* out_in_a, 
         fl = dl;
         if (a.ev_sorted) KS_TRY(cudaEventRecord(a.ev_sorted, stream));
         if (n_over == 0) {  // the bucket sort wrote keys / key_grp / grp_start itself: only the directory is left
-            dir_kernel<<<148 * 8, 256, 0, stream>>>(a.keys, a.d_counts, a.dir, a.dir_bits, a.dir_shift);
-            *csr_launches += 1;
+            if (bin && a.hash_written) *a.hash_written = 0;  // ... and the bin variant skipped the sorted hash column
+            if (f.dir_sub < 0) {                             // ... and, normally, its part of the directory
+                dir_kernel<<<148 * 8, 256, 0, stream>>>(a.keys, a.d_counts, a.dir, a.dir_bits, a.dir_shift);
+                *csr_launches += 1;
+            }
             return cudaGetLastError();
         }
     }

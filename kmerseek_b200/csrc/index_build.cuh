@@ -48,6 +48,7 @@ struct BuildArgs {
     int dir_bits, dir_shift;
     void* temp;
     size_t temp_bytes;
+    int* hash_written = nullptr;  // out (host): 0 when the sorted hash column was not written (see expand_sorted_hash)
     cudaEvent_t ev_partitioned;  // recorded after the partition by the top bits (stage timing); may be null
     cudaEvent_t ev_sorted;       // recorded between the sort and the CSR write; may be null
 };
@@ -57,5 +58,9 @@ size_t build_temp_bytes(uint64_t n, int end_bit);
 // Synchronises the stream once (oversize-bucket count).  Adds the kernels launched to the two counters.
 cudaError_t build_index(const BuildArgs& a, cudaStream_t stream, int* out_in_a, uint64_t* sort_launches,
                         uint64_t* csr_launches);
+
+// Rebuild hash[i] of the sorted tuples from keys / key_grp / grp_start (the fused bucket sort does not write the
+// column: nothing on the hot path reads it).
+cudaError_t expand_sorted_hash(const CsrView& v, uint64_t* hash, cudaStream_t stream);
 
 }  // namespace ks

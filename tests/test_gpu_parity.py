@@ -373,28 +373,10 @@ def test_general_sketch_path_at_scaled_1(K, O, monkeypatch):
         assert np.array_equal(h, oh) and np.array_equal(pid, opid) and np.array_equal(pos, opos)
 
 
-def test_bucket_sort_warp_path_for_long_sub_buckets(K, O, monkeypatch):
-    """Sub-buckets longer than a threshold are put in order by a whole warp (sortedness check, then ranking).
-    Lower the threshold to 1 so that every sub-bucket of a real proteome goes through that path."""
-    from kmerseek_b200 import synth
-    monkeypatch.setenv("KS_LS_LONG", "1")
-    res, offs = synth.proteome(14_000_000, 99)
-    prot = K.Proteome.from_packed(res, offs)
-    for k, moltype in ((24, "hp"), (7, "protein")):
-        with K.ProteomeIndex("db", k, 1, moltype) as idx:
-            idx.add_proteome(prot)
-            idx.finalize()
-            keys, row_ptr, pid, pos = idx.csr()
-            oh, opid, opos = O.sketch_tuples(res, offs, k, moltype, 1)
-            okeys, orow, ops, oqs = O.build_index(oh, opid, opos)
-            assert np.array_equal(keys, okeys) and np.array_equal(row_ptr, orow)
-            assert np.array_equal(pid, ops) and np.array_equal(pos, oqs)
-
-
-@pytest.mark.parametrize("variant", ["uni", "rep"])
+@pytest.mark.parametrize("variant", ["rep", "bs", "bn"])
 def test_bucket_sort_both_variants(K, O, monkeypatch, variant):
-    """The bucket sort picks the one-pass + insertion kernel (hashes rarely repeat) or the two-pass kernel (small
-    k-mer space, repeat-heavy); both must give the same index on both kinds of data."""
+    """The bucket sort picks the bin kernel (hashes rarely repeat) or the two-pass stable kernel (small k-mer space,
+    repeat-heavy); every variant must give the same index on both kinds of data."""
     from kmerseek_b200 import synth
     monkeypatch.setenv("KS_LS_VARIANT", variant)
     res, offs = synth.proteome(14_000_000, 2024)
