@@ -886,6 +886,9 @@ ks_status ks_search_resident(ks_index* x, uint32_t flags, ks_search_result** out
         ResultDevice* rd = new ResultDevice{keep, {}};
         if (!r) { delete rd; delete keep; throw std::bad_alloc(); }
         r->device_block = rd;
+        const bool dbg = getenv("KS_TIMING") != nullptr;
+        const double t0 = dbg ? now_ms() : 0;
+        double t1 = 0, t2 = 0;
         try {
             Arena tmp(st, &x->live_bytes);
             KS_CUDA(cudaEventRecord(x->ev[EV_Q0], st));
@@ -897,6 +900,7 @@ ks_status ks_search_resident(ks_index* x, uint32_t flags, ks_search_result** out
             search_device(*keep, tmp, view_of(x), qh, ql, nqt, (uint32_t)qb.n_prot, x->params.ksize, x->end_bit(),
                           (flags & KS_SEARCH_HITS) != 0, &qs, &sd, &x->l_search);
             KS_CUDA(cudaEventRecord(x->ev[EV_Q1], st));
+            if (dbg) t1 = now_ms();
             r->n_queries = qb.n_prot;
             r->n_pairs = sd.n_pairs;
             r->n_hits = sd.n_hits;
@@ -943,12 +947,15 @@ ks_status ks_search_resident(ks_index* x, uint32_t flags, ks_search_result** out
                 }
             }
             KS_CUDA(cudaStreamSynchronize(st));
+            if (dbg) t2 = now_ms();
             r->q_abunds = (uint64_t*)malloc((qs.n_entries ? qs.n_entries : 1) * 8);
             if (!r->q_abunds) throw std::bad_alloc();
             for (uint64_t e = 0; e < qs.n_entries; e++) r->q_abunds[e] = first[e + 1] - first[e];
             free(first);
             KS_CUDA(cudaEventElapsedTime(&r->ms_device, x->ev[EV_Q0], x->ev[EV_Q1]));
             x->ms_search = r->ms_device;
+            if (dbg) fprintf(stderr, "[ks] search: device %.3f ms; host: launch+syncs %.3f ms, read-back %.3f ms, tail %.3f ms\n",
+                             r->ms_device, t1 - t0, t2 - t1, now_ms() - t2);
             if (!(flags & KS_SEARCH_DEVICE_ONLY)) {
                 // the host copy is complete: give the device columns back now, so that the result no longer
                 // depends on the index (and its stream) staying alive

@@ -39,6 +39,9 @@ class SearchResult:
         if self._owner is not None:
             self.pairs = {k: v.copy() for k, v in self.pairs.items()} if self.pairs else self.pairs
             self.hits = {k: v.copy() for k, v in self.hits.items()} if self.hits else self.hits
+            q = self.query_sketches
+            if isinstance(q, _QuerySketches):
+                self.query_sketches = _QuerySketches(q._p, q._m.copy(), q._a.copy())
             self._owner = None
 
     @property
@@ -48,6 +51,30 @@ class SearchResult:
     @property
     def n_hits(self):
         return len(self.hits["hit_qid"]) if self.hits else 0
+
+
+class _QuerySketches:
+    """Sequence of (mins, abunds) per query over the concatenated arrays; a batch of 10 000 queries should not
+    pay for 10 000 slice pairs it may never look at."""
+
+    def __init__(self, sig_ptr, mins, abunds):
+        self._p, self._m, self._a = sig_ptr, mins, abunds
+
+    def __len__(self):
+        return len(self._p) - 1
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[j] for j in range(*i.indices(len(self)))]
+        if i < 0:
+            i += len(self)
+        if not 0 <= i < len(self):
+            raise IndexError(i)
+        a, b = int(self._p[i]), int(self._p[i + 1])
+        return self._m[a:b], self._a[a:b]
+
+    def __iter__(self):
+        return (self[i] for i in range(len(self)))
 
 
 class _Block:
@@ -85,9 +112,8 @@ def _collect(r, want_hits, owner=None):
     hits = {n: get(getattr(r, n), nh, dt) for n, dt in HIT_COLUMNS.items()} if want_hits else None
     sig_ptr = _np(r.q_sig_ptr, nq + 1, np.uint64)
     E = int(sig_ptr[-1]) if nq else 0
-    qm, qa = _np(r.q_mins, E, np.uint64), _np(r.q_abunds, E, np.uint64)
-    qs = [(qm[int(sig_ptr[i]):int(sig_ptr[i + 1])], qa[int(sig_ptr[i]):int(sig_ptr[i + 1])]) for i in range(nq)]
-    return SearchResult(pairs, hits, qs, r.ms_device, block)
+    qm, qa = get(r.q_mins, E, np.uint64), get(r.q_abunds, E, np.uint64)  # malloc'ed by the library, freed with the block
+    return SearchResult(pairs, hits, _QuerySketches(sig_ptr, qm, qa), r.ms_device, block)
 
 
 def search(index: ProteomeIndex, queries: Proteome, hits=True) -> SearchResult:
