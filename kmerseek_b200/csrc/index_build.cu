@@ -137,63 +137,60 @@ __device__ __forceinline__ void bucket_empty(uint32_t b, const CsrOut& f) {
     }
 }
 
-// SPLIT: the hashes are written back in a second pass, after the aggregate is published (part of the wait for the
-// predecessors hides behind those stores); !SPLIT: one pass writes both columns.
-template <bool SPLIT>
-__device__ __forceinline__ void bucket_finish(const uint64_t* items, uint32_t m, uint32_t s, uint32_t b, int lz, int tb,
-                                              const uint64_t* __restrict__ in_loc, uint64_t* __restrict__ out_hash,
-                                              uint64_t* __restrict__ out_loc, uint64_t* __restrict__ counts,
-                                              uint32_t* __restrict__ t_size, const CsrOut& f) {
-    __shared__ uint32_t s_cw[8 * LS_WARPS];  // per (chunk, warp): key heads | group heads << 16, then their prefix
+// The loc gathers of a thread are issued back to back; the protein ids are parked in shared memory (`spid`, 4 bytes per
+// tuple of scratch), so a head test reads two neighbouring slots.  No sorted hash column on the fused path: the CSR
+// arrays carry the hashes (keys) and nothing on the hot path reads hash[i] of the sorted tuples (expand_sorted_hash
+// rebuilds the column for the export calls).
+__device__ __forceinline__ void bucket_finish(const uint64_t* items, uint32_t* spid, uint32_t m, uint32_t s, uint32_t b,
+                                                  int lz, int tb, const uint64_t* __restrict__ in_loc,
+                                                  uint64_t* __restrict__ out_hash, uint64_t* __restrict__ out_loc,
+                                                  uint64_t* __restrict__ counts, uint32_t* __restrict__ t_size,
+                                                  const CsrOut& f) {
+    __shared__ uint32_t s_cw[8 * LS_WARPS];  // per (row, warp): key heads | group heads << 16, then their prefix
     __shared__ uint64_t s_base;
     __shared__ uint32_t s_tk;  // unique keys of this bucket
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t lt = (1u << lane) - 1u;
     const uint64_t top = tb ? ((uint64_t)b << (64 - tb)) : 0ull;
-    const uint32_t n_chunks = (m + LS_THREADS - 1) / LS_THREADS;
     const bool fused = f.oversize[0] == 0;
-    uint32_t flags = 0;  // 2 bits per chunk: this thread's element is a key head / a group head
-    // pass A: head flags and their counts (shared memory + the loc gather only)
-    for (uint32_t c = 0; c < n_chunks; c++) {
-        const uint32_t j = c * LS_THREADS + tid;
-        bool hk = false, hg = false;
-        uint64_t item = 0, loc = 0;
-        if (j < m) {
-            item = items[j];
-            loc = in_loc[s + (uint32_t)(item & 0xfffu)];  // the bucket's own 23 KB window (L1/L2)
-        }
-        const uint32_t pid = (uint32_t)(loc >> 32);
-        // the predecessor sits in the lane below; lane 0 looks it up
-        uint64_t prev = __shfl_up_sync(0xffffffffu, item, 1);
-        uint32_t ppid = __shfl_up_sync(0xffffffffu, pid, 1);
-        if (j < m) {
-            if (j == 0) {
-                hk = hg = true;  // a bucket's first tuple differs from everything before it in its top bits
-            } else {
-                if (lane == 0) { prev = items[j - 1]; ppid = (uint32_t)(in_loc[s + (uint32_t)(prev & 0xfffu)] >> 32); }
-                hk = ((prev ^ item) >> 12) != 0;
-                hg = hk || ppid != pid;
+    uint64_t loc[8];
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        const uint32_t j = r * LS_THREADS + tid;
+        if (j < m) loc[r] = in_loc[s + (uint32_t)(items[j] & 0xfffu)];  // the bucket's own window of the input (L1/L2)
+    }
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        const uint32_t j = r * LS_THREADS + tid;
+        if (j < m) spid[j] = (uint32_t)(loc[r] >> 32);
+    }
+    __syncthreads();
+    uint32_t flags = 0;  // 2 bits per row: this thread's element is a key head / a group head
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        const uint32_t j = r * LS_THREADS + tid;
+        if (r * LS_THREADS < m) {  // uniform
+            bool hk = false, hg = false;
+            if (j < m) {
+                const uint32_t pid = (uint32_t)(loc[r] >> 32);
+                hk = j == 0 || ((items[j - 1] ^ items[j]) >> 12) != 0;
+                hg = hk || spid[j - 1] != pid;
+                if (!hg) atomicSub(&t_size[pid], 1u);
             }
-            out_loc[s + j] = loc;
-            if (!hg) atomicSub(&t_size[pid], 1u);
-            if (!SPLIT) out_hash[s + j] = (top | ((item & ~0xfffull) >> tb)) >> lz;
+            flags |= ((hk ? 1u : 0u) | (hg ? 2u : 0u)) << (2 * r);
+            const uint32_t ck = __popc(__ballot_sync(0xffffffffu, hk)), cg = __popc(__ballot_sync(0xffffffffu, hg));
+            if (lane == 0) s_cw[r * LS_WARPS + warp] = ck | (cg << 16);
+        } else if (lane == 0) {
+            s_cw[r * LS_WARPS + warp] = 0;
         }
-        flags |= ((hk ? 1u : 0u) | (hg ? 2u : 0u)) << (2 * c);
-        const uint32_t ck = __popc(__ballot_sync(0xffffffffu, hk)), cg = __popc(__ballot_sync(0xffffffffu, hg));
-        if (lane == 0) s_cw[c * LS_WARPS + warp] = ck | (cg << 16);
     }
     __syncthreads();
     uint64_t agg = 0;
     if (warp == 0) {
-        // exclusive prefix over the (chunk, warp) counts, 4 entries per lane; both halves stay below 2^16
-        const uint32_t n_ent = n_chunks * LS_WARPS;
+        // exclusive prefix over the (row, warp) counts, 4 entries per lane; both halves stay below 2^16
         uint32_t v[4], local = 0;
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const uint32_t e = lane * 4 + i;
-            v[i] = e < n_ent ? s_cw[e] : 0u;
-            local += v[i];
-        }
+        for (int i = 0; i < 4; i++) { v[i] = s_cw[lane * 4 + i]; local += v[i]; }
         uint32_t incl = local;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -202,21 +199,21 @@ __device__ __forceinline__ void bucket_finish(const uint64_t* items, uint32_t m,
         }
         uint32_t run = incl - local;
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const uint32_t e = lane * 4 + i;
-            if (e < n_ent) s_cw[e] = run;
-            run += v[i];
-        }
+        for (int i = 0; i < 4; i++) { s_cw[lane * 4 + i] = run; run += v[i]; }
         const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
         const uint32_t tk = tot & 0xffffu, tg = tot >> 16;
         if (lane == 0) { counts[b] = (uint64_t)tk | ((uint64_t)tg << 32); s_tk = tk; }
         agg = (uint64_t)tk | ((uint64_t)tg << 31);
-        if (fused) scan_publish(f.status, b, agg);  // successors can go on; our own prefix is collected after pass B
+        if (fused) scan_publish(f.status, b, agg);  // successors can go on; our own prefix is collected after the stores
     }
-    // pass B: the tuples go back to HBM in final order (this is where the wait for the predecessors is hidden)
-    for (uint32_t c = 0; SPLIT && c < n_chunks; c++) {
-        const uint32_t j = c * LS_THREADS + tid;
-        if (j < m) out_hash[s + j] = (top | ((items[j] & ~0xfffull) >> tb)) >> lz;  // rebuilt from the item alone
+    // the tuples go back to HBM in final order (this is where part of the wait for the predecessors is hidden)
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        const uint32_t j = r * LS_THREADS + tid;
+        if (j < m) {
+            out_loc[s + j] = loc[r];
+            if (!fused) out_hash[s + j] = (top | ((items[j] & ~0xfffull) >> tb)) >> lz;  // the fallback passes read it
+        }
     }
     if (warp == 0) {
         uint64_t excl = ~0ull;
@@ -229,24 +226,27 @@ __device__ __forceinline__ void bucket_finish(const uint64_t* items, uint32_t m,
     __syncthreads();
     if (s_base == ~0ull) return;  // an oversize bucket exists: the CSR is written by csr_write_kernel after the fallback
     const uint32_t base_k = (uint32_t)(s_base & 0x7fffffffu), base_g = (uint32_t)(s_base >> 31);
-    for (uint32_t c = 0; c < n_chunks; c++) {
-        const uint32_t j = c * LS_THREADS + tid;
-        const bool hk = (flags >> (2 * c)) & 1u, hg = (flags >> (2 * c)) & 2u;
-        const uint32_t bk = __ballot_sync(0xffffffffu, hk), bg = __ballot_sync(0xffffffffu, hg);
-        const uint32_t pre = s_cw[c * LS_WARPS + warp];
-        const uint32_t g = base_g + (pre >> 16) + __popc(bg & lt);
-        if (hg) f.grp_start[g] = s + j;
-        if (hk) {
-            const uint32_t u = base_k + (pre & 0xffffu) + __popc(bk & lt);
-            const uint64_t full = top | ((items[j] & ~0xfffull) >> tb);
-            f.keys[u] = full >> lz;
-            f.key_grp[u] = g;
-            if (f.dir_sub >= 0)
-                dir_fill(f, j ? (int64_t)((top | ((items[j - 1] & ~0xfffull) >> tb)) >> (64 - f.dir_bits)) : ((int64_t)b << f.dir_sub) - 1,
-                         (int64_t)(full >> (64 - f.dir_bits)), u);
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        if (r * LS_THREADS < m) {  // uniform
+            const uint32_t j = r * LS_THREADS + tid;
+            const bool hk = (flags >> (2 * r)) & 1u, hg = (flags >> (2 * r)) & 2u;
+            const uint32_t bk = __ballot_sync(0xffffffffu, hk), bg = __ballot_sync(0xffffffffu, hg);
+            const uint32_t pre = s_cw[r * LS_WARPS + warp];
+            const uint32_t g = base_g + (pre >> 16) + __popc(bg & lt);
+            if (hg) f.grp_start[g] = s + j;
+            if (hk) {
+                const uint32_t u = base_k + (pre & 0xffffu) + __popc(bk & lt);
+                const uint64_t full = top | ((items[j] & ~0xfffull) >> tb);
+                f.keys[u] = full >> lz;
+                f.key_grp[u] = g;
+                if (f.dir_sub >= 0)
+                    dir_fill(f, j ? (int64_t)((top | ((items[j - 1] & ~0xfffull) >> tb)) >> (64 - f.dir_bits)) : ((int64_t)b << f.dir_sub) - 1,
+                             (int64_t)(full >> (64 - f.dir_bits)), u);
+            }
+            if (j == m - 1 && f.dir_sub >= 0)
+                dir_tail(f, b, (int64_t)((top | ((items[j] & ~0xfffull) >> tb)) >> (64 - f.dir_bits)), base_k + s_tk);
         }
-        if (j == m - 1 && f.dir_sub >= 0)
-            dir_tail(f, b, (int64_t)((top | ((items[j] & ~0xfffull) >> tb)) >> (64 - f.dir_bits)), base_k + s_tk);
     }
 }
 
@@ -258,7 +258,7 @@ __device__ __forceinline__ void bucket_finish(const uint64_t* items, uint32_t m,
 // ---------------------------------------------------------------------------------------------
 constexpr size_t LS_SMEM_REP = (size_t)LS_CAP * 8 * 2 + LS_WARPS * 256 * 2 + 256 * 4 + 64;  // 73 KB: 3 CTAs per SM
 
-__global__ void __launch_bounds__(LS_THREADS)
+__global__ void __launch_bounds__(LS_THREADS, 3)
 bucket_sort_rep_kernel(const uint64_t* __restrict__ in_hash, const uint64_t* __restrict__ in_loc,
                    uint64_t* __restrict__ out_hash, uint64_t* __restrict__ out_loc,
                    const uint32_t* __restrict__ start, int lz, int tb, uint64_t* __restrict__ counts,
@@ -464,122 +464,10 @@ bucket_sort_rep_kernel(const uint64_t* __restrict__ in_hash, const uint64_t* __r
         __syncthreads();
     }
 
-    bucket_finish<true>(src, m, s, b, lz, tb, in_loc, out_hash, out_loc, counts, t_size, f);
+    // src == A: the other item buffer is free and parks the protein ids of the tail
+    bucket_finish(src, reinterpret_cast<uint32_t*>(dst), m, s, b, lz, tb, in_loc, out_hash, out_loc, counts, t_size, f);
 }
 
-
-// Tail of the bin variant: like bucket_finish, with the loc gathers of a thread issued back to back, the protein ids
-// parked in shared memory (so a head test reads two neighbouring slots instead of shuffling and re-gathering), and no
-// sorted hash column: on the fused path the CSR arrays carry the hashes (keys) and nothing on the hot path reads
-// hash[i] of the sorted tuples (expand_sorted_hash rebuilds the column for the export calls).
-__device__ __forceinline__ void bucket_finish_bin(const uint64_t* items, uint32_t* spid, uint32_t m, uint32_t s, uint32_t b,
-                                                  int lz, int tb, const uint64_t* __restrict__ in_loc,
-                                                  uint64_t* __restrict__ out_hash, uint64_t* __restrict__ out_loc,
-                                                  uint64_t* __restrict__ counts, uint32_t* __restrict__ t_size,
-                                                  const CsrOut& f) {
-    __shared__ uint32_t s_cw[8 * LS_WARPS];  // per (row, warp): key heads | group heads << 16, then their prefix
-    __shared__ uint64_t s_base;
-    __shared__ uint32_t s_tk;  // unique keys of this bucket
-    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t lt = (1u << lane) - 1u;
-    const uint64_t top = tb ? ((uint64_t)b << (64 - tb)) : 0ull;
-    const bool fused = f.oversize[0] == 0;
-    uint64_t loc[8];
-#pragma unroll
-    for (int r = 0; r < 8; r++) {
-        const uint32_t j = r * LS_THREADS + tid;
-        if (j < m) loc[r] = in_loc[s + (uint32_t)(items[j] & 0xfffu)];  // the bucket's own window of the input (L1/L2)
-    }
-#pragma unroll
-    for (int r = 0; r < 8; r++) {
-        const uint32_t j = r * LS_THREADS + tid;
-        if (j < m) spid[j] = (uint32_t)(loc[r] >> 32);
-    }
-    __syncthreads();
-    uint32_t flags = 0;  // 2 bits per row: this thread's element is a key head / a group head
-#pragma unroll
-    for (int r = 0; r < 8; r++) {
-        const uint32_t j = r * LS_THREADS + tid;
-        if (r * LS_THREADS < m) {  // uniform
-            bool hk = false, hg = false;
-            if (j < m) {
-                const uint32_t pid = (uint32_t)(loc[r] >> 32);
-                hk = j == 0 || ((items[j - 1] ^ items[j]) >> 12) != 0;
-                hg = hk || spid[j - 1] != pid;
-                if (!hg) atomicSub(&t_size[pid], 1u);
-            }
-            flags |= ((hk ? 1u : 0u) | (hg ? 2u : 0u)) << (2 * r);
-            const uint32_t ck = __popc(__ballot_sync(0xffffffffu, hk)), cg = __popc(__ballot_sync(0xffffffffu, hg));
-            if (lane == 0) s_cw[r * LS_WARPS + warp] = ck | (cg << 16);
-        } else if (lane == 0) {
-            s_cw[r * LS_WARPS + warp] = 0;
-        }
-    }
-    __syncthreads();
-    uint64_t agg = 0;
-    if (warp == 0) {
-        // exclusive prefix over the (row, warp) counts, 4 entries per lane; both halves stay below 2^16
-        uint32_t v[4], local = 0;
-#pragma unroll
-        for (int i = 0; i < 4; i++) { v[i] = s_cw[lane * 4 + i]; local += v[i]; }
-        uint32_t incl = local;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-            if ((int)lane >= o) incl += t;
-        }
-        uint32_t run = incl - local;
-#pragma unroll
-        for (int i = 0; i < 4; i++) { s_cw[lane * 4 + i] = run; run += v[i]; }
-        const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
-        const uint32_t tk = tot & 0xffffu, tg = tot >> 16;
-        if (lane == 0) { counts[b] = (uint64_t)tk | ((uint64_t)tg << 32); s_tk = tk; }
-        agg = (uint64_t)tk | ((uint64_t)tg << 31);
-        if (fused) scan_publish(f.status, b, agg);  // successors can go on; our own prefix is collected after the stores
-    }
-    // the tuples go back to HBM in final order (this is where part of the wait for the predecessors is hidden)
-#pragma unroll
-    for (int r = 0; r < 8; r++) {
-        const uint32_t j = r * LS_THREADS + tid;
-        if (j < m) {
-            out_loc[s + j] = loc[r];
-            if (!fused) out_hash[s + j] = (top | ((items[j] & ~0xfffull) >> tb)) >> lz;  // the fallback passes read it
-        }
-    }
-    if (warp == 0) {
-        uint64_t excl = ~0ull;
-        if (fused) {
-            excl = scan_collect(f.status, b, agg);
-            if (b == f.nb - 1 && lane == 0) csr_totals(f, excl + agg);
-        }
-        if (lane == 0) s_base = excl;
-    }
-    __syncthreads();
-    if (s_base == ~0ull) return;  // an oversize bucket exists: the CSR is written by csr_write_kernel after the fallback
-    const uint32_t base_k = (uint32_t)(s_base & 0x7fffffffu), base_g = (uint32_t)(s_base >> 31);
-#pragma unroll
-    for (int r = 0; r < 8; r++) {
-        if (r * LS_THREADS < m) {  // uniform
-            const uint32_t j = r * LS_THREADS + tid;
-            const bool hk = (flags >> (2 * r)) & 1u, hg = (flags >> (2 * r)) & 2u;
-            const uint32_t bk = __ballot_sync(0xffffffffu, hk), bg = __ballot_sync(0xffffffffu, hg);
-            const uint32_t pre = s_cw[r * LS_WARPS + warp];
-            const uint32_t g = base_g + (pre >> 16) + __popc(bg & lt);
-            if (hg) f.grp_start[g] = s + j;
-            if (hk) {
-                const uint32_t u = base_k + (pre & 0xffffu) + __popc(bk & lt);
-                const uint64_t full = top | ((items[j] & ~0xfffull) >> tb);
-                f.keys[u] = full >> lz;
-                f.key_grp[u] = g;
-                if (f.dir_sub >= 0)
-                    dir_fill(f, j ? (int64_t)((top | ((items[j - 1] & ~0xfffull) >> tb)) >> (64 - f.dir_bits)) : ((int64_t)b << f.dir_sub) - 1,
-                             (int64_t)(full >> (64 - f.dir_bits)), u);
-            }
-            if (j == m - 1 && f.dir_sub >= 0)
-                dir_tail(f, b, (int64_t)((top | ((items[j] & ~0xfffull) >> tb)) >> (64 - f.dir_bits)), base_k + s_tk);
-        }
-    }
-}
 
 // ---------------------------------------------------------------------------------------------
 // Bucket-local sort, bin variant (the default): ONE unstable counting pass over the next 12 key bits with
@@ -692,7 +580,7 @@ bucket_sort_bin_kernel(const uint64_t* __restrict__ in_hash, const uint64_t* __r
         } while (again);
     }
 
-    bucket_finish_bin(B, cnt, m, s, b, lz, tb, in_loc, out_hash, out_loc, counts, t_size, f);
+    bucket_finish(B, cnt, m, s, b, lz, tb, in_loc, out_hash, out_loc, counts, t_size, f);
 }
 
 // Counts for ranges the bucket sort did not handle: oversize buckets (only_oversize = 1), or every range on the
@@ -1040,7 +928,7 @@ cudaError_t build_index(const BuildArgs& a, cudaStream_t stream, int* out_in_a, 
         fl = dl;
         if (a.ev_sorted) KS_TRY(cudaEventRecord(a.ev_sorted, stream));
         if (n_over == 0) {  // the bucket sort wrote keys / key_grp / grp_start itself: only the directory is left
-            if (bin && a.hash_written) *a.hash_written = 0;  // ... and the bin variant skipped the sorted hash column
+            if (a.hash_written) *a.hash_written = 0;  // ... and skipped the sorted hash column
             if (f.dir_sub < 0) {                             // ... and, normally, its part of the directory
                 dir_kernel<<<148 * 8, 256, 0, stream>>>(a.keys, a.d_counts, a.dir, a.dir_bits, a.dir_shift);
                 *csr_launches += 1;
