@@ -157,11 +157,13 @@ __device__ __forceinline__ void bucket_finish(const uint64_t* items, uint32_t* s
 #pragma unroll
     for (int r = 0; r < 8; r++) {
         const uint32_t j = r * LS_THREADS + tid;
+        if (r * LS_THREADS >= m) break;  // uniform
         if (j < m) loc[r] = in_loc[s + (uint32_t)(items[j] & 0xfffu)];  // the bucket's own window of the input (L1/L2)
     }
 #pragma unroll
     for (int r = 0; r < 8; r++) {
         const uint32_t j = r * LS_THREADS + tid;
+        if (r * LS_THREADS >= m) break;  // uniform
         if (j < m) spid[j] = (uint32_t)(loc[r] >> 32);
     }
     __syncthreads();
@@ -210,6 +212,7 @@ __device__ __forceinline__ void bucket_finish(const uint64_t* items, uint32_t* s
 #pragma unroll
     for (int r = 0; r < 8; r++) {
         const uint32_t j = r * LS_THREADS + tid;
+        if (r * LS_THREADS >= m) break;  // uniform
         if (j < m) {
             out_loc[s + j] = loc[r];
             if (!fused) out_hash[s + j] = (top | ((items[j] & ~0xfffull) >> tb)) >> lz;  // the fallback passes read it
@@ -519,11 +522,13 @@ bucket_sort_bin_kernel(const uint64_t* __restrict__ in_hash, const uint64_t* __r
 #pragma unroll
     for (int r = 0; r < 8; r++) {
         const uint32_t j = r * LS_THREADS + tid;
+        if (r * LS_THREADS >= m) break;  // uniform
         if (j < m) item[r] = ((in_hash[s + j] << sh) & ~0xfffull) | j;
     }
 #pragma unroll
     for (int r = 0; r < 8; r++) {
         const uint32_t j = r * LS_THREADS + tid;
+        if (r * LS_THREADS >= m) break;  // uniform
         if (j < m) slot[r >> 1] |= atomicAdd(&cnt[(uint32_t)(item[r] >> (64 - BN_BITS))], 1u) << (16 * (r & 1));
         if (STEPPED && (r + 1) * LS_THREADS < m) __syncthreads();  // uniform
     }
@@ -554,6 +559,7 @@ bucket_sort_bin_kernel(const uint64_t* __restrict__ in_hash, const uint64_t* __r
 #pragma unroll
     for (int r = 0; r < 8; r++) {
         const uint32_t j = r * LS_THREADS + tid;
+        if (r * LS_THREADS >= m) break;  // uniform
         if (j < m) B[cnt[(uint32_t)(item[r] >> (64 - BN_BITS))] + ((slot[r >> 1] >> (16 * (r & 1))) & 0xffffu)] = item[r];
     }
     __syncthreads();

@@ -491,11 +491,13 @@ sketch_quad_kernel(SketchArgs a, Lut256 lut, uint32_t* __restrict__ ticket, uint
         x[NW] = 0;
         uint64_t h[4], loc[4];
         bool keep[4];
+        // a quad that lies inside one protein with all four windows complete (9 in 10) skips the per-window walk
+        const bool inside = q * 4 + 3 + K <= pend_rel;  // the lane's protein state only moves forward: q * 4 is in p
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             const uint32_t w = q * 4 + j;
-            bool valid = false;
-            if (w < nres_rel) {
+            bool valid = inside;
+            if (!inside && w < nres_rel) {
                 while (w >= pend_rel) { p++; pstart_lo = (uint32_t)offs[p]; pend_rel = rel(offs[p + 1]); }
                 valid = w + K <= pend_rel;
             }
@@ -559,11 +561,26 @@ sketch_quad_kernel(SketchArgs a, Lut256 lut, uint32_t* __restrict__ ticket, uint
         base = s_base + wprefix;
     }
     const uint32_t sbase = warp * (SK_TILE / (SK_THREADS / 32));
-    for (uint32_t i = lane; i < wcount; i += 32) {
-        if (base + i < a.capacity) {
-            const uint32_t ad = stage_addr(sbase + i);
-            a.out_hash[base + i] = s_hash[ad];
-            a.out_loc[base + i] = s_loc[ad];
+    if (base + wcount <= a.capacity) {  // the usual case: the warp's 256 slots, 8 per lane, no per-element bound check
+        uint64_t* oh = a.out_hash + base;
+        uint64_t* ol = a.out_loc + base;
+#pragma unroll
+        for (uint32_t i0 = 0; i0 < SK_TILE / (SK_THREADS / 32); i0 += 32) {
+            const uint32_t i = i0 + lane;
+            if (i0 >= wcount) break;  // uniform
+            if (i < wcount) {
+                const uint32_t ad = stage_addr(sbase + i);
+                oh[i] = s_hash[ad];
+                ol[i] = s_loc[ad];
+            }
+        }
+    } else {
+        for (uint32_t i = lane; i < wcount; i += 32) {
+            if (base + i < a.capacity) {
+                const uint32_t ad = stage_addr(sbase + i);
+                a.out_hash[base + i] = s_hash[ad];
+                a.out_loc[base + i] = s_loc[ad];
+            }
         }
     }
 }
