@@ -34,9 +34,10 @@ constexpr int LS_CAP = 4096;  // tuples per bucket that fit the shared-memory la
 
 __global__ void protein_abund_kernel(const uint64_t* __restrict__ loc, uint64_t n, uint32_t n_prot,
                                      uint32_t* __restrict__ t_abund, uint32_t* __restrict__ t_size) {
-    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= n_prot) return;
-    // tuples are ordered by (protein, pos): count = lower_bound((p+1)<<32) - lower_bound(p<<32)
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31;
+    // tuples are ordered by (protein, pos): count = lower_bound((p+1)<<32) - lower_bound(p<<32); a lane takes its
+    // upper bound from the lane above (the last lane of a warp searches twice)
     auto lb = [&](uint64_t key) {
         uint64_t lo = 0, hi = n;
         while (lo < hi) {
@@ -45,7 +46,11 @@ __global__ void protein_abund_kernel(const uint64_t* __restrict__ loc, uint64_t 
         }
         return lo;
     };
-    const uint32_t c = (uint32_t)(lb(((uint64_t)p + 1) << 32) - lb((uint64_t)p << 32));
+    const uint64_t mine = p <= n_prot ? lb((uint64_t)p << 32) : n;
+    uint64_t next = __shfl_down_sync(0xffffffffu, mine, 1);
+    if (lane == 31 && p < n_prot) next = lb(((uint64_t)p + 1) << 32);
+    if (p >= n_prot) return;
+    const uint32_t c = (uint32_t)(next - mine);
     t_abund[p] = c;
     t_size[p] = c;  // repeats of a (hash, protein) pair are subtracted while the groups are counted
 }

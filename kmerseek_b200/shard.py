@@ -212,3 +212,38 @@ def search_and_gather(index, queries, pid_base=0, hits=False):
     finally:
         if out is not None:
             L.ks_search_result_free(out)
+
+
+def merge_combined_sketch(mins, abunds, device=None):
+    """Union of the shards' combined sketches with abundances summed (combined_minhash of the whole proteome,
+    src/rust/index.rs:824-827): all_gather of the sizes, one padded gather of (hash, count) to
+    rank 0, then sort + segmented sum there.  `mins` / `abunds`: this shard's sorted unique hashes and their counts
+    (uint64).  Returns (mins, abunds) on rank 0, None elsewhere.  Not on the search path: the per-shard indexes never
+    need it."""
+    import torch
+    dist = _dist()
+    mins = np.ascontiguousarray(mins, dtype=np.uint64)
+    abunds = np.ascontiguousarray(abunds, dtype=np.uint64)
+    if dist is None or dist.get_world_size() == 1:
+        return mins, abunds
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    block = torch.from_numpy(np.stack([mins, abunds]).view(np.int64)).to(device)
+    gathered, counts = gather_blocks({"c": block}, len(mins))
+    if dist.get_rank() != 0:
+        return None
+    g = gathered["c"]
+    # uint64 order through int64 tensors: flip the sign bit, sort, flip back
+    flipped = g[0] ^ torch.iinfo(torch.int64).min
+    order = torch.argsort(flipped, stable=True)
+    keys, inverse = torch.unique_consecutive(flipped[order], return_inverse=True)
+    sums = torch.zeros(keys.shape[0], dtype=torch.int64, device=g.device).index_add_(0, inverse, g[1][order])
+    keys = keys ^ torch.iinfo(torch.int64).min
+    return _to_host(keys).view(np.uint64).copy(), _to_host(sums).view(np.uint64).copy()
+
+
+def combined_minhash(index):
+    """(mins, abunds) of the combined sketch over all shards, on rank 0 (`index` is this rank's shard)."""
+    mins, abunds = index.get_combined_minhash()
+    return merge_combined_sketch(mins, abunds)
+

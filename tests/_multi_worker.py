@@ -31,6 +31,7 @@ def main():
     idx.finalize()
     out = shard.search_and_gather(idx, K.Proteome.from_packed(qres, qoffs), pid_base=bounds[rank], hits=True)
     ok = True
+    combined = shard.combined_minhash(idx)  # union of the shards' combined sketches (NCCL gather + merge on rank 0)
     if rank == 0:
         from oracle import oracle as O
         th, tpid, tpos = O.sketch_tuples(res, offs, k, moltype, scaled)
@@ -49,6 +50,8 @@ def main():
         mine = list(zip(h["hit_qid"].tolist(), h["hit_pid"].tolist(), h["hit_hash"].tolist(), h["hit_qpos"].tolist(),
                         h["hit_tpos"].tolist()))
         ok &= mine == ohits and len(mine) > 0
+        fmins, fab = np.unique(th, return_counts=True)
+        ok &= np.array_equal(combined[0], fmins) and np.array_equal(combined[1], fab.astype(np.uint64))
         print(f"multi-gpu check: world={world} pairs={len(rows)} hits={len(ohits)} ok={bool(ok)}", flush=True)
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, 0)

@@ -90,7 +90,20 @@ def _worker(rank, world, port, q):
             mine = list(zip(mh["hit_qid"].tolist(), mh["hit_pid"].tolist(), mh["hit_hash"].tolist(),
                             mh["hit_qpos"].tolist(), mh["hit_tpos"].tolist()))
             ok &= mine == full_hits and len(mine) > 0
+        # combined sketch of the whole proteome = union of the shards' combined sketches, abundances summed
+        # (src/rust/index.rs:824-827); hashes above 2^63 must keep their unsigned order through the int64 tensors
+        sh, spid, spos = O.sketch_tuples(sres, soffs, k, moltype, scaled)
+        smins, sab = np.unique(sh, return_counts=True)
+        merged_c = shard.merge_combined_sketch(smins, sab.astype(np.uint64))
+        if rank == 0:
+            fh, _, _ = O.sketch_tuples(res, offs, k, moltype, scaled)
+            fmins, fab = np.unique(fh, return_counts=True)
+            ok &= bool((fmins >> np.uint64(63)).any()) and np.array_equal(merged_c[0], fmins)
+            ok &= np.array_equal(merged_c[1], fab.astype(np.uint64))
             q.put(bool(ok))
+        else:
+            ok_none = merged_c is None
+            assert ok_none
     finally:
         dist.destroy_process_group()
 
