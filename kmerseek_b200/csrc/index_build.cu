@@ -495,6 +495,8 @@ constexpr int BN_PER_THREAD = BN_BINS / LS_THREADS;  // 8 consecutive bins per t
 constexpr size_t BN_SMEM = (size_t)LS_CAP * 8 + (size_t)BN_BINS * 4;  // 48 KB
 static_assert(BN_PER_THREAD == 8, "two 16-byte loads per thread in the scan");
 
+// 3 CTAs per SM: measured against 2 (2.14 ms on the 100 M-residue target run) and 4 (1.85 ms; the loc gather loses its
+// L1 lines to the larger shared-memory carve-out) -- 1.73 ms
 template <bool STEPPED>
 __global__ void __launch_bounds__(LS_THREADS, 3)
 bucket_sort_bin_kernel(const uint64_t* __restrict__ in_hash, const uint64_t* __restrict__ in_loc,
