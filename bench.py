@@ -88,8 +88,8 @@ class ClockSampler:
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures of the C2
 # workload (profiles/r01_*): only meaningful for that workload, null otherwise.
-TRAFFIC = {  # bytes per launch, C2 workload, profiles/r01_c_ncu_full_raw_c2.csv
-    "bucket_sort_kernel (+ fused CSR write)": 2_991_602_000 + 3_886_829_000,
+TRAFFIC = {  # bytes per launch, C2 workload, profiles/r01_d_ncu_full_raw_c2.csv
+    "bucket_sort_rep_kernel (+ fused CSR write, directory)": None,
     "sketch_quad_kernel": 205_893_000 + 2_934_864_000,
 }
 
@@ -256,7 +256,7 @@ def main():
         qres, qoffs = shard.broadcast_queries(qres, qoffs)
     queries = K.Proteome.from_packed(qres, qoffs)
     q_residues = queries.n_residues
-    search_ms = []
+    search_ms, lib_ms = [], []
     n_pairs_total = n_hits_total = 0
     for i in range(W + args.steps):
         barrier()
@@ -277,6 +277,8 @@ def main():
             search_ms.append((ms, wall))
         if rank == 0:
             n_pairs_total = gathered["n_pairs"]
+            if world == 1 and i >= W:
+                lib_ms.append(float(gathered["result"].ms_device))
     s_ms = float(np.mean([x[1] for x in search_ms]))  # wall: includes the H2D of the queries, NCCL gather and D2H
     search_value = q_residues * (world * n_res) / (s_ms * 1e-3)
 
@@ -289,13 +291,16 @@ def main():
     peak, peak_src = peaks()
     n_groups = st["n_groups"]
     ms = {k: float(np.mean(v)) for k, v in stage_ms.items()}
+    alphabet = {"protein": 20.0, "dayhoff": 6.0, "hp": 2.0}[cfg["moltype"]]
+    repeat_heavy = n_tuples > 0.25 * alphabet ** cfg["k"] / cfg["scaled"]  # the library's choice of bucket-sort variant
+    bucket_name = ("bucket_sort_rep_kernel" if repeat_heavy else "bucket_sort_bin_kernel") + " (+ fused CSR write, directory)"
     alg = {
         # BASELINE.md section 3; per launch = per step (every stage runs once per step)
         "sketch_quad_kernel": ("sketch", n_res + (n_prot + 1) * 8 + n_tuples * 16),
         "partition (2 library onesweep passes)": ("partition", n_tuples * 16 * 2),          # one read + one write
-        # one read + one write of every tuple, plus the CSR arrays the kernel emits (keys, key_grp, grp_start)
-        "bucket_sort_kernel (+ fused CSR write)": ("bucket", n_tuples * 16 * 2 + n_groups * 4 + n_unique * 12),
-        "dir_kernel": ("csr", n_unique * 8 + (st["n_tuples"] // 4) * 4),
+        # one read of every tuple, one write of its payload (loc), plus the CSR arrays the kernel emits (keys, key_grp,
+        # grp_start) and the bucket directory (about one entry per 4 tuples)
+        bucket_name: ("bucket", n_tuples * 16 + n_tuples * 8 + n_groups * 4 + n_unique * 12 + (n_tuples // 4) * 4),
     }
     stages = {name: {"ms": ms[key], "algorithmic_bytes": int(b), "achieved_gbs": b / ms[key] / 1e6 if ms[key] > 0 else 0.0}
               for name, (key, b) in alg.items()}
@@ -338,6 +343,8 @@ def main():
         "cpu_baseline": cpu,
         "search": {"metric": "query x proteome residues/s searched", "value": search_value, "unit": "residue pairs/s",
                    "ms_per_batch_wall": s_ms, "ms_per_batch_device": float(np.mean([x[0] for x in search_ms])),
+                   "ms_per_batch_kernels": float(np.mean(lib_ms)) if lib_ms else None,  # the library's own events: query
+                                                                                       # sketch .. scores, no copies
                    "queries": args.queries, "query_residues": int(q_residues), "pairs": int(n_pairs_total),
                    "includes": "query H2D, sketch, lookup, aggregation, scores, NCCL gather to rank 0, D2H"},
         "clocks": clocks,

@@ -415,12 +415,12 @@ void sketch_resident(ks_index* x) {
 
 // upload + sketch with the residues streamed in: the offsets go first (everything the tile -> protein map and
 // the exact tile bases need), then the residues in chunks on the copy stream; the fused kernel runs over the
-// tile range of a chunk as soon as that chunk has landed.  Exact path only (scaled == 1): tile bases are known
-// before any hash.  Returns false when the batch does not qualify (caller takes upload + sketch_resident).
+// tile range of a chunk as soon as that chunk has landed.  On the exact path (scaled == 1) tile bases are known
+// before any hash; on the look-back path (scaled > 1) tiles are taken by ticket, which simply continues across the
+// chunk launches.  Returns false when the batch does not qualify (caller takes upload + sketch_resident).
 bool add_proteome_pipelined(ks_index* x, const ks_proteome* p) {
     constexpr int CHUNKS = 8;
-    if (x->max_hash != ~0ull || x->params.ksize > (uint32_t)SK_MAX_TEMPLATE_K || getenv("KS_SKETCH_GENERAL") ||
-        getenv("KS_NO_PIPELINE"))  // test hooks
+    if (x->params.ksize > (uint32_t)SK_MAX_TEMPLATE_K || getenv("KS_NO_PIPELINE"))  // (test hook)
         return false;
     if (p->n_res < (64u << 20) || p->n_prot == 0) return false;  // small batches: one copy, one launch
     if (x->finalized) fail(KS_ERR_VALIDATION, "Validation error: index is finalized; ks_index_clear before adding more");
@@ -444,7 +444,7 @@ bool add_proteome_pipelined(ks_index* x, const ks_proteome* p) {
     b.n_prot = p->n_prot; b.n_res = p->n_res;
     b.n_windows = count_windows(p->offsets, p->n_prot, x->params.ksize);
     b.valid = true;
-    grow_tuples(x, x->n_tuples + b.n_windows);
+    grow_tuples(x, x->n_tuples + expected_kept(x, b.n_windows));
     ensure_ws(x, sketch_workspace_bytes(b.n_res));
     KS_CUDA(cudaEventRecord(x->ev[EV_UP0], x->stream));
     KS_CUDA(cudaEventRecord(x->ev[EV_SK0], x->stream));
@@ -456,7 +456,8 @@ bool add_proteome_pipelined(ks_index* x, const ks_proteome* p) {
     a.residues = b.res; a.packed = packed ? 1 : 0; a.offsets = b.offs; a.n_res = b.n_res; a.n_prot = b.n_prot;
     a.k = x->params.ksize; a.moltype = x->params.moltype; a.max_hash = x->max_hash; a.pid_base = (uint32_t)x->n_prot;
     a.out_hash = x->d_hash + x->n_tuples; a.out_loc = x->d_loc + x->n_tuples; a.capacity = x->cap - x->n_tuples;
-    a.d_count = x->d_count; a.workspace = x->ws; a.force_general = 0;
+    a.d_count = x->d_count; a.workspace = x->ws;
+    a.force_general = getenv("KS_SKETCH_GENERAL") ? 1 : 0;  // test hook: the look-back path at scaled == 1
     KS_CUDA(launch_sketch_prepare(a, x->stream, &x->l_sketch));
     const uint64_t nt = (b.n_res + SK_TILE - 1) / SK_TILE;
     const uint64_t per = (nt + CHUNKS - 1) / CHUNKS;
@@ -478,7 +479,9 @@ bool add_proteome_pipelined(ks_index* x, const ks_proteome* p) {
     KS_CUDA(cudaEventRecord(x->ev[EV_SK1], x->stream));
     KS_CUDA(cudaStreamSynchronize(x->stream));
     x->t_upload = x->t_sketch = true;
-    if ((r[1] >> 32) != 0) {  // a zero hash: redo the batch (now resident) on the look-back path
+    // a zero hash on the exact path, or more tuples than the estimate for scaled > 1 allowed for: redo the batch (now
+    // resident) through the plain path, which takes the look-back kernel / grows the buffer as needed
+    if ((r[1] >> 32) != 0 || r[0] > x->cap - x->n_tuples) {
         sketch_resident(x);
         return true;
     }

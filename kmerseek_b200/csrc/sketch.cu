@@ -587,7 +587,8 @@ sketch_quad_kernel(SketchArgs a, Lut256 lut, uint32_t* __restrict__ ticket, uint
 
 template <int K>
 cudaError_t launch_k(const SketchArgs& a, const Lut256& lut, const Workspace& w, uint64_t n_tiles, cudaStream_t st) {
-    const bool ranged = a.tile_end > a.tile_begin;  // exact path only: a sub-range of the tiles
+    const bool ranged = a.tile_end > a.tile_begin;  // a sub-range of the tiles (the look-back path takes them by ticket:
+                                                    // ranges must be launched in order, each exactly once)
     const unsigned grid = ranged ? (unsigned)(a.tile_end - a.tile_begin) : (unsigned)n_tiles;
     if constexpr (K == 0) {
         if (a.moltype == 0)

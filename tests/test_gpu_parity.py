@@ -435,9 +435,11 @@ def test_cli_search_and_index_against_goldens(K, golden_search, golden_sigs, tmp
     assert r.returncode != 0 and "required" in r.stderr  # test_cli.rs:135
 
 
-def test_pipelined_upload_matches_single_copy(K, monkeypatch):
-    """Batches above 64 MB stream the residues in chunks while earlier tiles are hashed (ks_index_add_proteome);
-    the index must be identical to the one built from a single copy + single launch."""
+@pytest.mark.parametrize("k,moltype,scaled", [(16, "dayhoff", 1), (7, "protein", 10)])
+def test_pipelined_upload_matches_single_copy(K, monkeypatch, k, moltype, scaled):
+    """Batches above 64 MB stream the residues in chunks while earlier tiles are hashed (ks_index_add_proteome), on
+    the exact path (scaled == 1) and on the look-back path (scaled > 1, tiles taken by ticket across the chunk
+    launches); the index must be identical to the one built from a single copy + single launch."""
     from kmerseek_b200 import synth
     res, offs = synth.proteome(80_000_000, 31337)
     prot = K.Proteome.from_packed(res, offs)
@@ -446,11 +448,14 @@ def test_pipelined_upload_matches_single_copy(K, monkeypatch):
     for no_pipe in (False, True):
         if no_pipe:
             monkeypatch.setenv("KS_NO_PIPELINE", "1")
-        with K.ProteomeIndex("db", 16, 1, "dayhoff") as idx:
+        with K.ProteomeIndex("db", k, scaled, moltype) as idx:
             idx.add_proteome(prot)
             idx.finalize()
             st = idx.stats()
-            assert st["n_tuples"] == int(np.maximum(lens - 15, 0).sum())
+            if scaled == 1:
+                assert st["n_tuples"] == int(np.maximum(lens - (k - 1), 0).sum())
+            else:
+                assert 0.09 < st["n_tuples"] / float(np.maximum(lens - (k - 1), 0).sum()) < 0.11
             out.append(idx.csr())
     for a, b in zip(*out):
         assert np.array_equal(a, b)
