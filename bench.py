@@ -89,7 +89,7 @@ class ClockSampler:
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures of the C2
 # workload (profiles/r01_*): only meaningful for that workload, null otherwise.
 TRAFFIC = {  # bytes per launch, C2 workload, profiles/r01_d_ncu_full_raw_c2.csv
-    "bucket_sort_rep_kernel (+ fused CSR write, directory)": None,
+    "bucket_sort_rep_kernel (+ fused CSR write, directory)": 2_991_587_000 + 2_473_064_000,
     "sketch_quad_kernel": 205_893_000 + 2_934_864_000,
 }
 
