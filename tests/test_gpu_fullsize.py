@@ -1,0 +1,100 @@
+"""BASELINE.json's full-size configurations on one B200, checked through size-independent properties (the oracle
+takes minutes at these sizes): the sort is a permutation of the sketch output, rows are ordered, counts add up, and
+planted queries find the protein they were cut from.  C2: 570 k proteins / 200 M residues, hp k=24 scaled=1 (index
+build); C3 on one GPU: 10 000 planted domains against the same proteome, dayhoff k=16."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def K():
+    import kmerseek_b200
+    return kmerseek_b200
+
+
+@pytest.fixture(scope="module")
+def proteome():
+    from kmerseek_b200 import synth
+    return synth.proteome(200_000_000, 20260102)
+
+
+def _check_index(K, res, offs, k, moltype, expect_max_unique=None):
+    prot = K.Proteome.from_packed(res, offs)
+    lens = np.diff(offs.astype(np.int64))
+    windows = np.maximum(lens - (k - 1), 0)
+    with K.ProteomeIndex("full", k, 1, moltype) as idx:
+        idx.add_proteome(prot)
+        idx.finalize()
+        st = idx.stats()
+        n = int(windows.sum())
+        assert st["n_tuples"] == n  # scaled == 1: every complete window is kept
+        keys, row_ptr, pid, pos = idx.csr()
+        U = len(keys)
+        assert U == st["n_unique_hashes"] and (expect_max_unique is None or U <= expect_max_unique)
+        assert np.all(keys[1:] > keys[:-1])                      # combined sketch: strictly increasing
+        assert row_ptr[0] == 0 and row_ptr[-1] == n and np.all(row_ptr[1:] > row_ptr[:-1])  # no empty row
+        # the postings are a permutation of all windows: every (protein, position) exactly once ...
+        g = offs[:-1].astype(np.int64)[pid] + pos.astype(np.int64)   # global residue index of the window start
+        assert np.all(pos.astype(np.int64) < windows[pid])
+        seen = np.zeros(len(res), dtype=np.uint8)
+        seen[g] = 1
+        assert int(seen.sum()) == n
+        # ... and inside a row they are ordered by (protein, position)
+        loc = (pid.astype(np.uint64) << np.uint64(32)) | pos.astype(np.uint64)
+        inner = np.ones(n, dtype=bool)
+        inner[row_ptr[:-1].astype(np.int64)] = False               # first posting of every row
+        assert np.all(loc[1:][inner[1:]] > loc[:-1][inner[1:]])
+        # per-protein sketch sizes: distinct hashes per protein add up to the (hash, protein) groups
+        grp_head = ~inner
+        grp_head[1:] |= pid[1:] != pid[:-1]
+        assert int(grp_head.sum()) == st["n_groups"]
+        return idx, st
+
+
+def test_c2_index_build_properties(K, proteome):
+    res, offs = proteome
+    _check_index(K, res, offs, 24, "hp", expect_max_unique=1 << 24)
+
+
+def test_c3_planted_queries_find_their_source(K, proteome):
+    from kmerseek_b200 import synth
+    res, offs = proteome
+    k, moltype = 16, "dayhoff"
+    prot = K.Proteome.from_packed(res, offs)
+    qres, qoffs, src = synth.queries(res, offs, 10_000, 79)
+    queries = K.Proteome.from_packed(qres, qoffs)
+    with K.ProteomeIndex("full", k, 1, moltype) as idx:
+        idx.add_proteome(prot)
+        idx.finalize()
+        r = K.search(idx, queries, hits=True)
+        p, h = r.pairs, r.hits
+        # ordered by (query, target); every pair has a positive overlap that fits both sketches
+        key = (p["pair_qid"].astype(np.uint64) << np.uint64(32)) | p["pair_pid"].astype(np.uint64)
+        assert np.all(key[1:] > key[:-1])
+        assert np.all(p["intersect_hashes"] > 0)
+        assert np.all(p["intersect_hashes"] <= p["q_size"]) and np.all(p["intersect_hashes"] <= p["t_size"])
+        np.testing.assert_allclose(p["containment"], p["intersect_hashes"] / p["q_size"], rtol=1e-12)
+        np.testing.assert_allclose(p["jaccard"], p["intersect_hashes"] /
+                                   (p["q_size"].astype(np.float64) + p["t_size"] - p["intersect_hashes"]), rtol=1e-12)
+        # a query with an unmutated 16-mer must hit the protein it was cut from; with 10 % substitutions and
+        # 50-300 residues nearly all have one (the few that do not may legitimately have no pair)
+        found = set(zip(p["pair_qid"].tolist(), p["pair_pid"].tolist()))
+        n_found = sum((q, int(s)) in found for q, s in enumerate(src))
+        assert n_found >= 0.9 * len(src)
+        # hit list: ordered by (query, qpos, target, tpos); every hit belongs to a scored pair; hits per pair >= overlap
+        hk1 = (h["hit_qid"].astype(np.uint64) << np.uint64(32)) | h["hit_qpos"].astype(np.uint64)
+        hk2 = (h["hit_pid"].astype(np.uint64) << np.uint64(32)) | h["hit_tpos"].astype(np.uint64)
+        assert np.all((hk1[1:] > hk1[:-1]) | ((hk1[1:] == hk1[:-1]) & (hk2[1:] > hk2[:-1])))
+        hp = np.unique((h["hit_qid"].astype(np.uint64) << np.uint64(32)) | h["hit_pid"].astype(np.uint64))
+        assert np.array_equal(hp, key)
+        assert len(h["hit_qid"]) >= int(p["intersect_hashes"].sum())
+        # a hit is a real shared window: same translated 16-mer in query and target
+        from kmerseek_b200.index import translate
+        rng = np.random.default_rng(5)
+        for i in rng.integers(0, len(h["hit_qid"]), size=200):
+            q, t = int(h["hit_qid"][i]), int(h["hit_pid"][i])
+            a, b = int(qoffs[q]) + int(h["hit_qpos"][i]), int(offs[t]) + int(h["hit_tpos"][i])
+            qs, ts = qres[a:a + k].tobytes().decode(), res[b:b + k].tobytes().decode()
+            assert translate(qs, moltype) == translate(ts, moltype)
