@@ -10,6 +10,7 @@
 #include <new>
 #include <time.h>
 
+#include "dense.cuh"
 #include "host_util.hpp"
 #include "index_build.cuh"
 #include "search.cuh"
@@ -241,6 +242,7 @@ struct DeviceBatch {  // residues + offsets resident in HBM
     uint64_t* offs = nullptr;
     uint64_t res_cap = 0, offs_cap = 0;
     uint64_t n_prot = 0, n_res = 0, n_windows = 0;
+    uint64_t max_len = 0;  // longest protein of the batch
     bool valid = false;
     bool packed = false;  // res holds 5-bit codes
 };
@@ -260,6 +262,12 @@ struct Buf {
         return (T*)p;
     }
 };
+
+uint64_t max_protein_len(const uint64_t* offs, uint64_t n_prot) {
+    uint64_t m = 0;
+    for (uint64_t i = 0; i < n_prot; i++) m = std::max(m, offs[i + 1] - offs[i]);
+    return m;
+}
 
 uint64_t count_windows(const uint64_t* offs, uint64_t n_prot, uint32_t k) {
     uint64_t w = 0;
@@ -294,6 +302,14 @@ struct ks_index {
     // csr
     bool finalized = false;
     bool hash_col_valid = true;  // false: d_hash of the sorted tuples is rebuilt on demand (ks_index_export)
+    // dense k-mer space path (hp, 8 <= k <= 24, scaled == 1): per-handle rank tables; a batch that qualifies is not
+    // sketched when it is added but built as a whole by finalize (pending_dense)
+    int dense_state = 0;  // 0: tables not built, 1: ready, -1: unusable for this k (two patterns share a hash)
+    uint32_t* dense_rank = nullptr;
+    uint64_t* dense_hash = nullptr;
+    uint32_t* dense_flags = nullptr;  // device u32[2]: [0] table check, [1] exception seen by the rank kernel
+    Buf b_dense_rank, b_dense_hash, b_dense_flags;
+    bool pending_dense = false;
     uint64_t* keys = nullptr;
     uint32_t *key_grp = nullptr, *grp_start = nullptr, *t_size = nullptr, *t_abund = nullptr, *dir = nullptr;
     uint64_t* d_counts = nullptr;
@@ -340,6 +356,7 @@ void upload_batch(ks_index* x, DeviceBatch& b, const ks_proteome* p, bool allow_
     b.n_prot = p->n_prot;
     b.n_res = p->n_res;
     b.n_windows = count_windows(p->offsets, p->n_prot, x->params.ksize);
+    b.max_len = max_protein_len(p->offsets, p->n_prot);
     b.valid = true;
 }
 
@@ -392,7 +409,50 @@ uint64_t run_sketch(ks_index* x, const DeviceBatch& b, uint32_t pid_base, uint64
     return r[0];
 }
 
+int bits_for_value(uint64_t v) {  // bits needed to hold values 0 .. v
+    int b = 1;
+    while (b < 64 && (v >> b)) b++;
+    return b;
+}
+
+// Dense k-mer space path (sketch_dense_kernel): the batch must be the index's only content, its k-mer space small and
+// well covered (otherwise the tables cost more than they save), and rank | protein | position must fit 64 bits.
+// KS_DENSE=0 switches the path off, KS_DENSE=1 drops the coverage condition (test hooks).
+bool dense_eligible(const ks_index* x, const DeviceBatch& b, uint64_t n_prot_before, uint64_t n_tuples_before) {
+    const char* env = getenv("KS_DENSE");
+    if (env && env[0] == '0') return false;
+    const uint32_t k = x->params.ksize;
+    if (x->params.moltype != KS_HP || k < (uint32_t)DENSE_MIN_K || k > (uint32_t)DENSE_MAX_K || x->max_hash != ~0ull) return false;
+    if (x->dense_state < 0 || n_prot_before || n_tuples_before || b.n_prot == 0 || b.n_res >= (1ull << 32)) return false;
+    if (!(env && env[0] == '1') && b.n_windows < (1ull << k) / 4) return false;
+    return (int)k + bits_for_value(b.n_prot - 1) + bits_for_value(b.max_len) <= 64;
+}
+
+void sketch_resident_general(ks_index* x);
+
+// A batch deferred to finalize (dense path) is sketched the general way after all: something else is about to touch
+// the tuples or the resident batch.
+void materialize_pending(ks_index* x) {
+    if (!x->pending_dense) return;
+    x->pending_dense = false;
+    x->n_tuples = x->n_prot = x->n_res = x->n_windows = 0;
+    sketch_resident_general(x);
+}
+
 void sketch_resident(ks_index* x) {
+    DeviceBatch& b = x->batch;
+    if (!b.valid) fail(KS_ERR_VALIDATION, "Validation error: no batch is resident (call ks_index_upload first)");
+    if (x->finalized) fail(KS_ERR_VALIDATION, "Validation error: index is finalized; ks_index_clear before adding more");
+    materialize_pending(x);  // the resident batch was already added once and is being added again
+    if (dense_eligible(x, b, x->n_prot, x->n_tuples)) {
+        x->pending_dense = true;  // finalize builds the index from the resident residues in one go
+        x->n_tuples = b.n_windows; x->n_prot = b.n_prot; x->n_res = b.n_res; x->n_windows = b.n_windows;
+        return;
+    }
+    sketch_resident_general(x);
+}
+
+void sketch_resident_general(ks_index* x) {
     DeviceBatch& b = x->batch;
     if (!b.valid) fail(KS_ERR_VALIDATION, "Validation error: no batch is resident (call ks_index_upload first)");
     if (x->n_prot + b.n_prot >= 0xffffffffull) fail(KS_ERR_CAPACITY, "more than 2^32-2 proteins on one shard");
@@ -424,6 +484,14 @@ bool add_proteome_pipelined(ks_index* x, const ks_proteome* p) {
         return false;
     if (p->n_res < (64u << 20) || p->n_prot == 0) return false;  // small batches: one copy, one launch
     if (x->finalized) fail(KS_ERR_VALIDATION, "Validation error: index is finalized; ks_index_clear before adding more");
+    materialize_pending(x);
+    {   // a batch for the dense path is uploaded whole and built by finalize
+        DeviceBatch probe;
+        probe.n_prot = p->n_prot; probe.n_res = p->n_res;
+        probe.n_windows = count_windows(p->offsets, p->n_prot, x->params.ksize);
+        probe.max_len = max_protein_len(p->offsets, p->n_prot);
+        if (dense_eligible(x, probe, x->n_prot, x->n_tuples)) return false;
+    }
     if (p->n_prot >= 0xffffffffull || x->n_prot + p->n_prot >= 0xffffffffull) fail(KS_ERR_CAPACITY, "more than 2^32-2 proteins on one shard");
     DeviceBatch& b = x->batch;
     const bool packed = p->packed != nullptr;  // 5 bits per residue over PCIe instead of 8
@@ -443,6 +511,7 @@ bool add_proteome_pipelined(ks_index* x, const ks_proteome* p) {
     b.packed = packed;
     b.n_prot = p->n_prot; b.n_res = p->n_res;
     b.n_windows = count_windows(p->offsets, p->n_prot, x->params.ksize);
+    b.max_len = max_protein_len(p->offsets, p->n_prot);
     b.valid = true;
     grow_tuples(x, x->n_tuples + expected_kept(x, b.n_windows));
     ensure_ws(x, sketch_workspace_bytes(b.n_res));
@@ -482,7 +551,7 @@ bool add_proteome_pipelined(ks_index* x, const ks_proteome* p) {
     // a zero hash on the exact path, or more tuples than the estimate for scaled > 1 allowed for: redo the batch (now
     // resident) through the plain path, which takes the look-back kernel / grows the buffer as needed
     if ((r[1] >> 32) != 0 || r[0] > x->cap - x->n_tuples) {
-        sketch_resident(x);
+        sketch_resident_general(x);
         return true;
     }
     x->n_tuples += r[0];
@@ -498,8 +567,101 @@ static double now_ms() {
     return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
 }
 
+CsrView view_of(const ks_index* x);
+
+// Build the index of the pending batch on the dense path.  Returns false (nothing changed that matters) when the path
+// turns out not to apply: the tables are unusable for this k, or a window holds a residue of neither hp class.
+bool dense_finalize(ks_index* x) {
+    DeviceBatch& b = x->batch;
+    const uint32_t k = x->params.ksize;
+    Arena* ar = x->arena;
+    x->dense_flags = x->b_dense_flags.ensure<uint32_t>(ar, 2);
+    if (x->dense_state == 0) {
+        x->dense_rank = x->b_dense_rank.ensure<uint32_t>(ar, (size_t)1 << k);
+        x->dense_hash = x->b_dense_hash.ensure<uint64_t>(ar, (size_t)1 << k);
+        const size_t tb = dense_table_temp_bytes(k);
+        void* tmp = x->b_temp.ensure<char>(ar, tb);
+        KS_CUDA(dense_build_tables(k, x->dense_rank, x->dense_hash, tmp, tb, x->dense_flags, x->stream, &x->l_sketch));
+        uint32_t bad = 0;
+        KS_CUDA(cudaMemcpyAsync(&bad, x->dense_flags, 4, cudaMemcpyDeviceToHost, x->stream));
+        KS_CUDA(cudaStreamSynchronize(x->stream));
+        x->dense_state = bad ? -1 : 1;
+    }
+    if (x->dense_state < 0) return false;
+    const uint64_t n = b.n_windows;
+    if (n > MAX_TUPLES) fail(KS_ERR_CAPACITY, "more than 2^31-1 tuples on one shard: shard the proteome over more GPUs");
+    const uint32_t P = (uint32_t)b.n_prot;
+    const int pid_bits = bits_for_value(b.n_prot - 1), pos_bits = bits_for_value(b.max_len);
+    x->n_tuples = 0;    // nothing is stored yet: the buffers may be replaced without a copy
+    grow_tuples(x, n);  // d_hash: the keys as the rank kernel emits them; d_loc: the postings
+    x->n_tuples = n;
+    uint64_t* keys_b = x->b_alt_hash.ensure<uint64_t>(ar, n);
+    // 1. rank kernel over the resident batch
+    ensure_ws(x, sketch_workspace_bytes(b.n_res));
+    SketchArgs a;
+    a.residues = b.res; a.packed = b.packed ? 1 : 0; a.offsets = b.offs; a.n_res = b.n_res; a.n_prot = b.n_prot;
+    a.k = k; a.moltype = x->params.moltype; a.max_hash = x->max_hash; a.pid_base = 0;
+    a.out_hash = nullptr; a.out_loc = nullptr; a.capacity = x->cap; a.d_count = x->d_count; a.workspace = x->ws;
+    a.force_general = 0;
+    DenseSketchArgs d;
+    d.rank_of_code = x->dense_rank; d.out_keys = x->d_hash; d.pid_bits = pid_bits; d.pos_bits = pos_bits;
+    d.exception_flag = x->dense_flags + 1;
+    KS_CUDA(cudaEventRecord(x->ev[EV_SK0], x->stream));
+    KS_CUDA(cudaMemsetAsync(x->dense_flags + 1, 0, 4, x->stream));
+    KS_CUDA(launch_sketch_prepare(a, x->stream, &x->l_sketch));
+    KS_CUDA(launch_sketch_dense(a, d, x->stream, &x->l_sketch));
+    KS_CUDA(cudaEventRecord(x->ev[EV_SK1], x->stream));
+    uint32_t exc = 0;
+    uint64_t produced = 0;
+    KS_CUDA(cudaMemcpyAsync(&exc, x->dense_flags + 1, 4, cudaMemcpyDeviceToHost, x->stream));
+    KS_CUDA(cudaMemcpyAsync(&produced, x->d_count, 8, cudaMemcpyDeviceToHost, x->stream));
+    KS_CUDA(cudaStreamSynchronize(x->stream));
+    if (exc) return false;
+    if (produced != n) fail(KS_ERR_CUDA, "internal error: dense path produced an unexpected number of tuples");
+    // 2. sort + CSR
+    int bits = 8;  // directory as on the general path
+    while (bits < 24 && (4ull << bits) < n) bits++;
+    x->dir_bits = bits;
+    x->dir_shift = 64 - x->lz - bits;
+    x->t_abund = x->b_t_abund.ensure<uint32_t>(ar, P);
+    x->t_size = x->b_t_size.ensure<uint32_t>(ar, P);
+    x->keys = x->b_keys.ensure<uint64_t>(ar, n);
+    x->key_grp = x->b_key_grp.ensure<uint32_t>(ar, n + 1);
+    x->grp_start = x->b_grp_start.ensure<uint32_t>(ar, n + 1);
+    x->dir = x->b_dir.ensure<uint32_t>(ar, (1ull << bits) + 1);
+    x->d_counts = x->b_counts.ensure<uint64_t>(ar, 2);
+    DenseCsrArgs c;
+    c.keys_a = x->d_hash; c.keys_b = keys_b; c.n = n; c.n_prot = P; c.k = k;
+    c.rank_bits = (int)k; c.pid_bits = pid_bits; c.pos_bits = pos_bits;
+    c.offsets = b.offs; c.sorted_hash = x->dense_hash;
+    c.loc = x->d_loc; c.keys = x->keys; c.key_grp = x->key_grp; c.grp_start = x->grp_start;
+    c.t_size = x->t_size; c.t_abund = x->t_abund; c.d_counts = x->d_counts;
+    c.temp_bytes = dense_csr_temp_bytes(n);
+    c.temp = x->b_temp.ensure<char>(ar, c.temp_bytes);
+    c.ev_sorted = x->ev[EV_PART];
+    KS_CUDA(cudaEventRecord(x->ev[EV_SO0], x->stream));
+    KS_CUDA(dense_build_csr(c, x->stream, &x->l_sort, &x->l_csr));
+    KS_CUDA(cudaEventRecord(x->ev[EV_SO1], x->stream));
+    KS_CUDA(launch_directory(x->keys, x->d_counts, x->dir, x->dir_bits, x->dir_shift, x->stream));
+    x->l_csr += 1;
+    KS_CUDA(cudaEventRecord(x->ev[EV_CS1], x->stream));
+    x->t_sketch = x->t_sort = x->t_csr = true;
+    uint64_t cnt[2];
+    KS_CUDA(cudaMemcpyAsync(cnt, x->d_counts, 16, cudaMemcpyDeviceToHost, x->stream));
+    KS_CUDA(cudaStreamSynchronize(x->stream));
+    x->U = cnt[0]; x->G = cnt[1];
+    x->hash_col_valid = false;  // d_hash holds rank keys: the sorted hash column is rebuilt from the CSR on demand
+    x->pending_dense = false;
+    x->finalized = true;
+    return true;
+}
+
 void finalize(ks_index* x) {
     if (x->finalized) return;
+    if (x->pending_dense) {
+        if (dense_finalize(x)) return;
+        materialize_pending(x);  // not applicable after all: the general path from here on
+    }
     const bool dbg = getenv("KS_TIMING") != nullptr;
     double t0 = dbg ? now_ms() : 0;
     const uint64_t n = x->n_tuples;
@@ -705,6 +867,7 @@ ks_status ks_index_upload(ks_index* x, const ks_proteome* p) {
     return guarded([&] {
         if (!x || !p) fail(KS_ERR_VALIDATION, "Validation error: null argument");
         x->use();
+        materialize_pending(x);  // the resident batch is about to be replaced
         KS_CUDA(cudaEventRecord(x->ev[EV_UP0], x->stream));
         upload_batch(x, x->batch, p, true);
         KS_CUDA(cudaEventRecord(x->ev[EV_UP1], x->stream));
@@ -732,6 +895,7 @@ ks_status ks_index_clear(ks_index* x) {
     return guarded([&] {
         x->use();
         drop_csr(x);
+        x->pending_dense = false;
         x->n_tuples = 0; x->n_prot = 0; x->n_res = 0; x->n_windows = 0;
     });
 }
@@ -749,6 +913,7 @@ ks_status ks_index_add_tuples(ks_index* x, const uint64_t* hash, const uint32_t*
     return guarded([&] {
         if (!x || (n && (!hash || !pid || !pos))) fail(KS_ERR_VALIDATION, "Validation error: null argument");
         x->use();
+        materialize_pending(x);
         if (x->n_prot + n_proteins >= 0xffffffffull) fail(KS_ERR_CAPACITY, "more than 2^32-2 proteins on one shard");
         std::vector<uint64_t> loc(n);
         for (uint64_t i = 0; i < n; i++) {

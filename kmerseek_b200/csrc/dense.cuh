@@ -1,0 +1,38 @@
+// Dense k-mer space index build (hp alphabet, small k, scaled == 1): internal interface.  See sketch_dense_kernel
+// (sketch.cu) for the idea; this file holds the per-handle rank tables and the CSR construction from sorted keys.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ks {
+
+// Scratch the table build needs next to its outputs (hashes + codes of all 2^k patterns, twice, + library sort space).
+size_t dense_table_temp_bytes(uint32_t k);
+// rank_of_code[2^k] (u32) and sorted_hash[2^k] (u64): the patterns' MurmurHash3 values in increasing order and every
+// pattern's position in that order.  *d_bad (device u32, zeroed here) becomes non-zero when two patterns share a hash
+// or one hashes to 0 (the path must not be used then).  Enqueued on `stream`; no synchronisation.
+cudaError_t dense_build_tables(uint32_t k, uint32_t* rank_of_code, uint64_t* sorted_hash, void* temp, size_t temp_bytes,
+                               uint32_t* d_bad, cudaStream_t stream, uint64_t* n_launches);
+
+struct DenseCsrArgs {
+    uint64_t *keys_a, *keys_b;  // packed keys (rank | protein | position) in (protein, position) order in `a`; `b` scratch
+    uint64_t n;
+    uint32_t n_prot;
+    uint32_t k;
+    int rank_bits, pid_bits, pos_bits;
+    const uint64_t* offsets;      // device, n_prot + 1 (protein boundaries of the batch)
+    const uint64_t* sorted_hash;  // table
+    // outputs
+    uint64_t* loc;  // [n] postings (protein << 32 | position), ordered by (hash, protein, position)
+    uint64_t* keys;
+    uint32_t *key_grp, *grp_start, *t_size, *t_abund;
+    uint64_t* d_counts;
+    void* temp;  // dense_csr_temp_bytes(n)
+    size_t temp_bytes;
+    cudaEvent_t ev_sorted;  // recorded between the key sort and the CSR passes; may be null
+};
+size_t dense_csr_temp_bytes(uint64_t n);
+// Library sort of the keys on their rank bits (stable), then two streaming passes: heads per tile, scan, CSR write.
+cudaError_t dense_build_csr(const DenseCsrArgs& a, cudaStream_t stream, uint64_t* sort_launches, uint64_t* csr_launches);
+
+}  // namespace ks

@@ -820,6 +820,12 @@ __global__ void expand_hash_kernel(const uint64_t* __restrict__ keys, const uint
 
 }  // namespace
 
+cudaError_t launch_directory(const uint64_t* keys, const uint64_t* d_counts, uint32_t* dir, int dir_bits, int dir_shift,
+                             cudaStream_t stream) {
+    dir_kernel<<<148 * 8, 256, 0, stream>>>(keys, d_counts, dir, dir_bits, dir_shift);
+    return cudaGetLastError();
+}
+
 cudaError_t expand_sorted_hash(const CsrView& v, uint64_t* hash, cudaStream_t stream) {
     if (v.n == 0) return cudaSuccess;
     expand_hash_kernel<<<148 * 8, 256, 0, stream>>>(v.keys, v.key_grp, v.grp_start, v.d_counts, hash);

@@ -59,6 +59,10 @@ size_t build_temp_bytes(uint64_t n, int end_bit);
 cudaError_t build_index(const BuildArgs& a, cudaStream_t stream, int* out_in_a, uint64_t* sort_launches,
                         uint64_t* csr_launches);
 
+// dir[x] = index of the first key whose top dir_bits bits (of the normalised hash) are >= x; dir[2^dir_bits] = U.
+cudaError_t launch_directory(const uint64_t* keys, const uint64_t* d_counts, uint32_t* dir, int dir_bits, int dir_shift,
+                             cudaStream_t stream);
+
 // Rebuild hash[i] of the sorted tuples from keys / key_grp / grp_start (the fused bucket sort does not write the
 // column: nothing on the hot path reads it).
 cudaError_t expand_sorted_hash(const CsrView& v, uint64_t* hash, cudaStream_t stream);

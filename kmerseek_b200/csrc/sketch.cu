@@ -585,6 +585,215 @@ sketch_quad_kernel(SketchArgs a, Lut256 lut, uint32_t* __restrict__ ticket, uint
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Dense k-mer space (two-letter hp alphabet, K <= 24, scaled == 1): a window is a K-bit pattern and its hash a
+// function of the pattern, so the index is built from ranks instead of hashes.  `rank_of_code[pattern]` (a
+// per-handle table: all 2^K patterns hashed and sorted once, dense.cu) is the position of the pattern's hash among
+// all patterns' hashes; a tuple becomes ONE 64-bit key  rank | protein | position , the library sorts the keys on
+// the rank bits alone (stable, three passes of 8-byte keys for K = 24), and equal ranks ARE equal hashes: no bucket
+// sort, no second look at the hash.  This kernel is the exact-path sketch kernel with the hash replaced by a table
+// read: residues are staged and translated once per tile, turned into two bit streams (hydrophobic / neither
+// class), and a window's pattern is one funnel shift.  A complete window that holds a residue of neither class
+// (X, U, O, *) has no pattern: the kernel flags it and the host builds this batch on the general path.
+// ---------------------------------------------------------------------------------------------
+template <int K>
+__global__ void __launch_bounds__(SK_THREADS)
+sketch_dense_kernel(SketchArgs a, Lut256 lut, const uint32_t* __restrict__ tile_pid, const uint64_t* __restrict__ tile_base,
+                    DenseSketchArgs d) {
+    constexpr int RES_WORDS = (SK_TILE + K + 16 + 3) / 4;
+    constexpr int N_BITW = (SK_TILE + K - 2) / 32 + 2;  // words of the bit streams a tile's windows reach
+    __shared__ __align__(16) uint32_t s_res[RES_WORDS];
+    __shared__ __align__(16) uint64_t s_key[4 * SQ_SEG];
+    __shared__ uint32_t s_hb[N_BITW], s_eb[N_BITW];
+    __shared__ uint64_t s_offs[OFFS_CACHE];
+    __shared__ uint8_t s_lut[256];
+    __shared__ uint8_t s_lut32[32];
+    __shared__ uint32_t s_wtot[SK_THREADS / 32];
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    s_lut[tid] = lut.b[tid];
+    if (tid < 32) {
+        const uint32_t c = tid;
+        s_lut32[c] = c == 0 ? 0 : c <= 26 ? lut.b['A' + c - 1] : c == 27 ? lut.b['*'] : 0;
+    }
+    __syncthreads();
+    const uint32_t tile = blockIdx.x + a.tile_begin;
+    const uint64_t g0 = (uint64_t)tile * SK_TILE;
+    const uint64_t n_tiles = n_tiles_of(a.n_res);
+    const uint32_t p_lo = tile_pid[tile], p_hi = tile_pid[tile + 1];
+    const uint32_t n_off = p_hi - p_lo + 2;
+    const bool cached = n_off <= OFFS_CACHE;
+    if (cached)
+        for (uint32_t i = tid; i < n_off; i += SK_THREADS) s_offs[i] = a.offsets[p_lo + i];
+    if (a.packed) {
+        constexpr uint32_t n_groups = (SK_TILE + K - 1 + 7) / 8;
+        for (uint32_t grp = tid; grp < n_groups; grp += SK_THREADS) {
+            const uint64_t group = g0 / 8 + grp;
+            const uint64_t byte = group * 5;
+            uint32_t w0 = 0, w1 = 0;
+            if (group * 8 < a.n_res) {  // groups past the last residue are not backed by memory
+                const uint32_t* w = reinterpret_cast<const uint32_t*>(a.residues + (byte & ~3ull));
+                w0 = __ldg(w);
+                w1 = __ldg(w + 1);
+            }
+            const uint32_t sh8 = (uint32_t)(byte & 3) * 8;
+            const uint32_t lo = __funnelshift_r(w0, w1, sh8), hi = (w1 >> sh8) & 0xffu;  // 40 bits: lo | hi << 32
+            uint32_t o0 = 0, o1 = 0;
+#pragma unroll
+            for (int i = 0; i < 4; i++) o0 |= (uint32_t)s_lut32[(lo >> (5 * i)) & 31u] << (8 * i);
+            o1 |= (uint32_t)s_lut32[(lo >> 20) & 31u];
+            o1 |= (uint32_t)s_lut32[(lo >> 25) & 31u] << 8;
+            o1 |= (uint32_t)s_lut32[((lo >> 30) | (hi << 2)) & 31u] << 16;
+            o1 |= (uint32_t)s_lut32[(hi >> 3) & 31u] << 24;
+            s_res[2 * grp] = o0;
+            s_res[2 * grp + 1] = o1;
+        }
+    } else {
+        constexpr uint32_t n_chunks = (SK_TILE + K - 1 + 15) / 16;
+        if (tid < n_chunks) {
+            const uint64_t g = g0 + 16ull * tid;
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (g < a.n_res) v = __ldg(reinterpret_cast<const uint4*>(a.residues + g));
+            uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const uint32_t x = w[i];
+                w[i] = (uint32_t)s_lut[x & 0xff] | ((uint32_t)s_lut[(x >> 8) & 0xff] << 8) |
+                       ((uint32_t)s_lut[(x >> 16) & 0xff] << 16) | ((uint32_t)s_lut[x >> 24] << 24);
+            }
+            reinterpret_cast<uint4*>(s_res)[tid] = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+    }
+    __syncthreads();
+    // bit streams over the staged residues: bit i of word w = residue 32 w + i is hydrophobic / of neither class
+    for (uint32_t wd = tid; wd < (uint32_t)N_BITW; wd += SK_THREADS) {
+        uint32_t hb = 0, eb = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const uint32_t wi = wd * 8 + i;
+            const uint32_t x = wi < (uint32_t)RES_WORDS ? s_res[wi] : 0u;
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const uint32_t ch = (x >> (8 * c)) & 0xffu;
+                hb |= (ch == 'h' ? 1u : 0u) << (4 * i + c);
+                eb |= ((ch != 'h' && ch != 'p') ? 1u : 0u) << (4 * i + c);
+            }
+        }
+        s_hb[wd] = hb;
+        s_eb[wd] = eb;
+    }
+    __syncthreads();
+
+    const uint64_t* offs = cached ? (const uint64_t*)s_offs - p_lo : a.offsets;
+    const uint64_t left = a.n_res - g0;
+    const uint32_t nres_rel = left > 0x40000000ull ? 0x40000000u : (uint32_t)left;  // residues from the tile start on
+    auto rel = [&](uint64_t o) -> uint32_t {  // protein end, relative to the tile start, clamped
+        const uint64_t dd = o - g0;
+        return dd > 0x7fffffffull ? 0x7fffffffu : (uint32_t)dd;
+    };
+    uint32_t p = p_lo, pstart_lo = 0, pend_rel = 0;
+    const uint32_t w_first = (warp * SQ_ROWS * 32 + lane) * 4;
+    if (w_first < nres_rel) {
+        const uint64_t g = g0 + w_first;
+        uint32_t lo = p_lo, hi = p_hi;
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi + 1) >> 1;
+            if (offs[mid] <= g) lo = mid; else hi = mid - 1;
+        }
+        p = lo;
+        pstart_lo = (uint32_t)offs[p];
+        pend_rel = rel(offs[p + 1]);
+    }
+
+    constexpr uint32_t KMASK = K >= 32 ? 0xffffffffu : ((1u << (K & 31)) - 1u);
+    const uint32_t lt = (1u << lane) - 1u;
+    const uint32_t g0_lo = (uint32_t)g0;
+    const int loc_bits = d.pid_bits + d.pos_bits;
+    bool exc_seen = false;
+    uint32_t wcount = 0;  // keys staged by this warp so far (uniform across the warp)
+#pragma unroll
+    for (int rr = 0; rr < SQ_ROWS; rr++) {
+        const uint32_t q = (warp * SQ_ROWS + rr) * 32 + lane;
+        const uint32_t hlo = s_hb[q >> 3], hhi = s_hb[(q >> 3) + 1];
+        const uint32_t elo = s_eb[q >> 3], ehi = s_eb[(q >> 3) + 1];
+        const bool inside = q * 4 + 3 + K <= pend_rel;  // the lane's protein state only moves forward: q * 4 is in p
+        uint32_t code[4], rank[4];
+        uint64_t locp[4];
+        bool keep[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint32_t w = q * 4 + j;
+            bool valid = inside;
+            if (!inside && w < nres_rel) {
+                while (w >= pend_rel) { p++; pstart_lo = (uint32_t)offs[p]; pend_rel = rel(offs[p + 1]); }
+                valid = w + K <= pend_rel;
+            }
+            const uint32_t bsh = ((q & 7u) << 2) + j;  // bit offset of window w in its stream word: (4q + j) mod 32
+            code[j] = __funnelshift_r(hlo, hhi, bsh) & KMASK;
+            exc_seen |= valid && (__funnelshift_r(elo, ehi, bsh) & KMASK) != 0;
+            keep[j] = valid;
+            locp[j] = ((uint64_t)p << d.pos_bits) | (uint64_t)(g0_lo + w - pstart_lo);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) rank[j] = __ldg(d.rank_of_code + code[j]);
+        uint32_t below = 0, total = 0;
+        uint32_t bal[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            bal[j] = __ballot_sync(0xffffffffu, keep[j]);
+            below += __popc(bal[j] & lt);
+            total += __popc(bal[j]);
+        }
+        uint32_t slot = warp * (SK_TILE / (SK_THREADS / 32)) + wcount + below;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            if (keep[j]) {
+                s_key[stage_addr(slot)] = ((uint64_t)rank[j] << loc_bits) | locp[j];
+                slot++;
+            }
+        }
+        wcount += total;
+    }
+    if (exc_seen) atomicOr(d.exception_flag, 1u);
+    if (lane == 0) s_wtot[warp] = wcount;
+    __syncthreads();
+    uint32_t wprefix = 0, btotal = 0;
+#pragma unroll
+    for (int i = 0; i < SK_THREADS / 32; i++) {
+        const uint32_t t = s_wtot[i];
+        if (i < (int)warp) wprefix += t;
+        btotal += t;
+    }
+    const uint64_t base = tile_base[tile] + wprefix;
+    if (tid == 0 && tile == n_tiles - 1) *a.d_count = tile_base[tile] + btotal;
+    const uint32_t sbase = warp * (SK_TILE / (SK_THREADS / 32));
+    uint64_t* ok = d.out_keys + base;
+#pragma unroll
+    for (uint32_t i0 = 0; i0 < SK_TILE / (SK_THREADS / 32); i0 += 32) {
+        const uint32_t i = i0 + lane;
+        if (i0 >= wcount) break;  // uniform
+        if (i < wcount && base + i < a.capacity) ok[i] = s_key[stage_addr(sbase + i)];
+    }
+}
+
+template <int K>
+struct DenseDispatch {
+    static cudaError_t run(const SketchArgs& a, const Lut256& lut, const Workspace& w, unsigned grid, const DenseSketchArgs& d,
+                           cudaStream_t st) {
+        if (a.k == (uint32_t)K) {
+            sketch_dense_kernel<K><<<grid, SK_THREADS, 0, st>>>(a, lut, w.tile_pid, w.tile_base, d);
+            return cudaGetLastError();
+        }
+        return DenseDispatch<K - 1>::run(a, lut, w, grid, d, st);
+    }
+};
+template <>
+struct DenseDispatch<DENSE_MIN_K - 1> {
+    static cudaError_t run(const SketchArgs&, const Lut256&, const Workspace&, unsigned, const DenseSketchArgs&, cudaStream_t) {
+        return cudaErrorInvalidValue;
+    }
+};
+
 template <int K>
 cudaError_t launch_k(const SketchArgs& a, const Lut256& lut, const Workspace& w, uint64_t n_tiles, cudaStream_t st) {
     const bool ranged = a.tile_end > a.tile_begin;  // a sub-range of the tiles (the look-back path takes them by ticket:
@@ -729,6 +938,21 @@ cudaError_t launch_sketch(const SketchArgs& a, cudaStream_t stream, uint64_t* n_
     e = launch_sketch_tiles(a, stream, n_launches);
     if (e != cudaSuccess) return e;
     return launch_sketch_finish(a, stream);
+}
+
+// Dense path: tile -> protein map, exact tile bases (launch_sketch_prepare), then the rank kernel over all tiles (or
+// [tile_begin, tile_end) when a.tile_end > a.tile_begin).  a.out_hash / a.out_loc are not used.
+cudaError_t launch_sketch_dense(const SketchArgs& a, const DenseSketchArgs& d, cudaStream_t stream, uint64_t* n_launches) {
+    if (a.n_res == 0 || a.n_prot == 0) return cudaSuccess;
+    if (a.moltype != 2 || a.k < (uint32_t)DENSE_MIN_K || a.k > (uint32_t)DENSE_MAX_K || a.max_hash != ~0ull) return cudaErrorInvalidValue;
+    const uint64_t nt = n_tiles_of(a.n_res);
+    Workspace w = carve(a.workspace, a.n_res);
+    Lut256 lut;
+    fill_lut(a.moltype, &lut);
+    const bool ranged = a.tile_end > a.tile_begin;
+    const unsigned grid = ranged ? (unsigned)(a.tile_end - a.tile_begin) : (unsigned)nt;
+    if (n_launches) *n_launches += 1;
+    return DenseDispatch<DENSE_MAX_K>::run(a, lut, w, grid, d, stream);
 }
 
 }  // namespace ks

@@ -34,6 +34,18 @@ struct SketchArgs {
     void* workspace;           // sketch_workspace_bytes(n_res)
 };
 
+// Dense k-mer space path (hp, DENSE_MIN_K <= k <= DENSE_MAX_K, scaled == 1): see sketch_dense_kernel.
+constexpr int DENSE_MIN_K = 8;
+constexpr int DENSE_MAX_K = 24;
+struct DenseSketchArgs {
+    const uint32_t* rank_of_code;  // device, 2^k entries: rank of the pattern's hash among all patterns' hashes
+    uint64_t* out_keys;            // device, capacity entries: rank << (pid_bits + pos_bits) | protein << pos_bits | position
+    int pid_bits, pos_bits;
+    uint32_t* exception_flag;      // device: set when a complete window holds a residue of neither class
+};
+// launch_sketch_prepare first (exact path: scaled == 1); then this instead of launch_sketch_tiles.
+cudaError_t launch_sketch_dense(const SketchArgs& a, const DenseSketchArgs& d, cudaStream_t stream, uint64_t* n_launches);
+
 size_t sketch_workspace_bytes(uint64_t n_res);
 // Enqueues memset + tile->protein map + the fused kernel on `stream`; adds the number of kernels launched.
 cudaError_t launch_sketch(const SketchArgs& a, cudaStream_t stream, uint64_t* n_launches);

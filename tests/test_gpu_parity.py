@@ -362,6 +362,80 @@ def test_bucket_sort_path_scaled(K, O):
         assert np.array_equal(pid, ops) and np.array_equal(pos, oqs)
 
 
+def _csr_equals_oracle(K, O, res, offs, k, moltype, scaled=1):
+    prot = K.Proteome.from_packed(res, offs)
+    with K.ProteomeIndex("db", k, scaled, moltype) as idx:
+        idx.add_proteome(prot)
+        idx.finalize()
+        keys, row_ptr, pid, pos = idx.csr()
+        oh, opid, opos = O.sketch_tuples(res, offs, k, moltype, scaled)
+        okeys, orow, ops, oqs = O.build_index(oh, opid, opos)
+        assert np.array_equal(keys, okeys) and np.array_equal(row_ptr, orow), (k, moltype)
+        assert np.array_equal(pid, ops) and np.array_equal(pos, oqs), (k, moltype)
+        st = idx.stats()
+        assert st["n_tuples"] == len(oh) and st["n_unique_hashes"] == len(okeys)
+        sk = idx.export_sketches()
+        osk = O.protein_sketches(oh, opid, len(offs) - 1)
+        for (m, a), (om, oa) in zip(sk, osk):
+            assert np.array_equal(m, om) and np.array_equal(a, oa)
+        return st
+
+
+def test_dense_kmer_space_path(K, O, monkeypatch):
+    """hp, 8 <= k <= 24, scaled == 1: the index is built from the ranks of the k-bit patterns (per-handle table, 8-byte
+    keys, library sort on the rank bits, no bucket sort).  Forced on for small inputs here; must equal the oracle for
+    every k, with proteins shorter than k, and fall back to the general path -- same result -- when a window holds a
+    residue of neither class (X, U, O, *) or when a second batch is added."""
+    from kmerseek_b200 import synth
+    monkeypatch.setenv("KS_DENSE", "1")
+    res, offs = synth.proteome(400_000, 606)
+    # a few degenerate proteins: empty, shorter than k, exactly k
+    extra = [b"", b"ACDEF", b"ACDEFGHIKLMNPQRSTVWYACDE", b"LLLLLLLLLLLLLLLLLLLLLLLLLLLLLLLLLLLLLLLL"]
+    eres = np.frombuffer(b"".join(extra), dtype=np.uint8)
+    eoffs = np.cumsum([0] + [len(e) for e in extra]).astype(np.uint64)
+    res2 = np.concatenate([res, eres])
+    offs2 = np.concatenate([offs, offs[-1] + eoffs[1:]])
+    for k in (8, 9, 15, 16, 17, 21, 24):
+        _csr_equals_oracle(K, O, res2, offs2, k, "hp")
+    # exceptions: X / * inside windows -> general path, same answer
+    res3 = res2.copy()
+    res3[[1000, 5000, 123456]] = [ord("X"), ord("*"), ord("U")]
+    _csr_equals_oracle(K, O, res3, offs2, 24, "hp")
+    # two batches: the first is deferred, the second forces it through the general sketch
+    half = len(offs) // 2
+    a = K.Proteome.from_packed(res[: int(offs[half])], offs[: half + 1])
+    b = K.Proteome.from_packed(res[int(offs[half]):], offs[half:] - offs[half])
+    with K.ProteomeIndex("db", 16, 1, "hp") as idx:
+        idx.add_proteome(a)
+        idx.add_proteome(b)
+        idx.finalize()
+        keys, row_ptr, pid, pos = idx.csr()
+        oh, opid, opos = O.sketch_tuples(res, offs, 16, "hp", 1)
+        okeys, orow, ops, oqs = O.build_index(oh, opid, opos)
+        assert np.array_equal(keys, okeys) and np.array_equal(row_ptr, orow)
+        assert np.array_equal(pid, ops) and np.array_equal(pos, oqs)
+    # search on a densely built index
+    qres, qoffs, _ = synth.queries(res, offs, 64, 5)
+    prot, queries = K.Proteome.from_packed(res, offs), K.Proteome.from_packed(qres, qoffs)
+    with K.ProteomeIndex("db", 16, 1, "hp") as idx:
+        idx.add_proteome(prot)
+        r = K.search(idx, queries, hits=True)
+        qh, qid, qpos = O.sketch_tuples(qres, qoffs, 16, "hp", 1)
+        oh, opid, opos = O.sketch_tuples(res, offs, 16, "hp", 1)
+        ohits = O.hits(qh, qid, qpos, oh, opid, opos)
+        h = r.hits
+        mine = list(zip(h["hit_qid"].tolist(), h["hit_pid"].tolist(), h["hit_hash"].tolist(), h["hit_qpos"].tolist(),
+                        h["hit_tpos"].tolist()))
+        assert mine == ohits and len(mine) > 0
+        rows = O.manysearch(O.protein_sketches(qh, qid, len(qoffs) - 1), O.protein_sketches(oh, opid, len(offs) - 1), 16, 1, "hp")
+        assert len(rows) == r.n_pairs
+        for j, row in enumerate(rows):
+            assert (int(r.pairs["pair_qid"][j]), int(r.pairs["pair_pid"][j])) == (row["qid"], row["pid"])
+            assert int(r.pairs["intersect_hashes"][j]) == row["intersect_hashes"]
+            assert float(r.pairs["containment"][j]) == pytest.approx(row["containment"], rel=SCORE_RTOL)
+            assert float(r.pairs["median_abund"][j]) == pytest.approx(row["median_abund"], rel=SCORE_RTOL)
+
+
 def test_general_sketch_path_at_scaled_1(K, O, monkeypatch):
     """scaled == 1 normally takes the chain-free exact path; the look-back path must give the same tuples
     (it is what a batch is redone on if a hash of exactly 0 ever shows up)."""
