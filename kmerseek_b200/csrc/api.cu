@@ -308,7 +308,7 @@ struct ks_index {
     uint32_t* dense_rank = nullptr;
     uint64_t* dense_hash = nullptr;
     uint32_t* dense_flags = nullptr;  // device u32[2]: [0] table check, [1] exception seen by the rank kernel
-    Buf b_dense_rank, b_dense_hash, b_dense_flags;
+    Buf b_dense_rank, b_dense_hash, b_dense_flags, b_dense_work;
     bool pending_dense = false;
     uint64_t* keys = nullptr;
     uint32_t *key_grp = nullptr, *grp_start = nullptr, *t_size = nullptr, *t_abund = nullptr, *dir = nullptr;
@@ -595,7 +595,18 @@ bool dense_finalize(ks_index* x) {
     x->n_tuples = 0;    // nothing is stored yet: the buffers may be replaced without a copy
     grow_tuples(x, n);  // d_hash: the keys as the rank kernel emits them; d_loc: the postings
     x->n_tuples = n;
-    uint64_t* keys_b = x->b_alt_hash.ensure<uint64_t>(ar, n);
+    // the key sort: hand-written (two scatter levels + a shared-memory sort per bucket) when the input fits its scheme,
+    // the library's otherwise (KS_DENSE_SORT=library is a test hook)
+    const char* sort_env = getenv("KS_DENSE_SORT");
+    const DenseSortPlan plan = sort_env && sort_env[0] == 'l' ? DenseSortPlan() : dense_sort_plan(n, (int)k);
+    uint64_t* keys_b = nullptr;
+    char* work = nullptr;
+    if (plan.custom) {
+        work = x->b_dense_work.ensure<char>(ar, plan.bytes);
+        KS_CUDA(cudaMemsetAsync(work + plan.off_small, 0, plan.small_bytes, x->stream));
+    } else {
+        keys_b = x->b_alt_hash.ensure<uint64_t>(ar, n);
+    }
     // 1. rank kernel over the resident batch
     ensure_ws(x, sketch_workspace_bytes(b.n_res));
     SketchArgs a;
@@ -606,6 +617,15 @@ bool dense_finalize(ks_index* x) {
     DenseSketchArgs d;
     d.rank_of_code = x->dense_rank; d.out_keys = x->d_hash; d.pid_bits = pid_bits; d.pos_bits = pos_bits;
     d.exception_flag = x->dense_flags + 1;
+    d.scatter = DenseScatter{nullptr, nullptr, 0, 0, 0, nullptr};
+    if (plan.custom) {
+        d.scatter.out = (uint64_t*)(work + plan.off_region1);
+        d.scatter.cursor = (uint32_t*)(work + plan.off_cursor1);
+        d.scatter.cap = plan.cap1;
+        d.scatter.shift = (int)k + pid_bits + pos_bits - plan.l1;
+        d.scatter.bits = plan.l1;
+        d.scatter.overflow = (uint32_t*)(work + plan.off_overflow);
+    }
     KS_CUDA(cudaEventRecord(x->ev[EV_SK0], x->stream));
     KS_CUDA(cudaMemsetAsync(x->dense_flags + 1, 0, 4, x->stream));
     KS_CUDA(launch_sketch_prepare(a, x->stream, &x->l_sketch));
@@ -631,6 +651,7 @@ bool dense_finalize(ks_index* x) {
     x->dir = x->b_dir.ensure<uint32_t>(ar, (1ull << bits) + 1);
     x->d_counts = x->b_counts.ensure<uint64_t>(ar, 2);
     DenseCsrArgs c;
+    c.plan = plan; c.work = work;
     c.keys_a = x->d_hash; c.keys_b = keys_b; c.n = n; c.n_prot = P; c.k = k;
     c.rank_bits = (int)k; c.pid_bits = pid_bits; c.pos_bits = pos_bits;
     c.offsets = b.offs; c.sorted_hash = x->dense_hash;
@@ -647,8 +668,11 @@ bool dense_finalize(ks_index* x) {
     KS_CUDA(cudaEventRecord(x->ev[EV_CS1], x->stream));
     x->t_sketch = x->t_sort = x->t_csr = true;
     uint64_t cnt[2];
+    uint32_t overflow = 0;
     KS_CUDA(cudaMemcpyAsync(cnt, x->d_counts, 16, cudaMemcpyDeviceToHost, x->stream));
+    if (plan.custom) KS_CUDA(cudaMemcpyAsync(&overflow, work + plan.off_overflow, 4, cudaMemcpyDeviceToHost, x->stream));
     KS_CUDA(cudaStreamSynchronize(x->stream));
+    if (overflow) return false;  // heavy repeats of one k-mer overflowed a sort bucket: the general path handles those
     x->U = cnt[0]; x->G = cnt[1];
     x->hash_col_valid = false;  // d_hash holds rank keys: the sorted hash column is rebuilt from the CSR on demand
     x->pending_dense = false;

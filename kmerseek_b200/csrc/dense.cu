@@ -11,6 +11,7 @@
 
 #include "common.cuh"
 #include "dense.cuh"
+#include "dense_scatter.cuh"
 
 namespace ks {
 
@@ -171,6 +172,287 @@ dense_write_kernel(const uint64_t* __restrict__ keys_in, uint64_t n, int loc_bit
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Key sort of the dense path without the library: keys are distinct and their final order is numeric, so nothing has to
+// be stable.  Level 1 (top <= 8 bits) is fused into the rank kernel; dense_partition_kernel is level 2 (next <= 8 bits);
+// dense_bucket_kernel sorts a final bucket (<= 4096 keys) in shared memory -- the bin variant of index_build.cu on whole
+// keys: one counting pass over the next 12 bits with shared-memory atomics, odd-even rounds until nothing moves -- and
+// writes the bucket's part of the postings and the CSR arrays (decoupled look-back over the buckets for the key / group
+// base, as bucket_finish does).
+// ---------------------------------------------------------------------------------------------
+__global__ void dense_chunks_kernel(const uint32_t* __restrict__ cursor1, uint32_t nb1, uint32_t cap1, uint32_t* __restrict__ chunk_pfx) {
+    __shared__ uint32_t s_w[8];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint32_t c = 0;
+    if (tid < nb1) c = (min(cursor1[tid], cap1) + DS_TILE - 1) / DS_TILE;
+    uint32_t incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((int)lane >= o) incl += v;
+    }
+    if (lane == 31) s_w[warp] = incl;
+    __syncthreads();
+    uint32_t off = 0;
+    for (uint32_t w = 0; w < warp; w++) off += s_w[w];
+    if (tid < nb1) chunk_pfx[tid] = off + incl - c;
+    if (tid == 255) chunk_pfx[nb1] = off + incl;  // nb1 <= 256
+}
+
+__global__ void __launch_bounds__(DS_THREADS)
+dense_partition_kernel(const uint64_t* __restrict__ region1, const uint32_t* __restrict__ cursor1, uint32_t cap1, uint32_t nb1,
+                       const uint32_t* __restrict__ chunk_pfx, DenseScatter sc) {
+    __shared__ DenseScatterSmem s_sc;
+    const uint32_t c = blockIdx.x;
+    if (c >= chunk_pfx[nb1]) return;
+    uint32_t lo = 0, hi = nb1 - 1;  // last bucket whose first chunk is <= c
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi + 1) >> 1;
+        if (chunk_pfx[mid] <= c) lo = mid; else hi = mid - 1;
+    }
+    const uint32_t b1 = lo;
+    const uint32_t cnt = min(cursor1[b1], cap1);
+    const uint32_t first = (c - chunk_pfx[b1]) * DS_TILE;
+    const uint64_t* src = region1 + (uint64_t)b1 * cap1 + first;
+    uint64_t key[DS_ITEMS];
+    uint32_t valid = 0;
+#pragma unroll
+    for (int it = 0; it < DS_ITEMS; it++) {
+        const uint32_t i = it * DS_THREADS + threadIdx.x;
+        key[it] = 0;
+        if (first + i < cnt) { key[it] = src[i]; valid |= 1u << it; }
+    }
+    scatter_keys(key, valid, sc, b1 << sc.bits, s_sc);
+}
+
+// tuple offset of every final bucket (exclusive scan of the clamped cursors), one CTA
+__global__ void __launch_bounds__(1024)
+dense_bucket_offsets_kernel(const uint32_t* __restrict__ cursor2, uint32_t nb, uint32_t cap, uint32_t* __restrict__ bstart) {
+    __shared__ uint32_t s_w[32];
+    __shared__ uint32_t s_carry;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < nb; base += 1024) {
+        const uint32_t i = base + tid;
+        const uint32_t v = i < nb ? min(cursor2[i], cap) : 0u;
+        uint32_t incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((int)lane >= o) incl += t;
+        }
+        if (lane == 31) s_w[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            const uint32_t w = s_w[lane];
+            uint32_t wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, wi, o);
+                if ((int)lane >= o) wi += t;
+            }
+            s_w[lane] = wi - w;
+        }
+        __syncthreads();
+        const uint32_t excl = s_carry + s_w[warp] + incl - v;
+        if (i < nb) bstart[i] = excl;
+        __syncthreads();
+        if (tid == 1023) s_carry = excl + v;
+        __syncthreads();
+    }
+    if (tid == 0) bstart[nb] = s_carry;
+}
+
+constexpr int DB_THREADS = 512;
+constexpr int DB_WARPS = DB_THREADS / 32;
+constexpr int DB_CAP = 4096;
+constexpr int DB_BINS = 4096;
+constexpr size_t DB_SMEM = (size_t)DB_CAP * 8 + (size_t)DB_BINS * 4;
+
+struct DenseBucketArgs {
+    const uint64_t* region2;   // final buckets, DB_CAP keys each
+    const uint32_t* cursor2;   // keys per bucket
+    const uint32_t* bstart;    // tuple offset of every bucket
+    uint32_t nb;
+    int rem_bits;              // key bits below the bucket bits
+    int loc_bits, pos_bits;
+    const uint64_t* sorted_hash;
+    uint64_t* status;          // look-back words, zeroed
+    uint32_t* ticket;
+    uint64_t* loc;
+    uint64_t* keys;
+    uint32_t *key_grp, *grp_start, *t_size;
+    uint64_t* d_counts;
+    uint64_t n;
+};
+
+__global__ void __launch_bounds__(DB_THREADS, 3)
+dense_bucket_kernel(DenseBucketArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t* B = reinterpret_cast<uint64_t*>(smem_raw);      // [DB_CAP] items: the key's bits below the bucket bits, left-aligned
+    uint32_t* cnt = reinterpret_cast<uint32_t*>(B + DB_CAP);  // [DB_BINS]
+    __shared__ uint32_t s_wsum[DB_WARPS];
+    __shared__ uint32_t s_cw[8 * DB_WARPS];
+    __shared__ uint64_t s_base;
+    __shared__ uint32_t s_bucket;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t lt = (1u << lane) - 1u;
+    if (tid == 0) s_bucket = atomicAdd(a.ticket, 1u);
+    reinterpret_cast<uint4*>(cnt)[tid] = make_uint4(0, 0, 0, 0);
+    reinterpret_cast<uint4*>(cnt)[tid + DB_THREADS] = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+    const uint32_t b = s_bucket;
+    const uint32_t m = min(a.cursor2[b], (uint32_t)DB_CAP);
+    if (m == 0) {  // pass the running totals on; the last bucket writes them out
+        if (warp == 0) {
+            const uint64_t excl = scan_lookback(a.status, b, 0);
+            if (b == a.nb - 1 && lane == 0) {
+                const uint64_t U = excl & 0x7fffffffu, G = excl >> 31;
+                a.d_counts[0] = U; a.d_counts[1] = G; a.key_grp[U] = (uint32_t)G; a.grp_start[G] = (uint32_t)a.n;
+            }
+        }
+        return;
+    }
+    const uint64_t* src = a.region2 + (uint64_t)b * DB_CAP;
+    const int up = 64 - a.rem_bits;  // item = key << up: the bucket bits fall off the top
+    uint64_t item[8];
+    uint32_t slot[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        const uint32_t j = r * DB_THREADS + tid;
+        if (r * DB_THREADS >= m) break;
+        if (j < m) item[r] = src[j] << up;
+    }
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        const uint32_t j = r * DB_THREADS + tid;
+        if (r * DB_THREADS >= m) break;
+        if (j < m) slot[r >> 1] |= atomicAdd(&cnt[(uint32_t)(item[r] >> 52)], 1u) << (16 * (r & 1));
+    }
+    __syncthreads();
+    {
+        uint4 c0 = reinterpret_cast<uint4*>(cnt)[2 * tid], c1 = reinterpret_cast<uint4*>(cnt)[2 * tid + 1];
+        const uint32_t total = c0.x + c0.y + c0.z + c0.w + c1.x + c1.y + c1.z + c1.w;
+        uint32_t incl = total;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((int)lane >= o) incl += v;
+        }
+        if (lane == 31) s_wsum[warp] = incl;
+        __syncthreads();
+        uint32_t off = 0;
+#pragma unroll
+        for (int w = 0; w < DB_WARPS; w++) off += w < (int)warp ? s_wsum[w] : 0u;
+        uint4 e0, e1;
+        e0.x = off + incl - total; e0.y = e0.x + c0.x; e0.z = e0.y + c0.y; e0.w = e0.z + c0.z;
+        e1.x = e0.w + c0.w; e1.y = e1.x + c1.x; e1.z = e1.y + c1.y; e1.w = e1.z + c1.z;
+        reinterpret_cast<uint4*>(cnt)[2 * tid] = e0;
+        reinterpret_cast<uint4*>(cnt)[2 * tid + 1] = e1;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        const uint32_t j = r * DB_THREADS + tid;
+        if (r * DB_THREADS >= m) break;
+        if (j < m) B[cnt[(uint32_t)(item[r] >> 52)] + ((slot[r >> 1] >> (16 * (r & 1))) & 0xffffu)] = item[r];
+    }
+    __syncthreads();
+    {   // odd-even transposition until nothing moves (a bin holds the few keys of one hash in a handful of proteins)
+        const uint32_t np0 = m >> 1, np1 = (m - 1) >> 1;
+        ulonglong2* B2 = reinterpret_cast<ulonglong2*>(B);
+        int again;
+        do {
+            int sw = 0;
+            for (uint32_t i = tid; i < np0; i += DB_THREADS) {
+                const ulonglong2 v = B2[i];
+                if (v.x > v.y) { B2[i] = make_ulonglong2(v.y, v.x); sw = 1; }
+            }
+            __syncthreads();
+            for (uint32_t i = tid; i < np1; i += DB_THREADS) {
+                const uint64_t x = B[2 * i + 1], y = B[2 * i + 2];
+                if (x > y) { B[2 * i + 1] = y; B[2 * i + 2] = x; sw = 1; }
+            }
+            again = __syncthreads_or(sw);
+        } while (again);
+    }
+    // heads: the bucket bits cover at most the rank bits, so a bucket's first key starts a new hash
+    const int rank_sh = up + a.loc_bits, grp_sh = up + a.pos_bits;  // item >> rank_sh: rank bits below the bucket bits
+    auto shr = [](uint64_t v, int sh) -> uint64_t { return sh >= 64 ? 0ull : v >> sh; };  // no rank bits may be left
+    const uint64_t pos_mask = (1ull << a.pos_bits) - 1ull, pid_mask = (1ull << (a.loc_bits - a.pos_bits)) - 1ull;
+    const uint32_t s0 = a.bstart[b];
+    uint32_t flags = 0;
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        const uint32_t j = r * DB_THREADS + tid;
+        if (r * DB_THREADS < m) {  // uniform
+            bool hk = false, hg = false;
+            if (j < m) {
+                const uint64_t it = B[j];
+                const uint64_t pv = j ? B[j - 1] : ~it;
+                hk = j == 0 || shr(it, rank_sh) != shr(pv, rank_sh);
+                hg = hk || (it >> grp_sh) != (pv >> grp_sh);
+                const uint64_t low = it >> up;  // the key's bits below the bucket bits: (rank low bits |) protein | position
+                const uint32_t pid = (uint32_t)((low >> a.pos_bits) & pid_mask);
+                a.loc[s0 + j] = ((uint64_t)pid << 32) | (low & pos_mask);
+                if (!hg) atomicSub(&a.t_size[pid], 1u);
+            }
+            flags |= ((hk ? 1u : 0u) | (hg ? 2u : 0u)) << (2 * r);
+            const uint32_t ck = __popc(__ballot_sync(0xffffffffu, hk)), cg = __popc(__ballot_sync(0xffffffffu, hg));
+            if (lane == 0) s_cw[r * DB_WARPS + warp] = ck | (cg << 16);
+        } else if (lane == 0) {
+            s_cw[r * DB_WARPS + warp] = 0;
+        }
+    }
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t v[4], local = 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++) { v[i] = s_cw[lane * 4 + i]; local += v[i]; }
+        uint32_t incl = local;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((int)lane >= o) incl += t;
+        }
+        uint32_t run = incl - local;
+#pragma unroll
+        for (int i = 0; i < 4; i++) { s_cw[lane * 4 + i] = run; run += v[i]; }
+        const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
+        const uint64_t agg = (uint64_t)(tot & 0xffffu) | ((uint64_t)(tot >> 16) << 31);
+        const uint64_t excl = scan_lookback(a.status, b, agg);
+        if (lane == 0) {
+            s_base = excl;
+            if (b == a.nb - 1) {
+                const uint64_t incl2 = excl + agg;
+                const uint64_t U = incl2 & 0x7fffffffu, G = incl2 >> 31;
+                a.d_counts[0] = U; a.d_counts[1] = G; a.key_grp[U] = (uint32_t)G; a.grp_start[G] = (uint32_t)a.n;
+            }
+        }
+    }
+    __syncthreads();
+    const uint32_t base_k = (uint32_t)(s_base & 0x7fffffffu), base_g = (uint32_t)(s_base >> 31);
+    const uint64_t rank_top = (uint64_t)b << (a.rem_bits - a.loc_bits);  // the rank bits that are the bucket index
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        if (r * DB_THREADS < m) {  // uniform
+            const uint32_t j = r * DB_THREADS + tid;
+            const bool hk = (flags >> (2 * r)) & 1u, hg = (flags >> (2 * r)) & 2u;
+            const uint32_t bk = __ballot_sync(0xffffffffu, hk), bg = __ballot_sync(0xffffffffu, hg);
+            const uint32_t pre = s_cw[r * DB_WARPS + warp];
+            const uint32_t g = base_g + (pre >> 16) + __popc(bg & lt);
+            if (hg) a.grp_start[g] = s0 + j;
+            if (hk) {
+                const uint32_t u = base_k + (pre & 0xffffu) + __popc(bk & lt);
+                const uint64_t low_rank = shr(B[j], rank_sh);
+                a.keys[u] = a.sorted_hash[rank_top | low_rank];
+                a.key_grp[u] = g;
+            }
+        }
+    }
+}
+
 size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
 
 size_t table_sort_bytes(uint32_t n) {
@@ -219,6 +501,33 @@ cudaError_t dense_build_tables(uint32_t k, uint32_t* rank_of_code, uint64_t* sor
     return cudaGetLastError();
 }
 
+DenseSortPlan dense_sort_plan(uint64_t n, int rank_bits) {
+    DenseSortPlan p;
+    int total = 0;
+    while (total <= 2 * DS_MAX_BITS && (n >> total) > 3072) total++;
+    if (total > 2 * DS_MAX_BITS || total > rank_bits || n == 0) return p;  // custom == 0
+    p.custom = 1;
+    p.total = total;
+    p.l1 = total < DS_MAX_BITS ? total : DS_MAX_BITS;
+    p.l2 = total - p.l1;
+    p.cap1 = p.l2 ? (uint32_t)((n >> p.l1) + (n >> (p.l1 + 3)) + 16384) : (uint32_t)DB_CAP;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { const size_t o = off; off += align256(bytes); return o; };
+    p.off_region1 = take(((size_t)p.cap1 << p.l1) * 8);
+    p.off_region2 = p.l2 ? take(((size_t)DB_CAP << total) * 8) : p.off_region1;
+    p.off_small = off;
+    p.off_cursor1 = take(((size_t)1 << p.l1) * 4);
+    p.off_cursor2 = p.l2 ? take(((size_t)1 << total) * 4) : p.off_cursor1;
+    p.off_status = take(((size_t)1 << total) * 8);
+    p.off_ticket = take(8);
+    p.off_overflow = take(8);
+    p.small_bytes = off - p.off_small;  // everything above is zeroed before a build
+    p.off_chunks = take(((size_t)1 << DS_MAX_BITS) * 4 + 4);
+    p.off_bstart = take((((size_t)1 << total) + 1) * 4);
+    p.bytes = off;
+    return p;
+}
+
 size_t dense_csr_temp_bytes(uint64_t n) {
     const uint64_t nt = (n + DC_TILE - 1) / DC_TILE;
     return key_sort_bytes(n) + 2 * align256((nt + 1) * 8) + scan_bytes(nt + 1) + 256;
@@ -238,6 +547,40 @@ cudaError_t dense_build_csr(const DenseCsrArgs& a, cudaStream_t stream, uint64_t
         KS_TRY(cudaMemsetAsync(a.grp_start, 0, 4, stream));
         if (a.ev_sorted) KS_TRY(cudaEventRecord(a.ev_sorted, stream));
         return cudaSuccess;
+    }
+    if (a.plan.custom) {
+        const DenseSortPlan& pl = a.plan;
+        char* w = (char*)a.work;
+        uint64_t* region1 = (uint64_t*)(w + pl.off_region1);
+        uint64_t* region2 = (uint64_t*)(w + pl.off_region2);
+        uint32_t* cursor1 = (uint32_t*)(w + pl.off_cursor1);
+        uint32_t* cursor2 = (uint32_t*)(w + pl.off_cursor2);
+        uint32_t* chunk_pfx = (uint32_t*)(w + pl.off_chunks);
+        uint32_t* bstart = (uint32_t*)(w + pl.off_bstart);
+        const uint32_t nb = 1u << pl.total;
+        const int total_bits = a.rank_bits + loc_bits;
+        if (pl.l2) {  // second level: every first-level region into 2^l2 final buckets
+            dense_chunks_kernel<<<1, 256, 0, stream>>>(cursor1, 1u << pl.l1, pl.cap1, chunk_pfx);
+            DenseScatter sc;
+            sc.out = region2; sc.cursor = cursor2; sc.cap = (uint32_t)DB_CAP; sc.shift = total_bits - pl.total; sc.bits = pl.l2;
+            sc.overflow = (uint32_t*)(w + pl.off_overflow);
+            const unsigned grid = (unsigned)(n / DS_TILE + (1u << pl.l1) + 1);  // every region's last chunk may be partial
+            dense_partition_kernel<<<grid, DS_THREADS, 0, stream>>>(region1, cursor1, pl.cap1, 1u << pl.l1, chunk_pfx, sc);
+            KS_TRY(cudaGetLastError());
+            if (sort_launches) *sort_launches += 2;
+        }
+        dense_bucket_offsets_kernel<<<1, 1024, 0, stream>>>(cursor2, nb, (uint32_t)DB_CAP, bstart);
+        if (a.ev_sorted) KS_TRY(cudaEventRecord(a.ev_sorted, stream));
+        DenseBucketArgs ba;
+        ba.region2 = region2; ba.cursor2 = cursor2; ba.bstart = bstart; ba.nb = nb;
+        ba.rem_bits = total_bits - pl.total; ba.loc_bits = loc_bits; ba.pos_bits = a.pos_bits; ba.sorted_hash = a.sorted_hash;
+        ba.status = (uint64_t*)(w + pl.off_status); ba.ticket = (uint32_t*)(w + pl.off_ticket);
+        ba.loc = a.loc; ba.keys = a.keys; ba.key_grp = a.key_grp; ba.grp_start = a.grp_start; ba.t_size = a.t_size;
+        ba.d_counts = a.d_counts; ba.n = n;
+        KS_TRY(cudaFuncSetAttribute(dense_bucket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DB_SMEM));
+        dense_bucket_kernel<<<nb, DB_THREADS, DB_SMEM, stream>>>(ba);
+        if (sort_launches) *sort_launches += 2;
+        return cudaGetLastError();
     }
     char* p = (char*)a.temp;
     size_t sort_bytes = key_sort_bytes(n);

@@ -14,8 +14,23 @@ size_t dense_table_temp_bytes(uint32_t k);
 cudaError_t dense_build_tables(uint32_t k, uint32_t* rank_of_code, uint64_t* sorted_hash, void* temp, size_t temp_bytes,
                                uint32_t* d_bad, cudaStream_t stream, uint64_t* n_launches);
 
+// Plan of the hand-written key sort (dense_scatter.cuh, dense_bucket_kernel): the top `total` = l1 + l2 key bits pick
+// one of 2^total final buckets of at most 4096 keys.  custom == 0: the input does not fit the scheme (more than
+// 2^16 x 3072 keys, or fewer rank bits than bucket bits) and the library sorts the keys.
+struct DenseSortPlan {
+    int custom = 0;
+    int l1 = 0, l2 = 0, total = 0;  // bits of the first level (fused into the rank kernel), the second, both
+    uint32_t cap1 = 0;              // keys per first-level region
+    // carve of the work buffer (bytes from its start)
+    size_t off_region1 = 0, off_region2 = 0, off_small = 0, small_bytes = 0, bytes = 0;
+    size_t off_cursor1 = 0, off_cursor2 = 0, off_chunks = 0, off_bstart = 0, off_status = 0, off_ticket = 0, off_overflow = 0;
+};
+DenseSortPlan dense_sort_plan(uint64_t n, int rank_bits);
+
 struct DenseCsrArgs {
-    uint64_t *keys_a, *keys_b;  // packed keys (rank | protein | position) in (protein, position) order in `a`; `b` scratch
+    DenseSortPlan plan;
+    void* work = nullptr;  // plan.bytes; the rank kernel has scattered the keys into its first-level regions (plan.custom)
+    uint64_t *keys_a, *keys_b;  // library sort only: packed keys in (protein, position) order in `a`; `b` scratch
     uint64_t n;
     uint32_t n_prot;
     uint32_t k;

@@ -766,6 +766,20 @@ sketch_dense_kernel(SketchArgs a, Lut256 lut, const uint32_t* __restrict__ tile_
     }
     const uint64_t base = tile_base[tile] + wprefix;
     if (tid == 0 && tile == n_tiles - 1) *a.d_count = tile_base[tile] + btotal;
+    if (d.scatter.out != nullptr) {  // first level of the key sort, straight out of shared memory
+        static_assert(DS_THREADS == SK_THREADS && DS_TILE == SK_TILE, "one scatter tile per sketch tile");
+        __shared__ DenseScatterSmem s_sc;
+        uint64_t key[DS_ITEMS];
+        uint32_t valid = 0;
+#pragma unroll
+        for (int it = 0; it < DS_ITEMS; it++) {
+            const uint32_t i = it * SK_THREADS + tid;  // slot: warp region i >> 8, offset i & 255
+            key[it] = s_key[stage_addr(i)];
+            valid |= ((i & 255u) < s_wtot[i >> 8] ? 1u : 0u) << it;
+        }
+        scatter_keys(key, valid, d.scatter, 0, s_sc);
+        return;
+    }
     const uint32_t sbase = warp * (SK_TILE / (SK_THREADS / 32));
     uint64_t* ok = d.out_keys + base;
 #pragma unroll

@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "dense_scatter.cuh"
+
 namespace ks {
 
 constexpr int SK_THREADS = 256;
@@ -42,6 +44,8 @@ struct DenseSketchArgs {
     uint64_t* out_keys;            // device, capacity entries: rank << (pid_bits + pos_bits) | protein << pos_bits | position
     int pid_bits, pos_bits;
     uint32_t* exception_flag;      // device: set when a complete window holds a residue of neither class
+    DenseScatter scatter;          // scatter.out != nullptr: the keys leave the kernel partitioned by their top bits
+                                   // (first level of the key sort, dense_scatter.cuh) instead of in tile order
 };
 // launch_sketch_prepare first (exact path: scaled == 1); then this instead of launch_sketch_tiles.
 cudaError_t launch_sketch_dense(const SketchArgs& a, const DenseSketchArgs& d, cudaStream_t stream, uint64_t* n_launches);

@@ -397,6 +397,10 @@ def test_dense_kmer_space_path(K, O, monkeypatch):
     offs2 = np.concatenate([offs, offs[-1] + eoffs[1:]])
     for k in (8, 9, 15, 16, 17, 21, 24):
         _csr_equals_oracle(K, O, res2, offs2, k, "hp")
+    monkeypatch.setenv("KS_DENSE_SORT", "library")  # the keys sorted by the library instead of the two scatter levels
+    for k in (8, 16, 24):
+        _csr_equals_oracle(K, O, res2, offs2, k, "hp")
+    monkeypatch.delenv("KS_DENSE_SORT")
     # exceptions: X / * inside windows -> general path, same answer
     res3 = res2.copy()
     res3[[1000, 5000, 123456]] = [ord("X"), ord("*"), ord("U")]
@@ -434,6 +438,20 @@ def test_dense_kmer_space_path(K, O, monkeypatch):
             assert int(r.pairs["intersect_hashes"][j]) == row["intersect_hashes"]
             assert float(r.pairs["containment"][j]) == pytest.approx(row["containment"], rel=SCORE_RTOL)
             assert float(r.pairs["median_abund"][j]) == pytest.approx(row["median_abund"], rel=SCORE_RTOL)
+
+
+def test_dense_path_two_scatter_levels(K, O):
+    """14 M residues of hp k=24 / k=16 take the dense path on their own (the k-mer space is covered) with both scatter
+    levels of the key sort (more than 2^8 x 3072 keys); a proteome with a heavily repeated k-mer overflows a sort bucket
+    and must come out of the general path with the same index."""
+    from kmerseek_b200 import synth
+    res, offs = synth.proteome(14_000_000, 515)
+    for k in (24, 16):
+        _csr_equals_oracle(K, O, res, offs, k, "hp")
+    rep = np.frombuffer(("AL" * 40_000).encode(), dtype=np.uint8)  # two patterns, ~40 000 windows each
+    res2 = np.concatenate([res, rep])
+    offs2 = np.concatenate([offs, [offs[-1] + len(rep)]]).astype(np.uint64)
+    _csr_equals_oracle(K, O, res2, offs2, 24, "hp")
 
 
 def test_general_sketch_path_at_scaled_1(K, O, monkeypatch):
