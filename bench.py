@@ -90,6 +90,7 @@ class ClockSampler:
 # workload (profiles/r01_*): only meaningful for that workload, null otherwise.
 TRAFFIC = {  # bytes per launch, C2 workload, profiles/r01_d_ncu_full_raw_c2.csv
     "bucket_sort_rep_kernel (+ fused CSR write, directory)": 2_991_587_000 + 2_473_064_000,
+    "dense_bucket_kernel (sort + CSR write)": None,
     "sketch_quad_kernel": 205_893_000 + 2_934_864_000,
 }
 
@@ -293,15 +294,28 @@ def main():
     ms = {k: float(np.mean(v)) for k, v in stage_ms.items()}
     alphabet = {"protein": 20.0, "dayhoff": 6.0, "hp": 2.0}[cfg["moltype"]]
     repeat_heavy = n_tuples > 0.25 * alphabet ** cfg["k"] / cfg["scaled"]  # the library's choice of bucket-sort variant
-    bucket_name = ("bucket_sort_rep_kernel" if repeat_heavy else "bucket_sort_bin_kernel") + " (+ fused CSR write, directory)"
-    alg = {
-        # BASELINE.md section 3; per launch = per step (every stage runs once per step)
-        "sketch_quad_kernel": ("sketch", n_res + (n_prot + 1) * 8 + n_tuples * 16),
-        "partition (2 library onesweep passes)": ("partition", n_tuples * 16 * 2),          # one read + one write
-        # one read of every tuple, one write of its payload (loc), plus the CSR arrays the kernel emits (keys, key_grp,
-        # grp_start) and the bucket directory (about one entry per 4 tuples)
-        bucket_name: ("bucket", n_tuples * 16 + n_tuples * 8 + n_groups * 4 + n_unique * 12 + (n_tuples // 4) * 4),
-    }
+    if st["build_path"] == 0:
+        bucket_name = ("bucket_sort_rep_kernel" if repeat_heavy else "bucket_sort_bin_kernel") + " (+ fused CSR write, directory)"
+        alg = {
+            # BASELINE.md section 3; per launch = per step (every stage runs once per step)
+            "sketch_quad_kernel": ("sketch", n_res + (n_prot + 1) * 8 + n_tuples * 16),
+            "partition (2 library onesweep passes)": ("partition", n_tuples * 16 * 2),          # one read + one write
+            # one read of every tuple, one write of its payload (loc), plus the CSR arrays the kernel emits (keys, key_grp,
+            # grp_start) and the bucket directory (about one entry per 4 tuples)
+            bucket_name: ("bucket", n_tuples * 16 + n_tuples * 8 + n_groups * 4 + n_unique * 12 + (n_tuples // 4) * 4),
+        }
+    else:
+        # dense k-mer space path (hp, small k): tuples are 8-byte rank keys.  The algorithmic bytes stay SURVEY 8(d)'s
+        # (16 B per tuple out of the sketch, 16 B read + 8 B payload written by the build): what the path does not
+        # move shows up as a higher achieved figure, which is the point of it.
+        alg = {
+            "sketch_dense_kernel (ranks + first scatter level)": ("sketch", n_res + (n_prot + 1) * 8 + n_tuples * 16),
+            ("dense_partition_kernel (second scatter level)" if st["build_path"] == 1 else "library key sort (3 onesweep passes)"):
+                ("partition", n_tuples * 8 * 2),
+            ("dense_bucket_kernel (sort + CSR write)" if st["build_path"] == 1 else "dense_count_kernel + dense_write_kernel"):
+                ("bucket", n_tuples * 16 + n_tuples * 8 + n_groups * 4 + n_unique * 12),
+            "dir_kernel": ("csr", n_unique * 8 + (n_tuples // 4) * 4),
+        }
     stages = {name: {"ms": ms[key], "algorithmic_bytes": int(b), "achieved_gbs": b / ms[key] / 1e6 if ms[key] > 0 else 0.0}
               for name, (key, b) in alg.items()}
     own = {k: v for k, v in stages.items() if "library" not in k}
@@ -335,6 +349,7 @@ def main():
         "config": {"workload": args.workload, "k": cfg["k"], "moltype": cfg["moltype"], "scaled": cfg["scaled"],
                    "residues_per_gpu": n_res, "proteins_per_gpu": n_prot, "tuples_per_gpu": n_tuples,
                    "unique_hashes_per_gpu": n_unique, "parallelism": f"protein-sharded x{world}",
+                   "build_path": {0: "general", 1: "dense k-mer space", 2: "dense k-mer space, library key sort"}[st["build_path"]],
                    "l2": "inputs (0.2 GB residues, 3 GB tuples) exceed the 126 MB L2; no flush needed"},
         "e2e": {"value": e2e_value, "unit": "residues/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": int((n_res + 7) // 8 * 5 + 72 + (n_prot + 1) * 8), "d2h_bytes_per_step": 8 + 16 + 136},

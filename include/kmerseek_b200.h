@@ -161,9 +161,14 @@ typedef struct ks_stats {
     uint64_t sketch_launches, sort_launches, csr_launches, search_launches; /* kernels launched so far */
     float ms_upload, ms_sketch, ms_sort, ms_csr; /* device time of the last run of each stage (CUDA events) */
     float ms_search;
-    float ms_sort_partition; /* part of ms_sort: partition by the top hash bits (library onesweep passes) */
-    float ms_sort_bucket;    /* part of ms_sort: bucket_sort_kernel (+ bucket table kernels) */
+    float ms_sort_partition; /* part of ms_sort: partition by the top hash bits (library onesweep passes); dense path: the
+                                second scatter level (or the library's key sort) */
+    float ms_sort_bucket;    /* part of ms_sort: the bucket sort kernel (+ bucket table kernels); dense path: dense_bucket_kernel
+                                (or the two streaming CSR passes) */
     uint32_t finalized;
+    uint32_t build_path;     /* how the last finalize built the index: 0 general (hash tuples, partition + bucket sort),
+                                1 dense k-mer space (hp, 8 <= k <= 24, scaled 1: rank keys), 2 the same with the keys
+                                sorted by the library */
 } ks_stats;
 /* Synchronises the handle's stream. */
 ks_status ks_index_stats(ks_index *idx, ks_stats *out);

@@ -33,7 +33,7 @@ class ks_stats(C.Structure):
         "device_bytes", "sketch_launches", "sort_launches", "csr_launches", "search_launches")] + [
         (n, C.c_float) for n in ("ms_upload", "ms_sketch", "ms_sort", "ms_csr", "ms_search", "ms_sort_partition",
                                  "ms_sort_bucket")] + [
-        ("finalized", C.c_uint32)]
+        ("finalized", C.c_uint32), ("build_path", C.c_uint32)]
 
 
 class ks_sketch(C.Structure):

@@ -9,7 +9,8 @@ CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libkmerseek_b200.so")
 SOURCES = ["api.cu", "sketch.cu", "index_build.cu", "dense.cu", "search.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+EXTRA = os.environ.get("KS_NVCC_EXTRA", "").split()  # experiments: -DKS_...=...
+FLAGS = EXTRA + ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
          "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unused-function", "--expt-relaxed-constexpr"]
 
 

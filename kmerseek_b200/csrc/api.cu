@@ -310,6 +310,10 @@ struct ks_index {
     uint32_t* dense_flags = nullptr;  // device u32[2]: [0] table check, [1] exception seen by the rank kernel
     Buf b_dense_rank, b_dense_hash, b_dense_flags, b_dense_work;
     bool pending_dense = false;
+    uint32_t build_path = 0;  // ks_stats.build_path of the last finalize
+    bool dense_sketched = false;  // pending batch: the rank kernel has already run over it (pipelined upload)
+    DenseSortPlan dense_plan;
+    int dense_pid_bits = 0, dense_pos_bits = 0;
     uint64_t* keys = nullptr;
     uint32_t *key_grp = nullptr, *grp_start = nullptr, *t_size = nullptr, *t_abund = nullptr, *dir = nullptr;
     uint64_t* d_counts = nullptr;
@@ -429,12 +433,15 @@ bool dense_eligible(const ks_index* x, const DeviceBatch& b, uint64_t n_prot_bef
 }
 
 void sketch_resident_general(ks_index* x);
+bool dense_begin(ks_index* x);
+void dense_rank_tiles(ks_index* x, uint32_t t0, uint32_t t1);
 
 // A batch deferred to finalize (dense path) is sketched the general way after all: something else is about to touch
 // the tuples or the resident batch.
 void materialize_pending(ks_index* x) {
     if (!x->pending_dense) return;
     x->pending_dense = false;
+    x->dense_sketched = false;
     x->n_tuples = x->n_prot = x->n_res = x->n_windows = 0;
     sketch_resident_general(x);
 }
@@ -485,12 +492,13 @@ bool add_proteome_pipelined(ks_index* x, const ks_proteome* p) {
     if (p->n_res < (64u << 20) || p->n_prot == 0) return false;  // small batches: one copy, one launch
     if (x->finalized) fail(KS_ERR_VALIDATION, "Validation error: index is finalized; ks_index_clear before adding more");
     materialize_pending(x);
-    {   // a batch for the dense path is uploaded whole and built by finalize
+    bool dense = false;
+    {   // a batch for the dense path: the rank kernel follows the chunks instead of the sketch kernel
         DeviceBatch probe;
         probe.n_prot = p->n_prot; probe.n_res = p->n_res;
         probe.n_windows = count_windows(p->offsets, p->n_prot, x->params.ksize);
         probe.max_len = max_protein_len(p->offsets, p->n_prot);
-        if (dense_eligible(x, probe, x->n_prot, x->n_tuples)) return false;
+        dense = dense_eligible(x, probe, x->n_prot, x->n_tuples);
     }
     if (p->n_prot >= 0xffffffffull || x->n_prot + p->n_prot >= 0xffffffffull) fail(KS_ERR_CAPACITY, "more than 2^32-2 proteins on one shard");
     DeviceBatch& b = x->batch;
@@ -513,21 +521,26 @@ bool add_proteome_pipelined(ks_index* x, const ks_proteome* p) {
     b.n_windows = count_windows(p->offsets, p->n_prot, x->params.ksize);
     b.max_len = max_protein_len(p->offsets, p->n_prot);
     b.valid = true;
-    grow_tuples(x, x->n_tuples + expected_kept(x, b.n_windows));
+    if (!dense) grow_tuples(x, x->n_tuples + expected_kept(x, b.n_windows));
     ensure_ws(x, sketch_workspace_bytes(b.n_res));
     KS_CUDA(cudaEventRecord(x->ev[EV_UP0], x->stream));
     KS_CUDA(cudaEventRecord(x->ev[EV_SK0], x->stream));
+    KS_CUDA(cudaMemcpyAsync(b.offs, p->offsets, (p->n_prot + 1) * 8, cudaMemcpyHostToDevice, x->stream));
+    if (dense && !dense_begin(x)) {  // the tables turned out unusable for this k: the general pipeline after all
+        dense = false;
+        x->n_tuples = 0;
+        grow_tuples(x, expected_kept(x, b.n_windows));
+    }
     // buffers were (re)allocated in compute-stream order: the copy stream must not run ahead of that
     KS_CUDA(cudaEventRecord(x->ev_chunk[CHUNKS], x->stream));
     KS_CUDA(cudaStreamWaitEvent(x->copy_stream, x->ev_chunk[CHUNKS], 0));
-    KS_CUDA(cudaMemcpyAsync(b.offs, p->offsets, (p->n_prot + 1) * 8, cudaMemcpyHostToDevice, x->stream));
     SketchArgs a;
     a.residues = b.res; a.packed = packed ? 1 : 0; a.offsets = b.offs; a.n_res = b.n_res; a.n_prot = b.n_prot;
     a.k = x->params.ksize; a.moltype = x->params.moltype; a.max_hash = x->max_hash; a.pid_base = (uint32_t)x->n_prot;
     a.out_hash = x->d_hash + x->n_tuples; a.out_loc = x->d_loc + x->n_tuples; a.capacity = x->cap - x->n_tuples;
     a.d_count = x->d_count; a.workspace = x->ws;
     a.force_general = getenv("KS_SKETCH_GENERAL") ? 1 : 0;  // test hook: the look-back path at scaled == 1
-    KS_CUDA(launch_sketch_prepare(a, x->stream, &x->l_sketch));
+    if (!dense) KS_CUDA(launch_sketch_prepare(a, x->stream, &x->l_sketch));  // (dense_begin has done it)
     const uint64_t nt = (b.n_res + SK_TILE - 1) / SK_TILE;
     const uint64_t per = (nt + CHUNKS - 1) / CHUNKS;
     for (int c = 0; c < CHUNKS; c++) {
@@ -539,7 +552,18 @@ bool add_proteome_pipelined(ks_index* x, const ks_proteome* p) {
         KS_CUDA(cudaEventRecord(x->ev_chunk[c], x->copy_stream));
         KS_CUDA(cudaStreamWaitEvent(x->stream, x->ev_chunk[c], 0));
         a.tile_begin = (uint32_t)t0; a.tile_end = (uint32_t)t1;
-        KS_CUDA(launch_sketch_tiles(a, x->stream, &x->l_sketch));
+        if (dense) dense_rank_tiles(x, (uint32_t)t0, (uint32_t)t1);
+        else KS_CUDA(launch_sketch_tiles(a, x->stream, &x->l_sketch));
+    }
+    if (dense) {  // finalize takes it from here (flags, second scatter level, buckets)
+        KS_CUDA(cudaEventRecord(x->ev[EV_UP1], x->stream));
+        KS_CUDA(cudaEventRecord(x->ev[EV_SK1], x->stream));
+        KS_CUDA(cudaStreamSynchronize(x->stream));
+        x->t_upload = x->t_sketch = true;
+        x->pending_dense = true;
+        x->dense_sketched = true;
+        x->n_tuples = b.n_windows; x->n_prot = b.n_prot; x->n_res = b.n_res; x->n_windows = b.n_windows;
+        return true;
     }
     KS_CUDA(launch_sketch_finish(a, x->stream));
     uint64_t r[2] = {0, 0};
@@ -569,9 +593,31 @@ static double now_ms() {
 
 CsrView view_of(const ks_index* x);
 
-// Build the index of the pending batch on the dense path.  Returns false (nothing changed that matters) when the path
-// turns out not to apply: the tables are unusable for this k, or a window holds a residue of neither hp class.
-bool dense_finalize(ks_index* x) {
+// ---- dense path (sketch_dense_kernel, dense.cu) -------------------------------------------------------------------
+void dense_kernel_args(ks_index* x, SketchArgs* a, DenseSketchArgs* d) {
+    const DeviceBatch& b = x->batch;
+    const DenseSortPlan& plan = x->dense_plan;
+    a->residues = b.res; a->packed = b.packed ? 1 : 0; a->offsets = b.offs; a->n_res = b.n_res; a->n_prot = b.n_prot;
+    a->k = x->params.ksize; a->moltype = x->params.moltype; a->max_hash = x->max_hash; a->pid_base = 0;
+    a->out_hash = nullptr; a->out_loc = nullptr; a->capacity = x->cap; a->d_count = x->d_count; a->workspace = x->ws;
+    a->force_general = 0;
+    d->rank_of_code = x->dense_rank; d->out_keys = x->d_hash; d->pid_bits = x->dense_pid_bits; d->pos_bits = x->dense_pos_bits;
+    d->exception_flag = x->dense_flags + 1;
+    d->scatter = DenseScatter{nullptr, nullptr, 0, 0, 0, nullptr};
+    if (plan.custom) {
+        char* work = (char*)x->b_dense_work.p;
+        d->scatter.out = (uint64_t*)(work + plan.off_region1);
+        d->scatter.cursor = (uint32_t*)(work + plan.off_cursor1);
+        d->scatter.cap = plan.cap1;
+        d->scatter.shift = (int)x->params.ksize + x->dense_pid_bits + x->dense_pos_bits - plan.l1;
+        d->scatter.bits = plan.l1;
+        d->scatter.overflow = (uint32_t*)(work + plan.off_overflow);
+    }
+}
+
+// Tables (first use of the handle), sort plan, buffers, tile -> protein map and exact tile bases.  The offsets of the
+// batch must be on their way to the device on x->stream.  Returns false when the tables are unusable for this k.
+bool dense_begin(ks_index* x) {
     DeviceBatch& b = x->batch;
     const uint32_t k = x->params.ksize;
     Arena* ar = x->arena;
@@ -590,47 +636,55 @@ bool dense_finalize(ks_index* x) {
     if (x->dense_state < 0) return false;
     const uint64_t n = b.n_windows;
     if (n > MAX_TUPLES) fail(KS_ERR_CAPACITY, "more than 2^31-1 tuples on one shard: shard the proteome over more GPUs");
-    const uint32_t P = (uint32_t)b.n_prot;
-    const int pid_bits = bits_for_value(b.n_prot - 1), pos_bits = bits_for_value(b.max_len);
+    x->dense_pid_bits = bits_for_value(b.n_prot - 1);
+    x->dense_pos_bits = bits_for_value(b.max_len);
     x->n_tuples = 0;    // nothing is stored yet: the buffers may be replaced without a copy
-    grow_tuples(x, n);  // d_hash: the keys as the rank kernel emits them; d_loc: the postings
+    grow_tuples(x, n);  // d_hash: the keys when the library sorts them; d_loc: the postings
     x->n_tuples = n;
     // the key sort: hand-written (two scatter levels + a shared-memory sort per bucket) when the input fits its scheme,
     // the library's otherwise (KS_DENSE_SORT=library is a test hook)
     const char* sort_env = getenv("KS_DENSE_SORT");
-    const DenseSortPlan plan = sort_env && sort_env[0] == 'l' ? DenseSortPlan() : dense_sort_plan(n, (int)k);
-    uint64_t* keys_b = nullptr;
-    char* work = nullptr;
-    if (plan.custom) {
-        work = x->b_dense_work.ensure<char>(ar, plan.bytes);
-        KS_CUDA(cudaMemsetAsync(work + plan.off_small, 0, plan.small_bytes, x->stream));
-    } else {
-        keys_b = x->b_alt_hash.ensure<uint64_t>(ar, n);
+    x->dense_plan = sort_env && sort_env[0] == 'l' ? DenseSortPlan() : dense_sort_plan(n, (int)k);
+    if (x->dense_plan.custom) {
+        char* work = x->b_dense_work.ensure<char>(ar, x->dense_plan.bytes);
+        KS_CUDA(cudaMemsetAsync(work + x->dense_plan.off_small, 0, x->dense_plan.small_bytes, x->stream));
     }
-    // 1. rank kernel over the resident batch
     ensure_ws(x, sketch_workspace_bytes(b.n_res));
     SketchArgs a;
-    a.residues = b.res; a.packed = b.packed ? 1 : 0; a.offsets = b.offs; a.n_res = b.n_res; a.n_prot = b.n_prot;
-    a.k = k; a.moltype = x->params.moltype; a.max_hash = x->max_hash; a.pid_base = 0;
-    a.out_hash = nullptr; a.out_loc = nullptr; a.capacity = x->cap; a.d_count = x->d_count; a.workspace = x->ws;
-    a.force_general = 0;
     DenseSketchArgs d;
-    d.rank_of_code = x->dense_rank; d.out_keys = x->d_hash; d.pid_bits = pid_bits; d.pos_bits = pos_bits;
-    d.exception_flag = x->dense_flags + 1;
-    d.scatter = DenseScatter{nullptr, nullptr, 0, 0, 0, nullptr};
-    if (plan.custom) {
-        d.scatter.out = (uint64_t*)(work + plan.off_region1);
-        d.scatter.cursor = (uint32_t*)(work + plan.off_cursor1);
-        d.scatter.cap = plan.cap1;
-        d.scatter.shift = (int)k + pid_bits + pos_bits - plan.l1;
-        d.scatter.bits = plan.l1;
-        d.scatter.overflow = (uint32_t*)(work + plan.off_overflow);
-    }
-    KS_CUDA(cudaEventRecord(x->ev[EV_SK0], x->stream));
+    dense_kernel_args(x, &a, &d);
     KS_CUDA(cudaMemsetAsync(x->dense_flags + 1, 0, 4, x->stream));
     KS_CUDA(launch_sketch_prepare(a, x->stream, &x->l_sketch));
+    return true;
+}
+
+// The rank kernel over tiles [t0, t1) of the resident batch (0, 0 = all).
+void dense_rank_tiles(ks_index* x, uint32_t t0, uint32_t t1) {
+    SketchArgs a;
+    DenseSketchArgs d;
+    dense_kernel_args(x, &a, &d);
+    a.tile_begin = t0; a.tile_end = t1;
     KS_CUDA(launch_sketch_dense(a, d, x->stream, &x->l_sketch));
-    KS_CUDA(cudaEventRecord(x->ev[EV_SK1], x->stream));
+}
+
+// Build the index of the pending batch on the dense path.  Returns false (nothing changed that matters) when the path
+// turns out not to apply: the tables are unusable for this k, a window holds a residue of neither hp class, or heavy
+// repeats of one k-mer overflowed a sort bucket.
+bool dense_finalize(ks_index* x) {
+    DeviceBatch& b = x->batch;
+    const uint32_t k = x->params.ksize;
+    Arena* ar = x->arena;
+    if (!x->dense_sketched) {
+        KS_CUDA(cudaEventRecord(x->ev[EV_SK0], x->stream));
+        if (!dense_begin(x)) return false;
+        dense_rank_tiles(x, 0, 0);
+        KS_CUDA(cudaEventRecord(x->ev[EV_SK1], x->stream));
+    }
+    x->dense_sketched = false;
+    const uint64_t n = b.n_windows;
+    const uint32_t P = (uint32_t)b.n_prot;
+    const DenseSortPlan plan = x->dense_plan;
+    char* work = (char*)x->b_dense_work.p;
     uint32_t exc = 0;
     uint64_t produced = 0;
     KS_CUDA(cudaMemcpyAsync(&exc, x->dense_flags + 1, 4, cudaMemcpyDeviceToHost, x->stream));
@@ -638,7 +692,7 @@ bool dense_finalize(ks_index* x) {
     KS_CUDA(cudaStreamSynchronize(x->stream));
     if (exc) return false;
     if (produced != n) fail(KS_ERR_CUDA, "internal error: dense path produced an unexpected number of tuples");
-    // 2. sort + CSR
+    // sort + CSR
     int bits = 8;  // directory as on the general path
     while (bits < 24 && (4ull << bits) < n) bits++;
     x->dir_bits = bits;
@@ -652,8 +706,9 @@ bool dense_finalize(ks_index* x) {
     x->d_counts = x->b_counts.ensure<uint64_t>(ar, 2);
     DenseCsrArgs c;
     c.plan = plan; c.work = work;
-    c.keys_a = x->d_hash; c.keys_b = keys_b; c.n = n; c.n_prot = P; c.k = k;
-    c.rank_bits = (int)k; c.pid_bits = pid_bits; c.pos_bits = pos_bits;
+    c.keys_a = x->d_hash; c.keys_b = plan.custom ? nullptr : x->b_alt_hash.ensure<uint64_t>(ar, n);
+    c.n = n; c.n_prot = P; c.k = k;
+    c.rank_bits = (int)k; c.pid_bits = x->dense_pid_bits; c.pos_bits = x->dense_pos_bits;
     c.offsets = b.offs; c.sorted_hash = x->dense_hash;
     c.loc = x->d_loc; c.keys = x->keys; c.key_grp = x->key_grp; c.grp_start = x->grp_start;
     c.t_size = x->t_size; c.t_abund = x->t_abund; c.d_counts = x->d_counts;
@@ -675,6 +730,7 @@ bool dense_finalize(ks_index* x) {
     if (overflow) return false;  // heavy repeats of one k-mer overflowed a sort bucket: the general path handles those
     x->U = cnt[0]; x->G = cnt[1];
     x->hash_col_valid = false;  // d_hash holds rank keys: the sorted hash column is rebuilt from the CSR on demand
+    x->build_path = plan.custom ? 1u : 2u;
     x->pending_dense = false;
     x->finalized = true;
     return true;
@@ -739,6 +795,7 @@ void finalize(ks_index* x) {
     KS_CUDA(cudaStreamSynchronize(x->stream));
     x->U = c[0]; x->G = c[1];
     x->hash_col_valid = hash_written != 0;
+    x->build_path = 0;
     x->finalized = true;
     if (dbg) fprintf(stderr, "[ks] finalize: alloc %.3f ms, build_index (host) %.3f ms, tail %.3f ms\n", t1 - t0, t2 - t1, now_ms() - t2);
 }
@@ -920,6 +977,7 @@ ks_status ks_index_clear(ks_index* x) {
         x->use();
         drop_csr(x);
         x->pending_dense = false;
+        x->dense_sketched = false;
         x->n_tuples = 0; x->n_prot = 0; x->n_res = 0; x->n_windows = 0;
     });
 }
@@ -976,6 +1034,7 @@ ks_status ks_index_stats(ks_index* x, ks_stats* out) {
         if (x->t_csr) KS_CUDA(cudaEventElapsedTime(&s.ms_csr, x->ev[EV_SO1], x->ev[EV_CS1]));
         s.ms_search = x->ms_search;
         s.finalized = x->finalized ? 1 : 0;
+        s.build_path = x->build_path;
         *out = s;
     });
 }

@@ -30,12 +30,12 @@ struct DenseScatterSmem {
     uint32_t start[(1 << DS_MAX_BITS) + 1];
     uint32_t gbase[1 << DS_MAX_BITS];
     uint32_t wsum[DS_THREADS / 32];
-    uint64_t dst[DS_TILE];
 };
 
 // Called by all DS_THREADS threads.  key[i] is meaningful where bit i of `valid` is set.  Contains block-wide barriers.
+// `dst`: DS_TILE keys of shared memory for the bin-ordered copy of the tile (may be the buffer the keys were read from).
 __device__ __forceinline__ void scatter_keys(const uint64_t (&key)[DS_ITEMS], uint32_t valid, const DenseScatter& sc,
-                                             uint32_t bucket_base, DenseScatterSmem& sm) {
+                                             uint32_t bucket_base, DenseScatterSmem& sm, uint64_t* dst) {
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t nbins = 1u << sc.bits, mask = nbins - 1u;
     if (tid < nbins) sm.hist[tid] = 0;
@@ -73,11 +73,11 @@ __device__ __forceinline__ void scatter_keys(const uint64_t (&key)[DS_ITEMS], ui
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < DS_ITEMS; i++)
-        if ((valid >> i) & 1u) sm.dst[sm.start[(uint32_t)(key[i] >> sc.shift) & mask] + slot[i]] = key[i];
+        if ((valid >> i) & 1u) dst[sm.start[(uint32_t)(key[i] >> sc.shift) & mask] + slot[i]] = key[i];
     __syncthreads();
     const uint32_t total = sm.start[nbins];
     for (uint32_t p = tid; p < total; p += DS_THREADS) {
-        const uint64_t k = sm.dst[p];
+        const uint64_t k = dst[p];
         const uint32_t b = (uint32_t)(k >> sc.shift) & mask;
         const uint32_t g = sm.gbase[b] + (p - sm.start[b]);
         if (g < sc.cap) sc.out[(uint64_t)(bucket_base + b) * sc.cap + g] = k;

@@ -596,8 +596,12 @@ sketch_quad_kernel(SketchArgs a, Lut256 lut, uint32_t* __restrict__ ticket, uint
 // class), and a window's pattern is one funnel shift.  A complete window that holds a residue of neither class
 // (X, U, O, *) has no pattern: the kernel flags it and the host builds this batch on the general path.
 // ---------------------------------------------------------------------------------------------
+// 5 CTAs per SM: measured 2.41 ms (4), 1.78 ms (5), 1.89 ms (6, 40 registers) on C2
+#ifndef KS_DK_CTAS
+#define KS_DK_CTAS 5
+#endif
 template <int K>
-__global__ void __launch_bounds__(SK_THREADS)
+__global__ void __launch_bounds__(SK_THREADS, KS_DK_CTAS)
 sketch_dense_kernel(SketchArgs a, Lut256 lut, const uint32_t* __restrict__ tile_pid, const uint64_t* __restrict__ tile_base,
                     DenseSketchArgs d) {
     constexpr int RES_WORDS = (SK_TILE + K + 16 + 3) / 4;
@@ -777,7 +781,7 @@ sketch_dense_kernel(SketchArgs a, Lut256 lut, const uint32_t* __restrict__ tile_
             key[it] = s_key[stage_addr(i)];
             valid |= ((i & 255u) < s_wtot[i >> 8] ? 1u : 0u) << it;
         }
-        scatter_keys(key, valid, d.scatter, 0, s_sc);
+        scatter_keys(key, valid, d.scatter, 0, s_sc, s_key);  // the staging buffer is free once the keys are in registers
         return;
     }
     const uint32_t sbase = warp * (SK_TILE / (SK_THREADS / 32));

@@ -38,6 +38,7 @@ pub struct ks_stats {
     pub ms_sort_partition: f32,
     pub ms_sort_bucket: f32,
     pub finalized: u32,
+    pub build_path: u32, // 0 general, 1 dense k-mer space, 2 dense with the library's key sort
 }
 
 #[repr(C)]
