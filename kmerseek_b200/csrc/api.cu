@@ -307,7 +307,7 @@ struct ks_index {
     int dense_state = 0;  // 0: tables not built, 1: ready, -1: unusable for this k (two patterns share a hash)
     uint32_t* dense_rank = nullptr;
     uint64_t* dense_hash = nullptr;
-    uint32_t* dense_flags = nullptr;  // device u32[2]: [0] table check, [1] exception seen by the rank kernel
+    uint32_t* dense_flags = nullptr;  // device u32[4]: [0] table check, [1] unhandled exception, [2] exception keys emitted
     Buf b_dense_rank, b_dense_hash, b_dense_flags, b_dense_work;
     bool pending_dense = false;
     uint32_t build_path = 0;  // ks_stats.build_path of the last finalize
@@ -429,7 +429,7 @@ bool dense_eligible(const ks_index* x, const DeviceBatch& b, uint64_t n_prot_bef
     if (x->params.moltype != KS_HP || k < (uint32_t)DENSE_MIN_K || k > (uint32_t)DENSE_MAX_K || x->max_hash != ~0ull) return false;
     if (x->dense_state < 0 || n_prot_before || n_tuples_before || b.n_prot == 0 || b.n_res >= (1ull << 32)) return false;
     if (!(env && env[0] == '1') && b.n_windows < (1ull << k) / 4) return false;
-    return (int)k + bits_for_value(b.n_prot - 1) + bits_for_value(b.max_len) <= 64;
+    return (int)k + 1 + bits_for_value(b.n_prot - 1) + bits_for_value(b.max_len) <= 64;  // rank' = 2 rank + 1 takes k + 1 bits
 }
 
 void sketch_resident_general(ks_index* x);
@@ -602,14 +602,16 @@ void dense_kernel_args(ks_index* x, SketchArgs* a, DenseSketchArgs* d) {
     a->out_hash = nullptr; a->out_loc = nullptr; a->capacity = x->cap; a->d_count = x->d_count; a->workspace = x->ws;
     a->force_general = 0;
     d->rank_of_code = x->dense_rank; d->out_keys = x->d_hash; d->pid_bits = x->dense_pid_bits; d->pos_bits = x->dense_pos_bits;
+    d->sorted_hash = x->dense_hash;
     d->exception_flag = x->dense_flags + 1;
+    d->handle_exceptions = plan.custom ? 1 : 0;  // the library-sorted variant has no exception handling: general path then
     d->scatter = DenseScatter{nullptr, nullptr, 0, 0, 0, nullptr};
     if (plan.custom) {
         char* work = (char*)x->b_dense_work.p;
         d->scatter.out = (uint64_t*)(work + plan.off_region1);
         d->scatter.cursor = (uint32_t*)(work + plan.off_cursor1);
         d->scatter.cap = plan.cap1;
-        d->scatter.shift = (int)x->params.ksize + x->dense_pid_bits + x->dense_pos_bits - plan.l1;
+        d->scatter.shift = (int)x->params.ksize + 1 + x->dense_pid_bits + x->dense_pos_bits - plan.l1;
         d->scatter.bits = plan.l1;
         d->scatter.overflow = (uint32_t*)(work + plan.off_overflow);
     }
@@ -621,7 +623,7 @@ bool dense_begin(ks_index* x) {
     DeviceBatch& b = x->batch;
     const uint32_t k = x->params.ksize;
     Arena* ar = x->arena;
-    x->dense_flags = x->b_dense_flags.ensure<uint32_t>(ar, 2);
+    x->dense_flags = x->b_dense_flags.ensure<uint32_t>(ar, 4);  // [0] table check, [1] unhandled exception, [2] exception keys
     if (x->dense_state == 0) {
         x->dense_rank = x->b_dense_rank.ensure<uint32_t>(ar, (size_t)1 << k);
         x->dense_hash = x->b_dense_hash.ensure<uint64_t>(ar, (size_t)1 << k);
@@ -644,7 +646,7 @@ bool dense_begin(ks_index* x) {
     // the key sort: hand-written (two scatter levels + a shared-memory sort per bucket) when the input fits its scheme,
     // the library's otherwise (KS_DENSE_SORT=library is a test hook)
     const char* sort_env = getenv("KS_DENSE_SORT");
-    x->dense_plan = sort_env && sort_env[0] == 'l' ? DenseSortPlan() : dense_sort_plan(n, (int)k);
+    x->dense_plan = sort_env && sort_env[0] == 'l' ? DenseSortPlan() : dense_sort_plan(n, (int)k + 1);
     if (x->dense_plan.custom) {
         char* work = x->b_dense_work.ensure<char>(ar, x->dense_plan.bytes);
         KS_CUDA(cudaMemsetAsync(work + x->dense_plan.off_small, 0, x->dense_plan.small_bytes, x->stream));
@@ -653,7 +655,7 @@ bool dense_begin(ks_index* x) {
     SketchArgs a;
     DenseSketchArgs d;
     dense_kernel_args(x, &a, &d);
-    KS_CUDA(cudaMemsetAsync(x->dense_flags + 1, 0, 4, x->stream));
+    KS_CUDA(cudaMemsetAsync(x->dense_flags + 1, 0, 8, x->stream));
     KS_CUDA(launch_sketch_prepare(a, x->stream, &x->l_sketch));
     return true;
 }
@@ -685,12 +687,12 @@ bool dense_finalize(ks_index* x) {
     const uint32_t P = (uint32_t)b.n_prot;
     const DenseSortPlan plan = x->dense_plan;
     char* work = (char*)x->b_dense_work.p;
-    uint32_t exc = 0;
+    uint32_t exc[2] = {0, 0};  // [0] unhandled exception (or a zero hash), [1] exception keys were emitted
     uint64_t produced = 0;
-    KS_CUDA(cudaMemcpyAsync(&exc, x->dense_flags + 1, 4, cudaMemcpyDeviceToHost, x->stream));
+    KS_CUDA(cudaMemcpyAsync(exc, x->dense_flags + 1, 8, cudaMemcpyDeviceToHost, x->stream));
     KS_CUDA(cudaMemcpyAsync(&produced, x->d_count, 8, cudaMemcpyDeviceToHost, x->stream));
     KS_CUDA(cudaStreamSynchronize(x->stream));
-    if (exc) return false;
+    if (exc[0]) return false;
     if (produced != n) fail(KS_ERR_CUDA, "internal error: dense path produced an unexpected number of tuples");
     // sort + CSR
     int bits = 8;  // directory as on the general path
@@ -708,8 +710,9 @@ bool dense_finalize(ks_index* x) {
     c.plan = plan; c.work = work;
     c.keys_a = x->d_hash; c.keys_b = plan.custom ? nullptr : x->b_alt_hash.ensure<uint64_t>(ar, n);
     c.n = n; c.n_prot = P; c.k = k;
-    c.rank_bits = (int)k; c.pid_bits = x->dense_pid_bits; c.pos_bits = x->dense_pos_bits;
+    c.rank_bits = (int)k + 1; c.pid_bits = x->dense_pid_bits; c.pos_bits = x->dense_pos_bits;
     c.offsets = b.offs; c.sorted_hash = x->dense_hash;
+    c.residues = b.res; c.packed = b.packed ? 1 : 0; c.has_exceptions = exc[1] ? 1 : 0;
     c.loc = x->d_loc; c.keys = x->keys; c.key_grp = x->key_grp; c.grp_start = x->grp_start;
     c.t_size = x->t_size; c.t_abund = x->t_abund; c.d_counts = x->d_counts;
     c.temp_bytes = dense_csr_temp_bytes(n);

@@ -44,6 +44,62 @@ __device__ uint64_t murmur_of_pattern(uint32_t pattern, uint32_t k) {
     return h1 + h2;
 }
 
+// MurmurHash3 of the translated k-mer at residue g of the batch, from the residues themselves (exception keys carry no
+// pattern): the byte path of the sketch kernels, one residue at a time -- only exception keys come here.
+// hp translation of one residue byte (fill_lut, moltype 2; src/rust/encoding.rs:43-53): hydrophobic AFGILMPVWY -> 'h',
+// polar CDEHKNQRST -> 'p', '*' stays, everything else 'X'
+__device__ __forceinline__ uint32_t hp_translate(uint32_t c) {
+    constexpr uint32_t H = (1u << 0) | (1u << 5) | (1u << 6) | (1u << 8) | (1u << 11) | (1u << 12) | (1u << 15) | (1u << 21) |
+                           (1u << 22) | (1u << 24);
+    constexpr uint32_t P = (1u << 2) | (1u << 3) | (1u << 4) | (1u << 7) | (1u << 10) | (1u << 13) | (1u << 16) | (1u << 17) |
+                           (1u << 18) | (1u << 19);
+    if (c == '*') return '*';
+    const uint32_t i = c - 'A';
+    if (i < 26u) {
+        if ((H >> i) & 1u) return 'h';
+        if ((P >> i) & 1u) return 'p';
+    }
+    return 'X';
+}
+
+__device__ __noinline__ uint64_t dense_window_hash(const uint8_t* __restrict__ res, int packed, uint64_t g, uint32_t k) {
+    uint64_t w[3] = {0, 0, 0};
+    for (uint32_t j = 0; j < k; j++) {
+        const uint64_t i = g + j;
+        uint32_t c;
+        if (packed) {
+            const uint64_t byte = (i >> 3) * 5;
+            uint64_t v = 0;
+            for (int t = 0; t < 5; t++) v |= (uint64_t)res[byte + t] << (8 * t);
+            const uint32_t code = (uint32_t)(v >> (5 * (i & 7))) & 31u;
+            c = code == 0 ? 0u : code <= 26 ? 'A' + code - 1 : code == 27 ? (uint32_t)'*' : 0u;
+        } else {
+            c = res[i];
+        }
+        w[j >> 3] |= (uint64_t)hp_translate(c) << (8 * (j & 7));
+    }
+    uint64_t h1 = SEED, h2 = SEED;
+    const uint32_t nb = k / 16, rem = k % 16;
+    if (nb) {
+        h1 ^= mix_k1(w[0]);
+        h1 = rotl64(h1, 27) + h2;
+        h1 = h1 * 5 + 0x52dce729;
+        h2 ^= mix_k2(w[1]);
+        h2 = rotl64(h2, 31) + h1;
+        h2 = h2 * 5 + 0x38495ab5;
+    }
+    const uint64_t t1 = w[2 * nb], t2 = nb ? 0 : w[1];
+    if (rem > 8) h2 ^= mix_k2(t2);
+    if (rem > 0) h1 ^= mix_k1(t1);
+    h1 ^= k;
+    h2 ^= k;
+    h1 += h2;
+    h2 += h1;
+    h1 = fmix64(h1);
+    h2 = fmix64(h2);
+    return h1 + h2;
+}
+
 __global__ void dense_hash_codes_kernel(uint32_t k, uint64_t* __restrict__ hash, uint32_t* __restrict__ code) {
     const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= (1u << k)) return;
@@ -157,7 +213,7 @@ dense_write_kernel(const uint64_t* __restrict__ keys_in, uint64_t n, int loc_bit
         if ((bg[r] >> lane) & 1u) grp_start[g] = (uint32_t)i;
         if ((bk[r] >> lane) & 1u) {
             const uint32_t u = rk + __popc(bk[r] & lt);
-            keys[u] = sorted_hash[key[r] >> loc_bits];
+            keys[u] = sorted_hash[(key[r] >> loc_bits) >> 1];  // rank' = 2 rank + 1 (no exception keys on this path)
             key_grp[u] = g;
         }
         rk += __popc(bk[r]);
@@ -286,12 +342,20 @@ struct DenseBucketArgs {
     uint32_t *key_grp, *grp_start, *t_size;
     uint64_t* d_counts;
     uint64_t n;
+    // exception keys (even rank'): their hash is recomputed from the residues
+    const uint8_t* residues;
+    const uint64_t* offsets;
+    int packed;
+    uint32_t k;
 };
 
 // 4 CTAs per SM (no loc gather here, so the smaller L1 does not hurt): 2.84 ms against 3.18 ms with 3 on C2
 #ifndef KS_DB_CTAS
 #define KS_DB_CTAS 4
 #endif
+// EXC: the batch holds exception keys (known to the host after the rank kernel); the common instantiation carries none
+// of that code.
+template <bool EXC>
 __global__ void __launch_bounds__(DB_THREADS, KS_DB_CTAS)
 dense_bucket_kernel(DenseBucketArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -321,6 +385,17 @@ dense_bucket_kernel(DenseBucketArgs a) {
     }
     const uint64_t* src = a.region2 + (uint64_t)b * DB_CAP;
     const int up = 64 - a.rem_bits;  // item = key << up: the bucket bits fall off the top
+    // bin = the item's top 12 bits with the parity bit of rank' squeezed out when it lies among them (it is 1 for every
+    // pattern key and would leave half of the bins empty).  An exception key (parity 0) can then land in a later bin than a
+    // larger key; the odd-even rounds below run until the whole bucket is in order, so that only costs rounds where
+    // exception keys are.
+    const int pb = up + a.loc_bits;  // bit of the item that holds the parity of rank'
+    const bool squeeze = pb >= 52 && pb < 63;
+    const int n_low = squeeze ? 12 - (63 - pb) : 0;  // bin bits taken from below the parity bit
+    auto bin_of = [&](uint64_t it) -> uint32_t {
+        if (!squeeze) return (uint32_t)(it >> 52);
+        return (uint32_t)(((it >> (pb + 1)) << n_low) | ((it >> (pb - n_low)) & ((1ull << n_low) - 1ull)));
+    };
     uint64_t item[8];
     uint32_t slot[4] = {0, 0, 0, 0};
 #pragma unroll
@@ -333,7 +408,7 @@ dense_bucket_kernel(DenseBucketArgs a) {
     for (int r = 0; r < 8; r++) {
         const uint32_t j = r * DB_THREADS + tid;
         if (r * DB_THREADS >= m) break;
-        if (j < m) slot[r >> 1] |= atomicAdd(&cnt[(uint32_t)(item[r] >> 52)], 1u) << (16 * (r & 1));
+        if (j < m) slot[r >> 1] |= atomicAdd(&cnt[bin_of(item[r])], 1u) << (16 * (r & 1));
     }
     __syncthreads();
     {
@@ -361,7 +436,7 @@ dense_bucket_kernel(DenseBucketArgs a) {
     for (int r = 0; r < 8; r++) {
         const uint32_t j = r * DB_THREADS + tid;
         if (r * DB_THREADS >= m) break;
-        if (j < m) B[cnt[(uint32_t)(item[r] >> 52)] + ((slot[r >> 1] >> (16 * (r & 1))) & 0xffffu)] = item[r];
+        if (j < m) B[cnt[bin_of(item[r])] + ((slot[r >> 1] >> (16 * (r & 1))) & 0xffffu)] = item[r];
     }
     __syncthreads();
     {   // odd-even transposition until nothing moves (a bin holds the few keys of one hash in a handful of proteins)
@@ -387,6 +462,43 @@ dense_bucket_kernel(DenseBucketArgs a) {
     auto shr = [](uint64_t v, int sh) -> uint64_t { return sh >= 64 ? 0ull : v >> sh; };  // no rank bits may be left
     const uint64_t pos_mask = (1ull << a.pos_bits) - 1ull, pid_mask = (1ull << (a.loc_bits - a.pos_bits)) - 1ull;
     const uint32_t s0 = a.bstart[b];
+    // Exception keys (even rank': a window with a residue of neither class, hashed from its bytes, ranked between two
+    // patterns).  Two different exception hashes can fall between the same two patterns and then share a rank': the
+    // run of that rank' is put in (hash, protein, position) order by the thread that owns its first key, and the head
+    // tests below compare recomputed hashes.  rank' parity is bit loc_bits of the key, i.e. bit rank_sh of the item --
+    // unless no rank bit is left below the bucket bits, in which case the bucket index carries it.
+    const bool any_exc = EXC;
+    auto is_exc = [&](uint64_t it) -> bool { return rank_sh < 64 ? ((it >> rank_sh) & 1ull) == 0ull : (b & 1u) == 0u; };
+    auto hash_of = [&](uint64_t it) -> uint64_t {
+        const uint64_t low = it >> up;
+        const uint32_t pid = (uint32_t)((low >> a.pos_bits) & pid_mask);
+        return dense_window_hash(a.residues, a.packed, a.offsets[pid] + (low & pos_mask), a.k);
+    };
+    if (any_exc) {  // uniform
+        for (uint32_t j = tid; j < m; j += DB_THREADS) {
+            const uint64_t it = B[j];
+            if (!is_exc(it) || (j && shr(B[j - 1], rank_sh) == shr(it, rank_sh))) continue;  // not the first key of a run
+            uint32_t e = j + 1;
+            while (e < m && shr(B[e], rank_sh) == shr(it, rank_sh)) e++;
+            if (e - j < 2) continue;
+            const uint64_t h0 = hash_of(it);
+            bool mixed = false;
+            for (uint32_t t = j + 1; t < e && !mixed; t++) mixed = hash_of(B[t]) != h0;
+            if (!mixed) continue;
+            for (uint32_t t = j + 1; t < e; t++) {  // insertion by (hash, key); hashes recomputed: runs are a handful of keys
+                const uint64_t x = B[t], hx = hash_of(x);
+                uint32_t u = t;
+                while (u > j) {
+                    const uint64_t y = B[u - 1], hy = hash_of(y);
+                    if (hy < hx || (hy == hx && y < x)) break;
+                    B[u] = y;
+                    u--;
+                }
+                B[u] = x;
+            }
+        }
+        __syncthreads();
+    }
     uint32_t flags = 0;
 #pragma unroll
     for (int r = 0; r < 8; r++) {
@@ -397,6 +509,7 @@ dense_bucket_kernel(DenseBucketArgs a) {
                 const uint64_t it = B[j];
                 const uint64_t pv = j ? B[j - 1] : ~it;
                 hk = j == 0 || shr(it, rank_sh) != shr(pv, rank_sh);
+                if (any_exc && !hk && is_exc(it)) hk = hash_of(it) != hash_of(pv);  // same rank', maybe another hash
                 hg = hk || (it >> grp_sh) != (pv >> grp_sh);
                 const uint64_t low = it >> up;  // the key's bits below the bucket bits: (rank low bits |) protein | position
                 const uint32_t pid = (uint32_t)((low >> a.pos_bits) & pid_mask);
@@ -451,7 +564,7 @@ dense_bucket_kernel(DenseBucketArgs a) {
             if (hk) {
                 const uint32_t u = base_k + (pre & 0xffffu) + __popc(bk & lt);
                 const uint64_t low_rank = shr(B[j], rank_sh);
-                a.keys[u] = a.sorted_hash[rank_top | low_rank];
+                a.keys[u] = (EXC && is_exc(B[j])) ? hash_of(B[j]) : a.sorted_hash[(rank_top | low_rank) >> 1];
                 a.key_grp[u] = g;
             }
         }
@@ -582,8 +695,11 @@ cudaError_t dense_build_csr(const DenseCsrArgs& a, cudaStream_t stream, uint64_t
         ba.status = (uint64_t*)(w + pl.off_status); ba.ticket = (uint32_t*)(w + pl.off_ticket);
         ba.loc = a.loc; ba.keys = a.keys; ba.key_grp = a.key_grp; ba.grp_start = a.grp_start; ba.t_size = a.t_size;
         ba.d_counts = a.d_counts; ba.n = n;
-        KS_TRY(cudaFuncSetAttribute(dense_bucket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DB_SMEM));
-        dense_bucket_kernel<<<nb, DB_THREADS, DB_SMEM, stream>>>(ba);
+        ba.residues = a.residues; ba.offsets = a.offsets; ba.packed = a.packed; ba.k = a.k;
+        KS_TRY(cudaFuncSetAttribute(dense_bucket_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DB_SMEM));
+        KS_TRY(cudaFuncSetAttribute(dense_bucket_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DB_SMEM));
+        if (a.has_exceptions) dense_bucket_kernel<true><<<nb, DB_THREADS, DB_SMEM, stream>>>(ba);
+        else dense_bucket_kernel<false><<<nb, DB_THREADS, DB_SMEM, stream>>>(ba);
         if (sort_launches) *sort_launches += 2;
         return cudaGetLastError();
     }

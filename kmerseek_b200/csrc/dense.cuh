@@ -34,8 +34,11 @@ struct DenseCsrArgs {
     uint64_t n;
     uint32_t n_prot;
     uint32_t k;
-    int rank_bits, pid_bits, pos_bits;
+    int rank_bits, pid_bits, pos_bits;  // rank_bits = k + 1: rank' = 2 rank + 1 (pattern) or 2 x lower bound (exception)
     const uint64_t* offsets;      // device, n_prot + 1 (protein boundaries of the batch)
+    const uint8_t* residues;      // device residues of the batch (bytes, or 5-bit codes when packed): the hash of an
+    int packed;                   // exception key (even rank') is recomputed from them (hp translation)
+    int has_exceptions;           // the rank kernel emitted exception keys (its flag, read back by the host)
     const uint64_t* sorted_hash;  // table
     // outputs
     uint64_t* loc;  // [n] postings (protein << 32 | position), ordered by (hash, protein, position)

@@ -713,7 +713,7 @@ sketch_dense_kernel(SketchArgs a, Lut256 lut, const uint32_t* __restrict__ tile_
     const uint32_t lt = (1u << lane) - 1u;
     const uint32_t g0_lo = (uint32_t)g0;
     const int loc_bits = d.pid_bits + d.pos_bits;
-    bool exc_seen = false;
+    bool exc_seen = false, exc_emitted = false;
     uint32_t wcount = 0;  // keys staged by this warp so far (uniform across the warp)
 #pragma unroll
     for (int rr = 0; rr < SQ_ROWS; rr++) {
@@ -723,7 +723,7 @@ sketch_dense_kernel(SketchArgs a, Lut256 lut, const uint32_t* __restrict__ tile_
         const bool inside = q * 4 + 3 + K <= pend_rel;  // the lane's protein state only moves forward: q * 4 is in p
         uint32_t code[4], rank[4];
         uint64_t locp[4];
-        bool keep[4];
+        bool keep[4], is_exc[4];
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             const uint32_t w = q * 4 + j;
@@ -734,12 +734,36 @@ sketch_dense_kernel(SketchArgs a, Lut256 lut, const uint32_t* __restrict__ tile_
             }
             const uint32_t bsh = ((q & 7u) << 2) + j;  // bit offset of window w in its stream word: (4q + j) mod 32
             code[j] = __funnelshift_r(hlo, hhi, bsh) & KMASK;
-            exc_seen |= valid && (__funnelshift_r(elo, ehi, bsh) & KMASK) != 0;
+            is_exc[j] = valid && (__funnelshift_r(elo, ehi, bsh) & KMASK) != 0;
             keep[j] = valid;
             locp[j] = ((uint64_t)p << d.pos_bits) | (uint64_t)(g0_lo + w - pstart_lo);
         }
 #pragma unroll
-        for (int j = 0; j < 4; j++) rank[j] = __ldg(d.rank_of_code + code[j]);
+        for (int j = 0; j < 4; j++) rank[j] = 2u * __ldg(d.rank_of_code + code[j]) + 1u;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            if (is_exc[j]) {  // rare: hash the translated bytes, place the hash among the patterns' hashes
+                if (!d.handle_exceptions) { exc_seen = true; continue; }
+                constexpr int NW = (K + 3 + 3) / 4, KW = (K + 3) / 4;
+                uint32_t x[NW + 1], bw[KW];
+#pragma unroll
+                for (int i = 0; i < NW; i++) x[i] = s_res[q + i];
+                x[NW] = 0;
+#pragma unroll
+                for (int i = 0; i < KW; i++) bw[i] = j == 0 ? x[i] : __funnelshift_r(x[i], x[i + 1], 8 * j);
+                if (K % 4) bw[KW - 1] &= (1u << (8 * (K % 4))) - 1u;
+                const uint64_t h = murmur_limbs<K>(bw);
+                uint32_t lo = 0, hi = 1u << K;  // first pattern hash >= h
+                while (lo < hi) {
+                    const uint32_t mid = (lo + hi) >> 1;
+                    if (__ldg(d.sorted_hash + mid) < h) lo = mid + 1; else hi = mid;
+                }
+                const bool same = lo < (1u << K) && __ldg(d.sorted_hash + lo) == h;  // a pattern with this very hash
+                rank[j] = 2u * lo + (same ? 1u : 0u);
+                if (h == 0) exc_seen = true;  // would have to be dropped: general path
+                exc_emitted = true;
+            }
+        }
         uint32_t below = 0, total = 0;
         uint32_t bal[4];
 #pragma unroll
@@ -759,6 +783,7 @@ sketch_dense_kernel(SketchArgs a, Lut256 lut, const uint32_t* __restrict__ tile_
         wcount += total;
     }
     if (exc_seen) atomicOr(d.exception_flag, 1u);
+    if (exc_emitted) atomicOr(d.exception_flag + 1, 1u);
     if (lane == 0) s_wtot[warp] = wcount;
     __syncthreads();
     uint32_t wprefix = 0, btotal = 0;

@@ -41,9 +41,14 @@ constexpr int DENSE_MIN_K = 8;
 constexpr int DENSE_MAX_K = 24;
 struct DenseSketchArgs {
     const uint32_t* rank_of_code;  // device, 2^k entries: rank of the pattern's hash among all patterns' hashes
-    uint64_t* out_keys;            // device, capacity entries: rank << (pid_bits + pos_bits) | protein << pos_bits | position
+    const uint64_t* sorted_hash;   // device, 2^k entries: the patterns' hashes in increasing order
+    uint64_t* out_keys;            // device, capacity entries: rank' << (pid_bits + pos_bits) | protein << pos_bits | position
+                                   // with rank' = 2 rank + 1 for a pattern; a window with a residue of neither class (no
+                                   // pattern) is hashed from its bytes and gets rank' = 2 x (pattern hashes below its hash),
+                                   // which sorts it between the right two patterns
     int pid_bits, pos_bits;
-    uint32_t* exception_flag;      // device: set when a complete window holds a residue of neither class
+    int handle_exceptions;         // 0: such a window only raises exception_flag[0] (the caller takes the general path)
+    uint32_t* exception_flag;      // device u32[2]: [0] unhandled exception / zero hash, [1] exception keys were emitted
     DenseScatter scatter;          // scatter.out != nullptr: the keys leave the kernel partitioned by their top bits
                                    // (first level of the key sort, dense_scatter.cuh) instead of in tile order
 };
