@@ -88,9 +88,10 @@ class ClockSampler:
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures of the C2
 # workload (profiles/r01_*): only meaningful for that workload, null otherwise.
-TRAFFIC = {  # bytes per launch, C2 workload, profiles/r01_d_ncu_full_raw_c2.csv
+TRAFFIC = {  # bytes per launch, C2 workload, profiles/r01_d_ncu_full_raw_rep_c2.csv, r01_e_ncu_full_raw_dense_*.csv
     "bucket_sort_rep_kernel (+ fused CSR write, directory)": 2_991_587_000 + 2_473_064_000,
-    "dense_bucket_kernel (sort + CSR write)": None,
+    "dense_bucket_kernel (sort + CSR write)": 1_638_007_000 + 3_419_163_000,
+    "sketch_dense_kernel (ranks + first scatter level)": 2_342_600_000 + 1_481_121_000,
     "sketch_quad_kernel": 205_893_000 + 2_934_864_000,
 }
 
