@@ -4,16 +4,16 @@
 // src/rust/signature.rs:273-274), the nested HashMap position records (src/rust/index.rs:770-780) and the
 // serial sorted-Vec merge into combined_minhash (src/rust/index.rs:824-827).
 //
-// Pipeline:
+// Pipeline of the general path (hp with k <= 24 normally takes the dense path of dense.cu):
 //   1. partition the tuples by the top `tb` bits of the hash (library onesweep passes over those bits only)
-//   2. bucket_sort_kernel: one CTA sorts one bucket (a few thousand tuples) entirely in shared memory, writes
-//      it back in final order and counts the bucket's unique hashes / (hash, protein) groups on the way out
-//   3. scan_counts_kernel: exclusive scan of the per-bucket counts (one CTA)
-//   4. csr_write_kernel: one CTA per bucket re-reads its sorted tuples once and writes keys / key_grp /
-//      grp_start at their final offsets -- no inter-CTA dependency, no look-back chain
-//   5. dir_kernel: bucket directory over the unique keys
-// Small inputs (and hash ranges where the shared-memory item layout does not apply) take the library sort for
-// all bits and the same steps 3-5 over fixed 4096-tuple ranges.
+//   2. bucket sort: one CTA sorts one bucket (a few thousand tuples) entirely in shared memory --
+//      bucket_sort_bin_kernel when hashes rarely repeat, bucket_sort_rep_kernel when they do -- and both end in
+//      bucket_finish: the postings go back in final order, the bucket's unique hashes / (hash, protein) groups are
+//      counted, and after a decoupled look-back over the buckets for its key / group base the bucket writes its part
+//      of keys / key_grp / grp_start and of the bucket directory straight from shared memory
+//   3. only when a bucket is too large for shared memory (heavy repeats of one hash): library sort of those ranges,
+//      then scan_counts_kernel + csr_write_kernel + dir_kernel build the CSR in separate passes
+// Small inputs take the library sort for all bits and step 3 over fixed 4096-tuple ranges.
 #include <cub/device/device_radix_sort.cuh>
 
 #include <algorithm>
