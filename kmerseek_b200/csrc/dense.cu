@@ -324,8 +324,9 @@ dense_bucket_offsets_kernel(const uint32_t* __restrict__ cursor2, uint32_t nb, u
 constexpr int DB_THREADS = 512;
 constexpr int DB_WARPS = DB_THREADS / 32;
 constexpr int DB_CAP = 4096;
-constexpr int DB_BINS = 4096;
-constexpr size_t DB_SMEM = (size_t)DB_CAP * 8 + (size_t)DB_BINS * 4;
+constexpr int DB_BIN_BITS = 13;
+constexpr int DB_BINS = 1 << DB_BIN_BITS;  // 16-bit counters, two per word: a bucket holds at most 4096 keys
+constexpr size_t DB_SMEM = (size_t)DB_CAP * 8 + (size_t)DB_BINS * 2;
 
 struct DenseBucketArgs {
     const uint64_t* region2;   // final buckets, DB_CAP keys each
@@ -360,7 +361,8 @@ __global__ void __launch_bounds__(DB_THREADS, KS_DB_CTAS)
 dense_bucket_kernel(DenseBucketArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t* B = reinterpret_cast<uint64_t*>(smem_raw);      // [DB_CAP] items: the key's bits below the bucket bits, left-aligned
-    uint32_t* cnt = reinterpret_cast<uint32_t*>(B + DB_CAP);  // [DB_BINS]
+    uint32_t* cnt = reinterpret_cast<uint32_t*>(B + DB_CAP);  // [DB_BINS / 2] words of two 16-bit bin counters, then offsets
+    const uint16_t* off16 = reinterpret_cast<const uint16_t*>(cnt);
     __shared__ uint32_t s_wsum[DB_WARPS];
     __shared__ uint32_t s_cw[8 * DB_WARPS];
     __shared__ uint64_t s_base;
@@ -385,15 +387,15 @@ dense_bucket_kernel(DenseBucketArgs a) {
     }
     const uint64_t* src = a.region2 + (uint64_t)b * DB_CAP;
     const int up = 64 - a.rem_bits;  // item = key << up: the bucket bits fall off the top
-    // bin = the item's top 12 bits with the parity bit of rank' squeezed out when it lies among them (it is 1 for every
+    // bin = the item's top 13 bits with the parity bit of rank' squeezed out when it lies among them (it is 1 for every
     // pattern key and would leave half of the bins empty).  An exception key (parity 0) can then land in a later bin than a
     // larger key; the odd-even rounds below run until the whole bucket is in order, so that only costs rounds where
     // exception keys are.
     const int pb = up + a.loc_bits;  // bit of the item that holds the parity of rank'
-    const bool squeeze = pb >= 52 && pb < 63;
-    const int n_low = squeeze ? 12 - (63 - pb) : 0;  // bin bits taken from below the parity bit
+    const bool squeeze = pb >= 64 - DB_BIN_BITS && pb < 63;
+    const int n_low = squeeze ? DB_BIN_BITS - (63 - pb) : 0;  // bin bits taken from below the parity bit
     auto bin_of = [&](uint64_t it) -> uint32_t {
-        if (!squeeze) return (uint32_t)(it >> 52);
+        if (!squeeze) return (uint32_t)(it >> (64 - DB_BIN_BITS));
         return (uint32_t)(((it >> (pb + 1)) << n_low) | ((it >> (pb - n_low)) & ((1ull << n_low) - 1ull)));
     };
     uint64_t item[8];
@@ -408,12 +410,19 @@ dense_bucket_kernel(DenseBucketArgs a) {
     for (int r = 0; r < 8; r++) {
         const uint32_t j = r * DB_THREADS + tid;
         if (r * DB_THREADS >= m) break;
-        if (j < m) slot[r >> 1] |= atomicAdd(&cnt[bin_of(item[r])], 1u) << (16 * (r & 1));
+        if (j < m) {
+            const uint32_t bin = bin_of(item[r]), sh16 = 16 * (bin & 1u);
+            const uint32_t old = (atomicAdd(&cnt[bin >> 1], 1u << sh16) >> sh16) & 0xffffu;  // no carry: counts <= 4096
+            slot[r >> 1] |= old << (16 * (r & 1));
+        }
     }
     __syncthreads();
-    {
+    {   // exclusive scan of the 8192 counters; thread t owns bins 16t .. 16t+15 (8 words)
         uint4 c0 = reinterpret_cast<uint4*>(cnt)[2 * tid], c1 = reinterpret_cast<uint4*>(cnt)[2 * tid + 1];
-        const uint32_t total = c0.x + c0.y + c0.z + c0.w + c1.x + c1.y + c1.z + c1.w;
+        uint32_t w[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+        uint32_t total = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) total += (w[i] & 0xffffu) + (w[i] >> 16);
         uint32_t incl = total;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -425,18 +434,22 @@ dense_bucket_kernel(DenseBucketArgs a) {
         uint32_t off = 0;
 #pragma unroll
         for (int w = 0; w < DB_WARPS; w++) off += w < (int)warp ? s_wsum[w] : 0u;
-        uint4 e0, e1;
-        e0.x = off + incl - total; e0.y = e0.x + c0.x; e0.z = e0.y + c0.y; e0.w = e0.z + c0.z;
-        e1.x = e0.w + c0.w; e1.y = e1.x + c1.x; e1.z = e1.y + c1.y; e1.w = e1.z + c1.z;
-        reinterpret_cast<uint4*>(cnt)[2 * tid] = e0;
-        reinterpret_cast<uint4*>(cnt)[2 * tid + 1] = e1;
+        uint32_t run = off + incl - total;  // < 4096: the exclusive offsets fit 16 bits as well
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const uint32_t lo = w[i] & 0xffffu, hi = w[i] >> 16;
+            w[i] = run | ((run + lo) << 16);
+            run += lo + hi;
+        }
+        reinterpret_cast<uint4*>(cnt)[2 * tid] = make_uint4(w[0], w[1], w[2], w[3]);
+        reinterpret_cast<uint4*>(cnt)[2 * tid + 1] = make_uint4(w[4], w[5], w[6], w[7]);
     }
     __syncthreads();
 #pragma unroll
     for (int r = 0; r < 8; r++) {
         const uint32_t j = r * DB_THREADS + tid;
         if (r * DB_THREADS >= m) break;
-        if (j < m) B[cnt[bin_of(item[r])] + ((slot[r >> 1] >> (16 * (r & 1))) & 0xffffu)] = item[r];
+        if (j < m) B[off16[bin_of(item[r])] + ((slot[r >> 1] >> (16 * (r & 1))) & 0xffffu)] = item[r];
     }
     __syncthreads();
     {   // odd-even transposition until nothing moves (a bin holds the few keys of one hash in a handful of proteins)
