@@ -295,12 +295,14 @@ def main():
     ms = {k: float(np.mean(v)) for k, v in stage_ms.items()}
     alphabet = {"protein": 20.0, "dayhoff": 6.0, "hp": 2.0}[cfg["moltype"]]
     repeat_heavy = n_tuples > 0.25 * alphabet ** cfg["k"] / cfg["scaled"]  # the library's choice of bucket-sort variant
-    if st["build_path"] == 0:
+    if st["build_path"] in (0, 3):
         bucket_name = ("bucket_sort_rep_kernel" if repeat_heavy else "bucket_sort_bin_kernel") + " (+ fused CSR write, directory)"
         alg = {
             # BASELINE.md section 3; per launch = per step (every stage runs once per step)
             "sketch_quad_kernel": ("sketch", n_res + (n_prot + 1) * 8 + n_tuples * 16),
-            "partition (2 library onesweep passes)": ("partition", n_tuples * 16 * 2),          # one read + one write
+            ("partition (2 library onesweep passes)" if st["build_path"] == 0 else
+             "pair_partition_kernel (second scatter level; the first is fused into the sketch kernel)"):
+                ("partition", n_tuples * 16 * 2),                                                # one read + one write
             # one read of every tuple, one write of its payload (loc), plus the CSR arrays the kernel emits (keys, key_grp,
             # grp_start) and the bucket directory (about one entry per 4 tuples)
             bucket_name: ("bucket", n_tuples * 16 + n_tuples * 8 + n_groups * 4 + n_unique * 12 + (n_tuples // 4) * 4),
@@ -350,7 +352,8 @@ def main():
         "config": {"workload": args.workload, "k": cfg["k"], "moltype": cfg["moltype"], "scaled": cfg["scaled"],
                    "residues_per_gpu": n_res, "proteins_per_gpu": n_prot, "tuples_per_gpu": n_tuples,
                    "unique_hashes_per_gpu": n_unique, "parallelism": f"protein-sharded x{world}",
-                   "build_path": {0: "general", 1: "dense k-mer space", 2: "dense k-mer space, library key sort"}[st["build_path"]],
+                   "build_path": {0: "general", 1: "dense k-mer space", 2: "dense k-mer space, library key sort",
+                                  3: "general, unstable partition"}[st["build_path"]],
                    "l2": "inputs (0.2 GB residues, 3 GB tuples) exceed the 126 MB L2; no flush needed"},
         "e2e": {"value": e2e_value, "unit": "residues/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": int((n_res + 7) // 8 * 5 + 72 + (n_prot + 1) * 8), "d2h_bytes_per_step": 8 + 16 + 136},

@@ -310,6 +310,9 @@ struct ks_index {
     uint32_t* dense_flags = nullptr;  // device u32[4]: [0] table check, [1] unhandled exception, [2] exception keys emitted
     Buf b_dense_rank, b_dense_hash, b_dense_flags, b_dense_work;
     bool pending_dense = false;
+    bool scattered = false;  // the only batch was sketched straight into the regions of the unstable partition (pair_plan)
+    PairSortPlan pair_plan;
+    Buf b_pair_work;
     uint32_t build_path = 0;  // ks_stats.build_path of the last finalize
     bool dense_sketched = false;  // pending batch: the rank kernel has already run over it (pipelined upload)
     DenseSortPlan dense_plan;
@@ -439,11 +442,51 @@ void dense_rank_tiles(ks_index* x, uint32_t t0, uint32_t t1);
 // A batch deferred to finalize (dense path) is sketched the general way after all: something else is about to touch
 // the tuples or the resident batch.
 void materialize_pending(ks_index* x) {
-    if (!x->pending_dense) return;
+    if (!x->pending_dense && !x->scattered) return;
     x->pending_dense = false;
     x->dense_sketched = false;
+    x->scattered = false;  // the scattered tuples are dropped: the batch is sketched again, in order
     x->n_tuples = x->n_prot = x->n_res = x->n_windows = 0;
     sketch_resident_general(x);
+}
+
+bool repeat_heavy(const ks_index* x, uint64_t n) {
+    // distinct k-mers possible under this alphabet vs tuples: hp k=24 has 2^24 of them for ~2*10^8 tuples
+    const double alphabet = x->params.moltype == KS_HP ? 2.0 : x->params.moltype == KS_DAYHOFF ? 6.0 : 20.0;
+    const double space = std::pow(alphabet, (double)x->params.ksize) / (double)x->params.scaled;
+    return (double)n > 0.25 * space;
+}
+
+// Unstable partition of the general path (dense_scatter.cuh, PairSortPlan): the batch is the index's only content, hashes
+// rarely repeat (the bucket sort orders equal hashes by loc, pair by pair), scaled == 1 (kept windows per protein come
+// from the offsets) and the tuple count fits two scatter levels.  KS_SCATTER=0 switches it off (test hook).
+bool scatter_eligible(const ks_index* x, const DeviceBatch& b, uint64_t n_prot_before, uint64_t n_tuples_before, PairSortPlan* plan) {
+    const char* env = getenv("KS_SCATTER");
+    if (env && env[0] == '0') return false;
+    if (x->max_hash != ~0ull || x->params.ksize > (uint32_t)SK_MAX_TEMPLATE_K || getenv("KS_SKETCH_GENERAL")) return false;
+    if (n_prot_before || n_tuples_before || b.n_prot == 0 || b.n_windows > MAX_TUPLES) return false;
+    if (repeat_heavy(x, b.n_windows)) return false;
+    *plan = pair_sort_plan(b.n_windows, x->end_bit(), x->max_hash);
+    return plan->custom != 0;
+}
+
+void scatter_args(ks_index* x, SketchArgs* a) {
+    const PairSortPlan& pl = x->pair_plan;
+    char* w = (char*)x->b_pair_work.p;
+    a->scatter.out_key = (uint64_t*)(w + pl.off_r1_hash);
+    a->scatter.out_val = (uint64_t*)(w + pl.off_r1_loc);
+    a->scatter.cursor = (uint32_t*)(w + pl.off_cursor1);
+    a->scatter.cap = pl.cap1;
+    a->scatter.shift = 64 - pl.l1;
+    a->scatter.bits = pl.l1;
+    a->scatter.lz = x->lz;
+    a->scatter.overflow = (uint32_t*)(w + pl.off_overflow);
+}
+
+void scatter_begin(ks_index* x, const PairSortPlan& plan) {
+    x->pair_plan = plan;
+    char* w = x->b_pair_work.ensure<char>(x->arena, plan.bytes);
+    KS_CUDA(cudaMemsetAsync(w + plan.off_small, 0, plan.small_bytes, x->stream));
 }
 
 void sketch_resident(ks_index* x) {
@@ -455,6 +498,30 @@ void sketch_resident(ks_index* x) {
         x->pending_dense = true;  // finalize builds the index from the resident residues in one go
         x->n_tuples = b.n_windows; x->n_prot = b.n_prot; x->n_res = b.n_res; x->n_windows = b.n_windows;
         return;
+    }
+    PairSortPlan plan;
+    if (scatter_eligible(x, b, x->n_prot, x->n_tuples, &plan)) {
+        scatter_begin(x, plan);
+        ensure_ws(x, sketch_workspace_bytes(b.n_res));
+        SketchArgs a;
+        a.residues = b.res; a.packed = b.packed ? 1 : 0; a.offsets = b.offs; a.n_res = b.n_res; a.n_prot = b.n_prot;
+        a.k = x->params.ksize; a.moltype = x->params.moltype; a.max_hash = x->max_hash; a.pid_base = 0;
+        a.out_hash = nullptr; a.out_loc = nullptr; a.capacity = 0; a.d_count = x->d_count; a.workspace = x->ws;
+        a.force_general = 0;
+        scatter_args(x, &a);
+        KS_CUDA(cudaEventRecord(x->ev[EV_SK0], x->stream));
+        KS_CUDA(launch_sketch(a, x->stream, &x->l_sketch));
+        KS_CUDA(cudaEventRecord(x->ev[EV_SK1], x->stream));
+        uint64_t r[2] = {0, 0};
+        KS_CUDA(cudaMemcpyAsync(r, x->d_count, 16, cudaMemcpyDeviceToHost, x->stream));
+        KS_CUDA(cudaStreamSynchronize(x->stream));
+        x->t_sketch = true;
+        if ((r[1] >> 32) == 0 && r[0] == b.n_windows) {
+            x->scattered = true;
+            x->n_tuples = b.n_windows; x->n_prot = b.n_prot; x->n_res = b.n_res; x->n_windows = b.n_windows;
+            return;
+        }
+        // a zero hash (it must be dropped): the ordered path below
     }
     sketch_resident_general(x);
 }
@@ -492,13 +559,15 @@ bool add_proteome_pipelined(ks_index* x, const ks_proteome* p) {
     if (p->n_res < (64u << 20) || p->n_prot == 0) return false;  // small batches: one copy, one launch
     if (x->finalized) fail(KS_ERR_VALIDATION, "Validation error: index is finalized; ks_index_clear before adding more");
     materialize_pending(x);
-    bool dense = false;
+    bool dense = false, scat = false;  // dense k-mer space path / unstable partition of the general path
+    PairSortPlan scat_plan;
     {   // a batch for the dense path: the rank kernel follows the chunks instead of the sketch kernel
         DeviceBatch probe;
         probe.n_prot = p->n_prot; probe.n_res = p->n_res;
         probe.n_windows = count_windows(p->offsets, p->n_prot, x->params.ksize);
         probe.max_len = max_protein_len(p->offsets, p->n_prot);
         dense = dense_eligible(x, probe, x->n_prot, x->n_tuples);
+        if (!dense) scat = scatter_eligible(x, probe, x->n_prot, x->n_tuples, &scat_plan);
     }
     if (p->n_prot >= 0xffffffffull || x->n_prot + p->n_prot >= 0xffffffffull) fail(KS_ERR_CAPACITY, "more than 2^32-2 proteins on one shard");
     DeviceBatch& b = x->batch;
@@ -521,7 +590,8 @@ bool add_proteome_pipelined(ks_index* x, const ks_proteome* p) {
     b.n_windows = count_windows(p->offsets, p->n_prot, x->params.ksize);
     b.max_len = max_protein_len(p->offsets, p->n_prot);
     b.valid = true;
-    if (!dense) grow_tuples(x, x->n_tuples + expected_kept(x, b.n_windows));
+    if (!dense && !scat) grow_tuples(x, x->n_tuples + expected_kept(x, b.n_windows));
+    if (scat) scatter_begin(x, scat_plan);
     ensure_ws(x, sketch_workspace_bytes(b.n_res));
     KS_CUDA(cudaEventRecord(x->ev[EV_UP0], x->stream));
     KS_CUDA(cudaEventRecord(x->ev[EV_SK0], x->stream));
@@ -540,6 +610,7 @@ bool add_proteome_pipelined(ks_index* x, const ks_proteome* p) {
     a.out_hash = x->d_hash + x->n_tuples; a.out_loc = x->d_loc + x->n_tuples; a.capacity = x->cap - x->n_tuples;
     a.d_count = x->d_count; a.workspace = x->ws;
     a.force_general = getenv("KS_SKETCH_GENERAL") ? 1 : 0;  // test hook: the look-back path at scaled == 1
+    if (scat) { a.out_hash = nullptr; a.out_loc = nullptr; a.capacity = 0; scatter_args(x, &a); }
     if (!dense) KS_CUDA(launch_sketch_prepare(a, x->stream, &x->l_sketch));  // (dense_begin has done it)
     const uint64_t nt = (b.n_res + SK_TILE - 1) / SK_TILE;
     const uint64_t per = (nt + CHUNKS - 1) / CHUNKS;
@@ -574,6 +645,15 @@ bool add_proteome_pipelined(ks_index* x, const ks_proteome* p) {
     x->t_upload = x->t_sketch = true;
     // a zero hash on the exact path, or more tuples than the estimate for scaled > 1 allowed for: redo the batch (now
     // resident) through the plain path, which takes the look-back kernel / grows the buffer as needed
+    if (scat) {
+        if ((r[1] >> 32) != 0 || r[0] != b.n_windows) {  // a zero hash: the ordered path
+            sketch_resident_general(x);
+            return true;
+        }
+        x->scattered = true;
+        x->n_tuples = b.n_windows; x->n_prot = b.n_prot; x->n_res = b.n_res; x->n_windows = b.n_windows;
+        return true;
+    }
     if ((r[1] >> 32) != 0 || r[0] > x->cap - x->n_tuples) {
         sketch_resident_general(x);
         return true;
@@ -767,10 +847,15 @@ void finalize(ks_index* x) {
     BuildArgs a;
     a.hash_a = x->d_hash; a.loc_a = x->d_loc; a.hash_b = hb; a.loc_b = lb;
     a.n = n; a.n_prot = P; a.end_bit = x->end_bit(); a.max_hash = x->max_hash;
-    {   // distinct k-mers possible under this alphabet vs tuples: hp k=24 has 2^24 of them for ~2*10^8 tuples
-        const double alphabet = x->params.moltype == KS_HP ? 2.0 : x->params.moltype == KS_DAYHOFF ? 6.0 : 20.0;
-        const double space = std::pow(alphabet, (double)x->params.ksize) / (double)x->params.scaled;
-        a.repeat_heavy = (double)n > 0.25 * space ? 1 : 0;  // measured: the one-pass kernel only wins when repeats are rare
+    a.repeat_heavy = repeat_heavy(x, n) ? 1 : 0;  // measured: the bin kernel only wins when repeats are rare
+    int overflowed = 0;
+    if (x->scattered) {  // the tuples sit in the regions of the unstable partition; the postings go to d_loc
+        x->n_tuples = 0;
+        grow_tuples(x, n);
+        x->n_tuples = n;
+        a.loc_a = x->d_loc; a.hash_a = x->d_hash;
+        a.plan = x->pair_plan; a.work = x->b_pair_work.p; a.offsets = x->batch.offs; a.k = x->params.ksize;
+        a.overflowed = &overflowed;
     }
     a.keys = x->keys; a.key_grp = x->key_grp; a.grp_start = x->grp_start; a.t_size = x->t_size; a.t_abund = x->t_abund;
     a.d_counts = x->d_counts; a.dir = x->dir; a.dir_bits = x->dir_bits; a.dir_shift = x->dir_shift;
@@ -784,6 +869,14 @@ void finalize(ks_index* x) {
     KS_CUDA(cudaEventRecord(x->ev[EV_SO0], x->stream));
     KS_CUDA(build_index(a, x->stream, &in_a, &x->l_sort, &x->l_csr));
     KS_CUDA(cudaEventRecord(x->ev[EV_CS1], x->stream));
+    if (overflowed) {  // a k-mer repeated thousands of times filled a region: sketch again in order, stable partition
+        KS_CUDA(cudaStreamSynchronize(x->stream));
+        materialize_pending(x);
+        finalize(x);
+        return;
+    }
+    const bool was_scattered = x->scattered;
+    x->scattered = false;
     double t2 = dbg ? now_ms() : 0;
     x->t_sort = x->t_csr = true;
     if (!in_a) {  // the sorted tuples sit in the alternate pair: swap roles, nothing is freed
@@ -798,7 +891,7 @@ void finalize(ks_index* x) {
     KS_CUDA(cudaStreamSynchronize(x->stream));
     x->U = c[0]; x->G = c[1];
     x->hash_col_valid = hash_written != 0;
-    x->build_path = 0;
+    x->build_path = was_scattered ? 3u : 0u;
     x->finalized = true;
     if (dbg) fprintf(stderr, "[ks] finalize: alloc %.3f ms, build_index (host) %.3f ms, tail %.3f ms\n", t1 - t0, t2 - t1, now_ms() - t2);
 }
@@ -981,6 +1074,7 @@ ks_status ks_index_clear(ks_index* x) {
         drop_csr(x);
         x->pending_dense = false;
         x->dense_sketched = false;
+        x->scattered = false;
         x->n_tuples = 0; x->n_prot = 0; x->n_res = 0; x->n_windows = 0;
     });
 }

@@ -236,25 +236,6 @@ dense_write_kernel(const uint64_t* __restrict__ keys_in, uint64_t n, int loc_bit
 // writes the bucket's part of the postings and the CSR arrays (decoupled look-back over the buckets for the key / group
 // base, as bucket_finish does).
 // ---------------------------------------------------------------------------------------------
-__global__ void dense_chunks_kernel(const uint32_t* __restrict__ cursor1, uint32_t nb1, uint32_t cap1, uint32_t* __restrict__ chunk_pfx) {
-    __shared__ uint32_t s_w[8];
-    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    uint32_t c = 0;
-    if (tid < nb1) c = (min(cursor1[tid], cap1) + DS_TILE - 1) / DS_TILE;
-    uint32_t incl = c;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
-        if ((int)lane >= o) incl += v;
-    }
-    if (lane == 31) s_w[warp] = incl;
-    __syncthreads();
-    uint32_t off = 0;
-    for (uint32_t w = 0; w < warp; w++) off += s_w[w];
-    if (tid < nb1) chunk_pfx[tid] = off + incl - c;
-    if (tid == 255) chunk_pfx[nb1] = off + incl;  // nb1 <= 256
-}
-
 __global__ void __launch_bounds__(DS_THREADS)
 dense_partition_kernel(const uint64_t* __restrict__ region1, const uint32_t* __restrict__ cursor1, uint32_t cap1, uint32_t nb1,
                        const uint32_t* __restrict__ chunk_pfx, DenseScatter sc) {
@@ -280,45 +261,6 @@ dense_partition_kernel(const uint64_t* __restrict__ region1, const uint32_t* __r
         if (first + i < cnt) { key[it] = src[i]; valid |= 1u << it; }
     }
     scatter_keys(key, valid, sc, b1 << sc.bits, s_sc, s_dst);
-}
-
-// tuple offset of every final bucket (exclusive scan of the clamped cursors), one CTA
-__global__ void __launch_bounds__(1024)
-dense_bucket_offsets_kernel(const uint32_t* __restrict__ cursor2, uint32_t nb, uint32_t cap, uint32_t* __restrict__ bstart) {
-    __shared__ uint32_t s_w[32];
-    __shared__ uint32_t s_carry;
-    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_carry = 0;
-    __syncthreads();
-    for (uint32_t base = 0; base < nb; base += 1024) {
-        const uint32_t i = base + tid;
-        const uint32_t v = i < nb ? min(cursor2[i], cap) : 0u;
-        uint32_t incl = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-            if ((int)lane >= o) incl += t;
-        }
-        if (lane == 31) s_w[warp] = incl;
-        __syncthreads();
-        if (warp == 0) {
-            const uint32_t w = s_w[lane];
-            uint32_t wi = w;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t t = __shfl_up_sync(0xffffffffu, wi, o);
-                if ((int)lane >= o) wi += t;
-            }
-            s_w[lane] = wi - w;
-        }
-        __syncthreads();
-        const uint32_t excl = s_carry + s_w[warp] + incl - v;
-        if (i < nb) bstart[i] = excl;
-        __syncthreads();
-        if (tid == 1023) s_carry = excl + v;
-        __syncthreads();
-    }
-    if (tid == 0) bstart[nb] = s_carry;
 }
 
 constexpr int DB_THREADS = 512;

@@ -84,4 +84,143 @@ __device__ __forceinline__ void scatter_keys(const uint64_t (&key)[DS_ITEMS], ui
     }
 }
 
+// The same for (hash, loc) pairs of the general path (hashes that rarely repeat: pairs are distinct, their final order
+// is numeric, and the bucket sort breaks ties between equal hashes by loc, so no stability is needed here either).
+// bin = the `bits` bits of the normalised hash (key << lz) that start `shift` bits from the bottom.
+struct PairScatter {
+    uint64_t *out_key, *out_val;  // regions of `cap` entries each, region index = bucket_base + bin
+    uint32_t* cursor;
+    uint32_t cap;
+    int shift, bits, lz;
+    uint32_t* overflow;
+};
+
+// fetch_val(i) returns the value that goes with key[i]; it is called after the keys have been moved, so the values
+// may live in a buffer that `dst_val` aliases (the sketch kernel's staging), while `dst_key` may alias the keys' source.
+template <class FetchVal>
+__device__ __forceinline__ void scatter_pairs(const uint64_t (&key)[DS_ITEMS], uint32_t valid, FetchVal fetch_val,
+                                              const PairScatter& sc, uint32_t bucket_base, DenseScatterSmem& sm,
+                                              uint64_t* dst_key, uint64_t* dst_val) {
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t nbins = 1u << sc.bits, mask = nbins - 1u;
+    auto bin_of = [&](uint64_t k) -> uint32_t { return sc.bits ? (uint32_t)((k << sc.lz) >> sc.shift) & mask : 0u; };
+    if (tid < nbins) sm.hist[tid] = 0;
+    __syncthreads();
+    uint32_t packed[DS_ITEMS];  // bin << 12 | slot in the bin (a tile holds 2048 pairs)
+#pragma unroll
+    for (int i = 0; i < DS_ITEMS; i++)
+        if ((valid >> i) & 1u) {
+            const uint32_t b = bin_of(key[i]);
+            packed[i] = (b << 12) | atomicAdd(&sm.hist[b], 1u);
+        }
+    __syncthreads();
+    {
+        const uint32_t c = tid < nbins ? sm.hist[tid] : 0u;
+        uint32_t incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((int)lane >= o) incl += v;
+        }
+        if (lane == 31) sm.wsum[warp] = incl;
+        __syncthreads();
+        uint32_t off = 0;
+#pragma unroll
+        for (int w = 0; w < DS_THREADS / 32; w++) off += w < (int)warp ? sm.wsum[w] : 0u;
+        if (tid < nbins) {
+            sm.start[tid] = off + incl - c;
+            uint32_t g = 0;
+            if (c) {
+                g = atomicAdd(&sc.cursor[bucket_base + tid], c);
+                if (g + c > sc.cap) atomicOr(sc.overflow, 1u);
+            }
+            sm.gbase[tid] = g;
+        }
+        if (tid == DS_THREADS - 1) sm.start[nbins] = off + incl;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < DS_ITEMS; i++)
+        if ((valid >> i) & 1u) dst_key[sm.start[packed[i] >> 12] + (packed[i] & 0xfffu)] = key[i];
+    uint64_t val[DS_ITEMS];
+#pragma unroll
+    for (int i = 0; i < DS_ITEMS; i++)
+        if ((valid >> i) & 1u) val[i] = fetch_val(i);
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < DS_ITEMS; i++)
+        if ((valid >> i) & 1u) dst_val[sm.start[packed[i] >> 12] + (packed[i] & 0xfffu)] = val[i];
+    __syncthreads();
+    const uint32_t total = sm.start[nbins];
+    for (uint32_t p = tid; p < total; p += DS_THREADS) {
+        const uint64_t k = dst_key[p];
+        const uint32_t b = bin_of(k);
+        const uint32_t g = sm.gbase[b] + (p - sm.start[b]);
+        if (g < sc.cap) {
+            const uint64_t at = (uint64_t)(bucket_base + b) * sc.cap + g;
+            sc.out_key[at] = k;
+            sc.out_val[at] = dst_val[p];
+        }
+    }
+}
+
+// chunk_pfx[b] = first DS_TILE-sized chunk of first-level region b (exclusive scan of the regions' chunk counts); one CTA
+static __global__ void dense_chunks_kernel(const uint32_t* __restrict__ cursor1, uint32_t nb1, uint32_t cap1, uint32_t* __restrict__ chunk_pfx) {
+    __shared__ uint32_t s_w[8];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint32_t c = 0;
+    if (tid < nb1) c = (min(cursor1[tid], cap1) + DS_TILE - 1) / DS_TILE;
+    uint32_t incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((int)lane >= o) incl += v;
+    }
+    if (lane == 31) s_w[warp] = incl;
+    __syncthreads();
+    uint32_t off = 0;
+    for (uint32_t w = 0; w < warp; w++) off += s_w[w];
+    if (tid < nb1) chunk_pfx[tid] = off + incl - c;
+    if (tid == 255) chunk_pfx[nb1] = off + incl;  // nb1 <= 256
+}
+
+// tuple offset of every final bucket (exclusive scan of the clamped cursors), one CTA
+static __global__ void __launch_bounds__(1024)
+dense_bucket_offsets_kernel(const uint32_t* __restrict__ cursor2, uint32_t nb, uint32_t cap, uint32_t* __restrict__ bstart) {
+    __shared__ uint32_t s_w[32];
+    __shared__ uint32_t s_carry;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < nb; base += 1024) {
+        const uint32_t i = base + tid;
+        const uint32_t v = i < nb ? min(cursor2[i], cap) : 0u;
+        uint32_t incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((int)lane >= o) incl += t;
+        }
+        if (lane == 31) s_w[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            const uint32_t w = s_w[lane];
+            uint32_t wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, wi, o);
+                if ((int)lane >= o) wi += t;
+            }
+            s_w[lane] = wi - w;
+        }
+        __syncthreads();
+        const uint32_t excl = s_carry + s_w[warp] + incl - v;
+        if (i < nb) bstart[i] = excl;
+        __syncthreads();
+        if (tid == 1023) s_carry = excl + v;
+        __syncthreads();
+    }
+    if (tid == 0) bstart[nb] = s_carry;
+}
+
 }  // namespace ks

@@ -22,6 +22,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "dense_scatter.cuh"
 #include "index_build.cuh"
 
 namespace ks {
@@ -146,7 +147,7 @@ __device__ __forceinline__ void bucket_empty(uint32_t b, const CsrOut& f) {
 // tuple of scratch), so a head test reads two neighbouring slots.  No sorted hash column on the fused path: the CSR
 // arrays carry the hashes (keys) and nothing on the hot path reads hash[i] of the sorted tuples (expand_sorted_hash
 // rebuilds the column for the export calls).
-__device__ __forceinline__ void bucket_finish(const uint64_t* items, uint32_t* spid, uint32_t m, uint32_t s, uint32_t b,
+__device__ __forceinline__ void bucket_finish(const uint64_t* items, uint32_t* spid, uint32_t m, uint32_t s_in, uint32_t s, uint32_t b,
                                                   int lz, int tb, const uint64_t* __restrict__ in_loc,
                                                   uint64_t* __restrict__ out_hash, uint64_t* __restrict__ out_loc,
                                                   uint64_t* __restrict__ counts, uint32_t* __restrict__ t_size,
@@ -163,7 +164,7 @@ __device__ __forceinline__ void bucket_finish(const uint64_t* items, uint32_t* s
     for (int r = 0; r < 8; r++) {
         const uint32_t j = r * LS_THREADS + tid;
         if (r * LS_THREADS >= m) break;  // uniform
-        if (j < m) loc[r] = in_loc[s + (uint32_t)(items[j] & 0xfffu)];  // the bucket's own window of the input (L1/L2)
+        if (j < m) loc[r] = in_loc[s_in + (uint32_t)(items[j] & 0xfffu)];  // the bucket's own window of the input (L1/L2)
     }
 #pragma unroll
     for (int r = 0; r < 8; r++) {
@@ -473,7 +474,7 @@ bucket_sort_rep_kernel(const uint64_t* __restrict__ in_hash, const uint64_t* __r
     }
 
     // src == A: the other item buffer is free and parks the protein ids of the tail
-    bucket_finish(src, reinterpret_cast<uint32_t*>(dst), m, s, b, lz, tb, in_loc, out_hash, out_loc, counts, t_size, f);
+    bucket_finish(src, reinterpret_cast<uint32_t*>(dst), m, s, s, b, lz, tb, in_loc, out_hash, out_loc, counts, t_size, f);
 }
 
 
@@ -497,12 +498,16 @@ static_assert(BN_PER_THREAD == 8, "two 16-byte loads per thread in the scan");
 
 // 3 CTAs per SM: measured against 2 (2.14 ms on the 100 M-residue target run) and 4 (1.85 ms; the loc gather loses its
 // L1 lines to the larger shared-memory carve-out) -- 1.73 ms
-template <bool STEPPED>
+// SCATTERED: the bucket's tuples come from an unstable partition (dense_scatter.cuh): bucket b holds `cursor[b]` tuples
+// at b * LS_CAP of the region arrays (in_hash / in_loc), in arbitrary order, and its output starts at start[b] (a scan of
+// the cursors).  The index in an item is then only an arrival number, so equal hashes are put in order by their loc in
+// the odd-even rounds (the loc gather of a tie: rare when hashes rarely repeat, which is when this path is taken).
+template <bool STEPPED, bool SCATTERED>
 __global__ void __launch_bounds__(LS_THREADS, 3)
 bucket_sort_bin_kernel(const uint64_t* __restrict__ in_hash, const uint64_t* __restrict__ in_loc,
                        uint64_t* __restrict__ out_hash, uint64_t* __restrict__ out_loc,
-                       const uint32_t* __restrict__ start, int lz, int tb, uint64_t* __restrict__ counts,
-                       uint32_t* __restrict__ t_size, CsrOut f) {
+                       const uint32_t* __restrict__ start, const uint32_t* __restrict__ cursor, int lz, int tb,
+                       uint64_t* __restrict__ counts, uint32_t* __restrict__ t_size, CsrOut f) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t* B = reinterpret_cast<uint64_t*>(smem_raw);            // [LS_CAP] items, grouped by bin
     uint32_t* cnt = reinterpret_cast<uint32_t*>(B + LS_CAP);        // [BN_BINS] counts, then exclusive offsets
@@ -515,8 +520,10 @@ bucket_sort_bin_kernel(const uint64_t* __restrict__ in_hash, const uint64_t* __r
     reinterpret_cast<uint4*>(cnt)[tid + LS_THREADS] = make_uint4(0, 0, 0, 0);
     __syncthreads();
     const uint32_t b = s_bucket;
-    const uint32_t s = start[b], e = start[b + 1];
-    const uint32_t m = e - s;
+    const uint32_t s = start[b];
+    const uint32_t s_in = SCATTERED ? b * (uint32_t)LS_CAP : s;
+    const uint32_t m = SCATTERED ? min(cursor[b], (uint32_t)LS_CAP) : start[b + 1] - s;  // (an overflowing region: the host
+                                                                                         // discards the build)
     if (m == 0) { if (tid == 0) counts[b] = 0; bucket_empty(b, f); return; }
     if (m > (uint32_t)LS_CAP) return;  // oversize: sorted and counted by the host-driven fallback
     const int sh = lz + tb;  // >= 12 on this path: the low 12 bits of (hash << sh) are zero and carry the index
@@ -530,7 +537,7 @@ bucket_sort_bin_kernel(const uint64_t* __restrict__ in_hash, const uint64_t* __r
     for (int r = 0; r < 8; r++) {
         const uint32_t j = r * LS_THREADS + tid;
         if (r * LS_THREADS >= m) break;  // uniform
-        if (j < m) item[r] = ((in_hash[s + j] << sh) & ~0xfffull) | j;
+        if (j < m) item[r] = ((in_hash[s_in + j] << sh) & ~0xfffull) | j;
     }
 #pragma unroll
     for (int r = 0; r < 8; r++) {
@@ -577,23 +584,68 @@ bucket_sort_bin_kernel(const uint64_t* __restrict__ in_hash, const uint64_t* __r
     {
         const uint32_t np0 = m >> 1, np1 = (m - 1) >> 1;  // pairs (2i, 2i+1) and (2i+1, 2i+2)
         ulonglong2* B2 = reinterpret_cast<ulonglong2*>(B);
+        // x belongs after y: by item; with arrival numbers instead of ordered indices, equal hashes by their loc
+        auto after = [&](uint64_t x, uint64_t y) -> bool {
+            if (!SCATTERED || ((x ^ y) >> 12)) return x > y;
+            return in_loc[s_in + (uint32_t)(x & 0xfffu)] > in_loc[s_in + (uint32_t)(y & 0xfffu)];
+        };
         int again;
         do {
             int sw = 0;
             for (uint32_t i = tid; i < np0; i += LS_THREADS) {
                 const ulonglong2 v = B2[i];
-                if (v.x > v.y) { B2[i] = make_ulonglong2(v.y, v.x); sw = 1; }
+                if (after(v.x, v.y)) { B2[i] = make_ulonglong2(v.y, v.x); sw = 1; }
             }
             __syncthreads();
             for (uint32_t i = tid; i < np1; i += LS_THREADS) {
                 const uint64_t x = B[2 * i + 1], y = B[2 * i + 2];
-                if (x > y) { B[2 * i + 1] = y; B[2 * i + 2] = x; sw = 1; }
+                if (after(x, y)) { B[2 * i + 1] = y; B[2 * i + 2] = x; sw = 1; }
             }
             again = __syncthreads_or(sw);
         } while (again);
     }
 
-    bucket_finish(B, cnt, m, s, b, lz, tb, in_loc, out_hash, out_loc, counts, t_size, f);
+    bucket_finish(B, cnt, m, s_in, s, b, lz, tb, in_loc, out_hash, out_loc, counts, t_size, f);
+}
+
+// scaled == 1: every complete window is a tuple; kept windows per protein straight from the offsets (the scattered
+// input has no (protein, pos)-ordered tuple array to search)
+__global__ void protein_windows_kernel(const uint64_t* __restrict__ offsets, uint32_t n_prot, uint32_t k,
+                                       uint32_t* __restrict__ t_abund, uint32_t* __restrict__ t_size) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_prot) return;
+    const uint64_t len = offsets[p + 1] - offsets[p];
+    const uint32_t w = len >= k ? (uint32_t)(len - k + 1) : 0u;
+    t_abund[p] = w;
+    t_size[p] = w;
+}
+
+// Second level of the unstable partition: DS_TILE-sized chunks of the first-level regions into the final buckets.
+__global__ void __launch_bounds__(DS_THREADS)
+pair_partition_kernel(const uint64_t* __restrict__ r1_hash, const uint64_t* __restrict__ r1_loc, const uint32_t* __restrict__ cursor1,
+                      uint32_t cap1, uint32_t nb1, const uint32_t* __restrict__ chunk_pfx, PairScatter sc) {
+    __shared__ DenseScatterSmem s_sc;
+    __shared__ uint64_t s_dk[DS_TILE], s_dv[DS_TILE];
+    const uint32_t c = blockIdx.x;
+    if (c >= chunk_pfx[nb1]) return;
+    uint32_t lo = 0, hi = nb1 - 1;  // last region whose first chunk is <= c
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi + 1) >> 1;
+        if (chunk_pfx[mid] <= c) lo = mid; else hi = mid - 1;
+    }
+    const uint32_t b1 = lo;
+    const uint32_t cnt = min(cursor1[b1], cap1);
+    const uint32_t first = (c - chunk_pfx[b1]) * DS_TILE;
+    const uint64_t base = (uint64_t)b1 * cap1 + first;
+    uint64_t key[DS_ITEMS], val[DS_ITEMS];
+    uint32_t valid = 0;
+#pragma unroll
+    for (int it = 0; it < DS_ITEMS; it++) {
+        const uint32_t i = it * DS_THREADS + threadIdx.x;
+        key[it] = val[it] = 0;
+        if (first + i < cnt) { key[it] = r1_hash[base + i]; val[it] = r1_loc[base + i]; valid |= 1u << it; }
+    }
+    scatter_pairs(key, valid, [&](int it) { return val[it]; }, sc, b1 << sc.bits, s_sc, s_dk, s_dv);
 }
 
 // Counts for ranges the bucket sort did not handle: oversize buckets (only_oversize = 1), or every range on the
@@ -832,6 +884,35 @@ cudaError_t expand_sorted_hash(const CsrView& v, uint64_t* hash, cudaStream_t st
     return cudaGetLastError();
 }
 
+PairSortPlan pair_sort_plan(uint64_t n, int end_bit, uint64_t max_hash) {
+    PairSortPlan p;
+    const int lz = 64 - end_bit;
+    const int tb = msd_top_bits(n, lz, max_hash);
+    if (tb < 0 || tb > 2 * DS_MAX_BITS) return p;
+    p.custom = 1;
+    p.total = tb;
+    p.l1 = tb < DS_MAX_BITS ? tb : DS_MAX_BITS;
+    p.l2 = tb - p.l1;
+    const double fill = lz >= 64 ? 1.0 : ((double)max_hash + 1.0) / std::ldexp(1.0, 64 - lz);  // used share of the bins
+    const double per1 = (double)n / (std::ldexp(1.0, p.l1) * fill);
+    p.cap1 = p.l2 ? (uint32_t)(per1 + per1 / 8 + 16384) : (uint32_t)LS_CAP;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+    p.off_r1_hash = take(((size_t)p.cap1 << p.l1) * 8);
+    p.off_r1_loc = take(((size_t)p.cap1 << p.l1) * 8);
+    p.off_r2_hash = p.l2 ? take(((size_t)LS_CAP << tb) * 8) : p.off_r1_hash;
+    p.off_r2_loc = p.l2 ? take(((size_t)LS_CAP << tb) * 8) : p.off_r1_loc;
+    p.off_small = off;
+    p.off_cursor1 = take(((size_t)1 << p.l1) * 4);
+    p.off_cursor2 = p.l2 ? take(((size_t)1 << tb) * 4) : p.off_cursor1;
+    p.off_overflow = take(8);
+    p.small_bytes = off - p.off_small;  // zeroed before the sketch kernel scatters into the regions
+    p.off_chunks = take(((size_t)1 << DS_MAX_BITS) * 4 + 4);
+    p.off_bstart = take((((size_t)1 << tb) + 1) * 4);
+    p.bytes = off;
+    return p;
+}
+
 size_t build_temp_bytes(uint64_t n, int end_bit) {
     size_t a = 0, b = 0;
     cub::DoubleBuffer<uint64_t> k(nullptr, nullptr), v(nullptr, nullptr);
@@ -848,6 +929,62 @@ cudaError_t build_index(const BuildArgs& a, cudaStream_t stream, int* out_in_a, 
     const int lz = 64 - a.end_bit;
     *out_in_a = 1;
     if (a.hash_written) *a.hash_written = 1;
+    if (a.overflowed) *a.overflowed = 0;
+    if (a.plan.custom && n) {
+        // scattered input: [second scatter level,] bucket offsets, bin kernel straight from the final buckets
+        const PairSortPlan& pl = a.plan;
+        char* w = (char*)a.work;
+        const uint32_t nb = 1u << pl.total;
+        uint32_t* cursor1 = (uint32_t*)(w + pl.off_cursor1);
+        uint32_t* cursor2 = (uint32_t*)(w + pl.off_cursor2);
+        uint32_t* overflow = (uint32_t*)(w + pl.off_overflow);
+        uint32_t* chunk_pfx = (uint32_t*)(w + pl.off_chunks);
+        uint32_t* bstart = (uint32_t*)(w + pl.off_bstart);
+        const uint64_t* r2h = (const uint64_t*)(w + pl.off_r2_hash);
+        const uint64_t* r2l = (const uint64_t*)(w + pl.off_r2_loc);
+        if (a.n_prot) protein_windows_kernel<<<(a.n_prot + 255) / 256, 256, 0, stream>>>(a.offsets, a.n_prot, a.k, a.t_abund, a.t_size);
+        if (pl.l2) {
+            dense_chunks_kernel<<<1, 256, 0, stream>>>(cursor1, 1u << pl.l1, pl.cap1, chunk_pfx);
+            PairScatter sc;
+            sc.out_key = (uint64_t*)(w + pl.off_r2_hash); sc.out_val = (uint64_t*)(w + pl.off_r2_loc); sc.cursor = cursor2;
+            sc.cap = (uint32_t)LS_CAP; sc.shift = 64 - pl.total; sc.bits = pl.l2; sc.lz = lz; sc.overflow = overflow;
+            const unsigned grid = (unsigned)(n / DS_TILE + (1u << pl.l1) + 1);
+            pair_partition_kernel<<<grid, DS_THREADS, 0, stream>>>((const uint64_t*)(w + pl.off_r1_hash), (const uint64_t*)(w + pl.off_r1_loc),
+                                                                  cursor1, pl.cap1, 1u << pl.l1, chunk_pfx, sc);
+            KS_TRY(cudaGetLastError());
+        }
+        dense_bucket_offsets_kernel<<<1, 1024, 0, stream>>>(cursor2, nb, (uint32_t)LS_CAP, bstart);
+        if (a.ev_partitioned) KS_TRY(cudaEventRecord(a.ev_partitioned, stream));
+        // tables of the bucket sort (oversize word stays 0: the CSR write is always fused here)
+        char* tp = (char*)a.temp;
+        uint32_t* oversize = (uint32_t*)tp + nb + 1;
+        uint64_t* counts = (uint64_t*)(tp + (((size_t)(nb + 8) * 4 + 7) & ~(size_t)7));
+        uint64_t* status = counts + 2 * (size_t)nb + 1;
+        uint32_t* ticket = (uint32_t*)(status + nb);
+        KS_TRY(cudaMemsetAsync(oversize, 0, 8, stream));
+        KS_TRY(cudaMemsetAsync(status, 0, (size_t)nb * 8 + 8, stream));
+        CsrOut f;
+        f.status = status; f.ticket = ticket; f.oversize = oversize; f.keys = a.keys; f.key_grp = a.key_grp; f.grp_start = a.grp_start;
+        f.d_counts = a.d_counts; f.n = n; f.nb = nb;
+        f.dir = a.dir; f.dir_bits = a.dir_bits; f.dir_sub = a.dir_bits >= pl.total ? a.dir_bits - pl.total : -1;
+        KS_TRY(cudaFuncSetAttribute(bucket_sort_bin_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BN_SMEM));
+        bucket_sort_bin_kernel<false, true><<<nb, LS_THREADS, BN_SMEM, stream>>>(r2h, r2l, a.hash_b, a.loc_a, bstart, cursor2, lz, pl.total,
+                                                                                 counts, a.t_size, f);
+        KS_TRY(cudaGetLastError());
+        *sort_launches += pl.l2 ? 5 : 3;
+        if (a.ev_sorted) KS_TRY(cudaEventRecord(a.ev_sorted, stream));
+        if (f.dir_sub < 0) {
+            dir_kernel<<<148 * 8, 256, 0, stream>>>(a.keys, a.d_counts, a.dir, a.dir_bits, a.dir_shift);
+            *csr_launches += 1;
+        }
+        uint32_t ovf = 0;
+        KS_TRY(cudaMemcpyAsync(&ovf, overflow, 4, cudaMemcpyDeviceToHost, stream));
+        KS_TRY(cudaStreamSynchronize(stream));
+        if (a.overflowed) *a.overflowed = ovf ? 1 : 0;
+        if (a.hash_written) *a.hash_written = 0;
+        *out_in_a = 1;
+        return cudaGetLastError();
+    }
     if (a.n_prot) {
         protein_abund_kernel<<<(a.n_prot + 255) / 256, 256, 0, stream>>>(a.loc_a, n, a.n_prot, a.t_abund, a.t_size);
         KS_TRY(cudaGetLastError());
@@ -912,11 +1049,11 @@ cudaError_t build_index(const BuildArgs& a, cudaStream_t stream, int* out_in_a, 
         const char* v_env = getenv("KS_LS_VARIANT");
         const bool bin = v_env ? (v_env[0] == 'b') : (a.repeat_heavy == 0);
         if (bin) {
-            KS_TRY(cudaFuncSetAttribute(bucket_sort_bin_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BN_SMEM));
-            KS_TRY(cudaFuncSetAttribute(bucket_sort_bin_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BN_SMEM));
+            KS_TRY(cudaFuncSetAttribute(bucket_sort_bin_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BN_SMEM));
+            KS_TRY(cudaFuncSetAttribute(bucket_sort_bin_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BN_SMEM));
             const bool stepped = v_env && v_env[1] == 's';
-            if (stepped) bucket_sort_bin_kernel<true><<<nb, LS_THREADS, BN_SMEM, stream>>>(sh, sl, dh, dl, start, lz, tb, counts, a.t_size, f);
-            else bucket_sort_bin_kernel<false><<<nb, LS_THREADS, BN_SMEM, stream>>>(sh, sl, dh, dl, start, lz, tb, counts, a.t_size, f);
+            if (stepped) bucket_sort_bin_kernel<true, false><<<nb, LS_THREADS, BN_SMEM, stream>>>(sh, sl, dh, dl, start, nullptr, lz, tb, counts, a.t_size, f);
+            else bucket_sort_bin_kernel<false, false><<<nb, LS_THREADS, BN_SMEM, stream>>>(sh, sl, dh, dl, start, nullptr, lz, tb, counts, a.t_size, f);
         } else {
             KS_TRY(cudaFuncSetAttribute(bucket_sort_rep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LS_SMEM_REP));
             bucket_sort_rep_kernel<<<nb, LS_THREADS, LS_SMEM_REP, stream>>>(sh, sl, dh, dl, start, lz, tb, counts, a.t_size, f);

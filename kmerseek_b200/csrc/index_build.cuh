@@ -31,7 +31,27 @@ struct CsrView {
     int dir_shift;
 };
 
+// Plan of the unstable partition of the general path (dense_scatter.cuh): the top `total` = l1 + l2 bits of the normalised
+// hash pick one of 2^total buckets of at most 4096 tuples; the first level is fused into the sketch kernel.  custom == 0:
+// the input does not fit (fewer than 2^16 tuples, more than 16 bucket bits) and the stable library partition is used.
+struct PairSortPlan {
+    int custom = 0;
+    int l1 = 0, l2 = 0, total = 0;
+    uint32_t cap1 = 0;  // tuples per first-level region
+    // carve of the work buffer
+    size_t off_r1_hash = 0, off_r1_loc = 0, off_r2_hash = 0, off_r2_loc = 0, off_small = 0, small_bytes = 0;
+    size_t off_cursor1 = 0, off_cursor2 = 0, off_overflow = 0, off_chunks = 0, off_bstart = 0, bytes = 0;
+};
+PairSortPlan pair_sort_plan(uint64_t n, int end_bit, uint64_t max_hash);
+
 struct BuildArgs {
+    // scattered input (plan.custom): the sketch kernel has put the tuples into the first-level regions of `work`; the
+    // postings are written to loc_a.  Needs scaled == 1 (kept windows per protein come from the offsets).
+    PairSortPlan plan;
+    void* work = nullptr;
+    const uint64_t* offsets = nullptr;  // device, n_prot + 1
+    uint32_t k = 0;
+    int* overflowed = nullptr;          // out (host): a region overflowed, the build must be redone from ordered tuples
     // tuples in (protein, pos) order in the `a` pair; `b` is scratch of the same size.
     uint64_t *hash_a, *loc_a, *hash_b, *loc_b;
     uint64_t n;

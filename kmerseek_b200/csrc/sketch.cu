@@ -377,8 +377,8 @@ __device__ __forceinline__ uint32_t stage_addr(uint32_t slot) { return (slot & 3
 
 // FULL (max_hash = 2^64 - 1, i.e. scaled == 1): tile bases come from tile_count_kernel + scan, so there is no
 // ticket, no look-back chain and no cross-CTA dependency at all.
-template <int K, bool TRANSLATE, bool FULL>
-__global__ void __launch_bounds__(SK_THREADS)
+template <int K, bool TRANSLATE, bool FULL, bool SCATTER>
+__global__ void __launch_bounds__(SK_THREADS, SCATTER ? 5 : 1)
 sketch_quad_kernel(SketchArgs a, Lut256 lut, uint32_t* __restrict__ ticket, uint64_t* __restrict__ status,
                    const uint32_t* __restrict__ tile_pid, const uint64_t* __restrict__ tile_base) {
     constexpr int RES_WORDS = (SK_TILE + K + 16 + 3) / 4;
@@ -544,6 +544,26 @@ sketch_quad_kernel(SketchArgs a, Lut256 lut, uint32_t* __restrict__ ticket, uint
         const uint32_t t = s_wtot[i];
         if (i < (int)warp) wprefix += t;
         btotal += t;
+    }
+    if (SCATTER) {
+        // unordered output: the tile's tuples go straight into the first-level regions of the partition -- no tile base,
+        // and on the look-back path no look-back either (the total is all that is left to collect)
+        static_assert(DS_THREADS == SK_THREADS && DS_TILE == SK_TILE, "one scatter tile per sketch tile");
+        __shared__ DenseScatterSmem s_sc;
+        if (tid == 0) {
+            if (FULL) { if (tile == n_tiles - 1) *a.d_count = tile_base[tile] + btotal; }
+            else if (btotal) atomicAdd(reinterpret_cast<unsigned long long*>(a.d_count), (unsigned long long)btotal);
+        }
+        uint64_t key[DS_ITEMS];
+        uint32_t valid = 0;
+#pragma unroll
+        for (int it = 0; it < DS_ITEMS; it++) {
+            const uint32_t i = it * SK_THREADS + tid;  // slot: warp region i >> 8, offset i & 255
+            key[it] = s_hash[stage_addr(i)];
+            valid |= ((i & 255u) < s_wtot[i >> 8] ? 1u : 0u) << it;
+        }
+        scatter_pairs(key, valid, [&](int it) { return s_loc[stage_addr(it * SK_THREADS + tid)]; }, a.scatter, 0, s_sc, s_hash, s_loc);
+        return;
     }
     uint64_t base;
     if (FULL) {
@@ -849,13 +869,17 @@ cudaError_t launch_k(const SketchArgs& a, const Lut256& lut, const Workspace& w,
             sketch_kernel<0, true><<<grid, SK_THREADS, 0, st>>>(a, lut, w.ticket, w.status, w.tile_pid);
     } else {
         const bool full = a.max_hash == ~0ull && !a.force_general;
+        const bool sc = a.scatter.out_key != nullptr;
+#define KS_LAUNCH_QUAD(T, F, S) \
+    sketch_quad_kernel<K, T, F, S><<<grid, SK_THREADS, 0, st>>>(a, lut, w.ticket, w.status, w.tile_pid, w.tile_base)
         if (a.moltype == 0) {
-            if (full) sketch_quad_kernel<K, false, true><<<grid, SK_THREADS, 0, st>>>(a, lut, w.ticket, w.status, w.tile_pid, w.tile_base);
-            else sketch_quad_kernel<K, false, false><<<grid, SK_THREADS, 0, st>>>(a, lut, w.ticket, w.status, w.tile_pid, w.tile_base);
+            if (full) { if (sc) KS_LAUNCH_QUAD(false, true, true); else KS_LAUNCH_QUAD(false, true, false); }
+            else { if (sc) KS_LAUNCH_QUAD(false, false, true); else KS_LAUNCH_QUAD(false, false, false); }
         } else {
-            if (full) sketch_quad_kernel<K, true, true><<<grid, SK_THREADS, 0, st>>>(a, lut, w.ticket, w.status, w.tile_pid, w.tile_base);
-            else sketch_quad_kernel<K, true, false><<<grid, SK_THREADS, 0, st>>>(a, lut, w.ticket, w.status, w.tile_pid, w.tile_base);
+            if (full) { if (sc) KS_LAUNCH_QUAD(true, true, true); else KS_LAUNCH_QUAD(true, true, false); }
+            else { if (sc) KS_LAUNCH_QUAD(true, false, true); else KS_LAUNCH_QUAD(true, false, false); }
         }
+#undef KS_LAUNCH_QUAD
     }
     return cudaGetLastError();
 }
@@ -940,6 +964,10 @@ cudaError_t launch_sketch_prepare(const SketchArgs& a, cudaStream_t stream, uint
     const bool exact = exact_path(a);
     cudaError_t e = cudaMemsetAsync(a.workspace, 0, exact ? 16 : 16 + nt * 8, stream);
     if (e != cudaSuccess) return e;
+    if (a.scatter.out_key != nullptr && !exact) {  // the tiles add their totals up
+        e = cudaMemsetAsync(a.d_count, 0, 8, stream);
+        if (e != cudaSuccess) return e;
+    }
     tile_pid_kernel<<<(unsigned)((nt + 1 + 255) / 256), 256, 0, stream>>>(a.offsets, a.n_prot, nt, w.tile_pid);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;

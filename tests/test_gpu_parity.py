@@ -468,6 +468,31 @@ def test_dense_path_two_scatter_levels(K, O):
     _csr_equals_oracle(K, O, res2, offs2, 24, "hp", path=0)
 
 
+def test_unstable_partition_of_the_general_path(K, O, monkeypatch):
+    """Hashes that rarely repeat, scaled == 1, one batch: the sketch kernel scatters the tuples straight into the
+    first-level regions of an unstable partition, a second level follows, and the bin kernel orders equal hashes by
+    their loc (build_path 3).  Checked on a proteome with thousands of duplicated proteins (equal hashes at different
+    positions, arriving in arbitrary order) at a size that needs both scatter levels, against the stable path and the
+    oracle; a k-mer repeated tens of thousands of times overflows a region and must come out of the stable path."""
+    from kmerseek_b200 import synth
+    res, offs = synth.proteome(14_000_000, 808)
+    # duplicate 3 000 proteins twice each (paralogs): every k-mer of theirs occurs three times
+    lens = np.diff(offs.astype(np.int64))
+    pick = np.arange(1000, 4000)
+    dup = np.concatenate([res[int(offs[p]):int(offs[p + 1])] for p in pick])
+    res2 = np.concatenate([res, dup, dup])
+    offs2 = np.concatenate([offs, offs[-1] + np.cumsum(np.tile(lens[pick], 2)).astype(np.uint64)])
+    for k, moltype in ((16, "dayhoff"), (7, "protein")):
+        st = _csr_equals_oracle(K, O, res2, offs2, k, moltype, path=3)
+        assert st["n_unique_hashes"] < st["n_tuples"]
+    rep = np.frombuffer(("ACDEFGHIKLMNPQRSTVWY" * 3000).encode(), dtype=np.uint8)  # 20 k-mers, 3 000 times each
+    res3 = np.concatenate([res, rep])
+    offs3 = np.concatenate([offs, [offs[-1] + len(rep)]]).astype(np.uint64)
+    _csr_equals_oracle(K, O, res3, offs3, 16, "dayhoff", path=0)
+    monkeypatch.setenv("KS_SCATTER", "0")
+    _csr_equals_oracle(K, O, res2, offs2, 16, "dayhoff", path=0)
+
+
 def test_general_sketch_path_at_scaled_1(K, O, monkeypatch):
     """scaled == 1 normally takes the chain-free exact path; the look-back path must give the same tuples
     (it is what a batch is redone on if a hash of exactly 0 ever shows up)."""
@@ -485,6 +510,8 @@ def test_bucket_sort_both_variants(K, O, monkeypatch, variant):
     repeat-heavy); every variant must give the same index on both kinds of data."""
     from kmerseek_b200 import synth
     monkeypatch.setenv("KS_LS_VARIANT", variant)
+    monkeypatch.setenv("KS_DENSE", "0")    # the stable partition + bucket sort of the general path is what is under test
+    monkeypatch.setenv("KS_SCATTER", "0")
     res, offs = synth.proteome(14_000_000, 2024)
     prot = K.Proteome.from_packed(res, offs)
     for k, moltype in ((24, "hp"), (16, "dayhoff")):
