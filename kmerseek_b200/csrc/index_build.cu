@@ -112,15 +112,10 @@ struct CsrOut {
     int dir_bits, dir_sub;
 };
 
-// dir[x] = index of the first key whose directory bucket is >= x.  The key with index u and directory bucket x1, whose
-// predecessor (in this sort bucket) sits in x0, owns the entries (x0, x1].
-__device__ __forceinline__ void dir_fill(const CsrOut& f, int64_t x0, int64_t x1, uint32_t u) {
-    for (int64_t x = x0 + 1; x <= x1; x++) f.dir[x] = u;
-}
-// entries after the last key of sort bucket b (and the sentinel after the last bucket) = keys up to and including b
-__device__ __forceinline__ void dir_tail(const CsrOut& f, uint32_t b, int64_t x_last, uint32_t u_end) {
-    const int64_t end = ((int64_t)(b + 1) << f.dir_sub) - (b == f.nb - 1 ? 0 : 1);
-    dir_fill(f, x_last, end, u_end);
+// dir[x] = index of the first key whose directory bucket is >= x.  Inside a sort bucket (2^dir_sub consecutive entries,
+// `dir_b`) the key with index u whose item has the local entry x1, and whose predecessor has x0, owns the entries (x0, x1].
+__device__ __forceinline__ void dir_fill(uint32_t* dir_b, int32_t x0, int32_t x1, uint32_t u) {
+    for (int32_t x = x0 + 1; x <= x1; x++) dir_b[x] = u;
 }
 
 __device__ __forceinline__ void csr_totals(const CsrOut& f, uint64_t incl) {
@@ -235,6 +230,8 @@ __device__ __forceinline__ void bucket_finish(const uint64_t* items, uint32_t* s
     __syncthreads();
     if (s_base == ~0ull) return;  // an oversize bucket exists: the CSR is written by csr_write_kernel after the fallback
     const uint32_t base_k = (uint32_t)(s_base & 0x7fffffffu), base_g = (uint32_t)(s_base >> 31);
+    uint32_t* dir_b = f.dir_sub >= 0 ? f.dir + ((uint64_t)b << f.dir_sub) : nullptr;
+    auto dir_local = [&](uint64_t item) -> uint32_t { return f.dir_sub > 0 ? (uint32_t)(item >> (64 - f.dir_sub)) : 0u; };
 #pragma unroll
     for (int r = 0; r < 8; r++) {
         if (r * LS_THREADS < m) {  // uniform
@@ -249,12 +246,11 @@ __device__ __forceinline__ void bucket_finish(const uint64_t* items, uint32_t* s
                 const uint64_t full = top | ((items[j] & ~0xfffull) >> tb);
                 f.keys[u] = full >> lz;
                 f.key_grp[u] = g;
-                if (f.dir_sub >= 0)
-                    dir_fill(f, j ? (int64_t)((top | ((items[j - 1] & ~0xfffull) >> tb)) >> (64 - f.dir_bits)) : ((int64_t)b << f.dir_sub) - 1,
-                             (int64_t)(full >> (64 - f.dir_bits)), u);
+                // directory entries this key owns: the bucket's 2^dir_sub entries are indexed by the item's top dir_sub bits
+                if (f.dir_sub >= 0) dir_fill(dir_b, j ? (int32_t)dir_local(items[j - 1]) : -1, (int32_t)dir_local(items[j]), u);
             }
-            if (j == m - 1 && f.dir_sub >= 0)
-                dir_tail(f, b, (int64_t)((top | ((items[j] & ~0xfffull) >> tb)) >> (64 - f.dir_bits)), base_k + s_tk);
+            if (j == m - 1 && f.dir_sub >= 0)  // entries after the last key (and the sentinel after the last bucket)
+                dir_fill(dir_b, (int32_t)dir_local(items[j]), (int32_t)(1u << f.dir_sub) - (b == f.nb - 1 ? 0 : 1), base_k + s_tk);
         }
     }
 }
