@@ -30,6 +30,8 @@ sys.path.insert(0, ROOT)
 WORKLOADS = {
     # BASELINE.json configs[1]: Swiss-Prot-sized index build, hp k=24 scaled=1 (the config the metric is quoted on)
     "c2_swissprot_hp_k24_s1": dict(n_residues=200_000_000, k=24, moltype="hp", scaled=1, seed=20260102),
+    # BASELINE.json configs[2] on one GPU: 10 000 planted query domains against the C2-sized proteome, dayhoff k=16
+    "c3_search_dayhoff_k16_s1": dict(n_residues=200_000_000, k=16, moltype="dayhoff", scaled=1, seed=20260102),
     # the north_star target run
     "target_100m_dayhoff_k16_s1": dict(n_residues=100_000_000, k=16, moltype="dayhoff", scaled=1, seed=20260103),
     "c4_slice_protein_k7_s10": dict(n_residues=1_000_000_000, k=7, moltype="protein", scaled=10, seed=20260104),
