@@ -842,8 +842,9 @@ void finalize(ks_index* x) {
     x->grp_start = x->b_grp_start.ensure<uint32_t>(ar, n + 1);
     x->dir = x->b_dir.ensure<uint32_t>(ar, (1ull << bits) + 1);
     x->d_counts = x->b_counts.ensure<uint64_t>(ar, 2);
-    uint64_t* hb = x->b_alt_hash.ensure<uint64_t>(ar, n);
-    uint64_t* lb = x->b_alt_loc.ensure<uint64_t>(ar, n);
+    // the second tuple pair is the sort's ping-pong partner; a scattered batch has its regions instead
+    uint64_t* hb = x->scattered ? nullptr : x->b_alt_hash.ensure<uint64_t>(ar, n);
+    uint64_t* lb = x->scattered ? nullptr : x->b_alt_loc.ensure<uint64_t>(ar, n);
     BuildArgs a;
     a.hash_a = x->d_hash; a.loc_a = x->d_loc; a.hash_b = hb; a.loc_b = lb;
     a.n = n; a.n_prot = P; a.end_bit = x->end_bit(); a.max_hash = x->max_hash;
