@@ -189,3 +189,30 @@ def test_synth_generator_is_deterministic_and_shaped():
     assert set(np.unique(r1)) <= set(b"ACDEFGHIKLMNPQRSTVWY")
     q, qo, src = synth.queries(r1, o1, 50, 78)
     assert len(qo) == 51 and qo[-1] == len(q) and (np.diff(qo.astype(np.int64)) >= 30).all()
+
+
+def test_ctypes_mirrors_match_the_header(tmp_path):
+    """The ctypes structures of kmerseek_b200/_ffi.py must have the size and field offsets of the C structs in
+    include/kmerseek_b200.h (compiled here with gcc: the header is plain C)."""
+    import ctypes as C
+    import shutil
+    import subprocess
+    from kmerseek_b200 import _ffi
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    structs = {"ks_stats": _ffi.ks_stats, "ks_sketch": _ffi.ks_sketch, "ks_csr": _ffi.ks_csr, "ks_params": _ffi.ks_params}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "kmerseek_b200.h"', 'int main(void) {']
+    for name, cls in structs.items():
+        lines.append(f'  printf("{name} %zu\\n", sizeof({name}));')
+        for field, _ in cls._fields_:
+            lines.append(f'  printf("{name}.{field} %zu\\n", offsetof({name}, {field}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = dict(l.split() for l in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    for name, cls in structs.items():
+        assert int(out[name]) == C.sizeof(cls), name
+        for field, _ in cls._fields_:
+            assert int(out[f"{name}.{field}"]) == getattr(cls, field).offset, f"{name}.{field}"
