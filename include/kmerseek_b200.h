@@ -168,8 +168,8 @@ typedef struct ks_stats {
     uint32_t finalized;
     uint32_t build_path;     /* how the last finalize built the index: 0 general (hash tuples, partition + bucket sort),
                                 1 dense k-mer space (hp, 8 <= k <= 24, scaled 1: rank keys), 2 the same with the keys
-                                sorted by the library, 3 general with the unstable two-level partition (hashes that
-                                rarely repeat, scaled 1) */
+                                sorted by the library, 3 general with the unstable two-level partition (one batch of
+                                hashes that rarely repeat) */
 } ks_stats;
 /* Synchronises the handle's stream. */
 ks_status ks_index_stats(ks_index *idx, ks_stats *out);

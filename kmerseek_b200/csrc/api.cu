@@ -458,15 +458,17 @@ bool repeat_heavy(const ks_index* x, uint64_t n) {
 }
 
 // Unstable partition of the general path (dense_scatter.cuh, PairSortPlan): the batch is the index's only content, hashes
-// rarely repeat (the bucket sort orders equal hashes by loc, pair by pair), scaled == 1 (kept windows per protein come
-// from the offsets) and the tuple count fits two scatter levels.  KS_SCATTER=0 switches it off (test hook).
+// rarely repeat (the bucket sort orders equal hashes by loc, pair by pair) and the tuple count fits two scatter levels.  KS_SCATTER=0 switches it off (test hook).
 bool scatter_eligible(const ks_index* x, const DeviceBatch& b, uint64_t n_prot_before, uint64_t n_tuples_before, PairSortPlan* plan) {
     const char* env = getenv("KS_SCATTER");
     if (env && env[0] == '0') return false;
-    if (x->max_hash != ~0ull || x->params.ksize > (uint32_t)SK_MAX_TEMPLATE_K || getenv("KS_SKETCH_GENERAL")) return false;
+    if (x->params.ksize > (uint32_t)SK_MAX_TEMPLATE_K || getenv("KS_SKETCH_GENERAL")) return false;
     if (n_prot_before || n_tuples_before || b.n_prot == 0 || b.n_windows > MAX_TUPLES) return false;
-    if (repeat_heavy(x, b.n_windows)) return false;
-    *plan = pair_sort_plan(b.n_windows, x->end_bit(), x->max_hash);
+    const uint64_t n_est = expected_kept(x, b.n_windows);  // exact for scaled == 1
+    // measured: with hashes that repeat the stable path wins -- the C4 slice (protein k7 scaled 10, every hash twice on
+    // average) takes 4.5 ms in the bin kernel with loc tie-breaks against 2.8 ms in the two-pass stable bucket sort
+    if (repeat_heavy(x, n_est)) return false;
+    *plan = pair_sort_plan(n_est, x->end_bit(), x->max_hash);
     return plan->custom != 0;
 }
 
@@ -481,12 +483,17 @@ void scatter_args(ks_index* x, SketchArgs* a) {
     a->scatter.bits = pl.l1;
     a->scatter.lz = x->lz;
     a->scatter.overflow = (uint32_t*)(w + pl.off_overflow);
+    a->t_abund = x->max_hash != ~0ull ? x->t_abund : nullptr;
 }
 
-void scatter_begin(ks_index* x, const PairSortPlan& plan) {
+void scatter_begin(ks_index* x, const PairSortPlan& plan, uint64_t n_prot) {
     x->pair_plan = plan;
     char* w = x->b_pair_work.ensure<char>(x->arena, plan.bytes);
     KS_CUDA(cudaMemsetAsync(w + plan.off_small, 0, plan.small_bytes, x->stream));
+    if (x->max_hash != ~0ull) {  // scaled > 1: the sketch kernel counts the kept windows per protein
+        x->t_abund = x->b_t_abund.ensure<uint32_t>(x->arena, n_prot);
+        KS_CUDA(cudaMemsetAsync(x->t_abund, 0, n_prot * 4, x->stream));
+    }
 }
 
 void sketch_resident(ks_index* x) {
@@ -501,7 +508,7 @@ void sketch_resident(ks_index* x) {
     }
     PairSortPlan plan;
     if (scatter_eligible(x, b, x->n_prot, x->n_tuples, &plan)) {
-        scatter_begin(x, plan);
+        scatter_begin(x, plan, b.n_prot);
         ensure_ws(x, sketch_workspace_bytes(b.n_res));
         SketchArgs a;
         a.residues = b.res; a.packed = b.packed ? 1 : 0; a.offsets = b.offs; a.n_res = b.n_res; a.n_prot = b.n_prot;
@@ -516,12 +523,13 @@ void sketch_resident(ks_index* x) {
         KS_CUDA(cudaMemcpyAsync(r, x->d_count, 16, cudaMemcpyDeviceToHost, x->stream));
         KS_CUDA(cudaStreamSynchronize(x->stream));
         x->t_sketch = true;
-        if ((r[1] >> 32) == 0 && r[0] == b.n_windows) {
+        const bool exact = x->max_hash == ~0ull;
+        if (exact ? ((r[1] >> 32) == 0 && r[0] == b.n_windows) : r[0] <= MAX_TUPLES) {
             x->scattered = true;
-            x->n_tuples = b.n_windows; x->n_prot = b.n_prot; x->n_res = b.n_res; x->n_windows = b.n_windows;
+            x->n_tuples = r[0]; x->n_prot = b.n_prot; x->n_res = b.n_res; x->n_windows = b.n_windows;
             return;
         }
-        // a zero hash (it must be dropped): the ordered path below
+        // a zero hash on the exact path (it must be dropped): the ordered path below
     }
     sketch_resident_general(x);
 }
@@ -591,7 +599,7 @@ bool add_proteome_pipelined(ks_index* x, const ks_proteome* p) {
     b.max_len = max_protein_len(p->offsets, p->n_prot);
     b.valid = true;
     if (!dense && !scat) grow_tuples(x, x->n_tuples + expected_kept(x, b.n_windows));
-    if (scat) scatter_begin(x, scat_plan);
+    if (scat) scatter_begin(x, scat_plan, p->n_prot);
     ensure_ws(x, sketch_workspace_bytes(b.n_res));
     KS_CUDA(cudaEventRecord(x->ev[EV_UP0], x->stream));
     KS_CUDA(cudaEventRecord(x->ev[EV_SK0], x->stream));
@@ -646,12 +654,13 @@ bool add_proteome_pipelined(ks_index* x, const ks_proteome* p) {
     // a zero hash on the exact path, or more tuples than the estimate for scaled > 1 allowed for: redo the batch (now
     // resident) through the plain path, which takes the look-back kernel / grows the buffer as needed
     if (scat) {
-        if ((r[1] >> 32) != 0 || r[0] != b.n_windows) {  // a zero hash: the ordered path
+        const bool exact = x->max_hash == ~0ull;
+        if (exact ? ((r[1] >> 32) != 0 || r[0] != b.n_windows) : r[0] > MAX_TUPLES) {  // a zero hash: the ordered path
             sketch_resident_general(x);
             return true;
         }
         x->scattered = true;
-        x->n_tuples = b.n_windows; x->n_prot = b.n_prot; x->n_res = b.n_res; x->n_windows = b.n_windows;
+        x->n_tuples = r[0]; x->n_prot = b.n_prot; x->n_res = b.n_res; x->n_windows = b.n_windows;
         return true;
     }
     if ((r[1] >> 32) != 0 || r[0] > x->cap - x->n_tuples) {
@@ -857,6 +866,7 @@ void finalize(ks_index* x) {
         a.loc_a = x->d_loc; a.hash_a = x->d_hash;
         a.plan = x->pair_plan; a.work = x->b_pair_work.p; a.offsets = x->batch.offs; a.k = x->params.ksize;
         a.overflowed = &overflowed;
+        a.abund_ready = x->max_hash != ~0ull ? 1 : 0;
     }
     a.keys = x->keys; a.key_grp = x->key_grp; a.grp_start = x->grp_start; a.t_size = x->t_size; a.t_abund = x->t_abund;
     a.d_counts = x->d_counts; a.dir = x->dir; a.dir_bits = x->dir_bits; a.dir_shift = x->dir_shift;

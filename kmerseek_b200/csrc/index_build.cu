@@ -938,7 +938,12 @@ cudaError_t build_index(const BuildArgs& a, cudaStream_t stream, int* out_in_a, 
         uint32_t* bstart = (uint32_t*)(w + pl.off_bstart);
         const uint64_t* r2h = (const uint64_t*)(w + pl.off_r2_hash);
         const uint64_t* r2l = (const uint64_t*)(w + pl.off_r2_loc);
-        if (a.n_prot) protein_windows_kernel<<<(a.n_prot + 255) / 256, 256, 0, stream>>>(a.offsets, a.n_prot, a.k, a.t_abund, a.t_size);
+        if (a.n_prot) {
+            if (a.abund_ready)  // distinct hashes per protein start from the kept windows the sketch kernel counted
+                KS_TRY(cudaMemcpyAsync(a.t_size, a.t_abund, (size_t)a.n_prot * 4, cudaMemcpyDeviceToDevice, stream));
+            else
+                protein_windows_kernel<<<(a.n_prot + 255) / 256, 256, 0, stream>>>(a.offsets, a.n_prot, a.k, a.t_abund, a.t_size);
+        }
         if (pl.l2) {
             dense_chunks_kernel<<<1, 256, 0, stream>>>(cursor1, 1u << pl.l1, pl.cap1, chunk_pfx);
             PairScatter sc;

@@ -46,12 +46,13 @@ PairSortPlan pair_sort_plan(uint64_t n, int end_bit, uint64_t max_hash);
 
 struct BuildArgs {
     // scattered input (plan.custom): the sketch kernel has put the tuples into the first-level regions of `work`; the
-    // postings are written to loc_a.  Needs scaled == 1 (kept windows per protein come from the offsets).
+    // postings are written to loc_a.
     PairSortPlan plan;
     void* work = nullptr;
     const uint64_t* offsets = nullptr;  // device, n_prot + 1
     uint32_t k = 0;
     int* overflowed = nullptr;          // out (host): a region overflowed, the build must be redone from ordered tuples
+    int abund_ready = 0;                // t_abund was filled by the sketch kernel (scaled > 1); else it comes from the offsets
     // tuples in (protein, pos) order in the `a` pair; `b` is scratch of the same size.
     uint64_t *hash_a, *loc_a, *hash_b, *loc_b;
     uint64_t n;

@@ -392,8 +392,11 @@ sketch_quad_kernel(SketchArgs a, Lut256 lut, uint32_t* __restrict__ ticket, uint
     __shared__ uint32_t s_wtot[SK_THREADS / 32];
     __shared__ uint32_t s_tile;
     __shared__ uint64_t s_base;
+    constexpr bool COUNT_ABUND = SCATTER && !FULL;  // kept windows per protein, counted per tile in shared memory
+    __shared__ uint32_t s_pcnt[COUNT_ABUND ? OFFS_CACHE : 1];
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (COUNT_ABUND) s_pcnt[tid] = 0;  // OFFS_CACHE == SK_THREADS; ordered before the first count by the barriers below
     if (!FULL && tid == 0) s_tile = atomicAdd(ticket, 1u);
     if (TRANSLATE) s_lut[tid] = lut.b[tid];
     if (!FULL || TRANSLATE) __syncthreads();
@@ -511,6 +514,10 @@ sketch_quad_kernel(SketchArgs a, Lut256 lut, uint32_t* __restrict__ ticket, uint
                 zero_seen |= valid && h[j] == 0;
             } else {
                 keep[j] = valid && h[j] != 0 && h[j] <= a.max_hash;
+                if (COUNT_ABUND && keep[j]) {
+                    if (cached) atomicAdd(&s_pcnt[p - p_lo], 1u);
+                    else atomicAdd(&a.t_abund[p], 1u);  // a tile of more than 254 tiny proteins
+                }
             }
             loc[j] = ((uint64_t)(a.pid_base + p) << 32) | (uint64_t)(g0_lo + w - pstart_lo);
         }
@@ -549,7 +556,12 @@ sketch_quad_kernel(SketchArgs a, Lut256 lut, uint32_t* __restrict__ ticket, uint
         // unordered output: the tile's tuples go straight into the first-level regions of the partition -- no tile base,
         // and on the look-back path no look-back either (the total is all that is left to collect)
         static_assert(DS_THREADS == SK_THREADS && DS_TILE == SK_TILE, "one scatter tile per sketch tile");
+        static_assert(OFFS_CACHE == SK_THREADS, "one protein counter per thread");
         __shared__ DenseScatterSmem s_sc;
+        if (COUNT_ABUND && cached && tid < n_off - 1) {  // (the barrier after s_wtot ordered the counts before this read)
+            const uint32_t c = s_pcnt[tid];
+            if (c) atomicAdd(&a.t_abund[p_lo + tid], c);
+        }
         if (tid == 0) {
             if (FULL) { if (tile == n_tiles - 1) *a.d_count = tile_base[tile] + btotal; }
             else if (btotal) atomicAdd(reinterpret_cast<unsigned long long*>(a.d_count), (unsigned long long)btotal);

@@ -34,6 +34,8 @@ struct SketchArgs {
     PairScatter scatter{};     // scatter.out_key != nullptr: the tuples leave the kernel partitioned by the top bits of the
                                // hash (first level of an unstable partition, dense_scatter.cuh) instead of in (protein,
                                // pos) order; out_hash / out_loc / capacity are not used, d_count[0] still gets the total
+    uint32_t* t_abund = nullptr;  // scatter mode with scaled > 1: kept windows per protein are counted here (device, n_prot,
+                                  // zeroed by the caller): there is no (protein, pos)-ordered tuple array to count them from
     int force_general;         // 1: take the look-back path even when scaled == 1
     uint32_t tile_begin = 0, tile_end = 0;  // exact path: launch_sketch_tiles covers [tile_begin, tile_end); 0,0 = all
     void* workspace;           // sketch_workspace_bytes(n_res)

@@ -485,6 +485,9 @@ def test_unstable_partition_of_the_general_path(K, O, monkeypatch):
     for k, moltype in ((16, "dayhoff"), (7, "protein")):
         st = _csr_equals_oracle(K, O, res2, offs2, k, moltype, path=3)
         assert st["n_unique_hashes"] < st["n_tuples"]
+    # scaled > 1: the look-back sketch path scatters too (kept windows per protein counted by the sketch kernel)
+    for k, moltype, scaled in ((7, "protein", 10), (16, "dayhoff", 5)):
+        _csr_equals_oracle(K, O, res2, offs2, k, moltype, scaled=scaled, path=3)
     rep = np.frombuffer(("ACDEFGHIKLMNPQRSTVWY" * 3000).encode(), dtype=np.uint8)  # 20 k-mers, 3 000 times each
     res3 = np.concatenate([res, rep])
     offs3 = np.concatenate([offs, [offs[-1] + len(rep)]]).astype(np.uint64)
