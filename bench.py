@@ -2,8 +2,10 @@
 """Benchmark of the kmerseek sketch-and-search hot path on B200 (contract: see the task brief, section 4).
 
 One "step" = one index build of the workload's proteome that is already resident in HBM:
-    fused sketch kernel -> radix sort by hash -> CSR build (ks_index_clear + ks_index_sketch_resident +
-    ks_index_finalize through the C ABI).
+    fused sketch kernel -> sort by hash -> CSR build (ks_index_clear + ks_index_sketch_resident +
+    ks_index_finalize through the C ABI).  The library picks the build path from the parameters and the data
+    (`config.build_path`: dense k-mer space path for hp with k <= 24; general path with the unstable or the stable
+    partition otherwise); the stage names in `roofline.stages` follow it.
 `value` = residues/s over all ranks with inputs resident in HBM; `e2e` = the same metric through the public
 host API with HOST buffers (pinned 5-bit packed residues + offsets -> H2D -> build -> stats read back) inside the timed
 region.  A batched search of 10 000 planted query domains against the built index is timed beside it
