@@ -1,26 +1,31 @@
 #!/usr/bin/env python3
 """Benchmark of the kmerseek sketch-and-search hot path on B200 (contract: see the task brief, section 4).
 
-One "step" = one index build of the workload's proteome that is already resident in HBM:
+One "step" = one index build of this rank's shard of the workload's proteome, already resident in HBM:
     fused sketch kernel -> sort by hash -> CSR build (ks_index_clear + ks_index_sketch_resident +
     ks_index_finalize through the C ABI).  The library picks the build path from the parameters and the data
     (`config.build_path`: dense k-mer space path for hp with k <= 24; general path with the unstable or the stable
-    partition otherwise); the stage names in `roofline.stages` follow it.
+    partition otherwise).
 `value` = residues/s over all ranks with inputs resident in HBM; `e2e` = the same metric through the public
 host API with HOST buffers (pinned 5-bit packed residues + offsets -> H2D -> build -> stats read back) inside the timed
-region.  A batched search of 10 000 planted query domains against the built index is timed beside it
-(`search`: query x proteome residues/s).  Multi-GPU: the proteome is sharded by protein, one rank per GPU,
-no data-path collective in the build (weak scaling: every rank builds a shard of the workload's size);
-the search gathers per-shard pair lists to rank 0 over NCCL.
+region.
 
---impl reference times the CPU restatement of the reference's own algorithm (oracle/, the reference is
-Rust and cannot be built in this image) on the host cores, on a bounded sample of the same workload.
+Multi-GPU (`--gpus N` under torchrun): STRONG scaling -- ONE fixed proteome (the workload's, same seed at every N) is
+sharded by protein over the ranks (shard.plan_shards); the build has no collective.  The search leg (BASELINE.json
+configs[2]: 10 000 planted query domains, dayhoff k=16) runs on an index of the same proteome through
+ks_shard_search_batch (NCCL all-gather of counts + grouped send/recv of the shards' result blocks + counting merge on
+rank 0) and is checked against a single-GPU search of the unsharded proteome on rank 0.
+
+--impl reference times the CPU restatement of the reference's own algorithm (oracle/, the reference is Rust with
+un-vendored crates and cannot be built in this image) on all host cores: the linear-cost variant on the FULL workload
+(same config as the GPU arm) and the faithful-cost port (quadratic) on a bounded sample.
 """
 import argparse
 import json
 import os
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 
@@ -32,15 +37,16 @@ sys.path.insert(0, ROOT)
 WORKLOADS = {
     # BASELINE.json configs[1]: Swiss-Prot-sized index build, hp k=24 scaled=1 (the config the metric is quoted on)
     "c2_swissprot_hp_k24_s1": dict(n_residues=200_000_000, k=24, moltype="hp", scaled=1, seed=20260102),
-    # BASELINE.json configs[2] on one GPU: 10 000 planted query domains against the C2-sized proteome, dayhoff k=16
+    # BASELINE.json configs[2]: the proteome of C2 under dayhoff k=16 (the search leg's index)
     "c3_search_dayhoff_k16_s1": dict(n_residues=200_000_000, k=16, moltype="dayhoff", scaled=1, seed=20260102),
     # the north_star target run
     "target_100m_dayhoff_k16_s1": dict(n_residues=100_000_000, k=16, moltype="dayhoff", scaled=1, seed=20260103),
     "c4_slice_protein_k7_s10": dict(n_residues=1_000_000_000, k=7, moltype="protein", scaled=10, seed=20260104),
     "small": dict(n_residues=5_000_000, k=24, moltype="hp", scaled=1, seed=20260102),
-    # one eighth of the target run: what a rank holds when the 100 M-residue proteome is sharded over 8 GPUs
-    "target_shard_12m_dayhoff_k16_s1": dict(n_residues=12_500_000, k=16, moltype="dayhoff", scaled=1, seed=20260103),
 }
+SEARCH_WORKLOAD = "c3_search_dayhoff_k16_s1"
+BUILD_PATHS = {0: "general", 1: "dense k-mer space", 2: "dense k-mer space, library key sort",
+               3: "general, unstable partition"}
 
 
 def peaks():
@@ -90,33 +96,37 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures of the C2
-# workload (profiles/r01_*): only meaningful for that workload, null otherwise.
-TRAFFIC = {  # bytes per launch, C2 workload, profiles/r01_d_ncu_full_raw_rep_c2.csv, r01_e_ncu_full_raw_dense_*.csv
-    "bucket_sort_rep_kernel (+ fused CSR write, directory)": 2_991_587_000 + 2_473_064_000,
-    "dense_bucket_kernel (sort + CSR write)": 1_638_007_000 + 3_419_163_000,
-    "sketch_dense_kernel (ranks + first scatter level)": 2_342_600_000 + 1_481_121_000,
-    "sketch_quad_kernel": 205_893_000 + 2_934_864_000,
-}
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the committed `ncu --set full`
+# captures of the C2 workload on one GPU (profiles/): only meaningful for that workload at N = 1, null otherwise.
+TRAFFIC_C2 = {"dense_bucket_kernel": 1_638_007_000 + 3_419_163_000}  # profiles/r01_e_ncu_full_raw_dense_bucket_c2.csv
 
 
-def algorithmic_bytes(n_res, n_prot, n_tuples, n_unique):
-    """BASELINE.md section 3."""
-    sketch = n_res + (n_prot + 1) * 8 + n_tuples * 16
-    build = n_tuples * 16 + n_tuples * 8 + n_unique * 8 + (n_unique + 1) * 4
-    return sketch, build
+def sketch_bytes(n_res, n_prot, n_tuples):
+    """SURVEY 8(d) / BASELINE.md section 3: read residues + offsets, write (u64 hash, u32 protein, u32 pos)."""
+    return n_res + (n_prot + 1) * 8 + n_tuples * 16
 
 
-def make_workload(cfg, rank):
-    from kmerseek_b200 import synth
-    res, offs = synth.proteome(cfg["n_residues"], cfg["seed"] + 7919 * rank)
-    return res, offs
+def build_bytes(n_tuples, n_unique):
+    """one logical pass -- tuples in, payload + keys + row_ptr out (extra passes are implementation traffic)."""
+    return n_tuples * 16 + n_tuples * 8 + n_unique * 8 + (n_unique + 1) * 4
+
+
+def search_bytes(q_res, q_hashes, hits, pairs):
+    """query in, one key probe + row_ptr pair per query hash, postings + hit rows, 48 B of scores per pair."""
+    return q_res + q_hashes * 8 + q_hashes * 16 + hits * 8 + hits * 20 + pairs * 48
+
+
+_PROTEOME_CACHE = {}
 
 
 def cpu_baseline_run(cfg, faithful, sample_residues, threads):
     from oracle import oracle as O
     from kmerseek_b200 import synth
-    res, offs = synth.proteome(sample_residues, cfg["seed"])
+    key = (sample_residues, cfg["seed"])
+    if key not in _PROTEOME_CACHE:
+        _PROTEOME_CACHE.clear()
+        _PROTEOME_CACHE[key] = synth.proteome(sample_residues, cfg["seed"])
+    res, offs = _PROTEOME_CACHE[key]
     t0 = time.perf_counter()
     n, uniq, kept = O.cpu_baseline(res, offs, cfg["k"], cfg["moltype"], cfg["scaled"], faithful=faithful, n_threads=threads)
     dt = time.perf_counter() - t0
@@ -124,29 +134,44 @@ def cpu_baseline_run(cfg, faithful, sample_residues, threads):
 
 
 def run_reference(args, cfg, wname):
-    """The reference arm: CPU restatement of the reference's own algorithm (two passes per protein, linear
-    `contains`, sorted-Vec combined insert -- src/rust/index.rs:749-830), all host threads."""
+    """The reference arm.  `value`: the CPU restatement of the reference's per-protein algorithm (translate, MurmurHash3,
+    FracMinHash filter, sorted mins + abundances, positions per hash) over the FULL workload on all host threads, in
+    1000-record batches like src/rust/index.rs:938-941,993-1005, with the reference's two super-linear steps made linear
+    (binary-search membership instead of `Vec::contains`, index.rs:769; no sorted-Vec combined insert, :824-827) -- the
+    only form of the algorithm that can finish this config.  `faithful`: the same port with the reference's
+    cost structure kept, on a bounded sample (quadratic: the rate depends on the sample)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    sample = args.reference_sample
+    # the whole run must end within a few minutes: size the per-step sample from a short trial (the full workload when
+    # the host is fast enough, which makes this arm the same config as the GPU arm)
+    trial = min(cfg["n_residues"], 10_000_000)
+    rate, _, _, _ = cpu_baseline_run(cfg, False, trial, threads)
+    budget_s = 200.0 / max(1, args.warmup + args.steps)
+    sample = int(min(cfg["n_residues"], max(trial, rate * budget_s)))
     vals = []
     for i in range(args.warmup + args.steps):
-        v, dt, uniq, kept = cpu_baseline_run(cfg, True, sample, threads)
+        v, dt, _, _ = cpu_baseline_run(cfg, False, sample, threads)
         if i >= args.warmup:
             vals.append((v, dt))
     v = float(np.mean([x[0] for x in vals]))
     ms = float(np.mean([x[1] for x in vals]) * 1e3)
-    sample_txt = (f"first {sample} residues of the synthetic workload; reference cost structure kept (the combined-"
-                  f"sketch insert is O(U) per new hash, so residues/s falls as the sample grows)")
+    fv, fdt, _, _ = cpu_baseline_run(cfg, True, args.reference_sample, threads)
     line = {
         "impl": "reference", "metric": "residues/s sketched+indexed", "value": v, "unit": "residues/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
         "config": {"workload": wname, "k": cfg["k"], "moltype": cfg["moltype"], "scaled": cfg["scaled"],
-                   "sample_residues": sample},
-        "cpu_baseline": {"value": v, "unit": "residues/s", "cores": threads, "kind": "port", "sample": sample_txt},
+                   "residues": sample, "same_config_as_gpu_arm": sample == cfg["n_residues"]},
+        "cpu_baseline": {"value": v, "unit": "residues/s", "cores": threads, "kind": "port",
+                         "sample": (f"the full workload ({sample} residues)" if sample == cfg["n_residues"] else
+                                    f"first {sample} of {cfg['n_residues']} residues") +
+                                   " per step; linear-cost variant of the reference's algorithm (binary-search membership, no "
+                                   "combined-sketch insert)",
+                         "faithful": {"value": fv, "unit": "residues/s", "cores": threads,
+                                      "sample": f"first {args.reference_sample} residues, reference cost structure kept (two "
+                                                f"passes, linear contains, sorted-Vec combined insert: quadratic), {fdt:.1f} s"}},
         "e2e": {"value": v, "unit": "residues/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -163,6 +188,7 @@ def main():
     ap.add_argument("--reference-sample", type=int, default=150_000)
     ap.add_argument("--cpu-fast-sample", type=int, default=20_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the target-run and ingest legs")
     args = ap.parse_args()
     cfg = WORKLOADS[args.workload]
     if args.impl == "reference":
@@ -181,200 +207,298 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    comm = shard.Comm(local) if world > 1 else None
     W = max(args.warmup, 3)
+    L = _ffi.lib()
+    chk = K.errors.check
+    dev = torch.device("cuda", local)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- workload: this rank's shard (weak scaling: each rank builds a shard of the workload's size) ----
-    res, offs = make_workload(cfg, rank)
-    prot = K.Proteome.from_packed(res, offs)
-    n_res, n_prot = prot.n_residues, prot.n_proteins
-    idx = K.ProteomeIndex("bench", cfg["k"], cfg["scaled"], cfg["moltype"], device=local)
-    L = _ffi.lib()
-    stream = torch.cuda.ExternalStream(L.ks_index_stream(idx._h), device=torch.device("cuda", local))
-    chk = K.errors.check
+    def max_over_ranks(*vals):
+        if world == 1:
+            return [float(v) for v in vals]
+        t = torch.tensor(list(vals), device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(x) for x in t.tolist()]
 
-    def build_resident():
-        chk(L.ks_index_clear(idx._h))
-        chk(L.ks_index_sketch_resident(idx._h))
-        chk(L.ks_index_finalize(idx._h))
+    def sum_over_ranks(*vals):
+        if world == 1:
+            return [int(v) for v in vals]
+        t = torch.tensor(list(vals), device="cuda", dtype=torch.int64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return [int(x) for x in t.tolist()]
 
-    def build_from_host():
-        chk(L.ks_index_clear(idx._h))
-        chk(L.ks_index_add_proteome(idx._h, prot._h))  # pinned host buffers -> HBM (chunked) overlapped with the sketch
-        chk(L.ks_index_finalize(idx._h))
-        return idx.stats()  # the step's result read back on the host
+    class Build:
+        """One index handle over this rank's shard of a workload's proteome + the timed build loops."""
 
-    def timed(fn, steps, per_step=None):
-        """EXACTLY `steps` calls between barrier+synchronize on both sides; device time by CUDA events on the
-        library's stream; max over ranks."""
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        for _ in range(steps):
-            fn()
-            if per_step:
-                per_step()
-        e1.record(stream)
-        barrier()
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms
+        def __init__(self, wcfg, res, offs):
+            self.cfg = wcfg
+            self.bounds = shard.plan_shards(offs, world)
+            sres, soffs = shard.shard_of(res, offs, self.bounds, rank)
+            self.prot = K.Proteome.from_packed(sres, soffs)
+            self.n_res, self.n_prot = self.prot.n_residues, self.prot.n_proteins
+            self.idx = K.ProteomeIndex("bench", wcfg["k"], wcfg["scaled"], wcfg["moltype"], device=local)
+            self.stream = torch.cuda.ExternalStream(L.ks_index_stream(self.idx._h), device=dev)
+            chk(L.ks_index_upload(self.idx._h, self.prot._h))
 
+        def resident(self):
+            chk(L.ks_index_clear(self.idx._h))
+            chk(L.ks_index_sketch_resident(self.idx._h))
+            chk(L.ks_index_finalize(self.idx._h))
+
+        def from_host(self):
+            chk(L.ks_index_clear(self.idx._h))
+            chk(L.ks_index_add_proteome(self.idx._h, self.prot._h))  # pinned host buffers -> HBM (chunked), overlapped with the sketch
+            chk(L.ks_index_finalize(self.idx._h))
+            return self.idx.stats()  # the step's result read back on the host
+
+        def timed(self, fn, steps, per_step=None):
+            """EXACTLY `steps` calls between barrier + synchronize on both sides; device time by CUDA events on the
+            library's stream; max over ranks."""
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(self.stream)
+            for _ in range(steps):
+                fn()
+                if per_step:
+                    per_step()
+            e1.record(self.stream)
+            barrier()
+            return max_over_ranks(e0.elapsed_time(e1))[0]
+
+        def close(self):
+            self.idx.close()
+            self.prot.close()
+
+    # ---- the workload: ONE fixed proteome, sharded by protein over the ranks (strong scaling) ----
+    res, offs = synth.proteome(cfg["n_residues"], cfg["seed"])
+    total_res = int(offs[-1])
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    chk(L.ks_index_upload(idx._h, prot._h))
+    b = Build(cfg, res, offs)
     for _ in range(W):
-        build_resident()
-    st0 = idx.stats()
+        b.resident()
+    st0 = b.idx.stats()
     stage_ms = {"sketch": [], "partition": [], "bucket": [], "csr": []}
 
     def collect():
-        s = idx.stats()
+        s = b.idx.stats()
         stage_ms["sketch"].append(s["ms_sketch"]); stage_ms["partition"].append(s["ms_sort_partition"])
         stage_ms["bucket"].append(s["ms_sort_bucket"]); stage_ms["csr"].append(s["ms_csr"])
 
-    ms_total = timed(build_resident, args.steps, per_step=collect)
-    st1 = idx.stats()
-    launches = sum(st1[k] - st0[k] for k in ("sketch_launches", "sort_launches", "csr_launches"))
-    ms_step = ms_total / args.steps
-    value = world * n_res / (ms_step * 1e-3)
+    ms_step = b.timed(b.resident, args.steps, per_step=collect) / args.steps
+    st1 = b.idx.stats()
+    launches = sum(st1[k] - st0[k] for k in ("sketch_launches", "sort_launches", "csr_launches"))  # this rank, timed region
+    value = total_res / (ms_step * 1e-3)
 
     # ---- e2e: host buffers -> H2D -> build -> stats back, through the public API ----
     for _ in range(2):
-        build_from_host()
-    ms_e2e = timed(build_from_host, args.steps) / args.steps
-    e2e_value = world * n_res / (ms_e2e * 1e-3)
+        b.from_host()
+    ms_e2e = b.timed(b.from_host, args.steps) / args.steps
+    e2e_value = total_res / (ms_e2e * 1e-3)
     clocks = sampler.stop() if rank == 0 else None
-    st = idx.stats()
-    n_tuples, n_unique = st["n_tuples"], st["n_unique_hashes"]
+    st = b.idx.stats()
+    n_tuples, n_unique, n_groups = sum_over_ranks(st["n_tuples"], st["n_unique_hashes"], st["n_groups"])
+    n_prot_total = len(offs) - 1
+    h2d = sum_over_ranks((b.n_res + 7) // 8 * 5 + 72 + (b.n_prot + 1) * 8)[0]
+    build_path = st["build_path"]
+    stage = {k: max_over_ranks(float(np.mean(v)))[0] for k, v in stage_ms.items()}
 
-    # ---- search: planted query domains against the built index; per-shard results gathered to rank 0 ----
-    qres, qoffs, _ = synth.queries(res, offs, args.queries, 77 + 2) if rank == 0 or world == 1 else (None, None, None)
-    if world > 1:
-        qres, qoffs = shard.broadcast_queries(qres, qoffs)
+    # ---- search leg: BASELINE.json configs[2] -- planted query domains against the same proteome, dayhoff k=16 ----
+    scfg = WORKLOADS[SEARCH_WORKLOAD] if cfg["n_residues"] == WORKLOADS[SEARCH_WORKLOAD]["n_residues"] else dict(cfg, k=16, moltype="dayhoff", scaled=1)
+    b.close()
+    sb = Build(scfg, res, offs)
+    sb.resident()
+    qres, qoffs, _ = synth.queries(res, offs, args.queries, 77 + 2)  # same seed on every rank: replicated queries
     queries = K.Proteome.from_packed(qres, qoffs)
     q_residues = queries.n_residues
-    search_ms, lib_ms = [], []
-    n_pairs_total = n_hits_total = 0
-    for i in range(W + args.steps):
-        barrier()
-        t0 = time.perf_counter()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        gathered = shard.search_and_gather(idx, queries, pid_base=0, hits=False)
-        e1.record(stream)
-        barrier()
-        ms = e0.elapsed_time(e1)
-        wall = (time.perf_counter() - t0) * 1e3
-        ms = max(ms, 0.0)
-        if world > 1:
-            t = torch.tensor([ms, wall], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms, wall = float(t[0].item()), float(t[1].item())
-        if i >= W:
-            search_ms.append((ms, wall))
+    search = {}
+    for label, hits in (("pairs", False), ("pairs_and_hits", True)):
+        walls, devs = [], []
+        out = None
+        for i in range(W + args.steps):
+            out = None
+            barrier()
+            t0 = time.perf_counter()
+            out = shard.search_and_gather(sb.idx, queries, comm, pid_base=sb.bounds[rank], hits=hits)
+            torch.cuda.synchronize()
+            wall = (time.perf_counter() - t0) * 1e3
+            wall, = max_over_ranks(wall)
+            if i >= W:
+                walls.append(wall)
+                devs.append(sb.idx.stats()["ms_search"])
+        n_pairs = out["n_pairs"] if rank == 0 else 0
+        n_hits = len(out["hits"]["hit_qid"]) if (rank == 0 and hits) else 0
+        q_hashes = int(out["result"].q_sizes.sum()) if rank == 0 else 0
+        alg = search_bytes(q_residues, q_hashes, n_hits, n_pairs)
+        wall_ms = float(np.mean(walls))
+        dev_ms = max_over_ranks(float(np.mean(devs)))[0]
+        search[label] = {"ms_per_batch_wall": wall_ms, "ms_per_batch_kernels": dev_ms, "pairs": int(n_pairs), "hits": int(n_hits),
+                         "query_hashes": q_hashes, "algorithmic_bytes": int(alg),
+                         "value": q_residues * total_res / (wall_ms * 1e-3)}
+        if rank == 0 and label == "pairs":
+            keep = {c: out["pairs"][c].copy() for c in ("pair_qid", "pair_pid", "intersect_hashes", "containment")}
+    sb.close()
+    verify = None
+    if world > 1 and rank == 0:
+        # the sharded search against a single-GPU search of the unsharded proteome, at full size
+        full = K.ProteomeIndex("verify", scfg["k"], scfg["scaled"], scfg["moltype"], device=local)
+        fp = K.Proteome.from_packed(res, offs)
+        full.add_proteome(fp)
+        full.finalize()
+        r1 = K.search(full, queries, hits=False, query_sketches=False)
+        verify = {"single_gpu_pairs": int(r1.n_pairs), "sharded_pairs": int(search["pairs"]["pairs"]),
+                  "identical": bool(r1.n_pairs == len(keep["pair_qid"]) and all(
+                      np.array_equal(r1.pairs[c], keep[c]) for c in keep))}
+        full.close()
+        fp.close()
+        assert verify["identical"], f"sharded search differs from the single-GPU search: {verify}"
+
+    # ---- extra legs (not the headline): the north_star target run, ingest ----
+    extra = {}
+    if not args.no_extra and args.workload == "c2_swissprot_hp_k24_s1":
+        tcfg = WORKLOADS["target_100m_dayhoff_k16_s1"]
+        tres, toffs = synth.proteome(tcfg["n_residues"], tcfg["seed"])
+        tb = Build(tcfg, tres, toffs)
+        for _ in range(W):
+            tb.resident()
+        t_ms = tb.timed(tb.resident, args.steps) / args.steps
+        for _ in range(2):
+            tb.from_host()
+        t_e2e = tb.timed(tb.from_host, args.steps) / args.steps
+        tst = tb.idx.stats()
+        tt, tu = sum_over_ranks(tst["n_tuples"], tst["n_unique_hashes"])
+        tbytes = sketch_bytes(int(toffs[-1]), len(toffs) - 1, tt) + build_bytes(tt, tu)
+        extra["target_100m_dayhoff_k16_s1"] = {
+            "ms_per_step": t_ms, "value": int(toffs[-1]) / (t_ms * 1e-3), "ms_per_step_e2e": t_e2e,
+            "e2e_value": int(toffs[-1]) / (t_e2e * 1e-3), "build_path": BUILD_PATHS[tst["build_path"]],
+            "algorithmic_bytes": int(tbytes), "whole_step_frac": tbytes / t_ms / 1e6 / peaks()[0] / world}
+        tb.close()
+        del tres, toffs
         if rank == 0:
-            n_pairs_total = gathered["n_pairs"]
-            if world == 1 and i >= W:
-                lib_ms.append(float(gathered["result"].ms_device))
-    s_ms = float(np.mean([x[1] for x in search_ms]))  # wall: includes the H2D of the queries, NCCL gather and D2H
-    search_value = q_residues * (world * n_res) / (s_ms * 1e-3)
+            extra["ingest"] = ingest_leg(K, L, chk, cfg, res, offs, local)
 
     if rank != 0:
+        if comm:
+            comm.close()
         if world > 1:
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (stage times: CUDA events the library records on its own stream) ----
+    # ---- roofline (SURVEY 8(d) bytes; stage times are CUDA events the library records on its own stream) ----
     peak, peak_src = peaks()
-    n_groups = st["n_groups"]
-    ms = {k: float(np.mean(v)) for k, v in stage_ms.items()}
-    alphabet = {"protein": 20.0, "dayhoff": 6.0, "hp": 2.0}[cfg["moltype"]]
-    repeat_heavy = n_tuples > 0.25 * alphabet ** cfg["k"] / cfg["scaled"]  # the library's choice of bucket-sort variant
-    if st["build_path"] in (0, 3):
-        bucket_name = ("bucket_sort_rep_kernel" if repeat_heavy else "bucket_sort_bin_kernel") + " (+ fused CSR write, directory)"
-        alg = {
-            # BASELINE.md section 3; per launch = per step (every stage runs once per step)
-            "sketch_quad_kernel": ("sketch", n_res + (n_prot + 1) * 8 + n_tuples * 16),
-            ("partition (2 library onesweep passes)" if st["build_path"] == 0 else
-             "pair_partition_kernel (second scatter level; the first is fused into the sketch kernel)"):
-                ("partition", n_tuples * 16 * 2),                                                # one read + one write
-            # one read of every tuple, one write of its payload (loc), plus the CSR arrays the kernel emits (keys, key_grp,
-            # grp_start) and the bucket directory (about one entry per 4 tuples)
-            bucket_name: ("bucket", n_tuples * 16 + n_tuples * 8 + n_groups * 4 + n_unique * 12 + (n_tuples // 4) * 4),
-        }
+    agg_peak = peak * world  # N GPUs: the job's roofline is N times one GPU's
+    sk_b, bd_b = sketch_bytes(total_res, n_prot_total, n_tuples), build_bytes(n_tuples, n_unique)
+    build_ms = stage["partition"] + stage["bucket"] + stage["csr"]
+    repeat_heavy = n_tuples > 0.25 * {"protein": 20.0, "dayhoff": 6.0, "hp": 2.0}[cfg["moltype"]] ** cfg["k"] / cfg["scaled"]
+    if build_path in (1, 2):
+        names = {"sketch": "sketch_dense_kernel (ranks + first scatter level)",
+                 "partition": "dense_partition_kernel (second scatter level)" if build_path == 1 else "library key sort",
+                 "bucket": "dense_bucket_kernel" if build_path == 1 else "dense_count_kernel + dense_write_kernel",
+                 "csr": "dir_kernel"}
     else:
-        # dense k-mer space path (hp, small k): tuples are 8-byte rank keys.  The algorithmic bytes stay SURVEY 8(d)'s
-        # (16 B per tuple out of the sketch, 16 B read + 8 B payload written by the build): what the path does not
-        # move shows up as a higher achieved figure, which is the point of it.
-        alg = {
-            "sketch_dense_kernel (ranks + first scatter level)": ("sketch", n_res + (n_prot + 1) * 8 + n_tuples * 16),
-            ("dense_partition_kernel (second scatter level)" if st["build_path"] == 1 else "library key sort (3 onesweep passes)"):
-                ("partition", n_tuples * 8 * 2),
-            ("dense_bucket_kernel (sort + CSR write)" if st["build_path"] == 1 else "dense_count_kernel + dense_write_kernel"):
-                ("bucket", n_tuples * 16 + n_tuples * 8 + n_groups * 4 + n_unique * 12),
-            "dir_kernel": ("csr", n_unique * 8 + (n_tuples // 4) * 4),
-        }
-    stages = {name: {"ms": ms[key], "algorithmic_bytes": int(b), "achieved_gbs": b / ms[key] / 1e6 if ms[key] > 0 else 0.0}
-              for name, (key, b) in alg.items()}
-    own = {k: v for k, v in stages.items() if "library" not in k}
-    dom = max(own, key=lambda k: own[k]["ms"])
-    sk_bytes, bd_bytes = algorithmic_bytes(n_res, n_prot, n_tuples, n_unique)
-    roof = {"bound": "hbm", "kernel": dom, "achieved": stages[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
-            "frac": stages[dom]["achieved_gbs"] / peak,
-            "traffic": TRAFFIC.get(dom) if args.workload == "c2_swissprot_hp_k24_s1" else None, "peak_source": peak_src,
-            "stages": {k: {"ms": round(v["ms"], 4), "achieved_gbs": round(v["achieved_gbs"], 1),
-                           "frac": round(v["achieved_gbs"] / peak, 4)} for k, v in stages.items()},
-            "whole_step": {"algorithmic_bytes": sk_bytes + bd_bytes,
-                           "achieved_gbs": (sk_bytes + bd_bytes) / ms_step / 1e6,
-                           "frac": (sk_bytes + bd_bytes) / ms_step / 1e6 / peak}}
+        names = {"sketch": "sketch_quad_kernel" + (" (+ first scatter level)" if build_path == 3 else ""),
+                 "partition": "pair_partition_kernel (second scatter level)" if build_path == 3 else "partition (library onesweep passes)",
+                 "bucket": "bucket_sort_rep_kernel" if repeat_heavy else "bucket_sort_bin_kernel", "csr": "(fused into the bucket kernel)"}
+    dom_key = max(("sketch", "bucket"), key=lambda k_: stage[k_])
+    dom_bytes = sk_b if dom_key == "sketch" else bd_b
+    roof = {
+        "bound": "hbm", "kernel": names[dom_key], "achieved": dom_bytes / stage[dom_key] / 1e6, "peak": agg_peak, "unit": "GB/s",
+        "frac": dom_bytes / stage[dom_key] / 1e6 / agg_peak,
+        "traffic": TRAFFIC_C2.get(names[dom_key]) if (args.workload == "c2_swissprot_hp_k24_s1" and world == 1) else None,
+        "peak_source": peak_src + (f" x {world} GPUs" if world > 1 else ""),
+        "bytes_model": "SURVEY 8(d): sketch N + 8(P+1) + 16K; index build 24K + 12U + 4 (one logical pass: the partition, bucket "
+                       "and directory kernels share it, so the dominant build kernel is charged with all of it); the two "
+                       "stages sum to whole_step.algorithmic_bytes",
+        "stages": {
+            "sketch": {"kernels": names["sketch"], "ms": round(stage["sketch"], 4), "algorithmic_bytes": int(sk_b),
+                       "frac": round(sk_b / stage["sketch"] / 1e6 / agg_peak, 4) if stage["sketch"] > 0 else None},
+            "index_build": {"kernels": [names["partition"], names["bucket"], names["csr"]],
+                            "ms": round(build_ms, 4), "ms_by_kernel": {"partition": round(stage["partition"], 4),
+                                                                       "bucket": round(stage["bucket"], 4), "directory": round(stage["csr"], 4)},
+                            "algorithmic_bytes": int(bd_b), "frac": round(bd_b / build_ms / 1e6 / agg_peak, 4) if build_ms > 0 else None}},
+        "whole_step": {"algorithmic_bytes": int(sk_b + bd_b), "achieved_gbs": (sk_b + bd_b) / ms_step / 1e6,
+                       "frac": (sk_b + bd_b) / ms_step / 1e6 / agg_peak}}
+    for v in search.values():
+        v["roofline"] = {"bound": "hbm", "algorithmic_bytes": v["algorithmic_bytes"], "peak": agg_peak,
+                         "frac_kernels": v["algorithmic_bytes"] / v["ms_per_batch_kernels"] / 1e6 / agg_peak if v["ms_per_batch_kernels"] else None,
+                         "frac_wall": v["algorithmic_bytes"] / v["ms_per_batch_wall"] / 1e6 / agg_peak}
 
     cpu = None
     if not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        v, dt, _, _ = cpu_baseline_run(cfg, True, args.reference_sample, threads)
         vf, dtf, _, _ = cpu_baseline_run(cfg, False, args.cpu_fast_sample, threads)
-        cpu = {"value": v, "unit": "residues/s", "cores": threads, "kind": "port",
-               "sample": f"first {args.reference_sample} residues, reference cost structure (two passes, linear contains, "
-                         f"sorted-Vec combined insert; quadratic, so the rate depends on the sample), {dt:.1f} s",
-               "fast_variant": {"value": vf, "unit": "residues/s", "cores": threads,
-                                "sample": f"{args.cpu_fast_sample} residues, binary-search membership and no combined "
-                                          f"insert (a linear-cost CPU variant), {dtf:.1f} s"}}
+        v, dt, _, _ = cpu_baseline_run(cfg, True, args.reference_sample, threads)
+        cpu = {"value": vf, "unit": "residues/s", "cores": threads, "kind": "port",
+               "sample": f"first {args.cpu_fast_sample} residues of the workload, linear-cost variant of the reference's algorithm "
+                         f"(binary-search membership, no combined-sketch insert), {dtf:.1f} s",
+               "faithful": {"value": v, "unit": "residues/s", "cores": threads,
+                            "sample": f"first {args.reference_sample} residues, reference cost structure (two passes, linear "
+                                      f"contains, sorted-Vec combined insert; quadratic, so the rate depends on the sample), {dt:.1f} s"}}
 
     line = {
         "metric": "residues/s sketched+indexed", "value": value, "unit": "residues/s", "n_gpus": world,
-        "steps": args.steps, "warmup": W, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "steps": args.steps, "warmup": W, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "u64", "data": "synthetic",
         "config": {"workload": args.workload, "k": cfg["k"], "moltype": cfg["moltype"], "scaled": cfg["scaled"],
-                   "residues_per_gpu": n_res, "proteins_per_gpu": n_prot, "tuples_per_gpu": n_tuples,
-                   "unique_hashes_per_gpu": n_unique, "parallelism": f"protein-sharded x{world}",
-                   "build_path": {0: "general", 1: "dense k-mer space", 2: "dense k-mer space, library key sort",
-                                  3: "general, unstable partition"}[st["build_path"]],
-                   "l2": "inputs (0.2 GB residues, 3 GB tuples) exceed the 126 MB L2; no flush needed"},
+                   "residues": total_res, "proteins": n_prot_total, "tuples": n_tuples, "unique_hashes": n_unique,
+                   "parallelism": f"one fixed proteome, protein-sharded x{world} (no collective in the build)",
+                   "build_path": BUILD_PATHS[build_path],
+                   "l2": "inputs (0.2 GB residues, 3 GB tuples over all ranks) exceed the 126 MB L2; no flush needed"},
         "e2e": {"value": e2e_value, "unit": "residues/s", "ms_per_step": ms_e2e,
-                "h2d_bytes_per_step": int((n_res + 7) // 8 * 5 + 72 + (n_prot + 1) * 8), "d2h_bytes_per_step": 8 + 16 + 136},
-        "gpu_launches": int(launches),
+                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": (8 + 16 + 136) * world},
+        "gpu_launches": int(launches), "gpu_launches_per_step": int(launches) // args.steps,
         "roofline": roof,
         "cpu_baseline": cpu,
-        "search": {"metric": "query x proteome residues/s searched", "value": search_value, "unit": "residue pairs/s",
-                   "ms_per_batch_wall": s_ms, "ms_per_batch_device": float(np.mean([x[0] for x in search_ms])),
-                   "ms_per_batch_kernels": float(np.mean(lib_ms)) if lib_ms else None,  # the library's own events: query
-                                                                                       # sketch .. scores, no copies
-                   "queries": args.queries, "query_residues": int(q_residues), "pairs": int(n_pairs_total),
-                   "includes": "query H2D, sketch, lookup, aggregation, scores, NCCL gather to rank 0, D2H"},
+        "search": {"metric": "query x proteome residues/s searched", "workload": SEARCH_WORKLOAD, "unit": "residue pairs/s",
+                   "value": search["pairs"]["value"], "queries": args.queries, "query_residues": int(q_residues),
+                   "includes": "query H2D, per-query kernels (sketch, lookup, aggregation), scores, "
+                               + ("NCCL all-gather + send/recv + merge on rank 0, " if world > 1 else "") + "D2H of the result block",
+                   **{k_: v for k_, v in search.items()}, "sharded_equals_single_gpu": verify},
+        "extra": extra,
         "clocks": clocks,
     }
     print(json.dumps(line), flush=True)
+    if comm:
+        comm.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def ingest_leg(K, L, chk, cfg, res, offs, local):
+    """Host-side ingest, timed on rank 0: packed buffers -> pinned ks_proteome, and plain FASTA -> finalized index
+    (ks_index_process_fasta = process_fasta, src/rust/index.rs:907-961)."""
+    from kmerseek_b200 import synth
+    t0 = time.perf_counter()
+    p = K.Proteome.from_packed(res, offs)
+    t_packed = time.perf_counter() - t0
+    p.close()
+    d = "/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir()
+    path = os.path.join(d, f"ks_bench_{os.getpid()}.fasta")
+    try:
+        synth.write_fasta(path, res, offs)
+        size = os.path.getsize(path)
+        best = None
+        for _ in range(3):
+            idx = K.ProteomeIndex("ingest", cfg["k"], cfg["scaled"], cfg["moltype"], device=local)
+            t0 = time.perf_counter()
+            chk(L.ks_index_process_fasta(idx._h, path.encode(), 0))
+            chk(L.ks_index_sync(idx._h))
+            dt = time.perf_counter() - t0
+            idx.close()
+            best = dt if best is None else min(best, dt)
+    finally:
+        if os.path.exists(path):
+            os.remove(path)
+    n = int(offs[-1])
+    return {"from_packed_s": t_packed, "from_packed_residues_per_s": n / t_packed,
+            "fasta_to_index_s": best, "fasta_to_index_residues_per_s": n / best, "fasta_bytes": size,
+            "what": "plain FASTA (60 columns) in " + d + " -> parse, normalise, pack, H2D, sketch, finalize (best of 3)"}
 
 
 if __name__ == "__main__":

@@ -215,12 +215,14 @@ void ks_csr_free(ks_csr *c);
  * k-mer join of search.py:204-213 / sig2kmer.py:113-155 (hit positions).
  * Scores follow SURVEY.md Appendix A.6; float columns are fp64.
  * ------------------------------------------------------------------------------------------- */
-#define KS_SEARCH_HITS 1u        /* also produce the hit list */
-#define KS_SEARCH_DEVICE_ONLY 2u /* leave results on the device; host arrays are NULL, counts are set */
+#define KS_SEARCH_HITS 1u           /* also produce the hit list */
+#define KS_SEARCH_DEVICE_ONLY 2u    /* leave results on the device; host arrays are NULL, counts are set */
+#define KS_SEARCH_QUERY_SKETCHES 4u /* also return the queries' sketches (q_mins / q_abunds; needed for query_md5) */
 
 typedef struct ks_search_result {
     uint64_t n_queries;
-    /* per query: sketch (sorted distinct mins + abundances), CSR by query */
+    /* per query: sketch (sorted distinct mins + abundances), CSR by query.  q_sig_ptr always comes back (|Q| of query q
+     * = q_sig_ptr[q+1] - q_sig_ptr[q]); q_mins / q_abunds only with KS_SEARCH_QUERY_SKETCHES, else NULL. */
     uint64_t *q_sig_ptr; /* [n_queries+1] */
     uint64_t *q_mins;
     uint64_t *q_abunds;
@@ -238,10 +240,9 @@ typedef struct ks_search_result {
     uint64_t n_hits;
     uint32_t *hit_qid, *hit_pid, *hit_qpos, *hit_tpos;
     uint64_t *hit_hash;
-    /* device-resident copies of the pair/hit columns (kept only with KS_SEARCH_DEVICE_ONLY, then valid until
-     * ks_search_result_free, which must precede ks_index_destroy); used by
-     * the multi-GPU host to gather shards with NCCL without a host round trip.  Layout: see
-     * ks_search_result_device_column(). */
+    /* Owner of the result's memory.  A result is ONE contiguous block -- every column above points into a single pinned
+     * host block that one cudaMemcpyAsync filled -- and, with KS_SEARCH_DEVICE_ONLY, one device block that stays valid until
+     * ks_search_result_free (which must then precede ks_index_destroy); see ks_search_result_device_column(). */
     void *device_block;
     float ms_device; /* device time of the search (query sketch + lookup + aggregation + scores [+ hits]) */
 } ks_search_result;
@@ -254,6 +255,31 @@ void *ks_search_result_device_column(const ks_search_result *r, const char *name
 /* Split search for benchmarking with the query batch already resident in HBM. */
 ks_status ks_query_upload(ks_index *idx, const ks_proteome *queries);
 ks_status ks_search_resident(ks_index *idx, uint32_t flags, ks_search_result **out);
+
+/* ---------------------------------------------------------------------------------------------
+ * Multi-GPU (the reference is single-process, src/rust/index.rs:993-1005 is its only parallel
+ * region).  One process per GPU; the proteome is sharded by protein in contiguous ranges (rank r owns index-wide protein
+ * ids [pid_base_r, pid_base_r + n_proteins_r), ascending with the rank); every rank builds its own index with the calls
+ * above -- the build has no collective.  Queries are replicated.  A target lives on exactly one shard, so each (query,
+ * target) pair is scored completely by its owner and the merge on rank 0 is a concatenation in (query, target) order.
+ * NCCL is bound at run time (dlopen of libnccl.so.2): without it these calls return KS_ERR_NCCL.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct ks_comm ks_comm;
+#define KS_COMM_ID_BYTES 128
+/* ncclGetUniqueId: call on one rank, hand the bytes to every rank (any side channel), then ks_comm_create everywhere. */
+ks_status ks_comm_unique_id(uint8_t id[KS_COMM_ID_BYTES]);
+/* ncclCommInitRank on `device`; collective over all `world` ranks (at most 16). */
+ks_status ks_comm_create(const uint8_t id[KS_COMM_ID_BYTES], int rank, int world, int device, ks_comm **out);
+void ks_comm_destroy(ks_comm *c);
+int ks_comm_rank(const ks_comm *c);
+int ks_comm_world(const ks_comm *c);
+/* ks_search_batch over all shards; collective.  Every rank passes the same query batch and its shard's pid_base.  Per
+ * batch: one ncclAllGather (four counts per rank), one grouped ncclSend/ncclRecv of each shard's result block (exact
+ * sizes) to rank 0 over NVLink, and a counting merge kernel there (no sort).  On rank 0 *out is the merged result
+ * (protein ids index-wide, pairs ordered by (query, target), hits by (query, qpos, target, tpos)); on the other ranks
+ * *out carries only this shard's n_pairs / n_hits.  Queries of more than 4096 windows: KS_ERR_CAPACITY. */
+ks_status ks_shard_search_batch(ks_index *idx, ks_comm *comm, const ks_proteome *queries, uint32_t flags, uint64_t pid_base,
+                                ks_search_result **out);
 
 #ifdef __cplusplus
 }

@@ -20,6 +20,8 @@ STATUS_NAMES = {
 }
 KS_SEARCH_HITS = 1
 KS_SEARCH_DEVICE_ONLY = 2
+KS_SEARCH_QUERY_SKETCHES = 4
+KS_COMM_ID_BYTES = 128
 
 
 class ks_params(C.Structure):
@@ -105,6 +107,13 @@ SIGNATURES = {
     "ks_search_result_device_column": (C.c_void_p, [C.POINTER(ks_search_result), C.c_char_p]),
     "ks_query_upload": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ks_search_resident": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(C.POINTER(ks_search_result))]),
+    "ks_comm_unique_id": (C.c_int, [u8p]),
+    "ks_comm_create": (C.c_int, [u8p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "ks_comm_destroy": (None, [C.c_void_p]),
+    "ks_comm_rank": (C.c_int, [C.c_void_p]),
+    "ks_comm_world": (C.c_int, [C.c_void_p]),
+    "ks_shard_search_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64,
+                                        C.POINTER(C.POINTER(ks_search_result))]),
 }
 
 _lib = None

@@ -10,6 +10,8 @@
 #include <new>
 #include <time.h>
 
+#include <nccl.h>  // types and prototypes only: the library is bound with dlopen (NcclApi), never linked
+
 #include "dense.cuh"
 #include "host_util.hpp"
 #include "index_build.cuh"
@@ -280,8 +282,32 @@ uint64_t count_windows(const uint64_t* offs, uint64_t n_prot, uint32_t k) {
 
 }  // namespace
 
+// Test / experiment hooks, read from the environment ONCE when the handle is created (never on the hot path).
+struct Hooks {
+    bool sketch_general = false;  // KS_SKETCH_GENERAL: take the look-back sketch path at scaled == 1
+    int dense = -1;               // KS_DENSE: 0 switches the dense k-mer space path off, 1 drops its coverage condition
+    bool scatter_off = false;     // KS_SCATTER=0: no unstable partition on the general path
+    bool no_pipeline = false;     // KS_NO_PIPELINE: one copy + one launch instead of the chunked upload
+    bool dense_sort_library = false;  // KS_DENSE_SORT=library: the dense path's keys sorted by the library
+    bool timing = false;          // KS_TIMING: host-side stage timings on stderr
+    bool search_legacy = false;   // KS_SEARCH_LEGACY: the library-sorted query path for every batch
+    void read() {
+        sketch_general = getenv("KS_SKETCH_GENERAL") != nullptr;
+        const char* d = getenv("KS_DENSE");
+        dense = d ? (d[0] == '0' ? 0 : d[0] == '1' ? 1 : -1) : -1;
+        const char* sc = getenv("KS_SCATTER");
+        scatter_off = sc && sc[0] == '0';
+        no_pipeline = getenv("KS_NO_PIPELINE") != nullptr;
+        const char* ds = getenv("KS_DENSE_SORT");
+        dense_sort_library = ds && ds[0] == 'l';
+        timing = getenv("KS_TIMING") != nullptr;
+        search_legacy = getenv("KS_SEARCH_LEGACY") != nullptr;
+    }
+};
+
 struct ks_index {
     ks_params params{};
+    Hooks hooks;
     uint64_t max_hash = 0;
     int lz = 0;  // known-zero leading bits of every kept hash
     cudaStream_t stream = nullptr;
@@ -323,6 +349,10 @@ struct ks_index {
     Buf b_keys, b_key_grp, b_grp_start, b_t_size, b_t_abund, b_dir, b_counts, b_alt_hash, b_alt_loc, b_temp;
     int dir_bits = 0, dir_shift = 0;
     uint64_t U = 0, G = 0, n_ids = 0;
+    // query path: per-handle scratch (grow-only) and a pinned word block for the counts the host reads back
+    Buf b_q_ecount, b_q_pcount, b_q_hcount, b_q_sig, b_q_poff, b_q_hoff, b_q_ent_hash, b_q_ent_abund, b_q_win_key,
+        b_q_win_hoff, b_q_stage, b_q_totals;
+    uint64_t* h_words = nullptr;  // pinned u64[H_WORDS]
     // bookkeeping
     uint64_t l_sketch = 0, l_sort = 0, l_csr = 0, l_search = 0;
     bool t_upload = false, t_sketch = false, t_sort = false, t_csr = false;
@@ -335,6 +365,9 @@ struct ks_index {
 namespace {
 
 enum { EV_UP0, EV_UP1, EV_SK0, EV_SK1, EV_SO0, EV_SO1, EV_CS0, EV_CS1, EV_Q0, EV_Q1, EV_PART };
+// pinned words of a handle: [0, QT_WORDS) totals of the query kernels; then this rank's header of a sharded search;
+// then every rank's header
+enum { HW_TOTALS = 0, HW_HDR = QT_WORDS, HW_ALL = QT_WORDS + 8, H_WORDS = QT_WORDS + 8 + 4 * MAX_SHARDS };
 
 void ensure_ws(ks_index* x, size_t bytes) {
     if (bytes <= x->ws_bytes) return;
@@ -396,19 +429,25 @@ uint64_t expected_kept(const ks_index* x, uint64_t windows) {
 }
 
 // Sketch batch `b` into (out_hash, out_loc) of `capacity`; returns the number of tuples the batch produces
-// (which may exceed capacity, in which case nothing past capacity was written).
+// (which may exceed capacity, in which case nothing past capacity was written).  d_count / ws: the counter pair and
+// workspace of the launch -- the handle's own for its batches, private ones for ks_sketch_batch and the query sketch (a
+// pipelined dense batch that is still pending keeps its counts in the handle's).
 uint64_t run_sketch(ks_index* x, const DeviceBatch& b, uint32_t pid_base, uint64_t* out_hash, uint64_t* out_loc,
-                    uint64_t capacity) {
-    ensure_ws(x, sketch_workspace_bytes(b.n_res));
+                    uint64_t capacity, uint64_t* d_count = nullptr, void* ws = nullptr) {
+    if (!d_count) {
+        ensure_ws(x, sketch_workspace_bytes(b.n_res));
+        d_count = x->d_count;
+        ws = x->ws;
+    }
     SketchArgs a;
     a.residues = b.res; a.packed = b.packed ? 1 : 0; a.offsets = b.offs; a.n_res = b.n_res; a.n_prot = b.n_prot;
     a.k = x->params.ksize; a.moltype = x->params.moltype; a.max_hash = x->max_hash; a.pid_base = pid_base;
-    a.out_hash = out_hash; a.out_loc = out_loc; a.capacity = capacity; a.d_count = x->d_count; a.workspace = x->ws;
-    a.force_general = getenv("KS_SKETCH_GENERAL") ? 1 : 0;  // test hook: exercise the look-back path at scaled == 1
+    a.out_hash = out_hash; a.out_loc = out_loc; a.capacity = capacity; a.d_count = d_count; a.workspace = ws;
+    a.force_general = x->hooks.sketch_general ? 1 : 0;  // test hook: exercise the look-back path at scaled == 1
     uint64_t r[2] = {0, 0};
     for (int attempt = 0; attempt < 2; attempt++) {
         KS_CUDA(launch_sketch(a, x->stream, &x->l_sketch));
-        KS_CUDA(cudaMemcpyAsync(r, x->d_count, 16, cudaMemcpyDeviceToHost, x->stream));
+        KS_CUDA(cudaMemcpyAsync(r, d_count, 16, cudaMemcpyDeviceToHost, x->stream));
         KS_CUDA(cudaStreamSynchronize(x->stream));
         if ((r[1] >> 32) == 0) break;  // no zero hash on the exact path
         a.force_general = 1;           // a hash of exactly 0 must be dropped: redo on the look-back path
@@ -426,12 +465,11 @@ int bits_for_value(uint64_t v) {  // bits needed to hold values 0 .. v
 // well covered (otherwise the tables cost more than they save), and rank | protein | position must fit 64 bits.
 // KS_DENSE=0 switches the path off, KS_DENSE=1 drops the coverage condition (test hooks).
 bool dense_eligible(const ks_index* x, const DeviceBatch& b, uint64_t n_prot_before, uint64_t n_tuples_before) {
-    const char* env = getenv("KS_DENSE");
-    if (env && env[0] == '0') return false;
+    if (x->hooks.dense == 0) return false;
     const uint32_t k = x->params.ksize;
     if (x->params.moltype != KS_HP || k < (uint32_t)DENSE_MIN_K || k > (uint32_t)DENSE_MAX_K || x->max_hash != ~0ull) return false;
     if (x->dense_state < 0 || n_prot_before || n_tuples_before || b.n_prot == 0 || b.n_res >= (1ull << 32)) return false;
-    if (!(env && env[0] == '1') && b.n_windows < (1ull << k) / 4) return false;
+    if (x->hooks.dense != 1 && b.n_windows < (1ull << k) / 4) return false;
     return (int)k + 1 + bits_for_value(b.n_prot - 1) + bits_for_value(b.max_len) <= 64;  // rank' = 2 rank + 1 takes k + 1 bits
 }
 
@@ -460,9 +498,8 @@ bool repeat_heavy(const ks_index* x, uint64_t n) {
 // Unstable partition of the general path (dense_scatter.cuh, PairSortPlan): the batch is the index's only content, hashes
 // rarely repeat (the bucket sort orders equal hashes by loc, pair by pair) and the tuple count fits two scatter levels.  KS_SCATTER=0 switches it off (test hook).
 bool scatter_eligible(const ks_index* x, const DeviceBatch& b, uint64_t n_prot_before, uint64_t n_tuples_before, PairSortPlan* plan) {
-    const char* env = getenv("KS_SCATTER");
-    if (env && env[0] == '0') return false;
-    if (x->params.ksize > (uint32_t)SK_MAX_TEMPLATE_K || getenv("KS_SKETCH_GENERAL")) return false;
+    if (x->hooks.scatter_off) return false;
+    if (x->params.ksize > (uint32_t)SK_MAX_TEMPLATE_K || x->hooks.sketch_general) return false;
     if (n_prot_before || n_tuples_before || b.n_prot == 0 || b.n_windows > MAX_TUPLES) return false;
     const uint64_t n_est = expected_kept(x, b.n_windows);  // exact for scaled == 1
     // measured: with hashes that repeat the stable path wins -- the C4 slice (protein k7 scaled 10, every hash twice on
@@ -562,7 +599,7 @@ void sketch_resident_general(ks_index* x) {
 // chunk launches.  Returns false when the batch does not qualify (caller takes upload + sketch_resident).
 bool add_proteome_pipelined(ks_index* x, const ks_proteome* p) {
     constexpr int CHUNKS = 8;
-    if (x->params.ksize > (uint32_t)SK_MAX_TEMPLATE_K || getenv("KS_NO_PIPELINE"))  // (test hook)
+    if (x->params.ksize > (uint32_t)SK_MAX_TEMPLATE_K || x->hooks.no_pipeline)  // (test hook)
         return false;
     if (p->n_res < (64u << 20) || p->n_prot == 0) return false;  // small batches: one copy, one launch
     if (x->finalized) fail(KS_ERR_VALIDATION, "Validation error: index is finalized; ks_index_clear before adding more");
@@ -617,7 +654,7 @@ bool add_proteome_pipelined(ks_index* x, const ks_proteome* p) {
     a.k = x->params.ksize; a.moltype = x->params.moltype; a.max_hash = x->max_hash; a.pid_base = (uint32_t)x->n_prot;
     a.out_hash = x->d_hash + x->n_tuples; a.out_loc = x->d_loc + x->n_tuples; a.capacity = x->cap - x->n_tuples;
     a.d_count = x->d_count; a.workspace = x->ws;
-    a.force_general = getenv("KS_SKETCH_GENERAL") ? 1 : 0;  // test hook: the look-back path at scaled == 1
+    a.force_general = x->hooks.sketch_general ? 1 : 0;  // test hook: the look-back path at scaled == 1
     if (scat) { a.out_hash = nullptr; a.out_loc = nullptr; a.capacity = 0; scatter_args(x, &a); }
     if (!dense) KS_CUDA(launch_sketch_prepare(a, x->stream, &x->l_sketch));  // (dense_begin has done it)
     const uint64_t nt = (b.n_res + SK_TILE - 1) / SK_TILE;
@@ -734,8 +771,7 @@ bool dense_begin(ks_index* x) {
     x->n_tuples = n;
     // the key sort: hand-written (two scatter levels + a shared-memory sort per bucket) when the input fits its scheme,
     // the library's otherwise (KS_DENSE_SORT=library is a test hook)
-    const char* sort_env = getenv("KS_DENSE_SORT");
-    x->dense_plan = sort_env && sort_env[0] == 'l' ? DenseSortPlan() : dense_sort_plan(n, (int)k + 1);
+    x->dense_plan = x->hooks.dense_sort_library ? DenseSortPlan() : dense_sort_plan(n, (int)k + 1);
     if (x->dense_plan.custom) {
         char* work = x->b_dense_work.ensure<char>(ar, x->dense_plan.bytes);
         KS_CUDA(cudaMemsetAsync(work + x->dense_plan.off_small, 0, x->dense_plan.small_bytes, x->stream));
@@ -834,7 +870,7 @@ void finalize(ks_index* x) {
         if (dense_finalize(x)) return;
         materialize_pending(x);  // not applicable after all: the general path from here on
     }
-    const bool dbg = getenv("KS_TIMING") != nullptr;
+    const bool dbg = x->hooks.timing;
     double t0 = dbg ? now_ms() : 0;
     const uint64_t n = x->n_tuples;
     if (n > MAX_TUPLES) fail(KS_ERR_CAPACITY, "more than 2^31-1 tuples on one shard: shard the proteome over more GPUs");
@@ -947,10 +983,13 @@ ks_sketch* sketch_to_host(const Grouped& g, const uint64_t* tuple_hash, const ui
     return s;
 }
 
+// What a ks_search_result owns besides its struct: the device block (until it has been copied out, or for as long as the
+// result lives with KS_SEARCH_DEVICE_ONLY) and the pinned host copy; both have layout L (search.cuh).
 struct ResultDevice {
-    Arena* arena;
-    std::map<std::string, void*> cols;
-    void* pinned = nullptr;   // one pinned block that holds every pair / hit column of the host copy
+    Arena* arena = nullptr;  // owns `block`
+    void* block = nullptr;
+    ResultLayout L;
+    void* pinned = nullptr;
     size_t pinned_bytes = 0;
 };
 
@@ -1006,6 +1045,7 @@ ks_status ks_index_create(const ks_params* params, ks_index** out) {
         if (params->device < 0 || params->device >= n) fail(KS_ERR_NO_DEVICE, "CUDA device ordinal out of range");
         ks_index* x = new ks_index();
         x->params = *params;
+        x->hooks.read();
         x->max_hash = ks_max_hash(params->scaled);
         x->lz = clz64(x->max_hash);
         try {
@@ -1020,6 +1060,7 @@ ks_status ks_index_create(const ks_params* params, ks_index** out) {
             KS_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
             x->arena = new Arena(x->stream, &x->live_bytes);
             x->d_count = x->arena->alloc<uint64_t>(2);
+            KS_CUDA(cudaHostAlloc((void**)&x->h_words, H_WORDS * 8, cudaHostAllocDefault));
         } catch (...) {
             ks_index_destroy(x);
             throw;
@@ -1036,6 +1077,7 @@ void ks_index_destroy(ks_index* x) {
     if (x->stream) cudaStreamSynchronize(x->stream);
     for (auto& e : x->ev) if (e) cudaEventDestroy(e);
     for (auto& e : x->ev_chunk) if (e) cudaEventDestroy(e);
+    if (x->h_words) cudaFreeHost(x->h_words);
     if (x->copy_stream) { cudaStreamSynchronize(x->copy_stream); cudaStreamDestroy(x->copy_stream); }
     if (x->stream) cudaStreamDestroy(x->stream);
     delete x;
@@ -1165,7 +1207,9 @@ ks_status ks_sketch_batch(ks_index* x, const ks_proteome* p, ks_sketch** out) {
         const uint64_t cap = b.n_windows;
         uint64_t* h = keep.alloc<uint64_t>(cap);
         uint64_t* l = keep.alloc<uint64_t>(cap);
-        uint64_t n = run_sketch(x, b, 0, h, l, cap);
+        uint64_t* cnt = tmp.alloc<uint64_t>(2);  // private: a pending pipelined batch keeps its counts in the handle's
+        void* ws = tmp.alloc<char>(sketch_workspace_bytes(b.n_res));
+        uint64_t n = run_sketch(x, b, 0, h, l, cap, cnt, ws);
         Grouped g;
         group_by_owner(keep, tmp, h, l, n, (uint32_t)p->n_prot, x->end_bit(), &g, &x->l_sketch);
         *out = sketch_to_host(g, h, l, n, p->n_prot, x->stream);
@@ -1224,6 +1268,177 @@ void ks_csr_free(ks_csr* c) {
 }
 
 // ---- search --------------------------------------------------------------------------------------
+}  // extern "C"
+
+namespace {
+
+QueryScratch ensure_query_scratch(ks_index* x, uint64_t nq, uint64_t n_res, bool hits) {
+    Arena* ar = x->arena;
+    QueryScratch s;
+    s.e_count = x->b_q_ecount.ensure<uint32_t>(ar, nq);
+    s.p_count = x->b_q_pcount.ensure<uint32_t>(ar, nq);
+    s.h_count = x->b_q_hcount.ensure<uint64_t>(ar, nq);
+    s.sig_ptr = x->b_q_sig.ensure<uint64_t>(ar, nq + 1);
+    s.pair_off = x->b_q_poff.ensure<uint64_t>(ar, nq + 1);
+    s.hit_off = x->b_q_hoff.ensure<uint64_t>(ar, nq + 1);
+    s.ent_hash = x->b_q_ent_hash.ensure<uint64_t>(ar, n_res);
+    s.ent_abund = x->b_q_ent_abund.ensure<uint32_t>(ar, n_res);
+    if (hits) {
+        s.win_key = x->b_q_win_key.ensure<uint32_t>(ar, n_res);
+        s.win_hoff = x->b_q_win_hoff.ensure<uint32_t>(ar, n_res);
+    }
+    const uint64_t want = std::max<uint64_t>(1u << 16, n_res / 2);  // first guess; grows to what a batch needed
+    if (x->b_q_stage.bytes < want * sizeof(StagedPair)) x->b_q_stage.ensure<StagedPair>(ar, want);
+    s.stage = (StagedPair*)x->b_q_stage.p;
+    s.stage_cap = x->b_q_stage.bytes / sizeof(StagedPair);
+    s.totals = x->b_q_totals.ensure<uint64_t>(ar, QT_WORDS);
+    return s;
+}
+
+struct SearchOut {
+    void* block = nullptr;
+    ResultLayout L;
+};
+
+// Device side of one search of the resident query batch; the result block is allocated from `keep`.  Synchronises the
+// stream once on the hand-written path (the totals that size the block).
+SearchOut search_resident_device(ks_index* x, Arena& keep, bool hits, bool sketches, bool wire, uint32_t pid_base) {
+    cudaStream_t st = x->stream;
+    const DeviceBatch& qb = x->qbatch;
+    const uint32_t k = x->params.ksize;
+    const uint64_t maxw = qb.max_len >= k ? qb.max_len - k + 1 : 0;
+    SearchOut o;
+    KS_CUDA(cudaEventRecord(x->ev[EV_Q0], st));
+    if (maxw > QK_MAX_WINDOWS || x->hooks.search_legacy) {
+        if (wire) fail(KS_ERR_CAPACITY, "sharded search: queries of more than 4096 k-mer windows are not supported");
+        Arena tmp(st, &x->live_bytes);
+        uint64_t* qh = tmp.alloc<uint64_t>(qb.n_windows);
+        uint64_t* ql = tmp.alloc<uint64_t>(qb.n_windows);
+        uint64_t* cnt = tmp.alloc<uint64_t>(2);
+        void* ws = tmp.alloc<char>(sketch_workspace_bytes(qb.n_res));
+        const uint64_t nqt = run_sketch(x, qb, 0, qh, ql, qb.n_windows, cnt, ws);
+        search_device_legacy(tmp, view_of(x), qh, ql, nqt, (uint32_t)qb.n_prot, k, x->end_bit(), hits, sketches, pid_base, keep,
+                             &o.block, &o.L, &x->l_search);
+    } else {
+        QueryScratch s = ensure_query_scratch(x, qb.n_prot, qb.n_res, hits);
+        QueryBatchView qv{qb.res, qb.offs, (uint32_t)qb.n_prot, qb.n_res, (uint32_t)maxw};
+        uint64_t* t = x->h_words + HW_TOTALS;
+        for (int attempt = 0;; attempt++) {
+            KS_CUDA(launch_query_phase1(qv, view_of(x), k, x->params.moltype, x->max_hash, hits, s, st, &x->l_search));
+            KS_CUDA(cudaMemcpyAsync(t, s.totals, QT_WORDS * 8, cudaMemcpyDeviceToHost, st));
+            KS_CUDA(cudaStreamSynchronize(st));
+            if (t[QT_FLAGS] & QF_HITS_OVERFLOW) fail(KS_ERR_CAPACITY, "one query has 2^32 or more hits");
+            if (t[QT_PAIRS] <= s.stage_cap) break;
+            if (attempt) fail(KS_ERR_CUDA, "internal error: the pair staging buffer overflowed twice");
+            x->b_q_stage.ensure<StagedPair>(x->arena, t[QT_PAIRS] + t[QT_PAIRS] / 4);  // counted in full: now it fits
+            s.stage = (StagedPair*)x->b_q_stage.p;
+            s.stage_cap = x->b_q_stage.bytes / sizeof(StagedPair);
+        }
+        o.L = result_layout(qb.n_prot, t[QT_PAIRS], t[QT_HITS], t[QT_ENTRIES], hits, sketches, wire, qb.n_res);
+        o.block = keep.alloc<char>(o.L.bytes);
+        KS_CUDA(launch_query_phase2(qv, view_of(x), k, pid_base, s, o.L, o.block, st, &x->l_search));
+    }
+    KS_CUDA(cudaEventRecord(x->ev[EV_Q1], st));
+    return o;
+}
+
+void set_host_columns(ks_search_result* r, const ResultLayout& L, char* base) {
+    r->q_sig_ptr = (uint64_t*)(base + L.off_sig_ptr);
+    uint32_t** u32[N_PAIR_U32] = {&r->pair_qid, &r->pair_pid, &r->intersect_hashes, &r->q_size, &r->t_size};
+    for (int i = 0; i < N_PAIR_U32; i++) *u32[i] = (uint32_t*)(base + L.off_u32[i]);
+    r->n_weighted_found = (uint64_t*)(base + L.off_u64[0]);
+    r->total_weighted_hashes = (uint64_t*)(base + L.off_u64[1]);
+    double** sc[N_SCORE_COLS] = {&r->containment, &r->containment_target_in_query, &r->max_containment, &r->jaccard,
+                                 &r->query_containment_ani, &r->match_containment_ani, &r->average_containment_ani,
+                                 &r->max_containment_ani, &r->average_abund, &r->median_abund, &r->std_abund,
+                                 &r->f_weighted_target_in_query};
+    for (int i = 0; i < N_SCORE_COLS; i++) *sc[i] = (double*)(base + L.off_score[i]);
+    if (L.hits) {
+        uint32_t** h32[N_HIT_U32] = {&r->hit_qid, &r->hit_pid, &r->hit_qpos, &r->hit_tpos};
+        for (int i = 0; i < N_HIT_U32; i++) *h32[i] = (uint32_t*)(base + L.off_hit32[i]);
+        r->hit_hash = (uint64_t*)(base + L.off_hit_hash);
+    }
+    if (L.sketches) {
+        r->q_mins = (uint64_t*)(base + L.off_q_mins);
+        r->q_abunds = (uint64_t*)(base + L.off_q_abunds);
+    }
+}
+
+// One D2H copy of the whole block into a pooled pinned block; the device block is given back.
+void result_to_host(ks_index* x, ks_search_result* r, ResultDevice* rd) {
+    rd->pinned = pinned_get(rd->L.bytes, &rd->pinned_bytes);
+    KS_CUDA(cudaMemcpyAsync(rd->pinned, rd->block, rd->L.bytes, cudaMemcpyDeviceToHost, x->stream));
+    KS_CUDA(cudaStreamSynchronize(x->stream));
+    set_host_columns(r, rd->L, (char*)rd->pinned);
+    // the host copy is complete: give the device block back now, so that the result no longer depends on the index
+    // (and its stream) staying alive
+    delete rd->arena;
+    rd->arena = nullptr;
+    rd->block = nullptr;
+}
+
+ks_search_result* new_result(ks_index* x, ResultDevice** rd_out) {
+    ks_search_result* r = (ks_search_result*)calloc(1, sizeof(ks_search_result));
+    if (!r) throw std::bad_alloc();
+    ResultDevice* rd = new ResultDevice();
+    rd->arena = new Arena(x->stream, &x->live_bytes);
+    r->device_block = rd;
+    *rd_out = rd;
+    return r;
+}
+
+// ---- NCCL, bound at run time (the library loads without it; multi-GPU calls then return KS_ERR_NCCL) ------------------
+struct NcclApi {
+    DlLib lib;
+    decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+    decltype(&ncclCommInitRank) CommInitRank = nullptr;
+    decltype(&ncclCommDestroy) CommDestroy = nullptr;
+    decltype(&ncclAllGather) AllGather = nullptr;
+    decltype(&ncclSend) Send = nullptr;
+    decltype(&ncclRecv) Recv = nullptr;
+    decltype(&ncclGroupStart) GroupStart = nullptr;
+    decltype(&ncclGroupEnd) GroupEnd = nullptr;
+    decltype(&ncclGetErrorString) GetErrorString = nullptr;
+    bool ok = false;
+    static const char* const* names() {
+        static const char* const n[] = {"libnccl.so.2", "libnccl.so", nullptr};
+        return n;
+    }
+    NcclApi() : lib(names()) {
+        GetUniqueId = lib.sym<decltype(GetUniqueId)>("ncclGetUniqueId");
+        CommInitRank = lib.sym<decltype(CommInitRank)>("ncclCommInitRank");
+        CommDestroy = lib.sym<decltype(CommDestroy)>("ncclCommDestroy");
+        AllGather = lib.sym<decltype(AllGather)>("ncclAllGather");
+        Send = lib.sym<decltype(Send)>("ncclSend");
+        Recv = lib.sym<decltype(Recv)>("ncclRecv");
+        GroupStart = lib.sym<decltype(GroupStart)>("ncclGroupStart");
+        GroupEnd = lib.sym<decltype(GroupEnd)>("ncclGroupEnd");
+        GetErrorString = lib.sym<decltype(GetErrorString)>("ncclGetErrorString");
+        ok = GetUniqueId && CommInitRank && CommDestroy && AllGather && Send && Recv && GroupStart && GroupEnd && GetErrorString;
+    }
+};
+
+NcclApi& nccl() {
+    static NcclApi api;  // process-wide; under torch this resolves to the libnccl.so.2 torch has already loaded
+    if (!api.ok) fail(KS_ERR_NCCL, "NCCL error: libnccl.so.2 could not be loaded");
+    return api;
+}
+
+void nccl_check(ncclResult_t r, const char* what) {
+    if (r == ncclSuccess) return;
+    fail(KS_ERR_NCCL, std::string("NCCL error: ") + nccl().GetErrorString(r) + " (" + what + ")");
+}
+#define KS_NCCL(x) nccl_check((x), #x)
+
+}  // namespace
+
+struct ks_comm {
+    ncclComm_t comm = nullptr;
+    int rank = 0, world = 1, device = 0;
+};
+
+extern "C" {
+
 ks_status ks_query_upload(ks_index* x, const ks_proteome* q) {
     return guarded([&] {
         if (!x || !q) fail(KS_ERR_VALIDATION, "Validation error: null argument");
@@ -1238,90 +1453,25 @@ ks_status ks_search_resident(ks_index* x, uint32_t flags, ks_search_result** out
         if (!x->finalized) fail(KS_ERR_NOT_FINALIZED, "index is not finalized");
         if (!x->qbatch.valid) fail(KS_ERR_VALIDATION, "Validation error: no query batch is resident");
         x->use();
-        cudaStream_t st = x->stream;
-        const DeviceBatch& qb = x->qbatch;
-        Arena* keep = new Arena(st, &x->live_bytes);
-        ks_search_result* r = (ks_search_result*)calloc(1, sizeof(ks_search_result));
-        ResultDevice* rd = new ResultDevice{keep, {}};
-        if (!r) { delete rd; delete keep; throw std::bad_alloc(); }
-        r->device_block = rd;
-        const bool dbg = getenv("KS_TIMING") != nullptr;
+        ResultDevice* rd = nullptr;
+        ks_search_result* r = new_result(x, &rd);
+        const bool dbg = x->hooks.timing;
         const double t0 = dbg ? now_ms() : 0;
-        double t1 = 0, t2 = 0;
         try {
-            Arena tmp(st, &x->live_bytes);
-            KS_CUDA(cudaEventRecord(x->ev[EV_Q0], st));
-            uint64_t* qh = tmp.alloc<uint64_t>(qb.n_windows);
-            uint64_t* ql = tmp.alloc<uint64_t>(qb.n_windows);
-            const uint64_t nqt = run_sketch(x, qb, 0, qh, ql, qb.n_windows);
-            Grouped qs;
-            SearchDevice sd;
-            search_device(*keep, tmp, view_of(x), qh, ql, nqt, (uint32_t)qb.n_prot, x->params.ksize, x->end_bit(),
-                          (flags & KS_SEARCH_HITS) != 0, &qs, &sd, &x->l_search);
-            KS_CUDA(cudaEventRecord(x->ev[EV_Q1], st));
-            if (dbg) t1 = now_ms();
-            r->n_queries = qb.n_prot;
-            r->n_pairs = sd.n_pairs;
-            r->n_hits = sd.n_hits;
-            static const char* score_names[N_SCORE_COLS] = {
-                "containment", "containment_target_in_query", "max_containment", "jaccard", "query_containment_ani",
-                "match_containment_ani", "average_containment_ani", "max_containment_ani", "average_abund",
-                "median_abund", "std_abund", "f_weighted_target_in_query"};
-            rd->cols["pair_qid"] = sd.pair_qid; rd->cols["pair_pid"] = sd.pair_pid;
-            rd->cols["intersect_hashes"] = sd.intersect; rd->cols["q_size"] = sd.q_size; rd->cols["t_size"] = sd.t_size;
-            rd->cols["n_weighted_found"] = sd.n_weighted_found; rd->cols["total_weighted_hashes"] = sd.total_weighted;
-            for (int i = 0; i < N_SCORE_COLS; i++) rd->cols[score_names[i]] = sd.score[i];
-            rd->cols["hit_qid"] = sd.hit_qid; rd->cols["hit_pid"] = sd.hit_pid; rd->cols["hit_qpos"] = sd.hit_qpos;
-            rd->cols["hit_tpos"] = sd.hit_tpos; rd->cols["hit_hash"] = sd.hit_hash;
-            rd->cols["q_sig_ptr"] = qs.sig_ptr; rd->cols["q_mins"] = qs.ent_hash;
-            // query sketches always come back (they are small): md5 / |Q| need them
-            r->q_sig_ptr = to_host(qs.sig_ptr, qb.n_prot + 1, st);
-            r->q_mins = to_host(qs.ent_hash, qs.n_entries, st);
-            uint32_t* first = to_host(qs.ent_first, qs.n_entries + 1, st);
-            if (!(flags & KS_SEARCH_DEVICE_ONLY)) {
-                const uint64_t np = sd.n_pairs, nh = (flags & KS_SEARCH_HITS) ? sd.n_hits : 0;
-                const size_t need = np * (5 * 4 + 2 * 8 + N_SCORE_COLS * 8) + nh * (4 * 4 + 8) + 64 * 32;
-                rd->pinned = pinned_get(need, &rd->pinned_bytes);
-                char* cur = (char*)rd->pinned;
-                auto take = [&](const void* dev, size_t bytes) -> void* {
-                    void* h = cur;
-                    if (bytes) KS_CUDA(cudaMemcpyAsync(h, dev, bytes, cudaMemcpyDeviceToHost, st));
-                    cur += (bytes + 63) & ~(size_t)63;
-                    return h;
-                };
-                r->pair_qid = (uint32_t*)take(sd.pair_qid, np * 4); r->pair_pid = (uint32_t*)take(sd.pair_pid, np * 4);
-                r->intersect_hashes = (uint32_t*)take(sd.intersect, np * 4);
-                r->q_size = (uint32_t*)take(sd.q_size, np * 4); r->t_size = (uint32_t*)take(sd.t_size, np * 4);
-                r->n_weighted_found = (uint64_t*)take(sd.n_weighted_found, np * 8);
-                r->total_weighted_hashes = (uint64_t*)take(sd.total_weighted, np * 8);
-                double** dst[N_SCORE_COLS] = {&r->containment, &r->containment_target_in_query, &r->max_containment,
-                                              &r->jaccard, &r->query_containment_ani, &r->match_containment_ani,
-                                              &r->average_containment_ani, &r->max_containment_ani, &r->average_abund,
-                                              &r->median_abund, &r->std_abund, &r->f_weighted_target_in_query};
-                for (int i = 0; i < N_SCORE_COLS; i++) *dst[i] = (double*)take(sd.score[i], np * 8);
-                if (flags & KS_SEARCH_HITS) {
-                    r->hit_qid = (uint32_t*)take(sd.hit_qid, nh * 4); r->hit_pid = (uint32_t*)take(sd.hit_pid, nh * 4);
-                    r->hit_qpos = (uint32_t*)take(sd.hit_qpos, nh * 4); r->hit_tpos = (uint32_t*)take(sd.hit_tpos, nh * 4);
-                    r->hit_hash = (uint64_t*)take(sd.hit_hash, nh * 8);
-                }
-            }
-            KS_CUDA(cudaStreamSynchronize(st));
-            if (dbg) t2 = now_ms();
-            r->q_abunds = (uint64_t*)malloc((qs.n_entries ? qs.n_entries : 1) * 8);
-            if (!r->q_abunds) throw std::bad_alloc();
-            for (uint64_t e = 0; e < qs.n_entries; e++) r->q_abunds[e] = first[e + 1] - first[e];
-            free(first);
+            const SearchOut o = search_resident_device(x, *rd->arena, (flags & KS_SEARCH_HITS) != 0,
+                                                       (flags & KS_SEARCH_QUERY_SKETCHES) != 0, false, 0);
+            const double t1 = dbg ? now_ms() : 0;
+            rd->block = o.block;
+            rd->L = o.L;
+            r->n_queries = o.L.nq;
+            r->n_pairs = o.L.n_pairs;
+            r->n_hits = o.L.n_hits;
+            if (flags & KS_SEARCH_DEVICE_ONLY) KS_CUDA(cudaStreamSynchronize(x->stream));
+            else result_to_host(x, r, rd);
             KS_CUDA(cudaEventElapsedTime(&r->ms_device, x->ev[EV_Q0], x->ev[EV_Q1]));
             x->ms_search = r->ms_device;
-            if (dbg) fprintf(stderr, "[ks] search: device %.3f ms; host: launch+syncs %.3f ms, read-back %.3f ms, tail %.3f ms\n",
-                             r->ms_device, t1 - t0, t2 - t1, now_ms() - t2);
-            if (!(flags & KS_SEARCH_DEVICE_ONLY)) {
-                // the host copy is complete: give the device columns back now, so that the result no longer
-                // depends on the index (and its stream) staying alive
-                delete rd->arena;
-                rd->arena = nullptr;
-                rd->cols.clear();
-            }
+            if (dbg) fprintf(stderr, "[ks] search: device %.3f ms; host: kernels + count read-back %.3f ms, block read-back %.3f ms\n",
+                             r->ms_device, t1 - t0, now_ms() - t1);
         } catch (...) {
             ks_search_result_free(r);
             throw;
@@ -1337,21 +1487,160 @@ ks_status ks_search_batch(ks_index* x, const ks_proteome* queries, uint32_t flag
 
 void* ks_search_result_device_column(const ks_search_result* r, const char* name) {
     if (!r || !r->device_block || !name) return nullptr;
-    ResultDevice* rd = (ResultDevice*)r->device_block;
-    auto it = rd->cols.find(name);
-    return it == rd->cols.end() ? nullptr : it->second;
+    const ResultDevice* rd = (const ResultDevice*)r->device_block;
+    if (!rd->block) return nullptr;
+    char* b = (char*)rd->block;
+    const ResultLayout& L = rd->L;
+    static const char* u32n[N_PAIR_U32] = {"pair_qid", "pair_pid", "intersect_hashes", "q_size", "t_size"};
+    static const char* u64n[N_PAIR_U64] = {"n_weighted_found", "total_weighted_hashes"};
+    static const char* scn[N_SCORE_COLS] = {
+        "containment", "containment_target_in_query", "max_containment", "jaccard", "query_containment_ani",
+        "match_containment_ani", "average_containment_ani", "max_containment_ani", "average_abund", "median_abund",
+        "std_abund", "f_weighted_target_in_query"};
+    static const char* h32n[N_HIT_U32] = {"hit_qid", "hit_pid", "hit_qpos", "hit_tpos"};
+    for (int i = 0; i < N_PAIR_U32; i++) if (!strcmp(name, u32n[i])) return b + L.off_u32[i];
+    for (int i = 0; i < N_PAIR_U64; i++) if (!strcmp(name, u64n[i])) return b + L.off_u64[i];
+    for (int i = 0; i < N_SCORE_COLS; i++) if (!strcmp(name, scn[i])) return b + L.off_score[i];
+    if (L.hits) {
+        for (int i = 0; i < N_HIT_U32; i++) if (!strcmp(name, h32n[i])) return b + L.off_hit32[i];
+        if (!strcmp(name, "hit_hash")) return b + L.off_hit_hash;
+    }
+    if (!strcmp(name, "q_sig_ptr")) return b + L.off_sig_ptr;
+    if (L.sketches && !strcmp(name, "q_mins")) return b + L.off_q_mins;
+    if (L.sketches && !strcmp(name, "q_abunds")) return b + L.off_q_abunds;
+    return nullptr;
 }
 
 void ks_search_result_free(ks_search_result* r) {
     if (!r) return;
-    free(r->q_sig_ptr); free(r->q_mins); free(r->q_abunds);  // the pair / hit columns live in the pinned block
-    if (r->device_block) {
+    if (r->device_block) {  // every column lives in the pinned block (or on the device only)
         ResultDevice* rd = (ResultDevice*)r->device_block;
         pinned_put(rd->pinned, rd->pinned_bytes);
         delete rd->arena;
         delete rd;
     }
     free(r);
+}
+
+// ---- multi-GPU: one process per GPU, the proteome sharded by protein ------------------------------------------------
+ks_status ks_comm_unique_id(uint8_t id[KS_COMM_ID_BYTES]) {
+    return guarded([&] {
+        if (!id) fail(KS_ERR_VALIDATION, "Validation error: null argument");
+        static_assert(sizeof(ncclUniqueId) == KS_COMM_ID_BYTES, "ncclUniqueId is 128 bytes");
+        ncclUniqueId u;
+        KS_NCCL(nccl().GetUniqueId(&u));
+        memcpy(id, &u, sizeof u);
+    });
+}
+
+ks_status ks_comm_create(const uint8_t id[KS_COMM_ID_BYTES], int rank, int world, int device, ks_comm** out) {
+    return guarded([&] {
+        if (!id || !out) fail(KS_ERR_VALIDATION, "Validation error: null argument");
+        if (world < 1 || world > MAX_SHARDS || rank < 0 || rank >= world)
+            fail(KS_ERR_VALIDATION, "Validation error: rank / world out of range (at most 16 shards)");
+        const int n = ks_device_count();
+        if (n == 0) fail(KS_ERR_NO_DEVICE, "no CUDA device: kmerseek_b200 has no CPU fallback");
+        if (device < 0 || device >= n) fail(KS_ERR_NO_DEVICE, "CUDA device ordinal out of range");
+        KS_CUDA(cudaSetDevice(device));
+        ncclUniqueId u;
+        memcpy(&u, id, sizeof u);
+        ks_comm* c = new ks_comm();
+        c->rank = rank; c->world = world; c->device = device;
+        try {
+            KS_NCCL(nccl().CommInitRank(&c->comm, world, u, rank));
+        } catch (...) {
+            delete c;
+            throw;
+        }
+        *out = c;
+    });
+}
+
+void ks_comm_destroy(ks_comm* c) {
+    if (!c) return;
+    if (c->comm) {
+        cudaSetDevice(c->device);
+        try { nccl().CommDestroy(c->comm); } catch (...) {}
+    }
+    delete c;
+}
+int ks_comm_rank(const ks_comm* c) { return c ? c->rank : 0; }
+int ks_comm_world(const ks_comm* c) { return c ? c->world : 1; }
+
+ks_status ks_shard_search_batch(ks_index* x, ks_comm* c, const ks_proteome* queries, uint32_t flags, uint64_t pid_base,
+                                ks_search_result** out) {
+    ks_status up = ks_query_upload(x, queries);
+    if (up != KS_OK) return up;
+    return guarded([&] {
+        if (!c || !out) fail(KS_ERR_VALIDATION, "Validation error: null argument");
+        if (!x->finalized) fail(KS_ERR_NOT_FINALIZED, "index is not finalized");
+        if (c->device != x->params.device) fail(KS_ERR_VALIDATION, "Validation error: communicator and index are on different devices");
+        if (pid_base + x->n_prot > 0xffffffffull) fail(KS_ERR_CAPACITY, "more than 2^32-1 proteins over all shards");
+        x->use();
+        cudaStream_t st = x->stream;
+        NcclApi& N = nccl();
+        const bool hits = (flags & KS_SEARCH_HITS) != 0;
+        const bool root = c->rank == 0;
+        const bool sketches = root && (flags & KS_SEARCH_QUERY_SKETCHES) != 0;  // replicated queries: rank 0's copy is the result's
+        ResultDevice* rd = nullptr;
+        ks_search_result* r = new_result(x, &rd);
+        try {
+            Arena tmp(st, &x->live_bytes);
+            // 1. this shard, in wire layout (the merge offsets travel with the block); protein ids already index-wide
+            const SearchOut mine = search_resident_device(x, tmp, hits, sketches, true, (uint32_t)pid_base);
+            // 2. every rank's counts: one all-gather of four words
+            uint64_t* hdr = x->h_words + HW_HDR;
+            hdr[0] = mine.L.n_pairs; hdr[1] = mine.L.n_hits; hdr[2] = mine.L.n_entries; hdr[3] = mine.L.bytes;
+            uint64_t* d_hdr = tmp.alloc<uint64_t>(4);
+            uint64_t* d_all = tmp.alloc<uint64_t>(4 * (size_t)c->world);
+            KS_CUDA(cudaMemcpyAsync(d_hdr, hdr, 32, cudaMemcpyHostToDevice, st));
+            KS_NCCL(N.AllGather(d_hdr, d_all, 4, ncclUint64, c->comm, st));
+            uint64_t* all = x->h_words + HW_ALL;
+            KS_CUDA(cudaMemcpyAsync(all, d_all, 32 * (size_t)c->world, cudaMemcpyDeviceToHost, st));
+            KS_CUDA(cudaStreamSynchronize(st));
+            r->n_queries = mine.L.nq;
+            if (!root) {
+                // 3. ship the block to rank 0: one send
+                KS_NCCL(N.GroupStart());
+                KS_NCCL(N.Send(mine.block, mine.L.bytes, ncclUint8, 0, c->comm, st));
+                KS_NCCL(N.GroupEnd());
+                KS_CUDA(cudaStreamSynchronize(st));
+                r->n_pairs = mine.L.n_pairs;  // this shard's counts; the columns are on rank 0
+                r->n_hits = mine.L.n_hits;
+            } else {
+                MergeArgs m;
+                m.n_shards = c->world; m.nq = (uint32_t)mine.L.nq; m.q_offs = x->qbatch.offs; m.k = x->params.ksize;
+                m.shard[0].block = mine.block; m.shard[0].layout = mine.L;
+                uint64_t np = mine.L.n_pairs, nh = mine.L.n_hits;
+                KS_NCCL(N.GroupStart());
+                for (int s = 1; s < c->world; s++) {
+                    const uint64_t* h = all + 4 * s;
+                    const ResultLayout Ls = result_layout(mine.L.nq, h[0], h[1], 0, hits, false, true, x->qbatch.n_res);
+                    if (Ls.bytes != h[3]) fail(KS_ERR_NCCL, "NCCL error: shard result layout mismatch between ranks");
+                    void* blk = tmp.alloc<char>(Ls.bytes);
+                    KS_NCCL(N.Recv(blk, Ls.bytes, ncclUint8, s, c->comm, st));
+                    m.shard[s].block = blk; m.shard[s].layout = Ls;
+                    np += h[0]; nh += h[1];
+                }
+                KS_NCCL(N.GroupEnd());
+                // 4. merge by counting (launch_merge): (query, target) order over ascending shards
+                rd->L = result_layout(mine.L.nq, np, nh, mine.L.n_entries, hits, sketches);
+                rd->block = rd->arena->alloc<char>(rd->L.bytes);
+                m.out_block = rd->block; m.out_layout = rd->L;
+                KS_CUDA(launch_merge(m, st, &x->l_search));
+                r->n_pairs = np;
+                r->n_hits = nh;
+                if (flags & KS_SEARCH_DEVICE_ONLY) KS_CUDA(cudaStreamSynchronize(st));
+                else result_to_host(x, r, rd);
+            }
+            KS_CUDA(cudaEventElapsedTime(&r->ms_device, x->ev[EV_Q0], x->ev[EV_Q1]));
+            x->ms_search = r->ms_device;
+        } catch (...) {
+            ks_search_result_free(r);
+            throw;
+        }
+        *out = r;
+    });
 }
 
 }  // extern "C"

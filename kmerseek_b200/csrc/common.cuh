@@ -22,6 +22,40 @@ __host__ __device__ __forceinline__ uint64_t fmix64(uint64_t k) {
 __host__ __device__ __forceinline__ uint64_t mix_k1(uint64_t k1) { return rotl64(k1 * C1, 31) * C2; }
 __host__ __device__ __forceinline__ uint64_t mix_k2(uint64_t k2) { return rotl64(k2 * C2, 33) * C1; }
 
+// MurmurHash3_x64_128 (seed 42, low word) of k bytes, one byte at a time: the generic-k sketch kernel (k > 32) and the
+// query kernel (queries are small) use it; the templated limb version of sketch.cu is the fast path of the build.
+__device__ __forceinline__ uint64_t murmur_bytes(const uint8_t* s, uint32_t k) {
+    uint64_t h1 = SEED, h2 = SEED;
+    uint32_t nb = k / 16;
+    for (uint32_t b = 0; b < nb; b++) {
+        uint64_t k1 = 0, k2 = 0;
+        for (int i = 0; i < 8; i++) {
+            k1 |= (uint64_t)s[16 * b + i] << (8 * i);
+            k2 |= (uint64_t)s[16 * b + 8 + i] << (8 * i);
+        }
+        h1 ^= mix_k1(k1);
+        h1 = rotl64(h1, 27) + h2;
+        h1 = h1 * 5 + 0x52dce729;
+        h2 ^= mix_k2(k2);
+        h2 = rotl64(h2, 31) + h1;
+        h2 = h2 * 5 + 0x38495ab5;
+    }
+    const uint8_t* t = s + 16 * nb;
+    uint32_t rem = k & 15;
+    uint64_t k1 = 0, k2 = 0;
+    for (uint32_t i = 8; i < rem; i++) k2 |= (uint64_t)t[i] << (8 * (i - 8));
+    for (uint32_t i = 0; i < (rem < 8 ? rem : 8); i++) k1 |= (uint64_t)t[i] << (8 * i);
+    if (rem > 8) h2 ^= mix_k2(k2);
+    if (rem > 0) h1 ^= mix_k1(k1);
+    h1 ^= k;
+    h2 ^= k;
+    h1 += h2;
+    h2 += h1;
+    h1 = fmix64(h1);
+    h2 = fmix64(h2);
+    return h1 + h2;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Single-pass chained scan state ("decoupled look-back").  One 64-bit word per tile carries the
 // flag in the top two bits and the value in the low 62, so a reader never sees a flag without its

@@ -63,39 +63,6 @@ __device__ __forceinline__ uint64_t murmur_words(const uint32_t* a) {
     return h1 + h2;
 }
 
-// Generic k (> SK_MAX_TEMPLATE_K): byte loop over shared memory.  Rare path, kept simple.
-__device__ __forceinline__ uint64_t murmur_bytes(const uint8_t* s, uint32_t k) {
-    uint64_t h1 = SEED, h2 = SEED;
-    uint32_t nb = k / 16;
-    for (uint32_t b = 0; b < nb; b++) {
-        uint64_t k1 = 0, k2 = 0;
-        for (int i = 0; i < 8; i++) {
-            k1 |= (uint64_t)s[16 * b + i] << (8 * i);
-            k2 |= (uint64_t)s[16 * b + 8 + i] << (8 * i);
-        }
-        h1 ^= mix_k1(k1);
-        h1 = rotl64(h1, 27) + h2;
-        h1 = h1 * 5 + 0x52dce729;
-        h2 ^= mix_k2(k2);
-        h2 = rotl64(h2, 31) + h1;
-        h2 = h2 * 5 + 0x38495ab5;
-    }
-    const uint8_t* t = s + 16 * nb;
-    uint32_t rem = k & 15;
-    uint64_t k1 = 0, k2 = 0;
-    for (uint32_t i = 8; i < rem; i++) k2 |= (uint64_t)t[i] << (8 * (i - 8));
-    for (uint32_t i = 0; i < (rem < 8 ? rem : 8); i++) k1 |= (uint64_t)t[i] << (8 * i);
-    if (rem > 8) h2 ^= mix_k2(k2);
-    if (rem > 0) h1 ^= mix_k1(k1);
-    h1 ^= k;
-    h2 ^= k;
-    h1 += h2;
-    h2 += h1;
-    h1 = fmix64(h1);
-    h2 = fmix64(h2);
-    return h1 + h2;
-}
-
 struct Workspace {
     uint32_t* ticket;      // [0] tile ticket, [1] zero-hash flag (exact path)
     uint64_t* status;      // look-back words, one per tile

@@ -97,13 +97,22 @@ class Proteome:
     def n_residues(self):
         return _ffi.lib().ks_proteome_n_residues(self._h)
 
+    def _view(self, ptr, n, dtype):
+        """Read-only numpy view of one of the proteome's pinned buffers (no copy; valid until close())."""
+        if n == 0:
+            return np.zeros(0, dtype=dtype)
+        a = np.ctypeslib.as_array(ptr, shape=(n,))
+        a.flags.writeable = False
+        return a
+
     @property
     def residues(self):
-        return _np(_ffi.lib().ks_proteome_residues(self._h), self.n_residues, np.uint8)
+        """The normalised residues: a read-only view of the pinned buffer (copy it to keep it past close())."""
+        return self._view(_ffi.lib().ks_proteome_residues(self._h), self.n_residues, np.uint8)
 
     @property
     def offsets(self):
-        return _np(_ffi.lib().ks_proteome_offsets(self._h), self.n_proteins + 1, np.uint64)
+        return self._view(_ffi.lib().ks_proteome_offsets(self._h), self.n_proteins + 1, np.uint64)
 
     def name(self, i):
         return _ffi.lib().ks_proteome_name(self._h, i).decode("utf-8", "replace")
@@ -113,7 +122,7 @@ class Proteome:
         return [self.name(i) for i in range(self.n_proteins)]
 
     def sequence(self, i):
-        o = self.offsets
+        o = self.offsets  # views: a call costs the protein's own bytes, not the proteome's
         return self.residues[int(o[i]):int(o[i + 1])].tobytes().decode()
 
     def close(self):

@@ -30,8 +30,9 @@ class SearchResult:
     The pair / hit columns are numpy views of the library's pinned result block (no second copy of what can be
     a gigabyte); the block is released when this object is."""
 
-    def __init__(self, pairs, hits, query_sketches, ms_device, owner=None):
+    def __init__(self, pairs, hits, query_sketches, ms_device, owner=None, q_sizes=None):
         self.pairs, self.hits, self.query_sketches, self.ms_device = pairs, hits, query_sketches, ms_device
+        self.q_sizes = q_sizes  # |Q| per query (always there; the sketches themselves only when asked for)
         self._owner = owner  # POINTER(ks_search_result) kept alive for the views
 
     def close(self):
@@ -104,22 +105,30 @@ def _view(ptr, n, dtype, block):
 def _collect(r, want_hits, owner=None):
     """owner given: columns are views of the pinned block (owner is freed with the SearchResult); else copies."""
     block = _Block(owner) if owner is not None else None
-    get = (lambda p, n, dt: _view(p, n, dt, block)) if owner is not None else _np
-    np_, nh, nq = r.n_pairs, r.n_hits, r.n_queries
-    pairs = {n: get(getattr(r, n), np_, dt) for n, dt in PAIR_INT_COLUMNS.items()}
-    for n in _ffi.SCORE_COLUMNS:
-        pairs[n] = get(getattr(r, n), np_, np.float64)
-    hits = {n: get(getattr(r, n), nh, dt) for n, dt in HIT_COLUMNS.items()} if want_hits else None
-    sig_ptr = _np(r.q_sig_ptr, nq + 1, np.uint64)
-    E = int(sig_ptr[-1]) if nq else 0
-    qm, qa = get(r.q_mins, E, np.uint64), get(r.q_abunds, E, np.uint64)  # malloc'ed by the library, freed with the block
-    return SearchResult(pairs, hits, _QuerySketches(sig_ptr, qm, qa), r.ms_device, block)
+    try:
+        get = (lambda p, n, dt: _view(p, n, dt, block)) if owner is not None else _np
+        np_, nh, nq = r.n_pairs, r.n_hits, r.n_queries
+        pairs = {n: get(getattr(r, n), np_, dt) for n, dt in PAIR_INT_COLUMNS.items()}
+        for n in _ffi.SCORE_COLUMNS:
+            pairs[n] = get(getattr(r, n), np_, np.float64)
+        hits = {n: get(getattr(r, n), nh, dt) for n, dt in HIT_COLUMNS.items()} if want_hits else None
+        sig_ptr = _np(r.q_sig_ptr, nq + 1, np.uint64)
+        sketches = None
+        if r.q_mins:  # KS_SEARCH_QUERY_SKETCHES
+            E = int(sig_ptr[-1]) if nq else 0
+            sketches = _QuerySketches(sig_ptr, get(r.q_mins, E, np.uint64), get(r.q_abunds, E, np.uint64))
+        return SearchResult(pairs, hits, sketches, r.ms_device, block, q_sizes=np.diff(sig_ptr).astype(np.uint32))
+    except Exception:
+        if block is not None:
+            block.ptr = None  # the caller frees the result on this path: exactly one owner of the free
+        raise
 
 
-def search(index: ProteomeIndex, queries: Proteome, hits=True) -> SearchResult:
-    """One batched search of `queries` against a finalized index (ks_search_batch)."""
+def search(index: ProteomeIndex, queries: Proteome, hits=True, query_sketches=True) -> SearchResult:
+    """One batched search of `queries` against a finalized index (ks_search_batch).  `query_sketches=False` leaves the
+    queries' mins / abundances on the device (they are only needed for the query_md5 column)."""
     index.finalize()
-    flags = _ffi.KS_SEARCH_HITS if hits else 0
+    flags = (_ffi.KS_SEARCH_HITS if hits else 0) | (_ffi.KS_SEARCH_QUERY_SKETCHES if query_sketches else 0)
     out = C.POINTER(_ffi.ks_search_result)()
     check(_ffi.lib().ks_search_batch(index._h, queries._h, flags, C.byref(out)))
     try:

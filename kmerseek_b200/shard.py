@@ -1,10 +1,11 @@
-"""Multi-GPU host logic: one process per GPU (torchrun), the proteome sharded by protein, queries replicated,
-per-shard scored pairs / hit lists gathered to rank 0 with NCCL (torch.distributed is the plumbing).
+"""Multi-GPU host logic: one process per GPU (torchrun), the proteome sharded by protein, queries replicated.
 
 The build has no data-path collective: every rank sketches, sorts and indexes its own contiguous protein
 range.  A target protein lives on exactly one shard, so a (query, target) pair is scored entirely by the
 owning rank (|T| and the abundances are local) and the merge is a concatenation ordered by (query, target):
-no reduction is needed.
+no reduction is needed.  The search exchange itself lives below the C ABI
+(ks_shard_search_batch: NCCL all-gather of counts, grouped send/recv of result blocks, a counting merge kernel on
+rank 0); this module shards the input, replicates the queries and bootstraps the library's communicator.
 """
 import ctypes as C
 
@@ -13,11 +14,7 @@ import numpy as np
 from . import _ffi
 from .errors import check
 
-PAIR_U32 = ["pair_qid", "pair_pid", "intersect_hashes", "q_size", "t_size"]
-PAIR_U64 = ["n_weighted_found", "total_weighted_hashes"]
 PAIR_F64 = list(_ffi.SCORE_COLUMNS)
-HIT_U32 = ["hit_qid", "hit_pid", "hit_qpos", "hit_tpos"]
-HIT_U64 = ["hit_hash"]
 
 
 def plan_shards(offsets, world):
@@ -68,31 +65,108 @@ def broadcast_queries(qres, qoffs, device=None):
     return host[:n_res].copy(), host[n_res:].view(np.uint64).copy()
 
 
-class _DevArray:
-    """Expose a raw device pointer to torch through __cuda_array_interface__ (no copy)."""
+class Comm:
+    """ks_comm: the library's own NCCL communicator (ncclCommInitRank inside libkmerseek_b200.so).  torch.distributed is
+    only the side channel that hands rank 0's ncclUniqueId to the other ranks."""
 
-    def __init__(self, ptr, n, typestr):
-        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 3,
-                                         "strides": None}
+    def __init__(self, device=None):
+        import torch
+        dist = _dist()
+        self.rank = dist.get_rank() if dist else 0
+        self.world = dist.get_world_size() if dist else 1
+        self.device = torch.cuda.current_device() if device is None else device
+        L = _ffi.lib()
+        ident = (C.c_uint8 * _ffi.KS_COMM_ID_BYTES)()
+        if self.rank == 0:
+            check(L.ks_comm_unique_id(ident))
+        if self.world > 1:
+            dev = torch.device("cuda", self.device) if dist.get_backend() == "nccl" else torch.device("cpu")
+            t = torch.tensor(list(ident), dtype=torch.uint8, device=dev)
+            dist.broadcast(t, 0)
+            ident = (C.c_uint8 * _ffi.KS_COMM_ID_BYTES)(*t.cpu().tolist())
+        h = C.c_void_p()
+        check(L.ks_comm_create(ident, self.rank, self.world, self.device, C.byref(h)))
+        self._h = h
+
+    def close(self):
+        if self._h:
+            _ffi.lib().ks_comm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
-def _device_columns(res_ptr, names, n, typestr, torch_dtype):
-    import torch
+def merge_positions(pair_offs):
+    """The counting merge that `merge_pairs_kernel` (csrc/search.cu) runs on rank 0, stated in numpy.
+    pair_offs[s] = shard s's exclusive pair offsets per query (length nq + 1).  Shards hold ascending protein ranges and
+    each is ordered by (query, target), so row j of shard s (its query q = the q with off_s[q] <= j < off_s[q + 1]) goes to
+        sum_s' off_s'[q]  +  sum_{s' < s} (off_s'[q + 1] - off_s'[q])  +  (j - off_s[q]).
+    Returns one destination array per shard.  No sort anywhere."""
+    offs = [np.asarray(o, dtype=np.int64) for o in pair_offs]
+    base = np.sum(offs, axis=0)  # merged exclusive offset of every query
+    out = []
+    before = np.zeros(len(base) - 1, dtype=np.int64)  # pairs of query q in the shards before s
+    for o in offs:
+        counts = np.diff(o)
+        q = np.repeat(np.arange(len(counts)), counts)
+        j = np.arange(int(o[-1]))
+        out.append(base[q] + before[q] + (j - o[q]))
+        before = before + counts
+    return out
+
+
+def search_and_gather(index, queries, comm=None, pid_base=0, hits=False, query_sketches=False):
+    """ks_shard_search_batch: search this rank's shard and merge on rank 0 (one NCCL all-gather of the counts, one
+    grouped send/recv of the shards' result blocks, a counting merge kernel).  Returns on rank 0 a dict with `pairs`
+    (and `hits`) as host column dicts with index-wide protein ids, plus `result` (the SearchResult that owns them);
+    elsewhere {"n_pairs": local count}."""
+    from .search import _collect
     L = _ffi.lib()
-    cols = []
-    for name in names:
-        if n == 0:
-            cols.append(torch.zeros(0, dtype=torch_dtype, device="cuda"))
-            continue
-        p = L.ks_search_result_device_column(res_ptr, name.encode())
-        t = torch.as_tensor(_DevArray(p, n, typestr), device="cuda")
-        cols.append(t.view(torch_dtype) if t.dtype != torch_dtype else t)
-    return torch.stack(cols) if cols else None
+    flags = (_ffi.KS_SEARCH_HITS if hits else 0) | (_ffi.KS_SEARCH_QUERY_SKETCHES if query_sketches else 0)
+    index.finalize()
+    out = C.POINTER(_ffi.ks_search_result)()
+    if comm is None or comm.world == 1:
+        check(L.ks_search_batch(index._h, queries._h, flags, C.byref(out)))
+        rank = 0
+    else:
+        check(L.ks_shard_search_batch(index._h, comm._h, queries._h, flags, pid_base, C.byref(out)))
+        rank = comm.rank
+    if rank != 0:
+        n = int(out.contents.n_pairs)
+        L.ks_search_result_free(out)
+        return {"n_pairs": n}
+    try:
+        res = _collect(out.contents, hits, owner=out)
+    except Exception:
+        L.ks_search_result_free(out)
+        raise
+    if (comm is None or comm.world == 1) and pid_base:
+        res.pairs["pair_pid"] = res.pairs["pair_pid"] + np.uint32(pid_base)
+        if hits:
+            res.hits["hit_pid"] = res.hits["hit_pid"] + np.uint32(pid_base)
+    return {"n_pairs": res.n_pairs, "pairs": res.pairs, "hits": res.hits, "query_sketches": res.query_sketches,
+            "result": res}
+
+
+def _to_host(t):
+    """Device tensor -> numpy through a pinned staging tensor (pageable D2H is several times slower)."""
+    import torch
+    if t.device.type == "cpu":
+        return t.numpy()
+    h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    h.copy_(t, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    return h.numpy()
 
 
 def gather_blocks(blocks, count):
     """blocks: {key: tensor [n_cols, count]} on every rank (same keys/dtypes) -> on rank 0 {key: [n_cols, total]}
-    concatenated in rank order, plus the per-rank counts; None elsewhere.  1 all_gather (counts) + 1 gather per block."""
+    concatenated in rank order, plus the per-rank counts; None elsewhere.  (Combined-sketch merge only: it is not on the
+    search path.)"""
     import torch
     dist = _dist()
     if dist is None or dist.get_world_size() == 1:
@@ -113,105 +187,6 @@ def gather_blocks(blocks, count):
         if rank == 0:
             out[key] = torch.cat([r[:, :c] for r, c in zip(recv, counts)], dim=1)
     return (out if rank == 0 else None), counts
-
-
-def _to_host(t):
-    """Device tensor -> numpy through a pinned staging tensor (pageable D2H is several times slower)."""
-    import torch
-    if t.device.type == "cpu":
-        return t.numpy()
-    h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
-    h.copy_(t, non_blocking=True)
-    torch.cuda.current_stream().synchronize()
-    return h.numpy()
-
-
-def _base_vector(counts, pid_bases, device):
-    import torch
-    return torch.repeat_interleave(torch.tensor(pid_bases, dtype=torch.int32, device=device),
-                                   torch.tensor(counts, dtype=torch.int64, device=device))
-
-
-def merge_pairs(gathered, counts, pid_bases):
-    """Rank-0 merge, on the device the blocks live on: globalise protein ids with each shard's base and order
-    rows by (query, target).  Shards arrive in rank order = ascending protein ranges and every shard is already
-    ordered by (query, target), so one stable sort by query is the whole merge."""
-    import torch
-    u32, u64, f64 = gathered["u32"], gathered["u64"], gathered["f64"]
-    u32 = u32.clone()
-    u32[1] += _base_vector(counts, pid_bases, u32.device)
-    order = torch.sort(u32[0], stable=True).indices
-    u32h = _to_host(u32[:, order].contiguous()).view(np.uint32)
-    u64h = _to_host(u64[:, order].contiguous()).view(np.uint64)
-    f64h = _to_host(f64[:, order].contiguous())
-    cols = {n: u32h[i] for i, n in enumerate(PAIR_U32)}
-    cols.update({n: u64h[i] for i, n in enumerate(PAIR_U64)})
-    cols.update({n: f64h[i] for i, n in enumerate(PAIR_F64)})
-    return cols
-
-
-def merge_hits(gathered, counts, pid_bases):
-    """Hits are ordered by (query, qpos, target, tpos) inside a shard; across shards targets ascend with the rank,
-    so a stable sort by (query, qpos) merges them."""
-    import torch
-    h32, h64 = gathered["h32"].clone(), gathered["h64"]
-    h32[1] += _base_vector(counts, pid_bases, h32.device)
-    key = (h32[0].to(torch.int64) << 32) | (h32[2].to(torch.int64) & 0xffffffff)
-    order = torch.sort(key, stable=True).indices
-    h32h = _to_host(h32[:, order].contiguous()).view(np.uint32)
-    h64h = _to_host(h64[:, order].contiguous()).view(np.uint64)
-    cols = {n: h32h[i] for i, n in enumerate(HIT_U32)}
-    cols["hit_hash"] = h64h[0]
-    return cols
-
-
-def search_and_gather(index, queries, pid_base=0, hits=False):
-    """Search this rank's shard and gather to rank 0.  Returns on rank 0 a dict with `pairs` (and `hits`)
-    as host column dicts with index-wide protein ids; elsewhere {"n_pairs": local count}."""
-    import torch
-    dist = _dist()
-    world = dist.get_world_size() if dist else 1
-    L = _ffi.lib()
-    flags = (_ffi.KS_SEARCH_HITS if hits else 0) | (_ffi.KS_SEARCH_DEVICE_ONLY if world > 1 else 0)
-    index.finalize()
-    out = C.POINTER(_ffi.ks_search_result)()
-    check(L.ks_search_batch(index._h, queries._h, flags, C.byref(out)))
-    try:
-        r = out.contents
-        if world == 1:
-            from .search import _collect
-            res = _collect(r, hits, owner=out)
-            out = None  # ownership moved to the SearchResult
-            if pid_base:
-                res.pairs["pair_pid"] = res.pairs["pair_pid"] + np.uint32(pid_base)
-                if hits:
-                    res.hits["hit_pid"] = res.hits["hit_pid"] + np.uint32(pid_base)
-            return {"n_pairs": res.n_pairs, "pairs": res.pairs, "hits": res.hits, "query_sketches": res.query_sketches,
-                    "result": res}
-        n = int(r.n_pairs)
-        # integer columns travel as their signed twins (same bits); merge_* views them back as unsigned
-        blocks = {"u32": _device_columns(out, PAIR_U32, n, "<i4", torch.int32),
-                  "u64": _device_columns(out, PAIR_U64, n, "<i8", torch.int64),
-                  "f64": _device_columns(out, PAIR_F64, n, "<f8", torch.float64)}
-        bases = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
-        dist.all_gather(bases, torch.tensor([pid_base], dtype=torch.int64, device="cuda"))
-        bases = [int(b.item()) for b in bases]
-        gathered, counts = gather_blocks(blocks, n)
-        result = {"n_pairs": n}
-        if hits:
-            nh = int(r.n_hits)
-            hb = {"h32": _device_columns(out, HIT_U32, nh, "<i4", torch.int32),
-                  "h64": _device_columns(out, HIT_U64, nh, "<i8", torch.int64)}
-            hg, hcounts = gather_blocks(hb, nh)
-        if dist.get_rank() == 0:
-            result["pairs"] = merge_pairs(gathered, counts, bases)
-            result["n_pairs"] = len(result["pairs"]["pair_qid"])
-            if hits:
-                result["hits"] = merge_hits(hg, hcounts, bases)
-        return result
-    finally:
-        if out is not None:
-            L.ks_search_result_free(out)
 
 
 def merge_combined_sketch(mins, abunds, device=None):

@@ -71,3 +71,28 @@ def queries(residues, offsets, n_queries, seed, min_len=50, max_len=300, sub_rat
 
 def names(n, prefix="syn"):
     return [f"{prefix}|{i:09d}" for i in range(n)]
+
+
+def write_fasta(path, residues, offsets, width=60, prefix="syn"):
+    """Plain FASTA of a packed proteome: `>syn|000000012` headers, sequences wrapped at `width` columns.  Assembled with
+    numpy in slabs of proteins (a 200 M-residue proteome is written in a few seconds)."""
+    offsets = np.asarray(offsets, dtype=np.int64)
+    P = len(offsets) - 1
+    with open(path, "wb") as f:
+        step = 50_000
+        for a in range(0, P, step):
+            b = min(P, a + step)
+            lens = offsets[a + 1:b + 1] - offsets[a:b]
+            lines = (lens + width - 1) // width  # newlines inside / after a sequence (an empty sequence has none)
+            head = len(prefix) + 1 + 9 + 2  # '>' + prefix + '|' + 9 digits + '\n'
+            rec = head + lens + lines
+            base = np.concatenate([[0], np.cumsum(rec)])
+            out = np.full(int(base[-1]), ord("\n"), dtype=np.uint8)
+            hdr = np.frombuffer("".join(f">{prefix}|{i:09d}\n" for i in range(a, b)).encode(), dtype=np.uint8).reshape(b - a, head)
+            hpos = (base[:-1, None] + np.arange(head)[None, :]).ravel()
+            out[hpos] = hdr.ravel()
+            n = int(offsets[b] - offsets[a])
+            within = np.arange(n) - np.repeat(offsets[a:b] - offsets[a], lens)
+            pos = np.repeat(base[:-1] + head, lens) + within + within // width
+            out[pos] = residues[int(offsets[a]):int(offsets[b])]
+            f.write(out.tobytes())

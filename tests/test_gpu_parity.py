@@ -261,6 +261,97 @@ def test_index_csr_and_search_bit_exact(K, O, k, moltype, scaled):
                 assert float(p[c][j]) == pytest.approx(o[c], rel=SCORE_RTOL, abs=1e-12), (c, j)
 
 
+SCORE_NAMES = ("containment", "containment_target_in_query", "max_containment", "jaccard", "query_containment_ani",
+               "match_containment_ani", "average_containment_ani", "max_containment_ani", "average_abund", "median_abund",
+               "std_abund", "f_weighted_target_in_query")
+
+
+def _search_equals_oracle(K, O, idx, res, offs, qres, qoffs, k, moltype, scaled, hits=True):
+    """Pairs (bit-exact integers, scores within SCORE_RTOL), hit list and query sketches of one search vs the oracle."""
+    queries = K.Proteome.from_packed(qres, qoffs)
+    r = K.search(idx, queries, hits=hits)
+    oh, opid, opos = O.sketch_tuples(res, offs, k, moltype, scaled)
+    qh, qid, qpos = O.sketch_tuples(qres, qoffs, k, moltype, scaled)
+    osk = O.protein_sketches(oh, opid, len(offs) - 1)
+    qsk = O.protein_sketches(qh, qid, len(qoffs) - 1)
+    for (m, a), (om, oa) in zip(r.query_sketches, qsk):
+        assert np.array_equal(m, om) and np.array_equal(a, oa)
+    assert np.array_equal(r.q_sizes, [len(m) for m, _ in qsk])
+    orows = O.manysearch(qsk, osk, k, scaled, moltype)
+    p = r.pairs
+    assert r.n_pairs == len(orows)
+    assert np.array_equal(p["pair_qid"], [o["qid"] for o in orows]) and np.array_equal(p["pair_pid"], [o["pid"] for o in orows])
+    for c in ("intersect_hashes", "n_weighted_found", "total_weighted_hashes"):
+        assert np.array_equal(p[c], [o[c] for o in orows]), c
+    for c in SCORE_NAMES:
+        np.testing.assert_allclose(p[c], [o[c] for o in orows], rtol=SCORE_RTOL, atol=1e-12, err_msg=c)
+    if hits:
+        ohits = O.hits(qh, qid, qpos, oh, opid, opos)
+        hh = r.hits
+        mine = list(zip(hh["hit_qid"].tolist(), hh["hit_pid"].tolist(), hh["hit_hash"].tolist(), hh["hit_qpos"].tolist(),
+                        hh["hit_tpos"].tolist()))
+        assert mine == ohits
+    return r
+
+
+def test_search_query_size_classes_and_library_path(K, O, monkeypatch):
+    """The hand-written query kernel has two instantiations (queries of up to 512 and up to 4096 windows); longer queries
+    and KS_SEARCH_LEGACY take the library-sorted path.  All must give the oracle's rows, a batch that mixes the classes
+    included, with empty / shorter-than-k queries in between."""
+    from kmerseek_b200 import synth
+    res, offs = synth.proteome(600_000, 2718)
+    rng = np.random.default_rng(5)
+    k, moltype = 12, "dayhoff"
+
+    def slices(lengths):
+        parts, lens = [], []
+        for n in lengths:
+            a = int(rng.integers(0, len(res) - n - 1)) if n else 0
+            piece = res[a:a + n].copy()
+            if n > 20:
+                piece[rng.integers(0, n, size=n // 12)] = ord("A")  # substitutions: hits are partial
+            parts.append(piece)
+            lens.append(n)
+        return np.concatenate(parts), np.cumsum([0] + lens).astype(np.uint64)
+
+    with K.ProteomeIndex("db", k, 1, moltype) as idx:
+        idx.add_proteome(K.Proteome.from_packed(res, offs))
+        idx.finalize()
+        for lengths in ([60, 0, 5, 523, 300, 11, 12], [3000, 100, 0, 4107, 700], [200, 9000, 50]):
+            qres, qoffs = slices(lengths)
+            _search_equals_oracle(K, O, idx, res, offs, qres, qoffs, k, moltype, 1)
+    monkeypatch.setenv("KS_SEARCH_LEGACY", "1")
+    with K.ProteomeIndex("db", k, 1, moltype) as idx:
+        idx.add_proteome(K.Proteome.from_packed(res, offs))
+        idx.finalize()
+        qres, qoffs = slices([60, 0, 523, 300])
+        _search_equals_oracle(K, O, idx, res, offs, qres, qoffs, k, moltype, 1)
+
+
+def test_search_many_targets_per_query(K, O):
+    """A tiny k-mer space (hp k = 8): every query hash has thousands of postings, a query meets every target and its
+    (target, abundance) records overflow the shared-memory window many times over (the protein-id windows of the query
+    kernel), abundances vary (median / deviation over more than ones), and the batch's pairs overflow the first staging
+    buffer (65 536 pairs) so that the retry path runs."""
+    from kmerseek_b200 import synth
+    res, offs = synth.proteome(300_000, 99)
+    qres, qoffs, _ = synth.queries(res, offs, 96, 13, min_len=60, max_len=400)
+    with K.ProteomeIndex("db", 8, 1, "hp") as idx:
+        idx.add_proteome(K.Proteome.from_packed(res, offs))
+        idx.finalize()
+        r = _search_equals_oracle(K, O, idx, res, offs, qres, qoffs, 8, "hp", 1, hits=False)
+        assert r.n_pairs > 65_536 and float(np.max(r.pairs["std_abund"])) > 0
+        r2 = K.search(idx, K.Proteome.from_packed(qres, qoffs), hits=False, query_sketches=False)  # buffers now sized
+        assert r2.query_sketches is None and r2.n_pairs == r.n_pairs
+        assert np.array_equal(r2.pairs["pair_pid"], r.pairs["pair_pid"]) and np.array_equal(r2.pairs["jaccard"], r.pairs["jaccard"])
+    # scaled > 1 and a handful of queries, with hits
+    qres, qoffs, _ = synth.queries(res, offs, 6, 14, min_len=60, max_len=200)
+    with K.ProteomeIndex("db", 9, 3, "hp") as idx:
+        idx.add_proteome(K.Proteome.from_packed(res, offs))
+        idx.finalize()
+        _search_equals_oracle(K, O, idx, res, offs, qres, qoffs, 9, "hp", 3, hits=True)
+
+
 def test_empty_and_degenerate_inputs(K, O):
     with K.ProteomeIndex("db", 7, 1, "dayhoff") as idx:
         idx.add_proteome(K.Proteome.from_sequences([], []))

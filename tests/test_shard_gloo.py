@@ -1,6 +1,6 @@
-"""world_size-2 gloo tests (CPU) of the multi-GPU host logic: shard planning, query broadcast, the
-variable-length gather to rank 0 and the (query, target) merge.  Per-shard search results are produced by
-the oracle here (no GPU in this container); the GPU test of the same path is in test_gpu_multi.py."""
+"""world_size-2 gloo tests (CPU) of the multi-GPU host logic: shard planning, query broadcast, and the counting merge
+rule of ks_shard_search_batch (shard.merge_positions, the numpy statement of the merge kernels) applied to per-shard
+oracle results (no GPU in this container); the GPU test of the real path (NCCL + kernels) is test_gpu_multi.py."""
 import os
 import sys
 
@@ -40,17 +40,9 @@ def _oracle_shard_pairs(O, res, offs, qres, qoffs, k, moltype, scaled):
     return rows, hits
 
 
-def _blocks_from_rows(rows):
-    n = len(rows)
-    u32 = np.zeros((5, n), np.uint32)
-    u64 = np.zeros((2, n), np.uint64)
-    f64 = np.zeros((len(shard.PAIR_F64), n), np.float64)
-    for j, r in enumerate(rows):
-        u32[:, j] = [r["qid"], r["pid"], r["intersect_hashes"], 0, 0]
-        u64[:, j] = [r["n_weighted_found"], r["total_weighted_hashes"]]
-        f64[:, j] = [r[c] for c in shard.PAIR_F64]
-    return {"u32": torch.from_numpy(u32.view(np.int32)), "u64": torch.from_numpy(u64.view(np.int64)),
-            "f64": torch.from_numpy(f64)}
+def _unit_offsets(units, n_units):
+    """exclusive offsets per unit (length n_units + 1) of rows that are ordered by unit"""
+    return np.concatenate([[0], np.cumsum(np.bincount(np.asarray(units, dtype=np.int64), minlength=n_units))]).astype(np.int64)
 
 
 def _worker(rank, world, port, q):
@@ -66,30 +58,43 @@ def _worker(rank, world, port, q):
         if rank == 0:
             qres, qoffs, _ = synth.queries(res, offs, 12, 9, min_len=30, max_len=90)
         qres, qoffs = shard.broadcast_queries(qres, qoffs)
+        nq = len(qoffs) - 1
         bounds = shard.plan_shards(offs, world)
         sres, soffs = shard.shard_of(res, offs, bounds, rank)
         rows, hits = _oracle_shard_pairs(O, sres, soffs, qres, qoffs, k, moltype, scaled)
-        gathered, counts = shard.gather_blocks(_blocks_from_rows(rows), len(rows))
-        bases = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
-        dist.all_gather(bases, torch.tensor([bounds[rank]], dtype=torch.int64))
-        bases = [int(b.item()) for b in bases]
-        h32 = np.array([[h[0] for h in hits], [h[1] for h in hits], [h[3] for h in hits], [h[4] for h in hits]], np.uint32).reshape(4, -1)
-        h64 = np.array([[h[2] for h in hits]], np.uint64).reshape(1, -1)
-        hg, hcounts = shard.gather_blocks({"h32": torch.from_numpy(h32.view(np.int32)), "h64": torch.from_numpy(h64.view(np.int64))}, len(hits))
+        # what ks_shard_search_batch does on the GPUs, with the oracle as the per-shard search: every shard's rows (protein
+        # ids made index-wide) reach rank 0 and land at the positions of the counting merge (shard.merge_positions is the
+        # numpy statement of merge_pairs_kernel / merge_hits_kernel)
+        rows = [dict(r, pid=r["pid"] + bounds[rank]) for r in rows]
+        hits = [(h[0], h[1] + bounds[rank], h[2], h[3], h[4]) for h in hits]
+        all_rows = [None] * world if rank == 0 else None
+        all_hits = [None] * world if rank == 0 else None
+        dist.gather_object(rows, all_rows, dst=0)
+        dist.gather_object(hits, all_hits, dst=0)
+        ok = True
         if rank == 0:
-            merged = shard.merge_pairs(gathered, counts, bases)
-            mh = shard.merge_hits(hg, hcounts, bases)
+            dst = shard.merge_positions([_unit_offsets([r["qid"] for r in rs], nq) for rs in all_rows])
+            merged = [None] * sum(len(rs) for rs in all_rows)
+            for rs, d in zip(all_rows, dst):
+                for r, j in zip(rs, d.tolist()):
+                    assert merged[j] is None
+                    merged[j] = r
             full_rows, full_hits = _oracle_shard_pairs(O, res, offs, qres, qoffs, k, moltype, scaled)
-            ok = len(full_rows) == len(merged["pair_qid"]) and len(full_rows) > 0
-            for j, r in enumerate(full_rows):
-                ok &= (int(merged["pair_qid"][j]), int(merged["pair_pid"][j])) == (r["qid"], r["pid"])
-                ok &= int(merged["intersect_hashes"][j]) == r["intersect_hashes"]
-                ok &= int(merged["total_weighted_hashes"][j]) == r["total_weighted_hashes"]
+            ok = len(full_rows) == len(merged) and len(full_rows) > 0
+            for m, r in zip(merged, full_rows):
+                ok &= (m["qid"], m["pid"]) == (r["qid"], r["pid"]) and m["intersect_hashes"] == r["intersect_hashes"]
+                ok &= m["total_weighted_hashes"] == r["total_weighted_hashes"]
                 for c in shard.PAIR_F64:
-                    ok &= float(merged[c][j]) == r[c]
-            mine = list(zip(mh["hit_qid"].tolist(), mh["hit_pid"].tolist(), mh["hit_hash"].tolist(),
-                            mh["hit_qpos"].tolist(), mh["hit_tpos"].tolist()))
-            ok &= mine == full_hits and len(mine) > 0
+                    ok &= m[c] == r[c]
+            # hits: the same rule per (query, window) unit
+            qo = np.asarray(qoffs, dtype=np.int64)
+            n_units = int(qo[-1])
+            dsth = shard.merge_positions([_unit_offsets([qo[h[0]] + h[3] for h in hs], n_units) for hs in all_hits])
+            mh = [None] * sum(len(hs) for hs in all_hits)
+            for hs, d in zip(all_hits, dsth):
+                for h, j in zip(hs, d.tolist()):
+                    mh[j] = h
+            ok &= mh == full_hits and len(mh) > 0
         # combined sketch of the whole proteome = union of the shards' combined sketches, abundances summed
         # (src/rust/index.rs:824-827); hashes above 2^63 must keep their unsigned order through the int64 tensors
         sh, spid, spos = O.sketch_tuples(sres, soffs, k, moltype, scaled)
