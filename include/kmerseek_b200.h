@@ -83,25 +83,36 @@ void ks_id_of_mins(const uint64_t *mins, uint64_t n, char out[17]);
  * Ingest: FASTA / sequences -> packed residues + offsets in pinned host memory.
  * Replaces needletail::parse_fastx_file + the per-record Vec copies (src/rust/index.rs:920-935),
  * `to_uppercase` (:1000) and AminoAcidAmbiguity::validate_and_resolve (src/rust/aminoacid.rs:74-105).
- * Normalisation: upper-case; keep and stop at the first '*'; reject anything outside the 20 standard
- * letters + X U O * + B Z J.  B/Z/J are resolved to D|N, E|Q, I|L -- at random in the reference
- * (rand::rng(), aminoacid.rs:45-54); here reproducibly:
- *     choice = splitmix64(ambig_seed ^ (protein_index << 32) ^ position_in_output) & 1
- * (0 -> D/E/I, 1 -> N/Q/L), which is one of the outcomes the reference can produce.
+ * Normalisation (KS_NORMALIZE_KMERSEEK, the index path of the Rust crate): upper-case; keep and stop at the first '*';
+ * reject anything outside the 20 standard letters + X U O * + B Z J.  B/Z/J are resolved to D|N, E|Q, I|L -- at random in
+ * the reference (rand::rng(), aminoacid.rs:45-54); here reproducibly:
+ *     choice = splitmix64(ambig_seed ^ position_in_output) & 1          (0 -> D/E/I, 1 -> N/Q/L)
+ * which is one of the outcomes the reference can produce, and depends on the residue's position in its own sequence only
+ * (the same sequence resolves the same way wherever it stands, so a query that copies a target matches it fully).
+ * KS_NORMALIZE_SOURMASH is what `kmerseek search` does to both of its inputs (src/python/kmerseek/sketch.py:28-40 ->
+ * branchwater manysketch -> sourmash add_protein): upper-case only -- no validation, no '*' truncation, no resolution
+ * (B/Z/J and anything else unknown translate to 'X' under dayhoff / hp and are hashed as they are under protein).
+ * FASTA files are parsed by all host threads at once (KS_INGEST_THREADS overrides the count), straight into the
+ * pinned upload buffers.
  * ------------------------------------------------------------------------------------------- */
+#define KS_NORMALIZE_KMERSEEK 0
+#define KS_NORMALIZE_SOURMASH 1
 typedef struct ks_proteome ks_proteome;
 
-/* plain or gzip FASTA; names are the full header line without '>' (needletail id()). */
+/* plain, gzip, zstd, bzip2 or xz FASTA; names are the full header line without '>' (needletail id()). */
 ks_status ks_proteome_from_fasta(const char *path, uint64_t ambig_seed, ks_proteome **out);
+ks_status ks_proteome_from_fasta_mode(const char *path, uint64_t ambig_seed, int mode, ks_proteome **out);
 /* n sequences (not NUL-terminated; lens in bytes); names may be NULL. */
 ks_status ks_proteome_from_sequences(const char *const *seqs, const uint64_t *lens, const char *const *names,
                                      uint64_t n, uint64_t ambig_seed, ks_proteome **out);
+ks_status ks_proteome_from_sequences_mode(const char *const *seqs, const uint64_t *lens, const char *const *names,
+                                          uint64_t n, uint64_t ambig_seed, int mode, ks_proteome **out);
 /* already-normalised residues: copied as is (no validation); offsets has n_proteins+1 entries. */
 ks_status ks_proteome_from_packed(const uint8_t *residues, const uint64_t *offsets, uint64_t n_proteins,
                                   ks_proteome **out);
 uint64_t ks_proteome_n_proteins(const ks_proteome *p);
 uint64_t ks_proteome_n_residues(const ks_proteome *p);
-const uint8_t *ks_proteome_residues(const ks_proteome *p); /* pinned, n_residues bytes (+64 zero pad) */
+const uint8_t *ks_proteome_residues(const ks_proteome *p); /* n_residues bytes (+64 zero pad) */
 const uint64_t *ks_proteome_offsets(const ks_proteome *p); /* pinned, n_proteins+1 */
 const char *ks_proteome_name(const ks_proteome *p, uint64_t i); /* "" when no names were given */
 void ks_proteome_free(ks_proteome *p);

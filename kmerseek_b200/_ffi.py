@@ -22,6 +22,8 @@ KS_SEARCH_HITS = 1
 KS_SEARCH_DEVICE_ONLY = 2
 KS_SEARCH_QUERY_SKETCHES = 4
 KS_COMM_ID_BYTES = 128
+KS_NORMALIZE_KMERSEEK = 0
+KS_NORMALIZE_SOURMASH = 1
 
 
 class ks_params(C.Structure):
@@ -77,6 +79,9 @@ SIGNATURES = {
     "ks_proteome_from_fasta": (C.c_int, [C.c_char_p, C.c_uint64, C.POINTER(C.c_void_p)]),
     "ks_proteome_from_sequences": (C.c_int, [C.POINTER(C.c_char_p), u64p, C.POINTER(C.c_char_p), C.c_uint64,
                                              C.c_uint64, C.POINTER(C.c_void_p)]),
+    "ks_proteome_from_fasta_mode": (C.c_int, [C.c_char_p, C.c_uint64, C.c_int, C.POINTER(C.c_void_p)]),
+    "ks_proteome_from_sequences_mode": (C.c_int, [C.POINTER(C.c_char_p), u64p, C.POINTER(C.c_char_p), C.c_uint64,
+                                                  C.c_uint64, C.c_int, C.POINTER(C.c_void_p)]),
     "ks_proteome_from_packed": (C.c_int, [u8p, u64p, C.c_uint64, C.POINTER(C.c_void_p)]),
     "ks_proteome_n_proteins": (C.c_uint64, [C.c_void_p]),
     "ks_proteome_n_residues": (C.c_uint64, [C.c_void_p]),

@@ -14,6 +14,7 @@
 
 #include "dense.cuh"
 #include "host_util.hpp"
+#include "ingest.hpp"
 #include "index_build.cuh"
 #include "search.cuh"
 #include "sketch.cuh"
@@ -57,55 +58,189 @@ int clz64(uint64_t x) { return x ? __builtin_clzll(x) : 64; }
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
-// proteome (pinned host buffers)
+// proteome (host buffers: the upload formats pinned, from a pool that outlives the objects)
 // ------------------------------------------------------------------------------------------------
-struct ks_proteome {
-    uint8_t* residues = nullptr;
-    uint64_t* offsets = nullptr;
-    uint64_t n_prot = 0, n_res = 0;
+namespace {
+
+// Pinned blocks are recycled (proteomes, search results): cudaHostAlloc of a few hundred MB costs more than filling them.
+std::mutex g_pin_mu;
+std::vector<std::pair<void*, size_t>> g_pin_free;
+size_t g_pin_pooled = 0;
+
+void* pinned_try_get(size_t bytes, size_t* got) {  // nullptr when there is no device to pin for
+    {
+        std::lock_guard<std::mutex> lk(g_pin_mu);
+        int best = -1;
+        for (size_t i = 0; i < g_pin_free.size(); i++)
+            if (g_pin_free[i].second >= bytes && (best < 0 || g_pin_free[i].second < g_pin_free[best].second)) best = (int)i;
+        if (best >= 0 && g_pin_free[best].second <= 2 * bytes + (1u << 20)) {
+            auto b = g_pin_free[best];
+            g_pin_free.erase(g_pin_free.begin() + best);
+            g_pin_pooled -= b.second;
+            *got = b.second;
+            return b.first;
+        }
+    }
+    const size_t want = bytes + bytes / 8 + (1u << 16);
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, want, cudaHostAllocDefault) != cudaSuccess) { (void)cudaGetLastError(); return nullptr; }
+    *got = want;
+    return p;
+}
+
+void* pinned_get(size_t bytes, size_t* got) {
+    void* p = pinned_try_get(bytes, got);
+    if (!p) fail(KS_ERR_OUT_OF_MEMORY, "cudaHostAlloc failed");
+    return p;
+}
+
+void pinned_put(void* p, size_t bytes) {
+    if (!p) return;
+    std::lock_guard<std::mutex> lk(g_pin_mu);
+    if (g_pin_pooled + bytes > (8ull << 30)) { cudaFreeHost(p); return; }
+    g_pin_free.emplace_back(p, bytes);
+    g_pin_pooled += bytes;
+}
+
+struct HostBuf {
+    void* p = nullptr;
+    size_t bytes = 0;  // of the block (pinned: as the pool knows it)
     bool pinned = false;
-    // upload format: 5-bit codes, 8 residues per 5 bytes (null when a byte outside A-Z and '*' is present)
+    // pinned (pooled) when a device is there and `want_pinned`; pageable otherwise (CPU-only host tests, or buffers that are
+    // not an upload format)
+    void alloc(size_t n, bool want_pinned) {
+        release();
+        if (want_pinned) {
+            p = pinned_try_get(n, &bytes);
+            pinned = p != nullptr;
+        }
+        if (!p) {
+            p = malloc(n ? n : 1);
+            if (!p) throw std::bad_alloc();
+            bytes = n;
+            pinned = false;
+        }
+    }
+    void release() {
+        if (!p) return;
+        if (pinned) pinned_put(p, bytes); else free(p);
+        p = nullptr; bytes = 0; pinned = false;
+    }
+};
+
+}  // namespace
+
+struct ks_proteome {
+    uint8_t* residues = nullptr;  // normalised residues (+ 64 zero bytes); pageable when the packed copy is the upload format
+    uint64_t* offsets = nullptr;  // pinned
+    uint64_t n_prot = 0, n_res = 0;
+    // upload format: 5-bit codes, 8 residues per 5 bytes, pinned (null when a byte outside A-Z and '*' is present: the
+    // residues themselves are then pinned and uploaded)
     uint8_t* packed = nullptr;
-    bool packed_pinned = false;
-    std::vector<std::string> names;
+    HostBuf b_res, b_offs, b_packed;
+    std::string name_blob;  // NUL-terminated names back to back; empty when no names were given
+    std::vector<uint64_t> name_off;
+    ~ks_proteome() { b_res.release(); b_offs.release(); b_packed.release(); }
 };
 
 namespace {
-void* host_alloc(size_t bytes, bool* pinned) {
-    void* p = nullptr;
-    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) == cudaSuccess) { *pinned = true; return p; }
-    (void)cudaGetLastError();  // no device in this process (CPU-only host tests): pageable memory
-    *pinned = false;
-    p = malloc(bytes);
-    if (!p) throw std::bad_alloc();
-    return p;
+
+// residues are in p->residues (pageable): build the packed upload copy, or pin the residues when they cannot be packed
+void finish_proteome(ks_proteome* p) {
+    memset(p->residues + p->n_res, 0, 64);
+    p->b_packed.alloc(packed_bytes(p->n_res), true);
+    p->packed = (uint8_t*)p->b_packed.p;
+    if (!pack_residues_parallel(p->residues, p->n_res, p->packed)) {
+        p->b_packed.release();
+        p->packed = nullptr;
+        HostBuf pin;
+        pin.alloc(p->n_res + 64, true);
+        memcpy(pin.p, p->residues, p->n_res + 64);
+        p->b_res.release();
+        p->b_res = pin;
+        p->residues = (uint8_t*)pin.p;
+    }
 }
-void host_free(void* p, bool pinned) {
-    if (!p) return;
-    if (pinned) cudaFreeHost(p); else free(p);
+
+ks_proteome* new_proteome(uint64_t n_res, uint64_t n_prot) {
+    ks_proteome* p = new ks_proteome();
+    try {
+        p->b_res.alloc(n_res + 64, false);
+        p->b_offs.alloc((n_prot + 1) * 8, true);
+    } catch (...) {
+        delete p;
+        throw;
+    }
+    p->residues = (uint8_t*)p->b_res.p;
+    p->offsets = (uint64_t*)p->b_offs.p;
+    p->n_prot = n_prot;
+    p->n_res = n_res;
+    return p;
 }
 
 ks_proteome* make_proteome(const uint8_t* res, uint64_t n_res, const uint64_t* offs, uint64_t n_prot) {
-    ks_proteome* p = new ks_proteome();
-    bool pin_a = false, pin_b = false;
-    p->residues = (uint8_t*)host_alloc(n_res + 64, &pin_a);
-    p->offsets = (uint64_t*)host_alloc((n_prot + 1) * 8, &pin_b);
-    p->pinned = pin_a && pin_b;
-    if (pin_a != pin_b) {  // keep one allocator for both
-        host_free(p->residues, pin_a); host_free(p->offsets, pin_b);
-        p->residues = (uint8_t*)malloc(n_res + 64); p->offsets = (uint64_t*)malloc((n_prot + 1) * 8);
-        p->pinned = false;
-        if (!p->residues || !p->offsets) throw std::bad_alloc();
+    ks_proteome* p = new_proteome(n_res, n_prot);
+    try {
+        if (n_res) {  // first touch of a fresh buffer: all host threads copy (and fault the pages in) at once
+            const int t = ingest_threads((size_t)n_res);
+            parallel_chunks(t, [&](int i) {
+                const uint64_t a = n_res * (uint64_t)i / t, b = n_res * (uint64_t)(i + 1) / t;
+                memcpy(p->residues + a, res + a, b - a);
+            });
+        }
+        memcpy(p->offsets, offs, (n_prot + 1) * 8);
+        finish_proteome(p);
+    } catch (...) {
+        delete p;
+        throw;
     }
-    if (n_res) memcpy(p->residues, res, n_res);
-    memset(p->residues + n_res, 0, 64);
-    memcpy(p->offsets, offs, (n_prot + 1) * 8);
-    p->n_prot = n_prot;
-    p->n_res = n_res;
-    p->packed = (uint8_t*)host_alloc(packed_bytes(n_res), &p->packed_pinned);
-    if (!pack_residues(p->residues, n_res, p->packed)) {
-        host_free(p->packed, p->packed_pinned);
-        p->packed = nullptr;
+    return p;
+}
+
+void set_names(ks_proteome* p, const std::vector<std::string>& names) {
+    p->name_off.resize(names.size());
+    size_t total = 0;
+    for (auto& n : names) total += n.size() + 1;
+    p->name_blob.resize(total);
+    size_t at = 0;
+    for (size_t i = 0; i < names.size(); i++) {
+        p->name_off[i] = at;
+        memcpy(&p->name_blob[at], names[i].c_str(), names[i].size() + 1);
+        at += names[i].size() + 1;
+    }
+}
+
+double wall_ms() {
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+
+ks_proteome* proteome_from_fasta(const char* path, uint64_t ambig_seed, NormalizeMode mode) {
+    static const bool timing = getenv("KS_TIMING") != nullptr;  // read once
+    const double t0 = timing ? wall_ms() : 0;
+    FastaBytes fb;
+    load_fasta_bytes(path, &fb);
+    const double t1 = timing ? wall_ms() : 0;
+    FastaParser parser(fb.data, fb.size, mode, ambig_seed);
+    const ParsedFasta t = parser.count();
+    const double t2 = timing ? wall_ms() : 0;
+    ks_proteome* p = new_proteome(t.n_res, t.n_rec);
+    try {
+        p->name_blob.resize(t.name_bytes);
+        p->name_off.resize(t.n_rec);
+        const double t3 = timing ? wall_ms() : 0;
+        InvalidResidue bad;
+        if (!parser.fill(p->residues, p->offsets, t.name_bytes ? &p->name_blob[0] : nullptr, p->name_off.data(), &bad)) fail_residue(bad);
+        for (uint64_t i = 0; i < t.n_rec; i++)
+            if (p->offsets[i + 1] - p->offsets[i] > 0xffffffffull) fail(KS_ERR_CAPACITY, "protein longer than 2^32-1 residues");
+        const double t4 = timing ? wall_ms() : 0;
+        finish_proteome(p);
+        if (timing) fprintf(stderr, "[ks] from_fasta: map %.1f ms, count %.1f, alloc %.1f, fill %.1f, pack %.1f ms\n", t1 - t0, t2 - t1,
+                            t3 - t2, t4 - t3, wall_ms() - t4);
+    } catch (...) {
+        delete p;
+        throw;
     }
     return p;
 }
@@ -164,10 +299,11 @@ void ks_id_of_mins(const uint64_t* mins, uint64_t n, char out[17]) {
 }
 
 // ---- ingest -------------------------------------------------------------------------------------
-ks_status ks_proteome_from_sequences(const char* const* seqs, const uint64_t* lens, const char* const* names, uint64_t n,
-                                     uint64_t ambig_seed, ks_proteome** out) {
+ks_status ks_proteome_from_sequences_mode(const char* const* seqs, const uint64_t* lens, const char* const* names, uint64_t n,
+                                          uint64_t ambig_seed, int mode, ks_proteome** out) {
     return guarded([&] {
         if (!out || (n && (!seqs || !lens))) fail(KS_ERR_VALIDATION, "Validation error: null argument");
+        if (mode != KS_NORMALIZE_KMERSEEK && mode != KS_NORMALIZE_SOURMASH) fail(KS_ERR_VALIDATION, "Validation error: unknown normalisation mode");
         std::vector<uint8_t> res;
         std::vector<uint64_t> offs(n + 1, 0);
         uint64_t total = 0;
@@ -175,34 +311,34 @@ ks_status ks_proteome_from_sequences(const char* const* seqs, const uint64_t* le
         res.reserve(total);
         for (uint64_t i = 0; i < n; i++) {
             InvalidResidue bad;
-            if (!normalize_into(seqs[i], lens[i], i, ambig_seed, res, &bad)) fail_residue(bad);
+            if (!normalize_into(seqs[i], lens[i], i, ambig_seed, mode == KS_NORMALIZE_SOURMASH, res, &bad)) fail_residue(bad);
             if (res.size() - offs[i] > 0xffffffffull) fail(KS_ERR_CAPACITY, "protein longer than 2^32-1 residues");
             offs[i + 1] = res.size();
         }
         ks_proteome* p = make_proteome(res.data(), res.size(), offs.data(), n);
-        if (names) for (uint64_t i = 0; i < n; i++) p->names.emplace_back(names[i] ? names[i] : "");
+        if (names) {
+            std::vector<std::string> nm;
+            nm.reserve(n);
+            for (uint64_t i = 0; i < n; i++) nm.emplace_back(names[i] ? names[i] : "");
+            set_names(p, nm);
+        }
         *out = p;
     });
 }
+ks_status ks_proteome_from_sequences(const char* const* seqs, const uint64_t* lens, const char* const* names, uint64_t n,
+                                     uint64_t ambig_seed, ks_proteome** out) {
+    return ks_proteome_from_sequences_mode(seqs, lens, names, n, ambig_seed, KS_NORMALIZE_KMERSEEK, out);
+}
 
-ks_status ks_proteome_from_fasta(const char* path, uint64_t ambig_seed, ks_proteome** out) {
+ks_status ks_proteome_from_fasta_mode(const char* path, uint64_t ambig_seed, int mode, ks_proteome** out) {
     return guarded([&] {
         if (!out || !path) fail(KS_ERR_VALIDATION, "Validation error: null argument");
-        std::vector<std::string> names, seqs;
-        read_fasta(path, names, seqs);
-        std::vector<uint8_t> res;
-        std::vector<uint64_t> offs(seqs.size() + 1, 0);
-        for (size_t i = 0; i < seqs.size(); i++) {
-            InvalidResidue bad;
-            if (!normalize_into(seqs[i].data(), seqs[i].size(), i, ambig_seed, res, &bad)) fail_residue(bad);
-            if (res.size() - offs[i] > 0xffffffffull) fail(KS_ERR_CAPACITY, "protein longer than 2^32-1 residues");
-            offs[i + 1] = res.size();
-            std::string().swap(seqs[i]);
-        }
-        ks_proteome* p = make_proteome(res.data(), res.size(), offs.data(), names.size());
-        p->names = std::move(names);
-        *out = p;
+        if (mode != KS_NORMALIZE_KMERSEEK && mode != KS_NORMALIZE_SOURMASH) fail(KS_ERR_VALIDATION, "Validation error: unknown normalisation mode");
+        *out = proteome_from_fasta(path, ambig_seed, (NormalizeMode)mode);
     });
+}
+ks_status ks_proteome_from_fasta(const char* path, uint64_t ambig_seed, ks_proteome** out) {
+    return ks_proteome_from_fasta_mode(path, ambig_seed, KS_NORMALIZE_KMERSEEK, out);
 }
 
 ks_status ks_proteome_from_packed(const uint8_t* residues, const uint64_t* offsets, uint64_t n_proteins, ks_proteome** out) {
@@ -222,15 +358,9 @@ uint64_t ks_proteome_n_residues(const ks_proteome* p) { return p ? p->n_res : 0;
 const uint8_t* ks_proteome_residues(const ks_proteome* p) { return p ? p->residues : nullptr; }
 const uint64_t* ks_proteome_offsets(const ks_proteome* p) { return p ? p->offsets : nullptr; }
 const char* ks_proteome_name(const ks_proteome* p, uint64_t i) {
-    return (p && i < p->names.size()) ? p->names[i].c_str() : "";
+    return (p && i < p->name_off.size()) ? p->name_blob.data() + p->name_off[i] : "";
 }
-void ks_proteome_free(ks_proteome* p) {
-    if (!p) return;
-    host_free(p->residues, p->pinned);
-    host_free(p->offsets, p->pinned);
-    host_free(p->packed, p->packed_pinned);
-    delete p;
-}
+void ks_proteome_free(ks_proteome* p) { delete p; }
 
 }  // extern "C"
 
@@ -337,6 +467,7 @@ struct ks_index {
     Buf b_dense_rank, b_dense_hash, b_dense_flags, b_dense_work;
     bool pending_dense = false;
     bool scattered = false;  // the only batch was sketched straight into the regions of the unstable partition (pair_plan)
+    bool scatter_unchecked = false;  // ... and its count / zero-hash flag (d_count) have not been read yet: finalize does
     PairSortPlan pair_plan;
     Buf b_pair_work;
     uint32_t build_path = 0;  // ks_stats.build_path of the last finalize
@@ -484,6 +615,7 @@ void materialize_pending(ks_index* x) {
     x->pending_dense = false;
     x->dense_sketched = false;
     x->scattered = false;  // the scattered tuples are dropped: the batch is sketched again, in order
+    x->scatter_unchecked = false;
     x->n_tuples = x->n_prot = x->n_res = x->n_windows = 0;
     sketch_resident_general(x);
 }
@@ -556,12 +688,20 @@ void sketch_resident(ks_index* x) {
         KS_CUDA(cudaEventRecord(x->ev[EV_SK0], x->stream));
         KS_CUDA(launch_sketch(a, x->stream, &x->l_sketch));
         KS_CUDA(cudaEventRecord(x->ev[EV_SK1], x->stream));
+        x->t_sketch = true;
+        const bool exact = x->max_hash == ~0ull;
+        if (exact) {
+            // scaled == 1: the tuple count is known from the offsets; the kernel's own count and its zero-hash flag are
+            // read together with the build's results at the end of finalize (no host round trip here)
+            x->scattered = true;
+            x->scatter_unchecked = true;
+            x->n_tuples = b.n_windows; x->n_prot = b.n_prot; x->n_res = b.n_res; x->n_windows = b.n_windows;
+            return;
+        }
         uint64_t r[2] = {0, 0};
         KS_CUDA(cudaMemcpyAsync(r, x->d_count, 16, cudaMemcpyDeviceToHost, x->stream));
         KS_CUDA(cudaStreamSynchronize(x->stream));
-        x->t_sketch = true;
-        const bool exact = x->max_hash == ~0ull;
-        if (exact ? ((r[1] >> 32) == 0 && r[0] == b.n_windows) : r[0] <= MAX_TUPLES) {
+        if (r[0] <= MAX_TUPLES) {
             x->scattered = true;
             x->n_tuples = r[0]; x->n_prot = b.n_prot; x->n_res = b.n_res; x->n_windows = b.n_windows;
             return;
@@ -812,14 +952,8 @@ bool dense_finalize(ks_index* x) {
     const uint32_t P = (uint32_t)b.n_prot;
     const DenseSortPlan plan = x->dense_plan;
     char* work = (char*)x->b_dense_work.p;
-    uint32_t exc[2] = {0, 0};  // [0] unhandled exception (or a zero hash), [1] exception keys were emitted
-    uint64_t produced = 0;
-    KS_CUDA(cudaMemcpyAsync(exc, x->dense_flags + 1, 8, cudaMemcpyDeviceToHost, x->stream));
-    KS_CUDA(cudaMemcpyAsync(&produced, x->d_count, 8, cudaMemcpyDeviceToHost, x->stream));
-    KS_CUDA(cudaStreamSynchronize(x->stream));
-    if (exc[0]) return false;
-    if (produced != n) fail(KS_ERR_CUDA, "internal error: dense path produced an unexpected number of tuples");
-    // sort + CSR
+    // No host round trip between the rank kernel and the CSR: the kernels read the rank kernel's flags on the device, and
+    // everything the host has to know (flags, counts, overflow) comes back in ONE read at the end.
     int bits = 8;  // directory as on the general path
     while (bits < 24 && (4ull << bits) < n) bits++;
     x->dir_bits = bits;
@@ -837,7 +971,8 @@ bool dense_finalize(ks_index* x) {
     c.n = n; c.n_prot = P; c.k = k;
     c.rank_bits = (int)k + 1; c.pid_bits = x->dense_pid_bits; c.pos_bits = x->dense_pos_bits;
     c.offsets = b.offs; c.sorted_hash = x->dense_hash;
-    c.residues = b.res; c.packed = b.packed ? 1 : 0; c.has_exceptions = exc[1] ? 1 : 0;
+    c.residues = b.res; c.packed = b.packed ? 1 : 0;
+    c.skip_flag = x->dense_flags + 1; c.exc_flag = x->dense_flags + 2;
     c.loc = x->d_loc; c.keys = x->keys; c.key_grp = x->key_grp; c.grp_start = x->grp_start;
     c.t_size = x->t_size; c.t_abund = x->t_abund; c.d_counts = x->d_counts;
     c.temp_bytes = dense_csr_temp_bytes(n);
@@ -850,13 +985,18 @@ bool dense_finalize(ks_index* x) {
     x->l_csr += 1;
     KS_CUDA(cudaEventRecord(x->ev[EV_CS1], x->stream));
     x->t_sketch = x->t_sort = x->t_csr = true;
-    uint64_t cnt[2];
-    uint32_t overflow = 0;
-    KS_CUDA(cudaMemcpyAsync(cnt, x->d_counts, 16, cudaMemcpyDeviceToHost, x->stream));
-    if (plan.custom) KS_CUDA(cudaMemcpyAsync(&overflow, work + plan.off_overflow, 4, cudaMemcpyDeviceToHost, x->stream));
+    uint64_t* hw = x->h_words + HW_TOTALS;  // pinned: [0..1] counts, [2] produced, [3] flags 1|2, [4] overflow
+    hw[4] = 0;
+    KS_CUDA(cudaMemcpyAsync(hw, x->d_counts, 16, cudaMemcpyDeviceToHost, x->stream));
+    KS_CUDA(cudaMemcpyAsync(hw + 2, x->d_count, 8, cudaMemcpyDeviceToHost, x->stream));
+    KS_CUDA(cudaMemcpyAsync(hw + 3, x->dense_flags + 1, 8, cudaMemcpyDeviceToHost, x->stream));
+    if (plan.custom) KS_CUDA(cudaMemcpyAsync(hw + 4, work + plan.off_overflow, 4, cudaMemcpyDeviceToHost, x->stream));
     KS_CUDA(cudaStreamSynchronize(x->stream));
-    if (overflow) return false;  // heavy repeats of one k-mer overflowed a sort bucket: the general path handles those
-    x->U = cnt[0]; x->G = cnt[1];
+    const uint32_t unhandled = (uint32_t)hw[3];  // [0] of the pair: an exception the path does not handle, or a zero hash
+    if (unhandled) return false;
+    if (hw[2] != n) fail(KS_ERR_CUDA, "internal error: dense path produced an unexpected number of tuples");
+    if ((uint32_t)hw[4]) return false;  // heavy repeats of one k-mer overflowed a sort bucket: the general path handles those
+    x->U = hw[0]; x->G = hw[1];
     x->hash_col_valid = false;  // d_hash holds rank keys: the sorted hash column is rebuilt from the CSR on demand
     x->build_path = plan.custom ? 1u : 2u;
     x->pending_dense = false;
@@ -894,14 +1034,14 @@ void finalize(ks_index* x) {
     a.hash_a = x->d_hash; a.loc_a = x->d_loc; a.hash_b = hb; a.loc_b = lb;
     a.n = n; a.n_prot = P; a.end_bit = x->end_bit(); a.max_hash = x->max_hash;
     a.repeat_heavy = repeat_heavy(x, n) ? 1 : 0;  // measured: the bin kernel only wins when repeats are rare
-    int overflowed = 0;
+    const uint32_t* d_overflow = nullptr;  // device flag of the unstable partition (a region overflowed)
     if (x->scattered) {  // the tuples sit in the regions of the unstable partition; the postings go to d_loc
         x->n_tuples = 0;
         grow_tuples(x, n);
         x->n_tuples = n;
         a.loc_a = x->d_loc; a.hash_a = x->d_hash;
         a.plan = x->pair_plan; a.work = x->b_pair_work.p; a.offsets = x->batch.offs; a.k = x->params.ksize;
-        a.overflowed = &overflowed;
+        a.overflow_dev = &d_overflow;
         a.abund_ready = x->max_hash != ~0ull ? 1 : 0;
     }
     a.keys = x->keys; a.key_grp = x->key_grp; a.grp_start = x->grp_start; a.t_size = x->t_size; a.t_abund = x->t_abund;
@@ -916,16 +1056,26 @@ void finalize(ks_index* x) {
     KS_CUDA(cudaEventRecord(x->ev[EV_SO0], x->stream));
     KS_CUDA(build_index(a, x->stream, &in_a, &x->l_sort, &x->l_csr));
     KS_CUDA(cudaEventRecord(x->ev[EV_CS1], x->stream));
-    if (overflowed) {  // a k-mer repeated thousands of times filled a region: sketch again in order, stable partition
-        KS_CUDA(cudaStreamSynchronize(x->stream));
+    const bool was_scattered = x->scattered;
+    double t2 = dbg ? now_ms() : 0;
+    x->t_sort = x->t_csr = true;
+    // everything the host has to know comes back in ONE read: the CSR totals, and for a scattered batch the partition's
+    // overflow flag and (when the sketch was not checked yet) the sketch kernel's count and zero-hash flag
+    uint64_t* hw = x->h_words + HW_TOTALS;
+    hw[2] = n; hw[3] = 0; hw[4] = 0;
+    KS_CUDA(cudaMemcpyAsync(hw, x->d_counts, 16, cudaMemcpyDeviceToHost, x->stream));
+    if (d_overflow) KS_CUDA(cudaMemcpyAsync(hw + 4, d_overflow, 4, cudaMemcpyDeviceToHost, x->stream));
+    if (x->scatter_unchecked) KS_CUDA(cudaMemcpyAsync(hw + 2, x->d_count, 16, cudaMemcpyDeviceToHost, x->stream));
+    KS_CUDA(cudaStreamSynchronize(x->stream));
+    if (was_scattered && ((uint32_t)hw[4] != 0 || hw[2] != n || (hw[3] >> 32) != 0)) {
+        // a k-mer repeated thousands of times filled a region, or a window hashed to exactly 0 (it must be dropped):
+        // sketch again in order, stable partition
         materialize_pending(x);
         finalize(x);
         return;
     }
-    const bool was_scattered = x->scattered;
     x->scattered = false;
-    double t2 = dbg ? now_ms() : 0;
-    x->t_sort = x->t_csr = true;
+    x->scatter_unchecked = false;
     if (!in_a) {  // the sorted tuples sit in the alternate pair: swap roles, nothing is freed
         std::swap(x->d_hash, hb); std::swap(x->d_loc, lb);
         const size_t cap_bytes = x->cap * 8;
@@ -933,10 +1083,7 @@ void finalize(ks_index* x) {
         x->b_alt_hash.p = hb; x->b_alt_hash.bytes = cap_bytes;
         x->b_alt_loc.p = lb; x->b_alt_loc.bytes = cap_bytes;
     }
-    uint64_t c[2];
-    KS_CUDA(cudaMemcpyAsync(c, x->d_counts, 16, cudaMemcpyDeviceToHost, x->stream));
-    KS_CUDA(cudaStreamSynchronize(x->stream));
-    x->U = c[0]; x->G = c[1];
+    x->U = hw[0]; x->G = hw[1];
     x->hash_col_valid = hash_written != 0;
     x->build_path = was_scattered ? 3u : 0u;
     x->finalized = true;
@@ -992,40 +1139,6 @@ struct ResultDevice {
     void* pinned = nullptr;
     size_t pinned_bytes = 0;
 };
-
-// Pinned blocks are recycled across searches: cudaHostAlloc of a result-sized block costs more than the copy.
-std::mutex g_pin_mu;
-std::vector<std::pair<void*, size_t>> g_pin_free;
-size_t g_pin_pooled = 0;
-
-void* pinned_get(size_t bytes, size_t* got) {
-    {
-        std::lock_guard<std::mutex> lk(g_pin_mu);
-        int best = -1;
-        for (size_t i = 0; i < g_pin_free.size(); i++)
-            if (g_pin_free[i].second >= bytes && (best < 0 || g_pin_free[i].second < g_pin_free[best].second)) best = (int)i;
-        if (best >= 0) {
-            auto b = g_pin_free[best];
-            g_pin_free.erase(g_pin_free.begin() + best);
-            g_pin_pooled -= b.second;
-            *got = b.second;
-            return b.first;
-        }
-    }
-    size_t want = bytes + bytes / 4 + (1u << 20);
-    void* p = nullptr;
-    KS_CUDA(cudaHostAlloc(&p, want, cudaHostAllocDefault));
-    *got = want;
-    return p;
-}
-
-void pinned_put(void* p, size_t bytes) {
-    if (!p) return;
-    std::lock_guard<std::mutex> lk(g_pin_mu);
-    if (g_pin_pooled + bytes > (8ull << 30)) { cudaFreeHost(p); return; }
-    g_pin_free.emplace_back(p, bytes);
-    g_pin_pooled += bytes;
-}
 
 }  // namespace
 
@@ -1128,6 +1241,7 @@ ks_status ks_index_clear(ks_index* x) {
         x->pending_dense = false;
         x->dense_sketched = false;
         x->scattered = false;
+        x->scatter_unchecked = false;
         x->n_tuples = 0; x->n_prot = 0; x->n_res = 0; x->n_windows = 0;
     });
 }

@@ -9,6 +9,8 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
+#include <algorithm>
+
 #include "common.cuh"
 #include "dense.cuh"
 #include "dense_scatter.cuh"
@@ -268,7 +270,10 @@ constexpr int DB_WARPS = DB_THREADS / 32;
 constexpr int DB_CAP = 4096;
 constexpr int DB_BIN_BITS = 13;
 constexpr int DB_BINS = 1 << DB_BIN_BITS;  // 16-bit counters, two per word: a bucket holds at most 4096 keys
-constexpr size_t DB_SMEM = (size_t)DB_CAP * 8 + (size_t)DB_BINS * 2;
+constexpr int DB_HASH_SLICE = 512;         // pattern hashes of a bucket's rank range kept in shared memory when they fit
+constexpr size_t DB_SMEM = (size_t)DB_CAP * 8 + (size_t)DB_BINS * 2 + (size_t)DB_HASH_SLICE * 8;
+constexpr int DB_BINS_PER_THREAD = DB_BINS / DB_THREADS;  // 16
+constexpr uint32_t DB_BIN_SORT_MAX = 24;   // a bin of more keys sends the bucket to the odd-even rounds
 
 struct DenseBucketArgs {
     const uint64_t* region2;   // final buckets, DB_CAP keys each
@@ -290,20 +295,33 @@ struct DenseBucketArgs {
     const uint64_t* offsets;
     int packed;
     uint32_t k;
+    const uint32_t* exc_flag;  // device: != 0 when the rank kernel emitted exception keys (picks the instantiation that runs)
+    const uint32_t* skip_flag; // device: != 0 when the build is void (unhandled exception / table unusable): nothing to do
 };
 
 // 4 CTAs per SM (no loc gather here, so the smaller L1 does not hurt): 2.84 ms against 3.18 ms with 3 on C2
 #ifndef KS_DB_CTAS
 #define KS_DB_CTAS 4
 #endif
-// EXC: the batch holds exception keys (known to the host after the rank kernel); the common instantiation carries none
-// of that code.
+// One CTA per final bucket (<= 4096 keys, all distinct, final order = numeric order):
+//   1. counting pass over the item's top 13 bits (shared-memory atomics on packed 16-bit counters), scan, scatter: the
+//      bucket is then ordered at bin granularity -- a bin is (rank, 1/32 of the proteins) on C2 and holds 0-3 keys;
+//   2. the thread that owns 16 consecutive bins puts each of them in order by insertion (no barrier, no rounds); a bin
+//      of more than DB_BIN_SORT_MAX keys (a k-mer repeated in one stretch of proteins) or exception keys (which can sit
+//      in a later bin than a larger key) send the whole bucket through odd-even transposition rounds instead;
+//   3. heads from the rank / protein fields; the aggregate (keys, groups) is published for the look-back BEFORE the
+//      postings are stored, the prefix collected after: the stores hide part of the wait for the predecessors;
+//   4. keys / key_grp / grp_start from shared memory; the pattern hashes of the bucket's rank range were preloaded with one
+//      coalesced read at the top (they are consecutive entries of sorted_hash).
+// EXC: the batch holds exception keys.  Both instantiations are launched back to back; the device flag decides which one
+// does the work (the other's CTAs exit at once), so that the host never waits for the rank kernel's flags.
 template <bool EXC>
 __global__ void __launch_bounds__(DB_THREADS, KS_DB_CTAS)
 dense_bucket_kernel(DenseBucketArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t* B = reinterpret_cast<uint64_t*>(smem_raw);      // [DB_CAP] items: the key's bits below the bucket bits, left-aligned
     uint32_t* cnt = reinterpret_cast<uint32_t*>(B + DB_CAP);  // [DB_BINS / 2] words of two 16-bit bin counters, then offsets
+    uint64_t* s_hash = reinterpret_cast<uint64_t*>(cnt + DB_BINS / 2);  // [DB_HASH_SLICE]
     const uint16_t* off16 = reinterpret_cast<const uint16_t*>(cnt);
     __shared__ uint32_t s_wsum[DB_WARPS];
     __shared__ uint32_t s_cw[8 * DB_WARPS];
@@ -311,12 +329,32 @@ dense_bucket_kernel(DenseBucketArgs a) {
     __shared__ uint32_t s_bucket;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t lt = (1u << lane) - 1u;
+    if (*a.skip_flag != 0) {  // the build is void (the host takes the general path): leave defined totals behind
+        if (!EXC && blockIdx.x == 0 && tid == 0) { a.d_counts[0] = 0; a.d_counts[1] = 0; }
+        return;
+    }
+    if ((*a.exc_flag != 0) != EXC) return;  // (uniform over the grid) the other instantiation does the work
+    // persistent CTAs: buckets are taken by ticket, so a bucket's predecessors have always started (look-back)
+    for (;;) {
+    __syncthreads();  // the previous bucket's shared memory is no longer read
     if (tid == 0) s_bucket = atomicAdd(a.ticket, 1u);
     reinterpret_cast<uint4*>(cnt)[tid] = make_uint4(0, 0, 0, 0);
     reinterpret_cast<uint4*>(cnt)[tid + DB_THREADS] = make_uint4(0, 0, 0, 0);
     __syncthreads();
     const uint32_t b = s_bucket;
+    if (b >= a.nb) break;
+    const uint64_t* src = a.region2 + (uint64_t)b * DB_CAP;
+    const int up = 64 - a.rem_bits;  // item = key << up: the bucket bits fall off the top
+    const int rrb = a.rem_bits - a.loc_bits;  // rank' bits below the bucket bits (the lowest is the parity)
+    uint64_t item[8];
+    // the first rows are read before the bucket's size is known (a bucket region is DB_CAP keys of allocated memory; what
+    // lies past the size is not used): the size and the keys come back in one round trip instead of two
+    constexpr int SPEC_ROWS = 4;
+#pragma unroll
+    for (int r = 0; r < SPEC_ROWS; r++) item[r] = src[r * DB_THREADS + tid];
     const uint32_t m = min(a.cursor2[b], (uint32_t)DB_CAP);
+    const bool hash_slice = rrb >= 1 && rrb <= 10;  // at most 512 pattern ranks under this bucket
+    if (hash_slice && tid < (1u << (rrb - 1))) s_hash[tid] = a.sorted_hash[((uint64_t)b << (rrb - 1)) + tid];
     if (m == 0) {  // pass the running totals on; the last bucket writes them out
         if (warp == 0) {
             const uint64_t excl = scan_lookback(a.status, b, 0);
@@ -325,14 +363,17 @@ dense_bucket_kernel(DenseBucketArgs a) {
                 a.d_counts[0] = U; a.d_counts[1] = G; a.key_grp[U] = (uint32_t)G; a.grp_start[G] = (uint32_t)a.n;
             }
         }
-        return;
+        continue;
     }
-    const uint64_t* src = a.region2 + (uint64_t)b * DB_CAP;
-    const int up = 64 - a.rem_bits;  // item = key << up: the bucket bits fall off the top
+#pragma unroll
+    for (int r = SPEC_ROWS; r < 8; r++) {
+        if (r * DB_THREADS >= m) break;
+        const uint32_t j = r * DB_THREADS + tid;
+        if (j < m) item[r] = src[j];
+    }
     // bin = the item's top 13 bits with the parity bit of rank' squeezed out when it lies among them (it is 1 for every
     // pattern key and would leave half of the bins empty).  An exception key (parity 0) can then land in a later bin than a
-    // larger key; the odd-even rounds below run until the whole bucket is in order, so that only costs rounds where
-    // exception keys are.
+    // larger key: the odd-even rounds of the EXC instantiation run until the whole bucket is in order.
     const int pb = up + a.loc_bits;  // bit of the item that holds the parity of rank'
     const bool squeeze = pb >= 64 - DB_BIN_BITS && pb < 63;
     const int n_low = squeeze ? DB_BIN_BITS - (63 - pb) : 0;  // bin bits taken from below the parity bit
@@ -340,31 +381,30 @@ dense_bucket_kernel(DenseBucketArgs a) {
         if (!squeeze) return (uint32_t)(it >> (64 - DB_BIN_BITS));
         return (uint32_t)(((it >> (pb + 1)) << n_low) | ((it >> (pb - n_low)) & ((1ull << n_low) - 1ull)));
     };
-    uint64_t item[8];
     uint32_t slot[4] = {0, 0, 0, 0};
 #pragma unroll
     for (int r = 0; r < 8; r++) {
         const uint32_t j = r * DB_THREADS + tid;
         if (r * DB_THREADS >= m) break;
-        if (j < m) item[r] = src[j] << up;
-    }
-#pragma unroll
-    for (int r = 0; r < 8; r++) {
-        const uint32_t j = r * DB_THREADS + tid;
-        if (r * DB_THREADS >= m) break;
         if (j < m) {
+            item[r] <<= up;
             const uint32_t bin = bin_of(item[r]), sh16 = 16 * (bin & 1u);
             const uint32_t old = (atomicAdd(&cnt[bin >> 1], 1u << sh16) >> sh16) & 0xffffu;  // no carry: counts <= 4096
             slot[r >> 1] |= old << (16 * (r & 1));
         }
     }
     __syncthreads();
+    bool big_bin = false;
     {   // exclusive scan of the 8192 counters; thread t owns bins 16t .. 16t+15 (8 words)
         uint4 c0 = reinterpret_cast<uint4*>(cnt)[2 * tid], c1 = reinterpret_cast<uint4*>(cnt)[2 * tid + 1];
         uint32_t w[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
         uint32_t total = 0;
 #pragma unroll
-        for (int i = 0; i < 8; i++) total += (w[i] & 0xffffu) + (w[i] >> 16);
+        for (int i = 0; i < 8; i++) {
+            const uint32_t lo = w[i] & 0xffffu, hi = w[i] >> 16;
+            total += lo + hi;
+            big_bin |= lo > DB_BIN_SORT_MAX || hi > DB_BIN_SORT_MAX;
+        }
         uint32_t incl = total;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -393,8 +433,28 @@ dense_bucket_kernel(DenseBucketArgs a) {
         if (r * DB_THREADS >= m) break;
         if (j < m) B[off16[bin_of(item[r])] + ((slot[r >> 1] >> (16 * (r & 1))) & 0xffffu)] = item[r];
     }
-    __syncthreads();
-    {   // odd-even transposition until nothing moves (a bin holds the few keys of one hash in a handful of proteins)
+    const int use_rounds = __syncthreads_or((EXC || big_bin) ? 1 : 0);
+    if (!use_rounds) {
+        // every bin in order, by the thread that owns it: bins hold a handful of keys at most
+        uint4 c0 = reinterpret_cast<uint4*>(cnt)[2 * tid], c1 = reinterpret_cast<uint4*>(cnt)[2 * tid + 1];
+        const uint32_t w[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+        const uint32_t end_all = tid == DB_THREADS - 1 ? m : (cnt[8 * (tid + 1)] & 0xffffu);
+        if (end_all - (w[0] & 0xffffu) >= 2) {  // (most threads: a few keys over 16 bins, most bins empty or single)
+#pragma unroll
+            for (int i = 0; i < DB_BINS_PER_THREAD; i++) {
+                const uint32_t lo = (w[i >> 1] >> (16 * (i & 1))) & 0xffffu;
+                const uint32_t hi = i == DB_BINS_PER_THREAD - 1 ? end_all : (w[(i + 1) >> 1] >> (16 * ((i + 1) & 1))) & 0xffffu;
+                for (uint32_t t = lo + 1; t < hi; t++) {
+                    const uint64_t x = B[t];
+                    uint32_t u = t;
+                    while (u > lo && B[u - 1] > x) { B[u] = B[u - 1]; u--; }
+                    B[u] = x;
+                }
+            }
+        }
+        __syncthreads();
+    } else {
+        // odd-even transposition until nothing moves
         const uint32_t np0 = m >> 1, np1 = (m - 1) >> 1;
         ulonglong2* B2 = reinterpret_cast<ulonglong2*>(B);
         int again;
@@ -422,14 +482,13 @@ dense_bucket_kernel(DenseBucketArgs a) {
     // run of that rank' is put in (hash, protein, position) order by the thread that owns its first key, and the head
     // tests below compare recomputed hashes.  rank' parity is bit loc_bits of the key, i.e. bit rank_sh of the item --
     // unless no rank bit is left below the bucket bits, in which case the bucket index carries it.
-    const bool any_exc = EXC;
     auto is_exc = [&](uint64_t it) -> bool { return rank_sh < 64 ? ((it >> rank_sh) & 1ull) == 0ull : (b & 1u) == 0u; };
     auto hash_of = [&](uint64_t it) -> uint64_t {
         const uint64_t low = it >> up;
         const uint32_t pid = (uint32_t)((low >> a.pos_bits) & pid_mask);
         return dense_window_hash(a.residues, a.packed, a.offsets[pid] + (low & pos_mask), a.k);
     };
-    if (any_exc) {  // uniform
+    if (EXC) {
         for (uint32_t j = tid; j < m; j += DB_THREADS) {
             const uint64_t it = B[j];
             if (!is_exc(it) || (j && shr(B[j - 1], rank_sh) == shr(it, rank_sh))) continue;  // not the first key of a run
@@ -464,12 +523,8 @@ dense_bucket_kernel(DenseBucketArgs a) {
                 const uint64_t it = B[j];
                 const uint64_t pv = j ? B[j - 1] : ~it;
                 hk = j == 0 || shr(it, rank_sh) != shr(pv, rank_sh);
-                if (any_exc && !hk && is_exc(it)) hk = hash_of(it) != hash_of(pv);  // same rank', maybe another hash
+                if (EXC && !hk && is_exc(it)) hk = hash_of(it) != hash_of(pv);  // same rank', maybe another hash
                 hg = hk || (it >> grp_sh) != (pv >> grp_sh);
-                const uint64_t low = it >> up;  // the key's bits below the bucket bits: (rank low bits |) protein | position
-                const uint32_t pid = (uint32_t)((low >> a.pos_bits) & pid_mask);
-                a.loc[s0 + j] = ((uint64_t)pid << 32) | (low & pos_mask);
-                if (!hg) atomicSub(&a.t_size[pid], 1u);
             }
             flags |= ((hk ? 1u : 0u) | (hg ? 2u : 0u)) << (2 * r);
             const uint32_t ck = __popc(__ballot_sync(0xffffffffu, hk)), cg = __popc(__ballot_sync(0xffffffffu, hg));
@@ -479,6 +534,7 @@ dense_bucket_kernel(DenseBucketArgs a) {
         }
     }
     __syncthreads();
+    uint64_t agg = 0;
     if (warp == 0) {
         uint32_t v[4], local = 0;
 #pragma unroll
@@ -493,8 +549,23 @@ dense_bucket_kernel(DenseBucketArgs a) {
 #pragma unroll
         for (int i = 0; i < 4; i++) { s_cw[lane * 4 + i] = run; run += v[i]; }
         const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
-        const uint64_t agg = (uint64_t)(tot & 0xffffu) | ((uint64_t)(tot >> 16) << 31);
-        const uint64_t excl = scan_lookback(a.status, b, agg);
+        agg = (uint64_t)(tot & 0xffffu) | ((uint64_t)(tot >> 16) << 31);
+        scan_publish(a.status, b, agg);  // successors can go on; our own prefix is collected after the stores below
+    }
+    // the postings go out in final order: this is where part of the wait for the predecessors is hidden
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        const uint32_t j = r * DB_THREADS + tid;
+        if (r * DB_THREADS >= m) break;
+        if (j < m) {
+            const uint64_t low = B[j] >> up;  // the key's bits below the bucket bits: (rank low bits |) protein | position
+            const uint32_t pid = (uint32_t)((low >> a.pos_bits) & pid_mask);
+            a.loc[s0 + j] = ((uint64_t)pid << 32) | (low & pos_mask);
+            if (!((flags >> (2 * r)) & 2u)) atomicSub(&a.t_size[pid], 1u);  // the hash again in the same protein
+        }
+    }
+    if (warp == 0) {
+        const uint64_t excl = scan_collect(a.status, b, agg);
         if (lane == 0) {
             s_base = excl;
             if (b == a.nb - 1) {
@@ -506,7 +577,7 @@ dense_bucket_kernel(DenseBucketArgs a) {
     }
     __syncthreads();
     const uint32_t base_k = (uint32_t)(s_base & 0x7fffffffu), base_g = (uint32_t)(s_base >> 31);
-    const uint64_t rank_top = (uint64_t)b << (a.rem_bits - a.loc_bits);  // the rank bits that are the bucket index
+    const uint64_t rank_top = (uint64_t)b << rrb;  // the rank bits that are the bucket index
 #pragma unroll
     for (int r = 0; r < 8; r++) {
         if (r * DB_THREADS < m) {  // uniform
@@ -519,11 +590,16 @@ dense_bucket_kernel(DenseBucketArgs a) {
             if (hk) {
                 const uint32_t u = base_k + (pre & 0xffffu) + __popc(bk & lt);
                 const uint64_t low_rank = shr(B[j], rank_sh);
-                a.keys[u] = (EXC && is_exc(B[j])) ? hash_of(B[j]) : a.sorted_hash[(rank_top | low_rank) >> 1];
+                uint64_t h;
+                if (EXC && is_exc(B[j])) h = hash_of(B[j]);
+                else if (hash_slice) h = s_hash[low_rank >> 1];
+                else h = a.sorted_hash[(rank_top | low_rank) >> 1];
+                a.keys[u] = h;
                 a.key_grp[u] = g;
             }
         }
     }
+    }  // bucket loop
 }
 
 size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
@@ -651,11 +727,15 @@ cudaError_t dense_build_csr(const DenseCsrArgs& a, cudaStream_t stream, uint64_t
         ba.loc = a.loc; ba.keys = a.keys; ba.key_grp = a.key_grp; ba.grp_start = a.grp_start; ba.t_size = a.t_size;
         ba.d_counts = a.d_counts; ba.n = n;
         ba.residues = a.residues; ba.offsets = a.offsets; ba.packed = a.packed; ba.k = a.k;
+        ba.exc_flag = a.exc_flag; ba.skip_flag = a.skip_flag;
         KS_TRY(cudaFuncSetAttribute(dense_bucket_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DB_SMEM));
         KS_TRY(cudaFuncSetAttribute(dense_bucket_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DB_SMEM));
-        if (a.has_exceptions) dense_bucket_kernel<true><<<nb, DB_THREADS, DB_SMEM, stream>>>(ba);
-        else dense_bucket_kernel<false><<<nb, DB_THREADS, DB_SMEM, stream>>>(ba);
-        if (sort_launches) *sort_launches += 2;
+        // both instantiations, back to back: the rank kernel's device flag picks the one that works (persistent CTAs, so
+        // the idle one costs a few hundred CTAs that exit at once) -- the host does not wait for the flag
+        const unsigned grid = std::min<unsigned>(nb, 148u * KS_DB_CTAS);
+        dense_bucket_kernel<false><<<grid, DB_THREADS, DB_SMEM, stream>>>(ba);
+        dense_bucket_kernel<true><<<grid, DB_THREADS, DB_SMEM, stream>>>(ba);
+        if (sort_launches) *sort_launches += 3;
         return cudaGetLastError();
     }
     char* p = (char*)a.temp;

@@ -38,7 +38,8 @@ struct DenseCsrArgs {
     const uint64_t* offsets;      // device, n_prot + 1 (protein boundaries of the batch)
     const uint8_t* residues;      // device residues of the batch (bytes, or 5-bit codes when packed): the hash of an
     int packed;                   // exception key (even rank') is recomputed from them (hp translation)
-    int has_exceptions;           // the rank kernel emitted exception keys (its flag, read back by the host)
+    const uint32_t* exc_flag;     // device: != 0 when the rank kernel emitted exception keys (picks the bucket kernel)
+    const uint32_t* skip_flag;    // device: != 0 when the build is void (an exception the path does not handle)
     const uint64_t* sorted_hash;  // table
     // outputs
     uint64_t* loc;  // [n] postings (protein << 32 | position), ordered by (hash, protein, position)

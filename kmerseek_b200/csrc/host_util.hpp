@@ -93,13 +93,16 @@ inline uint64_t splitmix64(uint64_t x) {
 struct InvalidResidue { uint32_t ch; uint64_t pos; uint64_t protein; };
 
 // Normalise one sequence into out (appends).  Mirrors to_uppercase (src/rust/index.rs:1000) followed by
-// validate_and_resolve (src/rust/aminoacid.rs:74-105).  Returns false and fills `bad` on an invalid residue.
-inline bool normalize_into(const char* s, uint64_t len, uint64_t protein_index, uint64_t ambig_seed,
+// validate_and_resolve (src/rust/aminoacid.rs:74-105); `raw`: upper-case only (what sourmash add_protein sees on the
+// `kmerseek search` path).  Returns false and fills `bad` on an invalid residue.  B/Z/J: resolved from the seed and the
+// residue's position in its own sequence (see resolve_ambiguous in ingest.hpp; the rule is restated here).
+inline bool normalize_into(const char* s, uint64_t len, uint64_t protein_index, uint64_t ambig_seed, bool raw,
                            std::vector<uint8_t>& out, InvalidResidue* bad) {
     const size_t start = out.size();
     for (uint64_t i = 0; i < len; i++) {
         uint8_t c = (uint8_t)s[i];
         if (c >= 'a' && c <= 'z') c -= 32;
+        if (raw) { out.push_back(c); continue; }
         if (c == '*') { out.push_back(c); break; }
         bool ok = false;
         switch (c) {
@@ -109,7 +112,7 @@ inline bool normalize_into(const char* s, uint64_t len, uint64_t protein_index, 
                 ok = true; break;
             case 'B': case 'Z': case 'J': {
                 const uint64_t n = out.size() - start;
-                const uint64_t r = splitmix64(ambig_seed ^ (protein_index << 32) ^ n) & 1;
+                const uint64_t r = splitmix64(ambig_seed ^ n) & 1;
                 c = c == 'B' ? (r ? 'N' : 'D') : c == 'Z' ? (r ? 'Q' : 'E') : (r ? 'L' : 'I');
                 ok = true; break;
             }

@@ -925,7 +925,7 @@ cudaError_t build_index(const BuildArgs& a, cudaStream_t stream, int* out_in_a, 
     const int lz = 64 - a.end_bit;
     *out_in_a = 1;
     if (a.hash_written) *a.hash_written = 1;
-    if (a.overflowed) *a.overflowed = 0;
+    if (a.overflow_dev) *a.overflow_dev = nullptr;
     if (a.plan.custom && n) {
         // scattered input: [second scatter level,] bucket offsets, bin kernel straight from the final buckets
         const PairSortPlan& pl = a.plan;
@@ -978,10 +978,7 @@ cudaError_t build_index(const BuildArgs& a, cudaStream_t stream, int* out_in_a, 
             dir_kernel<<<148 * 8, 256, 0, stream>>>(a.keys, a.d_counts, a.dir, a.dir_bits, a.dir_shift);
             *csr_launches += 1;
         }
-        uint32_t ovf = 0;
-        KS_TRY(cudaMemcpyAsync(&ovf, overflow, 4, cudaMemcpyDeviceToHost, stream));
-        KS_TRY(cudaStreamSynchronize(stream));
-        if (a.overflowed) *a.overflowed = ovf ? 1 : 0;
+        if (a.overflow_dev) *a.overflow_dev = overflow;  // read by the caller together with the totals: no round trip here
         if (a.hash_written) *a.hash_written = 0;
         *out_in_a = 1;
         return cudaGetLastError();

@@ -51,7 +51,8 @@ struct BuildArgs {
     void* work = nullptr;
     const uint64_t* offsets = nullptr;  // device, n_prot + 1
     uint32_t k = 0;
-    int* overflowed = nullptr;          // out (host): a region overflowed, the build must be redone from ordered tuples
+    const uint32_t** overflow_dev = nullptr;  // out: device flag, != 0 after the build when a region overflowed (the build
+                                              // must then be redone from ordered tuples); the caller reads it
     int abund_ready = 0;                // t_abund was filled by the sketch kernel (scaled > 1); else it comes from the offsets
     // tuples in (protein, pos) order in the `a` pair; `b` is scratch of the same size.
     uint64_t *hash_a, *loc_a, *hash_b, *loc_b;
@@ -76,7 +77,8 @@ struct BuildArgs {
 
 size_t build_temp_bytes(uint64_t n, int end_bit);
 // Sort by hash (stable) + CSR build + directory.  *out_in_a = 1 when the sorted tuples ended in the `a` pair.
-// Synchronises the stream once (oversize-bucket count).  Adds the kernels launched to the two counters.
+// Scattered input: no synchronisation (the caller reads *overflow_dev with the totals); ordered input: synchronises the
+// stream once (oversize-bucket count).  Adds the kernels launched to the two counters.
 cudaError_t build_index(const BuildArgs& a, cudaStream_t stream, int* out_in_a, uint64_t* sort_launches,
                         uint64_t* csr_launches);
 

@@ -132,7 +132,10 @@ int64_t kso_normalize(const uint8_t *seq, uint64_t len, uint64_t protein_index, 
         case 'X': case 'U': case 'O':
             ok = 1; break;
         case 'B': case 'Z': case 'J': {
-            uint64_t r = splitmix64(ambig_seed ^ (protein_index << 32) ^ n) & 1;
+            /* the reference draws at random (aminoacid.rs:45-54); the build fixes the draw by the seed and the residue's
+             * position in its own sequence, independent of the record's index (protein_index is kept for the signature) */
+            (void)protein_index;
+            uint64_t r = splitmix64(ambig_seed ^ n) & 1;
             c = c == 'B' ? (r ? 'N' : 'D') : c == 'Z' ? (r ? 'Q' : 'E') : (r ? 'L' : 'I');
             ok = 1; break;
         }

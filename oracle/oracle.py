@@ -125,8 +125,12 @@ class InvalidAminoAcid(ValueError):
         self.char, self.pos = char, pos
 
 
-def normalize(seq: str, protein_index: int = 0, ambig_seed: int = 0) -> str:
-    """to_uppercase (src/rust/index.rs:1000) + validate_and_resolve (src/rust/aminoacid.rs:74-105)."""
+def normalize(seq: str, protein_index: int = 0, ambig_seed: int = 0, mode: str = "kmerseek") -> str:
+    """to_uppercase (src/rust/index.rs:1000) + validate_and_resolve (src/rust/aminoacid.rs:74-105).
+    mode "sourmash": what the `kmerseek search` path does to its inputs (src/python/kmerseek/sketch.py:28-40 -> sourmash
+    add_protein): upper-case only."""
+    if mode == "sourmash":
+        return "".join(chr(ord(c) - 32) if "a" <= c <= "z" else c for c in seq)
     raw = seq.encode()
     out = ctypes.create_string_buffer(len(raw) + 1)
     bc, bp = ctypes.c_uint8(0), ctypes.c_uint64(0)
