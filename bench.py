@@ -177,19 +177,65 @@ def run_reference(args, cfg, wname):
     print(json.dumps(line), flush=True)
 
 
+def run_c5_sweep(args):
+    """BASELINE.json configs[4]: k 5..24 x {protein, dayhoff, hp}, scaled 1, 10 M-residue proteome, one GPU.  Per cell: the
+    fused sketch kernel's time (CUDA events of the library) and the whole resident build; hit-list equality of all 60
+    cells is tests/test_gpu_c5_sweep.py."""
+    import torch
+    import kmerseek_b200 as K
+    from kmerseek_b200 import _ffi, synth
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (kmerseek_b200 has no CPU fallback)")
+    L = _ffi.lib()
+    chk = K.errors.check
+    peak, _ = peaks()
+    n_res = 10_000_000
+    res, offs = synth.proteome(n_res, 20260105)
+    prot = K.Proteome.from_packed(res, offs)
+    cells = []
+    for moltype in ("protein", "dayhoff", "hp"):
+        for k in range(5, 25):
+            idx = K.ProteomeIndex("c5", k, 1, moltype)
+            chk(L.ks_index_upload(idx._h, prot._h))
+            sk, tot = [], []
+            for i in range(max(args.warmup, 2) + args.steps):
+                t0 = time.perf_counter()
+                chk(L.ks_index_clear(idx._h)); chk(L.ks_index_sketch_resident(idx._h)); chk(L.ks_index_finalize(idx._h))
+                st = idx.stats()
+                if i >= max(args.warmup, 2):
+                    tot.append((time.perf_counter() - t0) * 1e3)
+                    sk.append(st["ms_sketch"])
+            nt, nu = st["n_tuples"], st["n_unique_hashes"]
+            b = sketch_bytes(n_res, len(offs) - 1, nt)
+            cells.append({"moltype": moltype, "k": k, "ms_sketch": round(float(np.mean(sk)), 4), "ms_build_wall": round(float(np.mean(tot)), 4),
+                          "sketch_residues_per_s": n_res / (float(np.mean(sk)) * 1e-3), "sketch_frac_of_hbm": b / float(np.mean(sk)) / 1e6 / peak,
+                          "build_residues_per_s": n_res / (float(np.mean(tot)) * 1e-3), "tuples": nt, "unique_hashes": nu,
+                          "build_path": BUILD_PATHS[st["build_path"]]})
+            idx.close()
+    v = float(np.exp(np.mean([np.log(c["sketch_residues_per_s"]) for c in cells])))
+    print(json.dumps({"metric": "residues/s sketched (geometric mean over the 60 cells)", "value": v, "unit": "residues/s", "n_gpus": 1,
+                      "steps": args.steps, "warmup": max(args.warmup, 2), "higher_is_better": True, "dtype": "u64", "data": "synthetic",
+                      "config": {"workload": "c5_sweep", "residues": n_res, "scaled": 1, "k": "5..24",
+                                 "moltypes": ["protein", "dayhoff", "hp"]}, "cells": cells}), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c2_swissprot_hp_k24_s1", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c2_swissprot_hp_k24_s1", choices=sorted(WORKLOADS) + ["c5_sweep"])
     ap.add_argument("--queries", type=int, default=10_000)
     ap.add_argument("--reference-sample", type=int, default=150_000)
     ap.add_argument("--cpu-fast-sample", type=int, default=20_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the target-run and ingest legs")
     args = ap.parse_args()
+    if args.workload == "c5_sweep":
+        return run_c5_sweep(args)
     cfg = WORKLOADS[args.workload]
     if args.impl == "reference":
         return run_reference(args, cfg, args.workload)

@@ -126,7 +126,8 @@ typedef struct ks_params {
     uint32_t ksize;              /* residues per k-mer (sourmash ksize is 3x this) */
     uint32_t scaled;             /* FracMinHash scaled; max_hash = ks_max_hash(scaled) */
     int32_t moltype;             /* ks_moltype */
-    int32_t store_raw_sequences; /* keep residues on the device after sketching (index.rs:737-743) */
+    int32_t store_raw_sequences; /* recorded only (ks_index_params hands it back): the raw sequences of index.rs:737-743
+                                    are strings of the host mirror; the device keeps no residues beyond the resident batch */
     int32_t device;              /* CUDA device ordinal */
     uint32_t reserved;
 } ks_params;
@@ -146,8 +147,9 @@ ks_status ks_index_sync(ks_index *idx);
  *              (src/rust/index.rs:719-786) followed by store_signatures (:800-830).
  *   finalize : radix sort by hash + CSR build (unique hashes, postings, per-protein sketch sizes).
  *              = the end state of combined_minhash / signatures after process_fasta (:907-961).
- * ks_index_add_proteome = upload + sketch.  ks_index_clear drops tuples and the CSR (keeps the
- * resident batch), ks_index_resketch = clear + sketch the resident batch again (benchmark loop).  */
+ * ks_index_add_proteome = upload + sketch (residues streamed in chunks, hashed as they land).  ks_index_clear drops
+ * tuples and the CSR and keeps the resident batch: clear + ks_index_sketch_resident + ks_index_finalize builds it again
+ * (the benchmark loop).  A build costs ONE host read-back (counts and flags, at the end of finalize).  */
 ks_status ks_index_upload(ks_index *idx, const ks_proteome *p);
 ks_status ks_index_sketch_resident(ks_index *idx);
 ks_status ks_index_add_proteome(ks_index *idx, const ks_proteome *p);
@@ -167,7 +169,7 @@ typedef struct ks_stats {
     uint64_t n_tuples;        /* kept (hash, protein, pos) occurrences */
     uint64_t n_unique_hashes; /* combined_minhash_size(), src/rust/index.rs:519-521 (after finalize) */
     uint64_t n_groups;        /* distinct (hash, protein) pairs = sum of per-protein sketch sizes */
-    uint64_t n_distinct_ids;  /* signature_count(), src/rust/index.rs:514-516 (after finalize) */
+    uint64_t n_distinct_ids;  /* signature_count(): what the last ks_index_signature_count() returned (0 before) */
     uint64_t device_bytes;    /* bytes currently allocated on the device by this handle */
     uint64_t sketch_launches, sort_launches, csr_launches, search_launches; /* kernels launched so far */
     float ms_upload, ms_sketch, ms_sort, ms_csr; /* device time of the last run of each stage (CUDA events) */
@@ -184,6 +186,10 @@ typedef struct ks_stats {
 } ks_stats;
 /* Synchronises the handle's stream. */
 ks_status ks_index_stats(ks_index *idx, ks_stats *out);
+/* signature_count() (src/rust/index.rs:514-516): the signatures map is keyed by the id string (hex of the wrapping sum of
+ * the sketch's mins, src/rust/signature.rs:277-279) and equal ids overwrite (:817-820), so this is the number of DISTINCT
+ * ids over the proteins added.  Computed on demand from the finalized index (per-protein sums on the device). */
+ks_status ks_index_signature_count(ks_index *idx, uint64_t *out);
 
 /* ---------------------------------------------------------------------------------------------
  * Sketch export.  Replaces the accessors of ProteinSignature (src/rust/signature.rs:305-317):

@@ -46,9 +46,12 @@ def cmd_index(a):
 
 def cmd_search(a):
     idx = K.ProteomeIndex(a.target_fasta, a.ksize, a.scaled, a.moltype, device=a.device)
-    t = K.Proteome.from_fasta(a.target_fasta)
+    # the reference's search sketches both files through branchwater manysketch (src/python/kmerseek/sketch.py:28-40):
+    # records reach sourmash add_protein upper-cased and otherwise untouched -- no validation, no '*' truncation, B/Z/J
+    # kept (they translate to 'X' under dayhoff / hp); the index path's normalisation is not applied here
+    t = K.Proteome.from_fasta(a.target_fasta, mode="sourmash")
     idx.add_proteome(t)
-    q = K.Proteome.from_fasta(a.query_fasta)
+    q = K.Proteome.from_fasta(a.query_fasta, mode="sourmash")
     res = K.search(idx, q, hits=a.extract_kmers)
     rows = K.manysearch_rows(res, idx, q.names, targets=t)
     if a.sourmash_search_csv:

@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libkmerseek_b200.so")
+LIB_PATH = os.environ.get("KS_LIB_PATH") or os.path.join(_HERE, "libkmerseek_b200.so")  # (override: kernel experiments)
 
 u8p, u32p, u64p, f64p = (C.POINTER(t) for t in (C.c_uint8, C.c_uint32, C.c_uint64, C.c_double))
 
@@ -102,6 +102,7 @@ SIGNATURES = {
     "ks_index_process_fasta": (C.c_int, [C.c_void_p, C.c_char_p, C.c_uint64]),
     "ks_index_add_tuples": (C.c_int, [C.c_void_p, u64p, u32p, u32p, C.c_uint64, C.c_uint64]),
     "ks_index_stats": (C.c_int, [C.c_void_p, C.POINTER(ks_stats)]),
+    "ks_index_signature_count": (C.c_int, [C.c_void_p, u64p]),
     "ks_sketch_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.POINTER(ks_sketch))]),
     "ks_sketch_free": (None, [C.POINTER(ks_sketch)]),
     "ks_index_export": (C.c_int, [C.c_void_p, C.POINTER(C.POINTER(ks_sketch))]),

@@ -421,6 +421,7 @@ struct Hooks {
     bool dense_sort_library = false;  // KS_DENSE_SORT=library: the dense path's keys sorted by the library
     bool timing = false;          // KS_TIMING: host-side stage timings on stderr
     bool search_legacy = false;   // KS_SEARCH_LEGACY: the library-sorted query path for every batch
+    int ls_variant = 0;           // KS_LS_VARIANT = rep | bn | bs: bucket-sort variant of the stable path (1 / 2 / 3)
     void read() {
         sketch_general = getenv("KS_SKETCH_GENERAL") != nullptr;
         const char* d = getenv("KS_DENSE");
@@ -432,6 +433,8 @@ struct Hooks {
         dense_sort_library = ds && ds[0] == 'l';
         timing = getenv("KS_TIMING") != nullptr;
         search_legacy = getenv("KS_SEARCH_LEGACY") != nullptr;
+        const char* lv = getenv("KS_LS_VARIANT");
+        ls_variant = !lv ? 0 : lv[0] == 'r' ? 1 : (lv[0] == 'b' && lv[1] == 's') ? 3 : lv[0] == 'b' ? 2 : 0;
     }
 };
 
@@ -479,6 +482,11 @@ struct ks_index {
     uint64_t* d_counts = nullptr;
     Buf b_keys, b_key_grp, b_grp_start, b_t_size, b_t_abund, b_dir, b_counts, b_alt_hash, b_alt_loc, b_temp;
     int dir_bits = 0, dir_shift = 0;
+    int dir_sub = DIR_SUB_COMPACT;  // layout of keys / key_grp / grp_start (index_build.cuh): compact, or segmented
+    uint32_t seg_nb = 0;
+    uint32_t* seg_start = nullptr;
+    uint64_t* seg_counts = nullptr;
+    Buf b_seg_start, b_seg_counts;
     uint64_t U = 0, G = 0, n_ids = 0;
     // query path: per-handle scratch (grow-only) and a pinned word block for the counts the host reads back
     Buf b_q_ecount, b_q_pcount, b_q_hcount, b_q_sig, b_q_poff, b_q_hoff, b_q_ent_hash, b_q_ent_abund, b_q_win_key,
@@ -535,6 +543,7 @@ void drop_csr(ks_index* x) {  // the buffers stay with the handle (grow-only), o
     x->keys = nullptr; x->key_grp = x->grp_start = x->t_size = x->t_abund = x->dir = nullptr; x->d_counts = nullptr;
     x->finalized = false;
     x->hash_col_valid = true;
+    x->dir_sub = DIR_SUB_COMPACT; x->seg_nb = 0; x->seg_start = nullptr; x->seg_counts = nullptr;
     x->U = x->G = x->n_ids = 0;
 }
 
@@ -911,7 +920,8 @@ bool dense_begin(ks_index* x) {
     x->n_tuples = n;
     // the key sort: hand-written (two scatter levels + a shared-memory sort per bucket) when the input fits its scheme,
     // the library's otherwise (KS_DENSE_SORT=library is a test hook)
-    x->dense_plan = x->hooks.dense_sort_library ? DenseSortPlan() : dense_sort_plan(n, (int)k + 1);
+    x->dense_plan = x->hooks.dense_sort_library ? DenseSortPlan()
+                                                : dense_sort_plan(n, (int)k + 1, (int)k + 1 + x->dense_pid_bits + x->dense_pos_bits);
     if (x->dense_plan.custom) {
         char* work = x->b_dense_work.ensure<char>(ar, x->dense_plan.bytes);
         KS_CUDA(cudaMemsetAsync(work + x->dense_plan.off_small, 0, x->dense_plan.small_bytes, x->stream));
@@ -997,6 +1007,7 @@ bool dense_finalize(ks_index* x) {
     if (hw[2] != n) fail(KS_ERR_CUDA, "internal error: dense path produced an unexpected number of tuples");
     if ((uint32_t)hw[4]) return false;  // heavy repeats of one k-mer overflowed a sort bucket: the general path handles those
     x->U = hw[0]; x->G = hw[1];
+    x->dir_sub = DIR_SUB_COMPACT; x->seg_nb = 0; x->seg_start = nullptr; x->seg_counts = nullptr;
     x->hash_col_valid = false;  // d_hash holds rank keys: the sorted hash column is rebuilt from the CSR on demand
     x->build_path = plan.custom ? 1u : 2u;
     x->pending_dense = false;
@@ -1017,15 +1028,20 @@ void finalize(ks_index* x) {
     const uint32_t P = (uint32_t)x->n_prot;
     int bits = 8;  // ~4 tuples (<= 4 keys) per directory bucket: the table stays small next to the keys
     while (bits < 24 && (4ull << bits) < n) bits++;
+    // the bucket sort writes the CSR in the segmented layout: a directory bucket must not span two sort buckets, and the
+    // key / group arrays carry one sentinel slot per sort bucket
+    const int top_bits = x->scattered ? x->pair_plan.total : build_top_bits(n, x->end_bit(), x->max_hash);
+    if (top_bits > bits) bits = top_bits;
+    const uint64_t slack = std::max<uint64_t>(build_slack(n), top_bits > 0 ? (1ull << top_bits) + 2 : 2);
     x->dir_bits = bits;
     x->dir_shift = 64 - x->lz - bits;
     Arena* ar = x->arena;
     x->t_abund = x->b_t_abund.ensure<uint32_t>(ar, P);
     x->t_size = x->b_t_size.ensure<uint32_t>(ar, P);
-    x->keys = x->b_keys.ensure<uint64_t>(ar, n);
-    x->key_grp = x->b_key_grp.ensure<uint32_t>(ar, n + 1);
-    x->grp_start = x->b_grp_start.ensure<uint32_t>(ar, n + 1);
-    x->dir = x->b_dir.ensure<uint32_t>(ar, (1ull << bits) + 1);
+    x->keys = x->b_keys.ensure<uint64_t>(ar, n + slack);
+    x->key_grp = x->b_key_grp.ensure<uint32_t>(ar, n + slack);
+    x->grp_start = x->b_grp_start.ensure<uint32_t>(ar, n + slack);
+    x->dir = x->b_dir.ensure<uint32_t>(ar, (1ull << bits) + slack);
     x->d_counts = x->b_counts.ensure<uint64_t>(ar, 2);
     // the second tuple pair is the sort's ping-pong partner; a scattered batch has its regions instead
     uint64_t* hb = x->scattered ? nullptr : x->b_alt_hash.ensure<uint64_t>(ar, n);
@@ -1034,6 +1050,12 @@ void finalize(ks_index* x) {
     a.hash_a = x->d_hash; a.loc_a = x->d_loc; a.hash_b = hb; a.loc_b = lb;
     a.n = n; a.n_prot = P; a.end_bit = x->end_bit(); a.max_hash = x->max_hash;
     a.repeat_heavy = repeat_heavy(x, n) ? 1 : 0;  // measured: the bin kernel only wins when repeats are rare
+    a.ls_variant = x->hooks.ls_variant;
+    int out_dir_sub = DIR_SUB_COMPACT;
+    uint32_t out_seg_nb = 0;
+    const uint32_t* out_seg_start = nullptr;
+    const uint64_t* out_seg_counts = nullptr;
+    a.out_dir_sub = &out_dir_sub; a.out_seg_nb = &out_seg_nb; a.out_seg_start = &out_seg_start; a.out_seg_counts = &out_seg_counts;
     const uint32_t* d_overflow = nullptr;  // device flag of the unstable partition (a region overflowed)
     if (x->scattered) {  // the tuples sit in the regions of the unstable partition; the postings go to d_loc
         x->n_tuples = 0;
@@ -1056,6 +1078,15 @@ void finalize(ks_index* x) {
     KS_CUDA(cudaEventRecord(x->ev[EV_SO0], x->stream));
     KS_CUDA(build_index(a, x->stream, &in_a, &x->l_sort, &x->l_csr));
     KS_CUDA(cudaEventRecord(x->ev[EV_CS1], x->stream));
+    x->dir_sub = out_dir_sub;
+    x->seg_nb = out_seg_nb;
+    x->seg_start = nullptr; x->seg_counts = nullptr;
+    if (out_dir_sub != DIR_SUB_COMPACT) {  // the bucket tables live in scratch: keep a copy for the export calls
+        x->seg_start = x->b_seg_start.ensure<uint32_t>(ar, (size_t)out_seg_nb + 1);
+        x->seg_counts = x->b_seg_counts.ensure<uint64_t>(ar, out_seg_nb);
+        KS_CUDA(cudaMemcpyAsync(x->seg_start, out_seg_start, ((size_t)out_seg_nb + 1) * 4, cudaMemcpyDeviceToDevice, x->stream));
+        KS_CUDA(cudaMemcpyAsync(x->seg_counts, out_seg_counts, (size_t)out_seg_nb * 8, cudaMemcpyDeviceToDevice, x->stream));
+    }
     const bool was_scattered = x->scattered;
     double t2 = dbg ? now_ms() : 0;
     x->t_sort = x->t_csr = true;
@@ -1095,6 +1126,7 @@ CsrView view_of(const ks_index* x) {
     v.hash = x->d_hash; v.loc = x->d_loc; v.keys = x->keys; v.key_grp = x->key_grp; v.grp_start = x->grp_start;
     v.t_size = x->t_size; v.t_abund = x->t_abund; v.dir = x->dir; v.d_counts = x->d_counts; v.n = x->n_tuples;
     v.n_prot = (uint32_t)x->n_prot; v.dir_bits = x->dir_bits; v.dir_shift = x->dir_shift;
+    v.dir_sub = x->dir_sub; v.seg_nb = x->seg_nb; v.seg_start = x->seg_start; v.seg_counts = x->seg_counts;
     return v;
 }
 
@@ -1303,6 +1335,30 @@ ks_status ks_index_stats(ks_index* x, ks_stats* out) {
     });
 }
 
+// signature_count() (src/rust/index.rs:514-516): signatures are keyed by their id string -- the hex of the wrapping sum of
+// the sketch's mins (signature.rs:277-279) -- and equal ids overwrite (DashMap insert, index.rs:817-820), so the count is
+// the number of distinct sums over the proteins.  Sums on the device from the CSR, distinct count on the host.
+ks_status ks_index_signature_count(ks_index* x, uint64_t* out) {
+    return guarded([&] {
+        if (!x || !out) fail(KS_ERR_VALIDATION, "Validation error: null argument");
+        if (!x->finalized) fail(KS_ERR_NOT_FINALIZED, "index is not finalized");
+        x->use();
+        const uint64_t P = x->n_prot;
+        std::vector<uint64_t> sums(P ? P : 1, 0);
+        if (P) {
+            Arena tmp(x->stream, &x->live_bytes);
+            unsigned long long* d = (unsigned long long*)tmp.alloc<uint64_t>(P);
+            KS_CUDA(cudaMemsetAsync(d, 0, P * 8, x->stream));
+            KS_CUDA(launch_id_sums(view_of(x), x->U, d, x->stream));
+            KS_CUDA(cudaMemcpyAsync(sums.data(), d, P * 8, cudaMemcpyDeviceToHost, x->stream));
+            KS_CUDA(cudaStreamSynchronize(x->stream));
+        }
+        std::sort(sums.begin(), sums.begin() + P);
+        x->n_ids = (uint64_t)(std::unique(sums.begin(), sums.begin() + P) - sums.begin());
+        *out = x->n_ids;
+    });
+}
+
 // ---- sketch export ------------------------------------------------------------------------------
 ks_status ks_sketch_batch(ks_index* x, const ks_proteome* p, ks_sketch** out) {
     return guarded([&] {
@@ -1360,18 +1416,36 @@ ks_status ks_index_csr(ks_index* x, ks_csr** out) {
         ks_csr* c = (ks_csr*)calloc(1, sizeof(ks_csr));
         if (!c) throw std::bad_alloc();
         c->n_keys = x->U; c->n_postings = x->n_tuples;
-        c->keys = to_host(x->keys, x->U, x->stream);
-        uint32_t* kg = to_host(x->key_grp, x->U + 1, x->stream);
-        uint32_t* gs = to_host(x->grp_start, x->G + 1, x->stream);
+        const bool seg = x->dir_sub != DIR_SUB_COMPACT;
+        const uint64_t span = seg ? x->n_tuples + x->seg_nb + 1 : x->U + 1;  // key / group positions in use
+        uint64_t* keys = to_host(x->keys, seg ? span : x->U, x->stream);
+        uint32_t* kg = to_host(x->key_grp, span, x->stream);
+        uint32_t* gs = to_host(x->grp_start, seg ? span : x->G + 1, x->stream);
         uint64_t* loc = to_host(x->d_loc, x->n_tuples, x->stream);
+        uint32_t* st = seg ? to_host(x->seg_start, (uint64_t)x->seg_nb + 1, x->stream) : nullptr;
+        uint64_t* sc = seg ? to_host(x->seg_counts, x->seg_nb, x->stream) : nullptr;
         KS_CUDA(cudaStreamSynchronize(x->stream));
         c->row_ptr = (uint64_t*)malloc((x->U + 1) * 8);
         c->pid = (uint32_t*)malloc((x->n_tuples ? x->n_tuples : 1) * 4);
         c->pos = (uint32_t*)malloc((x->n_tuples ? x->n_tuples : 1) * 4);
         if (!c->row_ptr || !c->pid || !c->pos) throw std::bad_alloc();
-        for (uint64_t u = 0; u <= x->U; u++) c->row_ptr[u] = gs[kg[u]];
+        if (!seg) {
+            c->keys = keys;
+            for (uint64_t u = 0; u <= x->U; u++) c->row_ptr[u] = gs[kg[u]];
+        } else {  // segmented layout -> the compact table: bucket by bucket, keys at seg_start[b] + b + i
+            c->keys = (uint64_t*)malloc((x->U ? x->U : 1) * 8);
+            if (!c->keys) throw std::bad_alloc();
+            uint64_t u = 0;
+            for (uint32_t b = 0; b < x->seg_nb; b++) {
+                const uint64_t kb = (uint64_t)st[b] + b, tk = (uint32_t)sc[b];
+                for (uint64_t i = 0; i < tk && u < x->U; i++, u++) { c->keys[u] = keys[kb + i]; c->row_ptr[u] = gs[kg[kb + i]]; }
+            }
+            if (u != x->U) fail(KS_ERR_CUDA, "internal error: segmented CSR does not add up");
+            c->row_ptr[x->U] = x->n_tuples;
+            free(keys);
+        }
         for (uint64_t i = 0; i < x->n_tuples; i++) { c->pid[i] = (uint32_t)(loc[i] >> 32); c->pos[i] = (uint32_t)loc[i]; }
-        free(kg); free(gs); free(loc);
+        free(kg); free(gs); free(loc); free(st); free(sc);
         *out = c;
     });
 }

@@ -265,22 +265,35 @@ dense_partition_kernel(const uint64_t* __restrict__ region1, const uint32_t* __r
     scatter_keys(key, valid, sc, b1 << sc.bits, s_sc, s_dst);
 }
 
-constexpr int DB_THREADS = 512;
+// CTA shape of the bucket kernel: 512 threads x 4 CTAs per SM (8 keys per thread) or 1024 x 2 (4 keys per thread);
+// either way 2048 threads and 32 registers per thread -- with 4 keys per thread the key registers no longer spill
+#ifndef KS_DB_THREADS
+#define KS_DB_THREADS 512
+#endif
+constexpr int DB_THREADS = KS_DB_THREADS;
+constexpr int DB_CTAS = 2048 / DB_THREADS;
 constexpr int DB_WARPS = DB_THREADS / 32;
 constexpr int DB_CAP = 4096;
+constexpr int DB_ROWS = DB_CAP / DB_THREADS;  // keys per thread
 constexpr int DB_BIN_BITS = 13;
 constexpr int DB_BINS = 1 << DB_BIN_BITS;  // 16-bit counters, two per word: a bucket holds at most 4096 keys
+constexpr int DB_WORDS_PER_THREAD = DB_BINS / 2 / DB_THREADS;  // counter words a thread owns in the scan (8 or 4)
+#ifdef KS_DB_NOSLICE
+constexpr int DB_HASH_SLICE = 0;
+#else
 constexpr int DB_HASH_SLICE = 512;         // pattern hashes of a bucket's rank range kept in shared memory when they fit
+#endif
 constexpr size_t DB_SMEM = (size_t)DB_CAP * 8 + (size_t)DB_BINS * 2 + (size_t)DB_HASH_SLICE * 8;
-constexpr int DB_BINS_PER_THREAD = DB_BINS / DB_THREADS;  // 16
-constexpr uint32_t DB_BIN_SORT_MAX = 24;   // a bin of more keys sends the bucket to the odd-even rounds
+constexpr uint32_t DB_BIN_SORT_MAX = 32;   // a bin of more keys sends the bucket to the odd-even rounds
+constexpr int DB_SLOT_BITS = 12;           // low bits of an item that carry its slot (items are keys shifted up by >= 12)
+static_assert(DB_WORDS_PER_THREAD % 4 == 0 && DB_ROWS * DB_WARPS == 128, "scan layout");
 
 struct DenseBucketArgs {
     const uint64_t* region2;   // final buckets, DB_CAP keys each
     const uint32_t* cursor2;   // keys per bucket
     const uint32_t* bstart;    // tuple offset of every bucket
     uint32_t nb;
-    int rem_bits;              // key bits below the bucket bits
+    int rem_bits;              // key bits below the bucket bits (<= 64 - DB_SLOT_BITS)
     int loc_bits, pos_bits;
     const uint64_t* sorted_hash;
     uint64_t* status;          // look-back words, zeroed
@@ -299,14 +312,12 @@ struct DenseBucketArgs {
     const uint32_t* skip_flag; // device: != 0 when the build is void (unhandled exception / table unusable): nothing to do
 };
 
-// 4 CTAs per SM (no loc gather here, so the smaller L1 does not hurt): 2.84 ms against 3.18 ms with 3 on C2
-#ifndef KS_DB_CTAS
-#define KS_DB_CTAS 4
-#endif
-// One CTA per final bucket (<= 4096 keys, all distinct, final order = numeric order):
+// One CTA per final bucket (<= 4096 keys, all distinct, final order = numeric order), persistent CTAs that take buckets
+// by ticket:
 //   1. counting pass over the item's top 13 bits (shared-memory atomics on packed 16-bit counters), scan, scatter: the
-//      bucket is then ordered at bin granularity -- a bin is (rank, 1/32 of the proteins) on C2 and holds 0-3 keys;
-//   2. the thread that owns 16 consecutive bins puts each of them in order by insertion (no barrier, no rounds); a bin
+//      bucket is then ordered at bin granularity -- a bin is (rank, 1/32 of the proteins) on C2 and holds 0-3 keys.  The
+//      slot a key drew in its bin rides in the item's low bits (below every key bit), not in a register;
+//   2. every key finds its final slot by counting the smaller keys of its own bin (two barriers, no rounds); a bin
 //      of more than DB_BIN_SORT_MAX keys (a k-mer repeated in one stretch of proteins) or exception keys (which can sit
 //      in a later bin than a larger key) send the whole bucket through odd-even transposition rounds instead;
 //   3. heads from the rank / protein fields; the aggregate (keys, groups) is published for the look-back BEFORE the
@@ -316,7 +327,7 @@ struct DenseBucketArgs {
 // EXC: the batch holds exception keys.  Both instantiations are launched back to back; the device flag decides which one
 // does the work (the other's CTAs exit at once), so that the host never waits for the rank kernel's flags.
 template <bool EXC>
-__global__ void __launch_bounds__(DB_THREADS, KS_DB_CTAS)
+__global__ void __launch_bounds__(DB_THREADS, DB_CTAS)
 dense_bucket_kernel(DenseBucketArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t* B = reinterpret_cast<uint64_t*>(smem_raw);      // [DB_CAP] items: the key's bits below the bucket bits, left-aligned
@@ -324,7 +335,7 @@ dense_bucket_kernel(DenseBucketArgs a) {
     uint64_t* s_hash = reinterpret_cast<uint64_t*>(cnt + DB_BINS / 2);  // [DB_HASH_SLICE]
     const uint16_t* off16 = reinterpret_cast<const uint16_t*>(cnt);
     __shared__ uint32_t s_wsum[DB_WARPS];
-    __shared__ uint32_t s_cw[8 * DB_WARPS];
+    __shared__ uint32_t s_cw[DB_ROWS * DB_WARPS];
     __shared__ uint64_t s_base;
     __shared__ uint32_t s_bucket;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -334,26 +345,45 @@ dense_bucket_kernel(DenseBucketArgs a) {
         return;
     }
     if ((*a.exc_flag != 0) != EXC) return;  // (uniform over the grid) the other instantiation does the work
+    const int up = 64 - a.rem_bits;  // item = key << up: the bucket bits fall off the top
+    const int rrb = a.rem_bits - a.loc_bits;  // rank' bits below the bucket bits (the lowest is the parity)
+    // bin = the item's top 13 bits with the parity bit of rank' squeezed out when it lies among them (it is 1 for every
+    // pattern key and would leave half of the bins empty).  An exception key (parity 0) can then land in a later bin than a
+    // larger key: the odd-even rounds of the EXC instantiation run until the whole bucket is in order.
+    const int pb = up + a.loc_bits;  // bit of the item that holds the parity of rank'
+    const bool squeeze = pb >= 64 - DB_BIN_BITS && pb < 63;
+    const int n_low = squeeze ? DB_BIN_BITS - (63 - pb) : 0;  // bin bits taken from below the parity bit
+    auto bin_of = [&](uint64_t it) -> uint32_t {
+        if (!squeeze) return (uint32_t)(it >> (64 - DB_BIN_BITS));
+        return (uint32_t)(((it >> (pb + 1)) << n_low) | ((it >> (pb - n_low)) & ((1ull << n_low) - 1ull)));
+    };
+    const int rank_sh = up + a.loc_bits, grp_sh = up + a.pos_bits;  // item >> rank_sh: rank bits below the bucket bits
+    auto shr = [](uint64_t v, int sh) -> uint64_t { return sh >= 64 ? 0ull : v >> sh; };  // no rank bits may be left
+    const uint64_t pos_mask = (1ull << a.pos_bits) - 1ull, pid_mask = (1ull << (a.loc_bits - a.pos_bits)) - 1ull;
+    const bool hash_slice = DB_HASH_SLICE > 0 && rrb >= 1 && rrb <= 10;  // at most 512 pattern ranks under a bucket
+    constexpr uint64_t SLOT_MASK = (1ull << DB_SLOT_BITS) - 1ull;
     // persistent CTAs: buckets are taken by ticket, so a bucket's predecessors have always started (look-back)
-    for (;;) {
+    // EXC (the rare instantiation): persistent CTAs, so that its launch costs next to nothing when it has no work;
+    // the common instantiation runs one CTA per bucket (measured: 2.96 ms against 3.20 ms persistent on C2)
+    for (int pass = 0; EXC || pass < 1; pass++) {
     __syncthreads();  // the previous bucket's shared memory is no longer read
     if (tid == 0) s_bucket = atomicAdd(a.ticket, 1u);
-    reinterpret_cast<uint4*>(cnt)[tid] = make_uint4(0, 0, 0, 0);
-    reinterpret_cast<uint4*>(cnt)[tid + DB_THREADS] = make_uint4(0, 0, 0, 0);
+    for (uint32_t i = tid; i < DB_BINS / 8; i += DB_THREADS) reinterpret_cast<uint4*>(cnt)[i] = make_uint4(0, 0, 0, 0);
     __syncthreads();
     const uint32_t b = s_bucket;
     if (b >= a.nb) break;
     const uint64_t* src = a.region2 + (uint64_t)b * DB_CAP;
-    const int up = 64 - a.rem_bits;  // item = key << up: the bucket bits fall off the top
-    const int rrb = a.rem_bits - a.loc_bits;  // rank' bits below the bucket bits (the lowest is the parity)
-    uint64_t item[8];
-    // the first rows are read before the bucket's size is known (a bucket region is DB_CAP keys of allocated memory; what
-    // lies past the size is not used): the size and the keys come back in one round trip instead of two
-    constexpr int SPEC_ROWS = 4;
+    uint64_t item[DB_ROWS];
+    // the first half of the rows is read before the bucket's size is known (a bucket region is DB_CAP keys of allocated
+    // memory; what lies past the size is not used): the size and the keys come back in one round trip instead of two
+#ifdef KS_DB_NOSPEC
+    constexpr int SPEC_ROWS = 0;
+#else
+    constexpr int SPEC_ROWS = DB_ROWS / 2;
+#endif
 #pragma unroll
     for (int r = 0; r < SPEC_ROWS; r++) item[r] = src[r * DB_THREADS + tid];
     const uint32_t m = min(a.cursor2[b], (uint32_t)DB_CAP);
-    const bool hash_slice = rrb >= 1 && rrb <= 10;  // at most 512 pattern ranks under this bucket
     if (hash_slice && tid < (1u << (rrb - 1))) s_hash[tid] = a.sorted_hash[((uint64_t)b << (rrb - 1)) + tid];
     if (m == 0) {  // pass the running totals on; the last bucket writes them out
         if (warp == 0) {
@@ -366,41 +396,33 @@ dense_bucket_kernel(DenseBucketArgs a) {
         continue;
     }
 #pragma unroll
-    for (int r = SPEC_ROWS; r < 8; r++) {
+    for (int r = SPEC_ROWS; r < DB_ROWS; r++) {
         if (r * DB_THREADS >= m) break;
         const uint32_t j = r * DB_THREADS + tid;
         if (j < m) item[r] = src[j];
     }
-    // bin = the item's top 13 bits with the parity bit of rank' squeezed out when it lies among them (it is 1 for every
-    // pattern key and would leave half of the bins empty).  An exception key (parity 0) can then land in a later bin than a
-    // larger key: the odd-even rounds of the EXC instantiation run until the whole bucket is in order.
-    const int pb = up + a.loc_bits;  // bit of the item that holds the parity of rank'
-    const bool squeeze = pb >= 64 - DB_BIN_BITS && pb < 63;
-    const int n_low = squeeze ? DB_BIN_BITS - (63 - pb) : 0;  // bin bits taken from below the parity bit
-    auto bin_of = [&](uint64_t it) -> uint32_t {
-        if (!squeeze) return (uint32_t)(it >> (64 - DB_BIN_BITS));
-        return (uint32_t)(((it >> (pb + 1)) << n_low) | ((it >> (pb - n_low)) & ((1ull << n_low) - 1ull)));
-    };
-    uint32_t slot[4] = {0, 0, 0, 0};
 #pragma unroll
-    for (int r = 0; r < 8; r++) {
+    for (int r = 0; r < DB_ROWS; r++) {
         const uint32_t j = r * DB_THREADS + tid;
         if (r * DB_THREADS >= m) break;
         if (j < m) {
             item[r] <<= up;
             const uint32_t bin = bin_of(item[r]), sh16 = 16 * (bin & 1u);
-            const uint32_t old = (atomicAdd(&cnt[bin >> 1], 1u << sh16) >> sh16) & 0xffffu;  // no carry: counts <= 4096
-            slot[r >> 1] |= old << (16 * (r & 1));
+            item[r] |= (atomicAdd(&cnt[bin >> 1], 1u << sh16) >> sh16) & 0xffffu;  // no carry: counts <= 4096 = 2^DB_SLOT_BITS
         }
     }
     __syncthreads();
     bool big_bin = false;
-    {   // exclusive scan of the 8192 counters; thread t owns bins 16t .. 16t+15 (8 words)
-        uint4 c0 = reinterpret_cast<uint4*>(cnt)[2 * tid], c1 = reinterpret_cast<uint4*>(cnt)[2 * tid + 1];
-        uint32_t w[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+    {   // exclusive scan of the 8192 counters; thread t owns DB_WORDS_PER_THREAD consecutive words
+        uint32_t w[DB_WORDS_PER_THREAD];
+#pragma unroll
+        for (int q = 0; q < DB_WORDS_PER_THREAD / 4; q++) {
+            const uint4 c = reinterpret_cast<uint4*>(cnt)[tid * (DB_WORDS_PER_THREAD / 4) + q];
+            w[4 * q] = c.x; w[4 * q + 1] = c.y; w[4 * q + 2] = c.z; w[4 * q + 3] = c.w;
+        }
         uint32_t total = 0;
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
+        for (int i = 0; i < DB_WORDS_PER_THREAD; i++) {
             const uint32_t lo = w[i] & 0xffffu, hi = w[i] >> 16;
             total += lo + hi;
             big_bin |= lo > DB_BIN_SORT_MAX || hi > DB_BIN_SORT_MAX;
@@ -415,42 +437,51 @@ dense_bucket_kernel(DenseBucketArgs a) {
         __syncthreads();
         uint32_t off = 0;
 #pragma unroll
-        for (int w = 0; w < DB_WARPS; w++) off += w < (int)warp ? s_wsum[w] : 0u;
+        for (int w2 = 0; w2 < DB_WARPS; w2++) off += w2 < (int)warp ? s_wsum[w2] : 0u;
         uint32_t run = off + incl - total;  // < 4096: the exclusive offsets fit 16 bits as well
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
+        for (int i = 0; i < DB_WORDS_PER_THREAD; i++) {
             const uint32_t lo = w[i] & 0xffffu, hi = w[i] >> 16;
             w[i] = run | ((run + lo) << 16);
             run += lo + hi;
         }
-        reinterpret_cast<uint4*>(cnt)[2 * tid] = make_uint4(w[0], w[1], w[2], w[3]);
-        reinterpret_cast<uint4*>(cnt)[2 * tid + 1] = make_uint4(w[4], w[5], w[6], w[7]);
+#pragma unroll
+        for (int q = 0; q < DB_WORDS_PER_THREAD / 4; q++)
+            reinterpret_cast<uint4*>(cnt)[tid * (DB_WORDS_PER_THREAD / 4) + q] = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
     }
     __syncthreads();
 #pragma unroll
-    for (int r = 0; r < 8; r++) {
+    for (int r = 0; r < DB_ROWS; r++) {
         const uint32_t j = r * DB_THREADS + tid;
         if (r * DB_THREADS >= m) break;
-        if (j < m) B[off16[bin_of(item[r])] + ((slot[r >> 1] >> (16 * (r & 1))) & 0xffffu)] = item[r];
+        if (j < m) B[off16[bin_of(item[r])] + (uint32_t)(item[r] & SLOT_MASK)] = item[r];
     }
+#ifdef KS_DB_RANKSORT
     const int use_rounds = __syncthreads_or((EXC || big_bin) ? 1 : 0);
+#else
+    const int use_rounds = __syncthreads_or(1);  // measured on C2: the rounds 2.79 ms, in-bin counting 2.99 ms
+#endif
     if (!use_rounds) {
-        // every bin in order, by the thread that owns it: bins hold a handful of keys at most
-        uint4 c0 = reinterpret_cast<uint4*>(cnt)[2 * tid], c1 = reinterpret_cast<uint4*>(cnt)[2 * tid + 1];
-        const uint32_t w[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-        const uint32_t end_all = tid == DB_THREADS - 1 ? m : (cnt[8 * (tid + 1)] & 0xffffu);
-        if (end_all - (w[0] & 0xffffu) >= 2) {  // (most threads: a few keys over 16 bins, most bins empty or single)
+        // every key finds its place inside its bin by counting the bin's smaller keys (keys are distinct above the slot
+        // bits; a bin holds a handful): all lanes busy, a fixed number of barriers, no rounds
 #pragma unroll
-            for (int i = 0; i < DB_BINS_PER_THREAD; i++) {
-                const uint32_t lo = (w[i >> 1] >> (16 * (i & 1))) & 0xffffu;
-                const uint32_t hi = i == DB_BINS_PER_THREAD - 1 ? end_all : (w[(i + 1) >> 1] >> (16 * ((i + 1) & 1))) & 0xffffu;
-                for (uint32_t t = lo + 1; t < hi; t++) {
-                    const uint64_t x = B[t];
-                    uint32_t u = t;
-                    while (u > lo && B[u - 1] > x) { B[u] = B[u - 1]; u--; }
-                    B[u] = x;
-                }
+        for (int r = 0; r < DB_ROWS; r++) {
+            const uint32_t j = r * DB_THREADS + tid;
+            if (r * DB_THREADS >= m) break;
+            if (j < m) {
+                const uint32_t bin = bin_of(item[r]);
+                const uint32_t lo = off16[bin], hi = bin == DB_BINS - 1 ? m : off16[bin + 1];
+                uint32_t at = lo;
+                for (uint32_t t = lo; t < hi; t++) at += B[t] < item[r] ? 1u : 0u;
+                item[r] = (item[r] & ~SLOT_MASK) | at;
             }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < DB_ROWS; r++) {
+            const uint32_t j = r * DB_THREADS + tid;
+            if (r * DB_THREADS >= m) break;
+            if (j < m) B[(uint32_t)(item[r] & SLOT_MASK)] = item[r];
         }
         __syncthreads();
     } else {
@@ -473,9 +504,6 @@ dense_bucket_kernel(DenseBucketArgs a) {
         } while (again);
     }
     // heads: the bucket bits cover at most the rank bits, so a bucket's first key starts a new hash
-    const int rank_sh = up + a.loc_bits, grp_sh = up + a.pos_bits;  // item >> rank_sh: rank bits below the bucket bits
-    auto shr = [](uint64_t v, int sh) -> uint64_t { return sh >= 64 ? 0ull : v >> sh; };  // no rank bits may be left
-    const uint64_t pos_mask = (1ull << a.pos_bits) - 1ull, pid_mask = (1ull << (a.loc_bits - a.pos_bits)) - 1ull;
     const uint32_t s0 = a.bstart[b];
     // Exception keys (even rank': a window with a residue of neither class, hashed from its bytes, ranked between two
     // patterns).  Two different exception hashes can fall between the same two patterns and then share a rank': the
@@ -515,7 +543,7 @@ dense_bucket_kernel(DenseBucketArgs a) {
     }
     uint32_t flags = 0;
 #pragma unroll
-    for (int r = 0; r < 8; r++) {
+    for (int r = 0; r < DB_ROWS; r++) {
         const uint32_t j = r * DB_THREADS + tid;
         if (r * DB_THREADS < m) {  // uniform
             bool hk = false, hg = false;
@@ -550,11 +578,13 @@ dense_bucket_kernel(DenseBucketArgs a) {
         for (int i = 0; i < 4; i++) { s_cw[lane * 4 + i] = run; run += v[i]; }
         const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
         agg = (uint64_t)(tot & 0xffffu) | ((uint64_t)(tot >> 16) << 31);
+#ifndef KS_DB_FUSED_LOOKBACK
         scan_publish(a.status, b, agg);  // successors can go on; our own prefix is collected after the stores below
+#endif
     }
     // the postings go out in final order: this is where part of the wait for the predecessors is hidden
 #pragma unroll
-    for (int r = 0; r < 8; r++) {
+    for (int r = 0; r < DB_ROWS; r++) {
         const uint32_t j = r * DB_THREADS + tid;
         if (r * DB_THREADS >= m) break;
         if (j < m) {
@@ -565,7 +595,11 @@ dense_bucket_kernel(DenseBucketArgs a) {
         }
     }
     if (warp == 0) {
+#ifdef KS_DB_FUSED_LOOKBACK
+        const uint64_t excl = scan_lookback(a.status, b, agg);
+#else
         const uint64_t excl = scan_collect(a.status, b, agg);
+#endif
         if (lane == 0) {
             s_base = excl;
             if (b == a.nb - 1) {
@@ -579,7 +613,7 @@ dense_bucket_kernel(DenseBucketArgs a) {
     const uint32_t base_k = (uint32_t)(s_base & 0x7fffffffu), base_g = (uint32_t)(s_base >> 31);
     const uint64_t rank_top = (uint64_t)b << rrb;  // the rank bits that are the bucket index
 #pragma unroll
-    for (int r = 0; r < 8; r++) {
+    for (int r = 0; r < DB_ROWS; r++) {
         if (r * DB_THREADS < m) {  // uniform
             const uint32_t j = r * DB_THREADS + tid;
             const bool hk = (flags >> (2 * r)) & 1u, hg = (flags >> (2 * r)) & 2u;
@@ -650,11 +684,12 @@ cudaError_t dense_build_tables(uint32_t k, uint32_t* rank_of_code, uint64_t* sor
     return cudaGetLastError();
 }
 
-DenseSortPlan dense_sort_plan(uint64_t n, int rank_bits) {
+DenseSortPlan dense_sort_plan(uint64_t n, int rank_bits, int key_bits) {
     DenseSortPlan p;
     int total = 0;
     while (total <= 2 * DS_MAX_BITS && (n >> total) > 3072) total++;
     if (total > 2 * DS_MAX_BITS || total > rank_bits || n == 0) return p;  // custom == 0
+    if (key_bits - total > 64 - DB_SLOT_BITS) return p;  // the bucket kernel keeps a key's slot below its bits
     p.custom = 1;
     p.total = total;
     p.l1 = total < DS_MAX_BITS ? total : DS_MAX_BITS;
@@ -730,11 +765,10 @@ cudaError_t dense_build_csr(const DenseCsrArgs& a, cudaStream_t stream, uint64_t
         ba.exc_flag = a.exc_flag; ba.skip_flag = a.skip_flag;
         KS_TRY(cudaFuncSetAttribute(dense_bucket_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DB_SMEM));
         KS_TRY(cudaFuncSetAttribute(dense_bucket_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DB_SMEM));
-        // both instantiations, back to back: the rank kernel's device flag picks the one that works (persistent CTAs, so
-        // the idle one costs a few hundred CTAs that exit at once) -- the host does not wait for the flag
-        const unsigned grid = std::min<unsigned>(nb, 148u * KS_DB_CTAS);
-        dense_bucket_kernel<false><<<grid, DB_THREADS, DB_SMEM, stream>>>(ba);
-        dense_bucket_kernel<true><<<grid, DB_THREADS, DB_SMEM, stream>>>(ba);
+        // both instantiations, back to back: the rank kernel's device flag picks the one that works -- the host does not
+        // wait for the flag (the exception instantiation runs persistent CTAs: idle, it is a few hundred CTAs that exit)
+        dense_bucket_kernel<false><<<nb, DB_THREADS, DB_SMEM, stream>>>(ba);
+        dense_bucket_kernel<true><<<std::min<unsigned>(nb, 148u * DB_CTAS), DB_THREADS, DB_SMEM, stream>>>(ba);
         if (sort_launches) *sort_launches += 3;
         return cudaGetLastError();
     }

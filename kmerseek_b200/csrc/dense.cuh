@@ -16,7 +16,8 @@ cudaError_t dense_build_tables(uint32_t k, uint32_t* rank_of_code, uint64_t* sor
 
 // Plan of the hand-written key sort (dense_scatter.cuh, dense_bucket_kernel): the top `total` = l1 + l2 key bits pick
 // one of 2^total final buckets of at most 4096 keys.  custom == 0: the input does not fit the scheme (more than
-// 2^16 x 3072 keys, or fewer rank bits than bucket bits) and the library sorts the keys.
+// 2^16 x 3072 keys, fewer rank bits than bucket bits, or more than 52 key bits below the bucket bits) and the library
+// sorts the keys.
 struct DenseSortPlan {
     int custom = 0;
     int l1 = 0, l2 = 0, total = 0;  // bits of the first level (fused into the rank kernel), the second, both
@@ -25,7 +26,7 @@ struct DenseSortPlan {
     size_t off_region1 = 0, off_region2 = 0, off_small = 0, small_bytes = 0, bytes = 0;
     size_t off_cursor1 = 0, off_cursor2 = 0, off_chunks = 0, off_bstart = 0, off_status = 0, off_ticket = 0, off_overflow = 0;
 };
-DenseSortPlan dense_sort_plan(uint64_t n, int rank_bits);
+DenseSortPlan dense_sort_plan(uint64_t n, int rank_bits, int key_bits);
 
 struct DenseCsrArgs {
     DenseSortPlan plan;

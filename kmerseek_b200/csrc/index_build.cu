@@ -89,53 +89,36 @@ __global__ void oversize_count_kernel(const uint32_t* __restrict__ start, uint32
 
 // ---------------------------------------------------------------------------------------------
 // Shared tail of both bucket-sort kernels: stream the sorted bucket back to HBM, count its unique hashes and
-// (hash, protein) groups, and -- when no bucket is oversize -- write the bucket's part of the CSR arrays too.
-// The CSR offsets of a bucket are the totals of all buckets before it: they come from a decoupled look-back
-// over one status word per bucket.  Buckets are long-lived CTAs (tens of microseconds, ~20 finish per
-// microsecond), well inside what the chain sustains, and the CSR entries are produced from the items still in
-// shared memory instead of re-reading 16 bytes per tuple in a separate kernel.
+// (hash, protein) groups, and -- when no bucket is oversize -- write the bucket's part of the CSR arrays too, in the
+// SEGMENTED layout (index_build.cuh): the bucket's keys and groups live at positions start[b] + b + i, which every
+// bucket knows without looking at any other bucket.  There is no chain, no look-back and no ticket between buckets
+// (round 1 chained the buckets' key / group totals with a decoupled look-back: 19 % of the kernel's stall samples sat
+// behind it, and every slow bucket held up all of its successors).  The totals are two atomics per bucket.
 // ---------------------------------------------------------------------------------------------
 struct CsrOut {
-    uint64_t* status;          // [nb] look-back words, zeroed per build
-    uint32_t* ticket;          // bucket tickets: a bucket's predecessors have always started (no reliance on the
-                               // order in which the hardware dispatches blockIdx)
-    const uint32_t* oversize;  // [0] = number of oversize buckets; the CSR is fused only when it is 0
+    const uint32_t* oversize;  // [0] = number of oversize buckets; the CSR is written here only when it is 0
     uint64_t* keys;
     uint32_t* key_grp;
     uint32_t* grp_start;
-    uint64_t* d_counts;
-    uint64_t n;
+    unsigned long long* d_counts;  // [0] unique keys, [1] groups: accumulated (zeroed per build)
     uint32_t nb;
-    // bucket directory over the unique keys, filled by the bucket that owns the range (dir_sub = dir_bits - tb >= 0:
-    // a sort bucket spans 2^dir_sub directory entries); dir_sub < 0: left to dir_kernel
-    uint32_t* dir;
-    int dir_bits, dir_sub;
+    uint32_t* dir;  // every sort bucket owns 2^dir_sub + 1 consecutive entries (the last one is its end sentinel)
+    int dir_sub;
 };
 
-// dir[x] = index of the first key whose directory bucket is >= x.  Inside a sort bucket (2^dir_sub consecutive entries,
-// `dir_b`) the key with index u whose item has the local entry x1, and whose predecessor has x0, owns the entries (x0, x1].
+// dir[x] = position of the first key whose directory bucket is >= x.  Inside a sort bucket (`dir_b`) the key at position u
+// whose item has the local entry x1, and whose predecessor has x0, owns the entries (x0, x1].
 __device__ __forceinline__ void dir_fill(uint32_t* dir_b, int32_t x0, int32_t x1, uint32_t u) {
     for (int32_t x = x0 + 1; x <= x1; x++) dir_b[x] = u;
 }
 
-__device__ __forceinline__ void csr_totals(const CsrOut& f, uint64_t incl) {
-    const uint64_t U = incl & 0x7fffffffu, G = incl >> 31;
-    f.d_counts[0] = U;
-    f.d_counts[1] = G;
-    f.key_grp[U] = (uint32_t)G;
-    f.grp_start[G] = (uint32_t)f.n;
-}
-
-// An empty bucket still has to pass the running totals on (and the last bucket writes them out).
-__device__ __forceinline__ void bucket_empty(uint32_t b, const CsrOut& f) {
-    if ((threadIdx.x >> 5) != 0 || f.oversize[0] != 0) return;
-    const uint64_t excl = scan_lookback(f.status, b, 0);
-    if (b == f.nb - 1 && (threadIdx.x & 31) == 0) csr_totals(f, excl);
-    if (f.dir_sub >= 0) {
-        const uint32_t u = (uint32_t)(excl & 0x7fffffffu);
-        const int64_t x0 = (int64_t)b << f.dir_sub, x1 = ((int64_t)(b + 1) << f.dir_sub) + (b == f.nb - 1 ? 1 : 0);
-        for (int64_t x = x0 + (threadIdx.x & 31); x < x1; x += 32) f.dir[x] = u;
-    }
+// An empty bucket: an empty key / group segment (the two sentinels) and directory entries that all point at it.
+__device__ __forceinline__ void bucket_empty(uint32_t b, uint32_t s, const CsrOut& f) {
+    if (f.oversize[0] != 0) return;
+    const uint32_t kb = s + b;
+    if (threadIdx.x == 0) { f.key_grp[kb] = kb; f.grp_start[kb] = s; }
+    uint32_t* dir_b = f.dir + (uint64_t)b * ((1u << f.dir_sub) + 1u);
+    for (uint32_t x = threadIdx.x; x <= (1u << f.dir_sub); x += blockDim.x) dir_b[x] = kb;
 }
 
 // The loc gathers of a thread are issued back to back; the protein ids are parked in shared memory (`spid`, 4 bytes per
@@ -148,8 +131,7 @@ __device__ __forceinline__ void bucket_finish(const uint64_t* items, uint32_t* s
                                                   uint64_t* __restrict__ counts, uint32_t* __restrict__ t_size,
                                                   const CsrOut& f) {
     __shared__ uint32_t s_cw[8 * LS_WARPS];  // per (row, warp): key heads | group heads << 16, then their prefix
-    __shared__ uint64_t s_base;
-    __shared__ uint32_t s_tk;  // unique keys of this bucket
+    __shared__ uint32_t s_tk, s_tg;          // unique keys / groups of this bucket
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t lt = (1u << lane) - 1u;
     const uint64_t top = tb ? ((uint64_t)b << (64 - tb)) : 0ull;
@@ -188,7 +170,6 @@ __device__ __forceinline__ void bucket_finish(const uint64_t* items, uint32_t* s
         }
     }
     __syncthreads();
-    uint64_t agg = 0;
     if (warp == 0) {
         // exclusive prefix over the (row, warp) counts, 4 entries per lane; both halves stay below 2^16
         uint32_t v[4], local = 0;
@@ -205,11 +186,13 @@ __device__ __forceinline__ void bucket_finish(const uint64_t* items, uint32_t* s
         for (int i = 0; i < 4; i++) { s_cw[lane * 4 + i] = run; run += v[i]; }
         const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
         const uint32_t tk = tot & 0xffffu, tg = tot >> 16;
-        if (lane == 0) { counts[b] = (uint64_t)tk | ((uint64_t)tg << 32); s_tk = tk; }
-        agg = (uint64_t)tk | ((uint64_t)tg << 31);
-        if (fused) scan_publish(f.status, b, agg);  // successors can go on; our own prefix is collected after the stores
+        if (lane == 0) {
+            counts[b] = (uint64_t)tk | ((uint64_t)tg << 32);
+            s_tk = tk; s_tg = tg;
+            if (fused) { atomicAdd(f.d_counts, (unsigned long long)tk); atomicAdd(f.d_counts + 1, (unsigned long long)tg); }
+        }
     }
-    // the tuples go back to HBM in final order (this is where part of the wait for the predecessors is hidden)
+    // the tuples go back to HBM in final order
 #pragma unroll
     for (int r = 0; r < 8; r++) {
         const uint32_t j = r * LS_THREADS + tid;
@@ -219,18 +202,11 @@ __device__ __forceinline__ void bucket_finish(const uint64_t* items, uint32_t* s
             if (!fused) out_hash[s + j] = (top | ((items[j] & ~0xfffull) >> tb)) >> lz;  // the fallback passes read it
         }
     }
-    if (warp == 0) {
-        uint64_t excl = ~0ull;
-        if (fused) {
-            excl = scan_collect(f.status, b, agg);
-            if (b == f.nb - 1 && lane == 0) csr_totals(f, excl + agg);
-        }
-        if (lane == 0) s_base = excl;
-    }
+    if (!fused) return;  // an oversize bucket exists: the CSR is written by csr_write_kernel after the fallback
     __syncthreads();
-    if (s_base == ~0ull) return;  // an oversize bucket exists: the CSR is written by csr_write_kernel after the fallback
-    const uint32_t base_k = (uint32_t)(s_base & 0x7fffffffu), base_g = (uint32_t)(s_base >> 31);
-    uint32_t* dir_b = f.dir_sub >= 0 ? f.dir + ((uint64_t)b << f.dir_sub) : nullptr;
+    const uint32_t kb = s + b;  // first key / group position of this bucket's segment
+    const uint32_t tk = s_tk, tg = s_tg;
+    uint32_t* dir_b = f.dir + (uint64_t)b * ((1u << f.dir_sub) + 1u);
     auto dir_local = [&](uint64_t item) -> uint32_t { return f.dir_sub > 0 ? (uint32_t)(item >> (64 - f.dir_sub)) : 0u; };
 #pragma unroll
     for (int r = 0; r < 8; r++) {
@@ -239,18 +215,21 @@ __device__ __forceinline__ void bucket_finish(const uint64_t* items, uint32_t* s
             const bool hk = (flags >> (2 * r)) & 1u, hg = (flags >> (2 * r)) & 2u;
             const uint32_t bk = __ballot_sync(0xffffffffu, hk), bg = __ballot_sync(0xffffffffu, hg);
             const uint32_t pre = s_cw[r * LS_WARPS + warp];
-            const uint32_t g = base_g + (pre >> 16) + __popc(bg & lt);
+            const uint32_t g = kb + (pre >> 16) + __popc(bg & lt);
             if (hg) f.grp_start[g] = s + j;
             if (hk) {
-                const uint32_t u = base_k + (pre & 0xffffu) + __popc(bk & lt);
+                const uint32_t u = kb + (pre & 0xffffu) + __popc(bk & lt);
                 const uint64_t full = top | ((items[j] & ~0xfffull) >> tb);
                 f.keys[u] = full >> lz;
                 f.key_grp[u] = g;
                 // directory entries this key owns: the bucket's 2^dir_sub entries are indexed by the item's top dir_sub bits
-                if (f.dir_sub >= 0) dir_fill(dir_b, j ? (int32_t)dir_local(items[j - 1]) : -1, (int32_t)dir_local(items[j]), u);
+                dir_fill(dir_b, j ? (int32_t)dir_local(items[j - 1]) : -1, (int32_t)dir_local(items[j]), u);
             }
-            if (j == m - 1 && f.dir_sub >= 0)  // entries after the last key (and the sentinel after the last bucket)
-                dir_fill(dir_b, (int32_t)dir_local(items[j]), (int32_t)(1u << f.dir_sub) - (b == f.nb - 1 ? 0 : 1), base_k + s_tk);
+            if (j == m - 1) {  // the segment's sentinels, and the directory entries after the last key (its own end included)
+                f.key_grp[kb + tk] = kb + tg;
+                f.grp_start[kb + tg] = s + m;
+                dir_fill(dir_b, (int32_t)dir_local(items[j]), (int32_t)(1u << f.dir_sub), kb + tk);
+            }
         }
     }
 }
@@ -277,13 +256,10 @@ bucket_sort_rep_kernel(const uint64_t* __restrict__ in_hash, const uint64_t* __r
     __shared__ uint32_t s_ninv;
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    __shared__ uint32_t s_bucket;
-    if (tid == 0) s_bucket = atomicAdd(f.ticket, 1u);
-    __syncthreads();
-    const uint32_t b = s_bucket;
+    const uint32_t b = blockIdx.x;  // buckets are independent: no ticket, no order
     const uint32_t s = start[b], e = start[b + 1];
     const uint32_t m = e - s;
-    if (m == 0) { if (tid == 0) counts[b] = 0; bucket_empty(b, f); return; }
+    if (m == 0) { if (tid == 0) counts[b] = 0; bucket_empty(b, s, f); return; }
     if (m > (uint32_t)LS_CAP) return;  // oversize: sorted and counted by the host-driven fallback
     const int sh = lz + tb;  // >= 12 on this path: the low 12 bits of (hash << sh) are zero and carry the index
 
@@ -508,19 +484,16 @@ bucket_sort_bin_kernel(const uint64_t* __restrict__ in_hash, const uint64_t* __r
     uint64_t* B = reinterpret_cast<uint64_t*>(smem_raw);            // [LS_CAP] items, grouped by bin
     uint32_t* cnt = reinterpret_cast<uint32_t*>(B + LS_CAP);        // [BN_BINS] counts, then exclusive offsets
     __shared__ uint32_t s_wsum[LS_WARPS];
-    __shared__ uint32_t s_bucket;
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_bucket = atomicAdd(f.ticket, 1u);
+    const uint32_t b = blockIdx.x;  // buckets are independent: no ticket, no order
     reinterpret_cast<uint4*>(cnt)[tid] = make_uint4(0, 0, 0, 0);
     reinterpret_cast<uint4*>(cnt)[tid + LS_THREADS] = make_uint4(0, 0, 0, 0);
-    __syncthreads();
-    const uint32_t b = s_bucket;
     const uint32_t s = start[b];
     const uint32_t s_in = SCATTERED ? b * (uint32_t)LS_CAP : s;
     const uint32_t m = SCATTERED ? min(cursor[b], (uint32_t)LS_CAP) : start[b + 1] - s;  // (an overflowing region: the host
                                                                                          // discards the build)
-    if (m == 0) { if (tid == 0) counts[b] = 0; bucket_empty(b, f); return; }
+    if (m == 0) { if (tid == 0) counts[b] = 0; bucket_empty(b, s, f); return; }
     if (m > (uint32_t)LS_CAP) return;  // oversize: sorted and counted by the host-driven fallback
     const int sh = lz + tb;  // >= 12 on this path: the low 12 bits of (hash << sh) are zero and carry the index
 
@@ -535,6 +508,7 @@ bucket_sort_bin_kernel(const uint64_t* __restrict__ in_hash, const uint64_t* __r
         if (r * LS_THREADS >= m) break;  // uniform
         if (j < m) item[r] = ((in_hash[s_in + j] << sh) & ~0xfffull) | j;
     }
+    __syncthreads();  // the counters are zero
 #pragma unroll
     for (int r = 0; r < 8; r++) {
         const uint32_t j = r * LS_THREADS + tid;
@@ -866,6 +840,18 @@ __global__ void expand_hash_kernel(const uint64_t* __restrict__ keys, const uint
     }
 }
 
+// the same over the segmented layout: one CTA per sort bucket
+__global__ void expand_hash_seg_kernel(CsrView v, uint64_t* __restrict__ hash) {
+    const uint32_t b = blockIdx.x;
+    const uint32_t kb = v.seg_start[b] + b, tk = (uint32_t)v.seg_counts[b];
+    for (uint32_t i = threadIdx.x; i < tk; i += blockDim.x) {
+        const uint32_t u = kb + i;
+        const uint64_t h = v.keys[u];
+        const uint32_t e = v.grp_start[v.key_grp[u + 1]];
+        for (uint32_t t = v.grp_start[v.key_grp[u]]; t < e; t++) hash[t] = h;
+    }
+}
+
 }  // namespace
 
 cudaError_t launch_directory(const uint64_t* keys, const uint64_t* d_counts, uint32_t* dir, int dir_bits, int dir_shift,
@@ -876,9 +862,13 @@ cudaError_t launch_directory(const uint64_t* keys, const uint64_t* d_counts, uin
 
 cudaError_t expand_sorted_hash(const CsrView& v, uint64_t* hash, cudaStream_t stream) {
     if (v.n == 0) return cudaSuccess;
-    expand_hash_kernel<<<148 * 8, 256, 0, stream>>>(v.keys, v.key_grp, v.grp_start, v.d_counts, hash);
+    if (v.dir_sub != DIR_SUB_COMPACT) expand_hash_seg_kernel<<<v.seg_nb, 256, 0, stream>>>(v, hash);
+    else expand_hash_kernel<<<148 * 8, 256, 0, stream>>>(v.keys, v.key_grp, v.grp_start, v.d_counts, hash);
     return cudaGetLastError();
 }
+
+int build_top_bits(uint64_t n, int end_bit, uint64_t max_hash) { return n ? msd_top_bits(n, 64 - end_bit, max_hash) : -1; }
+uint64_t build_slack(uint64_t n) { return max_ranges(n) + 2; }
 
 PairSortPlan pair_sort_plan(uint64_t n, int end_bit, uint64_t max_hash) {
     PairSortPlan p;
@@ -926,6 +916,10 @@ cudaError_t build_index(const BuildArgs& a, cudaStream_t stream, int* out_in_a, 
     *out_in_a = 1;
     if (a.hash_written) *a.hash_written = 1;
     if (a.overflow_dev) *a.overflow_dev = nullptr;
+    if (a.out_dir_sub) *a.out_dir_sub = DIR_SUB_COMPACT;
+    if (a.out_seg_nb) *a.out_seg_nb = 0;
+    if (a.out_seg_start) *a.out_seg_start = nullptr;
+    if (a.out_seg_counts) *a.out_seg_counts = nullptr;
     if (a.plan.custom && n) {
         // scattered input: [second scatter level,] bucket offsets, bin kernel straight from the final buckets
         const PairSortPlan& pl = a.plan;
@@ -960,26 +954,25 @@ cudaError_t build_index(const BuildArgs& a, cudaStream_t stream, int* out_in_a, 
         char* tp = (char*)a.temp;
         uint32_t* oversize = (uint32_t*)tp + nb + 1;
         uint64_t* counts = (uint64_t*)(tp + (((size_t)(nb + 8) * 4 + 7) & ~(size_t)7));
-        uint64_t* status = counts + 2 * (size_t)nb + 1;
-        uint32_t* ticket = (uint32_t*)(status + nb);
         KS_TRY(cudaMemsetAsync(oversize, 0, 8, stream));
-        KS_TRY(cudaMemsetAsync(status, 0, (size_t)nb * 8 + 8, stream));
+        KS_TRY(cudaMemsetAsync(a.d_counts, 0, 16, stream));
+        if (a.dir_bits < pl.total) return cudaErrorInvalidValue;  // (the caller sizes the directory from build_top_bits)
         CsrOut f;
-        f.status = status; f.ticket = ticket; f.oversize = oversize; f.keys = a.keys; f.key_grp = a.key_grp; f.grp_start = a.grp_start;
-        f.d_counts = a.d_counts; f.n = n; f.nb = nb;
-        f.dir = a.dir; f.dir_bits = a.dir_bits; f.dir_sub = a.dir_bits >= pl.total ? a.dir_bits - pl.total : -1;
+        f.oversize = oversize; f.keys = a.keys; f.key_grp = a.key_grp; f.grp_start = a.grp_start;
+        f.d_counts = (unsigned long long*)a.d_counts; f.nb = nb;
+        f.dir = a.dir; f.dir_sub = a.dir_bits - pl.total;
         KS_TRY(cudaFuncSetAttribute(bucket_sort_bin_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BN_SMEM));
         bucket_sort_bin_kernel<false, true><<<nb, LS_THREADS, BN_SMEM, stream>>>(r2h, r2l, a.hash_b, a.loc_a, bstart, cursor2, lz, pl.total,
                                                                                  counts, a.t_size, f);
         KS_TRY(cudaGetLastError());
         *sort_launches += pl.l2 ? 5 : 3;
         if (a.ev_sorted) KS_TRY(cudaEventRecord(a.ev_sorted, stream));
-        if (f.dir_sub < 0) {
-            dir_kernel<<<148 * 8, 256, 0, stream>>>(a.keys, a.d_counts, a.dir, a.dir_bits, a.dir_shift);
-            *csr_launches += 1;
-        }
         if (a.overflow_dev) *a.overflow_dev = overflow;  // read by the caller together with the totals: no round trip here
         if (a.hash_written) *a.hash_written = 0;
+        if (a.out_dir_sub) *a.out_dir_sub = f.dir_sub;
+        if (a.out_seg_nb) *a.out_seg_nb = nb;
+        if (a.out_seg_start) *a.out_seg_start = bstart;
+        if (a.out_seg_counts) *a.out_seg_counts = counts;
         *out_in_a = 1;
         return cudaGetLastError();
     }
@@ -1009,8 +1002,6 @@ cudaError_t build_index(const BuildArgs& a, cudaStream_t stream, int* out_in_a, 
     uint32_t* oversize = start + nb + 1;                                          // [2]
     uint64_t* counts = (uint64_t*)(tp + (((size_t)(nb + 8) * 4 + 7) & ~(size_t)7));  // [nb]
     uint64_t* prefix = counts + nb;                                               // [nb + 1]
-    uint64_t* status = prefix + nb + 1;                                           // [nb] look-back words (fused CSR)
-    uint32_t* ticket = (uint32_t*)(status + nb);                                  // [1] bucket ticket
 
     const uint64_t *fh, *fl;  // final sorted tuples
     if (tb < 0) {
@@ -1037,19 +1028,19 @@ cudaError_t build_index(const BuildArgs& a, cudaStream_t stream, int* out_in_a, 
         // 2. bucket boundaries; one CTA per bucket sorts it in shared memory and counts its heads
         bucket_start_kernel<<<(nb + 1 + 255) / 256, 256, 0, stream>>>(sh, n, lz, tb, start, oversize);
         oversize_count_kernel<<<(nb + 255) / 256, 256, 0, stream>>>(start, nb, oversize);
+        if (a.dir_bits < tb) return cudaErrorInvalidValue;  // (the caller sizes the directory from build_top_bits)
         CsrOut f;
-        f.status = status; f.ticket = ticket; f.oversize = oversize; f.keys = a.keys; f.key_grp = a.key_grp; f.grp_start = a.grp_start;
-        f.d_counts = a.d_counts; f.n = n; f.nb = nb;
-        f.dir = a.dir; f.dir_bits = a.dir_bits; f.dir_sub = a.dir_bits >= tb && !getenv("KS_DIR_KERNEL") ? a.dir_bits - tb : -1;
-        KS_TRY(cudaMemsetAsync(status, 0, (size_t)nb * 8 + 8, stream));
+        f.oversize = oversize; f.keys = a.keys; f.key_grp = a.key_grp; f.grp_start = a.grp_start;
+        f.d_counts = (unsigned long long*)a.d_counts; f.nb = nb;
+        f.dir = a.dir; f.dir_sub = a.dir_bits - tb;
+        KS_TRY(cudaMemsetAsync(a.d_counts, 0, 16, stream));
         // repeat-heavy inputs (small k-mer space, e.g. hp k=24) take the two-pass stable variant, everything else the bin
-        // variant; KS_LS_VARIANT = rep | bn | bs (bin variant without / with a barrier per row) is a test hook
-        const char* v_env = getenv("KS_LS_VARIANT");
-        const bool bin = v_env ? (v_env[0] == 'b') : (a.repeat_heavy == 0);
+        // variant; ls_variant (KS_LS_VARIANT = rep | bn | bs: bin variant without / with a barrier per row) is a test hook
+        const bool bin = a.ls_variant ? a.ls_variant >= 2 : (a.repeat_heavy == 0);
         if (bin) {
             KS_TRY(cudaFuncSetAttribute(bucket_sort_bin_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BN_SMEM));
             KS_TRY(cudaFuncSetAttribute(bucket_sort_bin_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BN_SMEM));
-            const bool stepped = v_env && v_env[1] == 's';
+            const bool stepped = a.ls_variant == 3;
             if (stepped) bucket_sort_bin_kernel<true, false><<<nb, LS_THREADS, BN_SMEM, stream>>>(sh, sl, dh, dl, start, nullptr, lz, tb, counts, a.t_size, f);
             else bucket_sort_bin_kernel<false, false><<<nb, LS_THREADS, BN_SMEM, stream>>>(sh, sl, dh, dl, start, nullptr, lz, tb, counts, a.t_size, f);
         } else {
@@ -1081,12 +1072,12 @@ cudaError_t build_index(const BuildArgs& a, cudaStream_t stream, int* out_in_a, 
         fh = dh;
         fl = dl;
         if (a.ev_sorted) KS_TRY(cudaEventRecord(a.ev_sorted, stream));
-        if (n_over == 0) {  // the bucket sort wrote keys / key_grp / grp_start itself: only the directory is left
+        if (n_over == 0) {  // the bucket sort wrote keys / key_grp / grp_start and the directory itself (segmented layout)
             if (a.hash_written) *a.hash_written = 0;  // ... and skipped the sorted hash column
-            if (f.dir_sub < 0) {                             // ... and, normally, its part of the directory
-                dir_kernel<<<148 * 8, 256, 0, stream>>>(a.keys, a.d_counts, a.dir, a.dir_bits, a.dir_shift);
-                *csr_launches += 1;
-            }
+            if (a.out_dir_sub) *a.out_dir_sub = f.dir_sub;
+            if (a.out_seg_nb) *a.out_seg_nb = nb;
+            if (a.out_seg_start) *a.out_seg_start = start;
+            if (a.out_seg_counts) *a.out_seg_counts = counts;
             return cudaGetLastError();
         }
     }

@@ -15,6 +15,16 @@ constexpr uint64_t MAX_TUPLES = (1ull << 31) - 1;  // per shard: 32-bit postings
 //                              hash in that protein's sketch
 //   t_size[P], t_abund[P]      per protein: distinct hashes (|T|) and kept windows (sum of abundances)
 //   dir[2^dir_bits + 1]        bucket directory over the top hash bits: first key of each bucket
+//
+// Two layouts of keys / key_grp / grp_start (the postings loc[] are dense and ordered in both):
+//   compact    keys[0 .. U), groups [0 .. G): what the streaming passes (scan_counts + csr_write) write.
+//   segmented  (dir_sub < 31) what the bucket-sort kernels write themselves, WITHOUT any chain between buckets: sort
+//              bucket b -- tuples [seg_start[b], seg_start[b + 1]) -- keeps its keys at positions seg_start[b] + b + i and
+//              its groups at the same base (a bucket of m tuples has at most m keys and m groups, so the segments never
+//              meet; the spare slot per bucket holds the sentinel), key_grp / grp_start hold positions in that space, and
+//              every bucket has its own 2^dir_sub + 1 directory entries.  A reader only ever goes from a key position
+//              to u + 1, from a group position to g + 1: both layouts read the same way once find_key has mapped a hash to
+//              its directory slot (x + (x >> dir_sub)).  seg_counts[b] = keys | groups << 32 of bucket b (for exports).
 struct CsrView {
     const uint64_t* hash;
     const uint64_t* loc;
@@ -29,7 +39,12 @@ struct CsrView {
     uint32_t n_prot;
     int dir_bits;
     int dir_shift;
+    int dir_sub = 31;                        // 31: compact layout; else log2 of the directory entries per sort bucket
+    uint32_t seg_nb = 0;                     // segmented: sort buckets
+    const uint32_t* seg_start = nullptr;     // [seg_nb + 1]
+    const uint64_t* seg_counts = nullptr;    // [seg_nb]
 };
+constexpr int DIR_SUB_COMPACT = 31;
 
 // Plan of the unstable partition of the general path (dense_scatter.cuh): the top `total` = l1 + l2 bits of the normalised
 // hash pick one of 2^total buckets of at most 4096 tuples; the first level is fused into the sketch kernel.  custom == 0:
@@ -61,13 +76,20 @@ struct BuildArgs {
     int end_bit;  // hashes are < 2^end_bit (64 - leading zeros of max_hash)
     uint64_t max_hash;
     int repeat_heavy;  // the k-mer space is small next to n (hashes repeat many times): two local counting passes
+    int ls_variant = 0;  // test hook: 0 pick from repeat_heavy, 1 rep, 2 bin, 3 bin with a barrier per row
     // outputs (device, preallocated): keys[n], key_grp[n+1], grp_start[n+1], t_size[P], t_abund[P], d_counts[2],
     // dir[2^dir_bits + 1]
     uint64_t* keys;
     uint32_t *key_grp, *grp_start, *t_size, *t_abund;
     uint64_t* d_counts;
-    uint32_t* dir;
-    int dir_bits, dir_shift;
+    uint32_t* dir;        // [2^dir_bits + max buckets + 1]
+    int dir_bits, dir_shift;  // dir_bits >= build_top_bits(): a directory bucket never spans two sort buckets
+    // out (host): layout of what was written -- DIR_SUB_COMPACT, or the segmented layout's dir_sub with its bucket tables
+    // (device pointers into `temp` / `work`, valid until the next build; the caller keeps a copy)
+    int* out_dir_sub = nullptr;
+    uint32_t* out_seg_nb = nullptr;
+    const uint32_t** out_seg_start = nullptr;
+    const uint64_t** out_seg_counts = nullptr;
     void* temp;
     size_t temp_bytes;
     int* hash_written = nullptr;  // out (host): 0 when the sorted hash column was not written (see expand_sorted_hash)
@@ -76,6 +98,10 @@ struct BuildArgs {
 };
 
 size_t build_temp_bytes(uint64_t n, int end_bit);
+// Sort buckets the build of n ordered tuples uses (2^bits), or -1 when it takes the library sort for all bits (compact
+// layout); and the slack the key / group arrays need past n (one sentinel slot per bucket).
+int build_top_bits(uint64_t n, int end_bit, uint64_t max_hash);
+uint64_t build_slack(uint64_t n);
 // Sort by hash (stable) + CSR build + directory.  *out_in_a = 1 when the sorted tuples ended in the `a` pair.
 // Scattered input: no synchronisation (the caller reads *overflow_dev with the totals); ordered input: synchronises the
 // stream once (oversize-bucket count).  Adds the kernels launched to the two counters.

@@ -43,8 +43,9 @@ inline int bits_for(uint64_t max_value) {
 
 // ---- lookups ---------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t find_key(const CsrView& c, uint64_t h) {
-    const uint64_t b = h >> c.dir_shift;
-    if (b >= (1ull << c.dir_bits)) return 0xffffffffu;
+    const uint64_t x = h >> c.dir_shift;
+    if (x >= (1ull << c.dir_bits)) return 0xffffffffu;
+    const uint64_t b = x + (x >> c.dir_sub);  // segmented layout: every sort bucket has one more entry (its end); compact: + 0
     uint32_t lo = c.dir[b], hi = c.dir[b + 1];
     const uint32_t end = hi;
     while (lo < hi) {
@@ -718,6 +719,29 @@ cudaError_t launch_merge(const MergeArgs& m, cudaStream_t stream, uint64_t* n_la
     }
     return cudaFreeAsync(d, stream);
 #undef KS_TRY
+}
+
+namespace {
+__device__ __forceinline__ void id_sum_key(const CsrView& v, uint32_t u, unsigned long long* sums) {
+    const uint64_t h = v.keys[u];
+    for (uint32_t g = v.key_grp[u]; g < v.key_grp[u + 1]; g++) atomicAdd(sums + (uint32_t)(v.loc[v.grp_start[g]] >> 32), (unsigned long long)h);
+}
+__global__ void id_sums_compact_kernel(CsrView v, uint64_t n_keys, unsigned long long* sums) {
+    for (uint64_t u = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; u < n_keys; u += (uint64_t)gridDim.x * blockDim.x)
+        id_sum_key(v, (uint32_t)u, sums);
+}
+__global__ void id_sums_seg_kernel(CsrView v, unsigned long long* sums) {
+    const uint32_t b = blockIdx.x;
+    const uint32_t kb = v.seg_start[b] + b, tk = (uint32_t)v.seg_counts[b];
+    for (uint32_t i = threadIdx.x; i < tk; i += blockDim.x) id_sum_key(v, kb + i, sums);
+}
+}  // namespace
+
+cudaError_t launch_id_sums(const CsrView& v, uint64_t n_keys, unsigned long long* sums, cudaStream_t stream) {
+    if (n_keys == 0) return cudaSuccess;
+    if (v.dir_sub != DIR_SUB_COMPACT) id_sums_seg_kernel<<<v.seg_nb, 128, 0, stream>>>(v, sums);
+    else id_sums_compact_kernel<<<148 * 8, 256, 0, stream>>>(v, n_keys, sums);
+    return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------------------------------

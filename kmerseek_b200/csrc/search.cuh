@@ -139,4 +139,8 @@ struct MergeArgs {
 };
 cudaError_t launch_merge(const MergeArgs& m, cudaStream_t stream, uint64_t* n_launches);
 
+// sums[p] += every distinct hash of protein p (wrapping): the kmerseek id of a signature is the hex of that sum
+// (src/rust/signature.rs:277-279).  `sums` (n_prot words) must be zeroed.  signature_count() support; not a hot path.
+cudaError_t launch_id_sums(const CsrView& v, uint64_t n_keys, unsigned long long* sums, cudaStream_t stream);
+
 }  // namespace ks

@@ -61,14 +61,18 @@ class Proteome:
     def __init__(self, handle):
         self._h = handle
 
+    MODES = {"kmerseek": _ffi.KS_NORMALIZE_KMERSEEK, "sourmash": _ffi.KS_NORMALIZE_SOURMASH}
+
     @classmethod
-    def from_fasta(cls, path, ambig_seed=0):
+    def from_fasta(cls, path, ambig_seed=0, mode="kmerseek"):
+        """mode "kmerseek": the Rust crate's index path (upper-case, '*' truncation, B/Z/J resolved, validation);
+        "sourmash": what `kmerseek search` does to both inputs (upper-case only)."""
         h = C.c_void_p()
-        check(_ffi.lib().ks_proteome_from_fasta(os.fspath(path).encode(), ambig_seed, C.byref(h)))
+        check(_ffi.lib().ks_proteome_from_fasta_mode(os.fspath(path).encode(), ambig_seed, cls.MODES[mode], C.byref(h)))
         return cls(h)
 
     @classmethod
-    def from_sequences(cls, seqs, names=None, ambig_seed=0):
+    def from_sequences(cls, seqs, names=None, ambig_seed=0, mode="kmerseek"):
         n = len(seqs)
         raw = [s.encode() if isinstance(s, str) else bytes(s) for s in seqs]
         arr = (C.c_char_p * max(n, 1))(*raw)
@@ -77,7 +81,7 @@ class Proteome:
         if names is not None:
             nm = (C.c_char_p * max(n, 1))(*[x.encode() for x in names])
         h = C.c_void_p()
-        check(_ffi.lib().ks_proteome_from_sequences(arr, lens, nm, n, ambig_seed, C.byref(h)))
+        check(_ffi.lib().ks_proteome_from_sequences_mode(arr, lens, nm, n, ambig_seed, cls.MODES[mode], C.byref(h)))
         return cls(h)
 
     @classmethod
@@ -197,6 +201,10 @@ class ProteinSignature:
     def get_raw_sequence(self):
         return self._sequence if self._store_raw else None
 
+    def has_efficient_data(self):
+        """src/rust/signature.rs: the raw sequence is there (store_raw_sequences)."""
+        return self._store_raw
+
     def kmer_infos(self):
         """hashval -> KmerInfo (src/rust/index.rs:770-780)."""
         if self._infos is None:
@@ -209,6 +217,29 @@ class ProteinSignature:
                 ki.original_kmer_to_position.setdefault(orig, []).append(p)
             self._infos = infos
         return self._infos
+
+
+class StoredSignature(tuple):
+    """A signature as the index holds it (the value type of get_signatures()): unpacks as (name, mins, abunds) and
+    carries the raw sequence when the index was created with store_raw_sequences (src/rust/index.rs:737-743,
+    signature.rs:305-317)."""
+
+    def __new__(cls, name, mins, abunds, raw_sequence=None):
+        self = super().__new__(cls, (name, mins, abunds))
+        self.name, self.raw_sequence = name, raw_sequence
+        return self
+
+    def mins(self):
+        return self[1]
+
+    def abunds(self):
+        return self[2]
+
+    def get_raw_sequence(self):
+        return self.raw_sequence
+
+    def has_efficient_data(self):
+        return self.raw_sequence is not None
 
 
 class ProteomeIndexBuilder:
@@ -273,6 +304,7 @@ class ProteomeIndex:
         self._store_raw = bool(store_raw_sequences)
         self.ambig_seed = ambig_seed
         self._names = []
+        self._raw = []  # raw sequences, protein order (only with store_raw_sequences)
         self._h = None
         p = _ffi.ks_params(self.ksize, self.scaled, _moltype_id(moltype), int(self._store_raw), device, 0)
         h = C.c_void_p()
@@ -353,6 +385,8 @@ class ProteomeIndex:
         check(_ffi.lib().ks_index_add_tuples(self._h, h.ctypes.data_as(_ffi.u64p), pid.ctypes.data_as(_ffi.u32p),
                                              pos.ctypes.data_as(_ffi.u32p), len(h), len(protein_signatures)))
         self._names.extend(s.name for s in protein_signatures)
+        if self._store_raw:
+            self._raw.extend(s._sequence for s in protein_signatures)
 
     def store_signatures_batch(self, protein_signatures):
         self.store_signatures(list(protein_signatures))
@@ -360,6 +394,8 @@ class ProteomeIndex:
     def add_proteome(self, proteome: Proteome):
         check(_ffi.lib().ks_index_add_proteome(self._h, proteome._h))
         self._names.extend(proteome.names)
+        if self._store_raw:
+            self._raw.extend(proteome.sequence(i) for i in range(proteome.n_proteins))
 
     def process_fasta(self, fasta_path, progress_interval=0, batch_size=1000):
         """src/rust/index.rs:907-961.  `batch_size` is accepted for signature parity; the whole file is one
@@ -380,6 +416,7 @@ class ProteomeIndex:
     def clear(self):
         check(_ffi.lib().ks_index_clear(self._h))
         self._names = []
+        self._raw = []
 
     # -- accessors ----------------------------------------------------------------------------------
     def stats(self):
@@ -427,16 +464,20 @@ class ProteomeIndex:
         return [(mins[int(sig_ptr[i]):int(sig_ptr[i + 1])], abunds[int(sig_ptr[i]):int(sig_ptr[i + 1])]) for i in range(P)]
 
     def get_signatures(self):
-        """id string -> (name, mins, abunds); equal ids overwrite, last in input order wins
-        (DashMap insert at src/rust/index.rs:817-820)."""
+        """id string -> StoredSignature (name, mins, abunds, raw sequence when the index stores them); equal ids overwrite,
+        last in input order wins (DashMap insert at src/rust/index.rs:817-820)."""
         out = {}
         for i, (m, a) in enumerate(self.export_sketches()):
-            out[id_of_mins(m)] = (self._names[i] if i < len(self._names) else str(i), m, a)
+            raw = self._raw[i] if (self._store_raw and i < len(self._raw)) else None
+            out[id_of_mins(m)] = StoredSignature(self._names[i] if i < len(self._names) else str(i), m, a, raw)
         return out
 
     def signature_count(self):
-        """src/rust/index.rs:514-516"""
-        return len(self.get_signatures())
+        """src/rust/index.rs:514-516: distinct ids (equal ids overwrite), counted by the library from the device index."""
+        self.finalize()
+        out = C.c_uint64(0)
+        check(_ffi.lib().ks_index_signature_count(self._h, C.byref(out)))
+        return out.value
 
     def print_stats(self):
         """src/rust/index.rs:628-639"""

@@ -189,28 +189,31 @@ def _stitch(kmers, starts):
 
 
 def stitch_hits(result: SearchResult, index: ProteomeIndex, query_seqs, target_seqs, query_names, target_names):
-    """Per (query, match) pair, the stitched region table of `kmerseek search --extract-kmers`
-    (src/python/kmerseek/search.py:64-121), quirks included.  SURVEY section 8f row N4."""
+    """The stitched region table of `kmerseek search --extract-kmers` (src/python/kmerseek/search.py:64-121), quirks
+    included: the reference groups the joined k-mer rows by `match_name` ONLY (search.py:222-240, stitch_kmers_per_gene)
+    and labels the group with its first row's query_name after the sort by query start (search.py:70-74), so with several
+    queries the rows of different queries that hit one match are stitched together; the query is stitched with the MATCH starts (search.py:78).
+    SURVEY section 8f row N4."""
     h = result.hits
     k = index.ksize
     groups = {}
     for i in range(result.n_hits):
         q, t = int(h["hit_qid"][i]), int(h["hit_pid"][i])
-        a, b = int(h["hit_qpos"][i]), int(h["hit_tpos"][i])
-        groups.setdefault((q, t), []).append((a, b))
+        groups.setdefault(target_names[t], []).append((int(h["hit_qpos"][i]), int(h["hit_tpos"][i]), q, t))
     out = []
-    for (q, t), lst in groups.items():
-        lst.sort(key=lambda r: r[0])
-        qk = [query_seqs[q][a:a + k] for a, _ in lst]
-        tk = [target_seqs[t][b:b + k] for _, b in lst]
+    for name, lst in groups.items():
+        lst.sort(key=lambda r: r[0])  # df.sort("start_query"), search.py:70
+        first_q = lst[0][2]           # df["query_name"][0], search.py:74: the row with the smallest query start
+        qk = [query_seqs[q][a:a + k] for a, _, q, _ in lst]
+        tk = [target_seqs[t][b:b + k] for _, b, _, t in lst]
         ek = [translate(x, index.moltype) for x in qk]
-        qs_, ts_ = [a for a, _ in lst], [b for _, b in lst]
+        qs_, ts_ = [r[0] for r in lst], [r[1] for r in lst]
         query = _stitch(qk, ts_)  # the reference stitches the query with the match starts (search.py:78)
         alpha = _stitch(ek, qs_)
         match = _stitch(tk, ts_)
         if not (len(query) == len(alpha) == len(match)):
             raise AssertionError("stitched lengths differ (the reference asserts the same, search.py:87-88)")
-        out.append({"match_name": target_names[t], "query_name": query_names[q], "query_start": min(qs_),
+        out.append({"match_name": name, "query_name": query_names[first_q], "query_start": min(qs_),
                     "query_end": min(qs_) + len(query), "query": query, "match_start": min(ts_),
                     "match_end": min(ts_) + len(query), "match": match, "encoded": alpha, "length": len(query)})
     out.sort(key=lambda r: (r["query_start"], r["query_end"]))

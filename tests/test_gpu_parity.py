@@ -158,6 +158,104 @@ def test_golden_stitched(K, golden_search):
     idx.close()
 
 
+def test_ambiguous_residues_self_match_and_sourmash_mode(K, O):
+    """A query that is a copy of a target record must match it fully, B/Z/J included: the resolution depends on the seed
+    and the position in the sequence, not on the record's index.  In "sourmash" mode (what `kmerseek search` does to both
+    inputs) nothing is resolved, truncated or rejected: B/Z/J translate to X under dayhoff / hp, an inner '*' stays."""
+    rng = np.random.default_rng(21)
+    letters = list("ACDEFGHIKLMNPQRSTVWY")
+    seqs = []
+    for i in range(40):
+        s = rng.choice(letters, size=int(rng.integers(60, 200)))
+        s[rng.integers(0, len(s), size=6)] = rng.choice(list("BZJ"), size=6)
+        seqs.append("".join(s))
+    seqs[7] = seqs[7][:50] + "*" + seqs[7][50:]
+    seqs[9] = seqs[9].lower()
+    names = [f"p{i}" for i in range(len(seqs))]
+    for mode in ("kmerseek", "sourmash"):
+        for k, moltype in ((7, "protein"), (10, "dayhoff"), (14, "hp")):
+            t = K.Proteome.from_sequences(seqs, names, mode=mode)
+            q = K.Proteome.from_sequences([seqs[33], seqs[7], seqs[9]], ["a", "b", "c"], mode=mode)  # other record indices
+            with K.ProteomeIndex("db", k, 1, moltype) as idx:
+                idx.add_proteome(t)
+                r = K.search(idx, q, hits=False)
+                p = r.pairs
+                for qi, ti in ((0, 33), (1, 7), (2, 9)):
+                    j = [x for x in range(r.n_pairs) if p["pair_qid"][x] == qi and p["pair_pid"][x] == ti]
+                    assert len(j) == 1 and p["containment"][j[0]] == 1.0 and p["jaccard"][j[0]] == 1.0, (mode, moltype, qi)
+                # against the oracle on the oracle's own normalisation
+                norm = [O.normalize(s, i, 0, mode) for i, s in enumerate(seqs)]
+                assert [t.sequence(i) for i in range(len(seqs))] == norm
+                res, offs = O.pack(norm)
+                qres, qoffs = O.pack([O.normalize(s, 0, 0, mode) for s in (seqs[33], seqs[7], seqs[9])])
+                _search_equals_oracle(K, O, idx, res, offs, qres, qoffs, k, moltype, 1)
+    assert "*" in K.Proteome.from_sequences(seqs, names, mode="sourmash").sequence(7)[:-1]
+    assert K.Proteome.from_sequences(seqs, names).sequence(7).endswith("*") and len(K.Proteome.from_sequences(seqs, names).sequence(7)) == 51
+    K.Proteome.from_sequences(["AC1-DE"], ["x"], mode="sourmash")  # nothing is rejected on this path
+    with pytest.raises(K.InvalidAminoAcid):
+        K.Proteome.from_sequences(["AC1-DE"], ["x"])
+
+
+def test_stitch_groups_by_match_name_like_the_reference(K, O):
+    """stitch_kmers_per_gene groups by match_name only (src/python/kmerseek/search.py:222-240): two queries that hit one
+    match end in ONE stitched row, labelled with the query of the smallest query start."""
+    rng = np.random.default_rng(3)
+    letters = list("ACDEFGHIKLMNPQRSTVWY")
+    tseqs = ["".join(rng.choice(letters, size=150)) for _ in range(5)]
+    # (the two queries share their offset into t2: with unrelated offsets the reference's own length assertion fails,
+    # search.py:87-88, and so does stitch_hits)
+    qseqs = [tseqs[2][20:60], tseqs[2][20:75], tseqs[4][10:70]]
+    k = 9
+    t = K.Proteome.from_sequences(tseqs, [f"t{i}" for i in range(5)])
+    q = K.Proteome.from_sequences(qseqs, ["qa", "qb", "qc"])
+    with K.ProteomeIndex("db", k, 1, "dayhoff") as idx:
+        idx.add_proteome(t)
+        res = K.search(idx, q, hits=True)
+        rows = K.stitch_hits(res, idx, qseqs, tseqs, q.names, t.names)
+    assert sorted(r["match_name"] for r in rows) == ["t2", "t4"]
+    h = res.hits
+    merged = {}
+    for i in range(res.n_hits):
+        qi, ti, a, b = int(h["hit_qid"][i]), int(h["hit_pid"][i]), int(h["hit_qpos"][i]), int(h["hit_tpos"][i])
+        qk = qseqs[qi][a:a + k]
+        merged.setdefault(ti, []).append((a, b, qk, tseqs[ti][b:b + k], O.translate(qk, "dayhoff"), qi))
+    for r in rows:
+        ti = int(r["match_name"][1:])
+        o = O.stitch_pair([x[:5] for x in merged[ti]])
+        for col, v in o.items():
+            assert r[col] == v, col
+        first = sorted(merged[ti], key=lambda x: x[0])[0]
+        assert r["query_name"] == q.names[first[5]]
+    t2 = [r for r in rows if r["match_name"] == "t2"][0]
+    assert t2["query_name"] == "qa" and t2["length"] > 75 - 20  # both queries' k-mers in one row (duplicates concatenated)
+
+
+def test_raw_sequence_storage_and_signature_count(K):
+    """src/rust/index.rs:2713-2844 (raw-sequence storage) and :514-516 / :817-820 (signature_count: the signatures map is
+    keyed by the id, equal sketches overwrite)."""
+    seq = "ACDEFGHIKLMNPQRSTVWY"
+    for store in (True, False):
+        with K.ProteomeIndex("db", 5, 1, "protein", store_raw_sequences=store) as idx:
+            sig = idx.create_protein_signature(seq, "test_protein")
+            assert sig.has_efficient_data() == store
+            assert sig.get_raw_sequence() == (seq if store else None)
+            idx.store_signatures([sig])
+            assert idx.store_raw_sequences() == store and idx.signature_count() == 1
+            stored = next(iter(idx.get_signatures().values()))
+            assert stored.has_efficient_data() == store and stored.get_raw_sequence() == (seq if store else None)
+            assert stored.name == "test_protein" and np.array_equal(stored.mins(), sig.mins())
+    # duplicates overwrite: 5 records, two of them copies, one too short to have a sketch ("0" is an id too)
+    seqs = [seq, "PLANTANDANIMALGENQMES", seq, "LIVINGALIVEANDWELL", "ACD", "PLANTANDANIMALGENQMES", "AC"]
+    with K.ProteomeIndex("db", 5, 1, "protein", store_raw_sequences=True) as idx:
+        idx.add_proteome(K.Proteome.from_sequences(seqs, [f"p{i}" for i in range(len(seqs))]))
+        idx.finalize()
+        assert idx.signature_count() == 4 == len(idx.get_signatures())
+        assert idx.stats()["n_distinct_ids"] == 4 and idx.stats()["n_proteins"] == 7
+        sigs = idx.get_signatures()
+        assert sorted(s.name for s in sigs.values()) == ["p2", "p3", "p5", "p6"]  # the last of equal ids wins
+        assert all(s.get_raw_sequence() == seqs[int(s.name[1:])] for s in sigs.values())
+
+
 def test_invalid_residue_and_moltype_errors(K, golden_rust):
     with K.ProteomeIndex("db", 5, 1, "protein") as idx:
         for e in golden_rust["errors"]:  # src/rust/index.rs:2031-2046
