@@ -464,10 +464,16 @@ struct ks_index {
     // dense k-mer space path (hp, 8 <= k <= 24, scaled == 1): per-handle rank tables; a batch that qualifies is not
     // sketched when it is added but built as a whole by finalize (pending_dense)
     int dense_state = 0;  // 0: tables not built, 1: ready, -1: unusable for this k (two patterns share a hash)
-    uint32_t* dense_rank = nullptr;
-    uint64_t* dense_hash = nullptr;
-    uint32_t* dense_flags = nullptr;  // device u32[4]: [0] table check, [1] unhandled exception, [2] exception keys emitted
-    Buf b_dense_rank, b_dense_hash, b_dense_flags, b_dense_work;
+    uint32_t* dense_code = nullptr;   // pattern -> order-preserving code (DenseSketchArgs, sketch.cuh)
+    uint64_t* dense_hash = nullptr;   // the patterns' hashes in increasing order
+    uint32_t* dense_group = nullptr;  // first entry of every 16-bit hash-prefix group
+    int dense_rb_full = 0;            // bits of a code below the hash prefix, parity bit included
+    int dense_rb = 0, dense_parity = 1;   // layout of this build: rb = dense_rb_full - (1 - parity)
+    int dense_table_parity = -1;      // layout the code table currently holds
+    uint32_t* dense_por = nullptr;    // pattern of every rank (to rebuild the code table in the other layout)
+    uint32_t* dense_flags = nullptr;  // device u32[4]: [0] table check, [1] unhandled exception, [2] exception keys emitted,
+                                      // [3] largest rank of a pattern inside its prefix group (table build)
+    Buf b_dense_code, b_dense_hash, b_dense_group, b_dense_por, b_dense_flags, b_dense_work;
     bool pending_dense = false;
     bool scattered = false;  // the only batch was sketched straight into the regions of the unstable partition (pair_plan)
     bool scatter_unchecked = false;  // ... and its count / zero-hash flag (d_count) have not been read yet: finalize does
@@ -604,13 +610,30 @@ int bits_for_value(uint64_t v) {  // bits needed to hold values 0 .. v
 // Dense k-mer space path (sketch_dense_kernel): the batch must be the index's only content, its k-mer space small and
 // well covered (otherwise the tables cost more than they save), and rank | protein | position must fit 64 bits.
 // KS_DENSE=0 switches the path off, KS_DENSE=1 drops the coverage condition (test hooks).
+bool dense_eligible_(const ks_index* x, const DeviceBatch& b, uint64_t n_prot_before, uint64_t n_tuples_before);
 bool dense_eligible(const ks_index* x, const DeviceBatch& b, uint64_t n_prot_before, uint64_t n_tuples_before) {
+    const bool e = dense_eligible_(x, b, n_prot_before, n_tuples_before);
+    if (x->hooks.timing) fprintf(stderr, "[ks] dense eligible: %d (state %d, prot before %llu, tuples before %llu, windows %llu)\n", (int)e,
+                                 x->dense_state, (unsigned long long)n_prot_before, (unsigned long long)n_tuples_before,
+                                 (unsigned long long)b.n_windows);
+    return e;
+}
+bool dense_eligible_(const ks_index* x, const DeviceBatch& b, uint64_t n_prot_before, uint64_t n_tuples_before) {
     if (x->hooks.dense == 0) return false;
     const uint32_t k = x->params.ksize;
     if (x->params.moltype != KS_HP || k < (uint32_t)DENSE_MIN_K || k > (uint32_t)DENSE_MAX_K || x->max_hash != ~0ull) return false;
     if (x->dense_state < 0 || n_prot_before || n_tuples_before || b.n_prot == 0 || b.n_res >= (1ull << 32)) return false;
     if (x->hooks.dense != 1 && b.n_windows < (1ull << k) / 4) return false;
-    return (int)k + 1 + bits_for_value(b.n_prot - 1) + bits_for_value(b.max_len) <= 64;  // rank' = 2 rank + 1 takes k + 1 bits
+    // a key is code | protein | position; the code takes DENSE_PREFIX_BITS + rb bits (rb is known once the tables exist:
+    // at most k + 1 when every pattern shared one hash prefix)
+    // (without the parity bit -- then a window without a pattern sends the batch to the general path -- one bit less)
+    int rb_full = x->dense_rb_full;
+    if (x->dense_state != 1) {  // tables not built yet: the largest prefix group is about lambda + 6 sqrt(lambda) patterns
+        const double lambda = k > (uint32_t)DENSE_PREFIX_BITS ? std::ldexp(1.0, (int)k - DENSE_PREFIX_BITS) : 1.0;
+        rb_full = bits_for_value((uint64_t)(2.0 * (lambda + 6.0 * std::sqrt(lambda) + 4.0) + 2.0));
+    }
+    const int code_bits = DENSE_PREFIX_BITS + rb_full - 1;
+    return code_bits + bits_for_value(b.n_prot - 1) + bits_for_value(b.max_len) <= 64;
 }
 
 void sketch_resident_general(ks_index* x);
@@ -876,17 +899,18 @@ void dense_kernel_args(ks_index* x, SketchArgs* a, DenseSketchArgs* d) {
     a->k = x->params.ksize; a->moltype = x->params.moltype; a->max_hash = x->max_hash; a->pid_base = 0;
     a->out_hash = nullptr; a->out_loc = nullptr; a->capacity = x->cap; a->d_count = x->d_count; a->workspace = x->ws;
     a->force_general = 0;
-    d->rank_of_code = x->dense_rank; d->out_keys = x->d_hash; d->pid_bits = x->dense_pid_bits; d->pos_bits = x->dense_pos_bits;
-    d->sorted_hash = x->dense_hash;
+    d->code_of_pattern = x->dense_code; d->out_keys = x->d_hash; d->pid_bits = x->dense_pid_bits; d->pos_bits = x->dense_pos_bits;
+    d->sorted_hash = x->dense_hash; d->group_base = x->dense_group; d->rb = x->dense_rb; d->parity = x->dense_parity;
     d->exception_flag = x->dense_flags + 1;
-    d->handle_exceptions = plan.custom ? 1 : 0;  // the library-sorted variant has no exception handling: general path then
+    // the library-sorted variant and the layout without the parity bit have no exception handling: general path then
+    d->handle_exceptions = plan.custom && x->dense_parity ? 1 : 0;
     d->scatter = DenseScatter{nullptr, nullptr, 0, 0, 0, nullptr};
     if (plan.custom) {
         char* work = (char*)x->b_dense_work.p;
         d->scatter.out = (uint64_t*)(work + plan.off_region1);
         d->scatter.cursor = (uint32_t*)(work + plan.off_cursor1);
         d->scatter.cap = plan.cap1;
-        d->scatter.shift = (int)x->params.ksize + 1 + x->dense_pid_bits + x->dense_pos_bits - plan.l1;
+        d->scatter.shift = DENSE_PREFIX_BITS + x->dense_rb + x->dense_pid_bits + x->dense_pos_bits - plan.l1;
         d->scatter.bits = plan.l1;
         d->scatter.overflow = (uint32_t*)(work + plan.off_overflow);
     }
@@ -899,17 +923,23 @@ bool dense_begin(ks_index* x) {
     const uint32_t k = x->params.ksize;
     Arena* ar = x->arena;
     x->dense_flags = x->b_dense_flags.ensure<uint32_t>(ar, 4);  // [0] table check, [1] unhandled exception, [2] exception keys
-    if (x->dense_state == 0) {
-        x->dense_rank = x->b_dense_rank.ensure<uint32_t>(ar, (size_t)1 << k);
+    if (x->dense_state == 0) {  // first use of the handle: the tables (two steps, one host read in between)
+        x->dense_code = x->b_dense_code.ensure<uint32_t>(ar, (size_t)1 << k);
         x->dense_hash = x->b_dense_hash.ensure<uint64_t>(ar, (size_t)1 << k);
+        x->dense_group = x->b_dense_group.ensure<uint32_t>(ar, ((size_t)1 << DENSE_PREFIX_BITS) + 1);
+        x->dense_por = x->b_dense_por.ensure<uint32_t>(ar, (size_t)1 << k);
         const size_t tb = dense_table_temp_bytes(k);
         void* tmp = x->b_temp.ensure<char>(ar, tb);
-        KS_CUDA(dense_build_tables(k, x->dense_rank, x->dense_hash, tmp, tb, x->dense_flags, x->stream, &x->l_sketch));
-        uint32_t bad = 0;
-        KS_CUDA(cudaMemcpyAsync(&bad, x->dense_flags, 4, cudaMemcpyDeviceToHost, x->stream));
+        KS_CUDA(dense_build_tables(k, x->dense_hash, x->dense_group, x->dense_por, tmp, tb, x->dense_flags, x->stream, &x->l_sketch));
+        uint32_t fl[4] = {0, 0, 0, 0};
+        KS_CUDA(cudaMemcpyAsync(fl, x->dense_flags, 16, cudaMemcpyDeviceToHost, x->stream));
         KS_CUDA(cudaStreamSynchronize(x->stream));
-        x->dense_state = bad ? -1 : 1;
+        x->dense_state = fl[0] ? -1 : 1;
+        x->dense_rb_full = bits_for_value(2ull * fl[3] + 2);  // even codes go up to 2 x (group size), odd ones to 2 x rank + 1
+        if (DENSE_PREFIX_BITS + x->dense_rb_full > 32) x->dense_state = -1;  // (codes are 32-bit table entries)
+        x->dense_table_parity = -1;
     }
+    if (x->hooks.timing) fprintf(stderr, "[ks] dense begin: state %d rb %d\n", x->dense_state, x->dense_rb_full);
     if (x->dense_state < 0) return false;
     const uint64_t n = b.n_windows;
     if (n > MAX_TUPLES) fail(KS_ERR_CAPACITY, "more than 2^31-1 tuples on one shard: shard the proteome over more GPUs");
@@ -920,8 +950,20 @@ bool dense_begin(ks_index* x) {
     x->n_tuples = n;
     // the key sort: hand-written (two scatter levels + a shared-memory sort per bucket) when the input fits its scheme,
     // the library's otherwise (KS_DENSE_SORT=library is a test hook)
+    // layout of the keys: with the parity bit (exception windows handled) when code | protein | position fits 64 bits
+    const int loc_bits = x->dense_pid_bits + x->dense_pos_bits;
+    if (DENSE_PREFIX_BITS + x->dense_rb_full + loc_bits <= 64) x->dense_parity = 1;
+    else if (DENSE_PREFIX_BITS + x->dense_rb_full - 1 + loc_bits <= 64) x->dense_parity = 0;
+    else return false;  // (the estimate of dense_eligible was short)
+    x->dense_rb = x->dense_rb_full - (1 - x->dense_parity);
+    if (x->dense_table_parity != x->dense_parity) {
+        KS_CUDA(dense_build_codes(k, x->dense_hash, x->dense_group, x->dense_por, x->dense_rb, x->dense_parity, x->dense_code, x->stream,
+                                  &x->l_sketch));
+        x->dense_table_parity = x->dense_parity;
+    }
+    const int code_bits = DENSE_PREFIX_BITS + x->dense_rb;
     x->dense_plan = x->hooks.dense_sort_library ? DenseSortPlan()
-                                                : dense_sort_plan(n, (int)k + 1, (int)k + 1 + x->dense_pid_bits + x->dense_pos_bits);
+                                                : dense_sort_plan(n, code_bits, code_bits + x->dense_pid_bits + x->dense_pos_bits, (int)k);
     if (x->dense_plan.custom) {
         char* work = x->b_dense_work.ensure<char>(ar, x->dense_plan.bytes);
         KS_CUDA(cudaMemsetAsync(work + x->dense_plan.off_small, 0, x->dense_plan.small_bytes, x->stream));
@@ -966,21 +1008,30 @@ bool dense_finalize(ks_index* x) {
     // everything the host has to know (flags, counts, overflow) comes back in ONE read at the end.
     int bits = 8;  // directory as on the general path
     while (bits < 24 && (4ull << bits) < n) bits++;
+    if (plan.custom && plan.total > bits) bits = plan.total;  // a directory bucket never spans two sort buckets
+    const uint64_t slack = (plan.custom ? (1ull << plan.total) : 0) + 2;  // segmented layout: a sentinel slot per bucket
     x->dir_bits = bits;
     x->dir_shift = 64 - x->lz - bits;
     x->t_abund = x->b_t_abund.ensure<uint32_t>(ar, P);
     x->t_size = x->b_t_size.ensure<uint32_t>(ar, P);
-    x->keys = x->b_keys.ensure<uint64_t>(ar, n);
-    x->key_grp = x->b_key_grp.ensure<uint32_t>(ar, n + 1);
-    x->grp_start = x->b_grp_start.ensure<uint32_t>(ar, n + 1);
-    x->dir = x->b_dir.ensure<uint32_t>(ar, (1ull << bits) + 1);
+    x->keys = x->b_keys.ensure<uint64_t>(ar, n + slack);
+    x->key_grp = x->b_key_grp.ensure<uint32_t>(ar, n + slack);
+    x->grp_start = x->b_grp_start.ensure<uint32_t>(ar, n + slack);
+    x->dir = x->b_dir.ensure<uint32_t>(ar, (1ull << bits) + slack);
     x->d_counts = x->b_counts.ensure<uint64_t>(ar, 2);
+    int out_dir_sub = DIR_SUB_COMPACT;
+    uint32_t out_seg_nb = 0;
+    const uint32_t* out_seg_start = nullptr;
+    const uint64_t* out_seg_counts = nullptr;
     DenseCsrArgs c;
+    c.dir = x->dir; c.dir_bits = bits;
+    c.out_dir_sub = &out_dir_sub; c.out_seg_nb = &out_seg_nb; c.out_seg_start = &out_seg_start; c.out_seg_counts = &out_seg_counts;
     c.plan = plan; c.work = work;
     c.keys_a = x->d_hash; c.keys_b = plan.custom ? nullptr : x->b_alt_hash.ensure<uint64_t>(ar, n);
     c.n = n; c.n_prot = P; c.k = k;
-    c.rank_bits = (int)k + 1; c.pid_bits = x->dense_pid_bits; c.pos_bits = x->dense_pos_bits;
-    c.offsets = b.offs; c.sorted_hash = x->dense_hash;
+    c.rank_bits = DENSE_PREFIX_BITS + x->dense_rb; c.rb = x->dense_rb; c.parity = x->dense_parity;
+    c.pid_bits = x->dense_pid_bits; c.pos_bits = x->dense_pos_bits;
+    c.offsets = b.offs; c.sorted_hash = x->dense_hash; c.group_base = x->dense_group;
     c.residues = b.res; c.packed = b.packed ? 1 : 0;
     c.skip_flag = x->dense_flags + 1; c.exc_flag = x->dense_flags + 2;
     c.loc = x->d_loc; c.keys = x->keys; c.key_grp = x->key_grp; c.grp_start = x->grp_start;
@@ -991,9 +1042,18 @@ bool dense_finalize(ks_index* x) {
     KS_CUDA(cudaEventRecord(x->ev[EV_SO0], x->stream));
     KS_CUDA(dense_build_csr(c, x->stream, &x->l_sort, &x->l_csr));
     KS_CUDA(cudaEventRecord(x->ev[EV_SO1], x->stream));
-    KS_CUDA(launch_directory(x->keys, x->d_counts, x->dir, x->dir_bits, x->dir_shift, x->stream));
-    x->l_csr += 1;
+    if (out_dir_sub == DIR_SUB_COMPACT) {  // library-sorted keys: compact layout, the directory in its own pass
+        KS_CUDA(launch_directory(x->keys, x->d_counts, x->dir, x->dir_bits, x->dir_shift, x->stream));
+        x->l_csr += 1;
+    }
     KS_CUDA(cudaEventRecord(x->ev[EV_CS1], x->stream));
+    x->seg_start = nullptr; x->seg_counts = nullptr;
+    if (out_dir_sub != DIR_SUB_COMPACT) {  // the bucket tables live in the work buffer: keep a copy for the export calls
+        x->seg_start = x->b_seg_start.ensure<uint32_t>(ar, (size_t)out_seg_nb + 1);
+        x->seg_counts = x->b_seg_counts.ensure<uint64_t>(ar, out_seg_nb);
+        KS_CUDA(cudaMemcpyAsync(x->seg_start, out_seg_start, ((size_t)out_seg_nb + 1) * 4, cudaMemcpyDeviceToDevice, x->stream));
+        KS_CUDA(cudaMemcpyAsync(x->seg_counts, out_seg_counts, (size_t)out_seg_nb * 8, cudaMemcpyDeviceToDevice, x->stream));
+    }
     x->t_sketch = x->t_sort = x->t_csr = true;
     uint64_t* hw = x->h_words + HW_TOTALS;  // pinned: [0..1] counts, [2] produced, [3] flags 1|2, [4] overflow
     hw[4] = 0;
@@ -1003,12 +1063,16 @@ bool dense_finalize(ks_index* x) {
     if (plan.custom) KS_CUDA(cudaMemcpyAsync(hw + 4, work + plan.off_overflow, 4, cudaMemcpyDeviceToHost, x->stream));
     KS_CUDA(cudaStreamSynchronize(x->stream));
     const uint32_t unhandled = (uint32_t)hw[3];  // [0] of the pair: an exception the path does not handle, or a zero hash
+    if (x->hooks.timing)
+        fprintf(stderr, "[ks] dense finalize: n %llu produced %llu unhandled %u exc %u overflow %u U %llu G %llu plan l1 %d l2 %d rb %d\n",
+                (unsigned long long)n, (unsigned long long)hw[2], unhandled, (uint32_t)(hw[3] >> 32), (uint32_t)hw[4],
+                (unsigned long long)hw[0], (unsigned long long)hw[1], plan.l1, plan.l2, x->dense_rb);
     if (unhandled) return false;
     if (hw[2] != n) fail(KS_ERR_CUDA, "internal error: dense path produced an unexpected number of tuples");
     if ((uint32_t)hw[4]) return false;  // heavy repeats of one k-mer overflowed a sort bucket: the general path handles those
     x->U = hw[0]; x->G = hw[1];
-    x->dir_sub = DIR_SUB_COMPACT; x->seg_nb = 0; x->seg_start = nullptr; x->seg_counts = nullptr;
-    x->hash_col_valid = false;  // d_hash holds rank keys: the sorted hash column is rebuilt from the CSR on demand
+    x->dir_sub = out_dir_sub; x->seg_nb = out_seg_nb;
+    x->hash_col_valid = false;  // d_hash holds code keys: the sorted hash column is rebuilt from the CSR on demand
     x->build_path = plan.custom ? 1u : 2u;
     x->pending_dense = false;
     x->finalized = true;

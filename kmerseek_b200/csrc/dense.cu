@@ -10,10 +10,13 @@
 #include <cub/device/device_scan.cuh>
 
 #include <algorithm>
+#include <cmath>
 
 #include "common.cuh"
 #include "dense.cuh"
 #include "dense_scatter.cuh"
+#include "index_build.cuh"
+#include "sketch.cuh"
 
 namespace ks {
 
@@ -109,13 +112,40 @@ __global__ void dense_hash_codes_kernel(uint32_t k, uint64_t* __restrict__ hash,
     code[c] = c;
 }
 
-__global__ void dense_rank_kernel(uint32_t n, const uint64_t* __restrict__ sorted_hash, const uint32_t* __restrict__ code_of_rank,
-                                  uint32_t* __restrict__ rank_of_code, uint32_t* __restrict__ bad) {
+// group_base[p] = first entry of sorted_hash whose top DENSE_PREFIX_BITS bits are >= p (p = 2^16: n)
+__global__ void dense_group_base_kernel(uint32_t n, const uint64_t* __restrict__ sorted_hash, uint32_t* __restrict__ group_base) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p > (1u << DENSE_PREFIX_BITS)) return;
+    if (p == (1u << DENSE_PREFIX_BITS)) { group_base[p] = n; return; }
+    const uint64_t lim = (uint64_t)p << (64 - DENSE_PREFIX_BITS);
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (sorted_hash[mid] < lim) lo = mid + 1; else hi = mid;
+    }
+    group_base[p] = lo;
+}
+
+// flags[0] |= 1 when two patterns share a hash or one hashes to 0; flags[3] = largest rank of a pattern inside its group
+__global__ void dense_check_kernel(uint32_t n, const uint64_t* __restrict__ sorted_hash, const uint32_t* __restrict__ group_base,
+                                   uint32_t* __restrict__ flags) {
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n) return;
     const uint64_t h = sorted_hash[r];
-    if (h == 0 || (r && sorted_hash[r - 1] == h)) atomicOr(bad, 1u);
-    rank_of_code[code_of_rank[r]] = r;
+    if (h == 0 || (r && sorted_hash[r - 1] == h)) atomicOr(flags, 1u);
+    atomicMax(flags + 3, r - group_base[(uint32_t)(h >> (64 - DENSE_PREFIX_BITS))]);
+}
+
+// code_of_pattern[pattern] = prefix << rb | (2 x rank in the prefix group + 1)  (parity layout), or
+//                            prefix << rb | rank in the prefix group              (no room for the parity bit):
+// see DenseSketchArgs (sketch.cuh)
+__global__ void dense_code_kernel(uint32_t n, const uint64_t* __restrict__ sorted_hash, const uint32_t* __restrict__ pattern_of_rank,
+                                  const uint32_t* __restrict__ group_base, int rb, int parity, uint32_t* __restrict__ code_of_pattern) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const uint32_t pfx = (uint32_t)(sorted_hash[r] >> (64 - DENSE_PREFIX_BITS));
+    const uint32_t local = r - group_base[pfx];
+    code_of_pattern[pattern_of_rank[r]] = (pfx << rb) | (parity ? 2u * local + 1u : local);
 }
 
 // every complete window is a tuple (scaled == 1): kept windows per protein; distinct hashes start from the same number
@@ -128,6 +158,12 @@ __global__ void dense_windows_kernel(const uint64_t* __restrict__ offsets, uint3
     const uint32_t w = len >= k ? (uint32_t)(len - k + 1) : 0u;
     t_abund[p] = w;
     t_size[p] = w;
+}
+
+// The pattern hash behind an odd code: prefix group base + rank in the group.
+__device__ __forceinline__ uint64_t hash_of_code(uint32_t code, int rb, int parity, const uint32_t* __restrict__ group_base,
+                                                 const uint64_t* __restrict__ sorted_hash) {
+    return sorted_hash[group_base[code >> rb] + ((code & ((1u << rb) - 1u)) >> parity)];
 }
 
 constexpr int DC_THREADS = 256;
@@ -167,7 +203,8 @@ dense_count_kernel(const uint64_t* __restrict__ keys, uint64_t n, int loc_bits, 
 
 __global__ void __launch_bounds__(DC_THREADS)
 dense_write_kernel(const uint64_t* __restrict__ keys_in, uint64_t n, int loc_bits, int pos_bits, const uint64_t* __restrict__ tile_prefix,
-                   const uint64_t* __restrict__ sorted_hash, uint64_t* __restrict__ loc, uint64_t* __restrict__ keys,
+                   const uint64_t* __restrict__ sorted_hash, const uint32_t* __restrict__ group_base, int rb, int parity,
+                   uint64_t* __restrict__ loc, uint64_t* __restrict__ keys,
                    uint32_t* __restrict__ key_grp, uint32_t* __restrict__ grp_start, uint32_t* __restrict__ t_size,
                    uint64_t* __restrict__ d_counts) {
     __shared__ uint32_t s_k[DC_THREADS / 32], s_g[DC_THREADS / 32];
@@ -215,7 +252,7 @@ dense_write_kernel(const uint64_t* __restrict__ keys_in, uint64_t n, int loc_bit
         if ((bg[r] >> lane) & 1u) grp_start[g] = (uint32_t)i;
         if ((bk[r] >> lane) & 1u) {
             const uint32_t u = rk + __popc(bk[r] & lt);
-            keys[u] = sorted_hash[(key[r] >> loc_bits) >> 1];  // rank' = 2 rank + 1 (no exception keys on this path)
+            keys[u] = hash_of_code((uint32_t)(key[r] >> loc_bits), rb, parity, group_base, sorted_hash);  // (no exception keys here)
             key_grp[u] = g;
         }
         rk += __popc(bk[r]);
@@ -293,17 +330,20 @@ struct DenseBucketArgs {
     const uint32_t* cursor2;   // keys per bucket
     const uint32_t* bstart;    // tuple offset of every bucket
     uint32_t nb;
+    int bucket_bits;           // log2(nb): the buckets are the top bucket_bits (<= DENSE_PREFIX_BITS) bits of the hash
     int rem_bits;              // key bits below the bucket bits (<= 64 - DB_SLOT_BITS)
     int loc_bits, pos_bits;
+    int rb, parity;            // code bits below the hash prefix; its lowest bit is the pattern / exception parity (DenseSketchArgs)
     const uint64_t* sorted_hash;
-    uint64_t* status;          // look-back words, zeroed
-    uint32_t* ticket;
+    const uint32_t* group_base;
     uint64_t* loc;
-    uint64_t* keys;
+    uint64_t* keys;            // segmented layout (index_build.cuh): bucket b's keys / groups at bstart[b] + b + i
     uint32_t *key_grp, *grp_start, *t_size;
-    uint64_t* d_counts;
-    uint64_t n;
-    // exception keys (even rank'): their hash is recomputed from the residues
+    uint64_t* counts;          // [nb] keys | groups << 32 of every bucket
+    unsigned long long* d_counts;  // [0] unique keys, [1] groups: accumulated (zeroed per build)
+    uint32_t* dir;             // every bucket owns 2^dir_sub + 1 entries
+    int dir_sub, dir_shift;
+    // exception keys (even codes): their hash is recomputed from the residues
     const uint8_t* residues;
     const uint64_t* offsets;
     int packed;
@@ -312,20 +352,20 @@ struct DenseBucketArgs {
     const uint32_t* skip_flag; // device: != 0 when the build is void (unhandled exception / table unusable): nothing to do
 };
 
-// One CTA per final bucket (<= 4096 keys, all distinct, final order = numeric order), persistent CTAs that take buckets
-// by ticket:
+// One CTA per final bucket (<= 4096 keys, all distinct, final order = numeric order); buckets are independent:
 //   1. counting pass over the item's top 13 bits (shared-memory atomics on packed 16-bit counters), scan, scatter: the
-//      bucket is then ordered at bin granularity -- a bin is (rank, 1/32 of the proteins) on C2 and holds 0-3 keys.  The
+//      bucket is then ordered at bin granularity -- a bin is (code, 1/32 of the proteins) on C2 and holds 0-3 keys.  The
 //      slot a key drew in its bin rides in the item's low bits (below every key bit), not in a register;
-//   2. every key finds its final slot by counting the smaller keys of its own bin (two barriers, no rounds); a bin
-//      of more than DB_BIN_SORT_MAX keys (a k-mer repeated in one stretch of proteins) or exception keys (which can sit
-//      in a later bin than a larger key) send the whole bucket through odd-even transposition rounds instead;
-//   3. heads from the rank / protein fields; the aggregate (keys, groups) is published for the look-back BEFORE the
-//      postings are stored, the prefix collected after: the stores hide part of the wait for the predecessors;
-//   4. keys / key_grp / grp_start from shared memory; the pattern hashes of the bucket's rank range were preloaded with one
-//      coalesced read at the top (they are consecutive entries of sorted_hash).
+//   2. odd-even transposition rounds until nothing moves (2-3 rounds; measured against counting the smaller keys of the
+//      own bin, KS_DB_RANKSORT: 2.79 ms vs 2.99 ms on C2);
+//   3. heads from the code / protein fields, postings out in final order;
+//   4. keys / key_grp / grp_start in the SEGMENTED layout (index_build.cuh): positions bstart[b] + b + i, known without
+//      any other bucket -- no look-back chain, no ticket (round 1 chained the buckets' totals: 19-23 % of the stall
+//      samples sat behind it) -- and the bucket's own directory entries.  The pattern hashes of the bucket's prefix range
+//      are consecutive entries of sorted_hash, preloaded with one coalesced read at the top.
 // EXC: the batch holds exception keys.  Both instantiations are launched back to back; the device flag decides which one
-// does the work (the other's CTAs exit at once), so that the host never waits for the rank kernel's flags.
+// does the work (the other's CTAs exit at once), so that the host never waits for the rank kernel's flags.  The rare one
+// runs a grid-stride loop over the buckets so that its idle launch costs a few hundred CTAs.
 template <bool EXC>
 __global__ void __launch_bounds__(DB_THREADS, DB_CTAS)
 dense_bucket_kernel(DenseBucketArgs a) {
@@ -333,66 +373,56 @@ dense_bucket_kernel(DenseBucketArgs a) {
     uint64_t* B = reinterpret_cast<uint64_t*>(smem_raw);      // [DB_CAP] items: the key's bits below the bucket bits, left-aligned
     uint32_t* cnt = reinterpret_cast<uint32_t*>(B + DB_CAP);  // [DB_BINS / 2] words of two 16-bit bin counters, then offsets
     uint64_t* s_hash = reinterpret_cast<uint64_t*>(cnt + DB_BINS / 2);  // [DB_HASH_SLICE]
+    uint64_t* s_keyh = reinterpret_cast<uint64_t*>(cnt);      // [DB_BINS / 4] hashes of the bucket's keys (after the sort)
+    constexpr uint32_t KEYH_CAP = DB_BINS / 4;
     const uint16_t* off16 = reinterpret_cast<const uint16_t*>(cnt);
     __shared__ uint32_t s_wsum[DB_WARPS];
     __shared__ uint32_t s_cw[DB_ROWS * DB_WARPS];
-    __shared__ uint64_t s_base;
-    __shared__ uint32_t s_bucket;
+    __shared__ uint32_t s_tk, s_tg;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t lt = (1u << lane) - 1u;
-    if (*a.skip_flag != 0) {  // the build is void (the host takes the general path): leave defined totals behind
-        if (!EXC && blockIdx.x == 0 && tid == 0) { a.d_counts[0] = 0; a.d_counts[1] = 0; }
-        return;
-    }
+    if (*a.skip_flag != 0) return;  // the build is void (the host takes the general path)
     if ((*a.exc_flag != 0) != EXC) return;  // (uniform over the grid) the other instantiation does the work
     const int up = 64 - a.rem_bits;  // item = key << up: the bucket bits fall off the top
-    const int rrb = a.rem_bits - a.loc_bits;  // rank' bits below the bucket bits (the lowest is the parity)
-    // bin = the item's top 13 bits with the parity bit of rank' squeezed out when it lies among them (it is 1 for every
+    const int rrb = a.rem_bits - a.loc_bits;  // code bits below the bucket bits (the lowest is the parity)
+    // bin = the item's top 13 bits with the parity bit of the code squeezed out when it lies among them (it is 1 for every
     // pattern key and would leave half of the bins empty).  An exception key (parity 0) can then land in a later bin than a
-    // larger key: the odd-even rounds of the EXC instantiation run until the whole bucket is in order.
-    const int pb = up + a.loc_bits;  // bit of the item that holds the parity of rank'
-    const bool squeeze = pb >= 64 - DB_BIN_BITS && pb < 63;
+    // larger key: the odd-even rounds run until the whole bucket is in order.
+    const int pb = up + a.loc_bits;  // bit of the item that holds the parity of the code
+    const bool squeeze = a.parity && pb >= 64 - DB_BIN_BITS && pb < 63;
     const int n_low = squeeze ? DB_BIN_BITS - (63 - pb) : 0;  // bin bits taken from below the parity bit
     auto bin_of = [&](uint64_t it) -> uint32_t {
         if (!squeeze) return (uint32_t)(it >> (64 - DB_BIN_BITS));
         return (uint32_t)(((it >> (pb + 1)) << n_low) | ((it >> (pb - n_low)) & ((1ull << n_low) - 1ull)));
     };
-    const int rank_sh = up + a.loc_bits, grp_sh = up + a.pos_bits;  // item >> rank_sh: rank bits below the bucket bits
-    auto shr = [](uint64_t v, int sh) -> uint64_t { return sh >= 64 ? 0ull : v >> sh; };  // no rank bits may be left
+    const int rank_sh = up + a.loc_bits, grp_sh = up + a.pos_bits;  // item >> rank_sh: code bits below the bucket bits
     const uint64_t pos_mask = (1ull << a.pos_bits) - 1ull, pid_mask = (1ull << (a.loc_bits - a.pos_bits)) - 1ull;
-    const bool hash_slice = DB_HASH_SLICE > 0 && rrb >= 1 && rrb <= 10;  // at most 512 pattern ranks under a bucket
     constexpr uint64_t SLOT_MASK = (1ull << DB_SLOT_BITS) - 1ull;
-    // persistent CTAs: buckets are taken by ticket, so a bucket's predecessors have always started (look-back)
-    // EXC (the rare instantiation): persistent CTAs, so that its launch costs next to nothing when it has no work;
-    // the common instantiation runs one CTA per bucket (measured: 2.96 ms against 3.20 ms persistent on C2)
-    for (int pass = 0; EXC || pass < 1; pass++) {
-    __syncthreads();  // the previous bucket's shared memory is no longer read
-    if (tid == 0) s_bucket = atomicAdd(a.ticket, 1u);
+    const uint32_t dir_n = 1u << a.dir_sub;  // directory entries of a bucket (+ its end sentinel)
+    auto dir_local = [&](uint64_t h) -> int32_t { return (int32_t)((uint32_t)(h >> a.dir_shift) & (dir_n - 1u)); };
+    for (uint32_t b = blockIdx.x; b < a.nb; b += gridDim.x) {
+    __syncthreads();  // (grid-stride instantiation) the previous bucket's shared memory is no longer read
     for (uint32_t i = tid; i < DB_BINS / 8; i += DB_THREADS) reinterpret_cast<uint4*>(cnt)[i] = make_uint4(0, 0, 0, 0);
-    __syncthreads();
-    const uint32_t b = s_bucket;
-    if (b >= a.nb) break;
     const uint64_t* src = a.region2 + (uint64_t)b * DB_CAP;
     uint64_t item[DB_ROWS];
     // the first half of the rows is read before the bucket's size is known (a bucket region is DB_CAP keys of allocated
     // memory; what lies past the size is not used): the size and the keys come back in one round trip instead of two
-#ifdef KS_DB_NOSPEC
-    constexpr int SPEC_ROWS = 0;
-#else
     constexpr int SPEC_ROWS = DB_ROWS / 2;
-#endif
 #pragma unroll
     for (int r = 0; r < SPEC_ROWS; r++) item[r] = src[r * DB_THREADS + tid];
     const uint32_t m = min(a.cursor2[b], (uint32_t)DB_CAP);
-    if (hash_slice && tid < (1u << (rrb - 1))) s_hash[tid] = a.sorted_hash[((uint64_t)b << (rrb - 1)) + tid];
-    if (m == 0) {  // pass the running totals on; the last bucket writes them out
-        if (warp == 0) {
-            const uint64_t excl = scan_lookback(a.status, b, 0);
-            if (b == a.nb - 1 && lane == 0) {
-                const uint64_t U = excl & 0x7fffffffu, G = excl >> 31;
-                a.d_counts[0] = U; a.d_counts[1] = G; a.key_grp[U] = (uint32_t)G; a.grp_start[G] = (uint32_t)a.n;
-            }
-        }
+    const uint32_t s0 = a.bstart[b];
+    const uint32_t kb = s0 + b;  // first key / group position of this bucket's segment
+    uint32_t* dir_b = a.dir + (uint64_t)b * (dir_n + 1u);
+    // the pattern hashes of this bucket: the prefix groups [b << (16 - bucket_bits), (b + 1) << (16 - bucket_bits))
+    const uint32_t pshift = DENSE_PREFIX_BITS - a.bucket_bits;
+    const uint32_t slice_base = a.group_base[b << pshift];
+    const uint32_t slice_n = a.group_base[(b + 1) << pshift] - slice_base;
+    const bool hash_slice = DB_HASH_SLICE > 0 && slice_n <= (uint32_t)DB_HASH_SLICE;
+    if (hash_slice) for (uint32_t i = tid; i < slice_n; i += DB_THREADS) s_hash[i] = a.sorted_hash[slice_base + i];
+    if (m == 0) {  // an empty key / group segment (the two sentinels), directory entries that all point at it
+        if (tid == 0) { a.key_grp[kb] = kb; a.grp_start[kb] = s0; a.counts[b] = 0; }
+        for (uint32_t x = tid; x <= dir_n; x += DB_THREADS) dir_b[x] = kb;
         continue;
     }
 #pragma unroll
@@ -401,6 +431,7 @@ dense_bucket_kernel(DenseBucketArgs a) {
         const uint32_t j = r * DB_THREADS + tid;
         if (j < m) item[r] = src[j];
     }
+    __syncthreads();  // the counters are zero
 #pragma unroll
     for (int r = 0; r < DB_ROWS; r++) {
         const uint32_t j = r * DB_THREADS + tid;
@@ -459,11 +490,12 @@ dense_bucket_kernel(DenseBucketArgs a) {
 #ifdef KS_DB_RANKSORT
     const int use_rounds = __syncthreads_or((EXC || big_bin) ? 1 : 0);
 #else
-    const int use_rounds = __syncthreads_or(1);  // measured on C2: the rounds 2.79 ms, in-bin counting 2.99 ms
+    (void)big_bin;
+    const int use_rounds = __syncthreads_or(1);
 #endif
     if (!use_rounds) {
         // every key finds its place inside its bin by counting the bin's smaller keys (keys are distinct above the slot
-        // bits; a bin holds a handful): all lanes busy, a fixed number of barriers, no rounds
+        // bits; a bin holds a handful)
 #pragma unroll
         for (int r = 0; r < DB_ROWS; r++) {
             const uint32_t j = r * DB_THREADS + tid;
@@ -503,14 +535,11 @@ dense_bucket_kernel(DenseBucketArgs a) {
             again = __syncthreads_or(sw);
         } while (again);
     }
-    // heads: the bucket bits cover at most the rank bits, so a bucket's first key starts a new hash
-    const uint32_t s0 = a.bstart[b];
-    // Exception keys (even rank': a window with a residue of neither class, hashed from its bytes, ranked between two
-    // patterns).  Two different exception hashes can fall between the same two patterns and then share a rank': the
-    // run of that rank' is put in (hash, protein, position) order by the thread that owns its first key, and the head
-    // tests below compare recomputed hashes.  rank' parity is bit loc_bits of the key, i.e. bit rank_sh of the item --
-    // unless no rank bit is left below the bucket bits, in which case the bucket index carries it.
-    auto is_exc = [&](uint64_t it) -> bool { return rank_sh < 64 ? ((it >> rank_sh) & 1ull) == 0ull : (b & 1u) == 0u; };
+    // Exception keys (even code: a window with a residue of neither class, hashed from its bytes, placed between two
+    // patterns of its prefix group).  Two different exception hashes can fall between the same two patterns and then share a
+    // code: the run of that code is put in (hash, protein, position) order by the thread that owns its first key, and the
+    // head tests below compare recomputed hashes.  (rrb >= rb >= 2: the parity bit is always below the bucket bits.)
+    auto is_exc = [&](uint64_t it) -> bool { return ((it >> rank_sh) & 1ull) == 0ull; };
     auto hash_of = [&](uint64_t it) -> uint64_t {
         const uint64_t low = it >> up;
         const uint32_t pid = (uint32_t)((low >> a.pos_bits) & pid_mask);
@@ -519,9 +548,9 @@ dense_bucket_kernel(DenseBucketArgs a) {
     if (EXC) {
         for (uint32_t j = tid; j < m; j += DB_THREADS) {
             const uint64_t it = B[j];
-            if (!is_exc(it) || (j && shr(B[j - 1], rank_sh) == shr(it, rank_sh))) continue;  // not the first key of a run
+            if (!is_exc(it) || (j && (B[j - 1] >> rank_sh) == (it >> rank_sh))) continue;  // not the first key of a run
             uint32_t e = j + 1;
-            while (e < m && shr(B[e], rank_sh) == shr(it, rank_sh)) e++;
+            while (e < m && (B[e] >> rank_sh) == (it >> rank_sh)) e++;
             if (e - j < 2) continue;
             const uint64_t h0 = hash_of(it);
             bool mixed = false;
@@ -550,9 +579,13 @@ dense_bucket_kernel(DenseBucketArgs a) {
             if (j < m) {
                 const uint64_t it = B[j];
                 const uint64_t pv = j ? B[j - 1] : ~it;
-                hk = j == 0 || shr(it, rank_sh) != shr(pv, rank_sh);
-                if (EXC && !hk && is_exc(it)) hk = hash_of(it) != hash_of(pv);  // same rank', maybe another hash
+                hk = j == 0 || (it >> rank_sh) != (pv >> rank_sh);
+                if (EXC && !hk && is_exc(it)) hk = hash_of(it) != hash_of(pv);  // same code, maybe another hash
                 hg = hk || (it >> grp_sh) != (pv >> grp_sh);
+                const uint64_t low = it >> up;  // the key's bits below the bucket bits: code low bits | protein | position
+                const uint32_t pid = (uint32_t)((low >> a.pos_bits) & pid_mask);
+                a.loc[s0 + j] = ((uint64_t)pid << 32) | (low & pos_mask);
+                if (!hg) atomicSub(&a.t_size[pid], 1u);  // the hash again in the same protein: one distinct hash fewer
             }
             flags |= ((hk ? 1u : 0u) | (hg ? 2u : 0u)) << (2 * r);
             const uint32_t ck = __popc(__ballot_sync(0xffffffffu, hk)), cg = __popc(__ballot_sync(0xffffffffu, hg));
@@ -562,7 +595,6 @@ dense_bucket_kernel(DenseBucketArgs a) {
         }
     }
     __syncthreads();
-    uint64_t agg = 0;
     if (warp == 0) {
         uint32_t v[4], local = 0;
 #pragma unroll
@@ -577,41 +609,17 @@ dense_bucket_kernel(DenseBucketArgs a) {
 #pragma unroll
         for (int i = 0; i < 4; i++) { s_cw[lane * 4 + i] = run; run += v[i]; }
         const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
-        agg = (uint64_t)(tot & 0xffffu) | ((uint64_t)(tot >> 16) << 31);
-#ifndef KS_DB_FUSED_LOOKBACK
-        scan_publish(a.status, b, agg);  // successors can go on; our own prefix is collected after the stores below
-#endif
-    }
-    // the postings go out in final order: this is where part of the wait for the predecessors is hidden
-#pragma unroll
-    for (int r = 0; r < DB_ROWS; r++) {
-        const uint32_t j = r * DB_THREADS + tid;
-        if (r * DB_THREADS >= m) break;
-        if (j < m) {
-            const uint64_t low = B[j] >> up;  // the key's bits below the bucket bits: (rank low bits |) protein | position
-            const uint32_t pid = (uint32_t)((low >> a.pos_bits) & pid_mask);
-            a.loc[s0 + j] = ((uint64_t)pid << 32) | (low & pos_mask);
-            if (!((flags >> (2 * r)) & 2u)) atomicSub(&a.t_size[pid], 1u);  // the hash again in the same protein
-        }
-    }
-    if (warp == 0) {
-#ifdef KS_DB_FUSED_LOOKBACK
-        const uint64_t excl = scan_lookback(a.status, b, agg);
-#else
-        const uint64_t excl = scan_collect(a.status, b, agg);
-#endif
         if (lane == 0) {
-            s_base = excl;
-            if (b == a.nb - 1) {
-                const uint64_t incl2 = excl + agg;
-                const uint64_t U = incl2 & 0x7fffffffu, G = incl2 >> 31;
-                a.d_counts[0] = U; a.d_counts[1] = G; a.key_grp[U] = (uint32_t)G; a.grp_start[G] = (uint32_t)a.n;
-            }
+            const uint32_t tk = tot & 0xffffu, tg = tot >> 16;
+            s_tk = tk; s_tg = tg;
+            a.counts[b] = (uint64_t)tk | ((uint64_t)tg << 32);
+            atomicAdd(a.d_counts, (unsigned long long)tk);
+            atomicAdd(a.d_counts + 1, (unsigned long long)tg);
         }
     }
     __syncthreads();
-    const uint32_t base_k = (uint32_t)(s_base & 0x7fffffffu), base_g = (uint32_t)(s_base >> 31);
-    const uint64_t rank_top = (uint64_t)b << rrb;  // the rank bits that are the bucket index
+    const uint32_t tk = s_tk, tg = s_tg;
+    const uint32_t code_top = b << rrb;  // the code bits that are the bucket index
 #pragma unroll
     for (int r = 0; r < DB_ROWS; r++) {
         if (r * DB_THREADS < m) {  // uniform
@@ -619,21 +627,40 @@ dense_bucket_kernel(DenseBucketArgs a) {
             const bool hk = (flags >> (2 * r)) & 1u, hg = (flags >> (2 * r)) & 2u;
             const uint32_t bk = __ballot_sync(0xffffffffu, hk), bg = __ballot_sync(0xffffffffu, hg);
             const uint32_t pre = s_cw[r * DB_WARPS + warp];
-            const uint32_t g = base_g + (pre >> 16) + __popc(bg & lt);
+            const uint32_t g = kb + (pre >> 16) + __popc(bg & lt);
             if (hg) a.grp_start[g] = s0 + j;
             if (hk) {
-                const uint32_t u = base_k + (pre & 0xffffu) + __popc(bk & lt);
-                const uint64_t low_rank = shr(B[j], rank_sh);
+                const uint32_t ul = (pre & 0xffffu) + __popc(bk & lt);
+                const uint64_t it = B[j];
                 uint64_t h;
-                if (EXC && is_exc(B[j])) h = hash_of(B[j]);
-                else if (hash_slice) h = s_hash[low_rank >> 1];
-                else h = a.sorted_hash[(rank_top | low_rank) >> 1];
-                a.keys[u] = h;
-                a.key_grp[u] = g;
+                if (EXC && is_exc(it)) {
+                    h = hash_of(it);
+                } else {
+                    const uint32_t code = code_top | (uint32_t)(it >> rank_sh);
+                    const uint32_t idx = a.group_base[code >> a.rb] + ((code & ((1u << a.rb) - 1u)) >> a.parity);
+                    h = hash_slice ? s_hash[idx - slice_base] : a.sorted_hash[idx];
+                }
+                a.keys[kb + ul] = h;
+                a.key_grp[kb + ul] = g;
+                if (tk <= KEYH_CAP) s_keyh[ul] = h;  // (the bin offsets are no longer needed)
+            }
+            if (j == m - 1) {  // the segment's sentinels
+                a.key_grp[kb + tk] = kb + tg;
+                a.grp_start[kb + tg] = s0 + m;
             }
         }
     }
-    }  // bucket loop
+    __syncthreads();
+    // the bucket's directory entries: key i owns the entries (local entry of key i - 1, local entry of key i]
+    for (uint32_t i = tid; i < tk; i += DB_THREADS) {
+        const uint64_t h = tk <= KEYH_CAP ? s_keyh[i] : a.keys[kb + i];
+        const int32_t x1 = dir_local(h);
+        int32_t x0 = -1;
+        if (i) x0 = dir_local(tk <= KEYH_CAP ? s_keyh[i - 1] : a.keys[kb + i - 1]);
+        for (int32_t x = x0 + 1; x <= x1; x++) dir_b[x] = kb + i;
+        if (i == tk - 1) for (int32_t x = x1 + 1; x <= (int32_t)dir_n; x++) dir_b[x] = kb + tk;  // after the last key, the end
+    }
+    }  // buckets
 }
 
 size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
@@ -665,30 +692,52 @@ size_t dense_table_temp_bytes(uint32_t k) {
     return align256(n * 8) + 2 * align256(n * 4) + table_sort_bytes((uint32_t)n) + 256;
 }
 
-cudaError_t dense_build_tables(uint32_t k, uint32_t* rank_of_code, uint64_t* sorted_hash, void* temp, size_t temp_bytes,
-                               uint32_t* d_bad, cudaStream_t stream, uint64_t* n_launches) {
 #define KS_TRY(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return e_; } while (0)
+
+// Step 1: hash all 2^k patterns, sort the hashes, prefix-group bases, checks.  d_flags (u32[4], [0] and [3] zeroed here):
+// [0] != 0 when two patterns share a hash or one hashes to 0, [3] = largest rank of a pattern inside its prefix group
+// (the caller reads both and derives the code width `rb` for step 2).  Enqueued on `stream`; no synchronisation.
+cudaError_t dense_build_tables(uint32_t k, uint64_t* sorted_hash, uint32_t* group_base, uint32_t* pattern_of_rank, void* temp,
+                               size_t temp_bytes, uint32_t* d_flags, cudaStream_t stream, uint64_t* n_launches) {
     const uint32_t n = 1u << k;
     if (temp_bytes < dense_table_temp_bytes(k)) return cudaErrorInvalidValue;
     char* p = (char*)temp;
     uint64_t* hash = (uint64_t*)p; p += align256((size_t)n * 8);
     uint32_t* code = (uint32_t*)p; p += align256((size_t)n * 4);
-    uint32_t* code_of_rank = (uint32_t*)p; p += align256((size_t)n * 4);
     size_t sort_bytes = table_sort_bytes(n);
-    KS_TRY(cudaMemsetAsync(d_bad, 0, 4, stream));
+    KS_TRY(cudaMemsetAsync(d_flags, 0, 4, stream));
+    KS_TRY(cudaMemsetAsync(d_flags + 3, 0, 4, stream));
     dense_hash_codes_kernel<<<(n + 255) / 256, 256, 0, stream>>>(k, hash, code);
     KS_TRY(cudaGetLastError());
-    KS_TRY(cub::DeviceRadixSort::SortPairs(p, sort_bytes, hash, sorted_hash, code, code_of_rank, (int64_t)n, 0, 64, stream));
-    dense_rank_kernel<<<(n + 255) / 256, 256, 0, stream>>>(n, sorted_hash, code_of_rank, rank_of_code, d_bad);
-    if (n_launches) *n_launches += 2 + 10;
+    KS_TRY(cub::DeviceRadixSort::SortPairs(p, sort_bytes, hash, sorted_hash, code, pattern_of_rank, (int64_t)n, 0, 64, stream));
+    dense_group_base_kernel<<<((1u << DENSE_PREFIX_BITS) + 1 + 255) / 256, 256, 0, stream>>>(n, sorted_hash, group_base);
+    dense_check_kernel<<<(n + 255) / 256, 256, 0, stream>>>(n, sorted_hash, group_base, d_flags);
+    if (n_launches) *n_launches += 3 + 10;
     return cudaGetLastError();
 }
 
-DenseSortPlan dense_sort_plan(uint64_t n, int rank_bits, int key_bits) {
+// Step 2: the pattern -> code table for the code width and layout the host derived (again whenever the layout changes).
+cudaError_t dense_build_codes(uint32_t k, const uint64_t* sorted_hash, const uint32_t* group_base, const uint32_t* pattern_of_rank,
+                              int rb, int parity, uint32_t* code_of_pattern, cudaStream_t stream, uint64_t* n_launches) {
+    const uint32_t n = 1u << k;
+    dense_code_kernel<<<(n + 255) / 256, 256, 0, stream>>>(n, sorted_hash, pattern_of_rank, group_base, rb, parity, code_of_pattern);
+    if (n_launches) *n_launches += 1;
+    return cudaGetLastError();
+}
+
+DenseSortPlan dense_sort_plan(uint64_t n, int rank_bits, int key_bits, int k) {
     DenseSortPlan p;
     int total = 0;
     while (total <= 2 * DS_MAX_BITS && (n >> total) > 3072) total++;
-    if (total > 2 * DS_MAX_BITS || total > rank_bits || n == 0) return p;  // custom == 0
+    // a bucket is a hash-prefix range: it holds Poisson(2^k / 2^total) patterns of ~n / 2^k keys each.  With few patterns per
+    // bucket the loads are uneven: take more buckets until mean + 6 sigma fits one (or the prefix bits run out: a bucket
+    // that overflows sends the batch to the general path)
+    while (total < DENSE_PREFIX_BITS) {
+        const double lambda = std::ldexp(1.0, k - total), per_pattern = (double)n / std::ldexp(1.0, k);
+        if (lambda * per_pattern + 6.0 * per_pattern * std::sqrt(lambda > 1.0 ? lambda : 1.0) <= (double)DB_CAP) break;
+        total++;
+    }
+    if (total > 2 * DS_MAX_BITS || total > DENSE_PREFIX_BITS || total > rank_bits || n == 0) return p;  // custom == 0
     if (key_bits - total > 64 - DB_SLOT_BITS) return p;  // the bucket kernel keeps a key's slot below its bits
     p.custom = 1;
     p.total = total;
@@ -702,12 +751,11 @@ DenseSortPlan dense_sort_plan(uint64_t n, int rank_bits, int key_bits) {
     p.off_small = off;
     p.off_cursor1 = take(((size_t)1 << p.l1) * 4);
     p.off_cursor2 = p.l2 ? take(((size_t)1 << total) * 4) : p.off_cursor1;
-    p.off_status = take(((size_t)1 << total) * 8);
-    p.off_ticket = take(8);
     p.off_overflow = take(8);
     p.small_bytes = off - p.off_small;  // everything above is zeroed before a build
     p.off_chunks = take(((size_t)1 << DS_MAX_BITS) * 4 + 4);
     p.off_bstart = take((((size_t)1 << total) + 1) * 4);
+    p.off_counts = take(((size_t)1 << total) * 8);
     p.bytes = off;
     return p;
 }
@@ -718,6 +766,8 @@ size_t dense_csr_temp_bytes(uint64_t n) {
 }
 
 cudaError_t dense_build_csr(const DenseCsrArgs& a, cudaStream_t stream, uint64_t* sort_launches, uint64_t* csr_launches) {
+    if (a.out_dir_sub) *a.out_dir_sub = DIR_SUB_COMPACT;
+    if (a.out_seg_nb) *a.out_seg_nb = 0;
     const uint64_t n = a.n;
     const int loc_bits = a.pid_bits + a.pos_bits;
     if (a.n_prot) {
@@ -755,21 +805,28 @@ cudaError_t dense_build_csr(const DenseCsrArgs& a, cudaStream_t stream, uint64_t
         }
         dense_bucket_offsets_kernel<<<1, 1024, 0, stream>>>(cursor2, nb, (uint32_t)DB_CAP, bstart);
         if (a.ev_sorted) KS_TRY(cudaEventRecord(a.ev_sorted, stream));
+        if (a.dir_bits < pl.total) return cudaErrorInvalidValue;  // (the caller sizes the directory from the plan)
+        KS_TRY(cudaMemsetAsync(a.d_counts, 0, 16, stream));
         DenseBucketArgs ba;
-        ba.region2 = region2; ba.cursor2 = cursor2; ba.bstart = bstart; ba.nb = nb;
-        ba.rem_bits = total_bits - pl.total; ba.loc_bits = loc_bits; ba.pos_bits = a.pos_bits; ba.sorted_hash = a.sorted_hash;
-        ba.status = (uint64_t*)(w + pl.off_status); ba.ticket = (uint32_t*)(w + pl.off_ticket);
+        ba.region2 = region2; ba.cursor2 = cursor2; ba.bstart = bstart; ba.nb = nb; ba.bucket_bits = pl.total;
+        ba.rem_bits = total_bits - pl.total; ba.loc_bits = loc_bits; ba.pos_bits = a.pos_bits; ba.rb = a.rb; ba.parity = a.parity;
+        ba.sorted_hash = a.sorted_hash; ba.group_base = a.group_base;
         ba.loc = a.loc; ba.keys = a.keys; ba.key_grp = a.key_grp; ba.grp_start = a.grp_start; ba.t_size = a.t_size;
-        ba.d_counts = a.d_counts; ba.n = n;
+        ba.counts = (uint64_t*)(w + pl.off_counts); ba.d_counts = (unsigned long long*)a.d_counts;
+        ba.dir = a.dir; ba.dir_sub = a.dir_bits - pl.total; ba.dir_shift = 64 - a.dir_bits;
         ba.residues = a.residues; ba.offsets = a.offsets; ba.packed = a.packed; ba.k = a.k;
         ba.exc_flag = a.exc_flag; ba.skip_flag = a.skip_flag;
         KS_TRY(cudaFuncSetAttribute(dense_bucket_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DB_SMEM));
         KS_TRY(cudaFuncSetAttribute(dense_bucket_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DB_SMEM));
         // both instantiations, back to back: the rank kernel's device flag picks the one that works -- the host does not
-        // wait for the flag (the exception instantiation runs persistent CTAs: idle, it is a few hundred CTAs that exit)
+        // wait for the flag (the exception instantiation strides over the buckets: idle, it is a few hundred CTAs that exit)
         dense_bucket_kernel<false><<<nb, DB_THREADS, DB_SMEM, stream>>>(ba);
         dense_bucket_kernel<true><<<std::min<unsigned>(nb, 148u * DB_CTAS), DB_THREADS, DB_SMEM, stream>>>(ba);
         if (sort_launches) *sort_launches += 3;
+        if (a.out_dir_sub) *a.out_dir_sub = ba.dir_sub;
+        if (a.out_seg_nb) *a.out_seg_nb = nb;
+        if (a.out_seg_start) *a.out_seg_start = bstart;
+        if (a.out_seg_counts) *a.out_seg_counts = ba.counts;
         return cudaGetLastError();
     }
     char* p = (char*)a.temp;
@@ -790,9 +847,11 @@ cudaError_t dense_build_csr(const DenseCsrArgs& a, cudaStream_t stream, uint64_t
     dense_count_kernel<<<(unsigned)nt, DC_THREADS, 0, stream>>>(sorted, n, loc_bits, a.pos_bits, tile_counts);
     KS_TRY(cudaGetLastError());
     KS_TRY(cub::DeviceScan::ExclusiveSum(scan_temp, sbytes, tile_counts, tile_prefix, (int64_t)(nt + 1), stream));
-    dense_write_kernel<<<(unsigned)nt, DC_THREADS, 0, stream>>>(sorted, n, loc_bits, a.pos_bits, tile_prefix, a.sorted_hash, a.loc,
-                                                                a.keys, a.key_grp, a.grp_start, a.t_size, a.d_counts);
+    dense_write_kernel<<<(unsigned)nt, DC_THREADS, 0, stream>>>(sorted, n, loc_bits, a.pos_bits, tile_prefix, a.sorted_hash, a.group_base,
+                                                                a.rb, a.parity, a.loc, a.keys, a.key_grp, a.grp_start, a.t_size, a.d_counts);
     if (csr_launches) *csr_launches += 4;
+    if (a.out_dir_sub) *a.out_dir_sub = DIR_SUB_COMPACT;  // compact layout: the caller builds the directory (launch_directory)
+    if (a.out_seg_nb) *a.out_seg_nb = 0;
     return cudaGetLastError();
 #undef KS_TRY
 }

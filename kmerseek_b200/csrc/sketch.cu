@@ -738,7 +738,7 @@ sketch_dense_kernel(SketchArgs a, Lut256 lut, const uint32_t* __restrict__ tile_
             locp[j] = ((uint64_t)p << d.pos_bits) | (uint64_t)(g0_lo + w - pstart_lo);
         }
 #pragma unroll
-        for (int j = 0; j < 4; j++) rank[j] = 2u * __ldg(d.rank_of_code + code[j]) + 1u;
+        for (int j = 0; j < 4; j++) rank[j] = __ldg(d.code_of_pattern + code[j]);
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             if (is_exc[j]) {  // rare: hash the translated bytes, place the hash among the patterns' hashes
@@ -752,13 +752,15 @@ sketch_dense_kernel(SketchArgs a, Lut256 lut, const uint32_t* __restrict__ tile_
                 for (int i = 0; i < KW; i++) bw[i] = j == 0 ? x[i] : __funnelshift_r(x[i], x[i + 1], 8 * j);
                 if (K % 4) bw[KW - 1] &= (1u << (8 * (K % 4))) - 1u;
                 const uint64_t h = murmur_limbs<K>(bw);
-                uint32_t lo = 0, hi = 1u << K;  // first pattern hash >= h
+                const uint32_t pfx = (uint32_t)(h >> (64 - DENSE_PREFIX_BITS));
+                const uint32_t g0 = __ldg(d.group_base + pfx), g1 = __ldg(d.group_base + pfx + 1);
+                uint32_t lo = g0, hi = g1;  // first pattern hash >= h inside the prefix group
                 while (lo < hi) {
                     const uint32_t mid = (lo + hi) >> 1;
                     if (__ldg(d.sorted_hash + mid) < h) lo = mid + 1; else hi = mid;
                 }
-                const bool same = lo < (1u << K) && __ldg(d.sorted_hash + lo) == h;  // a pattern with this very hash
-                rank[j] = 2u * lo + (same ? 1u : 0u);
+                const bool same = lo < g1 && __ldg(d.sorted_hash + lo) == h;  // a pattern with this very hash
+                rank[j] = (pfx << d.rb) | (2u * (lo - g0) + (same ? 1u : 0u));
                 if (h == 0) exc_seen = true;  // would have to be dropped: general path
                 exc_emitted = true;
             }

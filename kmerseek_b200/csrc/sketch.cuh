@@ -44,13 +44,23 @@ struct SketchArgs {
 // Dense k-mer space path (hp, DENSE_MIN_K <= k <= DENSE_MAX_K, scaled == 1): see sketch_dense_kernel.
 constexpr int DENSE_MIN_K = 8;
 constexpr int DENSE_MAX_K = 24;
+constexpr int DENSE_PREFIX_BITS = 16;  // a pattern's code starts with the top 16 bits of its hash
+// Order-preserving code of a pattern (per-handle table, dense.cu): with p = the top DENSE_PREFIX_BITS bits of the pattern's
+// hash and l = the pattern's rank among the patterns that share p,
+//     code = p << rb | (2 l + 1)
+// Codes sort like the hashes, and a code's top bits ARE its hash's top bits, so a bucket of the key sort is a hash-prefix
+// range (the directory the search uses is over hash prefixes).  A window with a residue of neither class has no pattern:
+// it is hashed from its bytes and gets the EVEN code p << rb | 2 x (patterns of its prefix group below its hash), which
+// sorts it between the right two patterns (or onto a pattern with the very same hash: then the odd code).
+// When code | protein | position would not fit 64 bits with the parity bit but does without it (parity == 0), codes are
+// p << rb | l and a window without a pattern makes the batch take the general path (handle_exceptions must be 0).
 struct DenseSketchArgs {
-    const uint32_t* rank_of_code;  // device, 2^k entries: rank of the pattern's hash among all patterns' hashes
-    const uint64_t* sorted_hash;   // device, 2^k entries: the patterns' hashes in increasing order
-    uint64_t* out_keys;            // device, capacity entries: rank' << (pid_bits + pos_bits) | protein << pos_bits | position
-                                   // with rank' = 2 rank + 1 for a pattern; a window with a residue of neither class (no
-                                   // pattern) is hashed from its bytes and gets rank' = 2 x (pattern hashes below its hash),
-                                   // which sorts it between the right two patterns
+    const uint32_t* code_of_pattern;  // device, 2^k entries
+    const uint64_t* sorted_hash;      // device, 2^k entries: the patterns' hashes in increasing order
+    const uint32_t* group_base;       // device, 2^16 + 1 entries: first entry of sorted_hash of every prefix group
+    int rb;                           // bits of a code below the prefix (the parity bit included)
+    int parity;                       // 1: the lowest code bit tells patterns (1) from exception keys (0)
+    uint64_t* out_keys;               // device, capacity entries: code << (pid_bits + pos_bits) | protein << pos_bits | position
     int pid_bits, pos_bits;
     int handle_exceptions;         // 0: such a window only raises exception_flag[0] (the caller takes the general path)
     uint32_t* exception_flag;      // device u32[2]: [0] unhandled exception / zero hash, [1] exception keys were emitted
