@@ -652,12 +652,13 @@ void materialize_pending(ks_index* x) {
     sketch_resident_general(x);
 }
 
-bool repeat_heavy(const ks_index* x, uint64_t n) {
-    // distinct k-mers possible under this alphabet vs tuples: hp k=24 has 2^24 of them for ~2*10^8 tuples
+// tuples per possible hash: distinct k-mers under this alphabet (hp k=24 has 2^24 of them for ~2*10^8 tuples on C2)
+double avg_postings(const ks_index* x, uint64_t n) {
     const double alphabet = x->params.moltype == KS_HP ? 2.0 : x->params.moltype == KS_DAYHOFF ? 6.0 : 20.0;
     const double space = std::pow(alphabet, (double)x->params.ksize) / (double)x->params.scaled;
-    return (double)n > 0.25 * space;
+    return (double)n / space;
 }
+bool repeat_heavy(const ks_index* x, uint64_t n) { return avg_postings(x, n) > 0.25; }
 
 // Unstable partition of the general path (dense_scatter.cuh, PairSortPlan): the batch is the index's only content, hashes
 // rarely repeat (the bucket sort orders equal hashes by loc, pair by pair) and the tuple count fits two scatter levels.  KS_SCATTER=0 switches it off (test hook).
@@ -1094,7 +1095,7 @@ void finalize(ks_index* x) {
     while (bits < 24 && (4ull << bits) < n) bits++;
     // the bucket sort writes the CSR in the segmented layout: a directory bucket must not span two sort buckets, and the
     // key / group arrays carry one sentinel slot per sort bucket
-    const int top_bits = x->scattered ? x->pair_plan.total : build_top_bits(n, x->end_bit(), x->max_hash);
+    const int top_bits = x->scattered ? x->pair_plan.total : build_top_bits(n, x->end_bit(), x->max_hash, avg_postings(x, n));
     if (top_bits > bits) bits = top_bits;
     const uint64_t slack = std::max<uint64_t>(build_slack(n), top_bits > 0 ? (1ull << top_bits) + 2 : 2);
     x->dir_bits = bits;
@@ -1115,6 +1116,7 @@ void finalize(ks_index* x) {
     a.n = n; a.n_prot = P; a.end_bit = x->end_bit(); a.max_hash = x->max_hash;
     a.repeat_heavy = repeat_heavy(x, n) ? 1 : 0;  // measured: the bin kernel only wins when repeats are rare
     a.ls_variant = x->hooks.ls_variant;
+    a.avg_postings = avg_postings(x, n);
     int out_dir_sub = DIR_SUB_COMPACT;
     uint32_t out_seg_nb = 0;
     const uint32_t* out_seg_start = nullptr;

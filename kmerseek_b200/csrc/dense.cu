@@ -732,6 +732,9 @@ DenseSortPlan dense_sort_plan(uint64_t n, int rank_bits, int key_bits, int k) {
     // a bucket is a hash-prefix range: it holds Poisson(2^k / 2^total) patterns of ~n / 2^k keys each.  With few patterns per
     // bucket the loads are uneven: take more buckets until mean + 6 sigma fits one (or the prefix bits run out: a bucket
     // that overflows sends the batch to the general path)
+    // ... and with so few patterns that one of them fills a bucket on its own (hp k <= 13 at 10 M residues) the library
+    // sorts the keys on their code bits (stable; rows of one pattern are already in (protein, position) order)
+    if ((double)n / std::ldexp(1.0, k) > 1024.0) return p;
     while (total < DENSE_PREFIX_BITS) {
         const double lambda = std::ldexp(1.0, k - total), per_pattern = (double)n / std::ldexp(1.0, k);
         if (lambda * per_pattern + 6.0 * per_pattern * std::sqrt(lambda > 1.0 ? lambda : 1.0) <= (double)DB_CAP) break;

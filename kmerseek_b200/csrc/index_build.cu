@@ -792,7 +792,11 @@ __global__ void dir_kernel(const uint64_t* __restrict__ keys, const uint64_t* __
     for (uint64_t x = (uint64_t)b_last + 1 + i0; x <= nb; x += stride) dir[x] = (uint32_t)U;
 }
 
-int msd_top_bits(uint64_t n, int lz, uint64_t max_hash) {
+int msd_top_bits(uint64_t n, int lz, uint64_t max_hash, double avg_postings) {
+    // a k-mer space so small that its frequent hashes fill a bucket on their own (dayhoff k <= 7 at 10 M residues: 36 postings
+    // per hash on average, far more for the frequent ones): buckets would be oversize and take the per-range fallback;
+    // the library sort of all bits is the fast path there (measured: dayhoff k=6 56 ms -> 1.3 ms)
+    if (avg_postings > 16.0) return -1;
     // smallest tb whose average bucket is <= 3072 tuples (LS_CAP = 4096 leaves > 18 sigma for uniform hashes).
     // Hashes fill only [0, max_hash] of the 2^(64-lz) range the buckets span, so the used buckets are fuller.
     const double fill = lz >= 64 ? 1.0 : ((double)max_hash + 1.0) / std::ldexp(1.0, 64 - lz);
@@ -867,13 +871,15 @@ cudaError_t expand_sorted_hash(const CsrView& v, uint64_t* hash, cudaStream_t st
     return cudaGetLastError();
 }
 
-int build_top_bits(uint64_t n, int end_bit, uint64_t max_hash) { return n ? msd_top_bits(n, 64 - end_bit, max_hash) : -1; }
+int build_top_bits(uint64_t n, int end_bit, uint64_t max_hash, double avg_postings) {
+    return n ? msd_top_bits(n, 64 - end_bit, max_hash, avg_postings) : -1;
+}
 uint64_t build_slack(uint64_t n) { return max_ranges(n) + 2; }
 
 PairSortPlan pair_sort_plan(uint64_t n, int end_bit, uint64_t max_hash) {
     PairSortPlan p;
     const int lz = 64 - end_bit;
-    const int tb = msd_top_bits(n, lz, max_hash);
+    const int tb = msd_top_bits(n, lz, max_hash, 0.0);
     if (tb < 0 || tb > 2 * DS_MAX_BITS) return p;
     p.custom = 1;
     p.total = tb;
@@ -996,7 +1002,7 @@ cudaError_t build_index(const BuildArgs& a, cudaStream_t stream, int* out_in_a, 
     char* tp = (char*)a.temp;
     void* lib_temp = tp + tbytes;
     size_t lib_bytes = a.temp_bytes - tbytes;
-    const int tb = msd_top_bits(n, lz, a.max_hash);
+    const int tb = msd_top_bits(n, lz, a.max_hash, a.avg_postings);
     const uint32_t nb = tb >= 0 ? (1u << tb) : (uint32_t)((n + LS_CAP - 1) / LS_CAP);
     uint32_t* start = (uint32_t*)tp;                                             // [nb + 1]
     uint32_t* oversize = start + nb + 1;                                          // [2]

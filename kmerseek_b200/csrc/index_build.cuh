@@ -76,6 +76,8 @@ struct BuildArgs {
     int end_bit;  // hashes are < 2^end_bit (64 - leading zeros of max_hash)
     uint64_t max_hash;
     int repeat_heavy;  // the k-mer space is small next to n (hashes repeat many times): two local counting passes
+    double avg_postings = 0.0;  // tuples per possible hash (n / (alphabet^k / scaled)): above ~1000 a single hash fills a
+                                // bucket and the build takes the library sort of all bits
     int ls_variant = 0;  // test hook: 0 pick from repeat_heavy, 1 rep, 2 bin, 3 bin with a barrier per row
     // outputs (device, preallocated): keys[n], key_grp[n+1], grp_start[n+1], t_size[P], t_abund[P], d_counts[2],
     // dir[2^dir_bits + 1]
@@ -100,7 +102,7 @@ struct BuildArgs {
 size_t build_temp_bytes(uint64_t n, int end_bit);
 // Sort buckets the build of n ordered tuples uses (2^bits), or -1 when it takes the library sort for all bits (compact
 // layout); and the slack the key / group arrays need past n (one sentinel slot per bucket).
-int build_top_bits(uint64_t n, int end_bit, uint64_t max_hash);
+int build_top_bits(uint64_t n, int end_bit, uint64_t max_hash, double avg_postings);
 uint64_t build_slack(uint64_t n);
 // Sort by hash (stable) + CSR build + directory.  *out_in_a = 1 when the sorted tuples ended in the `a` pair.
 // Scattered input: no synchronisation (the caller reads *overflow_dev with the totals); ordered input: synchronises the

@@ -320,6 +320,60 @@ def manysearch(q_sketches, t_sketches, k, scaled, moltype, q_names=None, t_names
     return rows
 
 
+def manysearch_indexed(q_sketches, th, tpid, k, scaled, moltype):
+    """The rows of manysearch() for large target sets: the same formulae, but the overlaps come from a
+    sorted-hash index over the target tuples (th, tpid: every kept window's hash and protein) instead of from all-pairs
+    list intersections -- 1 000 queries against 10 M residues finish in seconds.  tests/test_oracle_golden.py checks it
+    against manysearch() itself.  Returns rows (qid, pid, numeric columns) ordered by (query, target)."""
+    th = np.asarray(th, dtype=np.uint64)
+    tpid = np.asarray(tpid, dtype=np.int64)
+    n_prot = int(tpid.max()) + 1 if len(tpid) else 0
+    # per (hash, protein): abundance; per protein: distinct hashes |T| and kept windows
+    order = np.lexsort((tpid, th))
+    hs, ps = th[order], tpid[order]
+    head = np.ones(len(hs), dtype=bool)
+    head[1:] = (hs[1:] != hs[:-1]) | (ps[1:] != ps[:-1])
+    g_start = np.flatnonzero(head)
+    g_hash, g_pid = hs[g_start], ps[g_start]
+    g_abund = np.diff(np.append(g_start, len(hs)))
+    t_size = np.bincount(g_pid, minlength=n_prot)
+    t_abund = np.bincount(tpid, minlength=n_prot)
+    keys, k_start = np.unique(g_hash, return_index=True)
+    k_end = np.append(k_start[1:], len(g_hash))
+    rows = []
+    K = float(3 * k)
+    for qi, (qm, _qa) in enumerate(q_sketches):
+        if len(qm) == 0:
+            continue
+        at = np.searchsorted(keys, qm)
+        ok = (at < len(keys))
+        ok[ok] &= keys[at[ok]] == qm[ok]
+        if not ok.any():
+            continue
+        segs = [np.arange(k_start[j], k_end[j]) for j in at[ok]]
+        g = np.concatenate(segs)
+        pids, ab = g_pid[g], g_abund[g].astype(np.float64)
+        o = np.lexsort((ab, pids))
+        pids, ab = pids[o], ab[o]
+        bounds = np.flatnonzero(np.append(True, pids[1:] != pids[:-1]))
+        ends = np.append(bounds[1:], len(pids))
+        for a, b in zip(bounds, ends):
+            pid = int(pids[a])
+            A = ab[a:b]
+            I = b - a
+            cont, cont_t = I / len(qm), I / t_size[pid]
+            qani, mani = cont ** (1.0 / K), cont_t ** (1.0 / K)
+            tw = float(t_abund[pid])
+            rows.append({
+                "qid": qi, "pid": pid, "containment": cont, "intersect_hashes": int(I), "jaccard": I / (len(qm) + t_size[pid] - I),
+                "max_containment": max(cont, cont_t), "average_abund": float(A.sum() / I), "median_abund": float(np.median(A)),
+                "std_abund": float(np.std(A)), "query_containment_ani": qani, "match_containment_ani": mani,
+                "average_containment_ani": (qani + mani) / 2.0, "max_containment_ani": max(qani, mani),
+                "n_weighted_found": int(A.sum()), "total_weighted_hashes": int(tw), "containment_target_in_query": cont_t,
+                "f_weighted_target_in_query": float(A.sum() / tw)})
+    return rows
+
+
 def allpairs_intersect(q_sketches, t_sketches):
     """manysearch's all-pairs merge in C (timing baseline)."""
     def csr(sk):

@@ -57,10 +57,10 @@ def test_c5_sweep_index_and_hits_equal_oracle(K, O, proteome, moltype):
         sub_res = int(min(150_000, max(20_000, 150_000 * space / (n_q * 120.0))))
         p = int(np.searchsorted(offs, sub_res))
         sres, soffs = res[:int(offs[p])], offs[:p + 1]
-        qres, qoffs, _ = synth.queries(sres, soffs, n_q, 77 + k, min_len=max(40, k + 8), max_len=160)
+        qres, qoffs, _ = synth.queries(sres, soffs, n_q, 77 + k, min_len=max(40, k + 8), max_len=160, sub_rate=0.03)
         with K.ProteomeIndex("c5s", k, 1, moltype) as idx:
             idx.add_proteome(K.Proteome.from_packed(sres, soffs))
             idx.finalize()
             r = _search_equals_oracle(K, O, idx, sres, soffs, qres, qoffs, k, moltype, 1, hits=True)
-            assert r.n_pairs >= n_q and r.n_hits > 0, (moltype, k)
+            assert r.n_pairs >= n_q // 2 and r.n_hits > 0, (moltype, k)  # (3 % substitutions: most queries keep a k-mer)
     prot.close()

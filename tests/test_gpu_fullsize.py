@@ -1,7 +1,9 @@
 """BASELINE.json's full-size configurations on one B200, checked through size-independent properties (the oracle
 takes minutes at these sizes): the sort is a permutation of the sketch output, rows are ordered, counts add up, and
 planted queries find the protein they were cut from.  C2: 570 k proteins / 200 M residues, hp k=24 scaled=1 (index
-build); C3 on one GPU: 10 000 planted domains against the same proteome, dayhoff k=16."""
+build); C3 on one GPU: 10 000 planted domains against the same proteome, dayhoff k=16.
+And against the oracle itself on the subsamples BASELINE.md section 4 names: C2 on a 10 M-residue prefix, C3 with 1 000
+queries against a 10 M-residue prefix (hit lists bit-exact, scores within 1e-6), C4 on a 50 M-residue prefix."""
 import numpy as np
 import pytest
 
@@ -98,3 +100,72 @@ def test_c3_planted_queries_find_their_source(K, proteome):
             a, b = int(qoffs[q]) + int(h["hit_qpos"][i]), int(offs[t]) + int(h["hit_tpos"][i])
             qs, ts = qres[a:a + k].tobytes().decode(), res[b:b + k].tobytes().decode()
             assert translate(qs, moltype) == translate(ts, moltype)
+
+
+SCORES = ("containment", "containment_target_in_query", "max_containment", "jaccard", "query_containment_ani",
+          "match_containment_ani", "average_containment_ani", "max_containment_ani", "average_abund", "median_abund",
+          "std_abund", "f_weighted_target_in_query")
+
+
+def _index_equals_oracle(K, res, offs, k, moltype, scaled, path=None):
+    from oracle import oracle as O
+    with K.ProteomeIndex("prefix", k, scaled, moltype) as idx:
+        idx.add_proteome(K.Proteome.from_packed(res, offs))
+        idx.finalize()
+        keys, row_ptr, pid, pos = idx.csr()
+        st = idx.stats()
+    oh, opid, opos = O.sketch_tuples(res, offs, k, moltype, scaled)
+    okeys, orow, ops, oqs = O.build_index(oh, opid, opos)
+    assert np.array_equal(keys, okeys) and np.array_equal(row_ptr, orow)
+    assert np.array_equal(pid, ops) and np.array_equal(pos, oqs)
+    assert path is None or st["build_path"] in path, st["build_path"]
+    return oh, opid, opos
+
+
+def _prefix(res, offs, n_res):
+    p = int(np.searchsorted(offs, n_res))
+    return res[:int(offs[p])], offs[:p + 1]
+
+
+def test_c2_prefix_equals_oracle(K, proteome):
+    """equality vs the CPU oracle on a 10 M-residue prefix (dense k-mer space path)."""
+    res, offs = _prefix(*proteome, 10_000_000)
+    _index_equals_oracle(K, res, offs, 24, "hp", 1, path=(1,))
+
+
+def test_c3_subsample_equals_oracle(K, proteome):
+    """1 000 planted queries against a 10 M-residue prefix, dayhoff k=16 -- pairs and hit lists
+    bit-exact, scores within 1e-6 relative, against the oracle (indexed restatement of manysearch)."""
+    from kmerseek_b200 import synth
+    from oracle import oracle as O
+    res, offs = _prefix(*proteome, 10_000_000)
+    k, moltype = 16, "dayhoff"
+    qres, qoffs, _ = synth.queries(res, offs, 1000, 79)
+    with K.ProteomeIndex("c3", k, 1, moltype) as idx:
+        idx.add_proteome(K.Proteome.from_packed(res, offs))
+        idx.finalize()
+        r = K.search(idx, K.Proteome.from_packed(qres, qoffs), hits=True)
+        p, h = r.pairs, r.hits
+        oh, opid, opos = O.sketch_tuples(res, offs, k, moltype, 1)
+        qh, qid, qpos = O.sketch_tuples(qres, qoffs, k, moltype, 1)
+        qsk = O.protein_sketches(qh, qid, len(qoffs) - 1)
+        for (m, a), (om, oa) in zip(r.query_sketches, qsk):
+            assert np.array_equal(m, om) and np.array_equal(a, oa)
+        rows = O.manysearch_indexed(qsk, oh, opid, k, 1, moltype)
+        assert r.n_pairs == len(rows) > 900
+        assert np.array_equal(p["pair_qid"], [x["qid"] for x in rows]) and np.array_equal(p["pair_pid"], [x["pid"] for x in rows])
+        for c in ("intersect_hashes", "n_weighted_found", "total_weighted_hashes"):
+            assert np.array_equal(p[c], [x[c] for x in rows]), c
+        for c in SCORES:
+            np.testing.assert_allclose(p[c], [x[c] for x in rows], rtol=1e-6, atol=0, err_msg=c)
+        ohits = O.hits(qh, qid, qpos, oh, opid, opos)
+        mine = list(zip(h["hit_qid"].tolist(), h["hit_pid"].tolist(), h["hit_hash"].tolist(), h["hit_qpos"].tolist(),
+                        h["hit_tpos"].tolist()))
+        assert mine == ohits and len(mine) > 10_000
+
+
+def test_c4_prefix_equals_oracle(K):
+    """BASELINE.md section 4, C4 (protein k=7 scaled=10): equality vs the oracle on a 50 M-residue prefix."""
+    from kmerseek_b200 import synth
+    res, offs = synth.proteome(50_000_000, 20260104)
+    _index_equals_oracle(K, res, offs, 7, "protein", 10)

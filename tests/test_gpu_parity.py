@@ -512,6 +512,7 @@ def test_medium_scale_against_oracle(K, O):
         okeys, orow, ops, oqs = O.build_index(oh, opid, opos)
         assert np.array_equal(keys, okeys) and np.array_equal(row_ptr, orow)
         assert np.array_equal(pid, ops) and np.array_equal(pos, oqs)
+        assert idx.stats()["build_path"] == 1  # the dense k-mer space path took it (the C2 configuration's path)
 
 
 def test_bucket_sort_path_with_oversize_buckets(K, O):

@@ -223,3 +223,20 @@ def test_cpu_baseline_modes_agree():
     assert n == len(res) and uniq == len(np.unique(h)) and kept == len(h)
     n2, _, kept2 = O.cpu_baseline(res, offs, 6, "hp", 1, faithful=False, n_threads=1)
     assert n2 == n and kept2 == kept
+
+
+def test_indexed_manysearch_equals_all_pairs():
+    """manysearch_indexed (used at full size) against manysearch (the all-pairs restatement pinned by the golden CSV)."""
+    from kmerseek_b200 import synth
+    res, offs = synth.proteome(60_000, 11)
+    qres, qoffs, _ = synth.queries(res, offs, 20, 5, min_len=40, max_len=150)
+    for k, moltype, scaled in ((8, "hp", 1), (7, "dayhoff", 1), (5, "protein", 2)):
+        th, tpid, _ = O.sketch_tuples(res, offs, k, moltype, scaled)
+        qh, qid, _ = O.sketch_tuples(qres, qoffs, k, moltype, scaled)
+        qsk = O.protein_sketches(qh, qid, len(qoffs) - 1)
+        a = O.manysearch(qsk, O.protein_sketches(th, tpid, len(offs) - 1), k, scaled, moltype)
+        b = O.manysearch_indexed(qsk, th, tpid, k, scaled, moltype)
+        assert len(a) == len(b) > 0
+        for x, y in zip(a, b):
+            for c, v in y.items():
+                assert x[c] == pytest.approx(v, rel=1e-12, abs=0), c
