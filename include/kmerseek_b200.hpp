@@ -151,6 +151,12 @@ class ProteomeIndex {
         check(ks_index_stats(h_, &s));
         return s.n_unique_hashes;
     }
+    size_t signature_count() {  // src/rust/index.rs:514-516: distinct ids (equal ids overwrite, :817-820)
+        check(ks_index_finalize(h_));
+        uint64_t n = 0;
+        check(ks_index_signature_count(h_, &n));
+        return (size_t)n;
+    }
     ks_stats stats() {
         ks_stats s;
         check(ks_index_stats(h_, &s));

@@ -345,7 +345,16 @@ __device__ __forceinline__ uint32_t stage_addr(uint32_t slot) { return (slot & 3
 // FULL (max_hash = 2^64 - 1, i.e. scaled == 1): tile bases come from tile_count_kernel + scan, so there is no
 // ticket, no look-back chain and no cross-CTA dependency at all.
 template <int K, bool TRANSLATE, bool FULL, bool SCATTER>
-__global__ void __launch_bounds__(SK_THREADS, SCATTER ? 5 : 1)
+#ifndef KS_SK_CTAS
+#define KS_SK_CTAS 5
+#endif
+#ifndef KS_SK_CTAS_LB
+#define KS_SK_CTAS_LB 6
+#endif
+// CTAs per SM the register allocation aims at (FULL: exact path / look-back path).  Measured (round 2, C4 slice, the
+// look-back path): 4 / 5 / 6 CTAs 9.26 / 7.75 / 6.77 ms (left to the compiler the non-scatter instantiations took 62-64
+// registers = 4 CTAs); the exact path is best at 5 (100 M-residue target run 0.90 ms against 0.97 ms at 6).
+__global__ void __launch_bounds__(SK_THREADS, FULL ? KS_SK_CTAS : KS_SK_CTAS_LB)
 sketch_quad_kernel(SketchArgs a, Lut256 lut, uint32_t* __restrict__ ticket, uint64_t* __restrict__ status,
                    const uint32_t* __restrict__ tile_pid, const uint64_t* __restrict__ tile_base) {
     constexpr int RES_WORDS = (SK_TILE + K + 16 + 3) / 4;

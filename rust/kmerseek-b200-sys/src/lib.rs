@@ -38,7 +38,7 @@ pub struct ks_stats {
     pub ms_sort_partition: f32,
     pub ms_sort_bucket: f32,
     pub finalized: u32,
-    pub build_path: u32, // 0 general, 1 dense k-mer space, 2 dense with the library's key sort
+    pub build_path: u32, // 0 general, 1 dense k-mer space, 2 dense with the library's key sort, 3 general / unstable partition
 }
 
 #[repr(C)]
@@ -56,6 +56,14 @@ pub struct ks_sketch {
 pub enum ks_index {}
 pub enum ks_proteome {}
 pub enum ks_search_result {} // field layout: see the header; read through accessors in the safe wrapper
+pub enum ks_comm {}
+
+pub const KS_SEARCH_HITS: u32 = 1;
+pub const KS_SEARCH_DEVICE_ONLY: u32 = 2;
+pub const KS_SEARCH_QUERY_SKETCHES: u32 = 4;
+pub const KS_NORMALIZE_KMERSEEK: c_int = 0; // index path: validate_and_resolve (src/rust/aminoacid.rs:74-105)
+pub const KS_NORMALIZE_SOURMASH: c_int = 1; // search path: upper-case only (sourmash add_protein)
+pub const KS_COMM_ID_BYTES: usize = 128;
 
 extern "C" {
     pub fn ks_last_error_message() -> *const c_char;
@@ -65,6 +73,9 @@ extern "C" {
     pub fn ks_proteome_from_fasta(path: *const c_char, ambig_seed: u64, out: *mut *mut ks_proteome) -> c_int;
     pub fn ks_proteome_from_sequences(seqs: *const *const c_char, lens: *const u64, names: *const *const c_char,
                                       n: u64, ambig_seed: u64, out: *mut *mut ks_proteome) -> c_int;
+    pub fn ks_proteome_from_fasta_mode(path: *const c_char, ambig_seed: u64, mode: c_int, out: *mut *mut ks_proteome) -> c_int;
+    pub fn ks_proteome_from_sequences_mode(seqs: *const *const c_char, lens: *const u64, names: *const *const c_char,
+                                           n: u64, ambig_seed: u64, mode: c_int, out: *mut *mut ks_proteome) -> c_int;
     pub fn ks_proteome_free(p: *mut ks_proteome);
     pub fn ks_index_create(params: *const ks_params, out: *mut *mut ks_index) -> c_int;
     pub fn ks_index_destroy(idx: *mut ks_index);
@@ -72,12 +83,19 @@ extern "C" {
     pub fn ks_index_finalize(idx: *mut ks_index) -> c_int;
     pub fn ks_index_process_fasta(idx: *mut ks_index, path: *const c_char, ambig_seed: u64) -> c_int;
     pub fn ks_index_stats(idx: *mut ks_index, out: *mut ks_stats) -> c_int;
+    pub fn ks_index_signature_count(idx: *mut ks_index, out: *mut u64) -> c_int; // src/rust/index.rs:514-516
     pub fn ks_sketch_batch(idx: *mut ks_index, p: *const ks_proteome, out: *mut *mut ks_sketch) -> c_int;
     pub fn ks_sketch_free(s: *mut ks_sketch);
     pub fn ks_search_batch(idx: *mut ks_index, queries: *const ks_proteome, flags: u32,
                            out: *mut *mut ks_search_result) -> c_int;
     pub fn ks_search_result_free(r: *mut ks_search_result);
     pub fn ks_search_result_device_column(r: *const ks_search_result, name: *const c_char) -> *mut c_void;
+    // multi-GPU: one process per GPU, proteome sharded by protein (no precedent in the reference, which is single-process)
+    pub fn ks_comm_unique_id(id: *mut u8) -> c_int;
+    pub fn ks_comm_create(id: *const u8, rank: c_int, world: c_int, device: c_int, out: *mut *mut ks_comm) -> c_int;
+    pub fn ks_comm_destroy(c: *mut ks_comm);
+    pub fn ks_shard_search_batch(idx: *mut ks_index, comm: *mut ks_comm, queries: *const ks_proteome, flags: u32,
+                                 pid_base: u64, out: *mut *mut ks_search_result) -> c_int;
 }
 
 /// How `IndexError` (src/rust/errors.rs:4-55) is rebuilt from a status code.
