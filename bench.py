@@ -102,7 +102,11 @@ class ClockSampler:
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the committed `ncu --set full`
 # captures of the C2 workload on one GPU (profiles/): only meaningful for that workload at N = 1, null otherwise.
-TRAFFIC_C2 = {"dense_bucket_kernel": 1_638_007_000 + 3_419_163_000}  # profiles/r01_e_ncu_full_raw_dense_bucket_c2.csv
+TRAFFIC_C2 = {"dense_bucket_kernel": 1_642_043_000 + 3_709_267_000}  # profiles/r02_k_ncu_full_raw_c2_build.csv
+# the same for the per-query kernel of the search leg (10 000 queries against the C3 index, pairs only):
+# profiles/r02_k_ncu_full_raw_c3_search.csv -- random 32-byte sector gathers (directory, keys, groups, postings, protein
+# sizes), which is why it is more than ten times the algorithmic bytes
+TRAFFIC_C3_SEARCH = {"query_kernel": 514_213_000 + 21_839_000}
 
 
 def sketch_bytes(n_res, n_prot, n_tuples):
@@ -495,7 +499,9 @@ def main():
     for v in search.values():
         v["roofline"] = {"bound": "hbm", "algorithmic_bytes": v["algorithmic_bytes"], "peak": agg_peak,
                          "frac_kernels": v["algorithmic_bytes"] / v["ms_per_batch_kernels"] / 1e6 / agg_peak if v["ms_per_batch_kernels"] else None,
-                         "frac_wall": v["algorithmic_bytes"] / v["ms_per_batch_wall"] / 1e6 / agg_peak}
+                         "frac_wall": v["algorithmic_bytes"] / v["ms_per_batch_wall"] / 1e6 / agg_peak,
+                         "kernel": "query_kernel",
+                         "traffic": TRAFFIC_C3_SEARCH["query_kernel"] if (world == 1 and args.queries == 10_000 and v["hits"] == 0) else None}
 
     cpu = None
     if not args.no_cpu_baseline:

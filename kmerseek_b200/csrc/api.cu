@@ -140,6 +140,11 @@ struct ks_proteome {
     HostBuf b_res, b_offs, b_packed;
     std::string name_blob;  // NUL-terminated names back to back; empty when no names were given
     std::vector<uint64_t> name_off;
+    // shape of the batch, computed once per k-mer size (one pass over the offsets; every add of the proteome needs it)
+    std::mutex shape_mu;
+    bool shape_valid = false;
+    uint32_t shape_k = 0;
+    uint64_t shape_windows = 0, shape_max_len = 0;
     ~ks_proteome() { b_res.release(); b_offs.release(); b_packed.release(); }
 };
 
@@ -401,6 +406,24 @@ uint64_t max_protein_len(const uint64_t* offs, uint64_t n_prot) {
     return m;
 }
 
+// k-mer windows and longest protein of a proteome for k-mer size k (cached on the proteome: one pass per k)
+void proteome_shape(const ks_proteome* cp, uint32_t k, uint64_t* n_windows, uint64_t* max_len) {
+    ks_proteome* p = const_cast<ks_proteome*>(cp);
+    std::lock_guard<std::mutex> g(p->shape_mu);
+    if (!p->shape_valid || p->shape_k != k) {
+        uint64_t w = 0, m = 0;
+        const uint64_t* offs = p->offsets;
+        for (uint64_t i = 0; i < p->n_prot; i++) {
+            const uint64_t len = offs[i + 1] - offs[i];
+            m = std::max(m, len);
+            if (len >= k) w += len - k + 1;
+        }
+        p->shape_windows = w; p->shape_max_len = m; p->shape_k = k; p->shape_valid = true;
+    }
+    *n_windows = p->shape_windows;
+    *max_len = p->shape_max_len;
+}
+
 uint64_t count_windows(const uint64_t* offs, uint64_t n_prot, uint32_t k) {
     uint64_t w = 0;
     for (uint64_t i = 0; i < n_prot; i++) {
@@ -445,7 +468,7 @@ struct ks_index {
     int lz = 0;  // known-zero leading bits of every kept hash
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;  // H2D of residue chunks while earlier tiles are being hashed
-    cudaEvent_t ev_chunk[9] = {};
+    cudaEvent_t ev_chunk[17] = {};
     cudaEvent_t ev[12] = {};
     uint64_t live_bytes = 0;
     Arena* arena = nullptr;
@@ -455,6 +478,10 @@ struct ks_index {
     uint64_t *d_hash = nullptr, *d_loc = nullptr;
     uint64_t cap = 0, n_tuples = 0;
     uint64_t n_prot = 0, n_res = 0, n_windows = 0;
+    // device words a build reports through, one block so that they are zeroed and read back together:
+    // [0..1] CSR totals (d_counts), [2..3] sketch count + zero-hash flag (d_count), [4] dense path flags (u32 pair:
+    // unhandled exception | exception keys emitted), [5] dense path: a sort bucket overflowed (u32)
+    uint64_t* d_status = nullptr;
     uint64_t* d_count = nullptr;
     void* ws = nullptr;
     size_t ws_bytes = 0;
@@ -471,8 +498,8 @@ struct ks_index {
     int dense_rb = 0, dense_parity = 1;   // layout of this build: rb = dense_rb_full - (1 - parity)
     int dense_table_parity = -1;      // layout the code table currently holds
     uint32_t* dense_por = nullptr;    // pattern of every rank (to rebuild the code table in the other layout)
-    uint32_t* dense_flags = nullptr;  // device u32[4]: [0] table check, [1] unhandled exception, [2] exception keys emitted,
-                                      // [3] largest rank of a pattern inside its prefix group (table build)
+    uint32_t* dense_flags = nullptr;  // device u32[4], table build: [0] table check, [3] largest rank of a pattern inside
+                                      // its prefix group
     Buf b_dense_code, b_dense_hash, b_dense_group, b_dense_por, b_dense_flags, b_dense_work;
     bool pending_dense = false;
     bool scattered = false;  // the only batch was sketched straight into the regions of the unstable partition (pair_plan)
@@ -486,13 +513,12 @@ struct ks_index {
     uint64_t* keys = nullptr;
     uint32_t *key_grp = nullptr, *grp_start = nullptr, *t_size = nullptr, *t_abund = nullptr, *dir = nullptr;
     uint64_t* d_counts = nullptr;
-    Buf b_keys, b_key_grp, b_grp_start, b_t_size, b_t_abund, b_dir, b_counts, b_alt_hash, b_alt_loc, b_temp;
+    Buf b_keys, b_key_grp, b_grp_start, b_t_size, b_t_abund, b_dir, b_alt_hash, b_alt_loc, b_temp;
     int dir_bits = 0, dir_shift = 0;
     int dir_sub = DIR_SUB_COMPACT;  // layout of keys / key_grp / grp_start (index_build.cuh): compact, or segmented
     uint32_t seg_nb = 0;
-    uint32_t* seg_start = nullptr;
-    uint64_t* seg_counts = nullptr;
-    Buf b_seg_start, b_seg_counts;
+    const uint32_t* seg_start = nullptr;  // (in the build's scratch, which stays with the handle until the next build)
+    const uint64_t* seg_counts = nullptr;
     uint64_t U = 0, G = 0, n_ids = 0;
     // query path: per-handle scratch (grow-only) and a pinned word block for the counts the host reads back
     Buf b_q_ecount, b_q_pcount, b_q_hcount, b_q_sig, b_q_poff, b_q_hoff, b_q_ent_hash, b_q_ent_abund, b_q_win_key,
@@ -540,8 +566,7 @@ void upload_batch(ks_index* x, DeviceBatch& b, const ks_proteome* p, bool allow_
     KS_CUDA(cudaMemcpyAsync(b.offs, p->offsets, (p->n_prot + 1) * 8, cudaMemcpyHostToDevice, x->stream));
     b.n_prot = p->n_prot;
     b.n_res = p->n_res;
-    b.n_windows = count_windows(p->offsets, p->n_prot, x->params.ksize);
-    b.max_len = max_protein_len(p->offsets, p->n_prot);
+    proteome_shape(p, x->params.ksize, &b.n_windows, &b.max_len);
     b.valid = true;
 }
 
@@ -771,7 +796,7 @@ void sketch_resident_general(ks_index* x) {
 // before any hash; on the look-back path (scaled > 1) tiles are taken by ticket, which simply continues across the
 // chunk launches.  Returns false when the batch does not qualify (caller takes upload + sketch_resident).
 bool add_proteome_pipelined(ks_index* x, const ks_proteome* p) {
-    constexpr int CHUNKS = 8;
+    constexpr int CHUNKS = 16;  // (the last chunk's kernel is all that is not hidden behind the copy)
     if (x->params.ksize > (uint32_t)SK_MAX_TEMPLATE_K || x->hooks.no_pipeline)  // (test hook)
         return false;
     if (p->n_res < (64u << 20) || p->n_prot == 0) return false;  // small batches: one copy, one launch
@@ -782,8 +807,7 @@ bool add_proteome_pipelined(ks_index* x, const ks_proteome* p) {
     {   // a batch for the dense path: the rank kernel follows the chunks instead of the sketch kernel
         DeviceBatch probe;
         probe.n_prot = p->n_prot; probe.n_res = p->n_res;
-        probe.n_windows = count_windows(p->offsets, p->n_prot, x->params.ksize);
-        probe.max_len = max_protein_len(p->offsets, p->n_prot);
+        proteome_shape(p, x->params.ksize, &probe.n_windows, &probe.max_len);
         dense = dense_eligible(x, probe, x->n_prot, x->n_tuples);
         if (!dense) scat = scatter_eligible(x, probe, x->n_prot, x->n_tuples, &scat_plan);
     }
@@ -805,8 +829,7 @@ bool add_proteome_pipelined(ks_index* x, const ks_proteome* p) {
     }
     b.packed = packed;
     b.n_prot = p->n_prot; b.n_res = p->n_res;
-    b.n_windows = count_windows(p->offsets, p->n_prot, x->params.ksize);
-    b.max_len = max_protein_len(p->offsets, p->n_prot);
+    proteome_shape(p, x->params.ksize, &b.n_windows, &b.max_len);
     b.valid = true;
     if (!dense && !scat) grow_tuples(x, x->n_tuples + expected_kept(x, b.n_windows));
     if (scat) scatter_begin(x, scat_plan, p->n_prot);
@@ -902,7 +925,7 @@ void dense_kernel_args(ks_index* x, SketchArgs* a, DenseSketchArgs* d) {
     a->force_general = 0;
     d->code_of_pattern = x->dense_code; d->out_keys = x->d_hash; d->pid_bits = x->dense_pid_bits; d->pos_bits = x->dense_pos_bits;
     d->sorted_hash = x->dense_hash; d->group_base = x->dense_group; d->rb = x->dense_rb; d->parity = x->dense_parity;
-    d->exception_flag = x->dense_flags + 1;
+    d->exception_flag = (uint32_t*)(x->d_status + 4);
     // the library-sorted variant and the layout without the parity bit have no exception handling: general path then
     d->handle_exceptions = plan.custom && x->dense_parity ? 1 : 0;
     d->scatter = DenseScatter{nullptr, nullptr, 0, 0, 0, nullptr};
@@ -913,8 +936,10 @@ void dense_kernel_args(ks_index* x, SketchArgs* a, DenseSketchArgs* d) {
         d->scatter.cap = plan.cap1;
         d->scatter.shift = DENSE_PREFIX_BITS + x->dense_rb + x->dense_pid_bits + x->dense_pos_bits - plan.l1;
         d->scatter.bits = plan.l1;
-        d->scatter.overflow = (uint32_t*)(work + plan.off_overflow);
+        d->scatter.overflow = (uint32_t*)(x->d_status + 5);
+        a->unordered = 1;
     }
+    a->count_zeroed = 1;  // (dense_begin zeroes the status block)
 }
 
 // Tables (first use of the handle), sort plan, buffers, tile -> protein map and exact tile bases.  The offsets of the
@@ -923,7 +948,7 @@ bool dense_begin(ks_index* x) {
     DeviceBatch& b = x->batch;
     const uint32_t k = x->params.ksize;
     Arena* ar = x->arena;
-    x->dense_flags = x->b_dense_flags.ensure<uint32_t>(ar, 4);  // [0] table check, [1] unhandled exception, [2] exception keys
+    x->dense_flags = x->b_dense_flags.ensure<uint32_t>(ar, 4);
     if (x->dense_state == 0) {  // first use of the handle: the tables (two steps, one host read in between)
         x->dense_code = x->b_dense_code.ensure<uint32_t>(ar, (size_t)1 << k);
         x->dense_hash = x->b_dense_hash.ensure<uint64_t>(ar, (size_t)1 << k);
@@ -973,7 +998,7 @@ bool dense_begin(ks_index* x) {
     SketchArgs a;
     DenseSketchArgs d;
     dense_kernel_args(x, &a, &d);
-    KS_CUDA(cudaMemsetAsync(x->dense_flags + 1, 0, 8, x->stream));
+    KS_CUDA(cudaMemsetAsync(x->d_status, 0, 64, x->stream));  // totals, count, flags, overflow: one memset, one read at the end
     KS_CUDA(launch_sketch_prepare(a, x->stream, &x->l_sketch));
     return true;
 }
@@ -1019,7 +1044,7 @@ bool dense_finalize(ks_index* x) {
     x->key_grp = x->b_key_grp.ensure<uint32_t>(ar, n + slack);
     x->grp_start = x->b_grp_start.ensure<uint32_t>(ar, n + slack);
     x->dir = x->b_dir.ensure<uint32_t>(ar, (1ull << bits) + slack);
-    x->d_counts = x->b_counts.ensure<uint64_t>(ar, 2);
+    x->d_counts = x->d_status;
     int out_dir_sub = DIR_SUB_COMPACT;
     uint32_t out_seg_nb = 0;
     const uint32_t* out_seg_start = nullptr;
@@ -1034,7 +1059,8 @@ bool dense_finalize(ks_index* x) {
     c.pid_bits = x->dense_pid_bits; c.pos_bits = x->dense_pos_bits;
     c.offsets = b.offs; c.sorted_hash = x->dense_hash; c.group_base = x->dense_group;
     c.residues = b.res; c.packed = b.packed ? 1 : 0;
-    c.skip_flag = x->dense_flags + 1; c.exc_flag = x->dense_flags + 2;
+    c.skip_flag = (uint32_t*)(x->d_status + 4); c.exc_flag = c.skip_flag + 1; c.overflow = (uint32_t*)(x->d_status + 5);
+    c.counts_zeroed = 1;
     c.loc = x->d_loc; c.keys = x->keys; c.key_grp = x->key_grp; c.grp_start = x->grp_start;
     c.t_size = x->t_size; c.t_abund = x->t_abund; c.d_counts = x->d_counts;
     c.temp_bytes = dense_csr_temp_bytes(n);
@@ -1048,21 +1074,15 @@ bool dense_finalize(ks_index* x) {
         x->l_csr += 1;
     }
     KS_CUDA(cudaEventRecord(x->ev[EV_CS1], x->stream));
-    x->seg_start = nullptr; x->seg_counts = nullptr;
-    if (out_dir_sub != DIR_SUB_COMPACT) {  // the bucket tables live in the work buffer: keep a copy for the export calls
-        x->seg_start = x->b_seg_start.ensure<uint32_t>(ar, (size_t)out_seg_nb + 1);
-        x->seg_counts = x->b_seg_counts.ensure<uint64_t>(ar, out_seg_nb);
-        KS_CUDA(cudaMemcpyAsync(x->seg_start, out_seg_start, ((size_t)out_seg_nb + 1) * 4, cudaMemcpyDeviceToDevice, x->stream));
-        KS_CUDA(cudaMemcpyAsync(x->seg_counts, out_seg_counts, (size_t)out_seg_nb * 8, cudaMemcpyDeviceToDevice, x->stream));
-    }
+    // (the bucket tables of the segmented layout live in the work buffer, which stays with the handle until the next build)
+    x->seg_start = out_seg_start; x->seg_counts = out_seg_counts;
     x->t_sketch = x->t_sort = x->t_csr = true;
-    uint64_t* hw = x->h_words + HW_TOTALS;  // pinned: [0..1] counts, [2] produced, [3] flags 1|2, [4] overflow
-    hw[4] = 0;
-    KS_CUDA(cudaMemcpyAsync(hw, x->d_counts, 16, cudaMemcpyDeviceToHost, x->stream));
-    KS_CUDA(cudaMemcpyAsync(hw + 2, x->d_count, 8, cudaMemcpyDeviceToHost, x->stream));
-    KS_CUDA(cudaMemcpyAsync(hw + 3, x->dense_flags + 1, 8, cudaMemcpyDeviceToHost, x->stream));
-    if (plan.custom) KS_CUDA(cudaMemcpyAsync(hw + 4, work + plan.off_overflow, 4, cudaMemcpyDeviceToHost, x->stream));
+    uint64_t st[6];  // the status block: [0..1] counts, [2] produced, [3] zero-hash flag, [4] flags, [5] overflow
+    uint64_t* hwp = x->h_words + HW_TOTALS;
+    KS_CUDA(cudaMemcpyAsync(hwp, x->d_status, 48, cudaMemcpyDeviceToHost, x->stream));
     KS_CUDA(cudaStreamSynchronize(x->stream));
+    memcpy(st, hwp, sizeof(st));
+    uint64_t hw[5] = {st[0], st[1], st[2], st[4], st[5]};
     const uint32_t unhandled = (uint32_t)hw[3];  // [0] of the pair: an exception the path does not handle, or a zero hash
     if (x->hooks.timing)
         fprintf(stderr, "[ks] dense finalize: n %llu produced %llu unhandled %u exc %u overflow %u U %llu G %llu plan l1 %d l2 %d rb %d\n",
@@ -1107,7 +1127,7 @@ void finalize(ks_index* x) {
     x->key_grp = x->b_key_grp.ensure<uint32_t>(ar, n + slack);
     x->grp_start = x->b_grp_start.ensure<uint32_t>(ar, n + slack);
     x->dir = x->b_dir.ensure<uint32_t>(ar, (1ull << bits) + slack);
-    x->d_counts = x->b_counts.ensure<uint64_t>(ar, 2);
+    x->d_counts = x->d_status;
     // the second tuple pair is the sort's ping-pong partner; a scattered batch has its regions instead
     uint64_t* hb = x->scattered ? nullptr : x->b_alt_hash.ensure<uint64_t>(ar, n);
     uint64_t* lb = x->scattered ? nullptr : x->b_alt_loc.ensure<uint64_t>(ar, n);
@@ -1146,13 +1166,8 @@ void finalize(ks_index* x) {
     KS_CUDA(cudaEventRecord(x->ev[EV_CS1], x->stream));
     x->dir_sub = out_dir_sub;
     x->seg_nb = out_seg_nb;
-    x->seg_start = nullptr; x->seg_counts = nullptr;
-    if (out_dir_sub != DIR_SUB_COMPACT) {  // the bucket tables live in scratch: keep a copy for the export calls
-        x->seg_start = x->b_seg_start.ensure<uint32_t>(ar, (size_t)out_seg_nb + 1);
-        x->seg_counts = x->b_seg_counts.ensure<uint64_t>(ar, out_seg_nb);
-        KS_CUDA(cudaMemcpyAsync(x->seg_start, out_seg_start, ((size_t)out_seg_nb + 1) * 4, cudaMemcpyDeviceToDevice, x->stream));
-        KS_CUDA(cudaMemcpyAsync(x->seg_counts, out_seg_counts, (size_t)out_seg_nb * 8, cudaMemcpyDeviceToDevice, x->stream));
-    }
+    // (the bucket tables of the segmented layout live in scratch that stays with the handle until the next build)
+    x->seg_start = out_seg_start; x->seg_counts = out_seg_counts;
     const bool was_scattered = x->scattered;
     double t2 = dbg ? now_ms() : 0;
     x->t_sort = x->t_csr = true;
@@ -1160,9 +1175,9 @@ void finalize(ks_index* x) {
     // overflow flag and (when the sketch was not checked yet) the sketch kernel's count and zero-hash flag
     uint64_t* hw = x->h_words + HW_TOTALS;
     hw[2] = n; hw[3] = 0; hw[4] = 0;
-    KS_CUDA(cudaMemcpyAsync(hw, x->d_counts, 16, cudaMemcpyDeviceToHost, x->stream));
+    // (d_counts and d_count are neighbours in the status block)
+    KS_CUDA(cudaMemcpyAsync(hw, x->d_status, x->scatter_unchecked ? 32 : 16, cudaMemcpyDeviceToHost, x->stream));
     if (d_overflow) KS_CUDA(cudaMemcpyAsync(hw + 4, d_overflow, 4, cudaMemcpyDeviceToHost, x->stream));
-    if (x->scatter_unchecked) KS_CUDA(cudaMemcpyAsync(hw + 2, x->d_count, 16, cudaMemcpyDeviceToHost, x->stream));
     KS_CUDA(cudaStreamSynchronize(x->stream));
     if (was_scattered && ((uint32_t)hw[4] != 0 || hw[2] != n || (hw[3] >> 32) != 0)) {
         // a k-mer repeated thousands of times filled a region, or a window hashed to exactly 0 (it must be dropped):
@@ -1270,7 +1285,8 @@ ks_status ks_index_create(const ks_params* params, ks_index** out) {
             uint64_t thr = UINT64_MAX;  // keep freed blocks in the pool: steady-state steps never reach the driver
             KS_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
             x->arena = new Arena(x->stream, &x->live_bytes);
-            x->d_count = x->arena->alloc<uint64_t>(2);
+            x->d_status = x->arena->alloc<uint64_t>(8);
+            x->d_count = x->d_status + 2;
             KS_CUDA(cudaHostAlloc((void**)&x->h_words, H_WORDS * 8, cudaHostAllocDefault));
         } catch (...) {
             ks_index_destroy(x);

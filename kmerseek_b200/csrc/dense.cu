@@ -800,7 +800,7 @@ cudaError_t dense_build_csr(const DenseCsrArgs& a, cudaStream_t stream, uint64_t
             dense_chunks_kernel<<<1, 256, 0, stream>>>(cursor1, 1u << pl.l1, pl.cap1, chunk_pfx);
             DenseScatter sc;
             sc.out = region2; sc.cursor = cursor2; sc.cap = (uint32_t)DB_CAP; sc.shift = total_bits - pl.total; sc.bits = pl.l2;
-            sc.overflow = (uint32_t*)(w + pl.off_overflow);
+            sc.overflow = a.overflow ? a.overflow : (uint32_t*)(w + pl.off_overflow);
             const unsigned grid = (unsigned)(n / DS_TILE + (1u << pl.l1) + 1);  // every region's last chunk may be partial
             dense_partition_kernel<<<grid, DS_THREADS, 0, stream>>>(region1, cursor1, pl.cap1, 1u << pl.l1, chunk_pfx, sc);
             KS_TRY(cudaGetLastError());
@@ -809,7 +809,7 @@ cudaError_t dense_build_csr(const DenseCsrArgs& a, cudaStream_t stream, uint64_t
         dense_bucket_offsets_kernel<<<1, 1024, 0, stream>>>(cursor2, nb, (uint32_t)DB_CAP, bstart);
         if (a.ev_sorted) KS_TRY(cudaEventRecord(a.ev_sorted, stream));
         if (a.dir_bits < pl.total) return cudaErrorInvalidValue;  // (the caller sizes the directory from the plan)
-        KS_TRY(cudaMemsetAsync(a.d_counts, 0, 16, stream));
+        if (!a.counts_zeroed) KS_TRY(cudaMemsetAsync(a.d_counts, 0, 16, stream));
         DenseBucketArgs ba;
         ba.region2 = region2; ba.cursor2 = cursor2; ba.bstart = bstart; ba.nb = nb; ba.bucket_bits = pl.total;
         ba.rem_bits = total_bits - pl.total; ba.loc_bits = loc_bits; ba.pos_bits = a.pos_bits; ba.rb = a.rb; ba.parity = a.parity;
@@ -819,8 +819,14 @@ cudaError_t dense_build_csr(const DenseCsrArgs& a, cudaStream_t stream, uint64_t
         ba.dir = a.dir; ba.dir_sub = a.dir_bits - pl.total; ba.dir_shift = 64 - a.dir_bits;
         ba.residues = a.residues; ba.offsets = a.offsets; ba.packed = a.packed; ba.k = a.k;
         ba.exc_flag = a.exc_flag; ba.skip_flag = a.skip_flag;
-        KS_TRY(cudaFuncSetAttribute(dense_bucket_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DB_SMEM));
-        KS_TRY(cudaFuncSetAttribute(dense_bucket_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DB_SMEM));
+        static thread_local int attr_device = -1;  // (the attribute is per device: once per host thread and device)
+        int dev = 0;
+        KS_TRY(cudaGetDevice(&dev));
+        if (attr_device != dev) {
+            KS_TRY(cudaFuncSetAttribute(dense_bucket_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DB_SMEM));
+            KS_TRY(cudaFuncSetAttribute(dense_bucket_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DB_SMEM));
+            attr_device = dev;
+        }
         // both instantiations, back to back: the rank kernel's device flag picks the one that works -- the host does not
         // wait for the flag (the exception instantiation strides over the buckets: idle, it is a few hundred CTAs that exit)
         dense_bucket_kernel<false><<<nb, DB_THREADS, DB_SMEM, stream>>>(ba);

@@ -47,6 +47,8 @@ struct DenseCsrArgs {
     int packed;                   // exception key (even code) is recomputed from them (hp translation)
     const uint32_t* exc_flag;     // device: != 0 when the rank kernel emitted exception keys (picks the bucket kernel)
     const uint32_t* skip_flag;    // device: != 0 when the build is void (an exception the path does not handle)
+    uint32_t* overflow = nullptr; // device: set when a sort bucket overflows (nullptr: the word in the plan's work buffer)
+    int counts_zeroed = 0;        // the caller has zeroed d_counts on the stream already
     const uint64_t* sorted_hash;  // tables
     const uint32_t* group_base;
     // outputs

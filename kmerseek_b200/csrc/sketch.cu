@@ -518,7 +518,7 @@ sketch_quad_kernel(SketchArgs a, Lut256 lut, uint32_t* __restrict__ ticket, uint
         wcount += total;
     }
 
-    if (FULL && zero_seen) atomicOr(ticket + 1, 1u);
+    if (FULL && zero_seen) atomicOr(reinterpret_cast<uint32_t*>(a.d_count + 1) + 1, 1u);
     if (lane == 0) s_wtot[warp] = wcount;
     __syncthreads();
     uint32_t wprefix = 0, btotal = 0;
@@ -539,8 +539,7 @@ sketch_quad_kernel(SketchArgs a, Lut256 lut, uint32_t* __restrict__ ticket, uint
             if (c) atomicAdd(&a.t_abund[p_lo + tid], c);
         }
         if (tid == 0) {
-            if (FULL) { if (tile == n_tiles - 1) *a.d_count = tile_base[tile] + btotal; }
-            else if (btotal) atomicAdd(reinterpret_cast<unsigned long long*>(a.d_count), (unsigned long long)btotal);
+            if (btotal) atomicAdd(reinterpret_cast<unsigned long long*>(a.d_count), (unsigned long long)btotal);
         }
         uint64_t key[DS_ITEMS];
         uint32_t valid = 0;
@@ -803,9 +802,8 @@ sketch_dense_kernel(SketchArgs a, Lut256 lut, const uint32_t* __restrict__ tile_
         if (i < (int)warp) wprefix += t;
         btotal += t;
     }
-    const uint64_t base = tile_base[tile] + wprefix;
-    if (tid == 0 && tile == n_tiles - 1) *a.d_count = tile_base[tile] + btotal;
-    if (d.scatter.out != nullptr) {  // first level of the key sort, straight out of shared memory
+    if (d.scatter.out != nullptr) {  // first level of the key sort, straight out of shared memory (no tile bases: unordered)
+        if (tid == 0 && btotal) atomicAdd(reinterpret_cast<unsigned long long*>(a.d_count), (unsigned long long)btotal);
         static_assert(DS_THREADS == SK_THREADS && DS_TILE == SK_TILE, "one scatter tile per sketch tile");
         __shared__ DenseScatterSmem s_sc;
         uint64_t key[DS_ITEMS];
@@ -819,6 +817,8 @@ sketch_dense_kernel(SketchArgs a, Lut256 lut, const uint32_t* __restrict__ tile_
         scatter_keys(key, valid, d.scatter, 0, s_sc, s_key);  // the staging buffer is free once the keys are in registers
         return;
     }
+    const uint64_t base = tile_base[tile] + wprefix;
+    if (tid == 0 && tile == n_tiles - 1) *a.d_count = tile_base[tile] + btotal;
     const uint32_t sbase = warp * (SK_TILE / (SK_THREADS / 32));
     uint64_t* ok = d.out_keys + base;
 #pragma unroll
@@ -948,21 +948,24 @@ static bool exact_path(const SketchArgs& a) {
 }
 
 cudaError_t launch_sketch_prepare(const SketchArgs& a, cudaStream_t stream, uint64_t* n_launches) {
-    if (a.n_res == 0 || a.n_prot == 0) return cudaMemsetAsync(a.d_count, 0, 16, stream);
+    if (a.n_res == 0 || a.n_prot == 0) return a.count_zeroed ? cudaSuccess : cudaMemsetAsync(a.d_count, 0, 16, stream);
     const uint64_t nt = n_tiles_of(a.n_res);
     Workspace w = carve(a.workspace, a.n_res);
     const bool exact = exact_path(a);
-    cudaError_t e = cudaMemsetAsync(a.workspace, 0, exact ? 16 : 16 + nt * 8, stream);
+    const bool unordered = a.unordered || a.scatter.out_key != nullptr;
+    cudaError_t e = cudaSuccess;
+    if (!exact) e = cudaMemsetAsync(a.workspace, 0, 16 + nt * 8, stream);  // ticket + look-back status
     if (e != cudaSuccess) return e;
-    if (a.scatter.out_key != nullptr && !exact) {  // the tiles add their totals up
-        e = cudaMemsetAsync(a.d_count, 0, 8, stream);
+    // exact path: [1] collects the zero-hash flag; unordered output: the tiles add their totals up in [0]
+    if ((exact || unordered) && !a.count_zeroed) {
+        e = cudaMemsetAsync(a.d_count, 0, 16, stream);
         if (e != cudaSuccess) return e;
     }
     tile_pid_kernel<<<(unsigned)((nt + 1 + 255) / 256), 256, 0, stream>>>(a.offsets, a.n_prot, nt, w.tile_pid);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     if (n_launches) *n_launches += 1;
-    if (exact) {
+    if (exact && !unordered) {  // ordered output: the exact number of windows per tile, scanned
         tile_count_kernel<<<(unsigned)((nt + 1 + 255) / 256), 256, 0, stream>>>(a.offsets, a.n_res, a.k, nt, w.tile_pid, w.tile_cnt);
         size_t tb = w.scan_temp_bytes;
         e = cub::DeviceScan::ExclusiveSum(w.scan_temp, tb, w.tile_cnt, w.tile_base, (int64_t)(nt + 1), stream);
@@ -984,11 +987,11 @@ cudaError_t launch_sketch_tiles(const SketchArgs& a, cudaStream_t stream, uint64
     return e;
 }
 
-// d_count[1] <- zero-hash flag of the exact path (always 0 on the general path)
+// Look-back path: d_count[1] <- 0 (no zero-hash flag there: such a hash fails h != 0 and is dropped in the kernel).  The
+// exact path sets the flag in d_count[1] itself.
 cudaError_t launch_sketch_finish(const SketchArgs& a, cudaStream_t stream) {
-    if (a.n_res == 0 || a.n_prot == 0) return cudaSuccess;
-    Workspace w = carve(a.workspace, a.n_res);
-    return cudaMemcpyAsync(a.d_count + 1, w.ticket, 8, cudaMemcpyDeviceToDevice, stream);
+    if (a.n_res == 0 || a.n_prot == 0 || exact_path(a)) return cudaSuccess;
+    return cudaMemsetAsync(a.d_count + 1, 0, 8, stream);
 }
 
 bool sketch_is_exact(const SketchArgs& a) { return exact_path(a); }

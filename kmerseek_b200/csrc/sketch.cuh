@@ -30,7 +30,7 @@ struct SketchArgs {
     uint64_t* out_loc;         // (pid << 32) | pos
     uint64_t capacity;
     uint64_t* d_count;         // device u64[2]: [0] tuples kept by this launch (may exceed capacity: nothing is written
-                               // past it); [1] low word = ticket, high word != 0: a zero hash was met on the exact path
+                               // past it); [1] high word != 0: a zero hash was met on the exact path
     PairScatter scatter{};     // scatter.out_key != nullptr: the tuples leave the kernel partitioned by the top bits of the
                                // hash (first level of an unstable partition, dense_scatter.cuh) instead of in (protein,
                                // pos) order; out_hash / out_loc / capacity are not used, d_count[0] still gets the total
@@ -38,6 +38,9 @@ struct SketchArgs {
                                   // zeroed by the caller): there is no (protein, pos)-ordered tuple array to count them from
     int force_general;         // 1: take the look-back path even when scaled == 1
     uint32_t tile_begin = 0, tile_end = 0;  // exact path: launch_sketch_tiles covers [tile_begin, tile_end); 0,0 = all
+    int unordered = 0;         // the output does not need the tiles' exact bases (scatter modes set it: the tiles add their
+                               // totals to d_count[0] instead, and launch_sketch_prepare skips the count + scan launches)
+    int count_zeroed = 0;      // the caller has zeroed d_count[0..1] on the stream already
     void* workspace;           // sketch_workspace_bytes(n_res)
 };
 
