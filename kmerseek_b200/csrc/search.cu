@@ -373,52 +373,55 @@ __global__ void __launch_bounds__(T) query_kernel(QueryKernelArgs a, Lut256 lut)
     if (tid == 0) a.s.p_count[q] = p_done;
 }
 
-// Exclusive scans over the queries of |Q|, pairs and hits; totals.  One CTA (the arrays are query-sized).
+// Exclusive scans over the queries of |Q|, pairs and hits; totals.  One CTA (the arrays are query-sized): every thread
+// owns a contiguous chunk of queries -- sums it, the 1024 chunk sums are scanned once (shuffles; warp 0 scans the warp
+// totals), and the chunk is walked again to write the offsets.  (Round 2 first scanned 1024 queries per iteration with
+// every thread adding up all 32 warp totals of three 64-bit columns: 56 us for 10 000 queries, issue-bound on one SM.)
 constexpr int QS_T = 1024;
 __global__ void __launch_bounds__(QS_T) query_scan_kernel(QueryScratch s, uint32_t nq) {
     __shared__ uint64_t s_w[3][QS_T / 32];
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    uint64_t carry[3] = {0, 0, 0};
-    for (uint32_t base = 0; base < nq; base += QS_T) {
-        const uint32_t q = base + tid;
-        uint64_t v[3] = {0, 0, 0};
-        if (q < nq) { v[0] = s.e_count[q]; v[1] = s.p_count[q]; v[2] = s.h_count[q]; }
-        uint64_t incl[3];
+    const uint32_t per = (nq + QS_T - 1) / QS_T;
+    const uint32_t q0 = min(tid * per, nq), q1 = min(q0 + per, nq);
+    uint64_t sum[3] = {0, 0, 0};
+    for (uint32_t q = q0; q < q1; q++) { sum[0] += s.e_count[q]; sum[1] += s.p_count[q]; sum[2] += s.h_count[q]; }
+    uint64_t incl[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        incl[c] = sum[c];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint64_t t = __shfl_up_sync(0xffffffffu, incl[c], o);
+            if ((int)lane >= o) incl[c] += t;
+        }
+        if (lane == 31) s_w[c][warp] = incl[c];
+    }
+    __syncthreads();
+    if (warp == 0) {
 #pragma unroll
         for (int c = 0; c < 3; c++) {
-            incl[c] = v[c];
+            const uint64_t w = s_w[c][lane];
+            uint64_t wi = w;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
-                const uint64_t t = __shfl_up_sync(0xffffffffu, incl[c], o);
-                if ((int)lane >= o) incl[c] += t;
+                const uint64_t t = __shfl_up_sync(0xffffffffu, wi, o);
+                if ((int)lane >= o) wi += t;
             }
-            if (lane == 31) s_w[c][warp] = incl[c];
-        }
-        __syncthreads();
-        uint64_t tot[3];
-#pragma unroll
-        for (int c = 0; c < 3; c++) {
-            uint64_t woff = 0, t = 0;
-            for (int w = 0; w < QS_T / 32; w++) {
-                const uint64_t x = s_w[c][w];
-                if (w < (int)warp) woff += x;
-                t += x;
+            s_w[c][lane] = wi - w;  // exclusive over the warps
+            if (lane == 31) {
+                if (c == 0) { s.sig_ptr[nq] = wi; s.totals[QT_ENTRIES] = wi; }
+                if (c == 1) { s.pair_off[nq] = wi; s.totals[QT_PAIRS] = wi; }
+                if (c == 2) { s.hit_off[nq] = wi; s.totals[QT_HITS] = wi; }
             }
-            tot[c] = t;
-            incl[c] += woff + carry[c];
         }
-        if (q < nq) {
-            s.sig_ptr[q] = incl[0] - v[0];
-            s.pair_off[q] = incl[1] - v[1];
-            s.hit_off[q] = incl[2] - v[2];
-        }
-#pragma unroll
-        for (int c = 0; c < 3; c++) carry[c] += tot[c];
-        __syncthreads();
     }
-    if (tid == 0) {
-        s.sig_ptr[nq] = carry[0]; s.pair_off[nq] = carry[1]; s.hit_off[nq] = carry[2];
-        s.totals[QT_ENTRIES] = carry[0]; s.totals[QT_PAIRS] = carry[1]; s.totals[QT_HITS] = carry[2];
+    __syncthreads();
+    uint64_t run[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) run[c] = s_w[c][warp] + incl[c] - sum[c];
+    for (uint32_t q = q0; q < q1; q++) {
+        s.sig_ptr[q] = run[0]; s.pair_off[q] = run[1]; s.hit_off[q] = run[2];
+        run[0] += s.e_count[q]; run[1] += s.p_count[q]; run[2] += s.h_count[q];
     }
 }
 

@@ -99,17 +99,16 @@ __host__ inline Workspace carve(void* ws, uint64_t n_res) {
 
 // tile_pid[t] = index of the protein that contains residue t*SK_TILE (last p with offsets[p] <= that
 // position, clipped to n_prot-1); one entry past the last tile bounds the last tile's protein range.
+// One thread per protein: a non-empty protein [a, b) owns the tile starts inside it (most own none or one), so the map
+// costs two coalesced reads per protein instead of a 20-step binary search per tile (9 us on a 12 M-residue shard).
 __global__ void tile_pid_kernel(const uint64_t* __restrict__ offsets, uint64_t n_prot, uint64_t n_tiles,
                                 uint32_t* __restrict__ tile_pid) {
-    uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    if (t > n_tiles) return;
-    uint64_t g = t * SK_TILE;
-    uint64_t lo = 0, hi = n_prot - 1;  // invariant offsets[lo] <= g (offsets[0] == 0)
-    while (lo < hi) {
-        uint64_t mid = (lo + hi + 1) >> 1;
-        if (offsets[mid] <= g) lo = mid; else hi = mid - 1;
-    }
-    tile_pid[t] = (uint32_t)lo;
+    const uint64_t p = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (p >= n_prot) return;
+    const uint64_t a = offsets[p], b = offsets[p + 1];
+    for (uint64_t t = (a + SK_TILE - 1) / SK_TILE; t <= n_tiles && t * SK_TILE < b; t++) tile_pid[t] = (uint32_t)p;
+    if (p == n_prot - 1)  // tile starts at or past the last residue (the bounding entry; n_tiles * SK_TILE >= n_res)
+        for (uint64_t t = (b + SK_TILE - 1) / SK_TILE; t <= n_tiles; t++) tile_pid[t] = (uint32_t)p;
 }
 
 // Exact path (scaled == 1): the number of tuples a tile emits is its number of valid windows, known from the
@@ -344,6 +343,9 @@ __device__ __forceinline__ uint32_t stage_addr(uint32_t slot) { return (slot & 3
 
 // FULL (max_hash = 2^64 - 1, i.e. scaled == 1): tile bases come from tile_count_kernel + scan, so there is no
 // ticket, no look-back chain and no cross-CTA dependency at all.
+#ifndef KS_DIRECT_SCATTER
+#define KS_DIRECT_SCATTER 1  // unordered output: keys go from registers straight into the scatter (no ranking, no staging in order)
+#endif
 template <int K, bool TRANSLATE, bool FULL, bool SCATTER>
 #ifndef KS_SK_CTAS
 #define KS_SK_CTAS 5
@@ -461,6 +463,12 @@ sketch_quad_kernel(SketchArgs a, Lut256 lut, uint32_t* __restrict__ ticket, uint
     const uint32_t g0_lo = (uint32_t)g0;
     bool zero_seen = false;
     uint32_t wcount = 0;  // tuples staged by this warp so far (uniform across the warp)
+    // unordered output (SCATTER: the first level of the partition follows in this kernel): hashes stay in registers, a
+    // window's loc waits in its own staging slot -- no ranking of the kept windows
+    constexpr bool DIRECT = SCATTER && KS_DIRECT_SCATTER;
+    static_assert(DS_ITEMS == SQ_ROWS * 4, "a thread's windows are its scatter items");
+    uint64_t dkey[DIRECT ? DS_ITEMS : 1];
+    uint32_t dvalid = 0;
 #pragma unroll
     for (int rr = 0; rr < SQ_ROWS; rr++) {
         const uint32_t q = (warp * SQ_ROWS + rr) * 32 + lane;
@@ -497,6 +505,15 @@ sketch_quad_kernel(SketchArgs a, Lut256 lut, uint32_t* __restrict__ ticket, uint
             }
             loc[j] = ((uint64_t)(a.pid_base + p) << 32) | (uint64_t)(g0_lo + w - pstart_lo);
         }
+        if (DIRECT) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                dkey[DIRECT ? rr * 4 + j : 0] = h[j];
+                dvalid |= (keep[j] ? 1u : 0u) << (rr * 4 + j);
+                s_loc[(rr * 4 + j) * SK_THREADS + tid] = loc[j];
+            }
+            continue;
+        }
         uint32_t below = 0, total = 0;
         uint32_t bal[4];
 #pragma unroll
@@ -519,6 +536,19 @@ sketch_quad_kernel(SketchArgs a, Lut256 lut, uint32_t* __restrict__ ticket, uint
     }
 
     if (FULL && zero_seen) atomicOr(reinterpret_cast<uint32_t*>(a.d_count + 1) + 1, 1u);
+    if (DIRECT) {
+        static_assert(DS_THREADS == SK_THREADS && DS_TILE == SK_TILE, "one scatter tile per sketch tile");
+        static_assert(OFFS_CACHE == SK_THREADS, "one protein counter per thread");
+        __shared__ DenseScatterSmem s_sc;
+        const uint32_t total = scatter_pairs(reinterpret_cast<const uint64_t (&)[DS_ITEMS]>(dkey), dvalid,
+                                             [&](int it) { return s_loc[it * SK_THREADS + tid]; }, a.scatter, 0, s_sc, s_hash, s_loc);
+        if (COUNT_ABUND && cached && tid < n_off - 1) {  // (the scatter's barriers ordered the counts before this read)
+            const uint32_t c = s_pcnt[tid];
+            if (c) atomicAdd(&a.t_abund[p_lo + tid], c);
+        }
+        if (tid == 0 && total) atomicAdd(reinterpret_cast<unsigned long long*>(a.d_count), (unsigned long long)total);
+        return;
+    }
     if (lane == 0) s_wtot[warp] = wcount;
     __syncthreads();
     uint32_t wprefix = 0, btotal = 0;
@@ -607,6 +637,7 @@ sketch_quad_kernel(SketchArgs a, Lut256 lut, uint32_t* __restrict__ ticket, uint
 #ifndef KS_DK_CTAS
 #define KS_DK_CTAS 5
 #endif
+
 template <int K>
 __global__ void __launch_bounds__(SK_THREADS, KS_DK_CTAS)
 sketch_dense_kernel(SketchArgs a, Lut256 lut, const uint32_t* __restrict__ tile_pid, const uint64_t* __restrict__ tile_base,
@@ -722,6 +753,12 @@ sketch_dense_kernel(SketchArgs a, Lut256 lut, const uint32_t* __restrict__ tile_
     const int loc_bits = d.pid_bits + d.pos_bits;
     bool exc_seen = false, exc_emitted = false;
     uint32_t wcount = 0;  // keys staged by this warp so far (uniform across the warp)
+    // unordered output (the first level of the key sort follows in this kernel): the keys stay in registers and go straight
+    // into the scatter -- no ranking of the kept windows, no staging in window order
+    static_assert(DS_ITEMS == SQ_ROWS * 4, "a thread's windows are its scatter items");
+    const bool direct = KS_DIRECT_SCATTER && d.scatter.out != nullptr;
+    uint64_t dkey[DS_ITEMS];
+    uint32_t dvalid = 0;
 #pragma unroll
     for (int rr = 0; rr < SQ_ROWS; rr++) {
         const uint32_t q = (warp * SQ_ROWS + rr) * 32 + lane;
@@ -773,6 +810,14 @@ sketch_dense_kernel(SketchArgs a, Lut256 lut, const uint32_t* __restrict__ tile_
                 exc_emitted = true;
             }
         }
+        if (direct) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                dkey[rr * 4 + j] = ((uint64_t)rank[j] << loc_bits) | locp[j];
+                dvalid |= (keep[j] ? 1u : 0u) << (rr * 4 + j);
+            }
+            continue;
+        }
         uint32_t below = 0, total = 0;
         uint32_t bal[4];
 #pragma unroll
@@ -793,6 +838,12 @@ sketch_dense_kernel(SketchArgs a, Lut256 lut, const uint32_t* __restrict__ tile_
     }
     if (exc_seen) atomicOr(d.exception_flag, 1u);
     if (exc_emitted) atomicOr(d.exception_flag + 1, 1u);
+    __shared__ DenseScatterSmem s_sc;
+    if (direct) {
+        const uint32_t total = scatter_keys(dkey, dvalid, d.scatter, 0, s_sc, s_key);
+        if (tid == 0 && total) atomicAdd(reinterpret_cast<unsigned long long*>(a.d_count), (unsigned long long)total);
+        return;
+    }
     if (lane == 0) s_wtot[warp] = wcount;
     __syncthreads();
     uint32_t wprefix = 0, btotal = 0;
@@ -805,7 +856,6 @@ sketch_dense_kernel(SketchArgs a, Lut256 lut, const uint32_t* __restrict__ tile_
     if (d.scatter.out != nullptr) {  // first level of the key sort, straight out of shared memory (no tile bases: unordered)
         if (tid == 0 && btotal) atomicAdd(reinterpret_cast<unsigned long long*>(a.d_count), (unsigned long long)btotal);
         static_assert(DS_THREADS == SK_THREADS && DS_TILE == SK_TILE, "one scatter tile per sketch tile");
-        __shared__ DenseScatterSmem s_sc;
         uint64_t key[DS_ITEMS];
         uint32_t valid = 0;
 #pragma unroll
@@ -961,7 +1011,7 @@ cudaError_t launch_sketch_prepare(const SketchArgs& a, cudaStream_t stream, uint
         e = cudaMemsetAsync(a.d_count, 0, 16, stream);
         if (e != cudaSuccess) return e;
     }
-    tile_pid_kernel<<<(unsigned)((nt + 1 + 255) / 256), 256, 0, stream>>>(a.offsets, a.n_prot, nt, w.tile_pid);
+    tile_pid_kernel<<<(unsigned)((a.n_prot + 255) / 256), 256, 0, stream>>>(a.offsets, a.n_prot, nt, w.tile_pid);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     if (n_launches) *n_launches += 1;
