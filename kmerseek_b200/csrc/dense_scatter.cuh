@@ -195,24 +195,22 @@ static __global__ void dense_chunks_kernel(const uint32_t* __restrict__ cursor1,
     if (tid == 255) chunk_pfx[nb1] = off + incl;  // nb1 <= 256
 }
 
-// tuple offset of every final bucket (exclusive scan of the clamped cursors), one CTA: every thread owns a contiguous run
-// of buckets (sum, one block scan of the 1024 sums, second walk to write).  (Scanning 1024 buckets per iteration took
-// 47 us for 2^16 buckets: 64 iterations of four barriers each.)
+// tuple offset of every final bucket (exclusive scan of the clamped cursors), one CTA: every warp owns a contiguous
+// segment of the buckets and walks it 32 at a time with coalesced reads -- once to sum it, once (after the 32 segment
+// sums are scanned) to write the offsets.  (Scanning 1024 buckets per iteration behind four barriers took 47 us for 2^16
+// buckets; a contiguous chunk per THREAD made every warp load touch 32 sectors and took twice that.)
 static __global__ void __launch_bounds__(1024)
 dense_bucket_offsets_kernel(const uint32_t* __restrict__ cursor2, uint32_t nb, uint32_t cap, uint32_t* __restrict__ bstart) {
     __shared__ uint32_t s_w[32];
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t per = (nb + 1023) / 1024;
-    const uint32_t b0 = min(tid * per, nb), b1 = min(b0 + per, nb);
+    const uint32_t seg = ((nb + 31) / 32 + 31) & ~31u;  // a multiple of 32: segments start on a 128-byte line
+    const uint32_t b0 = min(warp * seg, nb), b1 = min(b0 + seg, nb);
     uint32_t sum = 0;
-    for (uint32_t i = b0; i < b1; i++) sum += min(cursor2[i], cap);
-    uint32_t incl = sum;
+#pragma unroll 4
+    for (uint32_t i = b0 + lane; i < b1; i += 32) sum += min(cursor2[i], cap);
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-        if ((int)lane >= o) incl += t;
-    }
-    if (lane == 31) s_w[warp] = incl;
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (lane == 0) s_w[warp] = sum;
     __syncthreads();
     if (warp == 0) {
         const uint32_t w = s_w[lane];
@@ -226,8 +224,19 @@ dense_bucket_offsets_kernel(const uint32_t* __restrict__ cursor2, uint32_t nb, u
         if (lane == 31) bstart[nb] = wi;
     }
     __syncthreads();
-    uint32_t run = s_w[warp] + incl - sum;
-    for (uint32_t i = b0; i < b1; i++) { bstart[i] = run; run += min(cursor2[i], cap); }
+    uint32_t run = s_w[warp];
+    for (uint32_t base = b0; base < b1; base += 32) {
+        const uint32_t i = base + lane;
+        const uint32_t v = i < b1 ? min(cursor2[i], cap) : 0u;
+        uint32_t incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((int)lane >= o) incl += t;
+        }
+        if (i < b1) bstart[i] = run + incl - v;
+        run += __shfl_sync(0xffffffffu, incl, 31);
+    }
 }
 
 }  // namespace ks

@@ -207,7 +207,9 @@ __device__ __forceinline__ void bucket_finish(const uint64_t* items, uint32_t* s
     const uint32_t kb = s + b;  // first key / group position of this bucket's segment
     const uint32_t tk = s_tk, tg = s_tg;
     uint32_t* dir_b = f.dir + (uint64_t)b * ((1u << f.dir_sub) + 1u);
-    auto dir_local = [&](uint64_t item) -> uint32_t { return f.dir_sub > 0 ? (uint32_t)(item >> (64 - f.dir_sub)) : 0u; };
+    // (dir_sub <= 24: the entry is a 32-bit shift of the item's high word)
+    const uint32_t dir_sh = 32u - (uint32_t)f.dir_sub;
+    auto dir_local = [&](uint64_t item) -> uint32_t { return f.dir_sub > 0 ? (uint32_t)(item >> 32) >> dir_sh : 0u; };
 #pragma unroll
     for (int r = 0; r < 8; r++) {
         if (r * LS_THREADS < m) {  // uniform
@@ -474,6 +476,9 @@ static_assert(BN_PER_THREAD == 8, "two 16-byte loads per thread in the scan");
 // at b * LS_CAP of the region arrays (in_hash / in_loc), in arbitrary order, and its output starts at start[b] (a scan of
 // the cursors).  The index in an item is then only an arrival number, so equal hashes are put in order by their loc in
 // the odd-even rounds (the loc gather of a tie: rare when hashes rarely repeat, which is when this path is taken).
+#ifndef KS_BIN_TIEFIX
+#define KS_BIN_TIEFIX 1  // target run: bin kernel 1.60 -> 1.46 ms (no hash-equality test in every compare of every round)
+#endif
 template <bool STEPPED, bool SCATTERED>
 __global__ void __launch_bounds__(LS_THREADS, 3)
 bucket_sort_bin_kernel(const uint64_t* __restrict__ in_hash, const uint64_t* __restrict__ in_loc,
@@ -489,6 +494,13 @@ bucket_sort_bin_kernel(const uint64_t* __restrict__ in_hash, const uint64_t* __r
     const uint32_t b = blockIdx.x;  // buckets are independent: no ticket, no order
     reinterpret_cast<uint4*>(cnt)[tid] = make_uint4(0, 0, 0, 0);
     reinterpret_cast<uint4*>(cnt)[tid + LS_THREADS] = make_uint4(0, 0, 0, 0);
+    // a scattered bucket is a region of LS_CAP allocated entries at a position known without a load: the first half of
+    // its rows is read before the size is known (what lies past the size is not used), so the size and the hashes come
+    // back in one round trip instead of two (17 % of the kernel's stall samples sat on the dependent hash load: 1.46 -> 1.37 ms)
+    constexpr int SPEC_ROWS = SCATTERED ? 6 : 0;  // 3072 of the 4096 slots: all the rows of an average bucket
+    uint64_t item[8];
+#pragma unroll
+    for (int r = 0; r < SPEC_ROWS; r++) item[r] = in_hash[b * (uint32_t)LS_CAP + r * LS_THREADS + tid];
     const uint32_t s = start[b];
     const uint32_t s_in = SCATTERED ? b * (uint32_t)LS_CAP : s;
     const uint32_t m = SCATTERED ? min(cursor[b], (uint32_t)LS_CAP) : start[b + 1] - s;  // (an overflowing region: the host
@@ -500,13 +512,12 @@ bucket_sort_bin_kernel(const uint64_t* __restrict__ in_hash, const uint64_t* __r
     // 1. count: rows of 512 consecutive tuples, one per thread; the ticket a tuple draws is its slot in the bin
     // STEPPED (repeat-heavy input): a barrier after every row, so that a bin is ordered by row and only items of the
     // same row can be out of order -- the repeats of a hash then need a handful of moves instead of a full sort.
-    uint64_t item[8];
     uint32_t slot[4] = {0, 0, 0, 0};  // two 16-bit slots per word
 #pragma unroll
     for (int r = 0; r < 8; r++) {
         const uint32_t j = r * LS_THREADS + tid;
         if (r * LS_THREADS >= m) break;  // uniform
-        if (j < m) item[r] = ((in_hash[s_in + j] << sh) & ~0xfffull) | j;
+        if (j < m) item[r] = (((r < SPEC_ROWS ? item[r] : in_hash[s_in + j]) << sh) & ~0xfffull) | j;
     }
     __syncthreads();  // the counters are zero
 #pragma unroll
@@ -556,8 +567,12 @@ bucket_sort_bin_kernel(const uint64_t* __restrict__ in_hash, const uint64_t* __r
         ulonglong2* B2 = reinterpret_cast<ulonglong2*>(B);
         // x belongs after y: by item; with arrival numbers instead of ordered indices, equal hashes by their loc
         auto after = [&](uint64_t x, uint64_t y) -> bool {
+#if KS_BIN_TIEFIX
+            return x > y;  // (equal hashes are put in loc order after the rounds)
+#else
             if (!SCATTERED || ((x ^ y) >> 12)) return x > y;
             return in_loc[s_in + (uint32_t)(x & 0xfffu)] > in_loc[s_in + (uint32_t)(y & 0xfffu)];
+#endif
         };
         int again;
         do {
@@ -573,6 +588,32 @@ bucket_sort_bin_kernel(const uint64_t* __restrict__ in_hash, const uint64_t* __r
             }
             again = __syncthreads_or(sw);
         } while (again);
+#if KS_BIN_TIEFIX
+        if (SCATTERED) {
+            // equal hashes (rare on this path) sit next to each other in arrival order: the thread that owns the second
+            // item of a run puts the run in loc order.  Runs are disjoint and a run's items differ in their low 12 bits
+            // only, so the neighbour tests of other threads read the same hash bits whatever this thread has moved.
+            for (uint32_t j = tid + 1; j < m; j += LS_THREADS) {
+                const uint64_t it = B[j], pv = B[j - 1];
+                if ((it ^ pv) >> 12) continue;
+                if (j >= 2 && ((B[j - 2] ^ pv) >> 12) == 0) continue;  // not the second item of its run
+                uint32_t e = j + 1;
+                while (e < m && ((B[e] ^ it) >> 12) == 0) e++;
+                for (uint32_t t = j; t < e; t++) {  // insertion by loc
+                    const uint64_t x = B[t], lx = in_loc[s_in + (uint32_t)(x & 0xfffu)];
+                    uint32_t u = t;
+                    while (u > j - 1) {
+                        const uint64_t y = B[u - 1];
+                        if (in_loc[s_in + (uint32_t)(y & 0xfffu)] <= lx) break;
+                        B[u] = y;
+                        u--;
+                    }
+                    B[u] = x;
+                }
+            }
+            __syncthreads();
+        }
+#endif
     }
 
     bucket_finish(B, cnt, m, s_in, s, b, lz, tb, in_loc, out_hash, out_loc, counts, t_size, f);
@@ -596,16 +637,20 @@ pair_partition_kernel(const uint64_t* __restrict__ r1_hash, const uint64_t* __re
                       uint32_t cap1, uint32_t nb1, const uint32_t* __restrict__ chunk_pfx, PairScatter sc) {
     __shared__ DenseScatterSmem s_sc;
     __shared__ uint64_t s_dk[DS_TILE], s_dv[DS_TILE];
+    __shared__ uint32_t s_pfx[(1 << DS_MAX_BITS) + 1];
     const uint32_t c = blockIdx.x;
-    if (c >= chunk_pfx[nb1]) return;
+    // (one coalesced read of the chunk table, searched in shared memory: see dense_partition_kernel)
+    for (uint32_t i = threadIdx.x; i <= nb1; i += DS_THREADS) s_pfx[i] = chunk_pfx[i];
+    __syncthreads();
+    if (c >= s_pfx[nb1]) return;
     uint32_t lo = 0, hi = nb1 - 1;  // last region whose first chunk is <= c
     while (lo < hi) {
         const uint32_t mid = (lo + hi + 1) >> 1;
-        if (chunk_pfx[mid] <= c) lo = mid; else hi = mid - 1;
+        if (s_pfx[mid] <= c) lo = mid; else hi = mid - 1;
     }
     const uint32_t b1 = lo;
     const uint32_t cnt = min(cursor1[b1], cap1);
-    const uint32_t first = (c - chunk_pfx[b1]) * DS_TILE;
+    const uint32_t first = (c - s_pfx[b1]) * DS_TILE;
     const uint64_t base = (uint64_t)b1 * cap1 + first;
     uint64_t key[DS_ITEMS], val[DS_ITEMS];
     uint32_t valid = 0;

@@ -373,28 +373,24 @@ __global__ void __launch_bounds__(T) query_kernel(QueryKernelArgs a, Lut256 lut)
     if (tid == 0) a.s.p_count[q] = p_done;
 }
 
-// Exclusive scans over the queries of |Q|, pairs and hits; totals.  One CTA (the arrays are query-sized): every thread
-// owns a contiguous chunk of queries -- sums it, the 1024 chunk sums are scanned once (shuffles; warp 0 scans the warp
-// totals), and the chunk is walked again to write the offsets.  (Round 2 first scanned 1024 queries per iteration with
-// every thread adding up all 32 warp totals of three 64-bit columns: 56 us for 10 000 queries, issue-bound on one SM.)
+// Exclusive scans over the queries of |Q|, pairs and hits; totals.  One CTA (the arrays are query-sized): every warp
+// owns a contiguous segment of the queries and walks it 32 at a time with coalesced reads -- once to sum it, once (after
+// the 32 segment sums are scanned) to write the offsets.  (Round 2 first scanned 1024 queries per iteration with every
+// thread adding up all 32 warp totals of three 64-bit columns: 56 us for 10 000 queries, issue-bound on one SM.)
 constexpr int QS_T = 1024;
 __global__ void __launch_bounds__(QS_T) query_scan_kernel(QueryScratch s, uint32_t nq) {
     __shared__ uint64_t s_w[3][QS_T / 32];
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t per = (nq + QS_T - 1) / QS_T;
-    const uint32_t q0 = min(tid * per, nq), q1 = min(q0 + per, nq);
+    const uint32_t seg = ((nq + 31) / 32 + 31) & ~31u;  // a multiple of 32: segments start on a 128-byte line
+    const uint32_t q0 = min(warp * seg, nq), q1 = min(q0 + seg, nq);
     uint64_t sum[3] = {0, 0, 0};
-    for (uint32_t q = q0; q < q1; q++) { sum[0] += s.e_count[q]; sum[1] += s.p_count[q]; sum[2] += s.h_count[q]; }
-    uint64_t incl[3];
+#pragma unroll 4
+    for (uint32_t q = q0 + lane; q < q1; q += 32) { sum[0] += s.e_count[q]; sum[1] += s.p_count[q]; sum[2] += s.h_count[q]; }
 #pragma unroll
     for (int c = 0; c < 3; c++) {
-        incl[c] = sum[c];
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint64_t t = __shfl_up_sync(0xffffffffu, incl[c], o);
-            if ((int)lane >= o) incl[c] += t;
-        }
-        if (lane == 31) s_w[c][warp] = incl[c];
+        for (int o = 16; o > 0; o >>= 1) sum[c] += __shfl_xor_sync(0xffffffffu, sum[c], o);
+        if (lane == 0) s_w[c][warp] = sum[c];
     }
     __syncthreads();
     if (warp == 0) {
@@ -416,12 +412,23 @@ __global__ void __launch_bounds__(QS_T) query_scan_kernel(QueryScratch s, uint32
         }
     }
     __syncthreads();
-    uint64_t run[3];
+    uint64_t run[3] = {s_w[0][warp], s_w[1][warp], s_w[2][warp]};
+    for (uint32_t base = q0; base < q1; base += 32) {
+        const uint32_t q = base + lane;
+        uint64_t v[3] = {0, 0, 0};
+        if (q < q1) { v[0] = s.e_count[q]; v[1] = s.p_count[q]; v[2] = s.h_count[q]; }
 #pragma unroll
-    for (int c = 0; c < 3; c++) run[c] = s_w[c][warp] + incl[c] - sum[c];
-    for (uint32_t q = q0; q < q1; q++) {
-        s.sig_ptr[q] = run[0]; s.pair_off[q] = run[1]; s.hit_off[q] = run[2];
-        run[0] += s.e_count[q]; run[1] += s.p_count[q]; run[2] += s.h_count[q];
+        for (int c = 0; c < 3; c++) {
+            uint64_t incl = v[c];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint64_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                if ((int)lane >= o) incl += t;
+            }
+            const uint64_t excl = run[c] + incl - v[c];
+            if (q < q1) { if (c == 0) s.sig_ptr[q] = excl; else if (c == 1) s.pair_off[q] = excl; else s.hit_off[q] = excl; }
+            run[c] += __shfl_sync(0xffffffffu, incl, 31);
+        }
     }
 }
 
