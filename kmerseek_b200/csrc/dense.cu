@@ -275,7 +275,11 @@ dense_write_kernel(const uint64_t* __restrict__ keys_in, uint64_t n, int loc_bit
 // writes the bucket's part of the postings and the CSR arrays (decoupled look-back over the buckets for the key / group
 // base, as bucket_finish does).
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(DS_THREADS)
+// 5 CTAs per SM (48 registers): 0.786 ms on C2 against 0.815 ms at 6 (40 registers, spills) and 0.841 ms at 4 (64 registers)
+#ifndef KS_DP_CTAS
+#define KS_DP_CTAS 5
+#endif
+__global__ void __launch_bounds__(DS_THREADS, KS_DP_CTAS)
 dense_partition_kernel(const uint64_t* __restrict__ region1, const uint32_t* __restrict__ cursor1, uint32_t cap1, uint32_t nb1,
                        const uint32_t* __restrict__ chunk_pfx, DenseScatter sc) {
     __shared__ DenseScatterSmem s_sc;
@@ -386,8 +390,8 @@ dense_bucket_kernel(DenseBucketArgs a) {
     __shared__ uint32_t s_tk, s_tg;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t lt = (1u << lane) - 1u;
-    // (the two flags are tested after the first bucket's loads are in flight: one round trip less at the head of a CTA)
-    const uint32_t skip_flag = *a.skip_flag, exc_flag = *a.exc_flag;
+    if (*a.skip_flag != 0) return;  // the build is void (the host takes the general path)
+    if ((*a.exc_flag != 0) != EXC) return;  // (uniform over the grid) the other instantiation does the work
     const int up = 64 - a.rem_bits;  // item = key << up: the bucket bits fall off the top
     const int rrb = a.rem_bits - a.loc_bits;  // code bits below the bucket bits (the lowest is the parity)
     // bin = the item's top 13 bits with the parity bit of the code squeezed out when it lies among them (it is 1 for every
@@ -410,9 +414,9 @@ dense_bucket_kernel(DenseBucketArgs a) {
     for (uint32_t i = tid; i < DB_BINS / 8; i += DB_THREADS) reinterpret_cast<uint4*>(cnt)[i] = make_uint4(0, 0, 0, 0);
     const uint64_t* src = a.region2 + (uint64_t)b * DB_CAP;
     uint64_t item[DB_ROWS];
-    // three quarters of the rows are read before the bucket's size is known (a bucket region is DB_CAP keys of allocated
+    // the first half of the rows is read before the bucket's size is known (a bucket region is DB_CAP keys of allocated
     // memory; what lies past the size is not used): the size and the keys come back in one round trip instead of two
-    constexpr int SPEC_ROWS = DB_ROWS * 3 / 4;  // 3072 of the 4096 slots: all the rows of an average bucket (2850 keys)
+    constexpr int SPEC_ROWS = DB_ROWS / 2;  // (three quarters, and the flag tests after the loads: 2.65-2.67 ms against 2.64 ms)
 #pragma unroll
     for (int r = 0; r < SPEC_ROWS; r++) item[r] = src[r * DB_THREADS + tid];
     const uint32_t m = min(a.cursor2[b], (uint32_t)DB_CAP);
@@ -424,8 +428,6 @@ dense_bucket_kernel(DenseBucketArgs a) {
     const uint32_t slice_base = a.group_base[b << pshift];
     const uint32_t slice_n = a.group_base[(b + 1) << pshift] - slice_base;
     const bool hash_slice = DB_HASH_SLICE > 0 && slice_n <= (uint32_t)DB_HASH_SLICE;
-    if (skip_flag != 0) return;  // the build is void (the host takes the general path)
-    if ((exc_flag != 0) != EXC) return;  // (uniform over the grid) the other instantiation does the work
     if (hash_slice) for (uint32_t i = tid; i < slice_n; i += DB_THREADS) s_hash[i] = a.sorted_hash[slice_base + i];
     if (m == 0) {  // an empty key / group segment (the two sentinels), directory entries that all point at it
         if (tid == 0) { a.key_grp[kb] = kb; a.grp_start[kb] = s0; a.counts[b] = 0; }
@@ -644,7 +646,9 @@ dense_bucket_kernel(DenseBucketArgs a) {
                     h = hash_of(it);
                 } else {
                     const uint32_t code = code_top | (uint32_t)(it >> rank_sh);
-                    const uint32_t idx = a.group_base[code >> a.rb] + ((code & ((1u << a.rb) - 1u)) >> a.parity);
+                    // (a bucket that is one prefix group -- 2^16 buckets -- knows its group's base already)
+                    const uint32_t gb = pshift == 0 ? slice_base : a.group_base[code >> a.rb];
+                    const uint32_t idx = gb + ((code & ((1u << a.rb) - 1u)) >> a.parity);
                     h = hash_slice ? s_hash[idx - slice_base] : a.sorted_hash[idx];
                 }
                 a.keys[kb + ul] = h;

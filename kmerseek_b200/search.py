@@ -30,8 +30,9 @@ class SearchResult:
     The pair / hit columns are numpy views of the library's pinned result block (no second copy of what can be
     a gigabyte); the block is released when this object is."""
 
-    def __init__(self, pairs, hits, query_sketches, ms_device, owner=None, q_sizes=None):
+    def __init__(self, pairs, hits, query_sketches, ms_device, owner=None, q_sizes=None, n_pairs=None, n_hits=None):
         self.pairs, self.hits, self.query_sketches, self.ms_device = pairs, hits, query_sketches, ms_device
+        self._n_pairs, self._n_hits = n_pairs, n_hits
         self.q_sizes = q_sizes  # |Q| per query (always there; the sketches themselves only when asked for)
         self._owner = owner  # POINTER(ks_search_result) kept alive for the views
 
@@ -47,10 +48,12 @@ class SearchResult:
 
     @property
     def n_pairs(self):
-        return len(self.pairs["pair_qid"])
+        return self._n_pairs if self._n_pairs is not None else len(self.pairs["pair_qid"])
 
     @property
     def n_hits(self):
+        if self._n_hits is not None:
+            return self._n_hits
         return len(self.hits["hit_qid"]) if self.hits else 0
 
 
@@ -93,6 +96,52 @@ class _Block:
             pass
 
 
+class _LazyColumns(dict):
+    """Column dict whose numpy views of the pinned block are made on first use: a result has 19 pair columns (+ 5 hit
+    columns) and a caller usually reads a few -- building all of them costs more host time than a small batch's kernels.
+    Behaves like the plain dict it replaces (assignment, items(), iteration, `in`)."""
+
+    def __init__(self, spec):
+        super().__init__()
+        self._spec = spec  # name -> (pointer, n, dtype, block)
+
+    def __missing__(self, k):
+        p, n, dt, blk = self._spec.pop(k)  # KeyError for an unknown column
+        v = _view(p, n, dt, blk) if blk is not None else _np(p, n, dt)
+        super().__setitem__(k, v)
+        return v
+
+    def __setitem__(self, k, v):
+        self._spec.pop(k, None)
+        super().__setitem__(k, v)
+
+    def _all(self):
+        for k in list(self._spec):
+            self[k]
+        return self
+
+    def __contains__(self, k):
+        return k in self._spec or super().__contains__(k)
+
+    def __iter__(self):
+        return super(_LazyColumns, self._all()).__iter__()
+
+    def __len__(self):
+        return len(self._spec) + super().__len__()
+
+    def keys(self):
+        return super(_LazyColumns, self._all()).keys()
+
+    def values(self):
+        return super(_LazyColumns, self._all()).values()
+
+    def items(self):
+        return super(_LazyColumns, self._all()).items()
+
+    def get(self, k, default=None):
+        return self[k] if k in self else default
+
+
 def _view(ptr, n, dtype, block):
     if n == 0:
         return np.zeros(0, dtype=dtype)
@@ -107,17 +156,23 @@ def _collect(r, want_hits, owner=None):
     block = _Block(owner) if owner is not None else None
     try:
         get = (lambda p, n, dt: _view(p, n, dt, block)) if owner is not None else _np
-        np_, nh, nq = r.n_pairs, r.n_hits, r.n_queries
-        pairs = {n: get(getattr(r, n), np_, dt) for n, dt in PAIR_INT_COLUMNS.items()}
+        np_, nh, nq = int(r.n_pairs), int(r.n_hits), int(r.n_queries)
+        spec = {n: (getattr(r, n), np_, dt, block) for n, dt in PAIR_INT_COLUMNS.items()}
         for n in _ffi.SCORE_COLUMNS:
-            pairs[n] = get(getattr(r, n), np_, np.float64)
-        hits = {n: get(getattr(r, n), nh, dt) for n, dt in HIT_COLUMNS.items()} if want_hits else None
+            spec[n] = (getattr(r, n), np_, np.float64, block)
+        pairs = _LazyColumns(spec)
+        hits = _LazyColumns({n: (getattr(r, n), nh, dt, block) for n, dt in HIT_COLUMNS.items()}) if want_hits else None
+        if owner is None:  # copies: the caller frees the result right after this call
+            pairs._all()
+            if hits is not None:
+                hits._all()
         sig_ptr = _np(r.q_sig_ptr, nq + 1, np.uint64)
         sketches = None
         if r.q_mins:  # KS_SEARCH_QUERY_SKETCHES
             E = int(sig_ptr[-1]) if nq else 0
             sketches = _QuerySketches(sig_ptr, get(r.q_mins, E, np.uint64), get(r.q_abunds, E, np.uint64))
-        return SearchResult(pairs, hits, sketches, r.ms_device, block, q_sizes=np.diff(sig_ptr).astype(np.uint32))
+        return SearchResult(pairs, hits, sketches, r.ms_device, block, q_sizes=np.diff(sig_ptr).astype(np.uint32),
+                            n_pairs=np_, n_hits=nh if want_hits else 0)
     except Exception:
         if block is not None:
             block.ptr = None  # the caller frees the result on this path: exactly one owner of the free

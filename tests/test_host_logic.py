@@ -216,3 +216,24 @@ def test_ctypes_mirrors_match_the_header(tmp_path):
         assert int(out[name]) == C.sizeof(cls), name
         for field, _ in cls._fields_:
             assert int(out[f"{name}.{field}"]) == getattr(cls, field).offset, f"{name}.{field}"
+
+
+def test_search_result_columns_are_built_on_first_use():
+    """kmerseek_b200.search._LazyColumns: the dict of result columns makes its numpy arrays on first access and otherwise
+    behaves like the dict it replaced (items, iteration, `in`, assignment)."""
+    import ctypes as C
+    from kmerseek_b200.search import _LazyColumns
+    a = (C.c_uint32 * 4)(1, 2, 3, 4)
+    b = (C.c_double * 4)(0.5, 1.5, 2.5, 3.5)
+    cols = _LazyColumns({"pair_qid": (C.cast(a, C.POINTER(C.c_uint32)), 4, np.uint32, None),
+                         "jaccard": (C.cast(b, C.POINTER(C.c_double)), 4, np.float64, None)})
+    assert len(cols) == 2 and "jaccard" in cols and "nope" not in cols and bool(cols)
+    assert dict.__len__(cols) == 0  # nothing built yet
+    assert cols["pair_qid"].tolist() == [1, 2, 3, 4] and dict.__len__(cols) == 1
+    cols["pair_qid"] = cols["pair_qid"] + np.uint32(10)
+    assert cols["pair_qid"].tolist() == [11, 12, 13, 14]
+    assert sorted(cols) == ["jaccard", "pair_qid"]
+    assert {k: v.tolist() for k, v in cols.items()} == {"pair_qid": [11, 12, 13, 14], "jaccard": [0.5, 1.5, 2.5, 3.5]}
+    assert cols.get("nope") is None and cols.get("jaccard")[0] == 0.5
+    with pytest.raises(KeyError):
+        cols["nope"]
