@@ -280,33 +280,20 @@ dense_write_kernel(const uint64_t* __restrict__ keys_in, uint64_t n, int loc_bit
 #define KS_DP_CTAS 5
 #endif
 __global__ void __launch_bounds__(DS_THREADS, KS_DP_CTAS)
-dense_partition_kernel(const uint64_t* __restrict__ region1, const uint32_t* __restrict__ cursor1, uint32_t cap1, uint32_t nb1,
-                       const uint32_t* __restrict__ chunk_pfx, DenseScatter sc) {
+dense_partition_kernel(const uint64_t* __restrict__ region1, uint32_t cap1, const uint2* __restrict__ chunk_map, DenseScatter sc) {
     __shared__ DenseScatterSmem s_sc;
     __shared__ uint64_t s_dst[DS_TILE];
-    __shared__ uint32_t s_pfx[(1 << DS_MAX_BITS) + 1];
-    const uint32_t c = blockIdx.x;
-    // the chunk table (<= 257 entries) comes in with one coalesced read and is searched in shared memory: eight dependent
-    // global loads at the head of every CTA were 13 % of this kernel's instructions and 11 % of its stall samples
-    for (uint32_t i = threadIdx.x; i <= nb1; i += DS_THREADS) s_pfx[i] = chunk_pfx[i];
-    __syncthreads();
-    if (c >= s_pfx[nb1]) return;
-    uint32_t lo = 0, hi = nb1 - 1;  // last bucket whose first chunk is <= c
-    while (lo < hi) {
-        const uint32_t mid = (lo + hi + 1) >> 1;
-        if (s_pfx[mid] <= c) lo = mid; else hi = mid - 1;
-    }
-    const uint32_t b1 = lo;
-    const uint32_t cnt = min(cursor1[b1], cap1);
-    const uint32_t first = (c - s_pfx[b1]) * DS_TILE;
-    const uint64_t* src = region1 + (uint64_t)b1 * cap1 + first;
+    const uint2 e = chunk_map[blockIdx.x];  // (dense_chunks_kernel) region | keys << 16, offset in the region
+    const uint32_t nv = e.x >> 16, b1 = e.x & 0xffffu;
+    if (nv == 0) return;
+    const uint64_t* src = region1 + (uint64_t)b1 * cap1 + e.y;
     uint64_t key[DS_ITEMS];
     uint32_t valid = 0;
 #pragma unroll
     for (int it = 0; it < DS_ITEMS; it++) {
         const uint32_t i = it * DS_THREADS + threadIdx.x;
         key[it] = 0;
-        if (first + i < cnt) { key[it] = src[i]; valid |= 1u << it; }
+        if (i < nv) { key[it] = src[i]; valid |= 1u << it; }
     }
     scatter_keys(key, valid, sc, b1 << sc.bits, s_sc, s_dst);
 }
@@ -767,7 +754,8 @@ DenseSortPlan dense_sort_plan(uint64_t n, int rank_bits, int key_bits, int k) {
     p.off_cursor2 = p.l2 ? take(((size_t)1 << total) * 4) : p.off_cursor1;
     p.off_overflow = take(8);
     p.small_bytes = off - p.off_small;  // everything above is zeroed before a build
-    p.off_chunks = take(((size_t)1 << DS_MAX_BITS) * 4 + 4);
+    p.max_chunks = (uint32_t)(n / DS_TILE + ((size_t)1 << p.l1) + 1);  // every region's last chunk may be partial
+    p.off_chunks = take((size_t)p.max_chunks * 8);
     p.off_bstart = take((((size_t)1 << total) + 1) * 4);
     p.off_counts = take(((size_t)1 << total) * 8);
     p.bytes = off;
@@ -803,17 +791,16 @@ cudaError_t dense_build_csr(const DenseCsrArgs& a, cudaStream_t stream, uint64_t
         uint64_t* region2 = (uint64_t*)(w + pl.off_region2);
         uint32_t* cursor1 = (uint32_t*)(w + pl.off_cursor1);
         uint32_t* cursor2 = (uint32_t*)(w + pl.off_cursor2);
-        uint32_t* chunk_pfx = (uint32_t*)(w + pl.off_chunks);
+        uint2* chunk_map = (uint2*)(w + pl.off_chunks);
         uint32_t* bstart = (uint32_t*)(w + pl.off_bstart);
         const uint32_t nb = 1u << pl.total;
         const int total_bits = a.rank_bits + loc_bits;
         if (pl.l2) {  // second level: every first-level region into 2^l2 final buckets
-            dense_chunks_kernel<<<1, 256, 0, stream>>>(cursor1, 1u << pl.l1, pl.cap1, chunk_pfx);
+            dense_chunks_kernel<<<1, 256, 0, stream>>>(cursor1, 1u << pl.l1, pl.cap1, chunk_map, pl.max_chunks);
             DenseScatter sc;
             sc.out = region2; sc.cursor = cursor2; sc.cap = (uint32_t)DB_CAP; sc.shift = total_bits - pl.total; sc.bits = pl.l2;
             sc.overflow = a.overflow ? a.overflow : (uint32_t*)(w + pl.off_overflow);
-            const unsigned grid = (unsigned)(n / DS_TILE + (1u << pl.l1) + 1);  // every region's last chunk may be partial
-            dense_partition_kernel<<<grid, DS_THREADS, 0, stream>>>(region1, cursor1, pl.cap1, 1u << pl.l1, chunk_pfx, sc);
+            dense_partition_kernel<<<pl.max_chunks, DS_THREADS, 0, stream>>>(region1, pl.cap1, chunk_map, sc);
             KS_TRY(cudaGetLastError());
             if (sort_launches) *sort_launches += 2;
         }

@@ -30,6 +30,7 @@ struct DenseSortPlan {
     // carve of the work buffer (bytes from its start)
     size_t off_region1 = 0, off_region2 = 0, off_small = 0, small_bytes = 0, bytes = 0;
     size_t off_cursor1 = 0, off_cursor2 = 0, off_chunks = 0, off_bstart = 0, off_counts = 0, off_overflow = 0;
+    uint32_t max_chunks = 0;  // grid of the second level = entries of the chunk map (dense_chunks_kernel)
 };
 DenseSortPlan dense_sort_plan(uint64_t n, int rank_bits, int key_bits, int k);
 

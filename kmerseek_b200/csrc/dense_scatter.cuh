@@ -175,12 +175,18 @@ __device__ __forceinline__ uint32_t scatter_pairs(const uint64_t (&key)[DS_ITEMS
     return total;
 }
 
-// chunk_pfx[b] = first DS_TILE-sized chunk of first-level region b (exclusive scan of the regions' chunk counts); one CTA
-static __global__ void dense_chunks_kernel(const uint32_t* __restrict__ cursor1, uint32_t nb1, uint32_t cap1, uint32_t* __restrict__ chunk_pfx) {
+// The second partition level works on DS_TILE-sized chunks of the first-level regions.  chunk_map[c] says what chunk c is:
+// x = region | keys in the chunk << 16 (0 keys: the grid is an upper bound, nothing to do), y = offset of the chunk's first
+// key inside its region.  One CTA: scan of the regions' chunk counts, then thread b writes the entries of region b.  The
+// partition kernels read ONE broadcast word pair at their head instead of searching a prefix table (eight dependent global
+// loads first, then a shared-memory copy + search by every thread: 21 % of dense_partition_kernel's instructions).
+static __global__ void dense_chunks_kernel(const uint32_t* __restrict__ cursor1, uint32_t nb1, uint32_t cap1,
+                                           uint2* __restrict__ chunk_map, uint32_t max_chunks) {
     __shared__ uint32_t s_w[8];
+    __shared__ uint32_t s_total;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    uint32_t c = 0;
-    if (tid < nb1) c = (min(cursor1[tid], cap1) + DS_TILE - 1) / DS_TILE;
+    const uint32_t cnt = tid < nb1 ? min(cursor1[tid], cap1) : 0u;  // nb1 <= 256
+    const uint32_t c = (cnt + DS_TILE - 1) / DS_TILE;
     uint32_t incl = c;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -191,8 +197,14 @@ static __global__ void dense_chunks_kernel(const uint32_t* __restrict__ cursor1,
     __syncthreads();
     uint32_t off = 0;
     for (uint32_t w = 0; w < warp; w++) off += s_w[w];
-    if (tid < nb1) chunk_pfx[tid] = off + incl - c;
-    if (tid == 255) chunk_pfx[nb1] = off + incl;  // nb1 <= 256
+    const uint32_t first_chunk = off + incl - c;
+    if (tid == 255) s_total = off + incl;
+    for (uint32_t i = 0; i < c; i++) {
+        const uint32_t at = first_chunk + i, first = i * DS_TILE;
+        if (at < max_chunks) chunk_map[at] = make_uint2(tid | (min(cnt - first, (uint32_t)DS_TILE) << 16), first);
+    }
+    __syncthreads();
+    for (uint32_t at = s_total + tid; at < max_chunks; at += 256) chunk_map[at] = make_uint2(0u, 0u);
 }
 
 // tuple offset of every final bucket (exclusive scan of the clamped cursors), one CTA: every warp owns a contiguous

@@ -125,17 +125,26 @@ __device__ __forceinline__ void bucket_empty(uint32_t b, uint32_t s, const CsrOu
 // tuple of scratch), so a head test reads two neighbouring slots.  No sorted hash column on the fused path: the CSR
 // arrays carry the hashes (keys) and nothing on the hot path reads hash[i] of the sorted tuples (expand_sorted_hash
 // rebuilds the column for the export calls).
+// `n_oversize` = f.oversize[0], read by the caller at the head of the kernel (read here, the first use waited a full
+// round trip: 8 % of the bin kernel's stall samples).  DirFirst: the first tuple of the bucket's directory entries when
+// the caller knows them from its bin offsets (bucket_sort_bin_kernel: a directory entry is a prefix of a bin index) --
+// the directory is then one coalesced write per entry instead of a per-key loop (11 % of the bin kernel's instructions).
+struct DirFirst {
+    bool from_bins = false;
+    uint32_t first[2] = {0, 0};  // first tuple of entries tid and tid + LS_THREADS
+};
+
 __device__ __forceinline__ void bucket_finish(const uint64_t* items, uint32_t* spid, uint32_t m, uint32_t s_in, uint32_t s, uint32_t b,
                                                   int lz, int tb, const uint64_t* __restrict__ in_loc,
                                                   uint64_t* __restrict__ out_hash, uint64_t* __restrict__ out_loc,
                                                   uint64_t* __restrict__ counts, uint32_t* __restrict__ t_size,
-                                                  const CsrOut& f) {
+                                                  const CsrOut& f, uint32_t n_oversize, const DirFirst& df) {
     __shared__ uint32_t s_cw[8 * LS_WARPS];  // per (row, warp): key heads | group heads << 16, then their prefix
     __shared__ uint32_t s_tk, s_tg;          // unique keys / groups of this bucket
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t lt = (1u << lane) - 1u;
     const uint64_t top = tb ? ((uint64_t)b << (64 - tb)) : 0ull;
-    const bool fused = f.oversize[0] == 0;
+    const bool fused = n_oversize == 0;
     uint64_t loc[8];
 #pragma unroll
     for (int r = 0; r < 8; r++) {
@@ -224,15 +233,28 @@ __device__ __forceinline__ void bucket_finish(const uint64_t* items, uint32_t* s
                 const uint64_t full = top | ((items[j] & ~0xfffull) >> tb);
                 f.keys[u] = full >> lz;
                 f.key_grp[u] = g;
+                if (df.from_bins) spid[j] = u;  // (the protein ids are no longer needed) key position of a head tuple
                 // directory entries this key owns: the bucket's 2^dir_sub entries are indexed by the item's top dir_sub bits
-                dir_fill(dir_b, j ? (int32_t)dir_local(items[j - 1]) : -1, (int32_t)dir_local(items[j]), u);
+                else dir_fill(dir_b, j ? (int32_t)dir_local(items[j - 1]) : -1, (int32_t)dir_local(items[j]), u);
             }
             if (j == m - 1) {  // the segment's sentinels, and the directory entries after the last key (its own end included)
                 f.key_grp[kb + tk] = kb + tg;
                 f.grp_start[kb + tg] = s + m;
-                dir_fill(dir_b, (int32_t)dir_local(items[j]), (int32_t)(1u << f.dir_sub), kb + tk);
+                if (!df.from_bins) dir_fill(dir_b, (int32_t)dir_local(items[j]), (int32_t)(1u << f.dir_sub), kb + tk);
             }
         }
+    }
+    if (df.from_bins) {
+        // dir[x] = the first key whose entry is >= x = the key of the first tuple of entry x (a head: its predecessor lies
+        // in a lower bin), or the segment's end when no tuple is left
+        __syncthreads();
+        const uint32_t dir_n = 1u << f.dir_sub;
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+            const uint32_t x = tid + i * LS_THREADS;
+            if (x < dir_n) dir_b[x] = df.first[i] < m ? spid[df.first[i]] : kb + tk;
+        }
+        if (tid == 0) dir_b[dir_n] = kb + tk;
     }
 }
 
@@ -448,7 +470,8 @@ bucket_sort_rep_kernel(const uint64_t* __restrict__ in_hash, const uint64_t* __r
     }
 
     // src == A: the other item buffer is free and parks the protein ids of the tail
-    bucket_finish(src, reinterpret_cast<uint32_t*>(dst), m, s, s, b, lz, tb, in_loc, out_hash, out_loc, counts, t_size, f);
+    bucket_finish(src, reinterpret_cast<uint32_t*>(dst), m, s, s, b, lz, tb, in_loc, out_hash, out_loc, counts, t_size, f, f.oversize[0],
+                  DirFirst());
 }
 
 
@@ -501,6 +524,7 @@ bucket_sort_bin_kernel(const uint64_t* __restrict__ in_hash, const uint64_t* __r
     uint64_t item[8];
 #pragma unroll
     for (int r = 0; r < SPEC_ROWS; r++) item[r] = in_hash[b * (uint32_t)LS_CAP + r * LS_THREADS + tid];
+    const uint32_t n_oversize = f.oversize[0];  // (needed at the tail: on its way from here)
     const uint32_t s = start[b];
     const uint32_t s_in = SCATTERED ? b * (uint32_t)LS_CAP : s;
     const uint32_t m = SCATTERED ? min(cursor[b], (uint32_t)LS_CAP) : start[b + 1] - s;  // (an overflowing region: the host
@@ -556,6 +580,18 @@ bucket_sort_bin_kernel(const uint64_t* __restrict__ in_hash, const uint64_t* __r
         const uint32_t j = r * LS_THREADS + tid;
         if (r * LS_THREADS >= m) break;  // uniform
         if (j < m) B[cnt[(uint32_t)(item[r] >> (64 - BN_BITS))] + ((slot[r >> 1] >> (16 * (r & 1))) & 0xffffu)] = item[r];
+    }
+    // the bucket's directory entries are prefixes of the bin index (dir_sub <= BN_BITS bits of the item's top): the first
+    // tuple of entry x is the offset of bin x << (BN_BITS - dir_sub).  Picked up here, before the offsets are overwritten.
+    DirFirst df;
+    df.from_bins = n_oversize == 0 && f.dir_sub <= BN_BITS - 2;  // <= 2 entries per thread
+    if (df.from_bins) {
+        const int bs = BN_BITS - f.dir_sub;
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+            const uint32_t x = tid + i * LS_THREADS;
+            df.first[i] = x < (1u << f.dir_sub) ? cnt[x << bs] : m;
+        }
     }
     __syncthreads();
     // 4. odd-even transposition until nothing moves.  The array is ordered by bin and, within a bin, by row; only items
@@ -616,7 +652,7 @@ bucket_sort_bin_kernel(const uint64_t* __restrict__ in_hash, const uint64_t* __r
 #endif
     }
 
-    bucket_finish(B, cnt, m, s_in, s, b, lz, tb, in_loc, out_hash, out_loc, counts, t_size, f);
+    bucket_finish(B, cnt, m, s_in, s, b, lz, tb, in_loc, out_hash, out_loc, counts, t_size, f, n_oversize, df);
 }
 
 // scaled == 1: every complete window is a tuple; kept windows per protein straight from the offsets (the scattered
@@ -634,32 +670,21 @@ __global__ void protein_windows_kernel(const uint64_t* __restrict__ offsets, uin
 // Second level of the unstable partition: DS_TILE-sized chunks of the first-level regions into the final buckets.
 // (64 registers, 4 CTAs per SM: 0.650 ms on the target run; forced to 48 registers / 5 CTAs it spills and takes 0.707 ms)
 __global__ void __launch_bounds__(DS_THREADS)
-pair_partition_kernel(const uint64_t* __restrict__ r1_hash, const uint64_t* __restrict__ r1_loc, const uint32_t* __restrict__ cursor1,
-                      uint32_t cap1, uint32_t nb1, const uint32_t* __restrict__ chunk_pfx, PairScatter sc) {
+pair_partition_kernel(const uint64_t* __restrict__ r1_hash, const uint64_t* __restrict__ r1_loc, uint32_t cap1,
+                      const uint2* __restrict__ chunk_map, PairScatter sc) {
     __shared__ DenseScatterSmem s_sc;
     __shared__ uint64_t s_dk[DS_TILE], s_dv[DS_TILE];
-    __shared__ uint32_t s_pfx[(1 << DS_MAX_BITS) + 1];
-    const uint32_t c = blockIdx.x;
-    // (one coalesced read of the chunk table, searched in shared memory: see dense_partition_kernel)
-    for (uint32_t i = threadIdx.x; i <= nb1; i += DS_THREADS) s_pfx[i] = chunk_pfx[i];
-    __syncthreads();
-    if (c >= s_pfx[nb1]) return;
-    uint32_t lo = 0, hi = nb1 - 1;  // last region whose first chunk is <= c
-    while (lo < hi) {
-        const uint32_t mid = (lo + hi + 1) >> 1;
-        if (s_pfx[mid] <= c) lo = mid; else hi = mid - 1;
-    }
-    const uint32_t b1 = lo;
-    const uint32_t cnt = min(cursor1[b1], cap1);
-    const uint32_t first = (c - s_pfx[b1]) * DS_TILE;
-    const uint64_t base = (uint64_t)b1 * cap1 + first;
+    const uint2 e = chunk_map[blockIdx.x];  // (dense_chunks_kernel) region | pairs << 16, offset in the region
+    const uint32_t nv = e.x >> 16, b1 = e.x & 0xffffu;
+    if (nv == 0) return;
+    const uint64_t base = (uint64_t)b1 * cap1 + e.y;
     uint64_t key[DS_ITEMS], val[DS_ITEMS];
     uint32_t valid = 0;
 #pragma unroll
     for (int it = 0; it < DS_ITEMS; it++) {
         const uint32_t i = it * DS_THREADS + threadIdx.x;
         key[it] = val[it] = 0;
-        if (first + i < cnt) { key[it] = r1_hash[base + i]; val[it] = r1_loc[base + i]; valid |= 1u << it; }
+        if (i < nv) { key[it] = r1_hash[base + i]; val[it] = r1_loc[base + i]; valid |= 1u << it; }
     }
     scatter_pairs(key, valid, [&](int it) { return val[it]; }, sc, b1 << sc.bits, s_sc, s_dk, s_dv);
 }
@@ -945,7 +970,11 @@ PairSortPlan pair_sort_plan(uint64_t n, int end_bit, uint64_t max_hash) {
     p.off_cursor2 = p.l2 ? take(((size_t)1 << tb) * 4) : p.off_cursor1;
     p.off_overflow = take(8);
     p.small_bytes = off - p.off_small;  // zeroed before the sketch kernel scatters into the regions
-    p.off_chunks = take(((size_t)1 << DS_MAX_BITS) * 4 + 4);
+    // chunks of the second level: n is exact for scaled == 1 (every region's last chunk may be partial); for scaled > 1 it is
+    // an estimate, and the bound is what the regions can hold
+    p.max_chunks = max_hash == ~0ull ? (uint32_t)(n / DS_TILE + ((size_t)1 << p.l1) + 1)
+                                     : (uint32_t)((((size_t)p.cap1 + DS_TILE - 1) / DS_TILE) << p.l1);
+    p.off_chunks = take((size_t)p.max_chunks * 8);
     p.off_bstart = take((((size_t)1 << tb) + 1) * 4);
     p.bytes = off;
     return p;
@@ -980,7 +1009,7 @@ cudaError_t build_index(const BuildArgs& a, cudaStream_t stream, int* out_in_a, 
         uint32_t* cursor1 = (uint32_t*)(w + pl.off_cursor1);
         uint32_t* cursor2 = (uint32_t*)(w + pl.off_cursor2);
         uint32_t* overflow = (uint32_t*)(w + pl.off_overflow);
-        uint32_t* chunk_pfx = (uint32_t*)(w + pl.off_chunks);
+        uint2* chunk_map = (uint2*)(w + pl.off_chunks);
         uint32_t* bstart = (uint32_t*)(w + pl.off_bstart);
         const uint64_t* r2h = (const uint64_t*)(w + pl.off_r2_hash);
         const uint64_t* r2l = (const uint64_t*)(w + pl.off_r2_loc);
@@ -991,13 +1020,12 @@ cudaError_t build_index(const BuildArgs& a, cudaStream_t stream, int* out_in_a, 
                 protein_windows_kernel<<<(a.n_prot + 255) / 256, 256, 0, stream>>>(a.offsets, a.n_prot, a.k, a.t_abund, a.t_size);
         }
         if (pl.l2) {
-            dense_chunks_kernel<<<1, 256, 0, stream>>>(cursor1, 1u << pl.l1, pl.cap1, chunk_pfx);
+            dense_chunks_kernel<<<1, 256, 0, stream>>>(cursor1, 1u << pl.l1, pl.cap1, chunk_map, pl.max_chunks);
             PairScatter sc;
             sc.out_key = (uint64_t*)(w + pl.off_r2_hash); sc.out_val = (uint64_t*)(w + pl.off_r2_loc); sc.cursor = cursor2;
             sc.cap = (uint32_t)LS_CAP; sc.shift = 64 - pl.total; sc.bits = pl.l2; sc.lz = lz; sc.overflow = overflow;
-            const unsigned grid = (unsigned)(n / DS_TILE + (1u << pl.l1) + 1);
-            pair_partition_kernel<<<grid, DS_THREADS, 0, stream>>>((const uint64_t*)(w + pl.off_r1_hash), (const uint64_t*)(w + pl.off_r1_loc),
-                                                                  cursor1, pl.cap1, 1u << pl.l1, chunk_pfx, sc);
+            pair_partition_kernel<<<pl.max_chunks, DS_THREADS, 0, stream>>>((const uint64_t*)(w + pl.off_r1_hash),
+                                                                           (const uint64_t*)(w + pl.off_r1_loc), pl.cap1, chunk_map, sc);
             KS_TRY(cudaGetLastError());
         }
         dense_bucket_offsets_kernel<<<1, 1024, 0, stream>>>(cursor2, nb, (uint32_t)LS_CAP, bstart);

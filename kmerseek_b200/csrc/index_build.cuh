@@ -56,6 +56,7 @@ struct PairSortPlan {
     // carve of the work buffer
     size_t off_r1_hash = 0, off_r1_loc = 0, off_r2_hash = 0, off_r2_loc = 0, off_small = 0, small_bytes = 0;
     size_t off_cursor1 = 0, off_cursor2 = 0, off_overflow = 0, off_chunks = 0, off_bstart = 0, bytes = 0;
+    uint32_t max_chunks = 0;  // grid of the second level = entries of the chunk map (dense_chunks_kernel)
 };
 PairSortPlan pair_sort_plan(uint64_t n, int end_bit, uint64_t max_hash);
 

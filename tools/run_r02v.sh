@@ -1,0 +1,10 @@
+#!/bin/bash
+# round 2, session v: chunk map (one broadcast load at the head of the partition kernels instead of a table search)
+mkdir -p gpurun_out
+{
+python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "unstable or dense or csr_and_search or bucket_sort or pipelined" 2>&1 | tail -3
+for wl in target_100m_dayhoff_k16_s1 c3_search_dayhoff_k16_s1 c2_swissprot_hp_k24_s1; do python tools/quick_build_bench.py $wl 20 1.0; done
+python tools/quick_build_bench.py target_100m_dayhoff_k16_s1 20 0.125
+python tools/quick_build_bench.py c2_swissprot_hp_k24_s1 20 0.125
+} > gpurun_out/r02v_ab.log 2>&1
+cat gpurun_out/r02v_ab.log
