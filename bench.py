@@ -102,11 +102,11 @@ class ClockSampler:
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the committed `ncu --set full`
 # captures of the C2 workload on one GPU (profiles/): only meaningful for that workload at N = 1, null otherwise.
-TRAFFIC_C2 = {"dense_bucket_kernel": 1_642_043_000 + 3_709_267_000}  # profiles/r02_k_ncu_full_raw_c2_build.csv
+TRAFFIC_C2 = {"dense_bucket_kernel": 1_642_193_000 + 3_709_222_000}  # profiles/r02_s_ncu_full_raw_c2_build.csv
 # the same for the per-query kernel of the search leg (10 000 queries against the C3 index, pairs only):
-# profiles/r02_k_ncu_full_raw_c3_search.csv -- random 32-byte sector gathers (directory, keys, groups, postings, protein
+# profiles/r02_s_ncu_full_raw_c3_search.csv -- random 32-byte sector gathers (directory, keys, groups, postings, protein
 # sizes), which is why it is more than ten times the algorithmic bytes
-TRAFFIC_C3_SEARCH = {"query_kernel": 514_213_000 + 21_839_000}
+TRAFFIC_C3_SEARCH = {"query_kernel": 514_447_000 + 22_040_000}
 
 
 def sketch_bytes(n_res, n_prot, n_tuples):
