@@ -57,7 +57,9 @@ inline void load_fasta_bytes(const char* path, FastaBytes* fb) {
         struct stat st;
         if (fstat(fd, &st) != 0 || st.st_size <= 0) { close(fd); fb->owned = slurp(path); }
         else {
-            void* m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE | MAP_POPULATE, fd, 0);
+            // (no MAP_POPULATE: one thread filling the page table of a 200 MB file costs more than the parser threads
+            // faulting their own ranges in -- 13 + 19 ms against 25 ms for map + count on 8 cores)
+            void* m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
             close(fd);
             if (m == MAP_FAILED) fb->owned = slurp(path);
             else {
