@@ -114,6 +114,9 @@ uint64_t ks_proteome_n_proteins(const ks_proteome *p);
 uint64_t ks_proteome_n_residues(const ks_proteome *p);
 const uint8_t *ks_proteome_residues(const ks_proteome *p); /* n_residues bytes (+64 zero pad) */
 const uint64_t *ks_proteome_offsets(const ks_proteome *p); /* pinned, n_proteins+1 */
+/* The upload copy: 5-bit codes (A-Z = 1..26, '*' = 27), 8 residues per 5 bytes little-endian, + 72 zero bytes; NULL
+ * (*n_bytes = 0) when a byte outside A-Z and '*' is present -- the residues themselves are uploaded then. */
+const uint8_t *ks_proteome_packed(const ks_proteome *p, uint64_t *n_bytes);
 const char *ks_proteome_name(const ks_proteome *p, uint64_t i); /* "" when no names were given */
 void ks_proteome_free(ks_proteome *p);
 

@@ -87,6 +87,7 @@ SIGNATURES = {
     "ks_proteome_n_residues": (C.c_uint64, [C.c_void_p]),
     "ks_proteome_residues": (u8p, [C.c_void_p]),
     "ks_proteome_offsets": (u64p, [C.c_void_p]),
+    "ks_proteome_packed": (u8p, [C.c_void_p, u64p]),
     "ks_proteome_name": (C.c_char_p, [C.c_void_p, C.c_uint64]),
     "ks_proteome_free": (None, [C.c_void_p]),
     "ks_index_create": (C.c_int, [C.POINTER(ks_params), C.POINTER(C.c_void_p)]),

@@ -150,12 +150,16 @@ struct ks_proteome {
 
 namespace {
 
-// residues are in p->residues (pageable): build the packed upload copy, or pin the residues when they cannot be packed
-void finish_proteome(ks_proteome* p) {
+// residues are in p->residues (pageable): build the packed upload copy, or pin the residues when they cannot be packed.
+// `prepacked`: the caller has packed into p->packed already (the FASTA parser does it while it fills the residues);
+// 1 = every byte had a code, 0 = some byte had none.
+void finish_proteome(ks_proteome* p, int prepacked = -1) {
     memset(p->residues + p->n_res, 0, 64);
-    p->b_packed.alloc(packed_bytes(p->n_res), true);
-    p->packed = (uint8_t*)p->b_packed.p;
-    if (!pack_residues_parallel(p->residues, p->n_res, p->packed)) {
+    if (prepacked < 0) {
+        p->b_packed.alloc(packed_bytes(p->n_res), true);
+        p->packed = (uint8_t*)p->b_packed.p;
+    }
+    if (prepacked < 0 ? !pack_residues_parallel(p->residues, p->n_res, p->packed) : prepacked == 0) {
         p->b_packed.release();
         p->packed = nullptr;
         HostBuf pin;
@@ -234,14 +238,19 @@ ks_proteome* proteome_from_fasta(const char* path, uint64_t ambig_seed, Normaliz
     try {
         p->name_blob.resize(t.name_bytes);
         p->name_off.resize(t.n_rec);
+        p->b_packed.alloc(packed_bytes(t.n_res), true);  // the upload copy is packed in the same pass as the residues
+        p->packed = (uint8_t*)p->b_packed.p;
         const double t3 = timing ? wall_ms() : 0;
         InvalidResidue bad;
-        if (!parser.fill(p->residues, p->offsets, t.name_bytes ? &p->name_blob[0] : nullptr, p->name_off.data(), &bad)) fail_residue(bad);
+        bool packed_ok = true;
+        if (!parser.fill(p->residues, p->offsets, t.name_bytes ? &p->name_blob[0] : nullptr, p->name_off.data(), &bad, p->packed,
+                         &packed_ok))
+            fail_residue(bad);
         for (uint64_t i = 0; i < t.n_rec; i++)
             if (p->offsets[i + 1] - p->offsets[i] > 0xffffffffull) fail(KS_ERR_CAPACITY, "protein longer than 2^32-1 residues");
         const double t4 = timing ? wall_ms() : 0;
-        finish_proteome(p);
-        if (timing) fprintf(stderr, "[ks] from_fasta: map %.1f ms, count %.1f, alloc %.1f, fill %.1f, pack %.1f ms\n", t1 - t0, t2 - t1,
+        finish_proteome(p, packed_ok ? 1 : 0);
+        if (timing) fprintf(stderr, "[ks] from_fasta: map %.1f ms, count %.1f, alloc %.1f, fill + pack %.1f, finish %.1f ms\n", t1 - t0, t2 - t1,
                             t3 - t2, t4 - t3, wall_ms() - t4);
     } catch (...) {
         delete p;
@@ -362,6 +371,10 @@ uint64_t ks_proteome_n_proteins(const ks_proteome* p) { return p ? p->n_prot : 0
 uint64_t ks_proteome_n_residues(const ks_proteome* p) { return p ? p->n_res : 0; }
 const uint8_t* ks_proteome_residues(const ks_proteome* p) { return p ? p->residues : nullptr; }
 const uint64_t* ks_proteome_offsets(const ks_proteome* p) { return p ? p->offsets : nullptr; }
+const uint8_t* ks_proteome_packed(const ks_proteome* p, uint64_t* n_bytes) {
+    if (n_bytes) *n_bytes = (p && p->packed) ? packed_bytes(p->n_res) : 0;
+    return p ? p->packed : nullptr;
+}
 const char* ks_proteome_name(const ks_proteome* p, uint64_t i) {
     return (p && i < p->name_off.size()) ? p->name_blob.data() + p->name_off[i] : "";
 }

@@ -106,6 +106,47 @@ inline uint8_t resolve_ambiguous(uint8_t c, uint64_t ambig_seed, uint64_t pos) {
     return c == 'B' ? (r ? 'N' : 'D') : c == 'Z' ? (r ? 'Q' : 'E') : (r ? 'L' : 'I');
 }
 
+// 5-bit codes, 8 residues per 5 bytes, over [g0, g1) groups (pack_residues of sketch.cu, one group range per thread).
+// Returns false when a byte has no code.
+struct PackCodes {  // residue byte -> 5-bit code; 0x80 marks a byte that has none
+    uint8_t code[256];
+    PackCodes() {
+        for (int i = 0; i < 256; i++) code[i] = (i >= 'A' && i <= 'Z') ? (uint8_t)(i - 'A' + 1) : i == '*' ? 27 : 0x80;
+    }
+};
+
+inline bool pack_groups(const uint8_t* res, uint64_t n, uint8_t* out, uint64_t g0, uint64_t g1) {
+    static const PackCodes pc;
+    uint32_t bad = 0;
+    const uint64_t full = std::min<uint64_t>(g1, n / 8);  // groups with all 8 residues
+    for (uint64_t g = g0; g < full; g++) {
+        const uint8_t* r = res + g * 8;
+        const uint32_t c0 = pc.code[r[0]], c1 = pc.code[r[1]], c2 = pc.code[r[2]], c3 = pc.code[r[3]], c4 = pc.code[r[4]],
+                       c5 = pc.code[r[5]], c6 = pc.code[r[6]], c7 = pc.code[r[7]];
+        bad |= c0 | c1 | c2 | c3 | c4 | c5 | c6 | c7;
+        const uint64_t v = (uint64_t)(c0 & 31u) | ((uint64_t)(c1 & 31u) << 5) | ((uint64_t)(c2 & 31u) << 10) |
+                           ((uint64_t)(c3 & 31u) << 15) | ((uint64_t)(c4 & 31u) << 20) | ((uint64_t)(c5 & 31u) << 25) |
+                           ((uint64_t)(c6 & 31u) << 30) | ((uint64_t)(c7 & 31u) << 35);
+        uint8_t* o = out + g * 5;
+        const uint32_t lo = (uint32_t)v;
+        memcpy(o, &lo, 4);
+        o[4] = (uint8_t)(v >> 32);
+    }
+    for (uint64_t g = std::max(g0, full); g < g1; g++) {  // the last, partial group
+        uint64_t v = 0;
+        const uint64_t base = g * 8;
+        const int cnt = (int)std::min<uint64_t>(8, n - base);
+        for (int i = 0; i < cnt; i++) {
+            const uint32_t c = pc.code[res[base + i]];
+            bad |= c;
+            v |= (uint64_t)(c & 31u) << (5 * i);
+        }
+        uint8_t* o = out + g * 5;
+        o[0] = (uint8_t)v; o[1] = (uint8_t)(v >> 8); o[2] = (uint8_t)(v >> 16); o[3] = (uint8_t)(v >> 24); o[4] = (uint8_t)(v >> 32);
+    }
+    return (bad & 0x80u) == 0;
+}
+
 struct ParsedFasta {  // outputs of the parse; the buffers are the caller's (sized from the counts)
     uint64_t n_rec = 0, n_res = 0, name_bytes = 0;
 };
@@ -116,6 +157,7 @@ struct FastaChunk {
     uint64_t rec0 = 0, res0 = 0, name0 = 0;         // exclusive prefix over the chunks
     bool bad = false;
     InvalidResidue bad_res{0, 0, 0};
+    bool pack_ok = true;                            // pass 2: every byte of the chunk's own groups had a 5-bit code
 };
 
 inline int ingest_threads(size_t bytes) {
@@ -189,14 +231,32 @@ class FastaParser {
     // Pass 2: normalised residues into `res` (n_res bytes), offsets[n_rec + 1], NUL-terminated names into `names`
     // (name_bytes bytes) with name_off[n_rec].  Returns false (and fills `bad`: lowest protein index, then position) on
     // an invalid residue.
-    bool fill(uint8_t* res, uint64_t* offsets, char* names, uint64_t* name_off, InvalidResidue* bad) {
-        parallel_chunks((int)chunks_.size(), [&](int i) { fill_chunk(chunks_[i], res, offsets, names, name_off); });
+    // `packed` (optional, packed_bytes(n_res) bytes): the 5-bit upload copy is written in the same pass -- every thread packs
+    // the 8-residue groups that lie inside its own residue range while they are still in its cache (a separate pass read
+    // the 200 MB of a Swiss-Prot-sized proteome back from memory); the few groups that straddle two threads' ranges and the
+    // last, partial one are packed here afterwards.  *packed_ok = false when a byte has no code (the caller then uploads
+    // the residues themselves).
+    bool fill(uint8_t* res, uint64_t* offsets, char* names, uint64_t* name_off, InvalidResidue* bad, uint8_t* packed = nullptr,
+              bool* packed_ok = nullptr) {
         uint64_t total = 0;
         for (auto& c : chunks_) total = c.res0 + c.n_res;
+        parallel_chunks((int)chunks_.size(), [&](int i) { fill_chunk(chunks_[i], res, offsets, names, name_off, packed, total); });
         uint64_t n_rec = chunks_.empty() ? 0 : chunks_.back().rec0 + chunks_.back().n_rec;
         offsets[n_rec] = total;
         for (auto& c : chunks_)
             if (c.bad) { *bad = c.bad_res; return false; }  // chunks are in file order: the first bad chunk holds the first error
+        if (packed) {
+            const uint64_t groups = (total + 7) / 8;
+            bool ok = true;
+            for (auto& c : chunks_) {
+                ok = ok && c.pack_ok;
+                const uint64_t ga = c.res0 / 8, gb = (c.res0 + c.n_res) / 8;  // the groups that hold this chunk's two ends
+                if (ga < groups) ok = pack_groups(res, total, packed, ga, ga + 1) && ok;
+                if (gb < groups && gb != ga) ok = pack_groups(res, total, packed, gb, gb + 1) && ok;
+            }
+            memset(packed + groups * 5, 0, 72);
+            if (packed_ok) *packed_ok = ok;
+        }
         return true;
     }
 
@@ -228,11 +288,16 @@ class FastaParser {
             });
     }
 
-    void fill_chunk(FastaChunk& c, uint8_t* res, uint64_t* offsets, char* names, uint64_t* name_off) const {
+    void fill_chunk(FastaChunk& c, uint8_t* res, uint64_t* offsets, char* names, uint64_t* name_off, uint8_t* packed,
+                    uint64_t total) const {
         static const ResidueClass cls;
         uint64_t rec = c.rec0, out = c.res0, nm = c.name0;
         uint64_t rec_start = out;
         bool stopped = false;
+        uint64_t pk = (c.res0 + 7) / 8;  // next group of this chunk's own range to pack (groups whose 8 residues are all ours)
+        auto pack_upto = [&](uint64_t g1) {
+            if (packed && g1 > pk) { c.pack_ok = pack_groups(res, total, packed, pk, g1) && c.pack_ok; pk = g1; }
+        };
         for_each_line(d_, c.begin, c.end,
             [&](size_t b, size_t e) {
                 offsets[rec] = out;
@@ -249,6 +314,7 @@ class FastaParser {
                 const uint8_t* in = (const uint8_t*)d_ + b;
                 const size_t len = e - b;
                 uint8_t* o = res + out;
+                if (out / 8 >= pk + 512) pack_upto(out / 8);  // the last 4 KB of residues, still in this core's cache
                 if (mode_ == NORM_SOURMASH) {
                     for (size_t i = 0; i < len; i++) o[i] = cls.up[in[i]];
                     out += len;
@@ -272,6 +338,7 @@ class FastaParser {
                 }
                 out += lim;
             });
+        if (!c.bad) pack_upto((c.res0 + c.n_res) / 8);
     }
 
     const char* d_;
@@ -281,47 +348,6 @@ class FastaParser {
     size_t start_ = 0;
     std::vector<FastaChunk> chunks_;
 };
-
-// 5-bit codes, 8 residues per 5 bytes, over [g0, g1) groups (pack_residues of sketch.cu, one group range per thread).
-// Returns false when a byte has no code.
-struct PackCodes {  // residue byte -> 5-bit code; 0x80 marks a byte that has none
-    uint8_t code[256];
-    PackCodes() {
-        for (int i = 0; i < 256; i++) code[i] = (i >= 'A' && i <= 'Z') ? (uint8_t)(i - 'A' + 1) : i == '*' ? 27 : 0x80;
-    }
-};
-
-inline bool pack_groups(const uint8_t* res, uint64_t n, uint8_t* out, uint64_t g0, uint64_t g1) {
-    static const PackCodes pc;
-    uint32_t bad = 0;
-    const uint64_t full = std::min<uint64_t>(g1, n / 8);  // groups with all 8 residues
-    for (uint64_t g = g0; g < full; g++) {
-        const uint8_t* r = res + g * 8;
-        const uint32_t c0 = pc.code[r[0]], c1 = pc.code[r[1]], c2 = pc.code[r[2]], c3 = pc.code[r[3]], c4 = pc.code[r[4]],
-                       c5 = pc.code[r[5]], c6 = pc.code[r[6]], c7 = pc.code[r[7]];
-        bad |= c0 | c1 | c2 | c3 | c4 | c5 | c6 | c7;
-        const uint64_t v = (uint64_t)(c0 & 31u) | ((uint64_t)(c1 & 31u) << 5) | ((uint64_t)(c2 & 31u) << 10) |
-                           ((uint64_t)(c3 & 31u) << 15) | ((uint64_t)(c4 & 31u) << 20) | ((uint64_t)(c5 & 31u) << 25) |
-                           ((uint64_t)(c6 & 31u) << 30) | ((uint64_t)(c7 & 31u) << 35);
-        uint8_t* o = out + g * 5;
-        const uint32_t lo = (uint32_t)v;
-        memcpy(o, &lo, 4);
-        o[4] = (uint8_t)(v >> 32);
-    }
-    for (uint64_t g = std::max(g0, full); g < g1; g++) {  // the last, partial group
-        uint64_t v = 0;
-        const uint64_t base = g * 8;
-        const int cnt = (int)std::min<uint64_t>(8, n - base);
-        for (int i = 0; i < cnt; i++) {
-            const uint32_t c = pc.code[res[base + i]];
-            bad |= c;
-            v |= (uint64_t)(c & 31u) << (5 * i);
-        }
-        uint8_t* o = out + g * 5;
-        o[0] = (uint8_t)v; o[1] = (uint8_t)(v >> 8); o[2] = (uint8_t)(v >> 16); o[3] = (uint8_t)(v >> 24); o[4] = (uint8_t)(v >> 32);
-    }
-    return (bad & 0x80u) == 0;
-}
 
 inline bool pack_residues_parallel(const uint8_t* res, uint64_t n, uint8_t* out) {
     const uint64_t groups = (n + 7) / 8;

@@ -76,6 +76,7 @@ extern "C" {
     pub fn ks_proteome_from_fasta_mode(path: *const c_char, ambig_seed: u64, mode: c_int, out: *mut *mut ks_proteome) -> c_int;
     pub fn ks_proteome_from_sequences_mode(seqs: *const *const c_char, lens: *const u64, names: *const *const c_char,
                                            n: u64, ambig_seed: u64, mode: c_int, out: *mut *mut ks_proteome) -> c_int;
+    pub fn ks_proteome_packed(p: *const ks_proteome, n_bytes: *mut u64) -> *const u8;
     pub fn ks_proteome_free(p: *mut ks_proteome);
     pub fn ks_index_create(params: *const ks_params, out: *mut *mut ks_index) -> c_int;
     pub fn ks_index_destroy(idx: *mut ks_index);

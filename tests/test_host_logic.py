@@ -237,3 +237,92 @@ def test_search_result_columns_are_built_on_first_use():
     assert cols.get("nope") is None and cols.get("jaccard")[0] == 0.5
     with pytest.raises(KeyError):
         cols["nope"]
+
+
+def _np_pack5(res):
+    """5-bit upload format restated in numpy: A-Z = 1..26, '*' = 27, 8 residues per 5 bytes little-endian, + 72 zero bytes."""
+    n = len(res)
+    code = np.where((res >= 65) & (res <= 90), res - 64, np.where(res == 42, 27, 255)).astype(np.uint64)
+    assert int(code.max(initial=0)) < 32
+    groups = (n + 7) // 8
+    c = np.zeros(groups * 8, dtype=np.uint64)
+    c[:n] = code
+    c = c.reshape(groups, 8)
+    v = np.zeros(groups, dtype=np.uint64)
+    for i in range(8):
+        v |= c[:, i] << np.uint64(5 * i)
+    out = np.zeros(groups * 5 + 72, dtype=np.uint8)
+    for b in range(5):
+        out[b:groups * 5:5] = ((v >> np.uint64(8 * b)) & np.uint64(0xff)).astype(np.uint8)
+    return out
+
+
+def _packed_of(prot):
+    import ctypes as C
+    n = C.c_uint64(0)
+    ptr = _ffi.lib().ks_proteome_packed(prot._h, C.byref(n))
+    if not ptr or n.value == 0:
+        return None
+    return np.ctypeslib.as_array(ptr, shape=(n.value,)).copy()
+
+
+@pytest.mark.parametrize("threads", ["1", "3", "16"])
+def test_fasta_ingest_packs_the_upload_copy_in_the_same_pass(tmp_path, monkeypatch, threads):
+    """The FASTA parser writes the 5-bit upload copy while it fills the residues (every thread packs the groups inside its
+    own residue range, the straddling groups afterwards): byte-identical to the separate-pass packer behind
+    ks_proteome_from_packed and to a numpy restatement, for thread counts that put chunk boundaries at every offset mod 8."""
+    monkeypatch.setenv("KS_INGEST_THREADS", threads)
+    rng = np.random.default_rng(7 + int(threads))
+    aa = np.frombuffer(b"ACDEFGHIKLMNPQRSTVWYXUO", dtype=np.uint8)
+    path = str(tmp_path / "p.fasta")
+    want = []
+    N_REC = 48_000  # ~17 MB: the parser takes one thread per MB of file, so 16 threads means 16 chunks here
+    with open(path, "w") as f:
+        for i in range(N_REC):
+            n = int(rng.integers(0, 700)) if i % 97 else 0  # a few empty records
+            seq = aa[rng.integers(0, len(aa), n)].tobytes().decode()
+            if i % 211 == 5 and n > 10:
+                seq = seq[:n // 2] + "*" + seq[n // 2:]  # truncated after the '*' (kept)
+            if i % 5 == 0:
+                seq = seq.lower()
+            f.write(f">r{i}\n")
+            for j in range(0, len(seq), 61):
+                f.write(seq[j:j + 61] + "\n")
+            seq = seq.upper()
+            want.append(seq[:seq.index("*") + 1] if "*" in seq else seq)
+    # the parser reads its thread count once per process: run it in a child so that every parameter gets its own
+    import subprocess, sys, textwrap
+    code = textwrap.dedent(f"""
+        import sys, ctypes as C, numpy as np
+        sys.path.insert(0, {ROOT!r})
+        import kmerseek_b200 as K
+        from kmerseek_b200 import _ffi
+        p = K.Proteome.from_fasta({path!r})
+        n = C.c_uint64(0)
+        ptr = _ffi.lib().ks_proteome_packed(p._h, C.byref(n))
+        np.save({str(tmp_path / 'packed.npy')!r}, np.ctypeslib.as_array(ptr, shape=(n.value,)).copy())
+        np.save({str(tmp_path / 'res.npy')!r}, np.array(p.residues))
+        np.save({str(tmp_path / 'offs.npy')!r}, np.array(p.offsets))
+    """)
+    env = dict(os.environ, KS_INGEST_THREADS=threads)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    packed, res, offs = (np.load(str(tmp_path / f)) for f in ("packed.npy", "res.npy", "offs.npy"))
+    assert res.tobytes().decode() == "".join(want) and len(offs) == N_REC + 1
+    assert np.array_equal(packed, _np_pack5(res))
+    ref = K.Proteome.from_packed(res, offs)  # the separate-pass packer
+    assert np.array_equal(_packed_of(ref), packed)
+    ref.close()
+
+
+def test_unpackable_bytes_leave_no_packed_copy(tmp_path):
+    """sourmash-mode normalisation keeps any byte: one outside A-Z and '*' means the residues themselves are uploaded."""
+    path = str(tmp_path / "q.fasta")
+    open(path, "w").write(">a\nACDE-FGH\n>b\nKLMN\n")
+    p = K.Proteome.from_fasta(path, mode="sourmash")
+    assert _packed_of(p) is None and bytes(p.residues) == b"ACDE-FGHKLMN"
+    p.close()
+    open(path, "w").write(">a\nACDEFGH\n>b\nKLMN\n")
+    p = K.Proteome.from_fasta(path, mode="sourmash")
+    assert np.array_equal(_packed_of(p), _np_pack5(np.frombuffer(b"ACDEFGHKLMN", dtype=np.uint8)))
+    p.close()
